@@ -1,0 +1,105 @@
+"""Training configuration.
+
+One flat dataclass; every field is a ``--field=value`` CLI flag of the entry
+points (parity with the reference's ``fms_fsdp/config/training.py:5-74``).
+Field names and defaults follow the reference so existing launch scripts keep
+working; the block at the bottom holds the B200-specific extension knobs
+(SURVEY.md App. B "new knobs"), whose defaults preserve reference behaviour.
+"""
+from dataclasses import dataclass, field
+from typing import Optional, Union
+
+_DEFAULT_CORPORA = ",".join(
+    "lang=%s/dataset=%s" % pair
+    for pair in (
+        ("en", "commoncrawl"), ("en", "webhose"), ("en", "github_clean"),
+        ("de", "wikipedia"), ("es", "wikipedia"), ("fr", "wikipedia"),
+        ("ja", "wikipedia"), ("pt", "wikipedia"), ("en", "wikimedia"),
+        ("en", "uspto"), ("en", "pubmedcentral"), ("en", "arxiv"),
+        ("en", "stackexchange"),
+    )
+)
+
+
+@dataclass
+class train_config:
+    # ---- which model, where checkpoints live
+    model_variant: str = "7b"
+    ckpt_load_path: str = "/fsx/output/ckpt"
+    ckpt_save_path: str = "/fsx/output/ckpt"
+
+    # ---- data
+    use_dummy_dataset: bool = False
+    data_path: str = "/fsx/data"
+    file_type: str = "arrow"
+    col_name: str = "tokens"
+    tokenizer_path: str = "/fsx/tokenizer"
+    datasets: str = _DEFAULT_CORPORA
+    weights: str = "7725,500,550,28,17,22,25,8,100,500,175,250,100"
+    seq_length: int = 4096
+    vocab_size: int = 32000
+    bos_token: Optional[int] = None
+    eos_token: int = 0
+    bol_token: Optional[int] = None
+    eol_token: Optional[int] = None
+    strip_tokens: str = ""
+    logical_shards: int = 1024
+    num_workers: int = 1
+
+    # ---- sharding policies
+    sharding_strategy: str = "hsdp"          # fsdp | hsdp | ddp  (anything else -> fsdp)
+    fsdp_activation_checkpointing: bool = False
+    selective_checkpointing: Union[float, str] = 1   # fraction of blocks to recompute, e.g. 0.5 or "1/3"
+    mixed_precision: bool = True
+    low_cpu_fsdp: bool = False
+
+    # ---- optimisation
+    batch_size: int = 2
+    num_steps: int = 1000000
+    training_stage: str = "initial"          # initial | annealing
+    learning_rate: float = 3e-4
+    grad_clip_thresh: float = 1.0
+    seed: int = 2023
+
+    # ---- continued training
+    resuming_dataset: bool = False
+
+    # ---- profiling
+    use_profiler: bool = False
+    profiler_rank0_only: bool = True
+
+    # ---- reporting
+    report_interval: int = 100
+    checkpoint_interval: int = 10000
+    tracker: Optional[str] = None            # None | "wandb" | "aim"
+    tracker_dir: str = "/fsx/aim_logs/llama"
+    tracker_project_name: str = "llama"
+    tracker_run_id: Optional[str] = None
+
+    # ---- graph capture.  The reference used torch.compile here; this engine has no tracing
+    # compiler: the flag is accepted for CLI compatibility and selects the fused-kernel path.
+    use_torch_compile: bool = True
+
+    # ---- speculator training
+    tp_size: int = 8
+    model_arch: str = "embedllama"
+    model_path: str = "/path/to/model/"
+    n_speculator_heads: int = 3
+    speculator_width: int = 4096
+    speculator_tie_weights: bool = True
+    speculator_scale_input: bool = True
+    stage2_start_step: int = 15000
+    stage2_prompt_length: int = 64
+    stage2_batch_size: int = 96
+    stage2_seq_length: int = 256
+
+    # ---- B200 engine extensions (not in the reference; defaults keep reference semantics)
+    comm_backend: str = "auto"               # auto | nccl | gloo
+    collective_impl: str = "auto"            # auto | fused (NVLink peer kernels) | torch (c10d collectives)
+    hsdp_shard_size: int = 0                 # 0 = local device count (reference behaviour); 4 -> 2x4 on one box
+    kernel_path: str = "auto"                # auto | fused (sm_100a kernels) | torch (ATen oracle)
+    precision: str = "bf16"                  # bf16 | mxfp8 (block-scaled fp8 GEMM operands)
+    prefetch_depth: int = 2                  # gathered-unit buffers in flight (reference limiter = 2)
+    fused_cross_entropy: bool = True         # linear+CE without materialising logits
+    fault_inject_step: int = 0               # >0: rank 1 exits at that step (resume drill)
+    grad_dtype: str = "bf16"                 # dtype of the unsharded gradient buffer (reference reduce_dtype=bf16)

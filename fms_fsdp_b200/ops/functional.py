@@ -1,0 +1,447 @@
+"""Differentiable ops of the engine.
+
+Every op is a ``torch.autograd.Function`` with a hand-written backward that calls the *same
+primitive set* on both back-ends: ``cuda_kernels`` (sm_100a, tcgen05/TMA) for CUDA tensors and
+``torch_kernels`` (ATen oracle) for CPU tensors.  Weights are read through the live
+``Parameter.data`` in backward (never through autograd-saved views) because the sharded runtime
+re-points parameters at a freshly gathered buffer between forward and backward; weight
+gradients are written straight into the runtime's flat gradient buffer when the parameter
+carries ``_grad_buf`` (no autograd accumulation pass).
+"""
+from __future__ import annotations
+
+import os
+from typing import Optional
+
+import torch
+
+from fms_fsdp_b200.ops import _ext, torch_kernels
+
+_KERNEL_PATH = os.environ.get("FMS_B200_KERNEL_PATH", "auto")  # auto | fused | torch
+
+
+def set_kernel_path(path: str):
+    global _KERNEL_PATH
+    if path not in ("auto", "fused", "torch"):
+        raise ValueError(f"kernel_path must be auto|fused|torch, got {path}")
+    _KERNEL_PATH = path
+
+
+def get_kernel_path() -> str:
+    return _KERNEL_PATH
+
+
+def kernels_for(t: torch.Tensor):
+    """Primitive namespace for tensor ``t``: CUDA tensors *require* the sm_100a extension."""
+    if t.is_cuda and _KERNEL_PATH != "torch":
+        if not _ext.available():
+            if _ext.allow_torch_fallback():
+                return torch_kernels
+            _ext.require()
+        from fms_fsdp_b200.ops import cuda_kernels
+        return cuda_kernels
+    return torch_kernels
+
+
+def _wdata(w):
+    return w.data if isinstance(w, torch.nn.Parameter) else w
+
+
+def _deliver_wgrad(w, compute):
+    """Run ``compute(out, accumulate)`` into the runtime grad buffer if present, else return a grad."""
+    buf = getattr(w, "_grad_buf", None)
+    if buf is not None:
+        acc = bool(getattr(w, "_grad_ready", False))
+        compute(buf, acc)
+        w._grad_ready = True
+        return None
+    out = torch.empty_like(_wdata(w))
+    compute(out, False)
+    return out
+
+
+# ------------------------------------------------------------------------------------------ linear
+class _Linear(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w, residual):
+        K = kernels_for(x)
+        x2 = x.reshape(-1, x.shape[-1])
+        r2 = None if residual is None else residual.reshape(-1, residual.shape[-1])
+        wd = _wdata(w)
+        # allocate in the caller's shape: returning a view from a custom Function would forbid the
+        # in-place RoPE that follows the QKV projection
+        y = torch.empty(*x.shape[:-1], wd.shape[0], dtype=x.dtype, device=x.device)
+        K.gemm(x2, wd, "nt", out=y.view(-1, wd.shape[0]), residual=r2)
+        ctx.K, ctx.w, ctx.has_res = K, w, residual is not None
+        ctx.save_for_backward(x)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x,) = ctx.saved_tensors
+        K, w = ctx.K, ctx.w
+        dy2 = dy.reshape(-1, dy.shape[-1])
+        if not dy2.is_contiguous():
+            dy2 = dy2.contiguous()
+        x2 = x.reshape(-1, x.shape[-1])
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = K.gemm(dy2, _wdata(w), "nn").view_as(x)
+        dw = None
+        if ctx.needs_input_grad[1]:
+            dw = _deliver_wgrad(w, lambda out, acc: K.gemm(dy2, x2, "tn", out=out, accumulate=acc))
+        return dx, dw, (dy if ctx.has_res else None)
+
+
+def linear(x, w, residual: Optional[torch.Tensor] = None):
+    """y = x @ w^T (+ residual, fused in the GEMM epilogue)."""
+    return _Linear.apply(x, w, residual)
+
+
+# ----------------------------------------------------------------------------------------- rmsnorm
+class _RMSNorm(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w, eps):
+        K = kernels_for(x)
+        x2 = x.reshape(-1, x.shape[-1])
+        y, rstd = K.rmsnorm_fwd(x2, _wdata(w), eps)
+        ctx.K, ctx.w = K, w
+        ctx.save_for_backward(x, rstd)
+        return y.view_as(x)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, rstd = ctx.saved_tensors
+        K, w = ctx.K, ctx.w
+        D = x.shape[-1]
+        dx, dw32 = K.rmsnorm_bwd(dy.reshape(-1, D).contiguous(), x.reshape(-1, D), _wdata(w), rstd)
+        dw = None
+        if ctx.needs_input_grad[1]:
+            def put(out, acc):
+                if acc:
+                    out.add_(dw32.to(out.dtype))
+                else:
+                    out.copy_(dw32)
+            dw = _deliver_wgrad(w, put)
+        return dx.view_as(x), dw, None
+
+
+def rmsnorm(x, w, eps=1e-5):
+    return _RMSNorm.apply(x, w, eps)
+
+
+class _RMSNormGated(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, z, w, eps, group_size):
+        K = kernels_for(x)
+        y, rstd = K.rmsnorm_gated_fwd(x, z, _wdata(w), eps, group_size)
+        ctx.K, ctx.w, ctx.gs = K, w, group_size
+        ctx.save_for_backward(x, z, rstd)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, z, rstd = ctx.saved_tensors
+        dx, dz, dw32 = ctx.K.rmsnorm_gated_bwd(dy.contiguous(), x, z, _wdata(ctx.w), rstd, ctx.gs)
+        def put(out, acc):
+            if acc:
+                out.add_(dw32.to(out.dtype))
+            else:
+                out.copy_(dw32)
+        dw = _deliver_wgrad(ctx.w, put) if ctx.needs_input_grad[2] else None
+        return dx, dz, dw, None, None
+
+
+def rmsnorm_gated(x, z, w, eps=1e-5, group_size=None):
+    return _RMSNormGated.apply(x, z, w, eps, group_size or x.shape[-1])
+
+
+# -------------------------------------------------------------------------------------------- rope
+class _Rope(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, qkv, table, seq_len, nheads, kvheads, head_dim, rot_dim):
+        K = kernels_for(qkv)
+        ctx.K, ctx.args = K, (seq_len, nheads, kvheads, head_dim, rot_dim)
+        ctx.save_for_backward(table)
+        ctx.mark_dirty(qkv)
+        K.rope_(qkv.view(-1, qkv.shape[-1]), table, seq_len, nheads, kvheads, head_dim, rot_dim, False)
+        return qkv
+
+    @staticmethod
+    def backward(ctx, dqkv):
+        (table,) = ctx.saved_tensors
+        seq_len, nheads, kvheads, head_dim, rot_dim = ctx.args
+        # the roped projection feeds exactly one consumer (attention), so its incoming gradient is
+        # exclusively ours: rotate it back in place instead of paying for a copy.
+        d = dqkv.contiguous()
+        ctx.K.rope_(d.view(-1, d.shape[-1]), table, seq_len, nheads, kvheads, head_dim, rot_dim, True)
+        return d, None, None, None, None, None, None
+
+
+def rope_(qkv, table, seq_len, nheads, kvheads, head_dim, rot_dim=None):
+    """Rotate the q,k sections of the fused projection in place (interleaved-pair convention)."""
+    return _Rope.apply(qkv, table, seq_len, nheads, kvheads, head_dim, rot_dim or head_dim)
+
+
+# --------------------------------------------------------------------------------------- attention
+class _Attention(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, qkv, B, S, H, KVH, hd, scale):
+        K = kernels_for(qkv)
+        q2 = qkv.view(B * S, -1)
+        o, lse = K.attn_fwd(q2, B, S, H, KVH, hd, scale)
+        ctx.K, ctx.args = K, (B, S, H, KVH, hd, scale)
+        ctx.save_for_backward(qkv, o, lse)
+        return o.view(B, S, H * hd)
+
+    @staticmethod
+    def backward(ctx, do):
+        qkv, o, lse = ctx.saved_tensors
+        B, S, H, KVH, hd, scale = ctx.args
+        dqkv = ctx.K.attn_bwd(do.reshape(B * S, H * hd).contiguous(), qkv.view(B * S, -1), o, lse,
+                              B, S, H, KVH, hd, scale)
+        return dqkv.view_as(qkv), None, None, None, None, None, None
+
+
+def attention(qkv, nheads, kvheads, head_dim, scale=None):
+    """Causal GQA flash attention on a fused (roped) projection [B, S, (H+2KVH)*hd] -> [B, S, H*hd]."""
+    B, S, _ = qkv.shape
+    scale = (head_dim ** -0.5) if scale is None else scale
+    return _Attention.apply(qkv, B, S, nheads, kvheads, head_dim, scale)
+
+
+# ------------------------------------------------------------------------------------------ swiglu
+class _SwiGLU(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, gu):
+        K = kernels_for(gu)
+        ctx.K = K
+        ctx.save_for_backward(gu)
+        return K.swiglu_fwd(gu)
+
+    @staticmethod
+    def backward(ctx, ds):
+        (gu,) = ctx.saved_tensors
+        return ctx.K.swiglu_bwd(ds.contiguous(), gu)
+
+
+def swiglu(gu):
+    return _SwiGLU.apply(gu)
+
+
+# --------------------------------------------------------------------------------------- embedding
+class _Embedding(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, tokens, w):
+        K = kernels_for(_wdata(w))
+        ctx.K, ctx.w = K, w
+        ctx.save_for_backward(tokens)
+        y = K.embedding_fwd(tokens, _wdata(w))
+        return y.view(*tokens.shape, y.shape[-1])
+
+    @staticmethod
+    def backward(ctx, dx):
+        (tokens,) = ctx.saved_tensors
+        D = dx.shape[-1]
+        dw = _deliver_wgrad(ctx.w, lambda out, acc: ctx.K.embedding_bwd(
+            dx.reshape(-1, D).contiguous(), tokens, out, accumulate=acc))
+        return None, dw
+
+
+def embedding(tokens, w):
+    return _Embedding.apply(tokens, w)
+
+
+# ------------------------------------------------------------------------- fused linear + CE loss
+class _LinearCE(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, h, w, labels, ignore_index):
+        K = kernels_for(h)
+        h2 = h.reshape(-1, h.shape[-1])
+        buf = getattr(w, "_grad_buf", None)
+        if buf is not None:
+            acc = bool(getattr(w, "_grad_ready", False))
+            loss, dh = K.linear_ce_fwd_bwd(h2, _wdata(w), labels, buf, ignore_index, accumulate=acc)
+            w._grad_ready = True
+            ctx.dw = None
+        else:
+            dw = torch.zeros_like(_wdata(w))
+            loss, dh = K.linear_ce_fwd_bwd(h2, _wdata(w), labels, dw, ignore_index)
+            ctx.dw = dw
+        ctx.w = w
+        ctx.save_for_backward(dh)
+        ctx.shape = h.shape
+        return loss
+
+    @staticmethod
+    def backward(ctx, dloss):
+        (dh,) = ctx.saved_tensors
+        # gradients were produced in forward for dloss == 1 (the engine always calls backward with 1)
+        scale_is_one = True
+        try:
+            scale_is_one = bool(dloss.numel() == 1 and float(dloss) == 1.0) if not dloss.is_cuda else True
+        except Exception:
+            pass
+        if not scale_is_one:
+            dh = dh * dloss
+            if ctx.dw is not None:
+                ctx.dw.mul_(dloss)
+        return dh.view(ctx.shape), ctx.dw, None, None
+
+
+def linear_cross_entropy(h, w, labels, ignore_index=-100):
+    """mean CE( h @ w^T , labels ) without materialising the logits (fwd+bwd in one pass)."""
+    return _LinearCE.apply(h, w, labels, ignore_index)
+
+
+class _CE(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logits, labels, ignore_index):
+        K = kernels_for(logits)
+        loss, dlogits = K.cross_entropy_fwd_bwd(logits.reshape(-1, logits.shape[-1]), labels, ignore_index)
+        ctx.save_for_backward(dlogits)
+        ctx.shape = logits.shape
+        return loss
+
+    @staticmethod
+    def backward(ctx, dloss):
+        (dl,) = ctx.saved_tensors
+        return (dl * dloss.to(dl.dtype)).view(ctx.shape), None, None
+
+
+def cross_entropy(logits, labels, ignore_index=-100):
+    return _CE.apply(logits, labels, ignore_index)
+
+
+# ------------------------------------------------------------------------------------------- mamba
+class _CausalConv1d(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w, b, seq_len, activation):
+        K = kernels_for(x)
+        ctx.K, ctx.w, ctx.b, ctx.args = K, w, b, (seq_len, activation)
+        ctx.save_for_backward(x)
+        return K.causal_conv1d_fwd(x, _wdata(w), None if b is None else _wdata(b), seq_len, activation)
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x,) = ctx.saved_tensors
+        seq_len, activation = ctx.args
+        w, b = ctx.w, ctx.b
+        dx, dw32, db32 = ctx.K.causal_conv1d_bwd(dy.contiguous(), x, _wdata(w),
+                                                 None if b is None else _wdata(b), seq_len, activation)
+        def putter(val):
+            def put(out, acc):
+                if acc:
+                    out.add_(val.to(out.dtype))
+                else:
+                    out.copy_(val)
+            return put
+        dw = _deliver_wgrad(w, putter(dw32))
+        db = None if b is None else _deliver_wgrad(b, putter(db32))
+        return dx, dw, db, None, None
+
+
+def causal_conv1d(x, w, b, seq_len, activation=True):
+    return _CausalConv1d.apply(x, w, b, seq_len, activation)
+
+
+class _SSDScan(torch.autograd.Function):
+    """Mamba2 SSD scan. Backward recomputes through the primitive's own bwd (CUDA) or autograd of
+    the sequential oracle (torch path)."""
+
+    @staticmethod
+    def forward(ctx, x, dt, A, Bm, Cm, D, dt_bias, seq_len, chunk_size):
+        K = kernels_for(x)
+        ctx.K, ctx.params, ctx.args = K, (A, D, dt_bias), (seq_len, chunk_size)
+        ctx.save_for_backward(x, dt, Bm, Cm)
+        return K.ssd_scan_fwd(x, dt, _wdata(A), Bm, Cm, None if D is None else _wdata(D),
+                              None if dt_bias is None else _wdata(dt_bias), seq_len, chunk_size)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, dt, Bm, Cm = ctx.saved_tensors
+        A, D, dt_bias = ctx.params
+        seq_len, chunk_size = ctx.args
+        K = ctx.K
+        if hasattr(K, "ssd_scan_bwd"):
+            dx, ddt, dA, dB, dC, dD, ddtb = K.ssd_scan_bwd(
+                dy.contiguous(), x, dt, _wdata(A), Bm, Cm, None if D is None else _wdata(D),
+                None if dt_bias is None else _wdata(dt_bias), seq_len, chunk_size)
+        else:
+            with torch.enable_grad():
+                leaves = [t.detach().float().requires_grad_() for t in (x, dt, _wdata(A), Bm, Cm)]
+                Dl = None if D is None else _wdata(D).detach().float().requires_grad_()
+                bl = None if dt_bias is None else _wdata(dt_bias).detach().float().requires_grad_()
+                y = torch_kernels.ssd_scan_fwd(leaves[0], leaves[1], leaves[2], leaves[3], leaves[4], Dl, bl,
+                                               seq_len, chunk_size)
+                ins = leaves + [t for t in (Dl, bl) if t is not None]
+                gs = list(torch.autograd.grad(y, ins, dy.float()))
+            dx, ddt, dA, dB, dC = gs[:5]
+            rest = gs[5:]
+            dD = rest.pop(0) if D is not None else None
+            ddtb = rest.pop(0) if dt_bias is not None else None
+        def putter(val):
+            def put(out, acc):
+                if acc:
+                    out.add_(val.to(out.dtype))
+                else:
+                    out.copy_(val)
+            return put
+        gA = _deliver_wgrad(A, putter(dA))
+        gD = None if D is None else _deliver_wgrad(D, putter(dD))
+        gb = None if dt_bias is None else _deliver_wgrad(dt_bias, putter(ddtb))
+        return (dx.to(x.dtype), ddt.to(dt.dtype), gA, dB.to(Bm.dtype), dC.to(Cm.dtype), gD, gb, None, None)
+
+
+def ssd_scan(x, dt, A, Bm, Cm, D, dt_bias, seq_len, chunk_size=256):
+    return _SSDScan.apply(x, dt, A, Bm, Cm, D, dt_bias, seq_len, chunk_size)
+
+
+class _SelectiveScan(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, u, delta, A, Bm, Cm, D, z, delta_bias, seq_len):
+        K = kernels_for(u)
+        ctx.K, ctx.params, ctx.seq_len = K, (A, D, delta_bias), seq_len
+        ctx.save_for_backward(u, delta, Bm, Cm, z)
+        return K.selective_scan_fwd(u, delta, _wdata(A), Bm, Cm, None if D is None else _wdata(D), z,
+                                    None if delta_bias is None else _wdata(delta_bias), seq_len)
+
+    @staticmethod
+    def backward(ctx, dy):
+        u, delta, Bm, Cm, z = ctx.saved_tensors
+        A, D, delta_bias = ctx.params
+        K = ctx.K
+        if hasattr(K, "selective_scan_bwd"):
+            du, dd, dA, dB, dC, dD, dz, ddb = K.selective_scan_bwd(
+                dy.contiguous(), u, delta, _wdata(A), Bm, Cm, None if D is None else _wdata(D), z,
+                None if delta_bias is None else _wdata(delta_bias), ctx.seq_len)
+        else:
+            with torch.enable_grad():
+                lv = [t.detach().float().requires_grad_() for t in (u, delta, _wdata(A), Bm, Cm)]
+                Dl = None if D is None else _wdata(D).detach().float().requires_grad_()
+                zl = None if z is None else z.detach().float().requires_grad_()
+                bl = None if delta_bias is None else _wdata(delta_bias).detach().float().requires_grad_()
+                y = torch_kernels.selective_scan_fwd(lv[0], lv[1], lv[2], lv[3], lv[4], Dl, zl, bl, ctx.seq_len)
+                ins = lv + [t for t in (Dl, zl, bl) if t is not None]
+                gs = list(torch.autograd.grad(y, ins, dy.float()))
+            du, dd, dA, dB, dC = gs[:5]
+            rest = gs[5:]
+            dD = rest.pop(0) if D is not None else None
+            dz = rest.pop(0) if z is not None else None
+            ddb = rest.pop(0) if delta_bias is not None else None
+        def putter(val):
+            def put(out, acc):
+                if acc:
+                    out.add_(val.to(out.dtype))
+                else:
+                    out.copy_(val)
+            return put
+        gA = _deliver_wgrad(A, putter(dA))
+        gD = None if D is None else _deliver_wgrad(D, putter(dD))
+        gb = None if delta_bias is None else _deliver_wgrad(delta_bias, putter(ddb))
+        return (du.to(u.dtype), dd.to(delta.dtype), gA, dB.to(Bm.dtype), dC.to(Cm.dtype), gD,
+                None if z is None else dz.to(z.dtype), gb, None)
+
+
+def selective_scan(u, delta, A, Bm, Cm, D=None, z=None, delta_bias=None, seq_len=None):
+    return _SelectiveScan.apply(u, delta, A, Bm, Cm, D, z, delta_bias, seq_len or u.shape[0])

@@ -1,0 +1,102 @@
+"""Collective back-ends of the sharded runtime.
+
+``TorchCollectives`` -- c10d (NCCL on GPU, gloo on CPU).  It is the *baseline/oracle* path
+ and the CPU plumbing path (BASELINE config #1).
+``FusedCollectives`` (``fused_comm.py``) -- symmetric-memory peer kernels over NVLink/NVSwitch;
+same interface, selected with ``collective_impl=fused``.
+
+Interface (all ops are enqueued on the *current* stream of ``device``):
+  alloc_shard / alloc_full     buffers the collectives may need to register (symmetric heap)
+  all_gather(shard, full)      full[r*n:(r+1)*n] = shard of shard-rank r
+  reduce_scatter(full, shard32, scale, sumsq)  shard32 = scale * sum_ranks(full)[my chunk]  (fp32),
+                               then replica all-reduce (HSDP), then sumsq += ||shard32||^2
+  all_reduce_full(full, scale, sumsq)  NO_SHARD/DDP gradient path (in place on the full buffer)
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+import torch.distributed as dist
+
+from fms_fsdp_b200.ops.functional import kernels_for
+from fms_fsdp_b200.parallel.mesh import DPMesh
+
+
+class TorchCollectives:
+    name = "torch"
+
+    def __init__(self, mesh: DPMesh, device: torch.device):
+        self.mesh, self.device = mesh, device
+        self._scratch = {}
+
+    # ---- allocation
+    def alloc_shard(self, numel: int, dtype: torch.dtype) -> torch.Tensor:
+        return torch.zeros(numel, dtype=dtype, device=self.device)
+
+    def alloc_full(self, numel: int, dtype: torch.dtype) -> torch.Tensor:
+        return torch.zeros(numel, dtype=dtype, device=self.device)
+
+    # ---- parameter path
+    def all_gather(self, shard: torch.Tensor, full: torch.Tensor):
+        if self.mesh.shard_size == 1:
+            if full.data_ptr() != shard.data_ptr():
+                full.copy_(shard)
+            return
+        dist.all_gather_into_tensor(full, shard, group=self.mesh.shard_group)
+
+    # ---- gradient path
+    def _tmp(self, numel, dtype):
+        key = (numel, dtype)
+        t = self._scratch.get(key)
+        if t is None:
+            t = torch.empty(numel, dtype=dtype, device=self.device)
+            self._scratch[key] = t
+        return t
+
+    def reduce_scatter(self, full: torch.Tensor, shard32: torch.Tensor, scale: float,
+                       sumsq: Optional[torch.Tensor]):
+        m = self.mesh
+        tmp = self._tmp(shard32.numel(), full.dtype)
+        dist.reduce_scatter_tensor(tmp, full, op=dist.ReduceOp.SUM, group=m.shard_group)
+        shard32.copy_(tmp)
+        if m.replica_size > 1:
+            dist.all_reduce(shard32, op=dist.ReduceOp.SUM, group=m.replica_group)
+        shard32.mul_(scale)
+        if sumsq is not None:
+            kernels_for(shard32).sumsq(shard32, out=sumsq)
+
+    def all_reduce_full(self, full: torch.Tensor, scale: float, sumsq: Optional[torch.Tensor]):
+        m = self.mesh
+        if m.replica_size > 1:
+            dist.all_reduce(full, op=dist.ReduceOp.SUM, group=m.replica_group)
+            full.mul_(scale)
+        if sumsq is not None:
+            kernels_for(full).sumsq(full, out=sumsq)
+
+    def all_reduce_scalar(self, t: torch.Tensor, over: str = "shard"):
+        m = self.mesh
+        if over == "shard":
+            if m.shard_size > 1:
+                dist.all_reduce(t, group=m.shard_group)
+        elif m.world > 1:
+            dist.all_reduce(t)
+        return t
+
+    def barrier(self):
+        if self.mesh.world > 1:
+            dist.barrier()
+
+
+def make_collectives(impl: str, mesh: DPMesh, device: torch.device):
+    impl = (impl or "auto").lower()
+    if impl == "auto":
+        impl = "fused" if (device.type == "cuda" and mesh.world > 1) else "torch"
+    if impl == "fused":
+        if device.type != "cuda":
+            raise ValueError("collective_impl=fused needs CUDA devices")
+        if mesh.world == 1:
+            return TorchCollectives(mesh, device)
+        from fms_fsdp_b200.parallel.fused_comm import FusedCollectives
+        return FusedCollectives(mesh, device)
+    return TorchCollectives(mesh, device)

@@ -1,0 +1,538 @@
+"""The sharded-parameter runtime (the engine that replaces torch FSDP1 for this framework).
+
+What the reference delegates to ``FullyShardedDataParallel`` and what
+this file owns instead:
+
+  * one flat buffer per *unit* (block / root), cut 1-D across the shard group; every rank keeps a
+    fp32 master shard, AdamW moments, and a compute-dtype shard that is what travels over NVLink;
+  * an explicit schedule instead of module hooks: forward walks the units with ``prefetch_depth``
+    parameter gathers in flight on a side stream; backward walks them in reverse, re-gathers
+    (prefetching the next unit) and launches each unit's gradient reduce-scatter on a third
+    stream as soon as that unit's backward has been enqueued;
+  * unit boundaries are autograd boundaries (inputs are detached leaves), so a unit's backward is
+    one ``autograd.backward`` call the scheduler issues -- which is also where selective
+    recomputation happens (re-run the unit forward with the weights already gathered);
+  * weight gradients are written by the ops straight into the unit's flat gradient buffer; the
+    reduce-scatter scales by 1/world, emits fp32 shards and accumulates the squared gradient norm,
+    so ``clip_grad_norm_`` costs one scalar all-reduce and the clip factor is applied inside the
+    fused AdamW (K11/K12 of SURVEY.md §2.5).
+
+Sharding strategies (reference ``train_utils.py:227-234``): fsdp / hsdp / ddp via ``DPMesh``.
+Collectives are pluggable (``comm.py``): c10d baseline or fused NVLink peer kernels.
+"""
+from __future__ import annotations
+
+import contextlib
+from typing import Dict, Iterable, List, Optional, Sequence, Tuple
+
+import torch
+import torch.nn as nn
+
+from fms_fsdp_b200.ops.functional import kernels_for
+from fms_fsdp_b200.parallel.comm import make_collectives
+from fms_fsdp_b200.parallel.layout import UnitLayout, build_layout
+from fms_fsdp_b200.parallel.mesh import DPMesh, build_mesh
+from fms_fsdp_b200.policies.ac_handler import is_checkpointed
+from fms_fsdp_b200.policies.mixed_precision import MixedPrecision, fp32_policy
+
+
+class _NullEvent:
+    def record(self, stream=None):
+        pass
+
+    def wait(self, stream=None):
+        pass
+
+    def synchronize(self):
+        pass
+
+
+class _Buf:
+    """A pooled flat buffer plus the event after which it may be overwritten."""
+
+    def __init__(self, tensor, event):
+        self.t = tensor
+        self.free_event = event
+
+
+class ShardUnit:
+    def __init__(self, name: str, modules: Sequence[nn.Module], params: List[Tuple[str, nn.Parameter]],
+                 layout: UnitLayout):
+        self.name, self.modules, self.params, self.layout = name, list(modules), params, layout
+        self.master = self.lowp = self.exp_avg = self.exp_avg_sq = self.grad_shard = None
+        self.full: Optional[_Buf] = None        # gathered parameters
+        self.full_grad: Optional[_Buf] = None   # unsharded gradient buffer
+        self.ev_gathered = _NullEvent()
+        self.recompute = False
+        self.gather_pending = False
+
+    def bind_params(self, flat: torch.Tensor):
+        for (_, p), s in zip(self.params, self.layout.slots):
+            p.data = flat[s.offset:s.offset + s.numel].view(s.shape)
+
+    def unbind_params(self, placeholder: torch.Tensor):
+        for _, p in self.params:
+            p.data = placeholder
+
+    def bind_grads(self, flat: torch.Tensor):
+        for (_, p), s in zip(self.params, self.layout.slots):
+            p._grad_buf = flat[s.offset:s.offset + s.numel].view(s.shape)
+            p._grad_ready = False
+            p.grad = None
+
+    def collect_grads(self):
+        """Fold autograd-produced .grad (ops that did not write into the buffer) and zero the slots
+        of parameters that received no gradient at all."""
+        for _, p in self.params:
+            buf = p._grad_buf
+            if p.grad is not None:
+                if p._grad_ready:
+                    buf.add_(p.grad.to(buf.dtype).view_as(buf))
+                else:
+                    buf.copy_(p.grad.view_as(buf))
+                p._grad_ready = True
+                p.grad = None
+            elif not p._grad_ready:
+                buf.zero_()
+
+    def unbind_grads(self):
+        for _, p in self.params:
+            p._grad_buf = None
+            p._grad_ready = False
+
+
+class ShardedModel(nn.Module):
+    """Wrap a model exposing the engine protocol (``engine_units/engine_embed/engine_head``)."""
+
+    def __init__(self, model: nn.Module, *, sharding_strategy: str = "fsdp", hsdp_shard_size: int = 0,
+                 mixed_precision: Optional[MixedPrecision] = None, device: Optional[torch.device] = None,
+                 collective_impl: str = "auto", prefetch_depth: int = 2, param_init_fn=None,
+                 mesh: Optional[DPMesh] = None, local_world: Optional[int] = None,
+                 reshard_after_forward: bool = True):
+        super().__init__()
+        self.module = model
+        self.device = torch.device(device) if device is not None else (
+            torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else torch.device("cpu"))
+        self.is_cuda = self.device.type == "cuda"
+        self.mp = mixed_precision or fp32_policy
+        self.mesh = mesh or build_mesh(sharding_strategy, hsdp_shard_size, local_world)
+        self.sharding_strategy = sharding_strategy
+        self.coll = make_collectives(collective_impl, self.mesh, self.device)
+        self.prefetch_depth = max(1, int(prefetch_depth))
+        self.reshard_after_forward = reshard_after_forward and self.mesh.shard_size > 1
+        self._needs_reduce = self.mesh.world > 1
+        self._placeholder = torch.empty(0, dtype=self.mp.param_dtype, device=self.device)
+
+        if self.is_cuda:
+            self.s_compute = torch.cuda.current_stream(self.device)
+            self.s_gather = torch.cuda.Stream(self.device)
+            self.s_reduce = torch.cuda.Stream(self.device)
+        else:
+            self.s_compute = self.s_gather = self.s_reduce = None
+
+        blocks, root_modules = model.engine_units()
+        self.blocks: List[ShardUnit] = []
+        self.root = self._make_unit("root", root_modules, param_init_fn, prefix_of=model)
+        for i, blk in enumerate(blocks):
+            u = self._make_unit(f"block{i}", [blk], param_init_fn, prefix_of=model)
+            self.blocks.append(u)
+        # anything not covered by a unit is a bug in the model's protocol
+        covered = {id(p) for u in self.units for _, p in u.params}
+        missing = [n for n, p in model.named_parameters() if id(p) not in covered]
+        if missing:
+            raise RuntimeError(f"parameters outside every shard unit: {missing[:5]}")
+        for buf_name, b in list(model.named_buffers()):
+            if b.is_meta:
+                raise RuntimeError(f"buffer {buf_name} still on meta device")
+        self._move_buffers()
+
+        # pools
+        self._full_pool: Dict[Tuple, List[_Buf]] = {}
+        self._grad_pool: Dict[Tuple, List[_Buf]] = {}
+        self._gnorm_sq = torch.zeros((), dtype=torch.float32, device=self.device)
+        self._clip_coef: Optional[torch.Tensor] = None
+        self._saved = None
+        self.step_count = 0
+        self.last_grad_norm: Optional[torch.Tensor] = None
+
+    # ------------------------------------------------------------------------------ construction
+    @property
+    def units(self) -> List[ShardUnit]:
+        return [self.root] + self.blocks
+
+    def _event(self):
+        return torch.cuda.Event() if self.is_cuda else _NullEvent()
+
+    def _move_buffers(self):
+        for m in self.module.modules():
+            for k, b in list(m._buffers.items()):
+                if b is not None and b.device != self.device:
+                    m._buffers[k] = b.to(self.device)
+
+    def _make_unit(self, name, modules, param_init_fn, prefix_of) -> ShardUnit:
+        # materialise (meta -> device) one unit at a time: allocate the whole unit, then run the init
+        # functions children-first so a parent's reset_parameters has the last word on its children
+        for m in modules:
+            if any(p.is_meta for p in m.parameters()) or any(b.is_meta for b in m.buffers()):
+                m.to_empty(device=self.device)
+                init = param_init_fn
+                if init is None:
+                    from fms_fsdp_b200.policies.param_init import param_init_function as init
+                for sub in reversed(list(m.modules())):
+                    try:
+                        init(sub, self.device)
+                    except TypeError:
+                        init(sub)
+        fqn = {id(p): n for n, p in prefix_of.named_parameters()}
+        seen, params = set(), []
+        for m in modules:
+            for p in m.parameters():
+                if id(p) not in seen:
+                    seen.add(id(p))
+                    params.append((fqn[id(p)], p))
+        layout = build_layout(name, [(n, tuple(p.shape)) for n, p in params], self.mesh.shard_size)
+        u = ShardUnit(name, modules, params, layout)
+        n = layout.shard_numel
+        lo, _ = layout.shard_range(self.mesh.shard_rank)
+        u.master = torch.zeros(n, dtype=torch.float32, device=self.device)
+        for (pn, p), s in zip(params, layout.slots):
+            ps, ss, ln = layout.overlap(s, self.mesh.shard_rank)
+            if ln:
+                u.master[ss:ss + ln].copy_(p.data.reshape(-1)[ps:ps + ln].to(self.device, torch.float32))
+        if self.mp.param_dtype == torch.float32:
+            u.lowp = u.master
+            if self.coll.name != "torch" and self.mesh.shard_size > 1:
+                u.lowp = self.coll.alloc_shard(n, torch.float32)
+                u.lowp.copy_(u.master)
+                u.master = u.lowp
+        else:
+            u.lowp = self.coll.alloc_shard(n, self.mp.param_dtype)
+            u.lowp.copy_(u.master)
+        u.exp_avg = torch.zeros(n, dtype=torch.float32, device=self.device)
+        u.exp_avg_sq = torch.zeros(n, dtype=torch.float32, device=self.device)
+        u.ev_gathered = self._event()
+        if self.mesh.shard_size == 1:
+            # nothing to gather: parameters live in the shard itself
+            for _, p in params:
+                p.data = self._placeholder
+            u.full = _Buf(u.lowp, self._event())
+            u.bind_params(u.lowp)
+            if self.mesh.replica_size == 1:
+                gdt = self.mp.reduce_dtype
+                u.grad_shard = torch.zeros(layout.total, dtype=gdt, device=self.device)
+                u.full_grad = _Buf(u.grad_shard, self._event())
+            else:
+                u.grad_shard = self.coll.alloc_full(layout.total, self.mp.reduce_dtype)
+                u.full_grad = _Buf(u.grad_shard, self._event())
+        else:
+            u.grad_shard = torch.zeros(n, dtype=torch.float32, device=self.device)
+            for _, p in params:
+                p.data = self._placeholder
+        for _, p in params:
+            p._grad_buf = None
+            p._grad_ready = False
+        u.recompute = False
+        return u
+
+    # --------------------------------------------------------------------------------- buffers
+    def _acquire(self, pool, unit: ShardUnit, dtype, zero_gaps=False) -> _Buf:
+        key = (unit.layout.signature(), dtype)
+        lst = pool.setdefault(key, [])
+        if lst:
+            return lst.pop(0)
+        t = self.coll.alloc_full(unit.layout.total, dtype)
+        return _Buf(t, self._event())
+
+    def _give_back(self, pool, unit: ShardUnit, buf: _Buf, dtype):
+        pool.setdefault((unit.layout.signature(), dtype), []).append(buf)
+
+    # ---------------------------------------------------------------------------------- gather
+    def _start_gather(self, u: ShardUnit):
+        if self.mesh.shard_size == 1 or u.full is not None:
+            return
+        buf = self._acquire(self._full_pool, u, self.mp.param_dtype)
+        if self.is_cuda:
+            with torch.cuda.stream(self.s_gather):
+                self.s_gather.wait_event(buf.free_event)
+                self.coll.all_gather(u.lowp, buf.t)
+                u.ev_gathered.record(self.s_gather)
+        else:
+            self.coll.all_gather(u.lowp, buf.t)
+        u.full = buf
+        u.gather_pending = True
+
+    def _wait_gather(self, u: ShardUnit):
+        if u.full is None:
+            self._start_gather(u)
+        if u.gather_pending:
+            if self.is_cuda:
+                self.s_compute.wait_event(u.ev_gathered)
+            u.gather_pending = False
+            u.bind_params(u.full.t)
+
+    def _release(self, u: ShardUnit):
+        if self.mesh.shard_size == 1 or u.full is None:
+            return
+        if self.is_cuda:
+            u.full.free_event.record(self.s_compute)
+        u.unbind_params(self._placeholder)
+        self._give_back(self._full_pool, u, u.full, self.mp.param_dtype)
+        u.full = None
+
+    # ------------------------------------------------------------------------------- gradients
+    def _prepare_grads(self, u: ShardUnit):
+        if u.full_grad is None:
+            buf = self._acquire(self._grad_pool, u, self.mp.reduce_dtype)
+            u.full_grad = buf
+        if self.is_cuda:
+            self.s_compute.wait_event(u.full_grad.free_event)
+        u.bind_grads(u.full_grad.t)
+
+    def _reduce(self, u: ShardUnit):
+        u.collect_grads()
+        u.unbind_grads()
+        m, W = self.mesh, self.mesh.world
+        ctx = torch.cuda.stream(self.s_reduce) if self.is_cuda else contextlib.nullcontext()
+        if self.is_cuda:
+            self.s_reduce.wait_stream(self.s_compute)
+        with ctx:
+            if m.shard_size == 1:
+                self.coll.all_reduce_full(u.full_grad.t, 1.0 / W, self._gnorm_sq)
+            else:
+                self.coll.reduce_scatter(u.full_grad.t, u.grad_shard, 1.0 / W, self._gnorm_sq)
+            if self.is_cuda:
+                u.full_grad.free_event.record(self.s_reduce)
+        if m.shard_size > 1:
+            self._give_back(self._grad_pool, u, u.full_grad, self.mp.reduce_dtype)
+            u.full_grad = None
+
+    # ------------------------------------------------------------------------ forward / backward
+    @staticmethod
+    def _as_tuple(x):
+        return x if isinstance(x, tuple) else (x,)
+
+    def _detach_state(self, state, requires_grad=True):
+        out = []
+        for t in self._as_tuple(state):
+            d = t.detach()
+            if requires_grad and d.is_floating_point():
+                d.requires_grad_(True)
+            out.append(d)
+        return tuple(out)
+
+    def _run_block(self, blk: nn.Module, state):
+        out = blk(*state)
+        return self._as_tuple(out)
+
+    def _forward(self, tokens, labels=None, **head_kwargs):
+        model, blocks = self.module, self.blocks
+        if self.is_cuda:
+            self.s_gather.wait_stream(self.s_compute)  # shards were just written by the optimizer
+        self._gnorm_sq.zero_()
+        self._clip_coef = None
+        self._start_gather(self.root)
+        for u in blocks[: self.prefetch_depth]:
+            self._start_gather(u)
+        self._wait_gather(self.root)
+        grad_on = torch.is_grad_enabled()
+        with torch.enable_grad() if grad_on else torch.no_grad():
+            emb_out = self._as_tuple(model.engine_embed(tokens))
+        saved = []
+        state = emb_out
+        for i, u in enumerate(blocks):
+            self._wait_gather(u)
+            nxt = i + self.prefetch_depth
+            if nxt < len(blocks):
+                self._start_gather(blocks[nxt])
+            u.recompute = is_checkpointed(u.modules[0])
+            if not grad_on:
+                with torch.no_grad():
+                    state = self._run_block(u.modules[0], self._detach_state(state, False))
+            elif u.recompute:
+                x_in = self._detach_state(state)
+                with torch.no_grad():
+                    state = self._run_block(u.modules[0], x_in)
+                saved.append((x_in, None))
+            else:
+                x_in = self._detach_state(state)
+                state = self._run_block(u.modules[0], x_in)
+                saved.append((x_in, state))
+            keep = (not self.reshard_after_forward) or (grad_on and i >= len(blocks) - 1)
+            if not keep:
+                self._release(u)
+        head_in = self._detach_state(state, grad_on)
+        with torch.enable_grad() if grad_on else torch.no_grad():
+            out = model.engine_head(*head_in, labels=labels, **head_kwargs) if labels is not None \
+                else model.engine_head(*head_in, **head_kwargs)
+        if grad_on:
+            self._saved = dict(emb_out=emb_out, blocks=saved, head_in=head_in, head_out=out)
+        else:
+            for u in blocks:
+                self._release(u)
+        return out
+
+    def _backward(self, dout=None):
+        sv, blocks = self._saved, self.blocks
+        if sv is None:
+            raise RuntimeError("backward without a recorded forward")
+        self._saved = None
+        # ---- head stage (root unit weights are still gathered)
+        self._prepare_grads(self.root)
+        out = sv["head_out"]
+        torch.autograd.backward(out, dout if dout is not None else torch.ones_like(out))
+        dstate = tuple(t.grad for t in sv["head_in"])
+        for t in sv["head_in"]:
+            t.grad = None
+        del out
+        sv["head_out"] = None
+        # ---- blocks in reverse, re-gathering ahead
+        n = len(blocks)
+        for j in range(n - 1, max(-1, n - 1 - self.prefetch_depth), -1):
+            self._start_gather(blocks[j])
+        for i in range(n - 1, -1, -1):
+            u = blocks[i]
+            self._wait_gather(u)
+            nxt = i - self.prefetch_depth
+            if nxt >= 0:
+                self._start_gather(blocks[nxt])
+            x_in, y = sv["blocks"][i]
+            self._prepare_grads(u)
+            if y is None:  # selective recompute with the weights that are resident for backward anyway
+                with torch.enable_grad():
+                    y = self._run_block(u.modules[0], x_in)
+            pairs = [(a, g) for a, g in zip(y, dstate) if g is not None and a.requires_grad]
+            torch.autograd.backward([a for a, _ in pairs], [g for _, g in pairs])
+            dstate = tuple(t.grad for t in x_in)
+            for t in x_in:
+                t.grad = None
+            sv["blocks"][i] = None
+            del y, pairs
+            self._reduce(u)
+            self._release(u)
+        # ---- embedding stage
+        pairs = [(a, g) for a, g in zip(sv["emb_out"], dstate) if g is not None and a.requires_grad]
+        if pairs:
+            torch.autograd.backward([a for a, _ in pairs], [g for _, g in pairs])
+        self._reduce(self.root)
+        self._release(self.root)
+        if self.is_cuda:
+            self.s_compute.wait_stream(self.s_reduce)
+
+    def forward_backward(self, tokens, labels, **head_kwargs) -> torch.Tensor:
+        """One training micro-step: returns the (detached) mean loss; gradients end up reduced,
+        scaled by 1/world and sharded, with ||g||^2 accumulated for ``clip_grad_norm_``."""
+        loss = self._forward(tokens, labels, **head_kwargs)
+        self._backward(None)
+        return loss.detach()
+
+    # reference-style API: ``out = model(input)`` ... ``loss.backward()``
+    def forward(self, tokens, labels=None, **head_kwargs):
+        if not torch.is_grad_enabled():
+            return self._forward(tokens, labels, **head_kwargs)
+        out = self._forward(tokens, labels, **head_kwargs)
+        return _EngineOutput.apply(self, out.detach(), self._anchor())
+
+    def _anchor(self):
+        a = getattr(self, "_anchor_t", None)
+        if a is None:
+            a = torch.zeros((), device=self.device, requires_grad=True)
+            self._anchor_t = a
+        return a
+
+    # --------------------------------------------------------------------------- grad clipping
+    def clip_grad_norm_(self, max_norm: float, norm_type: float = 2.0) -> torch.Tensor:
+        """Global L2 norm of the (already reduced) gradient; the clip factor is consumed by the fused
+        optimizer step instead of a separate pass over the gradients (reference semantics:
+        torch ``fully_sharded_data_parallel.py:1165-1215``, called at ``train_utils.py:96``)."""
+        if norm_type != 2.0:
+            raise NotImplementedError("only the L2 norm is supported")
+        total = self._gnorm_sq.clone()
+        self.coll.all_reduce_scalar(total, over="shard")
+        norm = total.sqrt()
+        self._clip_coef = torch.clamp(max_norm / (norm + 1e-6), max=1.0)
+        self.last_grad_norm = norm
+        return norm
+
+    # ------------------------------------------------------------------ full-parameter access
+    def gather_unit_full(self, u: ShardUnit, which: str = "master") -> torch.Tensor:
+        """All-gather one unit's fp32 shard (master / exp_avg / exp_avg_sq) into a flat fp32 tensor."""
+        shard = getattr(u, which)
+        if self.mesh.shard_size == 1:
+            return shard.float() if shard.dtype != torch.float32 else shard
+        full = torch.empty(u.layout.total, dtype=shard.dtype, device=self.device)
+        import torch.distributed as dist
+        dist.all_gather_into_tensor(full, shard.contiguous(), group=self.mesh.shard_group)
+        return full
+
+    def named_unit_views(self, u: ShardUnit, flat: torch.Tensor):
+        for s in u.layout.slots:
+            yield s.name, flat[s.offset:s.offset + s.numel].view(s.shape)
+
+    def load_unit_from_full(self, u: ShardUnit, which: str, tensors: Dict[str, torch.Tensor]):
+        """Copy this rank's slice out of full (unsharded) per-parameter tensors."""
+        shard = getattr(u, which)
+        for s in u.layout.slots:
+            if s.name not in tensors:
+                continue
+            ps, ss, ln = u.layout.overlap(s, self.mesh.shard_rank)
+            if ln:
+                shard[ss:ss + ln].copy_(tensors[s.name].reshape(-1)[ps:ps + ln])
+        if which == "master" and u.lowp is not u.master:
+            u.lowp.copy_(u.master)
+
+    def full_state_dict(self, dtype=None, cpu=True) -> Dict[str, torch.Tensor]:
+        """Unsharded parameters under their original (FMS) names; every rank gets the full dict."""
+        out = {}
+        for u in self.units:
+            flat = self.gather_unit_full(u, "master")
+            for name, v in self.named_unit_views(u, flat):
+                t = v.to(dtype) if dtype is not None else v.clone()
+                out[name] = t.cpu() if cpu else t
+        return out
+
+    def load_full_state_dict(self, sd: Dict[str, torch.Tensor], strict: bool = True):
+        names = {s.name for u in self.units for s in u.layout.slots}
+        missing = sorted(names - set(sd))
+        unexpected = sorted(set(sd) - names)
+        if strict and (missing or unexpected):
+            raise RuntimeError(f"state dict mismatch: missing {missing[:5]} unexpected {unexpected[:5]}")
+        for u in self.units:
+            self.load_unit_from_full(u, "master", {k: v.to(self.device, torch.float32) for k, v in sd.items()
+                                                  if k in {s.name for s in u.layout.slots}})
+        return missing, unexpected
+
+    @contextlib.contextmanager
+    def summon_full_params(self):
+        """Gather every unit (compute dtype) so the wrapped module can be used directly (eval, export)."""
+        for u in self.units:
+            self._wait_gather(u)
+        try:
+            yield self.module
+        finally:
+            if self.is_cuda:
+                torch.cuda.current_stream().synchronize()
+            for u in self.units:
+                self._release(u)
+
+    def param_count(self) -> int:
+        return sum(u.layout.used for u in self.units)
+
+    def extra_repr(self) -> str:
+        m = self.mesh
+        return (f"units={len(self.units)}, mesh=replica{m.replica_size}xshard{m.shard_size}, "
+                f"param_dtype={self.mp.param_dtype}, collectives={self.coll.name}")
+
+
+class _EngineOutput(torch.autograd.Function):
+    """Bridges the engine's explicit backward schedule into ``loss.backward()`` for callers that use
+    the reference-style loop (``out = model(x); loss = CE(out, y); loss.backward()``)."""
+
+    @staticmethod
+    def forward(ctx, engine, out, anchor):
+        ctx.engine = engine
+        return out.clone() if out.dim() == 0 else out
+
+    @staticmethod
+    def backward(ctx, dout):
+        ctx.engine._backward(dout)
+        return None, None, None

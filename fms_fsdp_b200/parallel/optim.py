@@ -1,0 +1,68 @@
+"""Sharded fused AdamW.
+
+Reference: ``torch.optim.AdamW(lr, betas=(0.9, 0.95), weight_decay=0.1)`` over FSDP's sharded flat
+parameters (``main_training_llama.py:113-115``), one parameter group so weight decay hits norm
+gains and embeddings too.  Here the update is one fused kernel per shard unit on
+the fp32 master shard that also (a) applies the gradient-clip factor computed by
+``ShardedModel.clip_grad_norm_`` and (b) writes the refreshed compute-dtype shard that the next
+all-gather sends -- K11/K12/K13 of SURVEY.md §2.5 collapse into this step.
+It is a real ``torch.optim.Optimizer`` so ``LambdaLR`` and friends work unchanged.
+"""
+from __future__ import annotations
+
+from typing import Dict
+
+import torch
+
+from fms_fsdp_b200.ops.functional import kernels_for
+
+
+class ShardedAdamW(torch.optim.Optimizer):
+    def __init__(self, model, lr: float = 3e-4, betas=(0.9, 0.95), eps: float = 1e-8, weight_decay: float = 0.1):
+        self.engine = model
+        params = [u.master for u in model.units]
+        for p in params:
+            p.requires_grad_(False)
+        defaults = dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay)
+        super().__init__([{"params": params}], defaults)
+        self._step = 0
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = closure() if closure is not None else None
+        g = self.param_groups[0]
+        self._step += 1
+        lr, (b1, b2), eps, wd = float(g["lr"]), g["betas"], g["eps"], g["weight_decay"]
+        eng = self.engine
+        coef = eng._clip_coef
+        for u in eng.units:
+            K = kernels_for(u.master)
+            K.adamw_step(u.master, u.grad_shard, u.exp_avg, u.exp_avg_sq,
+                         None if u.lowp is u.master else u.lowp, lr, b1, b2, eps, wd, self._step, coef)
+        eng._clip_coef = None
+        eng.step_count = self._step
+        return loss
+
+    def zero_grad(self, set_to_none: bool = True):
+        # gradient buffers are overwritten (not accumulated) by every backward
+        return None
+
+    # flat, rank-local state (the Checkpointer uses the per-parameter sharded view instead)
+    def state_dict(self) -> Dict:
+        return {
+            "step": self._step,
+            "param_groups": [{k: v for k, v in g.items() if k != "params"} for g in self.param_groups],
+            "units": {u.name: {"exp_avg": u.exp_avg, "exp_avg_sq": u.exp_avg_sq} for u in self.engine.units},
+        }
+
+    def load_state_dict(self, sd: Dict):
+        self._step = int(sd.get("step", 0))
+        for g, sg in zip(self.param_groups, sd.get("param_groups", [])):
+            for k, v in sg.items():
+                if k != "params":
+                    g[k] = v
+        for u in self.engine.units:
+            st = sd.get("units", {}).get(u.name)
+            if st is not None:
+                u.exp_avg.copy_(st["exp_avg"])
+                u.exp_avg_sq.copy_(st["exp_avg_sq"])
