@@ -1,0 +1,334 @@
+// Python bindings (torch tensors -> raw launchers).  Compiled by g++ only; every kernel lives in a
+// torch-free .cu so nvcc never parses the torch headers.
+#include <ATen/cuda/CUDAContext.h>
+#include <c10/cuda/CUDAGuard.h>
+#include <torch/extension.h>
+
+#include <cmath>
+#include <cstdint>
+
+#define DECL extern "C"
+DECL int b200_gemm_bf16(const void*, const void*, void*, const void*, int, int, int, int, int, int, int, int, int, int,
+                        int, cudaStream_t);
+DECL int b200_rmsnorm_fwd(const void*, const void*, void*, float*, int, int, float, cudaStream_t);
+DECL int b200_rmsnorm_bwd_grid(int);
+DECL int b200_rmsnorm_bwd(const void*, const void*, const void*, const float*, void*, float*, float*, int, int,
+                          cudaStream_t);
+DECL int b200_rope(void*, const float*, int, int, int, int, int, int, int, int, cudaStream_t);
+DECL int b200_swiglu_fwd(const void*, void*, long long, int, cudaStream_t);
+DECL int b200_swiglu_bwd(const void*, const void*, void*, long long, int, cudaStream_t);
+DECL int b200_embedding_fwd(const void*, int, const void*, void*, long long, int, cudaStream_t);
+DECL int b200_embedding_bwd(const void*, int, const void*, void*, int, long long, int, cudaStream_t);
+DECL int b200_count_valid(const long long*, int, long long, float*, cudaStream_t);
+DECL int b200_ce_grad_inplace(void*, const long long*, const float*, float*, int, int, int, long long, cudaStream_t);
+DECL int b200_adamw(float*, const void*, int, float*, float*, void*, long long, float, float, float, float, float,
+                    float, float, const float*, cudaStream_t);
+DECL int b200_sumsq(const void*, int, long long, float*, cudaStream_t);
+DECL int b200_attn_fwd(const void*, void*, float*, int, int, int, int, int, float, cudaStream_t);
+DECL int b200_attn_bwd(const void*, const void*, const void*, const float*, void*, float*, int, int, int, int, int,
+                       float, cudaStream_t);
+DECL int b200_p2p_allgather(const void* const*, void*, long long, int, int, cudaStream_t);
+DECL int b200_reduce_scatter(const void* const*, float*, long long, long long, int, int, int, float, float*,
+                             cudaStream_t);
+DECL int b200_allreduce_inplace(void* const*, long long, int, int, int, float, float*, cudaStream_t);
+DECL int b200_signal_barrier(uint32_t* const*, int, int, uint32_t, cudaStream_t);
+DECL int b200_causal_conv1d_fwd(const void*, const void*, const void*, void*, int, int, int, int, int, cudaStream_t);
+DECL int b200_causal_conv1d_bwd(const void*, const void*, const void*, const void*, void*, float*, float*, int, int,
+                                int, int, int, cudaStream_t);
+
+namespace {
+
+static int64_t g_launches = 0;
+
+inline cudaStream_t cur_stream() { return at::cuda::getCurrentCUDAStream().stream(); }
+
+inline void check(int rc, const char* what, int n_kernels = 1) {
+  TORCH_CHECK(rc == 0, "fms_fsdp_b200 kernel '", what, "' failed with code ", rc, " (",
+              rc > 0 && rc < 1000 ? cudaGetErrorString((cudaError_t)rc) : "argument/descriptor error", ")");
+  g_launches += n_kernels;
+}
+inline void need(const at::Tensor& t, const char* name, at::ScalarType dt) {
+  TORCH_CHECK(t.is_cuda(), name, " must be a CUDA tensor");
+  TORCH_CHECK(t.scalar_type() == dt, name, " has dtype ", t.scalar_type(), ", expected ", dt);
+}
+inline void need_rowmajor2d(const at::Tensor& t, const char* name) {
+  TORCH_CHECK(t.dim() == 2 && t.stride(1) == 1, name, " must be 2-D with unit inner stride");
+  TORCH_CHECK((reinterpret_cast<uintptr_t>(t.data_ptr()) & 15) == 0 && (t.stride(0) * t.element_size()) % 16 == 0,
+              name, " must be 16-byte aligned (ptr and row stride)");
+}
+
+// layout: 0 = nt, 1 = nn, 2 = tn ; epi: 0 store, 1 +residual, 2 accumulate into c
+void gemm(const at::Tensor& a, const at::Tensor& b, at::Tensor& c, int64_t layout, int64_t epi,
+          const c10::optional<at::Tensor>& residual) {
+  c10::cuda::CUDAGuard guard(a.device());
+  need(a, "a", at::kBFloat16);
+  need(b, "b", at::kBFloat16);
+  need_rowmajor2d(a, "a");
+  need_rowmajor2d(b, "b");
+  need_rowmajor2d(c, "c");
+  TORCH_CHECK(c.scalar_type() == at::kBFloat16 || c.scalar_type() == at::kFloat, "c must be bf16 or fp32");
+  int M, N, K, a_mn = 0, b_mn = 0;
+  if (layout == 0) {
+    M = a.size(0); K = a.size(1); N = b.size(0);
+    TORCH_CHECK(b.size(1) == K, "nt: K mismatch");
+  } else if (layout == 1) {
+    M = a.size(0); K = a.size(1); N = b.size(1); b_mn = 1;
+    TORCH_CHECK(b.size(0) == K, "nn: K mismatch");
+  } else {
+    K = a.size(0); M = a.size(1); N = b.size(1); a_mn = b_mn = 1;
+    TORCH_CHECK(b.size(0) == K, "tn: K mismatch");
+  }
+  TORCH_CHECK(c.size(0) == M && c.size(1) == N, "c shape mismatch");
+  TORCH_CHECK(K % 8 == 0 && N % 8 == 0 && M % 8 == 0, "M, N, K must be multiples of 8");
+  const void* r = nullptr;
+  int ldr = 0;
+  if (epi == 1) {
+    TORCH_CHECK(residual.has_value(), "residual epilogue needs a residual");
+    need(*residual, "residual", at::kBFloat16);
+    need_rowmajor2d(*residual, "residual");
+    r = residual->data_ptr();
+    ldr = residual->stride(0);
+  }
+  check(b200_gemm_bf16(a.data_ptr(), b.data_ptr(), c.data_ptr(), r, M, N, K, a.stride(0), b.stride(0), c.stride(0),
+                       ldr, a_mn, b_mn, (int)epi, c.scalar_type() == at::kFloat ? 1 : 0, cur_stream()),
+        "gemm_bf16_tcgen05");
+}
+
+std::vector<at::Tensor> rmsnorm_fwd(const at::Tensor& x, const at::Tensor& w, double eps) {
+  c10::cuda::CUDAGuard guard(x.device());
+  need(x, "x", at::kBFloat16);
+  need(w, "w", at::kBFloat16);
+  TORCH_CHECK(x.is_contiguous() && w.is_contiguous());
+  const int D = x.size(-1), M = x.numel() / D;
+  auto y = at::empty_like(x);
+  auto rstd = at::empty({M}, x.options().dtype(at::kFloat));
+  check(b200_rmsnorm_fwd(x.data_ptr(), w.data_ptr(), y.data_ptr(), rstd.data_ptr<float>(), M, D, (float)eps,
+                         cur_stream()), "rmsnorm_fwd");
+  return {y, rstd};
+}
+std::vector<at::Tensor> rmsnorm_bwd(const at::Tensor& dy, const at::Tensor& x, const at::Tensor& w,
+                                    const at::Tensor& rstd) {
+  c10::cuda::CUDAGuard guard(x.device());
+  need(dy, "dy", at::kBFloat16);
+  need(x, "x", at::kBFloat16);
+  need(w, "w", at::kBFloat16);
+  need(rstd, "rstd", at::kFloat);
+  TORCH_CHECK(dy.is_contiguous() && x.is_contiguous());
+  const int D = x.size(-1), M = x.numel() / D;
+  auto dx = at::empty_like(x);
+  auto part = at::empty({b200_rmsnorm_bwd_grid(M), D}, x.options().dtype(at::kFloat));
+  auto dw = at::empty({D}, x.options().dtype(at::kFloat));
+  check(b200_rmsnorm_bwd(dy.data_ptr(), x.data_ptr(), w.data_ptr(), rstd.data_ptr<float>(), dx.data_ptr(),
+                         part.data_ptr<float>(), dw.data_ptr<float>(), M, D, cur_stream()), "rmsnorm_bwd", 2);
+  return {dx, dw};
+}
+void rope(at::Tensor& qkv, const at::Tensor& table, int64_t seq_len, int64_t nrot_heads, int64_t hd, int64_t rot,
+          bool inverse, int64_t pos_offset) {
+  c10::cuda::CUDAGuard guard(qkv.device());
+  need(qkv, "qkv", at::kBFloat16);
+  need(table, "table", at::kFloat);
+  TORCH_CHECK(qkv.dim() == 2 && qkv.stride(1) == 1 && table.is_contiguous());
+  TORCH_CHECK(table.size(0) >= seq_len + pos_offset && table.size(1) == rot / 2, "rope table too small");
+  check(b200_rope(qkv.data_ptr(), table.data_ptr<float>(), qkv.size(0), seq_len, qkv.stride(0), nrot_heads, hd, rot,
+                  inverse, pos_offset, cur_stream()), "rope");
+}
+at::Tensor swiglu_fwd(const at::Tensor& gu) {
+  c10::cuda::CUDAGuard guard(gu.device());
+  need(gu, "gu", at::kBFloat16);
+  TORCH_CHECK(gu.is_contiguous());
+  const int F = gu.size(-1) / 2;
+  const int64_t M = gu.numel() / (2 * F);
+  auto sizes = gu.sizes().vec();
+  sizes.back() = F;
+  auto out = at::empty(sizes, gu.options());
+  check(b200_swiglu_fwd(gu.data_ptr(), out.data_ptr(), M, F, cur_stream()), "swiglu_fwd");
+  return out;
+}
+at::Tensor swiglu_bwd(const at::Tensor& ds, const at::Tensor& gu) {
+  c10::cuda::CUDAGuard guard(gu.device());
+  need(gu, "gu", at::kBFloat16);
+  need(ds, "ds", at::kBFloat16);
+  TORCH_CHECK(gu.is_contiguous() && ds.is_contiguous());
+  const int F = gu.size(-1) / 2;
+  const int64_t M = gu.numel() / (2 * F);
+  auto dgu = at::empty_like(gu);
+  check(b200_swiglu_bwd(ds.data_ptr(), gu.data_ptr(), dgu.data_ptr(), M, F, cur_stream()), "swiglu_bwd");
+  return dgu;
+}
+at::Tensor embedding_fwd(const at::Tensor& tok, const at::Tensor& w) {
+  c10::cuda::CUDAGuard guard(w.device());
+  need(w, "w", at::kBFloat16);
+  TORCH_CHECK(tok.is_cuda() && tok.is_contiguous() &&
+              (tok.scalar_type() == at::kLong || tok.scalar_type() == at::kInt));
+  const int D = w.size(1);
+  const int64_t M = tok.numel();
+  auto out = at::empty({M, D}, w.options());
+  check(b200_embedding_fwd(tok.data_ptr(), tok.scalar_type() == at::kLong, w.data_ptr(), out.data_ptr(), M, D,
+                           cur_stream()), "embedding_fwd");
+  return out;
+}
+void embedding_bwd(const at::Tensor& dx, const at::Tensor& tok, at::Tensor& dw) {
+  c10::cuda::CUDAGuard guard(dx.device());
+  need(dx, "dx", at::kBFloat16);
+  TORCH_CHECK(dx.is_contiguous() && tok.is_contiguous() && dw.is_contiguous());
+  TORCH_CHECK(dw.scalar_type() == at::kBFloat16 || dw.scalar_type() == at::kFloat);
+  const int D = dx.size(-1);
+  const int64_t M = tok.numel();
+  check(b200_embedding_bwd(tok.data_ptr(), tok.scalar_type() == at::kLong, dx.data_ptr(), dw.data_ptr(),
+                           dw.scalar_type() == at::kFloat, M, D, cur_stream()), "embedding_bwd");
+}
+void count_valid(const at::Tensor& labels, int64_t ignore, at::Tensor& n_valid) {
+  c10::cuda::CUDAGuard guard(labels.device());
+  need(labels, "labels", at::kLong);
+  need(n_valid, "n_valid", at::kFloat);
+  check(b200_count_valid((const long long*)labels.data_ptr(), labels.numel(), ignore, n_valid.data_ptr<float>(),
+                         cur_stream()), "count_valid");
+}
+void ce_grad_inplace(at::Tensor& logits, const at::Tensor& labels, const at::Tensor& n_valid, at::Tensor& loss_sum,
+                     int64_t ignore) {
+  c10::cuda::CUDAGuard guard(logits.device());
+  need(logits, "logits", at::kBFloat16);
+  need(labels, "labels", at::kLong);
+  TORCH_CHECK(logits.dim() == 2 && logits.stride(1) == 1 && labels.is_contiguous());
+  check(b200_ce_grad_inplace(logits.data_ptr(), (const long long*)labels.data_ptr(), n_valid.data_ptr<float>(),
+                             loss_sum.data_ptr<float>(), logits.size(0), logits.size(1), logits.stride(0), ignore,
+                             cur_stream()), "ce_grad_inplace");
+}
+void adamw(at::Tensor& master, const at::Tensor& grad, at::Tensor& m, at::Tensor& v,
+           const c10::optional<at::Tensor>& lowp, double lr, double b1, double b2, double eps, double wd, int64_t step,
+           const c10::optional<at::Tensor>& grad_scale) {
+  c10::cuda::CUDAGuard guard(master.device());
+  need(master, "master", at::kFloat);
+  need(m, "m", at::kFloat);
+  need(v, "v", at::kFloat);
+  TORCH_CHECK(grad.scalar_type() == at::kBFloat16 || grad.scalar_type() == at::kFloat);
+  TORCH_CHECK(grad.numel() == master.numel());
+  void* lp = nullptr;
+  if (lowp.has_value()) {
+    need(*lowp, "lowp", at::kBFloat16);
+    lp = lowp->data_ptr();
+  }
+  const float* gs = grad_scale.has_value() ? grad_scale->data_ptr<float>() : nullptr;
+  const double bc1 = 1.0 - std::pow(b1, (double)step), bc2 = 1.0 - std::pow(b2, (double)step);
+  check(b200_adamw(master.data_ptr<float>(), grad.data_ptr(), grad.scalar_type() == at::kBFloat16,
+                   m.data_ptr<float>(), v.data_ptr<float>(), lp, master.numel(), (float)lr, (float)b1, (float)b2,
+                   (float)eps, (float)wd, (float)bc1, (float)std::sqrt(bc2), gs, cur_stream()), "adamw");
+}
+void sumsq(const at::Tensor& x, at::Tensor& out) {
+  c10::cuda::CUDAGuard guard(x.device());
+  TORCH_CHECK(x.is_contiguous() && (x.scalar_type() == at::kBFloat16 || x.scalar_type() == at::kFloat));
+  need(out, "out", at::kFloat);
+  check(b200_sumsq(x.data_ptr(), x.scalar_type() == at::kBFloat16, x.numel(), out.data_ptr<float>(), cur_stream()),
+        "sumsq");
+}
+
+std::vector<at::Tensor> attn_fwd(const at::Tensor& qkv, int64_t B, int64_t S, int64_t H, int64_t KVH, int64_t hd,
+                                 double scale) {
+  c10::cuda::CUDAGuard guard(qkv.device());
+  need(qkv, "qkv", at::kBFloat16);
+  TORCH_CHECK(qkv.is_contiguous());
+  auto o = at::empty({B * S, H * hd}, qkv.options());
+  auto lse = at::empty({B, H, S}, qkv.options().dtype(at::kFloat));
+  check(b200_attn_fwd(qkv.data_ptr(), o.data_ptr(), lse.data_ptr<float>(), B, S, H, KVH, hd, (float)scale,
+                      cur_stream()), "attn_fwd");
+  return {o, lse};
+}
+at::Tensor attn_bwd(const at::Tensor& dout, const at::Tensor& qkv, const at::Tensor& o, const at::Tensor& lse,
+                    int64_t B, int64_t S, int64_t H, int64_t KVH, int64_t hd, double scale) {
+  c10::cuda::CUDAGuard guard(qkv.device());
+  need(qkv, "qkv", at::kBFloat16);
+  need(dout, "do", at::kBFloat16);
+  need(o, "o", at::kBFloat16);
+  need(lse, "lse", at::kFloat);
+  TORCH_CHECK(qkv.is_contiguous() && dout.is_contiguous() && o.is_contiguous() && lse.is_contiguous());
+  auto dqkv = at::empty_like(qkv);
+  auto delta = at::empty({B, H, S}, qkv.options().dtype(at::kFloat));
+  check(b200_attn_bwd(dout.data_ptr(), qkv.data_ptr(), o.data_ptr(), lse.data_ptr<float>(), dqkv.data_ptr(),
+                      delta.data_ptr<float>(), B, S, H, KVH, hd, (float)scale, cur_stream()), "attn_bwd", 3);
+  return dqkv;
+}
+
+// ---- peer-memory collectives: pointer tables live on the device (int64 tensors of peer addresses)
+void p2p_allgather(const at::Tensor& peer_ptrs, at::Tensor& full, int64_t shard_bytes, int64_t world, int64_t rank) {
+  c10::cuda::CUDAGuard guard(full.device());
+  check(b200_p2p_allgather((const void* const*)peer_ptrs.data_ptr(), full.data_ptr(), shard_bytes, world, rank,
+                           cur_stream()), "p2p_allgather");
+}
+void reduce_scatter(const at::Tensor& peer_ptrs, at::Tensor& out32, int64_t elem_offset, int64_t world, int64_t rank,
+                    bool src_bf16, double scale, const c10::optional<at::Tensor>& sumsq_out) {
+  c10::cuda::CUDAGuard guard(out32.device());
+  need(out32, "out", at::kFloat);
+  check(b200_reduce_scatter((const void* const*)peer_ptrs.data_ptr(), out32.data_ptr<float>(), out32.numel(),
+                            elem_offset, world, rank, src_bf16, (float)scale,
+                            sumsq_out.has_value() ? sumsq_out->data_ptr<float>() : nullptr, cur_stream()),
+        "reduce_scatter");
+}
+void allreduce_inplace(const at::Tensor& peer_ptrs, int64_t numel, int64_t world, int64_t rank, bool is_bf16,
+                       double scale, const c10::optional<at::Tensor>& sumsq_out, const at::Tensor& anchor) {
+  c10::cuda::CUDAGuard guard(anchor.device());
+  check(b200_allreduce_inplace((void* const*)peer_ptrs.data_ptr(), numel, world, rank, is_bf16, (float)scale,
+                               sumsq_out.has_value() ? sumsq_out->data_ptr<float>() : nullptr, cur_stream()),
+        "allreduce_inplace");
+}
+void signal_barrier(const at::Tensor& pad_ptrs, int64_t world, int64_t rank, int64_t epoch, const at::Tensor& anchor) {
+  c10::cuda::CUDAGuard guard(anchor.device());
+  check(b200_signal_barrier((uint32_t* const*)pad_ptrs.data_ptr(), world, rank, (uint32_t)epoch, cur_stream()),
+        "signal_barrier");
+}
+
+at::Tensor causal_conv1d_fwd(const at::Tensor& x, const at::Tensor& w, const c10::optional<at::Tensor>& b,
+                             int64_t seq_len, bool act) {
+  c10::cuda::CUDAGuard guard(x.device());
+  need(x, "x", at::kBFloat16);
+  need(w, "w", at::kBFloat16);
+  TORCH_CHECK(x.is_contiguous() && w.is_contiguous());
+  auto y = at::empty_like(x);
+  check(b200_causal_conv1d_fwd(x.data_ptr(), w.data_ptr(), b.has_value() ? b->data_ptr() : nullptr, y.data_ptr(),
+                               x.size(0), x.size(1), w.size(1), seq_len, act, cur_stream()), "causal_conv1d_fwd");
+  return y;
+}
+std::vector<at::Tensor> causal_conv1d_bwd(const at::Tensor& dy, const at::Tensor& x, const at::Tensor& w,
+                                          const c10::optional<at::Tensor>& b, int64_t seq_len, bool act) {
+  c10::cuda::CUDAGuard guard(x.device());
+  need(x, "x", at::kBFloat16);
+  need(dy, "dy", at::kBFloat16);
+  TORCH_CHECK(x.is_contiguous() && dy.is_contiguous());
+  auto dx = at::empty_like(x);
+  auto dw = at::zeros({w.size(0), w.size(1)}, x.options().dtype(at::kFloat));
+  auto db = at::zeros({w.size(0)}, x.options().dtype(at::kFloat));
+  check(b200_causal_conv1d_bwd(dy.data_ptr(), x.data_ptr(), w.data_ptr(), b.has_value() ? b->data_ptr() : nullptr,
+                               dx.data_ptr(), dw.data_ptr<float>(), db.data_ptr<float>(), x.size(0), x.size(1),
+                               w.size(1), seq_len, act, cur_stream()), "causal_conv1d_bwd");
+  return {dx, dw, db};
+}
+
+int64_t launch_count() { return g_launches; }
+void reset_launch_count() { g_launches = 0; }
+
+}  // namespace
+
+PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
+  m.doc() = "fms_fsdp_b200 sm_100a kernels";
+  m.def("gemm", &gemm);
+  m.def("rmsnorm_fwd", &rmsnorm_fwd);
+  m.def("rmsnorm_bwd", &rmsnorm_bwd);
+  m.def("rope", &rope);
+  m.def("swiglu_fwd", &swiglu_fwd);
+  m.def("swiglu_bwd", &swiglu_bwd);
+  m.def("embedding_fwd", &embedding_fwd);
+  m.def("embedding_bwd", &embedding_bwd);
+  m.def("count_valid", &count_valid);
+  m.def("ce_grad_inplace", &ce_grad_inplace);
+  m.def("adamw", &adamw);
+  m.def("sumsq", &sumsq);
+  m.def("attn_fwd", &attn_fwd);
+  m.def("attn_bwd", &attn_bwd);
+  m.def("p2p_allgather", &p2p_allgather);
+  m.def("reduce_scatter", &reduce_scatter);
+  m.def("allreduce_inplace", &allreduce_inplace);
+  m.def("signal_barrier", &signal_barrier);
+  m.def("causal_conv1d_fwd", &causal_conv1d_fwd);
+  m.def("causal_conv1d_bwd", &causal_conv1d_bwd);
+  m.def("launch_count", &launch_count);
+  m.def("reset_launch_count", &reset_launch_count);
+}

@@ -1,0 +1,503 @@
+// Bandwidth-bound kernels of the engine (sm_100a): RMSNorm fwd/bwd, RoPE, SwiGLU fwd/bwd, embedding
+// fwd/bwd, softmax-cross-entropy gradient (in place on a logits chunk), fused sharded AdamW, sum of
+// squares.  All are single-pass over HBM with 16-byte vector accesses; fp32 math, bf16 I/O.
+// SURVEY.md K2/K5/K7/K9/K10(softmax part)/K11/K12.
+#include "common.cuh"
+
+namespace b200 {
+
+constexpr int NT = 256;  // threads per CTA for row kernels
+
+B200_DEVINL float block_sum(float v, float* sh) {
+  v = warp_sum(v);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  __syncthreads();  // protect sh from the previous use
+  if (l == 0) sh[w] = v;
+  __syncthreads();
+  float r = (l < (blockDim.x >> 5)) ? sh[l] : 0.f;
+  r = warp_sum(r);
+  return r;
+}
+B200_DEVINL float block_max(float v, float* sh) {
+  v = warp_max(v);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  __syncthreads();
+  if (l == 0) sh[w] = v;
+  __syncthreads();
+  float r = (l < (blockDim.x >> 5)) ? sh[l] : -INFINITY;
+  r = warp_max(r);
+  return r;
+}
+
+B200_DEVINL void load8(const __nv_bfloat16* p, float (&f)[8]) {
+  uint4 u = *reinterpret_cast<const uint4*>(p);
+  float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+  f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
+}
+B200_DEVINL void store8(__nv_bfloat16* p, const float (&f)[8]) {
+  uint4 u;
+  u.x = pack_bf16x2(f[0], f[1]); u.y = pack_bf16x2(f[2], f[3]);
+  u.z = pack_bf16x2(f[4], f[5]); u.w = pack_bf16x2(f[6], f[7]);
+  *reinterpret_cast<uint4*>(p) = u;
+}
+
+// ------------------------------------------------------------------------------------- RMSNorm
+// One CTA per row (grid-stride).  Row cached in registers: D <= NT*8*MAXC.
+constexpr int MAXC = 4;
+
+__global__ void __launch_bounds__(NT) rmsnorm_fwd_kernel(const __nv_bfloat16* __restrict__ x,
+                                                         const __nv_bfloat16* __restrict__ w,
+                                                         __nv_bfloat16* __restrict__ y, float* __restrict__ rstd,
+                                                         int M, int D, float eps) {
+  __shared__ float sh[32];
+  for (int row = blockIdx.x; row < M; row += gridDim.x) {
+    const __nv_bfloat16* xr = x + (size_t)row * D;
+    float v[MAXC][8];
+    float ss = 0.f;
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c) {
+      const int col = (c * NT + threadIdx.x) * 8;
+      if (col < D) {
+        load8(xr + col, v[c]);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) ss += v[c][i] * v[c][i];
+      }
+    }
+    ss = block_sum(ss, sh);
+    const float r = rsqrtf(ss / (float)D + eps);
+    if (threadIdx.x == 0) rstd[row] = r;
+    __nv_bfloat16* yr = y + (size_t)row * D;
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c) {
+      const int col = (c * NT + threadIdx.x) * 8;
+      if (col < D) {
+        float wv[8], o[8];
+        load8(w + col, wv);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] = v[c][i] * r * wv[i];
+        store8(yr + col, o);
+      }
+    }
+  }
+}
+
+// dx = r * (g - xhat * mean(g*xhat)),  g = dy*w,  xhat = x*r ;  dw_partial[cta] += dy*xhat
+__global__ void __launch_bounds__(NT) rmsnorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy,
+                                                         const __nv_bfloat16* __restrict__ x,
+                                                         const __nv_bfloat16* __restrict__ w,
+                                                         const float* __restrict__ rstd,
+                                                         __nv_bfloat16* __restrict__ dx, float* __restrict__ dw_part,
+                                                         int M, int D) {
+  __shared__ float sh[32];
+  float dwacc[MAXC][8];
+#pragma unroll
+  for (int c = 0; c < MAXC; ++c)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) dwacc[c][i] = 0.f;
+  float wv[MAXC][8];
+#pragma unroll
+  for (int c = 0; c < MAXC; ++c) {
+    const int col = (c * NT + threadIdx.x) * 8;
+    if (col < D) load8(w + col, wv[c]);
+  }
+  for (int row = blockIdx.x; row < M; row += gridDim.x) {
+    const float r = rstd[row];
+    float g[MAXC][8], xh[MAXC][8];
+    float dot = 0.f;
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c) {
+      const int col = (c * NT + threadIdx.x) * 8;
+      if (col < D) {
+        float a[8], b[8];
+        load8(dy + (size_t)row * D + col, a);
+        load8(x + (size_t)row * D + col, b);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          xh[c][i] = b[i] * r;
+          g[c][i] = a[i] * wv[c][i];
+          dot += g[c][i] * xh[c][i];
+          dwacc[c][i] += a[i] * xh[c][i];
+        }
+      }
+    }
+    dot = block_sum(dot, sh) / (float)D;
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c) {
+      const int col = (c * NT + threadIdx.x) * 8;
+      if (col < D) {
+        float o[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] = r * (g[c][i] - xh[c][i] * dot);
+        store8(dx + (size_t)row * D + col, o);
+      }
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < MAXC; ++c) {
+    const int col = (c * NT + threadIdx.x) * 8;
+    if (col < D) {
+      float4* o = reinterpret_cast<float4*>(dw_part + (size_t)blockIdx.x * D + col);
+      o[0] = make_float4(dwacc[c][0], dwacc[c][1], dwacc[c][2], dwacc[c][3]);
+      o[1] = make_float4(dwacc[c][4], dwacc[c][5], dwacc[c][6], dwacc[c][7]);
+    }
+  }
+}
+
+// out[d] = sum_p part[p, d]
+__global__ void colsum_kernel(const float* __restrict__ part, float* __restrict__ out, int P, int D) {
+  const int d = blockIdx.x * blockDim.x + threadIdx.x;
+  if (d >= D) return;
+  float s = 0.f;
+  for (int p = 0; p < P; ++p) s += part[(size_t)p * D + d];
+  out[d] = s;
+}
+
+// ---------------------------------------------------------------------------------------- RoPE
+// In place on heads [0, nrot) of a fused [M, nheads_total*hd] projection; pairs (2i, 2i+1);
+// table [S, rot/2, 2] fp32 (cos, sin).  One thread = 8 elements = 4 pairs.
+__global__ void rope_kernel(__nv_bfloat16* __restrict__ qkv, const float* __restrict__ table, int M, int seq_len,
+                            int row_stride, int nrot_heads, int hd, int rot, float sign, int pos_offset) {
+  const int vec_per_head = rot / 8;
+  const size_t total = (size_t)M * nrot_heads * vec_per_head;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (size_t)gridDim.x * blockDim.x) {
+    const int vi = (int)(idx % vec_per_head);
+    const size_t t = idx / vec_per_head;
+    const int head = (int)(t % nrot_heads);
+    const size_t row = t / nrot_heads;
+    const int pos = (int)(row % seq_len) + pos_offset;
+    __nv_bfloat16* p = qkv + row * row_stride + head * hd + vi * 8;
+    float f[8];
+    load8(p, f);
+    const float4* cs = reinterpret_cast<const float4*>(table + ((size_t)pos * (rot / 2) + vi * 4) * 2);
+    const float4 c0 = cs[0], c1 = cs[1];
+    const float cosv[4] = {c0.x, c0.z, c1.x, c1.z};
+    const float sinv[4] = {c0.y * sign, c0.w * sign, c1.y * sign, c1.w * sign};
+    float o[8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      o[2 * i] = f[2 * i] * cosv[i] - f[2 * i + 1] * sinv[i];
+      o[2 * i + 1] = f[2 * i] * sinv[i] + f[2 * i + 1] * cosv[i];
+    }
+    store8(p, o);
+  }
+}
+
+// -------------------------------------------------------------------------------------- SwiGLU
+__global__ void swiglu_fwd_kernel(const __nv_bfloat16* __restrict__ gu, __nv_bfloat16* __restrict__ out, size_t M,
+                                  int F) {
+  const int vec = F / 8;
+  const size_t total = M * vec;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (size_t)gridDim.x * blockDim.x) {
+    const size_t row = idx / vec;
+    const int c = (int)(idx % vec) * 8;
+    float g[8], u[8], o[8];
+    load8(gu + row * 2 * F + c, g);
+    load8(gu + row * 2 * F + F + c, u);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[i] = g[i] / (1.f + __expf(-g[i])) * u[i];
+    store8(out + row * F + c, o);
+  }
+}
+__global__ void swiglu_bwd_kernel(const __nv_bfloat16* __restrict__ ds, const __nv_bfloat16* __restrict__ gu,
+                                  __nv_bfloat16* __restrict__ dgu, size_t M, int F) {
+  const int vec = F / 8;
+  const size_t total = M * vec;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (size_t)gridDim.x * blockDim.x) {
+    const size_t row = idx / vec;
+    const int c = (int)(idx % vec) * 8;
+    float g[8], u[8], d[8], dg[8], du[8];
+    load8(gu + row * 2 * F + c, g);
+    load8(gu + row * 2 * F + F + c, u);
+    load8(ds + row * F + c, d);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float sig = 1.f / (1.f + __expf(-g[i]));
+      dg[i] = d[i] * u[i] * sig * (1.f + g[i] * (1.f - sig));
+      du[i] = d[i] * g[i] * sig;
+    }
+    store8(dgu + row * 2 * F + c, dg);
+    store8(dgu + row * 2 * F + F + c, du);
+  }
+}
+
+// ----------------------------------------------------------------------------------- embedding
+template <typename IdxT>
+__global__ void embedding_fwd_kernel(const IdxT* __restrict__ tok, const __nv_bfloat16* __restrict__ w,
+                                     __nv_bfloat16* __restrict__ out, size_t M, int D) {
+  const int vec = D / 8;
+  const size_t total = M * vec;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (size_t)gridDim.x * blockDim.x) {
+    const size_t row = idx / vec;
+    const int c = (int)(idx % vec) * 8;
+    const size_t t = (size_t)tok[row];
+    *reinterpret_cast<uint4*>(out + row * D + c) = *reinterpret_cast<const uint4*>(w + t * D + c);
+  }
+}
+template <typename IdxT>
+__global__ void embedding_bwd_kernel(const IdxT* __restrict__ tok, const __nv_bfloat16* __restrict__ dx,
+                                     __nv_bfloat16* __restrict__ dw, size_t M, int D) {
+  const int vec = D / 2;
+  const size_t total = M * vec;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (size_t)gridDim.x * blockDim.x) {
+    const size_t row = idx / vec;
+    const int c = (int)(idx % vec) * 2;
+    const size_t t = (size_t)tok[row];
+    const __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(dx + row * D + c);
+    atomicAdd(reinterpret_cast<__nv_bfloat162*>(dw + t * D + c), v);
+  }
+}
+template <typename IdxT>
+__global__ void embedding_bwd_f32_kernel(const IdxT* __restrict__ tok, const __nv_bfloat16* __restrict__ dx,
+                                         float* __restrict__ dw, size_t M, int D) {
+  const size_t total = M * D;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (size_t)gridDim.x * blockDim.x) {
+    const size_t row = idx / D;
+    const int c = (int)(idx % D);
+    atomicAdd(dw + (size_t)tok[row] * D + c, __bfloat162float(dx[idx]));
+  }
+}
+
+// ------------------------------------------------------------------ softmax cross-entropy gradient
+// count of labels != ignore_index  ->  *n_valid (float)
+__global__ void count_valid_kernel(const long long* __restrict__ labels, int M, long long ignore, float* n_valid) {
+  __shared__ float sh[32];
+  float c = 0.f;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < M; i += gridDim.x * blockDim.x)
+    c += (labels[i] != ignore) ? 1.f : 0.f;
+  c = block_sum(c, sh);
+  if (threadIdx.x == 0 && c != 0.f) atomicAdd(n_valid, c);
+}
+// One CTA per row of a bf16 logits chunk [rows, V] (row stride ld): in place logits -> (softmax - onehot)/n_valid,
+// loss_sum += (lse - logit[label]).  Rows with ignored labels get zero gradient.
+__global__ void __launch_bounds__(NT) ce_grad_inplace_kernel(__nv_bfloat16* __restrict__ logits,
+                                                             const long long* __restrict__ labels,
+                                                             const float* __restrict__ n_valid,
+                                                             float* __restrict__ loss_sum, int rows, int V, int ld,
+                                                             long long ignore) {
+  __shared__ float sh[32];
+  for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+    __nv_bfloat16* lr = logits + (size_t)row * ld;
+    const long long lab = labels[row];
+    const bool valid = lab != ignore;
+    // pass 1: row max
+    float mx = -INFINITY;
+    for (int c = threadIdx.x * 8; c < V; c += NT * 8) {
+      float f[8];
+      load8(lr + c, f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) mx = fmaxf(mx, f[i]);
+    }
+    mx = block_max(mx, sh);
+    // pass 2: sum exp (row is L2/L1 resident: 2*V bytes)
+    float se = 0.f;
+    for (int c = threadIdx.x * 8; c < V; c += NT * 8) {
+      float f[8];
+      load8(lr + c, f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) se += __expf(f[i] - mx);
+    }
+    se = block_sum(se, sh);
+    const float lse = mx + __logf(se);
+    const float inv_n = valid ? 1.f / fmaxf(*n_valid, 1.f) : 0.f;
+    if (threadIdx.x == 0 && valid) atomicAdd(loss_sum, lse - __bfloat162float(lr[lab]));
+    __syncthreads();  // the label logit must be read before it is overwritten
+    // pass 3: gradient in place
+    for (int c = threadIdx.x * 8; c < V; c += NT * 8) {
+      float f[8], o[8];
+      load8(lr + c, f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float p = __expf(f[i] - lse);
+        if (c + i == lab) p -= 1.f;
+        o[i] = p * inv_n;
+      }
+      store8(lr + c, o);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------ fused AdamW
+// Decoupled weight decay Adam on a flat fp32 master shard; applies the clip coefficient; refreshes the
+// bf16 compute shard.  (torch.optim.AdamW update order.)
+template <typename GradT>
+__global__ void adamw_kernel(float* __restrict__ master, const GradT* __restrict__ grad, float* __restrict__ m,
+                             float* __restrict__ v, __nv_bfloat16* __restrict__ lowp, size_t n, float lr, float b1,
+                             float b2, float eps, float wd, float bc1, float bc2_sqrt,
+                             const float* __restrict__ grad_scale) {
+  const float gs = grad_scale ? *grad_scale : 1.f;
+  const float decay = 1.f - lr * wd;
+  const float step_size = lr / bc1;
+  for (size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < n;
+       i += (size_t)gridDim.x * blockDim.x * 4) {
+    float4 p = *reinterpret_cast<const float4*>(master + i);
+    float4 mm = *reinterpret_cast<const float4*>(m + i);
+    float4 vv = *reinterpret_cast<const float4*>(v + i);
+    float g[4];
+    if constexpr (sizeof(GradT) == 2) {
+      uint2 u = *reinterpret_cast<const uint2*>(grad + i);
+      float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y);
+      g[0] = a.x; g[1] = a.y; g[2] = b.x; g[3] = b.y;
+    } else {
+      float4 gg = *reinterpret_cast<const float4*>(grad + i);
+      g[0] = gg.x; g[1] = gg.y; g[2] = gg.z; g[3] = gg.w;
+    }
+    float pp[4] = {p.x, p.y, p.z, p.w}, ma[4] = {mm.x, mm.y, mm.z, mm.w}, va[4] = {vv.x, vv.y, vv.z, vv.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float gk = g[k] * gs;
+      pp[k] *= decay;
+      ma[k] = b1 * ma[k] + (1.f - b1) * gk;
+      va[k] = b2 * va[k] + (1.f - b2) * gk * gk;
+      const float denom = sqrtf(va[k]) / bc2_sqrt + eps;
+      pp[k] -= step_size * ma[k] / denom;
+    }
+    *reinterpret_cast<float4*>(master + i) = make_float4(pp[0], pp[1], pp[2], pp[3]);
+    *reinterpret_cast<float4*>(m + i) = make_float4(ma[0], ma[1], ma[2], ma[3]);
+    *reinterpret_cast<float4*>(v + i) = make_float4(va[0], va[1], va[2], va[3]);
+    if (lowp) {
+      uint2 o;
+      o.x = pack_bf16x2(pp[0], pp[1]);
+      o.y = pack_bf16x2(pp[2], pp[3]);
+      *reinterpret_cast<uint2*>(lowp + i) = o;
+    }
+  }
+}
+
+template <typename T>
+__global__ void sumsq_kernel(const T* __restrict__ x, size_t n, float* __restrict__ out) {
+  __shared__ float sh[32];
+  float s = 0.f;
+  for (size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < n;
+       i += (size_t)gridDim.x * blockDim.x * 4) {
+    if constexpr (sizeof(T) == 2) {
+      uint2 u = *reinterpret_cast<const uint2*>(x + i);
+      float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y);
+      s += a.x * a.x + a.y * a.y + b.x * b.x + b.y * b.y;
+    } else {
+      float4 f = *reinterpret_cast<const float4*>(x + i);
+      s += f.x * f.x + f.y * f.y + f.z * f.z + f.w * f.w;
+    }
+  }
+  s = block_sum(s, sh);
+  if (threadIdx.x == 0) atomicAdd(out, s);
+}
+
+static inline int grid_for(size_t work_items, int threads, int max_blocks = 148 * 8) {
+  size_t b = (work_items + threads - 1) / threads;
+  if (b < 1) b = 1;
+  return (int)(b > (size_t)max_blocks ? max_blocks : b);
+}
+
+}  // namespace b200
+
+using namespace b200;
+#define CK() return (int)cudaGetLastError()
+
+extern "C" int b200_rmsnorm_fwd(const void* x, const void* w, void* y, float* rstd, int M, int D, float eps,
+                                cudaStream_t s) {
+  if (D % 8 || D > NT * 8 * MAXC) return -1;
+  rmsnorm_fwd_kernel<<<M < 148 * 8 ? M : 148 * 8, NT, 0, s>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)w,
+                                                             (__nv_bfloat16*)y, rstd, M, D, eps);
+  CK();
+}
+extern "C" int b200_rmsnorm_bwd_grid(int M) { return M < 148 * 4 ? M : 148 * 4; }
+extern "C" int b200_rmsnorm_bwd(const void* dy, const void* x, const void* w, const float* rstd, void* dx,
+                                float* dw_part, float* dw, int M, int D, cudaStream_t s) {
+  if (D % 8 || D > NT * 8 * MAXC) return -1;
+  const int grid = b200_rmsnorm_bwd_grid(M);
+  rmsnorm_bwd_kernel<<<grid, NT, 0, s>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, (const __nv_bfloat16*)w,
+                                         rstd, (__nv_bfloat16*)dx, dw_part, M, D);
+  colsum_kernel<<<(D + 255) / 256, 256, 0, s>>>(dw_part, dw, grid, D);
+  CK();
+}
+extern "C" int b200_rope(void* qkv, const float* table, int M, int seq_len, int row_stride, int nrot_heads, int hd,
+                         int rot, int inverse, int pos_offset, cudaStream_t s) {
+  if (rot % 8 || hd % 8 || row_stride % 8) return -1;
+  size_t total = (size_t)M * nrot_heads * (rot / 8);
+  rope_kernel<<<grid_for(total, 256), 256, 0, s>>>((__nv_bfloat16*)qkv, table, M, seq_len, row_stride, nrot_heads, hd,
+                                                   rot, inverse ? -1.f : 1.f, pos_offset);
+  CK();
+}
+extern "C" int b200_swiglu_fwd(const void* gu, void* out, long long M, int F, cudaStream_t s) {
+  if (F % 8) return -1;
+  swiglu_fwd_kernel<<<grid_for((size_t)M * (F / 8), 256), 256, 0, s>>>((const __nv_bfloat16*)gu, (__nv_bfloat16*)out,
+                                                                       (size_t)M, F);
+  CK();
+}
+extern "C" int b200_swiglu_bwd(const void* ds, const void* gu, void* dgu, long long M, int F, cudaStream_t s) {
+  if (F % 8) return -1;
+  swiglu_bwd_kernel<<<grid_for((size_t)M * (F / 8), 256), 256, 0, s>>>(
+      (const __nv_bfloat16*)ds, (const __nv_bfloat16*)gu, (__nv_bfloat16*)dgu, (size_t)M, F);
+  CK();
+}
+extern "C" int b200_embedding_fwd(const void* tok, int tok_is_i64, const void* w, void* out, long long M, int D,
+                                  cudaStream_t s) {
+  if (D % 8) return -1;
+  int g = grid_for((size_t)M * (D / 8), 256);
+  if (tok_is_i64)
+    embedding_fwd_kernel<long long><<<g, 256, 0, s>>>((const long long*)tok, (const __nv_bfloat16*)w,
+                                                      (__nv_bfloat16*)out, (size_t)M, D);
+  else
+    embedding_fwd_kernel<int><<<g, 256, 0, s>>>((const int*)tok, (const __nv_bfloat16*)w, (__nv_bfloat16*)out,
+                                                (size_t)M, D);
+  CK();
+}
+extern "C" int b200_embedding_bwd(const void* tok, int tok_is_i64, const void* dx, void* dw, int dw_is_f32,
+                                  long long M, int D, cudaStream_t s) {
+  if (D % 2) return -1;
+  if (dw_is_f32) {
+    int g = grid_for((size_t)M * D, 256);
+    if (tok_is_i64)
+      embedding_bwd_f32_kernel<long long><<<g, 256, 0, s>>>((const long long*)tok, (const __nv_bfloat16*)dx,
+                                                            (float*)dw, (size_t)M, D);
+    else
+      embedding_bwd_f32_kernel<int><<<g, 256, 0, s>>>((const int*)tok, (const __nv_bfloat16*)dx, (float*)dw,
+                                                      (size_t)M, D);
+  } else {
+    int g = grid_for((size_t)M * (D / 2), 256);
+    if (tok_is_i64)
+      embedding_bwd_kernel<long long><<<g, 256, 0, s>>>((const long long*)tok, (const __nv_bfloat16*)dx,
+                                                        (__nv_bfloat16*)dw, (size_t)M, D);
+    else
+      embedding_bwd_kernel<int><<<g, 256, 0, s>>>((const int*)tok, (const __nv_bfloat16*)dx, (__nv_bfloat16*)dw,
+                                                  (size_t)M, D);
+  }
+  CK();
+}
+extern "C" int b200_count_valid(const long long* labels, int M, long long ignore, float* n_valid, cudaStream_t s) {
+  count_valid_kernel<<<grid_for((size_t)M, 256, 64), 256, 0, s>>>(labels, M, ignore, n_valid);
+  CK();
+}
+extern "C" int b200_ce_grad_inplace(void* logits, const long long* labels, const float* n_valid, float* loss_sum,
+                                    int rows, int V, int ld, long long ignore, cudaStream_t s) {
+  if (V % 8 || ld % 8) return -1;
+  ce_grad_inplace_kernel<<<rows < 148 * 8 ? rows : 148 * 8, NT, 0, s>>>((__nv_bfloat16*)logits, labels, n_valid,
+                                                                       loss_sum, rows, V, ld, ignore);
+  CK();
+}
+extern "C" int b200_adamw(float* master, const void* grad, int grad_is_bf16, float* m, float* v, void* lowp,
+                          long long n, float lr, float b1, float b2, float eps, float wd, float bc1, float bc2_sqrt,
+                          const float* grad_scale, cudaStream_t s) {
+  if (n % 4) return -1;
+  int g = grid_for((size_t)n / 4, 256, 148 * 16);
+  if (grad_is_bf16)
+    adamw_kernel<__nv_bfloat16><<<g, 256, 0, s>>>(master, (const __nv_bfloat16*)grad, m, v, (__nv_bfloat16*)lowp,
+                                                  (size_t)n, lr, b1, b2, eps, wd, bc1, bc2_sqrt, grad_scale);
+  else
+    adamw_kernel<float><<<g, 256, 0, s>>>(master, (const float*)grad, m, v, (__nv_bfloat16*)lowp, (size_t)n, lr, b1,
+                                          b2, eps, wd, bc1, bc2_sqrt, grad_scale);
+  CK();
+}
+extern "C" int b200_sumsq(const void* x, int is_bf16, long long n, float* out, cudaStream_t s) {
+  if (n % 4) return -1;
+  int g = grid_for((size_t)n / 4, 256, 148 * 8);
+  if (is_bf16) sumsq_kernel<__nv_bfloat16><<<g, 256, 0, s>>>((const __nv_bfloat16*)x, (size_t)n, out);
+  else sumsq_kernel<float><<<g, 256, 0, s>>>((const float*)x, (size_t)n, out);
+  CK();
+}

@@ -1,0 +1,238 @@
+"""sm_100a primitive set (same signatures as ``torch_kernels``), backed by ``fms_fsdp_b200._C``.
+
+Every function here launches hand-written kernels from ``csrc/`` (tcgen05 GEMM / flash attention,
+fused elementwise, peer-memory collectives).  ``launch_count()`` reports how many of OUR kernels
+were launched (bench.py's ``gpu_launches``).
+"""
+from __future__ import annotations
+
+import math
+import os
+from typing import Optional
+
+import torch
+
+from fms_fsdp_b200.ops import _ext, torch_kernels
+
+NAME = "cuda"
+_C = _ext.require()
+
+_LAYOUT = {"nt": 0, "nn": 1, "tn": 2}
+# attention implementation: "tcgen05" (ours) | "sdpa" (library fallback, debugging only)
+ATTN_IMPL = os.environ.get("FMS_B200_ATTN_IMPL", "tcgen05")
+GEMM_IMPL = os.environ.get("FMS_B200_GEMM_IMPL", "tcgen05")  # "cublas" = library fallback, debugging only
+
+
+def launch_count() -> int:
+    return int(_C.launch_count())
+
+
+def reset_launch_count():
+    _C.reset_launch_count()
+
+
+def _bf16c(t):
+    if t.dtype != torch.bfloat16:
+        t = t.to(torch.bfloat16)
+    return t if t.is_contiguous() else t.contiguous()
+
+
+# ------------------------------------------------------------------------------------------ GEMM
+def gemm(a, b, layout="nt", out=None, accumulate=False, residual=None, out_dtype=None):
+    if GEMM_IMPL != "tcgen05" or a.dtype != torch.bfloat16 or b.dtype != torch.bfloat16:
+        return torch_kernels.gemm(a, b, layout, out=out, accumulate=accumulate, residual=residual, out_dtype=out_dtype)
+    if layout == "nt":
+        M, N = a.shape[0], b.shape[0]
+    elif layout == "nn":
+        M, N = a.shape[0], b.shape[1]
+    else:
+        M, N = a.shape[1], b.shape[1]
+    K = a.shape[1] if layout != "tn" else a.shape[0]
+    if (M % 8) or (N % 8) or (K % 8):
+        return torch_kernels.gemm(a, b, layout, out=out, accumulate=accumulate, residual=residual, out_dtype=out_dtype)
+    if a.stride(-1) != 1:
+        a = a.contiguous()
+    if b.stride(-1) != 1:
+        b = b.contiguous()
+    if out is None:
+        out = torch.empty(M, N, dtype=out_dtype or a.dtype, device=a.device)
+    epi = 0
+    if residual is not None:
+        if accumulate:
+            raise ValueError("residual and accumulate are mutually exclusive")
+        epi = 1
+    elif accumulate:
+        epi = 2
+    _C.gemm(a, b, out, _LAYOUT[layout], epi, residual)
+    return out
+
+
+# --------------------------------------------------------------------------------------- RMSNorm
+def rmsnorm_fwd(x, w, eps):
+    if x.dtype != torch.bfloat16 or x.shape[-1] % 8 or x.shape[-1] > 8192:
+        return torch_kernels.rmsnorm_fwd(x, w, eps)
+    y, rstd = _C.rmsnorm_fwd(x.contiguous(), _bf16c(w), float(eps))
+    return y, rstd
+
+
+def rmsnorm_bwd(dy, x, w, rstd):
+    if x.dtype != torch.bfloat16 or x.shape[-1] % 8 or x.shape[-1] > 8192:
+        return torch_kernels.rmsnorm_bwd(dy, x, w, rstd)
+    dx, dw = _C.rmsnorm_bwd(dy.contiguous(), x.contiguous(), _bf16c(w), rstd)
+    return dx, dw
+
+
+add_rmsnorm_fwd = torch_kernels.add_rmsnorm_fwd
+rmsnorm_gated_fwd = torch_kernels.rmsnorm_gated_fwd
+rmsnorm_gated_bwd = torch_kernels.rmsnorm_gated_bwd
+
+# ------------------------------------------------------------------------------------------ RoPE
+rope_table = torch_kernels.rope_table
+
+
+def rope_(qkv, table, seq_len, nheads, kvheads, head_dim, rot_dim=None, inverse=False, pos_offset=0):
+    rot_dim = head_dim if rot_dim is None else rot_dim
+    if qkv.dtype != torch.bfloat16 or rot_dim % 8 or head_dim % 8:
+        return torch_kernels.rope_(qkv, table, seq_len, nheads, kvheads, head_dim, rot_dim, inverse, pos_offset)
+    _C.rope(qkv, table, seq_len, nheads + kvheads, head_dim, rot_dim, bool(inverse), pos_offset)
+    return qkv
+
+
+# ------------------------------------------------------------------------------------- attention
+def _sdpa_fwd(qkv, B, S, H, KVH, hd, scale):
+    q, k, v = torch_kernels._split_qkv(qkv, B, S, H, KVH, hd)
+    q, k, v = (t.transpose(1, 2) for t in (q, k, v))
+    o = torch.nn.functional.scaled_dot_product_attention(q, k, v, is_causal=True, scale=scale, enable_gqa=(KVH != H))
+    return o.transpose(1, 2).reshape(B * S, H * hd).contiguous()
+
+
+def attn_fwd(qkv, B, S, H, KVH, hd, scale, causal=True):
+    if ATTN_IMPL == "tcgen05" and qkv.dtype == torch.bfloat16 and hd in (64, 128) and causal:
+        o, lse = _C.attn_fwd(qkv.contiguous(), B, S, H, KVH, hd, float(scale))
+        return o, lse
+    if ATTN_IMPL == "sdpa":
+        return _sdpa_fwd(qkv, B, S, H, KVH, hd, scale), torch.empty(0, device=qkv.device)
+    return torch_kernels.attn_fwd(qkv, B, S, H, KVH, hd, scale, causal)
+
+
+def attn_bwd(do, qkv, o, lse, B, S, H, KVH, hd, scale, causal=True):
+    if ATTN_IMPL == "tcgen05" and qkv.dtype == torch.bfloat16 and hd in (64, 128) and causal:
+        return _C.attn_bwd(do.contiguous(), qkv.contiguous(), o, lse, B, S, H, KVH, hd, float(scale))
+    if ATTN_IMPL == "sdpa":
+        with torch.enable_grad():
+            leaf = qkv.detach().requires_grad_(True)
+            out = _sdpa_fwd(leaf, B, S, H, KVH, hd, scale)
+            (g,) = torch.autograd.grad(out, leaf, do)
+        return g
+    return torch_kernels.attn_bwd(do, qkv, o, lse, B, S, H, KVH, hd, scale, causal)
+
+
+# ---------------------------------------------------------------------------------------- SwiGLU
+def swiglu_fwd(gu):
+    if gu.dtype != torch.bfloat16 or (gu.shape[-1] // 2) % 8:
+        return torch_kernels.swiglu_fwd(gu)
+    return _C.swiglu_fwd(gu.contiguous())
+
+
+def swiglu_bwd(ds, gu):
+    if gu.dtype != torch.bfloat16 or (gu.shape[-1] // 2) % 8:
+        return torch_kernels.swiglu_bwd(ds, gu)
+    return _C.swiglu_bwd(ds.contiguous(), gu.contiguous())
+
+
+# ------------------------------------------------------------------------------------- embedding
+def embedding_fwd(tokens, w):
+    if w.dtype != torch.bfloat16 or w.shape[1] % 8:
+        return torch_kernels.embedding_fwd(tokens, w)
+    return _C.embedding_fwd(tokens.contiguous(), w)
+
+
+def embedding_bwd(dx, tokens, out, accumulate=False):
+    if dx.dtype != torch.bfloat16 or dx.shape[-1] % 2 or out.dtype not in (torch.bfloat16, torch.float32):
+        return torch_kernels.embedding_bwd(dx, tokens, out, accumulate)
+    if not accumulate:
+        out.zero_()
+    _C.embedding_bwd(dx.contiguous(), tokens.contiguous(), out)
+    return out
+
+
+# ---------------------------------------------------------------------------- fused linear + CE
+def linear_ce_fwd_bwd(h, w, labels, dw_out, ignore_index=-100, chunk_rows=4096, accumulate=False):
+    M, D = h.shape
+    V = w.shape[0]
+    if h.dtype != torch.bfloat16 or V % 8 or D % 8 or M % 8:
+        return torch_kernels.linear_ce_fwd_bwd(h, w, labels, dw_out, ignore_index, chunk_rows, accumulate)
+    labels = labels.reshape(-1)
+    if labels.dtype != torch.long:
+        labels = labels.long()
+    n_valid = torch.zeros((), dtype=torch.float32, device=h.device)
+    loss_sum = torch.zeros((), dtype=torch.float32, device=h.device)
+    _C.count_valid(labels, ignore_index, n_valid)
+    dh = torch.empty_like(h)
+    chunk_rows = min(chunk_rows, M)
+    logits = torch.empty(chunk_rows, V, dtype=torch.bfloat16, device=h.device)
+    first = not accumulate
+    for s in range(0, M, chunk_rows):
+        e = min(M, s + chunk_rows)
+        lg = logits[: e - s]
+        gemm(h[s:e], w, "nt", out=lg)
+        _C.ce_grad_inplace(lg, labels[s:e], n_valid, loss_sum, ignore_index)   # lg <- (softmax - onehot)/n
+        gemm(lg, w, "nn", out=dh[s:e])
+        gemm(lg, h[s:e], "tn", out=dw_out, accumulate=not first)
+        first = False
+    return loss_sum / n_valid.clamp(min=1.0), dh
+
+
+def cross_entropy_fwd_bwd(logits, labels, ignore_index=-100):
+    V = logits.shape[-1]
+    if logits.dtype != torch.bfloat16 or V % 8:
+        return torch_kernels.cross_entropy_fwd_bwd(logits, labels, ignore_index)
+    labels = labels.reshape(-1).long()
+    n_valid = torch.zeros((), dtype=torch.float32, device=logits.device)
+    loss_sum = torch.zeros((), dtype=torch.float32, device=logits.device)
+    _C.count_valid(labels, ignore_index, n_valid)
+    g = logits.clone()
+    _C.ce_grad_inplace(g, labels, n_valid, loss_sum, ignore_index)
+    return loss_sum / n_valid.clamp(min=1.0), g
+
+
+# ------------------------------------------------------------------------------------- optimizer
+def sumsq(x, out=None):
+    if out is None:
+        out = torch.zeros((), dtype=torch.float32, device=x.device)
+    if x.dtype not in (torch.bfloat16, torch.float32) or x.numel() % 4 or not x.is_contiguous():
+        return torch_kernels.sumsq(x, out)
+    _C.sumsq(x, out)
+    return out
+
+
+def adamw_step(master, grad, exp_avg, exp_avg_sq, lowp_out, lr, beta1, beta2, eps, weight_decay, step,
+               grad_scale=None):
+    ok = (master.numel() % 4 == 0 and grad.dtype in (torch.bfloat16, torch.float32)
+          and (lowp_out is None or lowp_out.dtype == torch.bfloat16))
+    if not ok:
+        return torch_kernels.adamw_step(master, grad, exp_avg, exp_avg_sq, lowp_out, lr, beta1, beta2, eps,
+                                        weight_decay, step, grad_scale)
+    if grad_scale is not None and grad_scale.dtype != torch.float32:
+        grad_scale = grad_scale.float()
+    _C.adamw(master, grad, exp_avg, exp_avg_sq, lowp_out, lr, beta1, beta2, eps, weight_decay, step, grad_scale)
+    return master
+
+
+# ----------------------------------------------------------------------------------------- mamba
+def causal_conv1d_fwd(x, w, b, seq_len, activation=True):
+    if x.dtype != torch.bfloat16 or x.shape[1] % 8 or w.shape[1] > 4:
+        return torch_kernels.causal_conv1d_fwd(x, w, b, seq_len, activation)
+    return _C.causal_conv1d_fwd(x.contiguous(), _bf16c(w), None if b is None else _bf16c(b), seq_len, activation)
+
+
+def causal_conv1d_bwd(dy, x, w, b, seq_len, activation=True):
+    if x.dtype != torch.bfloat16 or x.shape[1] % 8 or w.shape[1] > 4:
+        return torch_kernels.causal_conv1d_bwd(dy, x, w, b, seq_len, activation)
+    dx, dw, db = _C.causal_conv1d_bwd(dy.contiguous(), x.contiguous(), _bf16c(w), None if b is None else _bf16c(b),
+                                      seq_len, activation)
+    return dx, dw, (None if b is None else db)
+
+
+ssd_scan_fwd = torch_kernels.ssd_scan_fwd
+selective_scan_fwd = torch_kernels.selective_scan_fwd

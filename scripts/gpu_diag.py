@@ -1,0 +1,213 @@
+"""On-box diagnostic: numerics + timing of every sm_100a kernel against the ATen oracle.
+Writes gpurun_out/diag.json (one record per check) so a single gpurun call answers many questions.
+Each check is isolated in try/except; a CUDA error aborts the remaining checks of that group only
+when the context is poisoned.
+"""
+import json
+import os
+import sys
+import time
+import traceback
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+os.makedirs(OUT, exist_ok=True)
+records = []
+
+
+def rec(name, **kw):
+    kw["name"] = name
+    records.append(kw)
+    print(json.dumps(kw), flush=True)
+    with open(os.path.join(OUT, "diag.json"), "w") as f:
+        json.dump(records, f, indent=1)
+
+
+def time_ms(fn, iters=10, warmup=3):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+def relerr(a, b):
+    a, b = a.float(), b.float()
+    return ((a - b).abs().max() / b.abs().max().clamp(min=1e-6)).item()
+
+
+def main(groups):
+    from fms_fsdp_b200.ops import torch_kernels as TK
+    from fms_fsdp_b200.ops import cuda_kernels as CK
+    dev = torch.device("cuda")
+    torch.manual_seed(0)
+    rec("env", device=torch.cuda.get_device_name(0), torch=torch.__version__)
+
+    if "gemm" in groups:
+        shapes = [(128, 256, 64), (256, 512, 256), (384, 768, 192), (8, 8, 8), (1000, 520, 72),
+                  (2048, 4096, 4096), (8192, 12288, 4096)]
+        for layout in ("nt", "nn", "tn"):
+            for (M, N, K) in shapes:
+                try:
+                    if layout == "nt":
+                        a = torch.randn(M, K, device=dev).bfloat16(); b = torch.randn(N, K, device=dev).bfloat16()
+                    elif layout == "nn":
+                        a = torch.randn(M, K, device=dev).bfloat16(); b = torch.randn(K, N, device=dev).bfloat16()
+                    else:
+                        a = torch.randn(K, M, device=dev).bfloat16(); b = torch.randn(K, N, device=dev).bfloat16()
+                    ref = TK.gemm(a.float(), b.float(), layout)
+                    out = CK.gemm(a, b, layout)
+                    torch.cuda.synchronize()
+                    e = relerr(out, ref)
+                    r = dict(layout=layout, M=M, N=N, K=K, relerr=e, ok=bool(e < 2e-2))
+                    if M >= 2048:
+                        ms = time_ms(lambda: CK.gemm(a, b, layout))
+                        ms_ref = time_ms(lambda: TK.gemm(a, b, layout))
+                        r.update(ms=ms, tflops=2 * M * N * K / ms / 1e9, cublas_ms=ms_ref,
+                                 cublas_tflops=2 * M * N * K / ms_ref / 1e9)
+                    rec("gemm", **r)
+                except Exception as ex:
+                    rec("gemm", layout=layout, M=M, N=N, K=K, ok=False, error=repr(ex)[:400])
+        # epilogues
+        try:
+            M, N, K = 512, 768, 256
+            a = torch.randn(M, K, device=dev).bfloat16(); b = torch.randn(N, K, device=dev).bfloat16()
+            r_ = torch.randn(M, N, device=dev).bfloat16()
+            ref = a.float() @ b.float().t()
+            out = CK.gemm(a, b, "nt", residual=r_)
+            rec("gemm_residual", relerr=relerr(out, ref + r_.float()))
+            c = torch.randn(M, N, device=dev).bfloat16(); c0 = c.clone()
+            CK.gemm(a, b, "nt", out=c, accumulate=True)
+            rec("gemm_accum_bf16", relerr=relerr(c, ref + c0.float()))
+            c = torch.randn(M, N, device=dev); c0 = c.clone()
+            CK.gemm(a, b, "nt", out=c, accumulate=True)
+            rec("gemm_accum_f32", relerr=relerr(c, ref + c0))
+            c = torch.empty(M, N, device=dev)
+            CK.gemm(a, b, "nt", out=c)
+            rec("gemm_out_f32", relerr=relerr(c, ref))
+        except Exception as ex:
+            rec("gemm_epilogues", ok=False, error=repr(ex)[:400])
+
+    if "elem" in groups:
+        def chk(name, fn):
+            try:
+                fn()
+            except Exception as ex:
+                rec(name, ok=False, error=repr(ex)[:400], tb=traceback.format_exc()[-600:])
+        M, D = 1024, 4096
+
+        def t_rms():
+            x = torch.randn(M, D, device=dev).bfloat16(); w = (1 + 0.1 * torch.randn(D, device=dev)).bfloat16()
+            dy = torch.randn(M, D, device=dev).bfloat16()
+            y0, r0 = TK.rmsnorm_fwd(x, w, 1e-5); y1, r1 = CK.rmsnorm_fwd(x, w, 1e-5)
+            dx0, dw0 = TK.rmsnorm_bwd(dy, x, w, r0); dx1, dw1 = CK.rmsnorm_bwd(dy, x, w, r1)
+            xb = torch.randn(8192, 4096, device=dev).bfloat16()
+            ms = time_ms(lambda: CK.rmsnorm_fwd(xb, w, 1e-5))
+            rec("rmsnorm", y=relerr(y1, y0), rstd=relerr(r1, r0), dx=relerr(dx1, dx0), dw=relerr(dw1, dw0),
+                fwd_ms_8192x4096=ms, fwd_gbs=2 * xb.numel() * 2 / ms / 1e6)
+        chk("rmsnorm", t_rms)
+
+        def t_rope():
+            S, H, KVH, hd = 256, 8, 4, 128
+            tab = TK.rope_table(S, hd, device=dev)
+            q = torch.randn(2 * S, (H + 2 * KVH) * hd, device=dev).bfloat16()
+            a = TK.rope_(q.clone(), tab, S, H, KVH, hd); b = CK.rope_(q.clone(), tab, S, H, KVH, hd)
+            ai = TK.rope_(a.clone(), tab, S, H, KVH, hd, inverse=True); bi = CK.rope_(b.clone(), tab, S, H, KVH, hd, inverse=True)
+            rec("rope", fwd=relerr(b, a), inv=relerr(bi, ai), roundtrip=relerr(bi, q))
+            tab2 = TK.rope_table(S, 64, device=dev)
+            a = TK.rope_(q.clone(), tab2, S, H, KVH, hd, 64); b = CK.rope_(q.clone(), tab2, S, H, KVH, hd, 64)
+            rec("rope_partial", fwd=relerr(b, a))
+        chk("rope", t_rope)
+
+        def t_swiglu():
+            gu = torch.randn(M, 2 * 11008, device=dev).bfloat16(); ds = torch.randn(M, 11008, device=dev).bfloat16()
+            rec("swiglu", fwd=relerr(CK.swiglu_fwd(gu), TK.swiglu_fwd(gu)), bwd=relerr(CK.swiglu_bwd(ds, gu), TK.swiglu_bwd(ds, gu)))
+        chk("swiglu", t_swiglu)
+
+        def t_emb():
+            V = 32000
+            w = torch.randn(V, D, device=dev).bfloat16(); tok = torch.randint(0, V, (M,), device=dev, dtype=torch.int32)
+            dx = torch.randn(M, D, device=dev).bfloat16()
+            o0 = TK.embedding_fwd(tok, w); o1 = CK.embedding_fwd(tok, w)
+            g0 = TK.embedding_bwd(dx, tok, torch.empty(V, D, device=dev)); g1 = CK.embedding_bwd(dx, tok, torch.empty(V, D, device=dev))
+            g2 = CK.embedding_bwd(dx, tok.long(), torch.empty(V, D, device=dev, dtype=torch.bfloat16))
+            rec("embedding", fwd=relerr(o1, o0), bwd_f32=relerr(g1, g0), bwd_bf16=relerr(g2, g0))
+        chk("embedding", t_emb)
+
+        def t_ce():
+            V, Dm, Mm = 32000, 1024, 2048
+            h = (0.5 * torch.randn(Mm, Dm, device=dev)).bfloat16(); w = (0.05 * torch.randn(V, Dm, device=dev)).bfloat16()
+            lab = torch.randint(0, V, (Mm,), device=dev); lab[::7] = -100
+            dw0 = torch.zeros(V, Dm, device=dev); dw1 = torch.zeros(V, Dm, device=dev, dtype=torch.bfloat16)
+            l0, dh0 = TK.linear_ce_fwd_bwd(h.float(), w.float(), lab, dw0)
+            l1, dh1 = CK.linear_ce_fwd_bwd(h, w, lab, dw1, chunk_rows=512)
+            rec("linear_ce", loss_ref=l0.item(), loss=l1.item(), dh=relerr(dh1, dh0), dw=relerr(dw1, dw0))
+        chk("linear_ce", t_ce)
+
+        def t_adam():
+            n = 1 << 20
+            p = torch.randn(n, device=dev); g = torch.randn(n, device=dev).bfloat16()
+            m = torch.zeros(n, device=dev); v = torch.zeros(n, device=dev)
+            p2, m2, v2 = p.clone(), m.clone(), v.clone(); lp = torch.empty(n, device=dev, dtype=torch.bfloat16); lp2 = lp.clone()
+            sc = torch.tensor(0.5, device=dev)
+            for step in (1, 2, 3):
+                TK.adamw_step(p, g, m, v, lp, 1e-3, 0.9, 0.95, 1e-8, 0.1, step, sc)
+                CK.adamw_step(p2, g, m2, v2, lp2, 1e-3, 0.9, 0.95, 1e-8, 0.1, step, sc)
+            s0 = TK.sumsq(g); s1 = CK.sumsq(g)
+            rec("adamw", p=relerr(p2, p), m=relerr(m2, m), v=relerr(v2, v), lowp=relerr(lp2, lp), sumsq=abs(s1.item() - s0.item()) / s0.item())
+        chk("adamw", t_adam)
+
+        def t_conv():
+            S, C = 256, 1024
+            x = torch.randn(2 * S, C, device=dev).bfloat16(); w = (0.5 * torch.randn(C, 4, device=dev)).bfloat16()
+            b = (0.1 * torch.randn(C, device=dev)).bfloat16(); dy = torch.randn(2 * S, C, device=dev).bfloat16()
+            y0 = TK.causal_conv1d_fwd(x, w, b, S); y1 = CK.causal_conv1d_fwd(x, w, b, S)
+            g0 = TK.causal_conv1d_bwd(dy, x, w, b, S); g1 = CK.causal_conv1d_bwd(dy, x, w, b, S)
+            rec("conv1d", fwd=relerr(y1, y0), dx=relerr(g1[0], g0[0]), dw=relerr(g1[1], g0[1]), db=relerr(g1[2], g0[2]))
+        chk("conv1d", t_conv)
+
+    if "attn" in groups:
+        for (B, S, H, KVH, hd) in [(1, 128, 1, 1, 128), (2, 256, 4, 2, 128), (1, 512, 2, 2, 64), (2, 4096, 32, 32, 128)]:
+            try:
+                qkv = torch.randn(B * S, (H + 2 * KVH) * hd, device=dev).bfloat16()
+                do = torch.randn(B * S, H * hd, device=dev).bfloat16()
+                sc = hd ** -0.5
+                r = dict(B=B, S=S, H=H, KVH=KVH, hd=hd)
+                o1, l1 = CK.attn_fwd(qkv, B, S, H, KVH, hd, sc)
+                torch.cuda.synchronize()
+                if S <= 1024:
+                    o0, l0 = TK.attn_fwd(qkv, B, S, H, KVH, hd, sc)
+                    r.update(o=relerr(o1, o0), lse=relerr(l1, l0))
+                    g1 = CK.attn_bwd(do, qkv, o1, l1, B, S, H, KVH, hd, sc)
+                    g0 = TK.attn_bwd(do, qkv, o0, l0, B, S, H, KVH, hd, sc)
+                    r.update(dqkv=relerr(g1, g0))
+                else:
+                    o0 = CK._sdpa_fwd(qkv, B, S, H, KVH, hd, sc)
+                    r.update(o_vs_sdpa=relerr(o1, o0))
+                    fl = 4 * B * H * S * S * hd / 2
+                    ms = time_ms(lambda: CK.attn_fwd(qkv, B, S, H, KVH, hd, sc))
+                    ms0 = time_ms(lambda: CK._sdpa_fwd(qkv, B, S, H, KVH, hd, sc))
+                    r.update(fwd_ms=ms, fwd_tflops=fl / ms / 1e9, sdpa_fwd_ms=ms0, sdpa_fwd_tflops=fl / ms0 / 1e9)
+                    ms = time_ms(lambda: CK.attn_bwd(do, qkv, o1, l1, B, S, H, KVH, hd, sc))
+                    r.update(bwd_ms=ms, bwd_tflops=2.5 * fl / ms / 1e9)
+                rec("attn", **r)
+            except Exception as ex:
+                rec("attn", B=B, S=S, H=H, KVH=KVH, hd=hd, ok=False, error=repr(ex)[:500])
+
+    rec("done", launches=CK.launch_count())
+
+
+if __name__ == "__main__":
+    g = sys.argv[1:] or ["gemm", "elem"]
+    try:
+        main(g)
+    except Exception as ex:
+        rec("fatal", error=repr(ex)[:500], tb=traceback.format_exc()[-1500:])
+        raise
