@@ -1,5 +1,664 @@
-// placeholder so the extension links; replaced by the tcgen05 flash-attention kernels
-#include <cuda_runtime.h>
-extern "C" int b200_attn_fwd(const void*, void*, float*, int, int, int, int, int, float, cudaStream_t) { return -100; }
-extern "C" int b200_attn_bwd(const void*, const void*, const void*, const float*, void*, float*, int, int, int, int, int,
-                             float, cudaStream_t) { return -100; }
+// Causal GQA flash attention for sm_100a on tcgen05 tensor cores.
+//
+// Input is the fused, already-roped projection qkv [B*S, (H+2*KVH)*HD] (bf16); one 2-D TMA map with a
+// {64 x 128|64}-element box serves Q, K and V.  All GEMMs run as tcgen05.mma with fp32 accumulators in
+// TMEM; softmax / dS math runs in "row-owner" threads (thread t <-> TMEM lane t, so row reductions need
+// no shuffles) that read S with tcgen05.ld and hand P / dS back to the tensor core through
+// 128B-swizzled shared memory.
+//
+//  forward   CTA = (q tile of 128, head, batch).  S_j = Q K_j^T (double-buffered in TMEM so QK_{j+1}
+//            overlaps softmax_j), online softmax with lazy rescale (O is only rescaled when the row max
+//            grows by > 2^8), O += P_j V_j with V consumed as an MN-major operand.
+//  backward  two kernels with one skeleton (templated):  MODE_DKDV: CTA = (kv tile 128, kv head, batch),
+//            streams (Q_i, dO_i) tiles of 64 rows, computes S^T = K Q^T and dP^T = V dO^T, accumulates
+//            dV += P^T dO and dK += dS^T Q in TMEM (GQA group summed in the accumulator, no atomics);
+//            MODE_DQ: CTA = (q tile 128, head, batch), streams (K_j, V_j) tiles of 64, dQ += dS K.
+//            The score GEMMs are recomputed in both kernels (7 GEMMs instead of 5) in exchange for a
+//            deterministic, atomic-free dQ.
+//
+// Warp roles (192 threads): warp 0 TMA producer, warp 1 MMA issuer / TMEM owner, warps 2-5 row owners.
+#include "common.cuh"
+#include "tensormap.h"
+
+namespace b200 {
+
+constexpr int ATT_THREADS = 192;
+constexpr float LOG2E = 1.4426950408889634f;
+constexpr float LN2 = 0.6931471805599453f;
+
+B200_DEVINL void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// Write 8 consecutive bf16 (16 B) of row `row`, 16-byte chunk index `chunk16` (0..7) into a K-major
+// SWIZZLE_128B tile whose rows are 128 B.
+B200_DEVINL void st_swz128(uint8_t* tile, int row, int chunk16, uint4 v) {
+  *reinterpret_cast<uint4*>(tile + row * 128 + ((chunk16 ^ (row & 7)) << 4)) = v;
+}
+
+// ============================================================================================ forward
+template <int HD>
+struct FwdCfg {
+  static constexpr int NCH = HD / 64;              // 64-column chunks of the head dim
+  static constexpr int TILE_BYTES = 128 * HD * 2;  // a 128-row Q/K/V tile
+  static constexpr int KV_STAGES = 2;
+  static constexpr int P_BYTES = 128 * 128 * 2;
+  static constexpr int SMEM = TILE_BYTES * (1 + 2 * KV_STAGES) + P_BYTES + 1024 + 256;
+};
+
+template <int HD>
+__global__ void __launch_bounds__(ATT_THREADS, 1)
+attn_fwd_kernel(const __grid_constant__ CUtensorMap tm, __nv_bfloat16* __restrict__ o, float* __restrict__ lse,
+                int S, int H, int KVH, float scale_log2, int n_qt) {
+  using C = FwdCfg<HD>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + C::TILE_BYTES;
+  uint8_t* sV = sK + C::KV_STAGES * C::TILE_BYTES;
+  uint8_t* sP = sV + C::KV_STAGES * C::TILE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + C::P_BYTES);
+  uint64_t* q_full = bars;
+  uint64_t* k_full = bars + 1;      // [2]
+  uint64_t* k_empty = bars + 3;     // [2]
+  uint64_t* v_full = bars + 5;      // [2]
+  uint64_t* v_empty = bars + 7;     // [2]
+  uint64_t* s_full = bars + 9;      // [2]
+  uint64_t* p_full = bars + 11;
+  uint64_t* pv_done = bars + 12;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // heavy (late) q tiles first
+  const int qt = n_qt - 1 - blockIdx.x;
+  const int h = blockIdx.y, b = blockIdx.z;
+  const int kvh = h / (H / KVH);
+  const int n_kv = qt + 1;  // causal: kv tiles 0..qt
+  const int row0 = b * S + qt * 128;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm);
+    mbar_init(q_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1);
+      mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1);
+      mbar_init(&s_full[i], 1);
+    }
+    mbar_init(p_full, 4);
+    mbar_init(pv_done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t tmem_S[2] = {tmem, tmem + 128};
+  const uint32_t tmem_O = tmem + 256;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(q_full, C::TILE_BYTES);
+      for (int c = 0; c < C::NCH; ++c) tma_load_2d(sQ + c * 16384, &tm, q_full, h * HD + 64 * c, row0);
+      for (int j = 0; j < n_kv; ++j) {
+        const int st = j & 1;
+        const uint32_t ph = (j >> 1) & 1;
+        const int krow = b * S + j * 128;
+        mbar_wait(&k_empty[st], ph ^ 1);
+        mbar_arrive_expect_tx(&k_full[st], C::TILE_BYTES);
+        for (int c = 0; c < C::NCH; ++c)
+          tma_load_2d(sK + st * C::TILE_BYTES + c * 16384, &tm, &k_full[st], (H + kvh) * HD + 64 * c, krow);
+        mbar_wait(&v_empty[st], ph ^ 1);
+        mbar_arrive_expect_tx(&v_full[st], C::TILE_BYTES);
+        for (int c = 0; c < C::NCH; ++c)
+          tma_load_2d(sV + st * C::TILE_BYTES + c * 16384, &tm, &v_full[st], (H + KVH + kvh) * HD + 64 * c, krow);
+      }
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t idesc_qk = make_idesc_bf16(128, 128, false, false);
+    constexpr uint32_t idesc_pv = make_idesc_bf16(128, HD, false, true);
+    auto issue_qk = [&](int j) {
+      const int st = j & 1;
+      mbar_wait(&k_full[st], (j >> 1) & 1);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t qa = smem_u32(sQ), ka = smem_u32(sK + st * C::TILE_BYTES);
+#pragma unroll
+        for (int kk = 0; kk < HD / 16; ++kk) {
+          const uint32_t off = (kk >> 2) * 16384 + (kk & 3) * 32;
+          umma_bf16_ss(tmem_S[j & 1], make_smem_desc(qa + off, 0, 1024), make_smem_desc(ka + off, 0, 1024), idesc_qk,
+                       kk != 0);
+        }
+        umma_commit(&k_empty[st]);
+        umma_commit(&s_full[j & 1]);
+      }
+      __syncwarp();
+    };
+    mbar_wait(q_full, 0);
+    issue_qk(0);
+    for (int j = 0; j < n_kv; ++j) {
+      if (j + 1 < n_kv) issue_qk(j + 1);
+      const int st = j & 1;
+      mbar_wait(p_full, j & 1);
+      mbar_wait(&v_full[st], (j >> 1) & 1);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t pa = smem_u32(sP), va = smem_u32(sV + st * C::TILE_BYTES);
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {  // 16 kv rows per step
+          const uint32_t poff = (t >> 2) * 16384 + (t & 3) * 32;
+          umma_bf16_ss(tmem_O, make_smem_desc(pa + poff, 0, 1024), make_smem_desc(va + t * 2048, 16384, 1024),
+                       idesc_pv, (j | t) != 0);
+        }
+        umma_commit(&v_empty[st]);
+        umma_commit(pv_done);
+      }
+      __syncwarp();
+    }
+  } else {
+    // ------------------------------------------------ row owners: online softmax, O rescale, epilogue
+    const int q4 = warp & 3;
+    const int r = q4 * 32 + lane;         // row within the q tile == TMEM lane
+    const int q_idx = qt * 128 + r;       // position in the sequence
+    const uint32_t lane_addr = static_cast<uint32_t>(q4 * 32) << 16;
+    float m_ref = -INFINITY, l_sum = 0.f;
+    for (int j = 0; j < n_kv; ++j) {
+      mbar_wait(&s_full[j & 1], (j >> 1) & 1);
+      tc_fence_after();
+      const uint32_t ts = tmem_S[j & 1] + lane_addr;
+      const bool diag = (j == qt);
+      const int kv0 = j * 128;
+      // pass 1: row max (scaled log2 domain)
+      float mx = -INFINITY;
+#pragma unroll 1
+      for (int c = 0; c < 128; c += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(ts + c, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          float x = __uint_as_float(v[i]) * scale_log2;
+          const int kv = kv0 + c + i;
+          if ((diag && kv > q_idx) || kv >= S) x = -INFINITY;
+          mx = fmaxf(mx, x);
+        }
+      }
+      const float m_new = fmaxf(m_ref, mx);
+      // P buffer and O are free only once PV_{j-1} has retired
+      if (j > 0) mbar_wait(pv_done, (j - 1) & 1);
+      tc_fence_after();
+      const bool grow = (m_new - m_ref) > 8.f;  // lazy rescale threshold (values stay < 2^8 above the reference)
+      if (j == 0) {
+        m_ref = m_new;
+      } else if (__any_sync(0xffffffffu, grow)) {
+        const float f = exp2f(m_ref - m_new);
+        l_sum *= f;
+        m_ref = m_new;
+#pragma unroll 1
+        for (int c = 0; c < HD; c += 32) {
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(tmem_O + lane_addr + c, v);
+          tmem_ld_wait();
+          uint32_t w0[16], w1[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            w0[i] = __float_as_uint(__uint_as_float(v[i]) * f);
+            w1[i] = __float_as_uint(__uint_as_float(v[16 + i]) * f);
+          }
+          tmem_st_32x32b_x16(tmem_O + lane_addr + c, w0);
+          tmem_st_32x32b_x16(tmem_O + lane_addr + c + 16, w1);
+        }
+        tmem_st_wait();
+      }
+      // pass 2: p = 2^(x - m_ref) -> bf16 -> swizzled smem (A operand of the PV GEMM)
+#pragma unroll 1
+      for (int c = 0; c < 128; c += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(ts + c, v);
+        tmem_ld_wait();
+        float p[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          float x = __uint_as_float(v[i]) * scale_log2;
+          const int kv = kv0 + c + i;
+          if ((diag && kv > q_idx) || kv >= S) x = -INFINITY;
+          p[i] = exp2f(x - m_ref);
+          l_sum += p[i];
+        }
+        uint8_t* tile = sP + (c >> 6) * 16384;
+        const int cb = (c & 63) >> 3;  // first 16-byte chunk of this group within the 128 B row
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint4 u;
+          u.x = pack_bf16x2(p[g * 8 + 0], p[g * 8 + 1]); u.y = pack_bf16x2(p[g * 8 + 2], p[g * 8 + 3]);
+          u.z = pack_bf16x2(p[g * 8 + 4], p[g * 8 + 5]); u.w = pack_bf16x2(p[g * 8 + 6], p[g * 8 + 7]);
+          st_swz128(tile, r, cb + g, u);
+        }
+      }
+      fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_full);
+    }
+    // epilogue: O / l -> bf16 ; lse
+    mbar_wait(pv_done, (n_kv - 1) & 1);
+    tc_fence_after();
+    const float inv_l = 1.f / l_sum;
+    if (q_idx < S) {
+      __nv_bfloat16* orow = o + (static_cast<size_t>(b) * S + q_idx) * (H * HD) + h * HD;
+#pragma unroll 1
+      for (int c = 0; c < HD; c += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(tmem_O + lane_addr + c, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint4 u;
+          u.x = pack_bf16x2(__uint_as_float(v[g * 8 + 0]) * inv_l, __uint_as_float(v[g * 8 + 1]) * inv_l);
+          u.y = pack_bf16x2(__uint_as_float(v[g * 8 + 2]) * inv_l, __uint_as_float(v[g * 8 + 3]) * inv_l);
+          u.z = pack_bf16x2(__uint_as_float(v[g * 8 + 4]) * inv_l, __uint_as_float(v[g * 8 + 5]) * inv_l);
+          u.w = pack_bf16x2(__uint_as_float(v[g * 8 + 6]) * inv_l, __uint_as_float(v[g * 8 + 7]) * inv_l);
+          *reinterpret_cast<uint4*>(orow + c + g * 8) = u;
+        }
+      }
+      lse[(static_cast<size_t>(b) * H + h) * S + q_idx] = (m_ref + log2f(l_sum)) * LN2;
+    } else {
+      // still drain TMEM reads are not required; nothing to store
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
+// ===================================================================================== backward prep
+// delta[b,h,s] = sum_d dO[b,s,h,d] * O[b,s,h,d]      (one warp per (row, head))
+__global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16* __restrict__ o,
+                                  float* __restrict__ delta, int B, int S, int H, int HD) {
+  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (gw >= B * S * H) return;
+  const int h = gw % H;
+  const size_t bs = gw / H;
+  const __nv_bfloat16* a = dout + (bs * H + h) * HD;
+  const __nv_bfloat16* c = o + (bs * H + h) * HD;
+  float s = 0.f;
+  for (int d = lane * 2; d < HD; d += 64) {
+    float2 x = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(a + d));
+    float2 y = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(c + d));
+    s += x.x * y.x + x.y * y.y;
+  }
+  s = warp_sum(s);
+  if (lane == 0) {
+    const int b = (int)(bs / S), sq = (int)(bs % S);
+    delta[((size_t)b * H + h) * S + sq] = s;
+  }
+}
+
+// ============================================================================================ backward
+// Skeleton shared by both kernels:
+//   resident pair (X1, X2): 128 rows x HD        streamed pair (Y1, Y2): 64 rows x HD, 2 stages
+//   T1 = X1 Y1^T, T2 = X2 Y2^T   (128 x 64 fp32 in TMEM, double buffered)
+//   row owners turn (T1, T2) into bf16 tiles W1 (and W2) of shape [128 x 64] in smem
+//   DKDV: X=(K_j, V_j), Y=(Q_i, dO_i): W1 = P^T, W2 = dS^T; acc1(dV) += W1 Y2, acc2(dK) += W2 Y1
+//   DQ  : X=(Q_i, dO_i), Y=(K_j, V_j): W2 = dS;             acc2(dQ) += W2 Y1
+enum { MODE_DKDV = 0, MODE_DQ = 1 };
+
+template <int HD>
+struct BwdCfg {
+  static constexpr int NCH = HD / 64;
+  static constexpr int X_BYTES = 128 * HD * 2;   // one resident operand
+  static constexpr int Y_BYTES = 64 * HD * 2;    // one streamed operand
+  static constexpr int Y_CHUNK = 64 * 128;       // bytes of one 64-row x 64-col chunk
+  static constexpr int W_BYTES = 128 * 64 * 2;
+  static constexpr int STAGES = 2;
+  static constexpr int SMEM = 2 * X_BYTES + STAGES * 2 * Y_BYTES + 2 * W_BYTES + 64 * 2 * 4 * 2 + 1024 + 256;
+};
+
+template <int HD, int MODE>
+__global__ void __launch_bounds__(ATT_THREADS, 1)
+attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv128, const __grid_constant__ CUtensorMap tm_qkv64,
+                const __grid_constant__ CUtensorMap tm_do128, const __grid_constant__ CUtensorMap tm_do64,
+                const float* __restrict__ lse, const float* __restrict__ delta, __nv_bfloat16* __restrict__ dqkv,
+                int S, int H, int KVH, float scale, int n_t128) {
+  using C = BwdCfg<HD>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sX1 = smem;
+  uint8_t* sX2 = sX1 + C::X_BYTES;
+  uint8_t* sY = sX2 + C::X_BYTES;                       // [stage][Y1 | Y2]
+  uint8_t* sW1 = sY + C::STAGES * 2 * C::Y_BYTES;
+  uint8_t* sW2 = sW1 + C::W_BYTES;
+  float* sStat = reinterpret_cast<float*>(sW2 + C::W_BYTES);  // [2 buffers][lse2 64 | delta 64]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sStat) + 64 * 2 * 4 * 2);
+  uint64_t* x_full = bars;
+  uint64_t* y_full = bars + 1;     // [2]
+  uint64_t* y_empty = bars + 3;    // [2]
+  uint64_t* t_full = bars + 5;     // [2]
+  uint64_t* w_full = bars + 7;
+  uint64_t* acc_done = bars + 8;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int G = H / KVH;
+  const int b = blockIdx.z;
+  const float scale_log2 = scale * LOG2E;
+
+  // iteration space of the streamed (64-row) tiles
+  int t128, head_lo, head_n, kvh;
+  if constexpr (MODE == MODE_DKDV) {
+    t128 = blockIdx.x;                 // kv tile; small index = most work, scheduled first
+    kvh = blockIdx.y;
+    head_lo = kvh * G;
+    head_n = G;
+  } else {
+    t128 = n_t128 - 1 - blockIdx.x;    // q tile; large index = most work
+    head_lo = blockIdx.y;
+    head_n = 1;
+    kvh = blockIdx.y / G;
+  }
+  const int n64 = (S + 63) / 64;
+  // DKDV: q tiles i64 in [2*t128, n64) ; DQ: kv tiles j64 in [0, 2*t128+2) clipped
+  const int s_lo = (MODE == MODE_DKDV) ? 2 * t128 : 0;
+  const int s_hi = (MODE == MODE_DKDV) ? n64 : min(n64, 2 * t128 + 2);
+  const int per_head = s_hi - s_lo;
+  const int n_iter = per_head * head_n;
+  const int xrow0 = b * S + t128 * 128;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_qkv128); tma_prefetch_desc(&tm_qkv64);
+    tma_prefetch_desc(&tm_do128); tma_prefetch_desc(&tm_do64);
+    mbar_init(x_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&y_full[i], 1); mbar_init(&y_empty[i], 1); mbar_init(&t_full[i], 1);
+    }
+    mbar_init(w_full, 4);
+    mbar_init(acc_done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  // TMEM columns: T1[0] 0..63, T2[0] 64..127, T1[1] 128..191, T2[1] 192..255, acc1 256.., acc2 384..
+  const uint32_t tmem_acc1 = tmem + 256, tmem_acc2 = tmem + 384;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // resident operands.  DKDV: per-CTA constant (K_j, V_j).  DQ: (Q_i, dO_i) of this head.
+      if constexpr (MODE == MODE_DKDV) {
+        mbar_arrive_expect_tx(x_full, 2 * C::X_BYTES);
+        for (int c = 0; c < C::NCH; ++c) {
+          tma_load_2d(sX1 + c * 16384, &tm_qkv128, x_full, (H + kvh) * HD + 64 * c, xrow0);
+          tma_load_2d(sX2 + c * 16384, &tm_qkv128, x_full, (H + KVH + kvh) * HD + 64 * c, xrow0);
+        }
+      } else {
+        mbar_arrive_expect_tx(x_full, 2 * C::X_BYTES);
+        for (int c = 0; c < C::NCH; ++c) {
+          tma_load_2d(sX1 + c * 16384, &tm_qkv128, x_full, head_lo * HD + 64 * c, xrow0);
+          tma_load_2d(sX2 + c * 16384, &tm_do128, x_full, head_lo * HD + 64 * c, xrow0);
+        }
+      }
+      for (int it = 0; it < n_iter; ++it) {
+        const int st = it & 1;
+        const uint32_t ph = (it >> 1) & 1;
+        const int hh = head_lo + it / per_head;
+        const int t64 = s_lo + it % per_head;
+        const int yrow = b * S + t64 * 64;
+        uint8_t* y1 = sY + st * 2 * C::Y_BYTES;
+        uint8_t* y2 = y1 + C::Y_BYTES;
+        mbar_wait(&y_empty[st], ph ^ 1);
+        mbar_arrive_expect_tx(&y_full[st], 2 * C::Y_BYTES);
+        for (int c = 0; c < C::NCH; ++c) {
+          if constexpr (MODE == MODE_DKDV) {
+            tma_load_2d(y1 + c * C::Y_CHUNK, &tm_qkv64, &y_full[st], hh * HD + 64 * c, yrow);   // Q_i
+            tma_load_2d(y2 + c * C::Y_CHUNK, &tm_do64, &y_full[st], hh * HD + 64 * c, yrow);    // dO_i
+          } else {
+            tma_load_2d(y1 + c * C::Y_CHUNK, &tm_qkv64, &y_full[st], (H + kvh) * HD + 64 * c, yrow);        // K_j
+            tma_load_2d(y2 + c * C::Y_CHUNK, &tm_qkv64, &y_full[st], (H + KVH + kvh) * HD + 64 * c, yrow);  // V_j
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t idesc_t = make_idesc_bf16(128, 64, false, false);   // scores: both K-major over HD
+    constexpr uint32_t idesc_a = make_idesc_bf16(128, HD, false, true);    // accumulate: A K-major, B MN-major
+    auto issue_scores = [&](int it) {
+      const int st = it & 1;
+      mbar_wait(&y_full[st], (it >> 1) & 1);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t x1 = smem_u32(sX1), x2 = smem_u32(sX2);
+        const uint32_t y1 = smem_u32(sY + st * 2 * C::Y_BYTES), y2 = y1 + C::Y_BYTES;
+        const uint32_t t1 = tmem + (it & 1) * 128, t2 = t1 + 64;
+#pragma unroll
+        for (int kk = 0; kk < HD / 16; ++kk) {
+          const uint32_t xo = (kk >> 2) * 16384 + (kk & 3) * 32;
+          const uint32_t yo = (kk >> 2) * C::Y_CHUNK + (kk & 3) * 32;
+          umma_bf16_ss(t1, make_smem_desc(x1 + xo, 0, 1024), make_smem_desc(y1 + yo, 0, 1024), idesc_t, kk != 0);
+        }
+#pragma unroll
+        for (int kk = 0; kk < HD / 16; ++kk) {
+          const uint32_t xo = (kk >> 2) * 16384 + (kk & 3) * 32;
+          const uint32_t yo = (kk >> 2) * C::Y_CHUNK + (kk & 3) * 32;
+          umma_bf16_ss(t2, make_smem_desc(x2 + xo, 0, 1024), make_smem_desc(y2 + yo, 0, 1024), idesc_t, kk != 0);
+        }
+        umma_commit(&t_full[it & 1]);
+      }
+      __syncwarp();
+    };
+    mbar_wait(x_full, 0);
+    if (n_iter > 0) issue_scores(0);
+    for (int it = 0; it < n_iter; ++it) {
+      if (it + 1 < n_iter) issue_scores(it + 1);
+      const int st = it & 1;
+      mbar_wait(w_full, it & 1);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t y1 = smem_u32(sY + st * 2 * C::Y_BYTES), y2 = y1 + C::Y_BYTES;
+        const uint32_t w1 = smem_u32(sW1), w2 = smem_u32(sW2);
+        // reduction over the 64 streamed rows: 4 steps of 16; Y as MN-major B: LBO = chunk stride, SBO = 1024
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          if constexpr (MODE == MODE_DKDV) {
+            umma_bf16_ss(tmem_acc1, make_smem_desc(w1 + t * 32, 0, 1024),
+                         make_smem_desc(y2 + t * 2048, C::Y_CHUNK, 1024), idesc_a, (it | t) != 0);   // dV += P^T dO
+          }
+          umma_bf16_ss(tmem_acc2, make_smem_desc(w2 + t * 32, 0, 1024),
+                       make_smem_desc(y1 + t * 2048, C::Y_CHUNK, 1024), idesc_a, (it | t) != 0);     // dK += dS^T Q | dQ += dS K
+        }
+        umma_commit(&y_empty[st]);
+        umma_commit(acc_done);
+      }
+      __syncwarp();
+    }
+  } else {
+    // ------------------------------------------------------------------- row owners
+    const int q4 = warp & 3;
+    const int r = q4 * 32 + lane;
+    const int tid128 = (warp - 2) * 32 + lane;
+    const uint32_t lane_addr = static_cast<uint32_t>(q4 * 32) << 16;
+    const int x_idx = t128 * 128 + r;  // sequence position of this thread's resident row
+    float row_lse2 = 0.f, row_delta = 0.f;
+    for (int it = 0; it < n_iter; ++it) {
+      const int hh = head_lo + it / per_head;
+      const int t64 = s_lo + it % per_head;
+      const int y0 = t64 * 64;
+      float* stat = sStat + (it & 1) * 128;
+      if constexpr (MODE == MODE_DKDV) {
+        // per-column statistics of the streamed q rows
+        const int qi = y0 + (tid128 & 63);
+        const size_t sidx = ((size_t)b * H + hh) * S + min(qi, S - 1);
+        stat[tid128] = (tid128 < 64) ? lse[sidx] * LOG2E : delta[sidx];
+        named_bar_sync(1, 128);
+      } else if (it == 0) {
+        const size_t sidx = ((size_t)b * H + hh) * S + min(x_idx, S - 1);
+        row_lse2 = lse[sidx] * LOG2E;
+        row_delta = delta[sidx];
+      }
+      mbar_wait(&t_full[it & 1], (it >> 1) & 1);
+      tc_fence_after();
+      // W tiles are free once the accumulate GEMMs of the previous iteration retired
+      if (it > 0) mbar_wait(acc_done, (it - 1) & 1);
+      const uint32_t t1 = tmem + (it & 1) * 128 + lane_addr, t2 = t1 + 64;
+#pragma unroll 1
+      for (int c = 0; c < 64; c += 32) {
+        uint32_t a[32], d[32];
+        tmem_ld_32x32b_x32(t1 + c, a);
+        tmem_ld_32x32b_x32(t2 + c, d);
+        tmem_ld_wait();
+        float p[32], ds[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const int y_idx = y0 + c + i;
+          float l2, dl;
+          bool masked;
+          if constexpr (MODE == MODE_DKDV) {
+            l2 = stat[c + i]; dl = stat[64 + c + i];
+            masked = (x_idx > y_idx) || (y_idx >= S) || (x_idx >= S);     // kv > q
+          } else {
+            l2 = row_lse2; dl = row_delta;
+            masked = (y_idx > x_idx) || (y_idx >= S) || (x_idx >= S);
+          }
+          const float pv = masked ? 0.f : exp2f(__uint_as_float(a[i]) * scale_log2 - l2);
+          p[i] = pv;
+          ds[i] = pv * (__uint_as_float(d[i]) - dl) * scale;
+        }
+        const int cb = c >> 3;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint4 u;
+          if constexpr (MODE == MODE_DKDV) {
+            u.x = pack_bf16x2(p[g * 8 + 0], p[g * 8 + 1]); u.y = pack_bf16x2(p[g * 8 + 2], p[g * 8 + 3]);
+            u.z = pack_bf16x2(p[g * 8 + 4], p[g * 8 + 5]); u.w = pack_bf16x2(p[g * 8 + 6], p[g * 8 + 7]);
+            st_swz128(sW1, r, cb + g, u);
+          }
+          u.x = pack_bf16x2(ds[g * 8 + 0], ds[g * 8 + 1]); u.y = pack_bf16x2(ds[g * 8 + 2], ds[g * 8 + 3]);
+          u.z = pack_bf16x2(ds[g * 8 + 4], ds[g * 8 + 5]); u.w = pack_bf16x2(ds[g * 8 + 6], ds[g * 8 + 7]);
+          st_swz128(sW2, r, cb + g, u);
+        }
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(w_full);
+    }
+    // epilogue: accumulators -> bf16 -> dqkv sections
+    if (n_iter > 0) mbar_wait(acc_done, (n_iter - 1) & 1);
+    tc_fence_after();
+    if (x_idx < S) {
+      const size_t row = (size_t)b * S + x_idx;
+      const int W = (H + 2 * KVH) * HD;
+      auto store_acc = [&](uint32_t tacc, int col0) {
+        __nv_bfloat16* dst = dqkv + row * W + col0;
+#pragma unroll 1
+        for (int c = 0; c < HD; c += 32) {
+          uint32_t v[32];
+          if (n_iter > 0) {
+            tmem_ld_32x32b_x32(tacc + lane_addr + c, v);
+            tmem_ld_wait();
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = 0u;
+          }
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            uint4 u;
+            u.x = pack_bf16x2(__uint_as_float(v[g * 8 + 0]), __uint_as_float(v[g * 8 + 1]));
+            u.y = pack_bf16x2(__uint_as_float(v[g * 8 + 2]), __uint_as_float(v[g * 8 + 3]));
+            u.z = pack_bf16x2(__uint_as_float(v[g * 8 + 4]), __uint_as_float(v[g * 8 + 5]));
+            u.w = pack_bf16x2(__uint_as_float(v[g * 8 + 6]), __uint_as_float(v[g * 8 + 7]));
+            *reinterpret_cast<uint4*>(dst + c + g * 8) = u;
+          }
+        }
+      };
+      if constexpr (MODE == MODE_DKDV) {
+        store_acc(tmem_acc2, (H + kvh) * HD);         // dK
+        store_acc(tmem_acc1, (H + KVH + kvh) * HD);   // dV
+      } else {
+        store_acc(tmem_acc2, head_lo * HD);           // dQ
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
+template <int HD>
+static int launch_fwd(const void* qkv, void* o, float* lse, int B, int S, int H, int KVH, float scale,
+                      cudaStream_t st) {
+  using C = FwdCfg<HD>;
+  CUtensorMap tm;
+  const int W = (H + 2 * KVH) * HD;
+  if (make_tmap_2d_bf16(&tm, qkv, (uint64_t)W, (uint64_t)B * S, (uint64_t)W, 64, 128)) return -3;
+  auto kern = attn_fwd_kernel<HD>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
+    if (e != cudaSuccess) return (int)e;
+    configured = true;
+  }
+  const int n_qt = (S + 127) / 128;
+  dim3 grid(n_qt, H, B);
+  kern<<<grid, ATT_THREADS, C::SMEM, st>>>(tm, (__nv_bfloat16*)o, lse, S, H, KVH, scale * LOG2E, n_qt);
+  return (int)cudaGetLastError();
+}
+
+template <int HD>
+static int launch_bwd(const void* dout, const void* qkv, const void* o, const float* lse, void* dqkv, float* delta,
+                      int B, int S, int H, int KVH, float scale, cudaStream_t st) {
+  using C = BwdCfg<HD>;
+  const int W = (H + 2 * KVH) * HD;
+  CUtensorMap q128, q64, d128, d64;
+  if (make_tmap_2d_bf16(&q128, qkv, (uint64_t)W, (uint64_t)B * S, (uint64_t)W, 64, 128)) return -3;
+  if (make_tmap_2d_bf16(&q64, qkv, (uint64_t)W, (uint64_t)B * S, (uint64_t)W, 64, 64)) return -3;
+  if (make_tmap_2d_bf16(&d128, dout, (uint64_t)H * HD, (uint64_t)B * S, (uint64_t)H * HD, 64, 128)) return -3;
+  if (make_tmap_2d_bf16(&d64, dout, (uint64_t)H * HD, (uint64_t)B * S, (uint64_t)H * HD, 64, 64)) return -3;
+  {
+    const long long warps = (long long)B * S * H;
+    const int threads = 256;
+    const long long blocks = (warps * 32 + threads - 1) / threads;
+    attn_delta_kernel<<<(unsigned)blocks, threads, 0, st>>>((const __nv_bfloat16*)dout, (const __nv_bfloat16*)o, delta,
+                                                            B, S, H, HD);
+  }
+  auto k1 = attn_bwd_kernel<HD, MODE_DKDV>;
+  auto k2 = attn_bwd_kernel<HD, MODE_DQ>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
+    if (e != cudaSuccess) return (int)e;
+    configured = true;
+  }
+  const int n_t = (S + 127) / 128;
+  k1<<<dim3(n_t, KVH, B), ATT_THREADS, C::SMEM, st>>>(q128, q64, d128, d64, lse, delta, (__nv_bfloat16*)dqkv, S, H, KVH,
+                                                     scale, n_t);
+  k2<<<dim3(n_t, H, B), ATT_THREADS, C::SMEM, st>>>(q128, q64, d128, d64, lse, delta, (__nv_bfloat16*)dqkv, S, H, KVH,
+                                                   scale, n_t);
+  return (int)cudaGetLastError();
+}
+
+}  // namespace b200
+
+extern "C" int b200_attn_fwd(const void* qkv, void* o, float* lse, int B, int S, int H, int KVH, int HD, float scale,
+                             cudaStream_t st) {
+  if (H % KVH) return -1;
+  if (HD == 128) return b200::launch_fwd<128>(qkv, o, lse, B, S, H, KVH, scale, st);
+  if (HD == 64) return b200::launch_fwd<64>(qkv, o, lse, B, S, H, KVH, scale, st);
+  return -2;
+}
+extern "C" int b200_attn_bwd(const void* dout, const void* qkv, const void* o, const float* lse, void* dqkv,
+                             float* delta, int B, int S, int H, int KVH, int HD, float scale, cudaStream_t st) {
+  if (H % KVH) return -1;
+  if (HD == 128) return b200::launch_bwd<128>(dout, qkv, o, lse, dqkv, delta, B, S, H, KVH, scale, st);
+  if (HD == 64) return b200::launch_bwd<64>(dout, qkv, o, lse, dqkv, delta, B, S, H, KVH, scale, st);
+  return -2;
+}
