@@ -34,8 +34,14 @@ class TorchCollectives:
     def alloc_shard(self, numel: int, dtype: torch.dtype) -> torch.Tensor:
         return torch.zeros(numel, dtype=dtype, device=self.device)
 
-    def alloc_full(self, numel: int, dtype: torch.dtype) -> torch.Tensor:
+    def alloc_full(self, numel: int, dtype: torch.dtype, symmetric: bool = True) -> torch.Tensor:
         return torch.zeros(numel, dtype=dtype, device=self.device)
+
+    def alloc_grad_shard(self, numel: int) -> torch.Tensor:
+        return torch.zeros(numel, dtype=torch.float32, device=self.device)
+
+    def begin_step(self):
+        pass
 
     # ---- parameter path
     def all_gather(self, shard: torch.Tensor, full: torch.Tensor):

@@ -225,7 +225,7 @@ class ShardedModel(nn.Module):
                 u.grad_shard = self.coll.alloc_full(layout.total, self.mp.reduce_dtype)
                 u.full_grad = _Buf(u.grad_shard, self._event())
         else:
-            u.grad_shard = torch.zeros(n, dtype=torch.float32, device=self.device)
+            u.grad_shard = self.coll.alloc_grad_shard(n)
             for _, p in params:
                 p.data = self._placeholder
         for _, p in params:
@@ -235,12 +235,13 @@ class ShardedModel(nn.Module):
         return u
 
     # --------------------------------------------------------------------------------- buffers
-    def _acquire(self, pool, unit: ShardUnit, dtype, zero_gaps=False) -> _Buf:
+    def _acquire(self, pool, unit: ShardUnit, dtype, symmetric: bool) -> _Buf:
         key = (unit.layout.signature(), dtype)
         lst = pool.setdefault(key, [])
         if lst:
             return lst.pop(0)
-        t = self.coll.alloc_full(unit.layout.total, dtype)
+        # gradient buffers are read by peers (symmetric heap); gathered parameters are local
+        t = self.coll.alloc_full(unit.layout.total, dtype, symmetric=symmetric)
         return _Buf(t, self._event())
 
     def _give_back(self, pool, unit: ShardUnit, buf: _Buf, dtype):
@@ -250,7 +251,7 @@ class ShardedModel(nn.Module):
     def _start_gather(self, u: ShardUnit):
         if self.mesh.shard_size == 1 or u.full is not None:
             return
-        buf = self._acquire(self._full_pool, u, self.mp.param_dtype)
+        buf = self._acquire(self._full_pool, u, self.mp.param_dtype, False)
         if self.is_cuda:
             with torch.cuda.stream(self.s_gather):
                 self.s_gather.wait_event(buf.free_event)
@@ -282,7 +283,7 @@ class ShardedModel(nn.Module):
     # ------------------------------------------------------------------------------- gradients
     def _prepare_grads(self, u: ShardUnit):
         if u.full_grad is None:
-            buf = self._acquire(self._grad_pool, u, self.mp.reduce_dtype)
+            buf = self._acquire(self._grad_pool, u, self.mp.reduce_dtype, True)
             u.full_grad = buf
         if self.is_cuda:
             self.s_compute.wait_event(u.full_grad.free_event)
@@ -328,6 +329,10 @@ class ShardedModel(nn.Module):
         model, blocks = self.module, self.blocks
         if self.is_cuda:
             self.s_gather.wait_stream(self.s_compute)  # shards were just written by the optimizer
+            with torch.cuda.stream(self.s_gather):
+                self.coll.begin_step()                 # ... on every rank (cross-GPU barrier, fused path)
+        else:
+            self.coll.begin_step()
         self._gnorm_sq.zero_()
         self._clip_coef = None
         self._start_gather(self.root)

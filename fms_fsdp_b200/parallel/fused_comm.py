@@ -1,0 +1,182 @@
+"""NVLink / NVSwitch collectives of the sharded runtime: our own peer-memory kernels, no NCCL on the
+parameter / gradient paths (SURVEY.md §5.8 "B200-native design").
+
+* buffers that peers must reach (compute-dtype parameter shards, unsharded gradient buffers, HSDP gradient
+  shards) are allocated from torch symmetric memory and rendezvoused once; we keep, per buffer, a device
+  table of the W peer addresses;
+* ``all_gather``      = pull kernel (``csrc/comm.cu::p2p_allgather_kernel``): every rank copies the 7 remote
+  shards with 16-byte peer loads, rotated start so all inbound NVLink flows are busy;
+* ``reduce_scatter``  = one-shot pull-reduce: rank r sums slice r of all W gradient buffers in fp32, scales by
+  1/world, writes the fp32 shard and accumulates ||g||^2 in the same pass (K11 folded into N8);
+* HSDP replica all-reduce / DDP all-reduce = two-phase (reduce own slice in place, barrier, gather slices);
+* ordering = signal-pad barriers (``st.release.sys`` / ``ld.acquire.sys``) enqueued on the same streams.
+
+Only scalars (grad-norm) and checkpoint metadata still travel through c10d.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+from fms_fsdp_b200.ops import _ext
+from fms_fsdp_b200.ops.functional import kernels_for
+from fms_fsdp_b200.parallel.mesh import DPMesh
+
+
+class _SymGroup:
+    """Symmetric allocations + barrier state for one process group."""
+
+    def __init__(self, group, size: int, my_index: int, device: torch.device):
+        import torch.distributed._symmetric_memory as symm_mem
+        self.symm_mem = symm_mem
+        self.group, self.size, self.index, self.device = group, size, my_index, device
+        self.tables: Dict[int, Tuple[torch.Tensor, list]] = {}  # data_ptr -> (device ptr table, host ptr list)
+        self.regions = []  # (base address, bytes, peer base addresses)
+        self._keep = []
+        self.epoch = 0
+        pad = self.alloc(64, torch.int32)
+        pad.zero_()
+        self.pad_table = self.tables[pad.data_ptr()][0]
+        torch.cuda.synchronize(device)
+        dist.barrier(group=group)
+
+    def alloc(self, numel: int, dtype: torch.dtype) -> torch.Tensor:
+        t = self.symm_mem.empty(numel, dtype=dtype, device=self.device)
+        hdl = self.symm_mem.rendezvous(t, self.group)
+        ptrs = [int(p) for p in hdl.buffer_ptrs]
+        table = torch.tensor(ptrs, dtype=torch.int64, device=self.device)
+        self.tables[t.data_ptr()] = (table, ptrs)
+        self.regions.append((t.data_ptr(), t.numel() * t.element_size(), ptrs))
+        self._keep.append((t, hdl))
+        return t
+
+    def table_of(self, t: torch.Tensor, byte_offset_per_peer=None) -> torch.Tensor:
+        """Device table of the W peer addresses of ``t`` (a registered buffer or a view into one; a view sits
+        at the same byte offset on every peer).  ``byte_offset_per_peer(i)`` adds a per-peer displacement."""
+        key = t.data_ptr()
+        if byte_offset_per_peer is None and key in self.tables:
+            return self.tables[key][0]
+        for base, nbytes, ptrs in self.regions:
+            if base <= key < base + nbytes:
+                off = key - base
+                break
+        else:
+            raise RuntimeError("tensor is not in the symmetric heap")
+        if byte_offset_per_peer is None:
+            host = [p + off for p in ptrs]
+            tab = torch.tensor(host, dtype=torch.int64, device=self.device)
+            self.tables[key] = (tab, host)
+            return tab
+        return torch.tensor([p + off + byte_offset_per_peer(i) for i, p in enumerate(ptrs)], dtype=torch.int64,
+                            device=self.device)
+
+    def barrier(self, C, anchor: torch.Tensor):
+        self.epoch += 1
+        C.signal_barrier(self.pad_table, self.size, self.index, self.epoch, anchor)
+
+
+class FusedCollectives:
+    name = "fused"
+
+    def __init__(self, mesh: DPMesh, device: torch.device):
+        self.mesh, self.device = mesh, device
+        self.C = _ext.require()
+        self.shard = _SymGroup(mesh.shard_group, mesh.shard_size, mesh.shard_rank, device) if mesh.shard_size > 1 else None
+        self.replica = _SymGroup(mesh.replica_group, mesh.replica_size, mesh.replica_rank, device) \
+            if mesh.replica_size > 1 else None
+        self._anchor = torch.zeros(1, device=device)
+        self._slice_tables: Dict[Tuple[int, int], torch.Tensor] = {}
+
+    # ---- allocation ---------------------------------------------------------------------------
+    def alloc_shard(self, numel: int, dtype: torch.dtype) -> torch.Tensor:
+        if self.shard is None:
+            return torch.zeros(numel, dtype=dtype, device=self.device)
+        t = self.shard.alloc(numel, dtype)
+        t.zero_()
+        return t
+
+    def alloc_full(self, numel: int, dtype: torch.dtype, symmetric: bool = True) -> torch.Tensor:
+        """Unsharded gradient buffers must be peer-visible; gathered-parameter buffers are local."""
+        if not symmetric:
+            return torch.zeros(numel, dtype=dtype, device=self.device)
+        g = self.shard if self.shard is not None else self.replica
+        if g is None:
+            return torch.zeros(numel, dtype=dtype, device=self.device)
+        t = g.alloc(numel, dtype)
+        t.zero_()
+        return t
+
+    def alloc_grad_shard(self, numel: int) -> torch.Tensor:
+        if self.replica is not None and self.shard is not None:  # hsdp: replicas all-reduce the fp32 shard
+            t = self.replica.alloc(numel, torch.float32)
+            t.zero_()
+            return t
+        return torch.zeros(numel, dtype=torch.float32, device=self.device)
+
+    # ---- parameter path -----------------------------------------------------------------------
+    def begin_step(self):
+        """All ranks' optimizer updates are visible before anyone gathers (enqueue on the gather stream)."""
+        if self.shard is not None:
+            self.shard.barrier(self.C, self._anchor)
+
+    def all_gather(self, shard: torch.Tensor, full: torch.Tensor):
+        if self.shard is None:
+            if full.data_ptr() != shard.data_ptr():
+                full.copy_(shard)
+            return
+        g = self.shard
+        self.C.p2p_allgather(g.table_of(shard), full, shard.numel() * shard.element_size(), g.size, g.index)
+
+    # ---- gradient path ------------------------------------------------------------------------
+    def reduce_scatter(self, full: torch.Tensor, shard32: torch.Tensor, scale: float, sumsq: Optional[torch.Tensor]):
+        g = self.shard
+        g.barrier(self.C, self._anchor)  # every rank's wgrads for this unit are complete
+        hsdp = self.replica is not None
+        self.C.reduce_scatter(g.table_of(full), shard32, g.index * shard32.numel(), g.size, g.index,
+                              full.dtype == torch.bfloat16, float(scale), None if hsdp else sumsq)
+        g.barrier(self.C, self._anchor)  # peers are done reading my buffer before it is rewritten
+        if hsdp:
+            self._allreduce(self.replica, shard32, 1.0, sumsq)
+
+    def all_reduce_full(self, full: torch.Tensor, scale: float, sumsq: Optional[torch.Tensor]):
+        if self.replica is None:
+            if sumsq is not None:
+                kernels_for(full).sumsq(full, out=sumsq)
+            return
+        self._allreduce(self.replica, full, scale, sumsq)
+
+    def _allreduce(self, g: _SymGroup, buf: torch.Tensor, scale: float, sumsq: Optional[torch.Tensor]):
+        n = buf.numel()
+        is_bf16 = buf.dtype == torch.bfloat16
+        unit = g.size * (8 if is_bf16 else 4)
+        if n % unit:
+            raise RuntimeError(f"all-reduce buffer of {n} elements is not a multiple of {unit}")
+        es = buf.element_size()
+        slice_bytes = n // g.size * es
+        g.barrier(self.C, self._anchor)
+        self.C.allreduce_inplace(g.table_of(buf), n, g.size, g.index, is_bf16, float(scale), None, self._anchor)
+        g.barrier(self.C, self._anchor)
+        key = (buf.data_ptr(), g.size)
+        tab = self._slice_tables.get(key)
+        if tab is None:
+            tab = g.table_of(buf, byte_offset_per_peer=lambda i: i * slice_bytes)
+            self._slice_tables[key] = tab
+        self.C.p2p_allgather(tab, buf, slice_bytes, g.size, g.index)
+        g.barrier(self.C, self._anchor)
+        if sumsq is not None:
+            kernels_for(buf).sumsq(buf, out=sumsq)
+
+    def all_reduce_scalar(self, t: torch.Tensor, over: str = "shard"):
+        m = self.mesh
+        if over == "shard":
+            if m.shard_size > 1:
+                dist.all_reduce(t, group=m.shard_group)
+        elif m.world > 1:
+            dist.all_reduce(t)
+        return t
+
+    def barrier(self):
+        if self.mesh.world > 1:
+            dist.barrier()

@@ -1,0 +1,121 @@
+"""Multi-GPU check (torchrun, one rank per GPU): fused NVLink collectives vs c10d/NCCL.
+ 1. raw kernels: p2p all-gather / pull reduce-scatter on 7B-block-sized buffers, numerics + bus bandwidth
+ 2. engine: same model/data trained with collective_impl=fused and =torch must agree
+Writes gpurun_out/multi_<world>.json from rank 0."""
+import json
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import torch.distributed as dist
+
+rank, world, lrank = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(lrank)
+dev = torch.device("cuda", lrank)
+dist.init_process_group("nccl", device_id=dev)
+out = {"world": world}
+
+
+def timed(fn, iters=10, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize(); dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record(); torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1) / iters], device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return t.item()
+
+
+from fms_fsdp_b200.parallel.mesh import build_mesh
+from fms_fsdp_b200.parallel.comm import TorchCollectives
+from fms_fsdp_b200.parallel.fused_comm import FusedCollectives
+
+mode = sys.argv[1] if len(sys.argv) > 1 else "all"
+if mode in ("all", "raw"):
+    mesh = build_mesh("fsdp")
+    fc, tc = FusedCollectives(mesh, dev), TorchCollectives(mesh, dev)
+    n_full = 202383360 // (world * 64) * (world * 64)  # one Llama2-7B block
+    n_sh = n_full // world
+    torch.manual_seed(rank)
+    sh = fc.alloc_shard(n_sh, torch.bfloat16); sh.copy_(torch.randn(n_sh, device=dev))
+    full_a = torch.empty(n_full, dtype=torch.bfloat16, device=dev); full_b = torch.empty_like(full_a)
+    fc.begin_step(); fc.all_gather(sh, full_a); tc.all_gather(sh, full_b); torch.cuda.synchronize()
+    out["allgather_equal"] = bool(torch.equal(full_a, full_b))
+    ms_f = timed(lambda: fc.all_gather(sh, full_a)); ms_t = timed(lambda: tc.all_gather(sh, full_b))
+    bytes_in = n_full * 2 * (world - 1) / world
+    out["allgather"] = dict(fused_ms=ms_f, nccl_ms=ms_t, fused_GBs_in=bytes_in / ms_f / 1e6, nccl_GBs_in=bytes_in / ms_t / 1e6)
+    g = fc.alloc_full(n_full, torch.bfloat16); g.copy_(torch.randn(n_full, device=dev) * 0.01)
+    o_f = torch.zeros(n_sh, device=dev); o_t = torch.zeros(n_sh, device=dev)
+    sq_f = torch.zeros((), device=dev); sq_t = torch.zeros((), device=dev)
+    fc.reduce_scatter(g, o_f, 1.0 / world, sq_f); tc.reduce_scatter(g, o_t, 1.0 / world, sq_t); torch.cuda.synchronize()
+    out["reduce_scatter_maxdiff"] = (o_f - o_t).abs().max().item()
+    out["reduce_scatter_ref_absmax"] = o_t.abs().max().item()
+    out["sumsq"] = [sq_f.item(), sq_t.item()]
+    ms_f = timed(lambda: fc.reduce_scatter(g, o_f, 1.0 / world, None)); ms_t = timed(lambda: tc.reduce_scatter(g, o_t, 1.0 / world, None))
+    out["reduce_scatter"] = dict(fused_ms=ms_f, nccl_ms=ms_t, fused_GBs_in=bytes_in / ms_f / 1e6, nccl_GBs_in=bytes_in / ms_t / 1e6)
+    del fc, tc, full_a, full_b, g
+
+if mode in ("all", "engine"):
+    from fms_fsdp_b200.models.llama import LLaMA, LLaMAConfig
+    from fms_fsdp_b200.parallel import ShardedAdamW, ShardedModel
+    from fms_fsdp_b200.policies import bfSixteen
+
+    def run(impl, strategy, shard=0, steps=4):
+        torch.manual_seed(0); torch.cuda.manual_seed(0)
+        cfg = LLaMAConfig(src_vocab_size=4096, emb_dim=1024, nheads=8, kvheads=4, nlayers=4, multiple_of=256, max_expected_seq_len=512)
+        with torch.device("meta"):
+            m = LLaMA(cfg)
+        eng = ShardedModel(m, sharding_strategy=strategy, hsdp_shard_size=shard, mixed_precision=bfSixteen, device=dev, collective_impl=impl)
+        opt = ShardedAdamW(eng, lr=1e-3)
+        res = []
+        for st in range(steps):
+            g = torch.Generator().manual_seed(100 * st + rank)
+            x = torch.randint(0, 4096, (2, 512), generator=g).to(dev)
+            loss = eng.forward_backward(x, x)
+            gn = eng.clip_grad_norm_(1.0)
+            opt.step()
+            res.append((loss.item(), gn.item()))
+        sd = eng.full_state_dict(cpu=False)
+        chk = sum(v.double().sum().item() for v in sd.values())
+        return res, chk
+
+    if mode == "engine" or True:
+        # per-unit gradient comparison after ONE backward (same weights, same data)
+        def grads(impl):
+            torch.manual_seed(0); torch.cuda.manual_seed(0)
+            cfg = LLaMAConfig(src_vocab_size=4096, emb_dim=1024, nheads=8, kvheads=4, nlayers=4, multiple_of=256, max_expected_seq_len=512)
+            with torch.device("meta"):
+                m = LLaMA(cfg)
+            eng = ShardedModel(m, sharding_strategy="fsdp", mixed_precision=bfSixteen, device=dev, collective_impl=impl)
+            g = torch.Generator().manual_seed(rank)
+            x = torch.randint(0, 4096, (2, 512), generator=g).to(dev)
+            eng.forward_backward(x, x)
+            torch.cuda.synchronize()
+            return {u.name: u.grad_shard.clone() for u in eng.units}, eng
+        ga, ea = grads("fused"); gb, eb = grads("torch")
+        rep = {}
+        for k in ga:
+            d = (ga[k] - gb[k]).abs()
+            rep[k] = dict(maxdiff=d.max().item(), absmax=gb[k].abs().max().item(), n_bad=int((d > 0.02 * gb[k].abs().max()).sum().item()),
+                          sumsq=[ga[k].pow(2).sum().item(), gb[k].pow(2).sum().item()], first_bad=int(torch.nonzero(d > 0.02 * gb[k].abs().max())[0].item()) if (d > 0.02 * gb[k].abs().max()).any() else -1,
+                          numel=ga[k].numel())
+        out["unit_grad_diff"] = rep
+        u = ea.root
+        out["root_slots"] = [(s.name, s.offset, s.numel) for s in u.layout.slots] + [("total", u.layout.total, u.layout.shard_numel)]
+        del ga, gb, ea, eb
+    combos = [("fsdp", 0)] + ([("ddp", 0)] if world <= 4 else []) + ([("hsdp", world // 2)] if world >= 4 else [])
+    for strat, shard in combos:
+        a, ca = run("fused", strat, shard); b, cb = run("torch", strat, shard)
+        out[f"engine_{strat}"] = dict(fused=a, torch=b, param_checksum=[ca, cb])
+
+if rank == 0:
+    os.makedirs("gpurun_out", exist_ok=True)
+    with open(f"gpurun_out/multi_{world}.json", "w") as f:
+        json.dump(out, f, indent=1)
+    print(json.dumps(out))
+dist.barrier(); dist.destroy_process_group()
