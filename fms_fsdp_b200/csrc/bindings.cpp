@@ -14,9 +14,9 @@ DECL int b200_rmsnorm_fwd(const void*, const void*, void*, float*, int, int, flo
 DECL int b200_rmsnorm_bwd_grid(int);
 DECL int b200_rmsnorm_bwd(const void*, const void*, const void*, const float*, void*, float*, float*, int, int,
                           cudaStream_t);
-DECL int b200_rope(void*, const float*, int, int, int, int, int, int, int, int, cudaStream_t);
-DECL int b200_swiglu_fwd(const void*, void*, long long, int, cudaStream_t);
-DECL int b200_swiglu_bwd(const void*, const void*, void*, long long, int, cudaStream_t);
+DECL int b200_rope(void*, const float*, int, int, int, int, int, int, int, int, int, cudaStream_t);
+DECL int b200_swiglu_fwd(const void*, void*, long long, int, int, cudaStream_t);
+DECL int b200_swiglu_bwd(const void*, const void*, void*, long long, int, int, cudaStream_t);
 DECL int b200_embedding_fwd(const void*, int, const void*, void*, long long, int, cudaStream_t);
 DECL int b200_embedding_bwd(const void*, int, const void*, void*, int, long long, int, cudaStream_t);
 DECL int b200_count_valid(const long long*, int, long long, float*, cudaStream_t);
@@ -123,16 +123,16 @@ std::vector<at::Tensor> rmsnorm_bwd(const at::Tensor& dy, const at::Tensor& x, c
   return {dx, dw};
 }
 void rope(at::Tensor& qkv, const at::Tensor& table, int64_t seq_len, int64_t nrot_heads, int64_t hd, int64_t rot,
-          bool inverse, int64_t pos_offset) {
+          bool inverse, int64_t pos_offset, bool interleaved) {
   c10::cuda::CUDAGuard guard(qkv.device());
   need(qkv, "qkv", at::kBFloat16);
   need(table, "table", at::kFloat);
   TORCH_CHECK(qkv.dim() == 2 && qkv.stride(1) == 1 && table.is_contiguous());
   TORCH_CHECK(table.size(0) >= seq_len + pos_offset && table.size(1) == rot / 2, "rope table too small");
   check(b200_rope(qkv.data_ptr(), table.data_ptr<float>(), qkv.size(0), seq_len, qkv.stride(0), nrot_heads, hd, rot,
-                  inverse, pos_offset, cur_stream()), "rope");
+                  inverse, pos_offset, interleaved, cur_stream()), "rope");
 }
-at::Tensor swiglu_fwd(const at::Tensor& gu) {
+at::Tensor swiglu_fwd(const at::Tensor& gu, bool gate_first) {
   c10::cuda::CUDAGuard guard(gu.device());
   need(gu, "gu", at::kBFloat16);
   TORCH_CHECK(gu.is_contiguous());
@@ -141,10 +141,10 @@ at::Tensor swiglu_fwd(const at::Tensor& gu) {
   auto sizes = gu.sizes().vec();
   sizes.back() = F;
   auto out = at::empty(sizes, gu.options());
-  check(b200_swiglu_fwd(gu.data_ptr(), out.data_ptr(), M, F, cur_stream()), "swiglu_fwd");
+  check(b200_swiglu_fwd(gu.data_ptr(), out.data_ptr(), M, F, gate_first, cur_stream()), "swiglu_fwd");
   return out;
 }
-at::Tensor swiglu_bwd(const at::Tensor& ds, const at::Tensor& gu) {
+at::Tensor swiglu_bwd(const at::Tensor& ds, const at::Tensor& gu, bool gate_first) {
   c10::cuda::CUDAGuard guard(gu.device());
   need(gu, "gu", at::kBFloat16);
   need(ds, "ds", at::kBFloat16);
@@ -152,7 +152,7 @@ at::Tensor swiglu_bwd(const at::Tensor& ds, const at::Tensor& gu) {
   const int F = gu.size(-1) / 2;
   const int64_t M = gu.numel() / (2 * F);
   auto dgu = at::empty_like(gu);
-  check(b200_swiglu_bwd(ds.data_ptr(), gu.data_ptr(), dgu.data_ptr(), M, F, cur_stream()), "swiglu_bwd");
+  check(b200_swiglu_bwd(ds.data_ptr(), gu.data_ptr(), dgu.data_ptr(), M, F, gate_first, cur_stream()), "swiglu_bwd");
   return dgu;
 }
 at::Tensor embedding_fwd(const at::Tensor& tok, const at::Tensor& w) {

@@ -155,6 +155,37 @@ __global__ void colsum_kernel(const float* __restrict__ part, float* __restrict_
 // ---------------------------------------------------------------------------------------- RoPE
 // In place on heads [0, nrot) of a fused [M, nheads_total*hd] projection; pairs (2i, 2i+1);
 // table [S, rot/2, 2] fp32 (cos, sin).  One thread = 8 elements = 4 pairs.
+// Half-split (GPT-NeoX / HF / mamba_ssm) convention: pairs (i, i + rot/2).  One thread = 8 pairs.
+__global__ void rope_halfsplit_kernel(__nv_bfloat16* __restrict__ qkv, const float* __restrict__ table, int M,
+                                      int seq_len, int row_stride, int nrot_heads, int hd, int rot, float sign,
+                                      int pos_offset) {
+  const int vec_per_head = rot / 16;
+  const size_t total = (size_t)M * nrot_heads * vec_per_head;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (size_t)gridDim.x * blockDim.x) {
+    const int vi = (int)(idx % vec_per_head);
+    const size_t t = idx / vec_per_head;
+    const int head = (int)(t % nrot_heads);
+    const size_t row = t / nrot_heads;
+    const int pos = (int)(row % seq_len) + pos_offset;
+    __nv_bfloat16* p0 = qkv + row * row_stride + head * hd + vi * 8;
+    __nv_bfloat16* p1 = p0 + rot / 2;
+    float a[8], b[8], oa[8], ob[8];
+    load8(p0, a);
+    load8(p1, b);
+    const float2* cs = reinterpret_cast<const float2*>(table + ((size_t)pos * (rot / 2) + vi * 8) * 2);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float2 c = cs[i];
+      const float sn = c.y * sign;
+      oa[i] = a[i] * c.x - b[i] * sn;
+      ob[i] = a[i] * sn + b[i] * c.x;
+    }
+    store8(p0, oa);
+    store8(p1, ob);
+  }
+}
+
 __global__ void rope_kernel(__nv_bfloat16* __restrict__ qkv, const float* __restrict__ table, int M, int seq_len,
                             int row_stride, int nrot_heads, int hd, int rot, float sign, int pos_offset) {
   const int vec_per_head = rot / 8;
@@ -185,7 +216,7 @@ __global__ void rope_kernel(__nv_bfloat16* __restrict__ qkv, const float* __rest
 
 // -------------------------------------------------------------------------------------- SwiGLU
 __global__ void swiglu_fwd_kernel(const __nv_bfloat16* __restrict__ gu, __nv_bfloat16* __restrict__ out, size_t M,
-                                  int F) {
+                                  int F, int goff, int uoff) {
   const int vec = F / 8;
   const size_t total = M * vec;
   for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
@@ -193,15 +224,15 @@ __global__ void swiglu_fwd_kernel(const __nv_bfloat16* __restrict__ gu, __nv_bfl
     const size_t row = idx / vec;
     const int c = (int)(idx % vec) * 8;
     float g[8], u[8], o[8];
-    load8(gu + row * 2 * F + c, g);
-    load8(gu + row * 2 * F + F + c, u);
+    load8(gu + row * 2 * F + goff + c, g);
+    load8(gu + row * 2 * F + uoff + c, u);
 #pragma unroll
     for (int i = 0; i < 8; ++i) o[i] = g[i] / (1.f + __expf(-g[i])) * u[i];
     store8(out + row * F + c, o);
   }
 }
 __global__ void swiglu_bwd_kernel(const __nv_bfloat16* __restrict__ ds, const __nv_bfloat16* __restrict__ gu,
-                                  __nv_bfloat16* __restrict__ dgu, size_t M, int F) {
+                                  __nv_bfloat16* __restrict__ dgu, size_t M, int F, int goff, int uoff) {
   const int vec = F / 8;
   const size_t total = M * vec;
   for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
@@ -209,8 +240,8 @@ __global__ void swiglu_bwd_kernel(const __nv_bfloat16* __restrict__ ds, const __
     const size_t row = idx / vec;
     const int c = (int)(idx % vec) * 8;
     float g[8], u[8], d[8], dg[8], du[8];
-    load8(gu + row * 2 * F + c, g);
-    load8(gu + row * 2 * F + F + c, u);
+    load8(gu + row * 2 * F + goff + c, g);
+    load8(gu + row * 2 * F + uoff + c, u);
     load8(ds + row * F + c, d);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
@@ -218,8 +249,8 @@ __global__ void swiglu_bwd_kernel(const __nv_bfloat16* __restrict__ ds, const __
       dg[i] = d[i] * u[i] * sig * (1.f + g[i] * (1.f - sig));
       du[i] = d[i] * g[i] * sig;
     }
-    store8(dgu + row * 2 * F + c, dg);
-    store8(dgu + row * 2 * F + F + c, du);
+    store8(dgu + row * 2 * F + goff + c, dg);
+    store8(dgu + row * 2 * F + uoff + c, du);
   }
 }
 
@@ -417,23 +448,32 @@ extern "C" int b200_rmsnorm_bwd(const void* dy, const void* x, const void* w, co
   CK();
 }
 extern "C" int b200_rope(void* qkv, const float* table, int M, int seq_len, int row_stride, int nrot_heads, int hd,
-                         int rot, int inverse, int pos_offset, cudaStream_t s) {
-  if (rot % 8 || hd % 8 || row_stride % 8) return -1;
-  size_t total = (size_t)M * nrot_heads * (rot / 8);
-  rope_kernel<<<grid_for(total, 256), 256, 0, s>>>((__nv_bfloat16*)qkv, table, M, seq_len, row_stride, nrot_heads, hd,
-                                                   rot, inverse ? -1.f : 1.f, pos_offset);
+                         int rot, int inverse, int pos_offset, int interleaved, cudaStream_t s) {
+  if (rot % 16 || hd % 8 || row_stride % 8) return -1;
+  if (interleaved) {
+    size_t total = (size_t)M * nrot_heads * (rot / 8);
+    rope_kernel<<<grid_for(total, 256), 256, 0, s>>>((__nv_bfloat16*)qkv, table, M, seq_len, row_stride, nrot_heads,
+                                                     hd, rot, inverse ? -1.f : 1.f, pos_offset);
+  } else {
+    size_t total = (size_t)M * nrot_heads * (rot / 16);
+    rope_halfsplit_kernel<<<grid_for(total, 256), 256, 0, s>>>((__nv_bfloat16*)qkv, table, M, seq_len, row_stride,
+                                                               nrot_heads, hd, rot, inverse ? -1.f : 1.f, pos_offset);
+  }
   CK();
 }
-extern "C" int b200_swiglu_fwd(const void* gu, void* out, long long M, int F, cudaStream_t s) {
+extern "C" int b200_swiglu_fwd(const void* gu, void* out, long long M, int F, int gate_first, cudaStream_t s) {
   if (F % 8) return -1;
   swiglu_fwd_kernel<<<grid_for((size_t)M * (F / 8), 256), 256, 0, s>>>((const __nv_bfloat16*)gu, (__nv_bfloat16*)out,
-                                                                       (size_t)M, F);
+                                                                       (size_t)M, F, gate_first ? 0 : F,
+                                                                       gate_first ? F : 0);
   CK();
 }
-extern "C" int b200_swiglu_bwd(const void* ds, const void* gu, void* dgu, long long M, int F, cudaStream_t s) {
+extern "C" int b200_swiglu_bwd(const void* ds, const void* gu, void* dgu, long long M, int F, int gate_first,
+                               cudaStream_t s) {
   if (F % 8) return -1;
   swiglu_bwd_kernel<<<grid_for((size_t)M * (F / 8), 256), 256, 0, s>>>(
-      (const __nv_bfloat16*)ds, (const __nv_bfloat16*)gu, (__nv_bfloat16*)dgu, (size_t)M, F);
+      (const __nv_bfloat16*)ds, (const __nv_bfloat16*)gu, (__nv_bfloat16*)dgu, (size_t)M, F, gate_first ? 0 : F,
+      gate_first ? F : 0);
   CK();
 }
 extern "C" int b200_embedding_fwd(const void* tok, int tok_is_i64, const void* w, void* out, long long M, int D,

@@ -90,11 +90,12 @@ rmsnorm_gated_bwd = torch_kernels.rmsnorm_gated_bwd
 rope_table = torch_kernels.rope_table
 
 
-def rope_(qkv, table, seq_len, nheads, kvheads, head_dim, rot_dim=None, inverse=False, pos_offset=0):
+def rope_(qkv, table, seq_len, nheads, kvheads, head_dim, rot_dim=None, inverse=False, pos_offset=0, interleaved=True):
     rot_dim = head_dim if rot_dim is None else rot_dim
-    if qkv.dtype != torch.bfloat16 or rot_dim % 8 or head_dim % 8:
-        return torch_kernels.rope_(qkv, table, seq_len, nheads, kvheads, head_dim, rot_dim, inverse, pos_offset)
-    _C.rope(qkv, table, seq_len, nheads + kvheads, head_dim, rot_dim, bool(inverse), pos_offset)
+    if qkv.dtype != torch.bfloat16 or rot_dim % 16 or head_dim % 8:
+        return torch_kernels.rope_(qkv, table, seq_len, nheads, kvheads, head_dim, rot_dim, inverse, pos_offset,
+                                   interleaved)
+    _C.rope(qkv, table, seq_len, nheads + kvheads, head_dim, rot_dim, bool(inverse), pos_offset, bool(interleaved))
     return qkv
 
 
@@ -128,16 +129,16 @@ def attn_bwd(do, qkv, o, lse, B, S, H, KVH, hd, scale, causal=True):
 
 
 # ---------------------------------------------------------------------------------------- SwiGLU
-def swiglu_fwd(gu):
+def swiglu_fwd(gu, gate_first=True):
     if gu.dtype != torch.bfloat16 or (gu.shape[-1] // 2) % 8:
-        return torch_kernels.swiglu_fwd(gu)
-    return _C.swiglu_fwd(gu.contiguous())
+        return torch_kernels.swiglu_fwd(gu, gate_first)
+    return _C.swiglu_fwd(gu.contiguous(), bool(gate_first))
 
 
-def swiglu_bwd(ds, gu):
+def swiglu_bwd(ds, gu, gate_first=True):
     if gu.dtype != torch.bfloat16 or (gu.shape[-1] // 2) % 8:
-        return torch_kernels.swiglu_bwd(ds, gu)
-    return _C.swiglu_bwd(ds.contiguous(), gu.contiguous())
+        return torch_kernels.swiglu_bwd(ds, gu, gate_first)
+    return _C.swiglu_bwd(ds.contiguous(), gu.contiguous(), bool(gate_first))
 
 
 # ------------------------------------------------------------------------------------- embedding

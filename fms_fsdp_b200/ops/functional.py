@@ -159,28 +159,29 @@ def rmsnorm_gated(x, z, w, eps=1e-5, group_size=None):
 # -------------------------------------------------------------------------------------------- rope
 class _Rope(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, qkv, table, seq_len, nheads, kvheads, head_dim, rot_dim):
+    def forward(ctx, qkv, table, seq_len, nheads, kvheads, head_dim, rot_dim, interleaved):
         K = kernels_for(qkv)
-        ctx.K, ctx.args = K, (seq_len, nheads, kvheads, head_dim, rot_dim)
+        ctx.K, ctx.args = K, (seq_len, nheads, kvheads, head_dim, rot_dim, interleaved)
         ctx.save_for_backward(table)
         ctx.mark_dirty(qkv)
-        K.rope_(qkv.view(-1, qkv.shape[-1]), table, seq_len, nheads, kvheads, head_dim, rot_dim, False)
+        K.rope_(qkv.view(-1, qkv.shape[-1]), table, seq_len, nheads, kvheads, head_dim, rot_dim, False, 0, interleaved)
         return qkv
 
     @staticmethod
     def backward(ctx, dqkv):
         (table,) = ctx.saved_tensors
-        seq_len, nheads, kvheads, head_dim, rot_dim = ctx.args
+        seq_len, nheads, kvheads, head_dim, rot_dim, interleaved = ctx.args
         # the roped projection feeds exactly one consumer (attention), so its incoming gradient is
         # exclusively ours: rotate it back in place instead of paying for a copy.
         d = dqkv.contiguous()
-        ctx.K.rope_(d.view(-1, d.shape[-1]), table, seq_len, nheads, kvheads, head_dim, rot_dim, True)
-        return d, None, None, None, None, None, None
+        ctx.K.rope_(d.view(-1, d.shape[-1]), table, seq_len, nheads, kvheads, head_dim, rot_dim, True, 0, interleaved)
+        return d, None, None, None, None, None, None, None
 
 
-def rope_(qkv, table, seq_len, nheads, kvheads, head_dim, rot_dim=None):
-    """Rotate the q,k sections of the fused projection in place (interleaved-pair convention)."""
-    return _Rope.apply(qkv, table, seq_len, nheads, kvheads, head_dim, rot_dim or head_dim)
+def rope_(qkv, table, seq_len, nheads, kvheads, head_dim, rot_dim=None, interleaved=True):
+    """Rotate the q,k sections of the fused projection in place.  ``interleaved=True`` is the FMS
+    pair convention (2i, 2i+1); False is the half-split (i, i+rot/2) convention of mamba_ssm / HF."""
+    return _Rope.apply(qkv, table, seq_len, nheads, kvheads, head_dim, rot_dim or head_dim, interleaved)
 
 
 # --------------------------------------------------------------------------------------- attention
@@ -213,20 +214,55 @@ def attention(qkv, nheads, kvheads, head_dim, scale=None):
 # ------------------------------------------------------------------------------------------ swiglu
 class _SwiGLU(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, gu):
+    def forward(ctx, gu, gate_first):
         K = kernels_for(gu)
-        ctx.K = K
+        ctx.K, ctx.gate_first = K, gate_first
         ctx.save_for_backward(gu)
-        return K.swiglu_fwd(gu)
+        return K.swiglu_fwd(gu, gate_first)
 
     @staticmethod
     def backward(ctx, ds):
         (gu,) = ctx.saved_tensors
-        return ctx.K.swiglu_bwd(ds.contiguous(), gu)
+        return ctx.K.swiglu_bwd(ds.contiguous(), gu, ctx.gate_first), None
 
 
-def swiglu(gu):
-    return _SwiGLU.apply(gu)
+def swiglu(gu, gate_first=True):
+    """silu(gate) * up on a fused projection; ``gate_first`` = FMS [gate | up], False = mamba_ssm [up | gate]."""
+    return _SwiGLU.apply(gu, gate_first)
+
+
+class _AddRMSNorm(torch.autograd.Function):
+    """residual_out = residual + x (kept in the residual stream dtype, fp32 for Mamba);
+    y = rmsnorm(residual_out) in x.dtype.  (mamba_ssm fused_add_norm)"""
+
+    @staticmethod
+    def forward(ctx, x, res, w, eps, res_fp32):
+        K = kernels_for(x)
+        D = x.shape[-1]
+        y, res_out, rstd = K.add_rmsnorm_fwd(x.reshape(-1, D), res.reshape(-1, D), _wdata(w), eps)
+        ctx.K, ctx.w, ctx.xdtype = K, w, x.dtype
+        ctx.save_for_backward(res_out, rstd)
+        return y.view(x.shape), res_out.view(res.shape)
+
+    @staticmethod
+    def backward(ctx, dy, dres_out):
+        res_out, rstd = ctx.saved_tensors
+        D = res_out.shape[-1]
+        dn, dw32 = ctx.K.rmsnorm_bwd(dy.reshape(-1, D).contiguous(), res_out, _wdata(ctx.w), rstd)
+        dres = dn.float()
+        if dres_out is not None:
+            dres = dres + dres_out.reshape(-1, D).float()
+        def put(out, acc):
+            if acc:
+                out.add_(dw32.to(out.dtype))
+            else:
+                out.copy_(dw32)
+        dw = _deliver_wgrad(ctx.w, put) if ctx.needs_input_grad[2] else None
+        return dres.to(ctx.xdtype).view(dy.shape), dres.to(res_out.dtype).view(dy.shape), dw, None, None
+
+
+def add_rmsnorm(x, residual, w, eps=1e-5, residual_in_fp32=True):
+    return _AddRMSNorm.apply(x, residual, w, eps, residual_in_fp32)
 
 
 # --------------------------------------------------------------------------------------- embedding

@@ -106,7 +106,7 @@ def rope_table(max_seq_len, rot_dim, theta=10000.0, ntk_alpha=1.0, device=None):
     return torch.stack([ang.cos(), ang.sin()], dim=-1).contiguous()  # [S, rot_dim/2, 2]
 
 
-def rope_(qkv, table, seq_len, nheads, kvheads, head_dim, rot_dim=None, inverse=False, pos_offset=0):
+def rope_(qkv, table, seq_len, nheads, kvheads, head_dim, rot_dim=None, inverse=False, pos_offset=0, interleaved=True):
     rot_dim = head_dim if rot_dim is None else rot_dim
     M = qkv.shape[0]
     nrot = nheads + kvheads
@@ -116,9 +116,14 @@ def rope_(qkv, table, seq_len, nheads, kvheads, head_dim, rot_dim=None, inverse=
     cos, sin = cs[..., 0].unsqueeze(1), cs[..., 1].unsqueeze(1)
     if inverse:
         sin = -sin
-    x = v.float().reshape(M, nrot, rot_dim // 2, 2)
-    x0, x1 = x[..., 0], x[..., 1]
-    out = torch.stack([x0 * cos - x1 * sin, x0 * sin + x1 * cos], dim=-1).reshape(M, nrot, rot_dim)
+    if interleaved:   # FMS convention: pairs (2i, 2i+1)
+        x = v.float().reshape(M, nrot, rot_dim // 2, 2)
+        x0, x1 = x[..., 0], x[..., 1]
+        out = torch.stack([x0 * cos - x1 * sin, x0 * sin + x1 * cos], dim=-1).reshape(M, nrot, rot_dim)
+    else:             # GPT-NeoX / HF convention: pairs (i, i + rot/2)
+        x = v.float()
+        x0, x1 = x[..., : rot_dim // 2], x[..., rot_dim // 2:]
+        out = torch.cat([x0 * cos - x1 * sin, x0 * sin + x1 * cos], dim=-1)
     v.copy_(out.to(qkv.dtype))
     return qkv
 
@@ -182,19 +187,21 @@ def attn_bwd(do, qkv, o, lse, B, S, H, KVH, hd, scale, causal=True):
 # ----------------------------------------------------------------------------------------------
 # SwiGLU on the fused gate/up projection gu = [gate | up] (FMS wg1_fused row order).
 # ----------------------------------------------------------------------------------------------
-def swiglu_fwd(gu):
+def swiglu_fwd(gu, gate_first=True):
     F_ = gu.shape[-1] // 2
-    g, u = gu[..., :F_].float(), gu[..., F_:].float()
+    a, b = gu[..., :F_].float(), gu[..., F_:].float()
+    g, u = (a, b) if gate_first else (b, a)
     return (F.silu(g) * u).to(gu.dtype)
 
 
-def swiglu_bwd(ds, gu):
+def swiglu_bwd(ds, gu, gate_first=True):
     F_ = gu.shape[-1] // 2
-    g, u, d = gu[..., :F_].float(), gu[..., F_:].float(), ds.float()
+    a, b, d = gu[..., :F_].float(), gu[..., F_:].float(), ds.float()
+    g, u = (a, b) if gate_first else (b, a)
     sig = torch.sigmoid(g)
     dg = d * u * sig * (1 + g * (1 - sig))
     du = d * g * sig
-    return torch.cat([dg, du], dim=-1).to(gu.dtype)
+    return torch.cat([dg, du] if gate_first else [du, dg], dim=-1).to(gu.dtype)
 
 
 # ----------------------------------------------------------------------------------------------

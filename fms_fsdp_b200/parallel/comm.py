@@ -35,6 +35,9 @@ class TorchCollectives:
         return torch.zeros(numel, dtype=dtype, device=self.device)
 
     def alloc_full(self, numel: int, dtype: torch.dtype, symmetric: bool = True) -> torch.Tensor:
+        if not symmetric:
+            # gathered-parameter buffer: first written on the gather stream, so no fill kernel on this stream
+            return torch.empty(numel, dtype=dtype, device=self.device)
         return torch.zeros(numel, dtype=dtype, device=self.device)
 
     def alloc_grad_shard(self, numel: int) -> torch.Tensor:

@@ -100,7 +100,9 @@ class FusedCollectives:
     def alloc_full(self, numel: int, dtype: torch.dtype, symmetric: bool = True) -> torch.Tensor:
         """Unsharded gradient buffers must be peer-visible; gathered-parameter buffers are local."""
         if not symmetric:
-            return torch.zeros(numel, dtype=dtype, device=self.device)
+            # NOT zero-filled: the fill would run on the caller's (compute) stream and race with the first
+            # gather that writes this buffer on the gather stream
+            return torch.empty(numel, dtype=dtype, device=self.device)
         g = self.shard if self.shard is not None else self.replica
         if g is None:
             return torch.zeros(numel, dtype=dtype, device=self.device)

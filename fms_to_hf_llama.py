@@ -1,0 +1,108 @@
+"""Export a sharded training checkpoint to a HuggingFace ``LlamaForCausalLM`` directory
+(CLI parity with reference ``fms_to_hf_llama.py:133-171``):
+
+    python fms_to_hf_llama.py --model_variant llama2_7b --nocompiled --load_path <step_N_ckp> \
+        --save_path <out> --tokenizer_name_or_path <tok>
+
+Reads the DCP checkpoint (``model_state.*`` keys, or ``model_state._orig_mod.*`` for checkpoints written under
+torch.compile by the reference) without any process group, splits the fused QKV / gate-up weights, and permutes
+q/k rows from the FMS interleaved-pair RoPE layout to HF's half-split layout.  Unlike the reference (SURVEY.md
+Q17) the exported config carries the right ``rope_theta`` / ``max_position_embeddings``, so llama3 / 34b exports
+round-trip (tests/test_exporters.py checks logits equality).
+"""
+import os
+
+import torch
+
+from fms_fsdp_b200.models.llama import LLaMA
+from fms_fsdp_b200.utils.cli import run
+from fms_fsdp_b200.utils.config_utils import get_model_config
+
+
+def _interleaved_to_halfsplit(w: torch.Tensor, nheads: int) -> torch.Tensor:
+    """rows [h, (pair, 2)] -> [h, (2, pair)]: (x0,x1,x2,x3,..) -> (x0,x2,..,x1,x3,..) per head."""
+    return w.view(nheads, -1, 2, w.size(1)).transpose(1, 2).reshape(*w.size())
+
+
+def convert_to_hf(model: LLaMA, model_variant: str, is_old_fms: bool = False):
+    from transformers import LlamaConfig, LlamaForCausalLM
+
+    c = model.config
+    rope_theta = c.rope_theta
+    if c.ntk_scaling:
+        alpha = model.rot_emb._alpha(c.max_expected_seq_len)
+        rope_theta = rope_theta * alpha ** (c.head_dim / (c.head_dim - 2))
+    kw = dict(
+        vocab_size=c.src_vocab_size, hidden_size=c.emb_dim, rms_norm_eps=c.norm_eps, num_attention_heads=c.nheads,
+        num_key_value_heads=c.kv_heads, num_hidden_layers=c.nlayers, intermediate_size=c.hidden_dim,
+        pad_token_id=None if c.pad_id == -1 else c.pad_id, max_position_embeddings=c.max_expected_seq_len,
+        rope_theta=rope_theta, tie_word_embeddings=False, attention_bias=False, mlp_bias=False,
+    )
+    if "llama3" in model_variant:
+        kw.update(bos_token_id=128000, eos_token_id=128001)
+    hf = LlamaForCausalLM(LlamaConfig(**kw))
+    sd = model.state_dict()
+    hd = c.head_dim
+    with torch.no_grad():
+        hf.model.embed_tokens.weight.copy_(sd["shared.emb.weight"])
+        for i, layer in enumerate(hf.model.layers):
+            p = f"layers.{i}."
+            if is_old_fms and p + "attn.query.weight" in sd:
+                q, k, v = sd[p + "attn.query.weight"], sd[p + "attn.key.weight"], sd[p + "attn.value.weight"]
+            else:
+                q, k, v = torch.split(sd[p + "attn.in_proj.qkv_fused.weight"],
+                                      [c.nheads * hd, c.kv_heads * hd, c.kv_heads * hd], dim=0)
+            layer.self_attn.q_proj.weight.copy_(_interleaved_to_halfsplit(q, c.nheads))
+            layer.self_attn.k_proj.weight.copy_(_interleaved_to_halfsplit(k, c.kv_heads))
+            layer.self_attn.v_proj.weight.copy_(v)
+            layer.self_attn.o_proj.weight.copy_(sd[p + "attn.dense.weight"])
+            if is_old_fms and p + "ff_sub_layer.wg.weight" in sd:
+                wg, w1 = sd[p + "ff_sub_layer.wg.weight"], sd[p + "ff_sub_layer.w1.weight"]
+            else:
+                fused = sd[p + "ff_sub_layer.wg1_fused.weight"]
+                wg, w1 = torch.split(fused, [fused.size(0) // 2, fused.size(0) // 2], dim=0)
+            layer.mlp.gate_proj.weight.copy_(wg)
+            layer.mlp.up_proj.weight.copy_(w1)
+            layer.mlp.down_proj.weight.copy_(sd[p + "ff_sub_layer.w2.weight"])
+            layer.input_layernorm.weight.copy_(sd[p + "ln.weight"])
+            layer.post_attention_layernorm.weight.copy_(sd[p + "ff_ln.weight"])
+        hf.model.norm.weight.copy_(sd["dec_norm.weight"])
+        hf.lm_head.weight.copy_(sd["shared.head.weight"])
+    return hf
+
+
+def load_dcp_into(model: torch.nn.Module, load_path: str, compiled: bool = False):
+    """no_dist DCP read of ``model_state`` into a full CPU model (handles the ``_orig_mod`` level)."""
+    import torch.distributed.checkpoint as dcp
+    from torch.distributed.checkpoint import FileSystemReader
+    keys = set(FileSystemReader(load_path).read_metadata().state_dict_metadata.keys())
+    if compiled or any(k.startswith("model_state._orig_mod.") for k in keys):
+        state = {"model_state": {"_orig_mod": model.state_dict()}}
+    else:
+        state = {"model_state": model.state_dict()}
+    dcp.load(state, checkpoint_id=load_path, no_dist=True)
+    sd = state["model_state"]
+    model.load_state_dict(sd.get("_orig_mod", sd))
+    return model
+
+
+def main(model_variant, load_path, save_path, tokenizer_name_or_path=None, compiled=False, is_old_fms=False):
+    print("Initializing model...")
+    cfg = get_model_config(model_variant)
+    with torch.device("meta"):
+        model = LLaMA(cfg)
+    model.to_empty(device="cpu")
+    print(f"Reading state dict from {load_path}")
+    load_dcp_into(model, load_path, compiled)
+    print("Converting to HF Llama...")
+    hf = convert_to_hf(model, model_variant, is_old_fms)
+    hf.save_pretrained(save_path)
+    print(f"Model saving at {save_path}")
+    if tokenizer_name_or_path:
+        from transformers import AutoTokenizer
+        AutoTokenizer.from_pretrained(tokenizer_name_or_path).save_pretrained(save_path)
+    print("Done.")
+
+
+if __name__ == "__main__":
+    run(main)

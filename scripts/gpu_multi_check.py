@@ -60,7 +60,7 @@ if mode in ("all", "raw"):
     out["reduce_scatter"] = dict(fused_ms=ms_f, nccl_ms=ms_t, fused_GBs_in=bytes_in / ms_f / 1e6, nccl_GBs_in=bytes_in / ms_t / 1e6)
     del fc, tc, full_a, full_b, g
 
-if mode in ("all", "engine"):
+if mode in ("all", "engine", "gn"):
     from fms_fsdp_b200.models.llama import LLaMA, LLaMAConfig
     from fms_fsdp_b200.parallel import ShardedAdamW, ShardedModel
     from fms_fsdp_b200.policies import bfSixteen
@@ -96,7 +96,10 @@ if mode in ("all", "engine"):
             x = torch.randint(0, 4096, (2, 512), generator=g).to(dev)
             eng.forward_backward(x, x)
             torch.cuda.synchronize()
-            return {u.name: u.grad_shard.clone() for u in eng.units}, eng
+            gs = {u.name: u.grad_shard.clone() for u in eng.units}
+            out.setdefault("gnorm_sq_check", {})[impl] = dict(engine=eng._gnorm_sq.item(), from_shards=sum(v.double().pow(2).sum().item() for v in gs.values()),
+                                                             clip=eng.clip_grad_norm_(1.0).item())
+            return gs, eng
         ga, ea = grads("fused"); gb, eb = grads("torch")
         rep = {}
         for k in ga:
@@ -109,6 +112,8 @@ if mode in ("all", "engine"):
         out["root_slots"] = [(s.name, s.offset, s.numel) for s in u.layout.slots] + [("total", u.layout.total, u.layout.shard_numel)]
         del ga, gb, ea, eb
     combos = [("fsdp", 0)] + ([("ddp", 0)] if world <= 4 else []) + ([("hsdp", world // 2)] if world >= 4 else [])
+    if mode == "gn":
+        combos = []
     for strat, shard in combos:
         a, ca = run("fused", strat, shard); b, cb = run("torch", strat, shard)
         out[f"engine_{strat}"] = dict(fused=a, torch=b, param_checksum=[ca, cb])

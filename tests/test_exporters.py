@@ -1,0 +1,64 @@
+"""HF export round-trips: logits of the exported HF model == ours (reference leaves this untested; its
+exporter drops rope_theta)."""
+import os
+import tempfile
+
+import pytest
+import torch
+
+from fms_fsdp_b200.models.llama import LLaMA, LLaMAConfig
+from fms_fsdp_b200.parallel import ShardedAdamW, ShardedModel
+from fms_fsdp_b200.utils.checkpointing_utils import Checkpointer
+
+
+@pytest.mark.parametrize("kv,theta", [(0, 10000.0), (2, 500000.0)])
+def test_llama_export_logits_roundtrip(kv, theta):
+    import fms_to_hf_llama as ex
+    torch.manual_seed(0)
+    cfg = LLaMAConfig(src_vocab_size=97, emb_dim=64, nheads=4, kvheads=kv, nlayers=2, multiple_of=16,
+                      max_expected_seq_len=64, rope_theta=theta)
+    m = LLaMA(cfg); m.reset_parameters(); m.eval()
+    hf = ex.convert_to_hf(m, "llama3_x" if theta > 1e5 else "llama2_x").eval()
+    rp = getattr(hf.config, 'rope_parameters', None) or {}
+    assert (rp.get('rope_theta') if rp else hf.config.rope_theta) == theta
+    x = torch.randint(0, 97, (2, 33))
+    with torch.no_grad():
+        ours = m(x)
+        theirs = hf(x).logits
+    assert torch.allclose(ours, theirs, atol=2e-4, rtol=1e-3), (ours - theirs).abs().max()
+
+
+def test_llama_export_from_sharded_checkpoint(monkeypatch):
+    import fms_to_hf_llama as ex
+    from fms_fsdp_b200.utils import config_utils
+    torch.manual_seed(1)
+    cfg = LLaMAConfig(src_vocab_size=64, emb_dim=32, nheads=2, nlayers=2, multiple_of=16, max_expected_seq_len=32)
+    m = LLaMA(cfg); m.reset_parameters()
+    ref_sd = {k: v.clone() for k, v in m.state_dict().items()}
+    eng = ShardedModel(m, device="cpu"); opt = ShardedAdamW(eng)
+    ck = tempfile.mkdtemp()
+    Checkpointer(ck, 2, "fsdp", 0, 0).save(7, eng, opt, None, tokens_seen=1)
+    monkeypatch.setattr(ex, "get_model_config", lambda v: LLaMAConfig(**cfg.__dict__))
+    out = tempfile.mkdtemp()
+    ex.main("llama2_test", os.path.join(ck, "checkpoints", "step_7_ckp"), out)
+    from transformers import LlamaForCausalLM
+    hf = LlamaForCausalLM.from_pretrained(out)
+    assert torch.equal(hf.model.embed_tokens.weight, ref_sd["shared.emb.weight"])
+    assert torch.equal(hf.lm_head.weight, ref_sd["shared.head.weight"])
+
+
+def test_mamba_export(monkeypatch):
+    import fms_to_hf_mamba as ex
+    from fms_fsdp_b200.models.mamba import MambaConfig, MambaLMHeadModel
+    from fms_fsdp_b200.utils.config_utils import get_model_config
+    torch.manual_seed(2)
+    m = MambaLMHeadModel(MambaConfig(**get_model_config("mamba_tiny"))); m.reset_parameters()
+    ref_sd = {k: v.clone() for k, v in m.state_dict().items()}
+    eng = ShardedModel(m, device="cpu")
+    ck = tempfile.mkdtemp()
+    Checkpointer(ck, 2, "fsdp", 0, 0).save(3, eng, None, None)
+    out = tempfile.mkdtemp()
+    ex.main("mamba_tiny", os.path.join(ck, "checkpoints", "step_3_ckp"), out)
+    sd = torch.load(os.path.join(out, "pytorch_model.bin"))
+    assert set(sd) == set(ref_sd) and all(torch.equal(sd[k], ref_sd[k]) for k in sd)
+    assert os.path.exists(os.path.join(out, "config.json"))
