@@ -430,6 +430,32 @@ class ShardedModel(nn.Module):
         self._backward(None)
         return loss.detach()
 
+    def forward_backward_custom(self, loss_closure) -> torch.Tensor:
+        """Training micro-step for models that are a single (root) unit, e.g. the MLP speculator under NO_SHARD:
+        ``loss_closure(module) -> scalar loss`` runs under autograd with the parameters gathered; gradients are
+        reduced (all-reduce / reduce-scatter + replica reduce), scaled by 1/world and norm-accumulated."""
+        if self.blocks:
+            raise RuntimeError("forward_backward_custom is for root-only models")
+        if self.is_cuda:
+            self.s_gather.wait_stream(self.s_compute)
+            with torch.cuda.stream(self.s_gather):
+                self.coll.begin_step()
+        else:
+            self.coll.begin_step()
+        self._gnorm_sq.zero_()
+        self._clip_coef = None
+        self._start_gather(self.root)
+        self._wait_gather(self.root)
+        self._prepare_grads(self.root)
+        with torch.enable_grad():
+            loss = loss_closure(self.module)
+        loss.backward()
+        self._reduce(self.root)
+        self._release(self.root)
+        if self.is_cuda:
+            self.s_compute.wait_stream(self.s_reduce)
+        return loss.detach()
+
     # reference-style API: ``out = model(input)`` ... ``loss.backward()``
     def forward(self, tokens, labels=None, **head_kwargs):
         if not torch.is_grad_enabled():

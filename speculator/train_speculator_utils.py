@@ -1,0 +1,393 @@
+"""Speculator training services (public names of reference ``speculator/train_speculator_utils.py``):
+``generate``, ``stage1_loss``, ``stage2_loss``, ``do_ckpt``, ``train_speculator``, the ``Embed*`` base models
+(forward returns hidden states next to the logits) and their registry
+(``embedllama.{7b,8b}``, ``embedgpt_bigcode.20b``, ``embedmixtral.8x7b``)."""
+from __future__ import annotations
+
+import os
+import time
+from typing import Any, Callable, MutableMapping, Optional, Union
+
+import torch
+import torch.distributed as dist
+import torch.nn as nn
+import torch.nn.functional as F
+
+from fms_fsdp_b200 import ops
+from fms_fsdp_b200.models.llama import LLaMA, LLaMAConfig
+from fms_fsdp_b200.parallel.tensor_parallel import tp_all_gather_last, tp_all_reduce
+
+
+# ---------------------------------------------------------------------------------- base models
+class EmbedLLaMA(LLaMA):
+    """Frozen LLaMA whose forward can also return the final hidden states ("embeds") and a KV cache.
+    Inference only: prefill uses the engine's flash attention; single-token decode steps attend over the
+    cache with SDPA.  With ``shard_llama_for_tp`` applied, row-parallel outputs are all-reduced."""
+
+    def forward(self, x, past_key_value_states=None, use_cache=False, include_embeds=False, **_):
+        tp = getattr(self, "_tp_group", None)
+        B, S = x.shape
+        h = self.shared(x)
+        past = past_key_value_states
+        pos0 = 0 if past is None else past[0][0].size(1)
+        new_cache = []
+        tab = self.rot_emb.table(h.device, pos0 + S)
+        for li, blk in enumerate(self.layers):
+            a = blk.attn
+            qkv = a.in_proj.qkv_fused(blk.ln(h))
+            K = ops.kernels_for(qkv)
+            K.rope_(qkv.view(B * S, -1), tab, S, a.nheads, a.kvheads, a.head_dim, a.head_dim, False, pos0)
+            if past is None and not use_cache:
+                ctx = ops.attention(qkv, a.nheads, a.kvheads, a.head_dim)
+            else:
+                t = qkv.view(B, S, a.nheads + 2 * a.kvheads, a.head_dim)
+                q, k, v = t[:, :, :a.nheads], t[:, :, a.nheads:a.nheads + a.kvheads], t[:, :, a.nheads + a.kvheads:]
+                if past is not None:
+                    k = torch.cat([past[li][0], k], dim=1)
+                    v = torch.cat([past[li][1], v], dim=1)
+                new_cache.append((k, v))
+                ctx = F.scaled_dot_product_attention(
+                    q.transpose(1, 2), k.transpose(1, 2), v.transpose(1, 2), is_causal=(past is None),
+                    enable_gqa=(a.kvheads != a.nheads)).transpose(1, 2).reshape(B, S, a.nheads * a.head_dim)
+            if tp is None:
+                h = a.dense(ctx, residual=h)
+                h = blk.ff_sub_layer.w2(ops.swiglu(blk.ff_sub_layer.wg1_fused(blk.ff_ln(h))), residual=h)
+            else:
+                h = h + tp_all_reduce(a.dense(ctx), tp)
+                h = h + tp_all_reduce(blk.ff_sub_layer.w2(ops.swiglu(blk.ff_sub_layer.wg1_fused(blk.ff_ln(h)))), tp)
+        embeds = self.dec_norm(h)
+        logits = self.shared(embeds, reverse=True)
+        if tp is not None:
+            logits = tp_all_gather_last(logits, tp)
+        out = [logits]
+        if use_cache:
+            out.append(new_cache)
+        if include_embeds:
+            out.append(embeds)
+        return out[0] if len(out) == 1 else tuple(out)
+
+
+class _GPTBigCodeBlock(nn.Module):
+    def __init__(self, d, nheads, hidden, eps):
+        super().__init__()
+        self.nheads, self.hd = nheads, d // nheads
+        self.ln = nn.LayerNorm(d, eps=eps)
+        self.ff_ln = nn.LayerNorm(d, eps=eps)
+        self.qkv = nn.Linear(d, d + 2 * self.hd)  # multi-query attention: one shared k/v head
+        self.dense = nn.Linear(d, d)
+        self.w1, self.w2 = nn.Linear(d, hidden), nn.Linear(hidden, d)
+
+    def forward(self, h, past=None, use_cache=False):
+        B, S, D = h.shape
+        q, k, v = self.qkv(self.ln(h)).split([D, self.hd, self.hd], dim=-1)
+        if past is not None:
+            k, v = torch.cat([past[0], k], 1), torch.cat([past[1], v], 1)
+        ctx = F.scaled_dot_product_attention(q.view(B, S, self.nheads, self.hd).transpose(1, 2), k.unsqueeze(1),
+                                             v.unsqueeze(1), is_causal=(past is None), enable_gqa=True)
+        h = h + self.dense(ctx.transpose(1, 2).reshape(B, S, D))
+        h = h + self.w2(F.gelu(self.w1(self.ff_ln(h)), approximate="tanh"))
+        return h, ((k, v) if use_cache else None)
+
+
+class EmbedGPTBigCode(nn.Module):
+    """GPT-BigCode (MQA, learned absolute positions, LayerNorm, GELU MLP) returning hidden states."""
+
+    def __init__(self, vocab=49152, emb_dim=6144, nheads=48, nlayers=52, max_pos=8192, hidden_mult=4, eps=1e-5, **_):
+        super().__init__()
+        self.emb = nn.Embedding(vocab, emb_dim)
+        self.pos = nn.Embedding(max_pos, emb_dim)
+        self.layers = nn.ModuleList([_GPTBigCodeBlock(emb_dim, nheads, hidden_mult * emb_dim, eps) for _ in range(nlayers)])
+        self.dec_norm = nn.LayerNorm(emb_dim, eps=eps)
+        self.head = nn.Linear(emb_dim, vocab, bias=False)
+
+    def forward(self, x, past_key_value_states=None, use_cache=False, include_embeds=False, **_):
+        past = past_key_value_states
+        p0 = 0 if past is None else past[0][0].size(1)
+        h = self.emb(x) + self.pos(torch.arange(p0, p0 + x.size(1), device=x.device))[None]
+        cache = []
+        for i, blk in enumerate(self.layers):
+            h, c = blk(h, None if past is None else past[i], use_cache)
+            cache.append(c)
+        embeds = self.dec_norm(h)
+        out = [self.head(embeds)] + ([cache] if use_cache else []) + ([embeds] if include_embeds else [])
+        return out[0] if len(out) == 1 else tuple(out)
+
+
+class _MoE(nn.Module):
+    def __init__(self, d, hidden, n_experts, top_k):
+        super().__init__()
+        self.top_k = top_k
+        self.gate = nn.Linear(d, n_experts, bias=False)
+        self.w1 = nn.Parameter(torch.empty(n_experts, 2 * hidden, d))
+        self.w2 = nn.Parameter(torch.empty(n_experts, d, hidden))
+        nn.init.trunc_normal_(self.w1, std=0.02); nn.init.trunc_normal_(self.w2, std=0.02)
+
+    def forward(self, x):
+        B, S, D = x.shape
+        xf = x.reshape(-1, D)
+        w, idx = torch.topk(torch.softmax(self.gate(xf).float(), -1), self.top_k, dim=-1)
+        w = (w / w.sum(-1, keepdim=True)).to(x.dtype)
+        out = torch.zeros_like(xf)
+        for e in range(self.w1.size(0)):
+            tok, slot = torch.where(idx == e)
+            if tok.numel() == 0:
+                continue
+            g, u = (xf[tok] @ self.w1[e].t()).chunk(2, dim=-1)
+            out.index_add_(0, tok, (F.silu(g) * u) @ self.w2[e].t() * w[tok, slot].unsqueeze(-1))
+        return out.view(B, S, D)
+
+
+class EmbedMixtral(EmbedLLaMA):
+    """Mixtral = the LLaMA block with a top-2-of-8 sparse MoE feed-forward; returns hidden states."""
+
+    def __init__(self, config: Optional[LLaMAConfig] = None, n_experts=8, top_k=2, **kw):
+        super().__init__(config, **kw)
+        for blk in self.layers:
+            blk.moe = _MoE(self.config.emb_dim, self.config.hidden_dim, n_experts, top_k)
+            del blk.ff_sub_layer
+
+    def forward(self, x, past_key_value_states=None, use_cache=False, include_embeds=False, **_):
+        B, S = x.shape
+        h = self.shared(x)
+        past = past_key_value_states
+        pos0 = 0 if past is None else past[0][0].size(1)
+        tab = self.rot_emb.table(h.device, pos0 + S)
+        cache = []
+        for li, blk in enumerate(self.layers):
+            a = blk.attn
+            qkv = a.in_proj.qkv_fused(blk.ln(h))
+            ops.kernels_for(qkv).rope_(qkv.view(B * S, -1), tab, S, a.nheads, a.kvheads, a.head_dim, a.head_dim, False, pos0)
+            t = qkv.view(B, S, a.nheads + 2 * a.kvheads, a.head_dim)
+            q, k, v = t[:, :, :a.nheads], t[:, :, a.nheads:a.nheads + a.kvheads], t[:, :, a.nheads + a.kvheads:]
+            if past is not None:
+                k, v = torch.cat([past[li][0], k], 1), torch.cat([past[li][1], v], 1)
+            cache.append((k, v))
+            ctx = F.scaled_dot_product_attention(q.transpose(1, 2), k.transpose(1, 2), v.transpose(1, 2),
+                                                 is_causal=(past is None), enable_gqa=(a.kvheads != a.nheads))
+            h = a.dense(ctx.transpose(1, 2).reshape(B, S, -1), residual=h)
+            h = h + blk.moe(blk.ff_ln(h))
+        embeds = self.dec_norm(h)
+        out = [self.shared(embeds, reverse=True)] + ([cache] if use_cache else []) + ([embeds] if include_embeds else [])
+        return out[0] if len(out) == 1 else tuple(out)
+
+
+_REGISTRY = {
+    ("embedllama", "7b"): lambda: EmbedLLaMA(LLaMAConfig(hidden_grow_factor=11008 / 4096, kvheads=32)),
+    ("embedllama", "8b"): lambda: EmbedLLaMA(LLaMAConfig(src_vocab_size=128256, emb_dim=4096, nheads=32, kvheads=8,
+                                                         nlayers=32, hidden_grow_factor=3.5, max_expected_seq_len=8192,
+                                                         rope_theta=500000.0)),
+    ("embedgpt_bigcode", "20b"): lambda: EmbedGPTBigCode(),
+    ("embedmixtral", "8x7b"): lambda: EmbedMixtral(LLaMAConfig(emb_dim=4096, nheads=32, kvheads=8, nlayers=32,
+                                                               hidden_grow_factor=14336 / 4096, max_expected_seq_len=32768,
+                                                               rope_theta=1e6)),
+}
+
+
+def register_model(arch: str, variant: str, factory: Callable[[], nn.Module]):
+    _REGISTRY[(arch, variant)] = factory
+
+
+def get_model(arch: str, variant: str, model_path: Optional[str] = None, device_type="cuda", source="hf",
+              distributed_strategy=None, group=None, dtype=torch.bfloat16):
+    """Stand-in for ``fms.models.get_model``: build a registered base model and (for ``source='hf'`` Llama
+    checkpoints) load weights; ``distributed_strategy='tp'`` shards it over ``group``."""
+    dev = torch.device(device_type, torch.cuda.current_device()) if device_type == "cuda" else torch.device("cpu")
+    if model_path and arch == "embedllama" and os.path.exists(os.path.join(model_path, "config.json")):
+        from fms_fsdp_b200.models.hf_loader import load_hf_llama
+        model = load_hf_llama(model_path, "cpu", dtype, EmbedLLaMA)
+    else:
+        if (arch, variant) not in _REGISTRY:
+            raise KeyError(f"unknown model {arch}.{variant}; registered: {sorted(_REGISTRY)}")
+        with torch.device("meta"):
+            model = _REGISTRY[(arch, variant)]()
+        model.to_empty(device="cpu")
+        if hasattr(model, "reset_parameters"):
+            model.reset_parameters()
+        model = model.to(dtype)
+    if distributed_strategy == "tp" and group is not None and dist.get_world_size(group) > 1:
+        from fms_fsdp_b200.parallel.tensor_parallel import shard_llama_for_tp
+        model = shard_llama_for_tp(model, group)
+    model = model.to(dev)
+    for p in model.parameters():
+        p.requires_grad_(False)
+    return model
+
+
+# ---------------------------------------------------------------------------------- generation
+def generate(model: Union[Callable, nn.Module], input_ids: torch.Tensor, max_seq_len: int = 2048,
+             max_new_tokens: int = 256, temperature: float = 1.0, top_k: int = 10, do_sample: bool = True,
+             num_beams: int = 1, use_cache: bool = False, contiguous_cache: bool = False, include_embeds: bool = True):
+    """Autoregressive decoding that can also return the embedding vector of every produced position
+    (reference ``:28-118``)."""
+    if num_beams != 1:
+        raise NotImplementedError("generate() does yet not support beam search")
+    if not isinstance(input_ids, torch.Tensor):
+        raise RuntimeError("generate() requires a tensor of token ids as the prefix")
+    batched = input_ids.dim() != 1
+    if not batched:
+        input_ids = input_ids.unsqueeze(0)
+    result, next_input, embeds = input_ids, input_ids, None
+    kwargs: MutableMapping[str, Any] = dict(past_key_value_states=None, use_cache=use_cache, include_embeds=include_embeds)
+    for _ in range(max_new_tokens):
+        out = model(next_input[:, -max_seq_len:], **kwargs)
+        if not use_cache and not include_embeds:
+            logits = out
+        else:
+            logits = out[0]
+            if include_embeds:
+                z = out[-1]
+            if use_cache:
+                kwargs["past_key_value_states"] = out[1]
+        logits = logits[:, -1, :]
+        if do_sample:
+            logits = logits.float() / temperature
+            if top_k:
+                v, _ = torch.topk(logits, top_k)
+                logits[logits < v[:, [-1]]] = -float("inf")
+            next_val = torch.multinomial(F.softmax(logits, dim=-1), num_samples=1)
+        else:
+            next_val = torch.argmax(logits, dim=-1, keepdim=True)
+        result = torch.cat((result, next_val), dim=-1)
+        next_input = next_val if use_cache else result
+        if include_embeds:
+            embeds = z if embeds is None else torch.cat((embeds, z), dim=-2)
+    if not batched:
+        result = result[0]
+    return (result, embeds) if include_embeds else result
+
+
+# -------------------------------------------------------------------------------------- losses
+def _tp_chunk(cfg, t, mesh):
+    if cfg.sharding_strategy == "tp" and mesh is not None:
+        return t.chunk(mesh["tp"].size())[mesh["tp"].get_local_rank()]
+    return t
+
+
+def _head_losses(preds, targets_of, loss_fn, ddp_stats):
+    losses = []
+    for i in range(preds.size(0)):
+        targ = targets_of(i, preds.size(2))
+        l = loss_fn(preds[i].reshape(-1, preds.size(3)).float(), targ.long().reshape(-1))
+        losses.append(l)
+        ddp_stats[2 + i] += l.detach()
+    return sum(losses)
+
+
+def stage1_loss(cfg, model, speculator, base_model_input, input, loss_fn, ddp_stats, base_model_mesh):
+    """Stage 1: embeddings from ONE parallel forward of the frozen base model on ground-truth text; head i
+    predicts token n+2+i (reference ``:122-171``)."""
+    with torch.no_grad():
+        _, embeds = model(base_model_input[:, : -speculator.n_predict - 1], include_embeds=True, use_cache=False)
+    embeds = _tp_chunk(cfg, embeds, base_model_mesh)
+    preds = speculator(embeds.detach(), input[:, 1:])
+    loss = _head_losses(preds, lambda i, n: input[:, i + 2: n + i + 2], loss_fn, ddp_stats)
+    return loss, ddp_stats, input.numel()
+
+
+def stage2_loss(cfg, model, speculator, base_model_input, input, loss_fn, ddp_stats, base_model_mesh):
+    """Stage 2: the base model *generates* (sampling, KV cache) from short prompts and the speculator is
+    trained to match the generated continuation (reference ``:175-242``)."""
+    with torch.no_grad():
+        grow = cfg.stage2_batch_size // cfg.batch_size
+        assert cfg.stage2_prompt_length * grow <= cfg.seq_length, "Error: batch is too small for specified partition"
+        prompts = base_model_input[:, : cfg.stage2_prompt_length * grow].reshape(
+            base_model_input.size(0) * grow, cfg.stage2_prompt_length)
+        targs, embeds = generate(model, prompts, cfg.seq_length, cfg.stage2_seq_length, do_sample=True, use_cache=True,
+                                 include_embeds=True)
+        targs, embeds = _tp_chunk(cfg, targs, base_model_mesh), _tp_chunk(cfg, embeds, base_model_mesh)
+        targs = targs[:, -cfg.stage2_seq_length:]
+        embeds = embeds[:, -cfg.stage2_seq_length: -speculator.n_predict]
+    preds = speculator(embeds.detach(), targs[:, :-1].detach())
+    loss = _head_losses(preds, lambda i, n: targs[:, i + 1: n + i + 1], loss_fn, ddp_stats)
+    return loss, ddp_stats, targs.numel()
+
+
+def do_ckpt(ckpt_save_path, reset=False):
+    """On-demand checkpoint trigger: ``echo 1 > <ckpt_save_path>/do_ckpt``."""
+    cmd = ckpt_save_path + "/do_ckpt"
+    if not os.path.exists(cmd):
+        return False
+    if reset:
+        with open(cmd, "w") as fd:
+            fd.write("0")
+        return False
+    with open(cmd) as fd:
+        return fd.read().strip() == "1"
+
+
+# ---------------------------------------------------------------------------------------- loop
+def train_speculator(cfg, model, speculator, local_rank, rank, train_loader, optimizer, scheduler, checkpointer,
+                     start_step: int = 0, n_tok: int = 0, profiler=None, base_model_mesh=None):
+    """Speculator training loop; ``speculator`` is a ``ShardedModel`` (NO_SHARD) around ``MLPSpeculator``."""
+    model.eval()
+    speculator.train()
+    device = speculator.device
+    is_cuda = device.type == "cuda"
+    n_predict = speculator.module.n_predict
+    ddp_stats = torch.zeros(2 + n_predict, device=device)
+    start = loop_start = time.time()
+    loss_fn = nn.CrossEntropyLoss()
+    elapsed_tokens, step_tok = 0, 0
+    world_size = int(os.environ.get("WORLD_SIZE", 1))
+    for batch_idx, input in enumerate(train_loader, start=start_step + 1):
+        if batch_idx > cfg.num_steps:
+            break
+        input = input.to(device)
+        if cfg.sharding_strategy == "tp" and base_model_mesh is not None:
+            tp = base_model_mesh["tp"]
+            base_model_input = torch.zeros(tp.size() * input.size(0), input.size(1), dtype=input.dtype, device=device)
+            dist.all_gather_into_tensor(base_model_input, input, group=tp.get_group())
+        else:
+            base_model_input = input
+        optimizer.zero_grad()
+        stage = stage1_loss if batch_idx <= cfg.stage2_start_step else stage2_loss
+        holder = {}
+
+        def closure(spec_module):
+            loss, _, holder["tok"] = stage(cfg, model, spec_module, base_model_input, input, loss_fn, ddp_stats,
+                                           base_model_mesh)
+            return loss
+
+        speculator.forward_backward_custom(closure)
+        step_tok = holder["tok"]
+        ddp_stats[0] += speculator.clip_grad_norm_(cfg.grad_clip_thresh)
+        optimizer.step()
+        scheduler.step()
+        ddp_stats[1] += 1
+        if profiler:
+            profiler.step()
+
+        if batch_idx % cfg.report_interval == 0:
+            if world_size > 1:
+                dist.all_reduce(ddp_stats, op=dist.ReduceOp.SUM)
+            train_loss = ddp_stats[2:] / ddp_stats[1]
+            g_norm = ddp_stats[0] / ddp_stats[1]
+            elapsed_time = time.time() - loop_start
+            elapsed_tokens += cfg.report_interval * world_size * step_tok
+            if rank == 0:
+                print(f"{time.time()}")
+                print("step:", batch_idx)
+                print("tokens seen:", n_tok + elapsed_tokens)
+                for i in range(len(train_loss)):
+                    print(f"loss {i + 1}:", train_loss[i].item())
+                print("gradient norm:", g_norm.item())
+                print(f"speed for these {cfg.report_interval} steps:", (time.time() - start) / cfg.report_interval)
+                print("overall speed:", elapsed_time / (batch_idx - start_step))
+                print("LR:", scheduler.get_last_lr())
+                print("reserved memory:", torch.cuda.max_memory_reserved(device) if is_cuda else 0)
+                print("active memory:", torch.cuda.max_memory_allocated(device) if is_cuda else 0)
+                print("overall token per gpu per sec:", int(elapsed_tokens / world_size / elapsed_time))
+                print("token per day:", int(elapsed_tokens / elapsed_time * 3600 * 24))
+                print()
+            start = time.time()
+            ddp_stats.zero_()
+        if is_cuda:
+            torch.cuda.reset_peak_memory_stats(device)
+
+        if batch_idx % cfg.checkpoint_interval == 0 or batch_idx == cfg.num_steps or do_ckpt(cfg.ckpt_save_path) is True:
+            if is_cuda:
+                torch.cuda.empty_cache()
+            checkpointer.save(batch_idx, speculator, optimizer, train_loader if hasattr(train_loader, "dataset") else None,
+                              tokens_seen=elapsed_tokens + n_tok)
+            do_ckpt(cfg.ckpt_save_path, reset=True)
+    return ddp_stats
