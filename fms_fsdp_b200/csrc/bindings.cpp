@@ -10,6 +10,8 @@
 #define DECL extern "C"
 DECL int b200_gemm_bf16(const void*, const void*, void*, const void*, int, int, int, int, int, int, int, int, int, int,
                         int, cudaStream_t);
+DECL int b200_gemm2_bf16(const void*, const void*, void*, const void*, int, int, int, int, int, int, int, int, int, int,
+                         int, cudaStream_t);
 DECL int b200_rmsnorm_fwd(const void*, const void*, void*, float*, int, int, float, cudaStream_t);
 DECL int b200_rmsnorm_bwd_grid(int);
 DECL int b200_rmsnorm_bwd(const void*, const void*, const void*, const float*, void*, float*, float*, int, int,
@@ -39,6 +41,7 @@ DECL int b200_causal_conv1d_bwd(const void*, const void*, const void*, const voi
 namespace {
 
 static int64_t g_launches = 0;
+static bool g_gemm_2cta = true;
 
 inline cudaStream_t cur_stream() { return at::cuda::getCurrentCUDAStream().stream(); }
 
@@ -88,6 +91,13 @@ void gemm(const at::Tensor& a, const at::Tensor& b, at::Tensor& c, int64_t layou
     need_rowmajor2d(*residual, "residual");
     r = residual->data_ptr();
     ldr = residual->stride(0);
+  }
+  // CTA-pair kernel (cta_group::2, 256x256 tiles) for anything with at least one full pair tile of rows
+  if (g_gemm_2cta && M >= 256) {
+    check(b200_gemm2_bf16(a.data_ptr(), b.data_ptr(), c.data_ptr(), r, M, N, K, a.stride(0), b.stride(0), c.stride(0),
+                          ldr, a_mn, b_mn, (int)epi, c.scalar_type() == at::kFloat ? 1 : 0, cur_stream()),
+          "gemm2_bf16_tcgen05");
+    return;
   }
   check(b200_gemm_bf16(a.data_ptr(), b.data_ptr(), c.data_ptr(), r, M, N, K, a.stride(0), b.stride(0), c.stride(0),
                        ldr, a_mn, b_mn, (int)epi, c.scalar_type() == at::kFloat ? 1 : 0, cur_stream()),
@@ -302,6 +312,8 @@ std::vector<at::Tensor> causal_conv1d_bwd(const at::Tensor& dy, const at::Tensor
   return {dx, dw, db};
 }
 
+void set_gemm_2cta(bool on) { g_gemm_2cta = on; }
+bool get_gemm_2cta() { return g_gemm_2cta; }
 int64_t launch_count() { return g_launches; }
 void reset_launch_count() { g_launches = 0; }
 
@@ -329,6 +341,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("signal_barrier", &signal_barrier);
   m.def("causal_conv1d_fwd", &causal_conv1d_fwd);
   m.def("causal_conv1d_bwd", &causal_conv1d_bwd);
+  m.def("set_gemm_2cta", &set_gemm_2cta);
+  m.def("get_gemm_2cta", &get_gemm_2cta);
   m.def("launch_count", &launch_count);
   m.def("reset_launch_count", &reset_launch_count);
 }

@@ -1,0 +1,281 @@
+// 2-CTA (cta_group::2) persistent bf16 GEMM for sm_100a: a cluster of two CTAs computes a 256x256 output
+// tile with ONE tcgen05.mma stream issued by the leader CTA.  Each CTA stages 128 rows of A and 128 of the
+// 256 B rows per k-block (32 KiB/stage instead of 48 KiB) -- the single-CTA kernel in gemm_sm100.cu is
+// shared-memory-bandwidth bound (TMA writes + UMMA operand reads = 192 B/clk/SM > 128 B/clk); pairing halves
+// the B traffic per SM (128 B/clk) and lets the ring go 6 stages deep.
+//
+// Same operand layouts / epilogues / warp roles as gemm_sm100.cu.  Differences:
+//   * __cluster_dims__(2,1,1); TMEM allocated with cta_group::2; TMA loads use the cta_group::2 form so the
+//     bytes of BOTH CTAs complete on the leader's "full" barrier;
+//   * only the leader's warp 1 issues MMAs; tcgen05.commit multicasts to the "empty"/"accumulator full"
+//     barriers of both CTAs; both CTAs' epilogue warps arrive on the leader's "accumulator empty" barrier.
+#include "common.cuh"
+#include "tensormap.h"
+
+namespace b200 {
+
+constexpr int P_BM = 256;       // rows per CTA pair
+constexpr int C_BM = 128;       // rows per CTA
+constexpr int P_BN = 256;       // tile columns
+constexpr int C_BN = 128;       // B rows staged per CTA
+constexpr int P_BK = 64;
+constexpr int P_STAGES = 6;
+constexpr int PA_BYTES = C_BM * P_BK * 2;   // 16 KiB
+constexpr int PB_BYTES = C_BN * P_BK * 2;   // 16 KiB
+constexpr int P_STAGE_BYTES = PA_BYTES + PB_BYTES;
+constexpr int P_THREADS = 192;
+constexpr int P_SMEM = P_STAGES * P_STAGE_BYTES + 1024 + 256;
+
+enum { P_EPI_STORE = 0, P_EPI_RESIDUAL = 1, P_EPI_ACCUM = 2 };
+
+struct Gemm2Params {
+  int M, N, K;
+  int ldc, ldr;
+  void* C;
+  const void* R;
+  int m_tiles, n_tiles;  // in units of 256 x 256
+};
+
+template <bool A_MN, bool B_MN, int EPI, typename OutT>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(P_THREADS, 1)
+gemm2_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, Gemm2Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* bar_base = smem + P_STAGES * P_STAGE_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(bar_base);   // leader's copy is the one in use
+  uint64_t* empty_bar = full_bar + P_STAGES;                    // per CTA
+  uint64_t* tfull_bar = empty_bar + P_STAGES;                   // per CTA
+  uint64_t* tempty_bar = tfull_bar + 2;                         // leader's copy is the one in use
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+  const int num_kb = (p.K + P_BK - 1) / P_BK;
+  const int num_tiles = p.m_tiles * p.n_tiles;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < P_STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull_bar[a], 1);
+      mbar_init(&tempty_bar[a], 8);  // 4 epilogue warps x 2 CTAs
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc_2cta(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();   // both CTAs' barriers are initialised before anyone signals across the pair
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer (one per CTA: its own A rows and its half of B) =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = pair; t < num_tiles; t += n_pairs) {
+        const int m0 = (t % p.m_tiles) * P_BM + (int)rank * C_BM;
+        const int n0 = (t / p.m_tiles) * P_BN + (int)rank * C_BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * P_STAGE_BYTES;
+          uint8_t* sb = sa + PA_BYTES;
+          if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * P_STAGE_BYTES);
+          const int k0 = kb * P_BK;
+          if constexpr (!A_MN) {
+            tma_load_2d_2cta(sa, &tmA, &full_bar[stage], k0, m0);
+          } else {
+#pragma unroll
+            for (int j = 0; j < C_BM / 64; ++j)
+              tma_load_2d_2cta(sa + j * (64 * P_BK * 2), &tmA, &full_bar[stage], m0 + 64 * j, k0);
+          }
+          if constexpr (!B_MN) {
+            tma_load_2d_2cta(sb, &tmB, &full_bar[stage], k0, n0);
+          } else {
+#pragma unroll
+            for (int j = 0; j < C_BN / 64; ++j)
+              tma_load_2d_2cta(sb + j * (64 * P_BK * 2), &tmB, &full_bar[stage], n0 + 64 * j, k0);
+          }
+          if (++stage == P_STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (leader) {
+      constexpr uint32_t idesc = make_idesc_bf16(P_BM, P_BN, A_MN, B_MN);
+      int stage = 0, acc = 0;
+      uint32_t phase = 0, acc_phase = 0;
+      for (int t = pair; t < num_tiles; t += n_pairs) {
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * P_BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          if (lane == 0) {
+            const uint32_t sa = smem_u32(smem + stage * P_STAGE_BYTES);
+            const uint32_t sb = sa + PA_BYTES;
+#pragma unroll
+            for (int k = 0; k < P_BK / 16; ++k) {
+              uint64_t adesc, bdesc;
+              if constexpr (!A_MN) adesc = make_smem_desc(sa + k * 32, 0, 1024);
+              else                 adesc = make_smem_desc(sa + k * 2048, 64 * P_BK * 2, 1024);
+              if constexpr (!B_MN) bdesc = make_smem_desc(sb + k * 32, 0, 1024);
+              else                 bdesc = make_smem_desc(sb + k * 2048, 64 * P_BK * 2, 1024);
+              umma_bf16_ss_2cta(tmem_d, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+            }
+            umma_commit_2cta_mcast(&empty_bar[stage], 0x3);
+            if (kb == num_kb - 1) umma_commit_2cta_mcast(&tfull_bar[acc], 0x3);
+          }
+          __syncwarp();
+          if (++stage == P_STAGES) { stage = 0; phase ^= 1; }
+        }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // ===================== epilogue (both CTAs: own 128 accumulator lanes) =====================
+    const int q = warp & 3;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int t = pair; t < num_tiles; t += n_pairs) {
+      const int m0 = (t % p.m_tiles) * P_BM + (int)rank * C_BM;
+      const int n0 = (t / p.m_tiles) * P_BN;
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const int row = m0 + q * 32 + lane;
+      const bool row_ok = row < p.M;
+      OutT* crow = reinterpret_cast<OutT*>(p.C) + static_cast<size_t>(row) * p.ldc;
+      const __nv_bfloat16* rrow = reinterpret_cast<const __nv_bfloat16*>(p.R) + static_cast<size_t>(row) * p.ldr;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * P_BN;
+#pragma unroll 1
+      for (int c = 0; c < P_BN; c += 64) {
+        uint32_t v0[32], v1[32];
+        tmem_ld_32x32b_x32(taddr + c, v0);
+        tmem_ld_32x32b_x32(taddr + c + 32, v1);
+        tmem_ld_wait();
+        const int col = n0 + c;
+        if (row_ok && col < p.N) {
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            uint32_t* v = h ? v1 : v0;
+            const int cb = col + 32 * h;
+            if (cb >= p.N) break;
+            if constexpr (sizeof(OutT) == 2) {
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                if (cb + g * 8 >= p.N) break;
+                float f[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(v[g * 8 + i]);
+                if constexpr (EPI != P_EPI_STORE) {
+                  const __nv_bfloat16* src = (EPI == P_EPI_RESIDUAL) ? (rrow + cb + g * 8)
+                                                                     : (reinterpret_cast<const __nv_bfloat16*>(crow) + cb + g * 8);
+                  uint4 r = *reinterpret_cast<const uint4*>(src);
+                  float2 a = unpack_bf16x2(r.x), b = unpack_bf16x2(r.y), c2 = unpack_bf16x2(r.z), d = unpack_bf16x2(r.w);
+                  f[0] += a.x; f[1] += a.y; f[2] += b.x; f[3] += b.y; f[4] += c2.x; f[5] += c2.y; f[6] += d.x; f[7] += d.y;
+                }
+                uint4 o;
+                o.x = pack_bf16x2(f[0], f[1]); o.y = pack_bf16x2(f[2], f[3]);
+                o.z = pack_bf16x2(f[4], f[5]); o.w = pack_bf16x2(f[6], f[7]);
+                *reinterpret_cast<uint4*>(crow + cb + g * 8) = o;
+              }
+            } else {
+#pragma unroll
+              for (int g = 0; g < 8; ++g) {
+                if (cb + g * 4 >= p.N) break;
+                float4 o;
+                o.x = __uint_as_float(v[g * 4 + 0]); o.y = __uint_as_float(v[g * 4 + 1]);
+                o.z = __uint_as_float(v[g * 4 + 2]); o.w = __uint_as_float(v[g * 4 + 3]);
+                if constexpr (EPI == P_EPI_RESIDUAL) {
+                  uint2 r = *reinterpret_cast<const uint2*>(rrow + cb + g * 4);
+                  float2 a = unpack_bf16x2(r.x), b = unpack_bf16x2(r.y);
+                  o.x += a.x; o.y += a.y; o.z += b.x; o.w += b.y;
+                } else if constexpr (EPI == P_EPI_ACCUM) {
+                  float4 r = *reinterpret_cast<const float4*>(crow + cb + g * 4);
+                  o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+                }
+                *reinterpret_cast<float4*>(crow + cb + g * 4) = o;
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_leader(&tempty_bar[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // the peer may still be reading our smem / signalling our barriers
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_2cta(tmem_base, 512);
+  }
+}
+
+template <bool A_MN, bool B_MN, int EPI, typename OutT>
+static int launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gemm2Params& p, cudaStream_t stream) {
+  auto kern = gemm2_bf16_tcgen05<A_MN, B_MN, EPI, OutT>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM);
+    if (e != cudaSuccess) return (int)e;
+    configured = true;
+  }
+  int tiles = p.m_tiles * p.n_tiles;
+  int pairs = sm_count() / 2;
+  if (tiles < pairs) pairs = tiles;
+  kern<<<pairs * 2, P_THREADS, P_SMEM, stream>>>(tmA, tmB, p);
+  return (int)cudaGetLastError();
+}
+
+template <bool A_MN, bool B_MN>
+static int dispatch2(const CUtensorMap& a, const CUtensorMap& b, const Gemm2Params& p, int epi, int out_fp32,
+                     cudaStream_t s) {
+  if (out_fp32) {
+    if (epi == P_EPI_STORE) return launch2<A_MN, B_MN, P_EPI_STORE, float>(a, b, p, s);
+    if (epi == P_EPI_RESIDUAL) return launch2<A_MN, B_MN, P_EPI_RESIDUAL, float>(a, b, p, s);
+    return launch2<A_MN, B_MN, P_EPI_ACCUM, float>(a, b, p, s);
+  }
+  if (epi == P_EPI_STORE) return launch2<A_MN, B_MN, P_EPI_STORE, __nv_bfloat16>(a, b, p, s);
+  if (epi == P_EPI_RESIDUAL) return launch2<A_MN, B_MN, P_EPI_RESIDUAL, __nv_bfloat16>(a, b, p, s);
+  return launch2<A_MN, B_MN, P_EPI_ACCUM, __nv_bfloat16>(a, b, p, s);
+}
+
+}  // namespace b200
+
+extern "C" int b200_gemm2_bf16(const void* A, const void* B, void* C, const void* R, int M, int N, int K, int lda,
+                               int ldb, int ldc, int ldr, int a_mn, int b_mn, int epi, int out_fp32,
+                               cudaStream_t stream) {
+  using namespace b200;
+  CUtensorMap tmA, tmB;
+  int rc;
+  if (!a_mn) rc = make_tmap_2d_bf16(&tmA, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, P_BK, C_BM);
+  else       rc = make_tmap_2d_bf16(&tmA, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, 64, P_BK);
+  if (rc) return 1000 - rc;
+  if (!b_mn) rc = make_tmap_2d_bf16(&tmB, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, P_BK, C_BN);
+  else       rc = make_tmap_2d_bf16(&tmB, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, 64, P_BK);
+  if (rc) return 2000 - rc;
+  Gemm2Params p;
+  p.M = M; p.N = N; p.K = K; p.ldc = ldc; p.ldr = ldr; p.C = C; p.R = R;
+  p.m_tiles = (M + P_BM - 1) / P_BM;
+  p.n_tiles = (N + P_BN - 1) / P_BN;
+  if (a_mn) {
+    if (b_mn) return dispatch2<true, true>(tmA, tmB, p, epi, out_fp32, stream);
+    return dispatch2<true, false>(tmA, tmB, p, epi, out_fp32, stream);
+  }
+  if (b_mn) return dispatch2<false, true>(tmA, tmB, p, epi, out_fp32, stream);
+  return dispatch2<false, false>(tmA, tmB, p, epi, out_fp32, stream);
+}

@@ -21,6 +21,7 @@ _LAYOUT = {"nt": 0, "nn": 1, "tn": 2}
 # attention implementation: "tcgen05" (ours) | "sdpa" (library fallback, debugging only)
 ATTN_IMPL = os.environ.get("FMS_B200_ATTN_IMPL", "tcgen05")
 GEMM_IMPL = os.environ.get("FMS_B200_GEMM_IMPL", "tcgen05")  # "cublas" = library fallback, debugging only
+_C.set_gemm_2cta(os.environ.get("FMS_B200_GEMM_2CTA", "1") == "1")  # CTA-pair (cta_group::2) GEMM for M >= 256
 
 
 def launch_count() -> int:

@@ -50,6 +50,45 @@ def main(groups):
     torch.manual_seed(0)
     rec("env", device=torch.cuda.get_device_name(0), torch=torch.__version__)
 
+    if "gemm2" in groups:
+        # CTA-pair kernel vs single-CTA kernel vs cuBLAS on training shapes
+        for layout, (M, N, K) in [("nt", (8192, 12288, 4096)), ("nt", (8192, 22016, 4096)), ("nt", (8192, 4096, 11008)),
+                                  ("nn", (8192, 4096, 12288)), ("nn", (8192, 4096, 22016)), ("tn", (12288, 4096, 8192)),
+                                  ("tn", (22016, 4096, 8192)), ("nt", (256, 512, 128)), ("nn", (512, 768, 192)), ("tn", (1000, 520, 72))]:
+            try:
+                if layout == "nt":
+                    a = torch.randn(M, K, device=dev).bfloat16(); b = torch.randn(N, K, device=dev).bfloat16()
+                elif layout == "nn":
+                    a = torch.randn(M, K, device=dev).bfloat16(); b = torch.randn(K, N, device=dev).bfloat16()
+                else:
+                    a = torch.randn(K, M, device=dev).bfloat16(); b = torch.randn(K, N, device=dev).bfloat16()
+                ref = TK.gemm(a, b, layout).float()
+                r = dict(layout=layout, M=M, N=N, K=K)
+                for two in (True, False):
+                    CK._C.set_gemm_2cta(two)
+                    out = CK.gemm(a, b, layout)
+                    torch.cuda.synchronize()
+                    r["relerr_2cta" if two else "relerr_1cta"] = relerr(out, ref)
+                    if M >= 4096:
+                        ms = time_ms(lambda: CK.gemm(a, b, layout))
+                        r["tflops_2cta" if two else "tflops_1cta"] = 2 * M * N * K / ms / 1e9
+                if M >= 4096:
+                    ms = time_ms(lambda: TK.gemm(a, b, layout))
+                    r["tflops_cublas"] = 2 * M * N * K / ms / 1e9
+                CK._C.set_gemm_2cta(True)
+                rec("gemm2", **r)
+            except Exception as ex:
+                rec("gemm2", layout=layout, M=M, N=N, K=K, ok=False, error=repr(ex)[:400])
+        try:
+            M, N, K = 512, 768, 256
+            a = torch.randn(M, K, device=dev).bfloat16(); b = torch.randn(N, K, device=dev).bfloat16()
+            r_ = torch.randn(M, N, device=dev).bfloat16(); ref = a.float() @ b.float().t()
+            rec("gemm2_residual", relerr=relerr(CK.gemm(a, b, "nt", residual=r_), ref + r_.float()))
+            c = torch.randn(M, N, device=dev); c0 = c.clone(); CK.gemm(a, b, "nt", out=c, accumulate=True)
+            rec("gemm2_accum_f32", relerr=relerr(c, ref + c0))
+        except Exception as ex:
+            rec("gemm2_epilogues", ok=False, error=repr(ex)[:400])
+
     if "gemm" in groups:
         shapes = [(128, 256, 64), (256, 512, 256), (384, 768, 192), (8, 8, 8), (1000, 520, 72),
                   (2048, 4096, 4096), (8192, 12288, 4096)]
