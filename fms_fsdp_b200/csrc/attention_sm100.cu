@@ -274,6 +274,261 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm, __nv_bfloat16* __restric
   }
 }
 
+// ===================================================================================== forward v2
+// Two 128-row Q tiles per CTA ("ping-pong"): the tiles share every K/V load, each has its own softmax
+// warpgroup, and P never touches shared memory -- it is written back into the TMEM columns of S (two bf16 per
+// 32-bit column, row per lane) and consumed by the PV GEMM through tcgen05.mma's TMEM-A operand form.  While one
+// tile's softmax runs, the tensor core works on the other tile's QK^T / PV.
+//   TMEM: S0/P0 [0,128)  S1/P1 [128,256)  O0 [256,256+HD)  O1 [384,384+HD)
+//   smem: Q 2 x tile, K 2 stages, V 2 stages  (192 KiB at HD=128)
+//   warps: 0 TMA, 1 MMA, 2-3 idle, 4-7 softmax tile 0, 8-11 softmax tile 1   (384 threads)
+constexpr int ATT2_THREADS = 384;
+
+template <int HD>
+struct Fwd2Cfg {
+  static constexpr int NCH = HD / 64;
+  static constexpr int TILE_BYTES = 128 * HD * 2;
+  static constexpr int SMEM = TILE_BYTES * (2 + 2 + 2) + 1024 + 256;
+};
+
+template <int HD>
+__global__ void __launch_bounds__(ATT2_THREADS, 1)
+attn_fwd2_kernel(const __grid_constant__ CUtensorMap tm, __nv_bfloat16* __restrict__ o, float* __restrict__ lse,
+                 int S, int H, int KVH, float scale_log2, int n_pt) {
+  using C = Fwd2Cfg<HD>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;                              // [2 tiles]
+  uint8_t* sK = sQ + 2 * C::TILE_BYTES;            // [2 stages]
+  uint8_t* sV = sK + 2 * C::TILE_BYTES;            // [2 stages]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + 2 * C::TILE_BYTES);
+  uint64_t* q_full = bars;
+  uint64_t* k_full = bars + 1;     // [2]
+  uint64_t* k_empty = bars + 3;    // [2]
+  uint64_t* v_full = bars + 5;     // [2]
+  uint64_t* v_empty = bars + 7;    // [2]
+  uint64_t* s_full = bars + 9;     // [2 tiles]
+  uint64_t* p_full = bars + 11;    // [2 tiles]
+  uint64_t* pv_done = bars + 13;   // [2 tiles]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int pt = n_pt - 1 - blockIdx.x;  // pair-tile index, heavy first
+  const int h = blockIdx.y, b = blockIdx.z;
+  const int kvh = h / (H / KVH);
+  const int row0 = b * S + pt * 256;
+  // kv tiles (128 rows): tile t of the pair attends kv tiles 0 .. 2*pt + t (clipped to the sequence)
+  const int n_kv_total = (S + 127) / 128;
+  const int n_kv[2] = {min(2 * pt + 1, n_kv_total), (pt * 256 + 128 < S) ? min(2 * pt + 2, n_kv_total) : 0};
+  const int n_it = max(n_kv[0], n_kv[1]);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm);
+    mbar_init(q_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1);
+      mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1);
+      mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 4); mbar_init(&pv_done[i], 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(q_full, 2 * C::TILE_BYTES);
+      for (int t = 0; t < 2; ++t)
+        for (int c = 0; c < C::NCH; ++c)
+          tma_load_2d(sQ + t * C::TILE_BYTES + c * 16384, &tm, q_full, h * HD + 64 * c, row0 + 128 * t);
+      for (int j = 0; j < n_it; ++j) {
+        const int st = j & 1;
+        const uint32_t ph = (j >> 1) & 1;
+        const int krow = b * S + j * 128;
+        mbar_wait(&k_empty[st], ph ^ 1);
+        mbar_arrive_expect_tx(&k_full[st], C::TILE_BYTES);
+        for (int c = 0; c < C::NCH; ++c)
+          tma_load_2d(sK + st * C::TILE_BYTES + c * 16384, &tm, &k_full[st], (H + kvh) * HD + 64 * c, krow);
+        mbar_wait(&v_empty[st], ph ^ 1);
+        mbar_arrive_expect_tx(&v_full[st], C::TILE_BYTES);
+        for (int c = 0; c < C::NCH; ++c)
+          tma_load_2d(sV + st * C::TILE_BYTES + c * 16384, &tm, &v_full[st], (H + KVH + kvh) * HD + 64 * c, krow);
+      }
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t idesc_qk = make_idesc_bf16(128, 128, false, false);
+    constexpr uint32_t idesc_pv = make_idesc_bf16(128, HD, false, true);
+    mbar_wait(q_full, 0);
+    // Tensor-pipe issue order (the pipe executes in issue order, which is what makes the S/P aliasing safe):
+    //   QK0_0 QK1_0 | PV0_0 QK0_1 PV1_0 QK1_1 | PV0_1 QK0_2 PV1_1 QK1_2 | ...
+    // QK_t(j+1) overwrites S_t only after PV_t(j) -- which reads P_t from the same TMEM columns -- was issued.
+    auto qk = [&](int t, int j) {
+      const uint32_t qa = smem_u32(sQ + t * C::TILE_BYTES), ka = smem_u32(sK + (j & 1) * C::TILE_BYTES);
+#pragma unroll
+      for (int kk = 0; kk < HD / 16; ++kk) {
+        const uint32_t off = (kk >> 2) * 16384 + (kk & 3) * 32;
+        umma_bf16_ss(tmem + t * 128, make_smem_desc(qa + off, 0, 1024), make_smem_desc(ka + off, 0, 1024), idesc_qk,
+                     kk != 0);
+      }
+      umma_commit(&s_full[t]);
+    };
+    mbar_wait(&k_full[0], 0);
+    tc_fence_after();
+    if (lane == 0) {
+      if (0 < n_kv[0]) qk(0, 0);
+      if (0 < n_kv[1]) qk(1, 0);
+      umma_commit(&k_empty[0]);
+    }
+    __syncwarp();
+    for (int j = 0; j < n_it; ++j) {
+      const int st = j & 1;
+      const bool next = j + 1 < n_it;
+      mbar_wait(&v_full[st], (j >> 1) & 1);
+      if (next) mbar_wait(&k_full[(j + 1) & 1], ((j + 1) >> 1) & 1);
+      for (int t = 0; t < 2; ++t) {
+        if (j < n_kv[t]) {
+          mbar_wait(&p_full[t], j & 1);
+          tc_fence_after();
+          if (lane == 0) {
+            const uint32_t va = smem_u32(sV + st * C::TILE_BYTES);
+#pragma unroll
+            for (int k = 0; k < 8; ++k)  // 16 kv rows per step; P: 8 packed TMEM columns per step
+              umma_bf16_ts(tmem + 256 + t * 128, tmem + t * 128 + k * 8, make_smem_desc(va + k * 2048, 16384, 1024),
+                           idesc_pv, (j | k) != 0);
+            umma_commit(&pv_done[t]);
+          }
+          __syncwarp();
+        }
+        if (next && j + 1 < n_kv[t]) {
+          if (lane == 0) qk(t, j + 1);
+          __syncwarp();
+        }
+      }
+      if (lane == 0) {
+        umma_commit(&v_empty[st]);
+        if (next) umma_commit(&k_empty[(j + 1) & 1]);
+      }
+      __syncwarp();
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------ softmax warpgroup of tile t (row owner = TMEM lane)
+    const int t = (warp - 4) >> 2;
+    const int q4 = warp & 3;
+    const int r = q4 * 32 + lane;
+    const int q_idx = pt * 256 + t * 128 + r;
+    const uint32_t lane_addr = static_cast<uint32_t>(q4 * 32) << 16;
+    const uint32_t tS = tmem + t * 128 + lane_addr;
+    const uint32_t tO = tmem + 256 + t * 128 + lane_addr;
+    const int nk = n_kv[t];
+    float m_ref = -INFINITY, l_sum = 0.f;
+    for (int j = 0; j < nk; ++j) {
+      mbar_wait(&s_full[t], j & 1);
+      tc_fence_after();
+      const bool diag = (j == 2 * pt + t);
+      const int kv0 = j * 128;
+      uint32_t v[128];
+      tmem_ld_32x32b_x32(tS, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
+      tmem_ld_32x32b_x32(tS + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
+      tmem_ld_32x32b_x32(tS + 64, *reinterpret_cast<uint32_t(*)[32]>(&v[64]));
+      tmem_ld_32x32b_x32(tS + 96, *reinterpret_cast<uint32_t(*)[32]>(&v[96]));
+      tmem_ld_wait();
+      float mx = -INFINITY;
+      if (diag || kv0 + 128 > S) {
+#pragma unroll
+        for (int i = 0; i < 128; ++i) {
+          const int kv = kv0 + i;
+          float x = __uint_as_float(v[i]) * scale_log2;
+          if (kv > q_idx || kv >= S) x = -INFINITY;
+          v[i] = __float_as_uint(x);
+          mx = fmaxf(mx, x);
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 128; ++i) {
+          const float x = __uint_as_float(v[i]) * scale_log2;
+          v[i] = __float_as_uint(x);
+          mx = fmaxf(mx, x);
+        }
+      }
+      const float m_new = fmaxf(m_ref, mx);
+      const bool grow = (m_new - m_ref) > 8.f;
+      if (j == 0) {
+        m_ref = m_new;
+      } else if (__any_sync(0xffffffffu, grow)) {
+        mbar_wait(&pv_done[t], (j - 1) & 1);   // O_t is stable only once PV_t of the previous tile retired
+        tc_fence_after();
+        const float f = exp2f(m_ref - m_new);
+        l_sum *= f;
+        m_ref = m_new;
+#pragma unroll 1
+        for (int c = 0; c < HD; c += 32) {
+          uint32_t ov[32];
+          tmem_ld_32x32b_x32(tO + c, ov);
+          tmem_ld_wait();
+          uint32_t w0[16], w1[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            w0[i] = __float_as_uint(__uint_as_float(ov[i]) * f);
+            w1[i] = __float_as_uint(__uint_as_float(ov[16 + i]) * f);
+          }
+          tmem_st_32x32b_x16(tO + c, w0);
+          tmem_st_32x32b_x16(tO + c + 16, w1);
+        }
+      }
+      // P = 2^(x - m_ref) packed two bf16 per column, written over S's own columns (in order => no hazard)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t w[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float p0 = exp2f(__uint_as_float(v[c * 32 + 2 * i]) - m_ref);
+          const float p1 = exp2f(__uint_as_float(v[c * 32 + 2 * i + 1]) - m_ref);
+          l_sum += p0 + p1;
+          w[i] = pack_bf16x2(p0, p1);
+        }
+        tmem_st_32x32b_x16(tS + c * 16, w);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[t]);
+    }
+    if (nk > 0) {
+      mbar_wait(&pv_done[t], (nk - 1) & 1);
+      tc_fence_after();
+      if (q_idx < S) {
+        const float inv_l = 1.f / l_sum;
+        __nv_bfloat16* orow = o + (static_cast<size_t>(b) * S + q_idx) * (H * HD) + h * HD;
+#pragma unroll 1
+        for (int c = 0; c < HD; c += 32) {
+          uint32_t ov[32];
+          tmem_ld_32x32b_x32(tO + c, ov);
+          tmem_ld_wait();
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            uint4 u;
+            u.x = pack_bf16x2(__uint_as_float(ov[g * 8 + 0]) * inv_l, __uint_as_float(ov[g * 8 + 1]) * inv_l);
+            u.y = pack_bf16x2(__uint_as_float(ov[g * 8 + 2]) * inv_l, __uint_as_float(ov[g * 8 + 3]) * inv_l);
+            u.z = pack_bf16x2(__uint_as_float(ov[g * 8 + 4]) * inv_l, __uint_as_float(ov[g * 8 + 5]) * inv_l);
+            u.w = pack_bf16x2(__uint_as_float(ov[g * 8 + 6]) * inv_l, __uint_as_float(ov[g * 8 + 7]) * inv_l);
+            *reinterpret_cast<uint4*>(orow + c + g * 8) = u;
+          }
+        }
+        lse[(static_cast<size_t>(b) * H + h) * S + q_idx] = (m_ref + log2f(l_sum)) * LN2;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
 // ===================================================================================== backward prep
 // delta[b,h,s] = sum_d dO[b,s,h,d] * O[b,s,h,d]      (one warp per (row, head))
 __global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16* __restrict__ o,
@@ -591,9 +846,32 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv128, const __grid_cons
   }
 }
 
+static int g_attn_fwd_version = 2;
+
+template <int HD>
+static int launch_fwd2(const void* qkv, void* o, float* lse, int B, int S, int H, int KVH, float scale,
+                       cudaStream_t st) {
+  using C = Fwd2Cfg<HD>;
+  CUtensorMap tm;
+  const int W = (H + 2 * KVH) * HD;
+  if (make_tmap_2d_bf16(&tm, qkv, (uint64_t)W, (uint64_t)B * S, (uint64_t)W, 64, 128)) return -3;
+  auto kern = attn_fwd2_kernel<HD>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
+    if (e != cudaSuccess) return (int)e;
+    configured = true;
+  }
+  const int n_pt = (S + 255) / 256;
+  dim3 grid(n_pt, H, B);
+  kern<<<grid, ATT2_THREADS, C::SMEM, st>>>(tm, (__nv_bfloat16*)o, lse, S, H, KVH, scale * LOG2E, n_pt);
+  return (int)cudaGetLastError();
+}
+
 template <int HD>
 static int launch_fwd(const void* qkv, void* o, float* lse, int B, int S, int H, int KVH, float scale,
                       cudaStream_t st) {
+  if (g_attn_fwd_version == 2) return launch_fwd2<HD>(qkv, o, lse, B, S, H, KVH, scale, st);
   using C = FwdCfg<HD>;
   CUtensorMap tm;
   const int W = (H + 2 * KVH) * HD;
@@ -648,6 +926,7 @@ static int launch_bwd(const void* dout, const void* qkv, const void* o, const fl
 
 }  // namespace b200
 
+extern "C" void b200_attn_set_fwd_version(int v) { b200::g_attn_fwd_version = v; }
 extern "C" int b200_attn_fwd(const void* qkv, void* o, float* lse, int B, int S, int H, int KVH, int HD, float scale,
                              cudaStream_t st) {
   if (H % KVH) return -1;

@@ -12,6 +12,7 @@ DECL int b200_gemm_bf16(const void*, const void*, void*, const void*, int, int, 
                         int, cudaStream_t);
 DECL int b200_gemm2_bf16(const void*, const void*, void*, const void*, int, int, int, int, int, int, int, int, int, int,
                          int, cudaStream_t);
+DECL int b200_ts_mma_probe(const void*, const void*, float*, cudaStream_t);
 DECL int b200_rmsnorm_fwd(const void*, const void*, void*, float*, int, int, float, cudaStream_t);
 DECL int b200_rmsnorm_bwd_grid(int);
 DECL int b200_rmsnorm_bwd(const void*, const void*, const void*, const float*, void*, float*, float*, int, int,
@@ -26,6 +27,7 @@ DECL int b200_ce_grad_inplace(void*, const long long*, const float*, float*, int
 DECL int b200_adamw(float*, const void*, int, float*, float*, void*, long long, float, float, float, float, float,
                     float, float, const float*, cudaStream_t);
 DECL int b200_sumsq(const void*, int, long long, float*, cudaStream_t);
+DECL void b200_attn_set_fwd_version(int);
 DECL int b200_attn_fwd(const void*, void*, float*, int, int, int, int, int, float, cudaStream_t);
 DECL int b200_attn_bwd(const void*, const void*, const void*, const float*, void*, float*, int, int, int, int, int,
                        float, cudaStream_t);
@@ -312,8 +314,18 @@ std::vector<at::Tensor> causal_conv1d_bwd(const at::Tensor& dy, const at::Tensor
   return {dx, dw, db};
 }
 
+void set_attn_fwd_version(int64_t v) { b200_attn_set_fwd_version((int)v); }
 void set_gemm_2cta(bool on) { g_gemm_2cta = on; }
 bool get_gemm_2cta() { return g_gemm_2cta; }
+at::Tensor ts_mma_probe(const at::Tensor& a, const at::Tensor& b) {
+  c10::cuda::CUDAGuard guard(a.device());
+  need(a, "a", at::kBFloat16);
+  need(b, "b", at::kBFloat16);
+  TORCH_CHECK(a.is_contiguous() && b.is_contiguous() && a.size(0) == 128 && a.size(1) == 64 && b.size(0) == 64 && b.size(1) == 64);
+  auto d = at::empty({128, 64}, a.options().dtype(at::kFloat));
+  check(b200_ts_mma_probe(a.data_ptr(), b.data_ptr(), d.data_ptr<float>(), cur_stream()), "ts_mma_probe");
+  return d;
+}
 int64_t launch_count() { return g_launches; }
 void reset_launch_count() { g_launches = 0; }
 
@@ -341,8 +353,10 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("signal_barrier", &signal_barrier);
   m.def("causal_conv1d_fwd", &causal_conv1d_fwd);
   m.def("causal_conv1d_bwd", &causal_conv1d_bwd);
+  m.def("set_attn_fwd_version", &set_attn_fwd_version);
   m.def("set_gemm_2cta", &set_gemm_2cta);
   m.def("get_gemm_2cta", &get_gemm_2cta);
+  m.def("ts_mma_probe", &ts_mma_probe);
   m.def("launch_count", &launch_count);
   m.def("reset_launch_count", &reset_launch_count);
 }

@@ -28,6 +28,20 @@ constexpr int P_SMEM = P_STAGES * P_STAGE_BYTES + 1024 + 256;
 
 enum { P_EPI_STORE = 0, P_EPI_RESIDUAL = 1, P_EPI_ACCUM = 2 };
 
+
+// L2-friendly rasterisation: sweep all n-tiles for a band of GROUP_M m-tiles before moving to the next band, so the
+// band's A rows (GROUP_M x 256 x K) stay L2-resident while B streams through once per band.
+constexpr int P_GROUP_M = 8;
+B200_DEVINL void tile_coords2(int t, int m_tiles, int n_tiles, int& mt, int& nt) {
+  const int per_band = P_GROUP_M * n_tiles;
+  const int band = t / per_band;
+  const int first_m = band * P_GROUP_M;
+  const int band_m = min(P_GROUP_M, m_tiles - first_m);
+  const int r = t - band * per_band;
+  mt = first_m + r % band_m;
+  nt = r / band_m;
+}
+
 struct Gemm2Params {
   int M, N, K;
   int ldc, ldr;
@@ -81,8 +95,10 @@ gemm2_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       int stage = 0;
       uint32_t phase = 0;
       for (int t = pair; t < num_tiles; t += n_pairs) {
-        const int m0 = (t % p.m_tiles) * P_BM + (int)rank * C_BM;
-        const int n0 = (t / p.m_tiles) * P_BN + (int)rank * C_BN;
+        int mt, nt;
+        tile_coords2(t, p.m_tiles, p.n_tiles, mt, nt);
+        const int m0 = mt * P_BM + (int)rank * C_BM;
+        const int n0 = nt * P_BN + (int)rank * C_BN;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * P_STAGE_BYTES;
@@ -147,8 +163,10 @@ gemm2_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int t = pair; t < num_tiles; t += n_pairs) {
-      const int m0 = (t % p.m_tiles) * P_BM + (int)rank * C_BM;
-      const int n0 = (t / p.m_tiles) * P_BN;
+      int mt, nt;
+      tile_coords2(t, p.m_tiles, p.n_tiles, mt, nt);
+      const int m0 = mt * P_BM + (int)rank * C_BM;
+      const int n0 = nt * P_BN;
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const int row = m0 + q * 32 + lane;

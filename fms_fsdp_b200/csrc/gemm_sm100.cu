@@ -30,6 +30,19 @@ constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*b
 
 enum { EPI_STORE = 0, EPI_RESIDUAL = 1, EPI_ACCUM = 2 };
 
+
+// L2-friendly rasterisation (see gemm2_sm100.cu): bands of GROUP_M m-tiles, n fastest across a band.
+constexpr int GROUP_M = 16;
+B200_DEVINL void tile_coords(int t, int m_tiles, int n_tiles, int& mt, int& nt) {
+  const int per_band = GROUP_M * n_tiles;
+  const int band = t / per_band;
+  const int first_m = band * GROUP_M;
+  const int band_m = min(GROUP_M, m_tiles - first_m);
+  const int r = t - band * per_band;
+  mt = first_m + r % band_m;
+  nt = r / band_m;
+}
+
 struct GemmParams {
   int M, N, K;          // C is [M,N], reduction length K
   int ldc, ldr;         // row strides (elements) of C and residual
@@ -81,8 +94,9 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       int stage = 0;
       uint32_t phase = 0;
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-        const int m0 = (t % p.m_tiles) * BM;
-        const int n0 = (t / p.m_tiles) * BN;
+        int mt, nt;
+        tile_coords(t, p.m_tiles, p.n_tiles, mt, nt);
+        const int m0 = mt * BM, n0 = nt * BN;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * STAGE_BYTES;
@@ -145,8 +159,9 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-      const int m0 = (t % p.m_tiles) * BM;
-      const int n0 = (t / p.m_tiles) * BN;
+      int mt, nt;
+      tile_coords(t, p.m_tiles, p.n_tiles, mt, nt);
+      const int m0 = mt * BM, n0 = nt * BN;
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const int row = m0 + q * 32 + lane;

@@ -21,6 +21,7 @@ _LAYOUT = {"nt": 0, "nn": 1, "tn": 2}
 # attention implementation: "tcgen05" (ours) | "sdpa" (library fallback, debugging only)
 ATTN_IMPL = os.environ.get("FMS_B200_ATTN_IMPL", "tcgen05")
 GEMM_IMPL = os.environ.get("FMS_B200_GEMM_IMPL", "tcgen05")  # "cublas" = library fallback, debugging only
+_C.set_attn_fwd_version(int(os.environ.get("FMS_B200_ATTN_FWD", "2")))  # 2 = two Q tiles/CTA, P in TMEM
 _C.set_gemm_2cta(os.environ.get("FMS_B200_GEMM_2CTA", "1") == "1")  # CTA-pair (cta_group::2) GEMM for M >= 256
 
 
@@ -236,5 +237,5 @@ def causal_conv1d_bwd(dy, x, w, b, seq_len, activation=True):
     return dx, dw, (None if b is None else db)
 
 
-ssd_scan_fwd = torch_kernels.ssd_scan_fwd
+ssd_scan_fwd = torch_kernels.ssd_scan_chunked   # matmul (chunked SSD) form in ATen until ssd.cu lands
 selective_scan_fwd = torch_kernels.selective_scan_fwd

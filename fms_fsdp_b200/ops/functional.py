@@ -408,8 +408,8 @@ class _SSDScan(torch.autograd.Function):
                 leaves = [t.detach().float().requires_grad_() for t in (x, dt, _wdata(A), Bm, Cm)]
                 Dl = None if D is None else _wdata(D).detach().float().requires_grad_()
                 bl = None if dt_bias is None else _wdata(dt_bias).detach().float().requires_grad_()
-                y = torch_kernels.ssd_scan_fwd(leaves[0], leaves[1], leaves[2], leaves[3], leaves[4], Dl, bl,
-                                               seq_len, chunk_size)
+                y = torch_kernels.ssd_scan_chunked(leaves[0], leaves[1], leaves[2], leaves[3], leaves[4], Dl, bl,
+                                                   seq_len, chunk_size)
                 ins = leaves + [t for t in (Dl, bl) if t is not None]
                 gs = list(torch.autograd.grad(y, ins, dy.float()))
             dx, ddt, dA, dB, dC = gs[:5]

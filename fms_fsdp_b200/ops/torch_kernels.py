@@ -355,6 +355,55 @@ def ssd_scan_fwd(x, dt, A, Bm, Cm, D, dt_bias, seq_len, chunk_size, dt_softplus=
     return y.reshape(M, H, P).to(x.dtype)
 
 
+def _segsum(x):
+    """out[..., i, j] = sum_{j < k <= i} x[..., k]  (lower triangle; -inf above the diagonal)."""
+    T = x.size(-1)
+    cs = torch.cumsum(x, dim=-1)
+    d = cs[..., :, None] - cs[..., None, :]
+    mask = torch.tril(torch.ones(T, T, device=x.device, dtype=torch.bool), diagonal=0)
+    return d.masked_fill(~mask, float("-inf"))
+
+
+def ssd_scan_chunked(x, dt, A, Bm, Cm, D, dt_bias, seq_len, chunk_size, dt_softplus=True):
+    """Mamba2 SSD in its chunked (state-space dual) matmul form -- differentiable ATen, the formulation the
+    tensor-core kernel follows: intra-chunk quadratic term + chunk states + inter-chunk state passing."""
+    M, H, P = x.shape
+    Bsz = M // seq_len
+    G, N = Bm.shape[1], Bm.shape[2]
+    L = min(chunk_size, seq_len)
+    pad = (-seq_len) % L
+    xf = x.float().view(Bsz, seq_len, H, P)
+    dtf = dt.float().view(Bsz, seq_len, H)
+    if dt_bias is not None:
+        dtf = dtf + dt_bias.float()
+    if dt_softplus:
+        dtf = F.softplus(dtf)
+    Bf = Bm.float().view(Bsz, seq_len, G, N).repeat_interleave(H // G, dim=2)
+    Cf = Cm.float().view(Bsz, seq_len, G, N).repeat_interleave(H // G, dim=2)
+    if pad:
+        xf, dtf = F.pad(xf, (0, 0, 0, 0, 0, pad)), F.pad(dtf, (0, 0, 0, pad))
+        Bf, Cf = F.pad(Bf, (0, 0, 0, 0, 0, pad)), F.pad(Cf, (0, 0, 0, 0, 0, pad))
+    S2 = seq_len + pad
+    nc = S2 // L
+    X = (xf * dtf.unsqueeze(-1)).view(Bsz, nc, L, H, P)
+    Ad = (dtf * A.float()).view(Bsz, nc, L, H).permute(0, 3, 1, 2)        # [b,h,c,L]
+    Bc = Bf.view(Bsz, nc, L, H, N)
+    Cc = Cf.view(Bsz, nc, L, H, N)
+    A_cs = torch.cumsum(Ad, dim=-1)
+    Lm = torch.exp(_segsum(Ad))                                              # [b,h,c,L,L]
+    Y_diag = torch.einsum("bclhn,bcshn,bhcls,bcshp->bclhp", Cc, Bc, Lm, X)
+    decay_states = torch.exp(A_cs[..., -1:] - A_cs)                          # [b,h,c,L]
+    states = torch.einsum("bclhn,bhcl,bclhp->bchpn", Bc, decay_states, X)    # [b,c,h,p,n]
+    states = torch.cat([torch.zeros_like(states[:, :1]), states], dim=1)
+    decay_chunk = torch.exp(_segsum(F.pad(A_cs[..., -1], (1, 0))))           # [b,h,c+1,c+1]
+    new_states = torch.einsum("bhzc,bchpn->bzhpn", decay_chunk, states)[:, :-1]
+    Y_off = torch.einsum("bclhn,bchpn,bhcl->bclhp", Cc, new_states, torch.exp(A_cs))
+    y = (Y_diag + Y_off).reshape(Bsz, S2, H, P)[:, :seq_len]
+    if D is not None:
+        y = y + xf[:, :seq_len] * D.float()[None, None, :, None]
+    return y.reshape(M, H, P).to(x.dtype)
+
+
 def selective_scan_fwd(u, delta, A, Bm, Cm, D, z, delta_bias, seq_len, delta_softplus=True):
     """Mamba1 selective scan oracle. u, delta, z: [M, Dm]; A: [Dm, N]; Bm, Cm: [M, N]; D: [Dm]."""
     M, Dm = u.shape

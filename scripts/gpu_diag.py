@@ -50,6 +50,17 @@ def main(groups):
     torch.manual_seed(0)
     rec("env", device=torch.cuda.get_device_name(0), torch=torch.__version__)
 
+    if "probe" in groups:
+        try:
+            a = torch.randn(128, 64, device=dev).bfloat16(); b = torch.randn(64, 64, device=dev).bfloat16()
+            d = CK._C.ts_mma_probe(a, b)
+            torch.cuda.synchronize()
+            ref = a.float() @ b.float().t()
+            a_sw = a.view(128, 32, 2).flip(-1).reshape(128, 64)
+            rec("ts_mma_probe", err_low_even=relerr(d, ref), err_low_odd=relerr(d, a_sw.float() @ b.float().t()))
+        except Exception as ex:
+            rec("ts_mma_probe", ok=False, error=repr(ex)[:400])
+
     if "gemm2" in groups:
         # CTA-pair kernel vs single-CTA kernel vs cuBLAS on training shapes
         for layout, (M, N, K) in [("nt", (8192, 12288, 4096)), ("nt", (8192, 22016, 4096)), ("nt", (8192, 4096, 11008)),
@@ -213,12 +224,14 @@ def main(groups):
         chk("conv1d", t_conv)
 
     if "attn" in groups:
-        for (B, S, H, KVH, hd) in [(1, 128, 1, 1, 128), (2, 256, 4, 2, 128), (1, 512, 2, 2, 64), (2, 4096, 32, 32, 128)]:
+        for ver in ([int(x) for x in os.environ.get("DIAG_ATTN_VERS", "2").split(",")]):
+          CK._C.set_attn_fwd_version(ver)
+          for (B, S, H, KVH, hd) in [(1, 128, 1, 1, 128), (2, 256, 4, 2, 128), (1, 384, 2, 1, 128), (1, 512, 2, 2, 64), (2, 4096, 32, 32, 128)]:
             try:
                 qkv = torch.randn(B * S, (H + 2 * KVH) * hd, device=dev).bfloat16()
                 do = torch.randn(B * S, H * hd, device=dev).bfloat16()
                 sc = hd ** -0.5
-                r = dict(B=B, S=S, H=H, KVH=KVH, hd=hd)
+                r = dict(B=B, S=S, H=H, KVH=KVH, hd=hd, fwd_version=ver)
                 o1, l1 = CK.attn_fwd(qkv, B, S, H, KVH, hd, sc)
                 torch.cuda.synchronize()
                 if S <= 1024:
