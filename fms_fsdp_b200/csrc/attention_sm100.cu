@@ -847,6 +847,277 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv128, const __grid_cons
 }
 
 static int g_attn_fwd_version = 2;
+static int g_attn_bwd_version = 2;
+
+// ============================================================================================ backward v2
+// Same math / operand layouts as attn_bwd_kernel, re-pipelined: two row-owner warpgroups alternate iterations
+// (WG p owns T[p] and its own P^T/dS^T smem tiles), the streamed (Q,dO)/(K,V) ring is 3 deep and the score GEMMs
+// run two iterations ahead of the accumulate GEMMs, so neither the tensor pipe nor the row owners wait on a
+// single-buffered hand-off.  384 threads: warp 0 TMA, warp 1 MMA, warps 4-7 WG0, warps 8-11 WG1.
+template <int HD>
+struct Bwd2Cfg {
+  static constexpr int NCH = HD / 64;
+  static constexpr int X_BYTES = 128 * HD * 2;
+  static constexpr int Y_BYTES = 64 * HD * 2;
+  static constexpr int Y_CHUNK = 64 * 128;
+  static constexpr int W_BYTES = 128 * 64 * 2;
+  static constexpr int STAGES = 3;
+  static constexpr int SMEM = 2 * X_BYTES + STAGES * 2 * Y_BYTES + 4 * W_BYTES + 2 * 128 * 4 + 1024 + 256;
+};
+
+template <int HD, int MODE>
+__global__ void __launch_bounds__(ATT2_THREADS, 1)
+attn_bwd2_kernel(const __grid_constant__ CUtensorMap tm_qkv128, const __grid_constant__ CUtensorMap tm_qkv64,
+                 const __grid_constant__ CUtensorMap tm_do128, const __grid_constant__ CUtensorMap tm_do64,
+                 const float* __restrict__ lse, const float* __restrict__ delta, __nv_bfloat16* __restrict__ dqkv,
+                 int S, int H, int KVH, float scale, int n_t128) {
+  using C = Bwd2Cfg<HD>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sX1 = smem;
+  uint8_t* sX2 = sX1 + C::X_BYTES;
+  uint8_t* sY = sX2 + C::X_BYTES;                          // [stage][Y1 | Y2]
+  uint8_t* sW = sY + C::STAGES * 2 * C::Y_BYTES;           // [parity][W1 | W2]
+  float* sStat = reinterpret_cast<float*>(sW + 4 * C::W_BYTES);   // [parity][lse2 64 | delta 64]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sStat) + 2 * 128 * 4);
+  uint64_t* x_full = bars;
+  uint64_t* y_full = bars + 1;     // [3]
+  uint64_t* y_empty = bars + 4;    // [3]
+  uint64_t* t_full = bars + 7;     // [2]
+  uint64_t* w_full = bars + 9;     // [2]
+  uint64_t* acc_done = bars + 11;  // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int G = H / KVH;
+  const int b = blockIdx.z;
+  const float scale_log2 = scale * LOG2E;
+  int t128, head_lo, head_n, kvh;
+  if constexpr (MODE == MODE_DKDV) {
+    t128 = blockIdx.x; kvh = blockIdx.y; head_lo = kvh * G; head_n = G;
+  } else {
+    t128 = n_t128 - 1 - blockIdx.x; head_lo = blockIdx.y; head_n = 1; kvh = blockIdx.y / G;
+  }
+  const int n64 = (S + 63) / 64;
+  const int s_lo = (MODE == MODE_DKDV) ? 2 * t128 : 0;
+  const int s_hi = (MODE == MODE_DKDV) ? n64 : min(n64, 2 * t128 + 2);
+  const int per_head = s_hi - s_lo;
+  const int n_iter = per_head * head_n;
+  const int xrow0 = b * S + t128 * 128;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_qkv128); tma_prefetch_desc(&tm_qkv64);
+    tma_prefetch_desc(&tm_do128); tma_prefetch_desc(&tm_do64);
+    mbar_init(x_full, 1);
+    for (int i = 0; i < 3; ++i) { mbar_init(&y_full[i], 1); mbar_init(&y_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&t_full[i], 1); mbar_init(&w_full[i], 4); mbar_init(&acc_done[i], 1); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t tmem_acc1 = tmem + 256, tmem_acc2 = tmem + 384;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(x_full, 2 * C::X_BYTES);
+      for (int c = 0; c < C::NCH; ++c) {
+        if constexpr (MODE == MODE_DKDV) {
+          tma_load_2d(sX1 + c * 16384, &tm_qkv128, x_full, (H + kvh) * HD + 64 * c, xrow0);
+          tma_load_2d(sX2 + c * 16384, &tm_qkv128, x_full, (H + KVH + kvh) * HD + 64 * c, xrow0);
+        } else {
+          tma_load_2d(sX1 + c * 16384, &tm_qkv128, x_full, head_lo * HD + 64 * c, xrow0);
+          tma_load_2d(sX2 + c * 16384, &tm_do128, x_full, head_lo * HD + 64 * c, xrow0);
+        }
+      }
+      int st = 0;
+      uint32_t ph = 0;
+      for (int it = 0; it < n_iter; ++it) {
+        const int hh = head_lo + it / per_head;
+        const int t64 = s_lo + it % per_head;
+        const int yrow = b * S + t64 * 64;
+        uint8_t* y1 = sY + st * 2 * C::Y_BYTES;
+        uint8_t* y2 = y1 + C::Y_BYTES;
+        mbar_wait(&y_empty[st], ph ^ 1);
+        mbar_arrive_expect_tx(&y_full[st], 2 * C::Y_BYTES);
+        for (int c = 0; c < C::NCH; ++c) {
+          if constexpr (MODE == MODE_DKDV) {
+            tma_load_2d(y1 + c * C::Y_CHUNK, &tm_qkv64, &y_full[st], hh * HD + 64 * c, yrow);
+            tma_load_2d(y2 + c * C::Y_CHUNK, &tm_do64, &y_full[st], hh * HD + 64 * c, yrow);
+          } else {
+            tma_load_2d(y1 + c * C::Y_CHUNK, &tm_qkv64, &y_full[st], (H + kvh) * HD + 64 * c, yrow);
+            tma_load_2d(y2 + c * C::Y_CHUNK, &tm_qkv64, &y_full[st], (H + KVH + kvh) * HD + 64 * c, yrow);
+          }
+        }
+        if (++st == 3) { st = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t idesc_t = make_idesc_bf16(128, 64, false, false);
+    constexpr uint32_t idesc_a = make_idesc_bf16(128, HD, false, true);
+    auto issue_scores = [&](int it) {
+      const int st = it % 3;
+      mbar_wait(&y_full[st], (it / 3) & 1);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t x1 = smem_u32(sX1), x2 = smem_u32(sX2);
+        const uint32_t y1 = smem_u32(sY + st * 2 * C::Y_BYTES), y2 = y1 + C::Y_BYTES;
+        const uint32_t t1 = tmem + (it & 1) * 128, t2 = t1 + 64;
+#pragma unroll
+        for (int kk = 0; kk < HD / 16; ++kk) {
+          const uint32_t xo = (kk >> 2) * 16384 + (kk & 3) * 32;
+          const uint32_t yo = (kk >> 2) * C::Y_CHUNK + (kk & 3) * 32;
+          umma_bf16_ss(t1, make_smem_desc(x1 + xo, 0, 1024), make_smem_desc(y1 + yo, 0, 1024), idesc_t, kk != 0);
+        }
+#pragma unroll
+        for (int kk = 0; kk < HD / 16; ++kk) {
+          const uint32_t xo = (kk >> 2) * 16384 + (kk & 3) * 32;
+          const uint32_t yo = (kk >> 2) * C::Y_CHUNK + (kk & 3) * 32;
+          umma_bf16_ss(t2, make_smem_desc(x2 + xo, 0, 1024), make_smem_desc(y2 + yo, 0, 1024), idesc_t, kk != 0);
+        }
+        umma_commit(&t_full[it & 1]);
+      }
+      __syncwarp();
+    };
+    mbar_wait(x_full, 0);
+    if (n_iter > 0) issue_scores(0);
+    if (n_iter > 1) issue_scores(1);
+    for (int it = 0; it < n_iter; ++it) {
+      const int p = it & 1, st = it % 3;
+      mbar_wait(&w_full[p], (it >> 1) & 1);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t y1 = smem_u32(sY + st * 2 * C::Y_BYTES), y2 = y1 + C::Y_BYTES;
+        const uint32_t w1 = smem_u32(sW + p * 2 * C::W_BYTES), w2 = w1 + C::W_BYTES;
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          if constexpr (MODE == MODE_DKDV)
+            umma_bf16_ss(tmem_acc1, make_smem_desc(w1 + t * 32, 0, 1024),
+                         make_smem_desc(y2 + t * 2048, C::Y_CHUNK, 1024), idesc_a, (it | t) != 0);
+          umma_bf16_ss(tmem_acc2, make_smem_desc(w2 + t * 32, 0, 1024),
+                       make_smem_desc(y1 + t * 2048, C::Y_CHUNK, 1024), idesc_a, (it | t) != 0);
+        }
+        umma_commit(&y_empty[st]);
+        umma_commit(&acc_done[p]);
+      }
+      __syncwarp();
+      if (it + 2 < n_iter) issue_scores(it + 2);
+    }
+  } else if (warp >= 4) {
+    const int p = (warp - 4) >> 2;            // warpgroup parity
+    const int q4 = warp & 3;
+    const int r = q4 * 32 + lane;
+    const int tid128 = (warp & 3) * 32 + lane;
+    const uint32_t lane_addr = static_cast<uint32_t>(q4 * 32) << 16;
+    const int x_idx = t128 * 128 + r;
+    uint8_t* sW1 = sW + p * 2 * C::W_BYTES;
+    uint8_t* sW2 = sW1 + C::W_BYTES;
+    float* stat = sStat + p * 128;
+    float row_lse2 = 0.f, row_delta = 0.f;
+    if constexpr (MODE == MODE_DQ) {
+      const size_t sidx = ((size_t)b * H + head_lo) * S + min(x_idx, S - 1);
+      row_lse2 = lse[sidx] * LOG2E;
+      row_delta = delta[sidx];
+    }
+    for (int it = p; it < n_iter; it += 2) {
+      const int hh = head_lo + it / per_head;
+      const int t64 = s_lo + it % per_head;
+      const int y0 = t64 * 64;
+      if constexpr (MODE == MODE_DKDV) {
+        named_bar_sync(1 + p, 128);  // previous iteration's readers of stat[p] are done
+        const int qi = y0 + (tid128 & 63);
+        const size_t sidx = ((size_t)b * H + hh) * S + min(qi, S - 1);
+        stat[tid128] = (tid128 < 64) ? lse[sidx] * LOG2E : delta[sidx];
+        named_bar_sync(1 + p, 128);
+      }
+      mbar_wait(&t_full[p], (it >> 1) & 1);
+      tc_fence_after();
+      if (it >= 2) mbar_wait(&acc_done[p], ((it >> 1) - 1) & 1);  // W[p] free again
+      const uint32_t t1 = tmem + p * 128 + lane_addr, t2 = t1 + 64;
+#pragma unroll 1
+      for (int c = 0; c < 64; c += 32) {
+        uint32_t a[32], d[32];
+        tmem_ld_32x32b_x32(t1 + c, a);
+        tmem_ld_32x32b_x32(t2 + c, d);
+        tmem_ld_wait();
+        float pr[32], ds[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const int y_idx = y0 + c + i;
+          float l2, dl;
+          bool masked;
+          if constexpr (MODE == MODE_DKDV) {
+            l2 = stat[c + i]; dl = stat[64 + c + i];
+            masked = (x_idx > y_idx) || (y_idx >= S) || (x_idx >= S);
+          } else {
+            l2 = row_lse2; dl = row_delta;
+            masked = (y_idx > x_idx) || (y_idx >= S) || (x_idx >= S);
+          }
+          const float pv = masked ? 0.f : exp2f(__uint_as_float(a[i]) * scale_log2 - l2);
+          pr[i] = pv;
+          ds[i] = pv * (__uint_as_float(d[i]) - dl) * scale;
+        }
+        const int cb = c >> 3;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint4 u;
+          if constexpr (MODE == MODE_DKDV) {
+            u.x = pack_bf16x2(pr[g * 8 + 0], pr[g * 8 + 1]); u.y = pack_bf16x2(pr[g * 8 + 2], pr[g * 8 + 3]);
+            u.z = pack_bf16x2(pr[g * 8 + 4], pr[g * 8 + 5]); u.w = pack_bf16x2(pr[g * 8 + 6], pr[g * 8 + 7]);
+            st_swz128(sW1, r, cb + g, u);
+          }
+          u.x = pack_bf16x2(ds[g * 8 + 0], ds[g * 8 + 1]); u.y = pack_bf16x2(ds[g * 8 + 2], ds[g * 8 + 3]);
+          u.z = pack_bf16x2(ds[g * 8 + 4], ds[g * 8 + 5]); u.w = pack_bf16x2(ds[g * 8 + 6], ds[g * 8 + 7]);
+          st_swz128(sW2, r, cb + g, u);
+        }
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&w_full[p]);
+    }
+    // epilogue: WG0 stores acc2 (dK | dQ), WG1 stores acc1 (dV); in DQ mode the two groups split acc2's columns
+    if (n_iter > 0) mbar_wait(&acc_done[(n_iter - 1) & 1], ((n_iter - 1) >> 1) & 1);
+    tc_fence_after();
+    if (x_idx < S) {
+      const size_t row = (size_t)b * S + x_idx;
+      const int Wd = (H + 2 * KVH) * HD;
+      auto store_acc = [&](uint32_t tacc, int col0, int c_lo, int c_hi) {
+        __nv_bfloat16* dst = dqkv + row * Wd + col0;
+#pragma unroll 1
+        for (int c = c_lo; c < c_hi; c += 32) {
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(tacc + lane_addr + c, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            uint4 u;
+            u.x = pack_bf16x2(__uint_as_float(v[g * 8 + 0]), __uint_as_float(v[g * 8 + 1]));
+            u.y = pack_bf16x2(__uint_as_float(v[g * 8 + 2]), __uint_as_float(v[g * 8 + 3]));
+            u.z = pack_bf16x2(__uint_as_float(v[g * 8 + 4]), __uint_as_float(v[g * 8 + 5]));
+            u.w = pack_bf16x2(__uint_as_float(v[g * 8 + 6]), __uint_as_float(v[g * 8 + 7]));
+            *reinterpret_cast<uint4*>(dst + c + g * 8) = u;
+          }
+        }
+      };
+      if constexpr (MODE == MODE_DKDV) {
+        if (p == 0) store_acc(tmem_acc2, (H + kvh) * HD, 0, HD);
+        else        store_acc(tmem_acc1, (H + KVH + kvh) * HD, 0, HD);
+      } else {
+        if (p == 0) store_acc(tmem_acc2, head_lo * HD, 0, HD / 2);
+        else        store_acc(tmem_acc2, head_lo * HD, HD / 2, HD);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
 
 template <int HD>
 static int launch_fwd2(const void* qkv, void* o, float* lse, int B, int S, int H, int KVH, float scale,
@@ -906,6 +1177,25 @@ static int launch_bwd(const void* dout, const void* qkv, const void* o, const fl
     attn_delta_kernel<<<(unsigned)blocks, threads, 0, st>>>((const __nv_bfloat16*)dout, (const __nv_bfloat16*)o, delta,
                                                             B, S, H, HD);
   }
+  const int n_t = (S + 127) / 128;
+  if (g_attn_bwd_version == 2) {
+    using C2 = Bwd2Cfg<HD>;
+    auto j1 = attn_bwd2_kernel<HD, MODE_DKDV>;
+    auto j2 = attn_bwd2_kernel<HD, MODE_DQ>;
+    static bool configured2 = false;
+    if (!configured2) {
+      cudaError_t e = cudaFuncSetAttribute(j1, cudaFuncAttributeMaxDynamicSharedMemorySize, C2::SMEM);
+      if (e != cudaSuccess) return (int)e;
+      e = cudaFuncSetAttribute(j2, cudaFuncAttributeMaxDynamicSharedMemorySize, C2::SMEM);
+      if (e != cudaSuccess) return (int)e;
+      configured2 = true;
+    }
+    j1<<<dim3(n_t, KVH, B), ATT2_THREADS, C2::SMEM, st>>>(q128, q64, d128, d64, lse, delta, (__nv_bfloat16*)dqkv, S, H,
+                                                         KVH, scale, n_t);
+    j2<<<dim3(n_t, H, B), ATT2_THREADS, C2::SMEM, st>>>(q128, q64, d128, d64, lse, delta, (__nv_bfloat16*)dqkv, S, H, KVH,
+                                                       scale, n_t);
+    return (int)cudaGetLastError();
+  }
   auto k1 = attn_bwd_kernel<HD, MODE_DKDV>;
   auto k2 = attn_bwd_kernel<HD, MODE_DQ>;
   static bool configured = false;
@@ -916,7 +1206,6 @@ static int launch_bwd(const void* dout, const void* qkv, const void* o, const fl
     if (e != cudaSuccess) return (int)e;
     configured = true;
   }
-  const int n_t = (S + 127) / 128;
   k1<<<dim3(n_t, KVH, B), ATT_THREADS, C::SMEM, st>>>(q128, q64, d128, d64, lse, delta, (__nv_bfloat16*)dqkv, S, H, KVH,
                                                      scale, n_t);
   k2<<<dim3(n_t, H, B), ATT_THREADS, C::SMEM, st>>>(q128, q64, d128, d64, lse, delta, (__nv_bfloat16*)dqkv, S, H, KVH,
@@ -927,6 +1216,7 @@ static int launch_bwd(const void* dout, const void* qkv, const void* o, const fl
 }  // namespace b200
 
 extern "C" void b200_attn_set_fwd_version(int v) { b200::g_attn_fwd_version = v; }
+extern "C" void b200_attn_set_bwd_version(int v) { b200::g_attn_bwd_version = v; }
 extern "C" int b200_attn_fwd(const void* qkv, void* o, float* lse, int B, int S, int H, int KVH, int HD, float scale,
                              cudaStream_t st) {
   if (H % KVH) return -1;

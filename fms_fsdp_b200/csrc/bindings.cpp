@@ -28,6 +28,7 @@ DECL int b200_adamw(float*, const void*, int, float*, float*, void*, long long, 
                     float, float, const float*, cudaStream_t);
 DECL int b200_sumsq(const void*, int, long long, float*, cudaStream_t);
 DECL void b200_attn_set_fwd_version(int);
+DECL void b200_attn_set_bwd_version(int);
 DECL int b200_attn_fwd(const void*, void*, float*, int, int, int, int, int, float, cudaStream_t);
 DECL int b200_attn_bwd(const void*, const void*, const void*, const float*, void*, float*, int, int, int, int, int,
                        float, cudaStream_t);
@@ -315,6 +316,7 @@ std::vector<at::Tensor> causal_conv1d_bwd(const at::Tensor& dy, const at::Tensor
 }
 
 void set_attn_fwd_version(int64_t v) { b200_attn_set_fwd_version((int)v); }
+void set_attn_bwd_version(int64_t v) { b200_attn_set_bwd_version((int)v); }
 void set_gemm_2cta(bool on) { g_gemm_2cta = on; }
 bool get_gemm_2cta() { return g_gemm_2cta; }
 at::Tensor ts_mma_probe(const at::Tensor& a, const at::Tensor& b) {
@@ -354,6 +356,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("causal_conv1d_fwd", &causal_conv1d_fwd);
   m.def("causal_conv1d_bwd", &causal_conv1d_bwd);
   m.def("set_attn_fwd_version", &set_attn_fwd_version);
+  m.def("set_attn_bwd_version", &set_attn_bwd_version);
   m.def("set_gemm_2cta", &set_gemm_2cta);
   m.def("get_gemm_2cta", &get_gemm_2cta);
   m.def("ts_mma_probe", &ts_mma_probe);

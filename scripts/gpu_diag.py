@@ -225,7 +225,7 @@ def main(groups):
 
     if "attn" in groups:
         for ver in ([int(x) for x in os.environ.get("DIAG_ATTN_VERS", "2").split(",")]):
-          CK._C.set_attn_fwd_version(ver)
+          CK._C.set_attn_fwd_version(ver); CK._C.set_attn_bwd_version(ver)
           for (B, S, H, KVH, hd) in [(1, 128, 1, 1, 128), (2, 256, 4, 2, 128), (1, 384, 2, 1, 128), (1, 512, 2, 2, 64), (2, 4096, 32, 32, 128)]:
             try:
                 qkv = torch.randn(B * S, (H + 2 * KVH) * hd, device=dev).bfloat16()
