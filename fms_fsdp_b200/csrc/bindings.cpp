@@ -12,6 +12,10 @@ DECL int b200_gemm_bf16(const void*, const void*, void*, const void*, int, int, 
                         int, cudaStream_t);
 DECL int b200_gemm2_bf16(const void*, const void*, void*, const void*, int, int, int, int, int, int, int, int, int, int,
                          int, cudaStream_t);
+DECL int b200_gemm2_ag_bf16(const void*, const void*, void*, const void*, int, int, int, int, int, int, int, int, int, int,
+                            const void* const*, void*, unsigned long long, unsigned long long, unsigned long long, int, int,
+                            uint32_t*, uint32_t, int, cudaStream_t);
+DECL int b200_p2p_gather_range(const void* const*, void*, long long, long long, long long, cudaStream_t);
 DECL int b200_ts_mma_probe(const void*, const void*, float*, cudaStream_t);
 DECL int b200_rmsnorm_fwd(const void*, const void*, void*, float*, int, int, float, cudaStream_t);
 DECL int b200_rmsnorm_bwd_grid(int);
@@ -319,6 +323,44 @@ void set_attn_fwd_version(int64_t v) { b200_attn_set_fwd_version((int)v); }
 void set_attn_bwd_version(int64_t v) { b200_attn_set_bwd_version((int)v); }
 void set_gemm_2cta(bool on) { g_gemm_2cta = on; }
 bool get_gemm_2cta() { return g_gemm_2cta; }
+// GEMM with the all-gather of a unit's parameters fused in (comm warps over NVLink peer memory)
+void gemm_ag(const at::Tensor& a, const at::Tensor& b, at::Tensor& c, int64_t layout, int64_t epi,
+             const c10::optional<at::Tensor>& residual, const at::Tensor& peer_ptrs, at::Tensor& full,
+             int64_t shard_bytes, int64_t begin, int64_t end, int64_t world, int64_t rank, at::Tensor& flags,
+             int64_t epoch, bool dependent) {
+  c10::cuda::CUDAGuard guard(a.device());
+  need(a, "a", at::kBFloat16);
+  need(b, "b", at::kBFloat16);
+  need(c, "c", at::kBFloat16);
+  need(flags, "flags", at::kInt);
+  need_rowmajor2d(a, "a");
+  need_rowmajor2d(b, "b");
+  need_rowmajor2d(c, "c");
+  int M, N, K, a_mn = 0, b_mn = 0;
+  if (layout == 0) { M = a.size(0); K = a.size(1); N = b.size(0); TORCH_CHECK(b.size(1) == K); }
+  else if (layout == 1) { M = a.size(0); K = a.size(1); N = b.size(1); b_mn = 1; TORCH_CHECK(b.size(0) == K); }
+  else { K = a.size(0); M = a.size(1); N = b.size(1); a_mn = b_mn = 1; TORCH_CHECK(b.size(0) == K); }
+  TORCH_CHECK(c.size(0) == M && c.size(1) == N && M >= 256 && K % 8 == 0 && N % 8 == 0 && M % 8 == 0);
+  const void* r = nullptr;
+  int ldr = 0;
+  if (epi == 1) {
+    TORCH_CHECK(residual.has_value());
+    need(*residual, "residual", at::kBFloat16);
+    r = residual->data_ptr();
+    ldr = residual->stride(0);
+  }
+  check(b200_gemm2_ag_bf16(a.data_ptr(), b.data_ptr(), c.data_ptr(), r, M, N, K, a.stride(0), b.stride(0), c.stride(0), ldr,
+                           a_mn, b_mn, (int)epi, (const void* const*)peer_ptrs.data_ptr(), full.data_ptr(),
+                           (unsigned long long)shard_bytes, (unsigned long long)begin, (unsigned long long)end, (int)world,
+                           (int)rank, (uint32_t*)flags.data_ptr(), (uint32_t)epoch, dependent ? 1 : 0, cur_stream()),
+        "gemm2_ag_bf16_tcgen05");
+}
+void p2p_gather_range(const at::Tensor& peer_ptrs, at::Tensor& full, int64_t shard_bytes, int64_t begin, int64_t end) {
+  c10::cuda::CUDAGuard guard(full.device());
+  check(b200_p2p_gather_range((const void* const*)peer_ptrs.data_ptr(), full.data_ptr(), shard_bytes, begin, end, cur_stream()),
+        "p2p_gather_range");
+}
+
 at::Tensor ts_mma_probe(const at::Tensor& a, const at::Tensor& b) {
   c10::cuda::CUDAGuard guard(a.device());
   need(a, "a", at::kBFloat16);
@@ -359,6 +401,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("set_attn_bwd_version", &set_attn_bwd_version);
   m.def("set_gemm_2cta", &set_gemm_2cta);
   m.def("get_gemm_2cta", &get_gemm_2cta);
+  m.def("gemm_ag", &gemm_ag);
+  m.def("p2p_gather_range", &p2p_gather_range);
   m.def("ts_mma_probe", &ts_mma_probe);
   m.def("launch_count", &launch_count);
   m.def("reset_launch_count", &reset_launch_count);

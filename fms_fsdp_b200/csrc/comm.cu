@@ -86,6 +86,18 @@ __global__ void __launch_bounds__(512) p2p_allgather_kernel(const void* const* s
   for (; i < nvec; i += stride) *reinterpret_cast<uint4*>(d + i * 16) = ld_relaxed_v4(s + i * 16);
 }
 
+// Gather an arbitrary byte range [begin, end) of the unit (flat = concatenation of the W shards) from the owners.
+__global__ void __launch_bounds__(512) p2p_gather_range_kernel(const void* const* shard_ptrs, uint8_t* full,
+                                                               size_t shard_bytes, size_t begin, size_t end) {
+  const size_t nvec = (end - begin) / 16;
+  for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += (size_t)gridDim.x * blockDim.x) {
+    const size_t off = begin + v * 16;
+    const size_t src = off / shard_bytes;
+    *reinterpret_cast<uint4*>(full + off) =
+        ld_relaxed_v4(reinterpret_cast<const uint8_t*>(shard_ptrs[src]) + (off - src * shard_bytes));
+  }
+}
+
 B200_DEVINL float block_sum256(float v, float* sh) {
   v = warp_sum(v);
   const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
@@ -219,6 +231,17 @@ extern "C" int b200_p2p_allgather(const void* const* shard_ptrs, void* full, lon
   int per_peer = 64 / world;
   if (per_peer < 1) per_peer = 1;
   p2p_allgather_kernel<<<per_peer * world, 512, 0, s>>>(shard_ptrs, (uint8_t*)full, (size_t)shard_bytes, world, rank);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int b200_p2p_gather_range(const void* const* shard_ptrs, void* full, long long shard_bytes, long long begin,
+                                     long long end, cudaStream_t s) {
+  if ((begin % 16) || (end % 16) || end < begin) return -1;
+  if (end == begin) return 0;
+  long long nvec = (end - begin) / 16;
+  int grid = (int)((nvec + 511) / 512);
+  if (grid > 64) grid = 64;
+  p2p_gather_range_kernel<<<grid, 512, 0, s>>>(shard_ptrs, (uint8_t*)full, (size_t)shard_bytes, (size_t)begin, (size_t)end);
   return (int)cudaGetLastError();
 }
 

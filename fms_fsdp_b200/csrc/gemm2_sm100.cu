@@ -42,6 +42,61 @@ B200_DEVINL void tile_coords2(int t, int m_tiles, int n_tiles, int& mt, int& nt)
   nt = r / band_m;
 }
 
+// ---- fused all-gather (ag_gemm): extra "comm" warps of the same persistent GEMM pull a unit's parameter shards from
+// the 7 peers over NVLink (16-byte ld.relaxed.sys on symmetric-heap addresses) into the local gathered buffer and
+// publish per-chunk ready flags.  dependent=1: the B operand of THIS GEMM lives in that buffer, so the TMA producer
+// acquires the flags of the chunks under each B tile before issuing its loads -- weights flow peer HBM -> NVLink ->
+// local L2 -> TMA -> smem -> tcgen05 tile by tile while the tensor core works on the tiles that already landed.
+// dependent=0: the gather is the NEXT unit's prefetch riding inside this GEMM.
+constexpr int AG_CHUNK = 65536;       // bytes per ready flag
+constexpr int AG_WARPS = 2;           // comm warps per CTA
+struct AgParams {
+  const void* const* peer_shards;     // device table [world] of shard base addresses (own rank included)
+  uint8_t* full;                      // local gathered buffer
+  unsigned long long shard_bytes;
+  unsigned long long begin, end;      // byte range of `full` to gather
+  int world, rank;
+  uint32_t* flags;                    // [ceil(total/AG_CHUNK)] epochs, local memory
+  uint32_t epoch;
+  int dependent;
+  unsigned long long b_off;           // byte offset of the B matrix inside `full`
+  unsigned long long b_row_bytes;     // bytes per stored B row (ldb * 2)
+};
+
+B200_DEVINL uint32_t ld_acquire_gpu(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+B200_DEVINL void st_release_gpu(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+B200_DEVINL uint4 ld_peer_v4(const void* p) {
+  uint4 r;
+  asm volatile("ld.global.relaxed.sys.v4.u32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p) : "memory");
+  return r;
+}
+// block until chunks [lo, hi] of the gathered buffer have been published for this epoch
+B200_DEVINL void ag_wait_chunks(const AgParams& ag, unsigned long long byte_lo, unsigned long long byte_hi) {
+  if (byte_lo < ag.begin) byte_lo = ag.begin;
+  if (byte_hi > ag.end) byte_hi = ag.end;
+  if (byte_hi <= byte_lo) return;
+  const unsigned c0 = (unsigned)(byte_lo / AG_CHUNK), c1 = (unsigned)((byte_hi - 1) / AG_CHUNK);
+  for (unsigned c = c0; c <= c1; ++c) {
+    uint64_t t0 = 0;
+    uint32_t spins = 0;
+    while (ld_acquire_gpu(ag.flags + c) != ag.epoch) {
+      if ((++spins & 0x3ff) == 0) {
+        uint64_t now = global_timer_ns();
+        if (t0 == 0) t0 = now;
+        else if (now - t0 > B200_WAIT_TIMEOUT_NS) __trap();
+      }
+    }
+  }
+  asm volatile("fence.proxy.async;" ::: "memory");  // generic-proxy writes of the comm warps -> TMA (async proxy) reads
+}
+
 struct Gemm2Params {
   int M, N, K;
   int ldc, ldr;
@@ -50,9 +105,10 @@ struct Gemm2Params {
   int m_tiles, n_tiles;  // in units of 256 x 256
 };
 
-template <bool A_MN, bool B_MN, int EPI, typename OutT>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(P_THREADS, 1)
-gemm2_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, Gemm2Params p) {
+template <bool A_MN, bool B_MN, int EPI, typename OutT, bool AG>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(P_THREADS + (AG ? 32 * AG_WARPS : 0), 1)
+gemm2_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, Gemm2Params p,
+                   AgParams ag) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* bar_base = smem + P_STAGES * P_STAGE_BYTES;
@@ -105,6 +161,19 @@ gemm2_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           uint8_t* sb = sa + PA_BYTES;
           if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * P_STAGE_BYTES);
           const int k0 = kb * P_BK;
+          if constexpr (AG) {
+            if (ag.dependent) {
+              // stored rows of B under this CTA's loads: K-major -> rows [n0, n0+128) (once per tile);
+              // MN-major -> rows [k0, k0+64) (every k-block)
+              if constexpr (!B_MN) {
+                if (kb == 0) ag_wait_chunks(ag, ag.b_off + (unsigned long long)n0 * ag.b_row_bytes,
+                                            ag.b_off + (unsigned long long)min(n0 + C_BN, p.N) * ag.b_row_bytes);
+              } else {
+                ag_wait_chunks(ag, ag.b_off + (unsigned long long)k0 * ag.b_row_bytes,
+                               ag.b_off + (unsigned long long)min(k0 + P_BK, p.K) * ag.b_row_bytes);
+              }
+            }
+          }
           if constexpr (!A_MN) {
             tma_load_2d_2cta(sa, &tmA, &full_bar[stage], k0, m0);
           } else {
@@ -155,6 +224,48 @@ gemm2_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           if (++stage == P_STAGES) { stage = 0; phase ^= 1; }
         }
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (AG && warp >= 6) {
+    // ===================== comm warps: pull peer shards into the local gathered buffer =====================
+    if constexpr (AG) {
+      const int ct = (warp - 6) * 32 + lane;              // 0 .. 63
+      const unsigned long long total = ag.end - ag.begin;
+      const unsigned n_chunks = (unsigned)((total + AG_CHUNK - 1) / AG_CHUNK);
+      const unsigned first = (unsigned)(ag.begin / AG_CHUNK);
+      // rotate the start so the 8 ranks do not all hit the same peer first
+      const unsigned rot = (unsigned)(((unsigned long long)ag.rank * n_chunks) / (unsigned)ag.world);
+      for (unsigned i = blockIdx.x; i < n_chunks; i += gridDim.x) {
+        const unsigned ci = ag.dependent ? i : (i + rot) % n_chunks;   // dependent mode keeps B-first order
+        const unsigned long long lo = ag.begin + (unsigned long long)ci * AG_CHUNK;
+        const unsigned long long hi = (lo + AG_CHUNK < ag.end) ? lo + AG_CHUNK : ag.end;
+        const unsigned nvec = (unsigned)((hi - lo) / 16);
+        const unsigned src_lo = (unsigned)(lo / ag.shard_bytes), src_hi = (unsigned)((hi - 1) / ag.shard_bytes);
+        const uint8_t* base_lo = reinterpret_cast<const uint8_t*>(ag.peer_shards[src_lo]) - (unsigned long long)src_lo * ag.shard_bytes;
+        const uint8_t* base_hi = reinterpret_cast<const uint8_t*>(ag.peer_shards[src_hi]) - (unsigned long long)src_hi * ag.shard_bytes;
+        const unsigned long long split = (unsigned long long)src_hi * ag.shard_bytes;  // a chunk spans <= 2 shards
+        for (unsigned v0 = ct; v0 < nvec; v0 += 64 * 8) {
+          uint4 buf[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const unsigned v = v0 + u * 64;
+            if (v < nvec) {
+              const unsigned long long off = lo + (unsigned long long)v * 16;
+              buf[u] = ld_peer_v4(((src_lo != src_hi && off >= split) ? base_hi : base_lo) + off);
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const unsigned v = v0 + u * 64;
+            if (v < nvec) *reinterpret_cast<uint4*>(ag.full + lo + (unsigned long long)v * 16) = buf[u];
+          }
+        }
+        __threadfence();
+        asm volatile("bar.sync 2, 64;" ::: "memory");      // both comm warps finished this chunk
+        if (ct == 0) {
+          asm volatile("fence.proxy.async;" ::: "memory");
+          st_release_gpu(ag.flags + first + ci, ag.epoch);
+        }
       }
     }
   } else {
@@ -244,8 +355,24 @@ gemm2_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 }
 
 template <bool A_MN, bool B_MN, int EPI, typename OutT>
+static int launch2_ag(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gemm2Params& p, const AgParams& ag,
+                      cudaStream_t stream) {
+  auto kern = gemm2_bf16_tcgen05<A_MN, B_MN, EPI, OutT, true>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM);
+    if (e != cudaSuccess) return (int)e;
+    configured = true;
+  }
+  // the comm warps of ALL SMs carry the gather, so always launch the full machine even for few tiles
+  int pairs = sm_count() / 2;
+  kern<<<pairs * 2, P_THREADS + 32 * AG_WARPS, P_SMEM, stream>>>(tmA, tmB, p, ag);
+  return (int)cudaGetLastError();
+}
+
+template <bool A_MN, bool B_MN, int EPI, typename OutT>
 static int launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gemm2Params& p, cudaStream_t stream) {
-  auto kern = gemm2_bf16_tcgen05<A_MN, B_MN, EPI, OutT>;
+  auto kern = gemm2_bf16_tcgen05<A_MN, B_MN, EPI, OutT, false>;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM);
@@ -255,7 +382,7 @@ static int launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gemm2Pa
   int tiles = p.m_tiles * p.n_tiles;
   int pairs = sm_count() / 2;
   if (tiles < pairs) pairs = tiles;
-  kern<<<pairs * 2, P_THREADS, P_SMEM, stream>>>(tmA, tmB, p);
+  kern<<<pairs * 2, P_THREADS, P_SMEM, stream>>>(tmA, tmB, p, AgParams{});
   return (int)cudaGetLastError();
 }
 
@@ -296,4 +423,39 @@ extern "C" int b200_gemm2_bf16(const void* A, const void* B, void* C, const void
   }
   if (b_mn) return dispatch2<false, true>(tmA, tmB, p, epi, out_fp32, stream);
   return dispatch2<false, false>(tmA, tmB, p, epi, out_fp32, stream);
+}
+
+// GEMM + fused all-gather.  Supported: bf16 output, EPI store|residual, layouts nt (forward first GEMM) and
+// nn / tn (backward first GEMMs).
+extern "C" int b200_gemm2_ag_bf16(const void* A, const void* B, void* C, const void* R, int M, int N, int K, int lda,
+                                  int ldb, int ldc, int ldr, int a_mn, int b_mn, int epi,
+                                  const void* const* peer_shards, void* full, unsigned long long shard_bytes,
+                                  unsigned long long begin, unsigned long long end, int world, int rank,
+                                  uint32_t* flags, uint32_t epoch, int dependent, cudaStream_t stream) {
+  using namespace b200;
+  if ((begin % 16) || (end % 16) || (begin % AG_CHUNK)) return -5;
+  CUtensorMap tmA, tmB;
+  int rc;
+  if (!a_mn) rc = make_tmap_2d_bf16(&tmA, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, P_BK, C_BM);
+  else       rc = make_tmap_2d_bf16(&tmA, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, 64, P_BK);
+  if (rc) return 1000 - rc;
+  if (!b_mn) rc = make_tmap_2d_bf16(&tmB, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, P_BK, C_BN);
+  else       rc = make_tmap_2d_bf16(&tmB, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, 64, P_BK);
+  if (rc) return 2000 - rc;
+  Gemm2Params p;
+  p.M = M; p.N = N; p.K = K; p.ldc = ldc; p.ldr = ldr; p.C = C; p.R = R;
+  p.m_tiles = (M + P_BM - 1) / P_BM;
+  p.n_tiles = (N + P_BN - 1) / P_BN;
+  AgParams ag;
+  ag.peer_shards = peer_shards; ag.full = (uint8_t*)full; ag.shard_bytes = shard_bytes; ag.begin = begin; ag.end = end;
+  ag.world = world; ag.rank = rank; ag.flags = flags; ag.epoch = epoch; ag.dependent = dependent;
+  ag.b_off = (unsigned long long)((const uint8_t*)B - (const uint8_t*)full);
+  ag.b_row_bytes = (unsigned long long)ldb * 2;
+  if (dependent && ((const uint8_t*)B < (const uint8_t*)full)) return -6;
+#define AGL(AM, BM_, E) return launch2_ag<AM, BM_, E, __nv_bfloat16>(tmA, tmB, p, ag, stream)
+  if (!a_mn && !b_mn) { if (epi == P_EPI_RESIDUAL) AGL(false, false, P_EPI_RESIDUAL); AGL(false, false, P_EPI_STORE); }
+  if (!a_mn && b_mn)  { if (epi == P_EPI_RESIDUAL) AGL(false, true, P_EPI_RESIDUAL);  AGL(false, true, P_EPI_STORE); }
+  if (a_mn && b_mn)   { if (epi == P_EPI_ACCUM) AGL(true, true, P_EPI_ACCUM);        AGL(true, true, P_EPI_STORE); }
+#undef AGL
+  return -7;
 }
