@@ -21,6 +21,8 @@ DECL int b200_rmsnorm_fwd(const void*, const void*, void*, float*, int, int, flo
 DECL int b200_rmsnorm_bwd_grid(int);
 DECL int b200_rmsnorm_bwd(const void*, const void*, const void*, const float*, void*, float*, float*, int, int,
                           cudaStream_t);
+DECL int b200_add_rmsnorm_fwd(const void*, const float*, const void*, void*, float*, float*, int, int, float, cudaStream_t);
+DECL int b200_rmsnorm_bwd_f32(const void*, const float*, const void*, const float*, float*, float*, float*, int, int, cudaStream_t);
 DECL int b200_rope(void*, const float*, int, int, int, int, int, int, int, int, int, cudaStream_t);
 DECL int b200_swiglu_fwd(const void*, void*, long long, int, int, cudaStream_t);
 DECL int b200_swiglu_bwd(const void*, const void*, void*, long long, int, int, cudaStream_t);
@@ -137,6 +139,35 @@ std::vector<at::Tensor> rmsnorm_bwd(const at::Tensor& dy, const at::Tensor& x, c
   auto dw = at::empty({D}, x.options().dtype(at::kFloat));
   check(b200_rmsnorm_bwd(dy.data_ptr(), x.data_ptr(), w.data_ptr(), rstd.data_ptr<float>(), dx.data_ptr(),
                          part.data_ptr<float>(), dw.data_ptr<float>(), M, D, cur_stream()), "rmsnorm_bwd", 2);
+  return {dx, dw};
+}
+std::vector<at::Tensor> add_rmsnorm_fwd(const at::Tensor& x, const at::Tensor& res, const at::Tensor& w, double eps) {
+  c10::cuda::CUDAGuard guard(x.device());
+  need(x, "x", at::kBFloat16);
+  need(res, "res", at::kFloat);
+  need(w, "w", at::kBFloat16);
+  TORCH_CHECK(x.is_contiguous() && res.is_contiguous() && w.is_contiguous());
+  const int D = x.size(-1), M = x.numel() / D;
+  auto y = at::empty_like(x);
+  auto res_out = at::empty_like(res);
+  auto rstd = at::empty({M}, x.options().dtype(at::kFloat));
+  check(b200_add_rmsnorm_fwd(x.data_ptr(), res.data_ptr<float>(), w.data_ptr(), y.data_ptr(), res_out.data_ptr<float>(),
+                             rstd.data_ptr<float>(), M, D, (float)eps, cur_stream()), "add_rmsnorm_fwd");
+  return {y, res_out, rstd};
+}
+std::vector<at::Tensor> rmsnorm_bwd_f32(const at::Tensor& dy, const at::Tensor& x, const at::Tensor& w,
+                                        const at::Tensor& rstd) {
+  c10::cuda::CUDAGuard guard(x.device());
+  need(dy, "dy", at::kBFloat16);
+  need(x, "x", at::kFloat);
+  need(w, "w", at::kBFloat16);
+  TORCH_CHECK(dy.is_contiguous() && x.is_contiguous());
+  const int D = x.size(-1), M = x.numel() / D;
+  auto dx = at::empty_like(x);
+  auto part = at::empty({b200_rmsnorm_bwd_grid(M), D}, x.options());
+  auto dw = at::empty({D}, x.options());
+  check(b200_rmsnorm_bwd_f32(dy.data_ptr(), x.data_ptr<float>(), w.data_ptr(), rstd.data_ptr<float>(), dx.data_ptr<float>(),
+                             part.data_ptr<float>(), dw.data_ptr<float>(), M, D, cur_stream()), "rmsnorm_bwd_f32", 2);
   return {dx, dw};
 }
 void rope(at::Tensor& qkv, const at::Tensor& table, int64_t seq_len, int64_t nrot_heads, int64_t hd, int64_t rot,
@@ -380,6 +411,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("gemm", &gemm);
   m.def("rmsnorm_fwd", &rmsnorm_fwd);
   m.def("rmsnorm_bwd", &rmsnorm_bwd);
+  m.def("add_rmsnorm_fwd", &add_rmsnorm_fwd);
+  m.def("rmsnorm_bwd_f32", &rmsnorm_bwd_f32);
   m.def("rope", &rope);
   m.def("swiglu_fwd", &swiglu_fwd);
   m.def("swiglu_bwd", &swiglu_bwd);

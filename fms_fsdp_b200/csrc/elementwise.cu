@@ -152,6 +152,112 @@ __global__ void colsum_kernel(const float* __restrict__ part, float* __restrict_
   out[d] = s;
 }
 
+// ------------------------------------------------------------- fused add + RMSNorm (fp32 residual stream)
+// res_out = res + x (fp32) ; y = rmsnorm(res_out) * w (bf16).  Mamba block prologue.
+__global__ void __launch_bounds__(NT) add_rmsnorm_fwd_kernel(const __nv_bfloat16* __restrict__ x,
+                                                             const float* __restrict__ res,
+                                                             const __nv_bfloat16* __restrict__ w,
+                                                             __nv_bfloat16* __restrict__ y, float* __restrict__ res_out,
+                                                             float* __restrict__ rstd, int M, int D, float eps) {
+  __shared__ float sh[32];
+  for (int row = blockIdx.x; row < M; row += gridDim.x) {
+    float v[MAXC][8];
+    float ss = 0.f;
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c) {
+      const int col = (c * NT + threadIdx.x) * 8;
+      if (col < D) {
+        float a[8];
+        load8(x + (size_t)row * D + col, a);
+        const float4* rp = reinterpret_cast<const float4*>(res + (size_t)row * D + col);
+        const float4 r0 = rp[0], r1 = rp[1];
+        v[c][0] = a[0] + r0.x; v[c][1] = a[1] + r0.y; v[c][2] = a[2] + r0.z; v[c][3] = a[3] + r0.w;
+        v[c][4] = a[4] + r1.x; v[c][5] = a[5] + r1.y; v[c][6] = a[6] + r1.z; v[c][7] = a[7] + r1.w;
+        float4* op = reinterpret_cast<float4*>(res_out + (size_t)row * D + col);
+        op[0] = make_float4(v[c][0], v[c][1], v[c][2], v[c][3]);
+        op[1] = make_float4(v[c][4], v[c][5], v[c][6], v[c][7]);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) ss += v[c][i] * v[c][i];
+      }
+    }
+    ss = block_sum(ss, sh);
+    const float r = rsqrtf(ss / (float)D + eps);
+    if (threadIdx.x == 0) rstd[row] = r;
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c) {
+      const int col = (c * NT + threadIdx.x) * 8;
+      if (col < D) {
+        float wv[8], o[8];
+        load8(w + col, wv);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] = v[c][i] * r * wv[i];
+        store8(y + (size_t)row * D + col, o);
+      }
+    }
+  }
+}
+
+// RMSNorm backward with an fp32 input stream: dx (fp32) = r * (g - xhat * mean(g*xhat)), dw_part += dy * xhat
+__global__ void __launch_bounds__(NT) rmsnorm_bwd_f32_kernel(const __nv_bfloat16* __restrict__ dy,
+                                                             const float* __restrict__ x,
+                                                             const __nv_bfloat16* __restrict__ w,
+                                                             const float* __restrict__ rstd, float* __restrict__ dx,
+                                                             float* __restrict__ dw_part, int M, int D) {
+  __shared__ float sh[32];
+  float dwacc[MAXC][8], wv[MAXC][8];
+#pragma unroll
+  for (int c = 0; c < MAXC; ++c) {
+    const int col = (c * NT + threadIdx.x) * 8;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) dwacc[c][i] = 0.f;
+    if (col < D) load8(w + col, wv[c]);
+  }
+  for (int row = blockIdx.x; row < M; row += gridDim.x) {
+    const float r = rstd[row];
+    float g[MAXC][8], xh[MAXC][8];
+    float dot = 0.f;
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c) {
+      const int col = (c * NT + threadIdx.x) * 8;
+      if (col < D) {
+        float a[8];
+        load8(dy + (size_t)row * D + col, a);
+        const float4* xp = reinterpret_cast<const float4*>(x + (size_t)row * D + col);
+        const float4 x0 = xp[0], x1 = xp[1];
+        const float b[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          xh[c][i] = b[i] * r;
+          g[c][i] = a[i] * wv[c][i];
+          dot += g[c][i] * xh[c][i];
+          dwacc[c][i] += a[i] * xh[c][i];
+        }
+      }
+    }
+    dot = block_sum(dot, sh) / (float)D;
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c) {
+      const int col = (c * NT + threadIdx.x) * 8;
+      if (col < D) {
+        float4* op = reinterpret_cast<float4*>(dx + (size_t)row * D + col);
+        op[0] = make_float4(r * (g[c][0] - xh[c][0] * dot), r * (g[c][1] - xh[c][1] * dot),
+                            r * (g[c][2] - xh[c][2] * dot), r * (g[c][3] - xh[c][3] * dot));
+        op[1] = make_float4(r * (g[c][4] - xh[c][4] * dot), r * (g[c][5] - xh[c][5] * dot),
+                            r * (g[c][6] - xh[c][6] * dot), r * (g[c][7] - xh[c][7] * dot));
+      }
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < MAXC; ++c) {
+    const int col = (c * NT + threadIdx.x) * 8;
+    if (col < D) {
+      float4* o = reinterpret_cast<float4*>(dw_part + (size_t)blockIdx.x * D + col);
+      o[0] = make_float4(dwacc[c][0], dwacc[c][1], dwacc[c][2], dwacc[c][3]);
+      o[1] = make_float4(dwacc[c][4], dwacc[c][5], dwacc[c][6], dwacc[c][7]);
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------- RoPE
 // In place on heads [0, nrot) of a fused [M, nheads_total*hd] projection; pairs (2i, 2i+1);
 // table [S, rot/2, 2] fp32 (cos, sin).  One thread = 8 elements = 4 pairs.
@@ -444,6 +550,21 @@ extern "C" int b200_rmsnorm_bwd(const void* dy, const void* x, const void* w, co
   const int grid = b200_rmsnorm_bwd_grid(M);
   rmsnorm_bwd_kernel<<<grid, NT, 0, s>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, (const __nv_bfloat16*)w,
                                          rstd, (__nv_bfloat16*)dx, dw_part, M, D);
+  colsum_kernel<<<(D + 255) / 256, 256, 0, s>>>(dw_part, dw, grid, D);
+  CK();
+}
+extern "C" int b200_add_rmsnorm_fwd(const void* x, const float* res, const void* w, void* y, float* res_out, float* rstd,
+                                    int M, int D, float eps, cudaStream_t s) {
+  if (D % 8 || D > NT * 8 * MAXC) return -1;
+  add_rmsnorm_fwd_kernel<<<M < 148 * 8 ? M : 148 * 8, NT, 0, s>>>((const __nv_bfloat16*)x, res, (const __nv_bfloat16*)w,
+                                                                 (__nv_bfloat16*)y, res_out, rstd, M, D, eps);
+  CK();
+}
+extern "C" int b200_rmsnorm_bwd_f32(const void* dy, const float* x, const void* w, const float* rstd, float* dx,
+                                    float* dw_part, float* dw, int M, int D, cudaStream_t s) {
+  if (D % 8 || D > NT * 8 * MAXC) return -1;
+  const int grid = b200_rmsnorm_bwd_grid(M);
+  rmsnorm_bwd_f32_kernel<<<grid, NT, 0, s>>>((const __nv_bfloat16*)dy, x, (const __nv_bfloat16*)w, rstd, dx, dw_part, M, D);
   colsum_kernel<<<(D + 255) / 256, 256, 0, s>>>(dw_part, dw, grid, D);
   CK();
 }

@@ -40,6 +40,58 @@ def _bf16c(t):
     return t if t.is_contiguous() else t.contiguous()
 
 
+# ------------------------------------------------------------- fused all-gather requests (ag_gemm)
+# The sharded runtime queues "gather this unit's parameters" requests; the next eligible GEMM launched on the
+# compute stream carries one inside its own kernel (comm warps pulling peer shards over NVLink while the tensor
+# core works).  dependent requests (the GEMM's own weight is being gathered) make the TMA producer wait on
+# per-chunk ready flags; others are next-unit prefetches.  Anything left over is flushed as a standalone gather.
+_AG_QUEUE = []
+AG_STATS = {"fused": 0, "flushed": 0}
+
+
+def push_ag_request(req: dict):
+    req["consumed"] = False
+    _AG_QUEUE.append(req)
+
+
+def _standalone_gather(req):
+    _C.p2p_gather_range(req["table"], req["full"], req["shard_bytes"], req["begin"], req["end"])
+    req["consumed"] = True
+    AG_STATS["flushed"] += 1
+
+
+def flush_ag_request(req=None):
+    """Run pending request(s) as plain range gathers (no GEMM came along to carry them)."""
+    for r in list(_AG_QUEUE):
+        if req is None or r is req:
+            _AG_QUEUE.remove(r)
+            if not r["consumed"]:
+                _standalone_gather(r)
+
+
+def _try_fused_gather(a, b, layout, out, epi, residual) -> bool:
+    if not _AG_QUEUE:
+        return False
+    req = _AG_QUEUE[0]
+    M = a.shape[1] if layout == "tn" else a.shape[0]
+    ok = (M >= 256 and out.dtype == torch.bfloat16 and _C.get_gemm_2cta()
+          and ((layout in ("nt", "nn") and epi in (0, 1)) or (layout == "tn" and epi in (0, 2))))
+    if ok and req["dependent"]:
+        lo = req["full"].data_ptr() + req["begin"]
+        ok = lo <= b.data_ptr() < req["full"].data_ptr() + req["end"]
+    if not ok:
+        if req["dependent"]:          # this GEMM may read the weights right now: they must be there
+            _AG_QUEUE.pop(0)
+            _standalone_gather(req)
+        return False
+    _AG_QUEUE.pop(0)
+    _C.gemm_ag(a, b, out, _LAYOUT[layout], epi, residual, req["table"], req["full"], req["shard_bytes"], req["begin"],
+               req["end"], req["world"], req["rank"], req["flags"], req["epoch"], bool(req["dependent"]))
+    req["consumed"] = True
+    AG_STATS["fused"] += 1
+    return True
+
+
 # ------------------------------------------------------------------------------------------ GEMM
 def gemm(a, b, layout="nt", out=None, accumulate=False, residual=None, out_dtype=None):
     if GEMM_IMPL != "tcgen05" or a.dtype != torch.bfloat16 or b.dtype != torch.bfloat16:
@@ -66,6 +118,8 @@ def gemm(a, b, layout="nt", out=None, accumulate=False, residual=None, out_dtype
         epi = 1
     elif accumulate:
         epi = 2
+    if _AG_QUEUE and _try_fused_gather(a, b, layout, out, epi, residual):
+        return out
     _C.gemm(a, b, out, _LAYOUT[layout], epi, residual)
     return out
 
@@ -79,13 +133,22 @@ def rmsnorm_fwd(x, w, eps):
 
 
 def rmsnorm_bwd(dy, x, w, rstd):
+    if x.dtype == torch.float32 and dy.dtype == torch.bfloat16 and x.shape[-1] % 8 == 0 and x.shape[-1] <= 8192:
+        dx, dw = _C.rmsnorm_bwd_f32(dy.contiguous(), x.contiguous(), _bf16c(w), rstd)   # fp32 residual stream
+        return dx, dw
     if x.dtype != torch.bfloat16 or x.shape[-1] % 8 or x.shape[-1] > 8192:
         return torch_kernels.rmsnorm_bwd(dy, x, w, rstd)
     dx, dw = _C.rmsnorm_bwd(dy.contiguous(), x.contiguous(), _bf16c(w), rstd)
     return dx, dw
 
 
-add_rmsnorm_fwd = torch_kernels.add_rmsnorm_fwd
+def add_rmsnorm_fwd(x, res, w, eps):
+    if x.dtype != torch.bfloat16 or res.dtype != torch.float32 or x.shape[-1] % 8 or x.shape[-1] > 8192:
+        return torch_kernels.add_rmsnorm_fwd(x, res, w, eps)
+    y, res_out, rstd = _C.add_rmsnorm_fwd(x.contiguous(), res.contiguous(), _bf16c(w), float(eps))
+    return y, res_out, rstd
+
+
 rmsnorm_gated_fwd = torch_kernels.rmsnorm_gated_fwd
 rmsnorm_gated_bwd = torch_kernels.rmsnorm_gated_bwd
 

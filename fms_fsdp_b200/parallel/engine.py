@@ -121,6 +121,10 @@ class ShardedModel(nn.Module):
         self.prefetch_depth = max(1, int(prefetch_depth))
         self.reshard_after_forward = reshard_after_forward and self.mesh.shard_size > 1
         self._needs_reduce = self.mesh.world > 1
+        import os as _os
+        # fused all-gather: unit gathers ride inside GEMM kernels on the compute stream (fused collectives only)
+        self._fuse_gather = (self.coll.name == "fused" and self.mesh.shard_size > 1
+                             and _os.environ.get("FMS_B200_FUSED_GATHER", "1") == "1")
         self._placeholder = torch.empty(0, dtype=self.mp.param_dtype, device=self.device)
 
         if self.is_cuda:
@@ -190,6 +194,7 @@ class ShardedModel(nn.Module):
                 if id(p) not in seen:
                     seen.add(id(p))
                     params.append((fqn[id(p)], p))
+        params.sort(key=lambda np_: np_[1].dim() > 1)  # stable: vectors (norm gains, biases) first, matrices after
         layout = build_layout(name, [(n, tuple(p.shape)) for n, p in params], self.mesh.shard_size)
         u = ShardUnit(name, modules, params, layout)
         n = layout.shard_numel
@@ -248,10 +253,30 @@ class ShardedModel(nn.Module):
         pool.setdefault((unit.layout.signature(), dtype), []).append(buf)
 
     # ---------------------------------------------------------------------------------- gather
-    def _start_gather(self, u: ShardUnit):
+    def _start_gather(self, u: ShardUnit, dependent: bool = False, fuse: Optional[bool] = None):
         if self.mesh.shard_size == 1 or u.full is not None:
             return
         buf = self._acquire(self._full_pool, u, self.mp.param_dtype, False)
+        fuse = self._fuse_gather if fuse is None else fuse
+        if fuse:
+            # compute-stream gather: the small vector prefix now, the matrices inside the next GEMM kernel
+            from fms_fsdp_b200.ops import cuda_kernels as CK
+            self.s_compute.wait_event(buf.free_event)
+            es = u.lowp.element_size()
+            mb, total = u.layout.matrix_begin * es, u.layout.total * es
+            if mb > 0:
+                self.coll.gather_range(u.lowp, buf.t, 0, mb)
+            u.ag_req = None
+            if total > mb:
+                u.ag_req = self.coll.ag_request(u.lowp, buf.t, mb, total, dependent)
+                CK.push_ag_request(u.ag_req)
+            u.full = buf
+            u.gather_pending = True
+            u.gather_fused = True
+            if dependent:
+                u.bind_params(buf.t)   # the carrier GEMM must already see its weight inside the buffer
+            return
+        u.gather_fused = False
         if self.is_cuda:
             with torch.cuda.stream(self.s_gather):
                 self.s_gather.wait_event(buf.free_event)
@@ -262,11 +287,16 @@ class ShardedModel(nn.Module):
         u.full = buf
         u.gather_pending = True
 
-    def _wait_gather(self, u: ShardUnit):
+    def _wait_gather(self, u: ShardUnit, allow_pending_dependent: bool = False):
         if u.full is None:
             self._start_gather(u)
         if u.gather_pending:
-            if self.is_cuda:
+            if getattr(u, "gather_fused", False):
+                req = getattr(u, "ag_req", None)
+                if req is not None and not req["consumed"] and not (allow_pending_dependent and req["dependent"]):
+                    from fms_fsdp_b200.ops import cuda_kernels as CK
+                    CK.flush_ag_request(req)       # no GEMM carried it: standalone gather on the compute stream
+            elif self.is_cuda:
                 self.s_compute.wait_event(u.ev_gathered)
             u.gather_pending = False
             u.bind_params(u.full.t)
@@ -327,17 +357,26 @@ class ShardedModel(nn.Module):
 
     def _forward(self, tokens, labels=None, **head_kwargs):
         model, blocks = self.module, self.blocks
+        fuse = self._fuse_gather and torch.is_grad_enabled()
+        depth = 1 if fuse else self.prefetch_depth
         if self.is_cuda:
+            if fuse:
+                self.coll.begin_step()                 # cross-GPU barrier on the compute stream
             self.s_gather.wait_stream(self.s_compute)  # shards were just written by the optimizer
-            with torch.cuda.stream(self.s_gather):
-                self.coll.begin_step()                 # ... on every rank (cross-GPU barrier, fused path)
+            if not fuse:
+                with torch.cuda.stream(self.s_gather):
+                    self.coll.begin_step()             # ... on every rank (cross-GPU barrier, fused path)
         else:
             self.coll.begin_step()
         self._gnorm_sq.zero_()
         self._clip_coef = None
-        self._start_gather(self.root)
-        for u in blocks[: self.prefetch_depth]:
-            self._start_gather(u)
+        self._start_gather(self.root, fuse=False)
+        if fuse and blocks:
+            # block 0's own weights arrive INSIDE its first GEMM (QKV projection), consumed tile by tile
+            self._start_gather(blocks[0], dependent=True)
+        else:
+            for u in blocks[: depth]:
+                self._start_gather(u, fuse=False)
         self._wait_gather(self.root)
         grad_on = torch.is_grad_enabled()
         with torch.enable_grad() if grad_on else torch.no_grad():
@@ -345,10 +384,10 @@ class ShardedModel(nn.Module):
         saved = []
         state = emb_out
         for i, u in enumerate(blocks):
-            self._wait_gather(u)
-            nxt = i + self.prefetch_depth
+            self._wait_gather(u, allow_pending_dependent=True)
+            nxt = i + depth
             if nxt < len(blocks):
-                self._start_gather(blocks[nxt])
+                self._start_gather(blocks[nxt], fuse=fuse)   # fused: rides in one of block i's GEMMs
             u.recompute = is_checkpointed(u.modules[0])
             if not grad_on:
                 with torch.no_grad():
@@ -381,6 +420,12 @@ class ShardedModel(nn.Module):
         if sv is None:
             raise RuntimeError("backward without a recorded forward")
         self._saved = None
+        fuse = self._fuse_gather
+        depth = 1 if fuse else self.prefetch_depth
+        n = len(blocks)
+        # re-gather ahead (the last block is still resident from forward)
+        for j in range(n - 1, max(-1, n - 1 - depth), -1):
+            self._start_gather(blocks[j], fuse=fuse)
         # ---- head stage (root unit weights are still gathered)
         self._prepare_grads(self.root)
         out = sv["head_out"]
@@ -391,15 +436,12 @@ class ShardedModel(nn.Module):
         del out
         sv["head_out"] = None
         # ---- blocks in reverse, re-gathering ahead
-        n = len(blocks)
-        for j in range(n - 1, max(-1, n - 1 - self.prefetch_depth), -1):
-            self._start_gather(blocks[j])
         for i in range(n - 1, -1, -1):
             u = blocks[i]
             self._wait_gather(u)
-            nxt = i - self.prefetch_depth
+            nxt = i - depth
             if nxt >= 0:
-                self._start_gather(blocks[nxt])
+                self._start_gather(blocks[nxt], fuse=fuse)   # fused: rides inside block i's backward GEMMs
             x_in, y = sv["blocks"][i]
             self._prepare_grads(u)
             if y is None:  # selective recompute with the weights that are resident for backward anyway

@@ -88,6 +88,7 @@ class FusedCollectives:
             if mesh.replica_size > 1 else None
         self._anchor = torch.zeros(1, device=device)
         self._slice_tables: Dict[Tuple[int, int], torch.Tensor] = {}
+        self._ag_state: Dict[int, list] = {}
 
     # ---- allocation ---------------------------------------------------------------------------
     def alloc_shard(self, numel: int, dtype: torch.dtype) -> torch.Tensor:
@@ -130,6 +131,28 @@ class FusedCollectives:
             return
         g = self.shard
         self.C.p2p_allgather(g.table_of(shard), full, shard.numel() * shard.element_size(), g.size, g.index)
+
+    # ---- fused gather (ag_gemm) ----------------------------------------------------------------
+    AG_CHUNK = 65536
+
+    def gather_range(self, shard: torch.Tensor, full: torch.Tensor, begin_bytes: int, end_bytes: int):
+        g = self.shard
+        self.C.p2p_gather_range(g.table_of(shard), full, shard.numel() * shard.element_size(), begin_bytes, end_bytes)
+
+    def ag_request(self, shard: torch.Tensor, full: torch.Tensor, begin_bytes: int, end_bytes: int, dependent: bool):
+        """Descriptor of 'gather bytes [begin, end) of this unit into `full`' for a GEMM to carry."""
+        g = self.shard
+        key = full.data_ptr()
+        st = self._ag_state.get(key)
+        total = full.numel() * full.element_size()
+        if st is None:
+            n_chunks = (total + self.AG_CHUNK - 1) // self.AG_CHUNK
+            st = [torch.zeros(n_chunks, dtype=torch.int32, device=self.device), 0]
+            self._ag_state[key] = st
+        st[1] += 1
+        return dict(table=g.table_of(shard), full=full, shard_bytes=shard.numel() * shard.element_size(),
+                    begin=int(begin_bytes), end=int(end_bytes), world=g.size, rank=g.index, flags=st[0], epoch=st[1],
+                    dependent=bool(dependent))
 
     # ---- gradient path ------------------------------------------------------------------------
     def reduce_scatter(self, full: torch.Tensor, shard32: torch.Tensor, scale: float, sumsq: Optional[torch.Tensor]):

@@ -14,6 +14,7 @@ from dataclasses import dataclass, field
 from typing import Dict, Iterable, List, Sequence, Tuple
 
 ALIGN_ELEMS = 64  # 128 B at bf16, 256 B at fp32
+MATRIX_ALIGN_ELEMS = 32768  # the first matrix starts on a 64 KiB (bf16) boundary = one fused-gather ready-flag chunk
 
 
 def _ceil_to(x: int, m: int) -> int:
@@ -34,6 +35,7 @@ class UnitLayout:
     slots: List[ParamSlot]
     total: int        # padded flat length (elements)
     shard_world: int
+    matrix_begin: int = 0   # element offset of the first >=2-D parameter (vectors/norm gains come before it)
 
     @property
     def shard_numel(self) -> int:
@@ -72,17 +74,22 @@ class UnitLayout:
 
 
 def build_layout(name: str, named_shapes: Sequence[Tuple[str, Tuple[int, ...]]], shard_world: int,
-                 align: int = ALIGN_ELEMS) -> UnitLayout:
-    slots, cur = [], 0
+                 align: int = ALIGN_ELEMS, matrix_align: int = MATRIX_ALIGN_ELEMS) -> UnitLayout:
+    """Slots in the given order.  Callers list vectors (norm gains, biases) first: they form a small prefix that
+    is gathered on its own, and everything from ``matrix_begin`` on can ride inside a GEMM (fused all-gather)."""
+    slots, cur, matrix_begin = [], 0, None
     for pname, shape in named_shapes:
         n = 1
         for d in shape:
             n *= int(d)
         cur = _ceil_to(cur, align)
+        if matrix_begin is None and len(shape) >= 2:
+            cur = _ceil_to(cur, matrix_align)
+            matrix_begin = cur
         slots.append(ParamSlot(pname, tuple(int(d) for d in shape), n, cur))
         cur += n
     total = _ceil_to(max(cur, 1), shard_world * align)
-    return UnitLayout(name, slots, total, shard_world)
+    return UnitLayout(name, slots, total, shard_world, total if matrix_begin is None else matrix_begin)
 
 
 def dim0_chunk(rows: int, world: int, rank: int) -> Tuple[int, int]:

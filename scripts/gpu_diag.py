@@ -164,6 +164,14 @@ def main(groups):
                 fwd_ms_8192x4096=ms, fwd_gbs=2 * xb.numel() * 2 / ms / 1e6)
         chk("rmsnorm", t_rms)
 
+        def t_addnorm():
+            x = torch.randn(M, D, device=dev).bfloat16(); res = torch.randn(M, D, device=dev); w = (1 + 0.1 * torch.randn(D, device=dev)).bfloat16()
+            dy = torch.randn(M, D, device=dev).bfloat16()
+            y0, ro0, r0 = TK.add_rmsnorm_fwd(x, res, w, 1e-5); y1, ro1, r1 = CK.add_rmsnorm_fwd(x, res, w, 1e-5)
+            dx0, dw0 = TK.rmsnorm_bwd(dy, ro0, w, r0); dx1, dw1 = CK.rmsnorm_bwd(dy, ro1, w, r1)
+            rec("add_rmsnorm", y=relerr(y1, y0), res=relerr(ro1, ro0), rstd=relerr(r1, r0), dx=relerr(dx1, dx0), dw=relerr(dw1, dw0))
+        chk("add_rmsnorm", t_addnorm)
+
         def t_rope():
             S, H, KVH, hd = 256, 8, 4, 128
             tab = TK.rope_table(S, hd, device=dev)

@@ -60,12 +60,51 @@ if mode in ("all", "raw"):
     out["reduce_scatter"] = dict(fused_ms=ms_f, nccl_ms=ms_t, fused_GBs_in=bytes_in / ms_f / 1e6, nccl_GBs_in=bytes_in / ms_t / 1e6)
     del fc, tc, full_a, full_b, g
 
+if mode in ("all", "ag"):
+    # raw fused all-gather GEMM: y = x W^T where W is gathered from the peers INSIDE the GEMM kernel
+    from fms_fsdp_b200.ops import cuda_kernels as CK
+    mesh = build_mesh("fsdp")
+    fc = FusedCollectives(mesh, dev)
+    N, Kd, Mx = 12288, 4096, 8192
+    n_full = (N * Kd + 65536) // (world * 64) * (world * 64)
+    n_sh = n_full // world
+    torch.manual_seed(rank)
+    sh = fc.alloc_shard(n_sh, torch.bfloat16); sh.copy_(torch.randn(n_sh, device=dev) * 0.02)
+    full_ref = torch.empty(n_full, dtype=torch.bfloat16, device=dev)
+    fc.begin_step(); fc.all_gather(sh, full_ref)
+    x = torch.randn(Mx, Kd, device=dev).bfloat16()
+    res = {}
+    for dep in (True, False):
+        full = torch.zeros(n_full, dtype=torch.bfloat16, device=dev)
+        W = full[:N * Kd].view(N, Kd)
+        Wref = full_ref[:N * Kd].view(N, Kd)
+        req = fc.ag_request(sh, full, 0, n_full * 2, dep)
+        CK.push_ag_request(req)
+        if not dep:   # prefetch mode: the GEMM reads an already-complete weight, the gather fills `full`
+            y = CK.gemm(x, Wref, "nt")
+        else:
+            y = CK.gemm(x, W, "nt")
+        torch.cuda.synchronize()
+        yref = CK.gemm(x, Wref, "nt")
+        res["dep" if dep else "prefetch"] = dict(consumed=bool(req["consumed"]), gathered_equal=bool(torch.equal(full, full_ref)),
+                                                  y_maxdiff=(y.float() - yref.float()).abs().max().item())
+        def run():
+            r = fc.ag_request(sh, full, 0, n_full * 2, dep); CK.push_ag_request(r); CK.gemm(x, W if dep else Wref, "nt")
+        ms = timed(run)
+        res["dep_ms" if dep else "prefetch_ms"] = ms
+    res["plain_gemm_ms"] = timed(lambda: CK.gemm(x, Wref, "nt"))
+    res["standalone_allgather_ms"] = timed(lambda: fc.all_gather(sh, full_ref))
+    res["bytes_in_MB"] = n_full * 2 * (world - 1) / world / 1e6
+    out["ag_gemm"] = res
+    del fc
+
 if mode in ("all", "engine", "gn"):
     from fms_fsdp_b200.models.llama import LLaMA, LLaMAConfig
     from fms_fsdp_b200.parallel import ShardedAdamW, ShardedModel
     from fms_fsdp_b200.policies import bfSixteen
 
-    def run(impl, strategy, shard=0, steps=4):
+    def run(impl, strategy, shard=0, steps=4, fused_gather="1"):
+        os.environ["FMS_B200_FUSED_GATHER"] = fused_gather
         torch.manual_seed(0); torch.cuda.manual_seed(0)
         cfg = LLaMAConfig(src_vocab_size=4096, emb_dim=1024, nheads=8, kvheads=4, nlayers=4, multiple_of=256, max_expected_seq_len=512)
         with torch.device("meta"):
@@ -117,6 +156,10 @@ if mode in ("all", "engine", "gn"):
     for strat, shard in combos:
         a, ca = run("fused", strat, shard); b, cb = run("torch", strat, shard)
         out[f"engine_{strat}"] = dict(fused=a, torch=b, param_checksum=[ca, cb])
+        if strat == "fsdp":
+            c, cc = run("fused", strat, shard, fused_gather="0")
+            from fms_fsdp_b200.ops import cuda_kernels as CK
+            out["engine_fsdp_fused_nogemmgather"] = dict(res=c, checksum=cc, ag_stats=dict(CK.AG_STATS))
 
 if rank == 0:
     os.makedirs("gpurun_out", exist_ok=True)
