@@ -131,8 +131,12 @@ class ShardedModel(nn.Module):
             self.s_compute = torch.cuda.current_stream(self.device)
             self.s_gather = torch.cuda.Stream(self.device)
             self.s_reduce = torch.cuda.Stream(self.device)
+            self.s_opt = torch.cuda.Stream(self.device)
         else:
-            self.s_compute = self.s_gather = self.s_reduce = None
+            self.s_compute = self.s_gather = self.s_reduce = self.s_opt = None
+        import os as _os0
+        self.async_optimizer = (self.is_cuda and self.mesh.shard_size == 1
+                                and _os0.environ.get("FMS_B200_ASYNC_OPT", "1") == "1")
 
         blocks, root_modules = model.engine_units()
         self.blocks: List[ShardUnit] = []
@@ -216,6 +220,7 @@ class ShardedModel(nn.Module):
         u.exp_avg = torch.zeros(n, dtype=torch.float32, device=self.device)
         u.exp_avg_sq = torch.zeros(n, dtype=torch.float32, device=self.device)
         u.ev_gathered = self._event()
+        u.ev_updated = self._event()
         if self.mesh.shard_size == 1:
             # nothing to gather: parameters live in the shard itself
             for _, p in params:
@@ -290,6 +295,8 @@ class ShardedModel(nn.Module):
     def _wait_gather(self, u: ShardUnit, allow_pending_dependent: bool = False):
         if u.full is None:
             self._start_gather(u)
+        if self.async_optimizer:
+            self.s_compute.wait_event(u.ev_updated)   # this unit's (asynchronous) AdamW update has landed
         if u.gather_pending:
             if getattr(u, "gather_fused", False):
                 req = getattr(u, "ag_req", None)
@@ -529,6 +536,8 @@ class ShardedModel(nn.Module):
     # ------------------------------------------------------------------ full-parameter access
     def gather_unit_full(self, u: ShardUnit, which: str = "master") -> torch.Tensor:
         """All-gather one unit's fp32 shard (master / exp_avg / exp_avg_sq) into a flat fp32 tensor."""
+        if self.async_optimizer:
+            torch.cuda.current_stream(self.device).wait_stream(self.s_opt)
         shard = getattr(u, which)
         if self.mesh.shard_size == 1:
             return shard.float() if shard.dtype != torch.float32 else shard

@@ -35,10 +35,24 @@ class ShardedAdamW(torch.optim.Optimizer):
         lr, (b1, b2), eps, wd = float(g["lr"]), g["betas"], g["eps"], g["weight_decay"]
         eng = self.engine
         coef = eng._clip_coef
-        for u in eng.units:
-            K = kernels_for(u.master)
-            K.adamw_step(u.master, u.grad_shard, u.exp_avg, u.exp_avg_sq,
-                         None if u.lowp is u.master else u.lowp, lr, b1, b2, eps, wd, self._step, coef)
+
+        def update_all():
+            for u in eng.units:  # root first, then blocks in forward order: the order the next forward needs them
+                K = kernels_for(u.master)
+                K.adamw_step(u.master, u.grad_shard, u.exp_avg, u.exp_avg_sq,
+                             None if u.lowp is u.master else u.lowp, lr, b1, b2, eps, wd, self._step, coef)
+                if eng.async_optimizer:
+                    u.ev_updated.record(eng.s_opt)
+
+        if eng.async_optimizer:
+            # Bandwidth-bound update on a side stream: it overlaps the next forward's (compute-bound) GEMMs; each
+            # unit's forward waits only for that unit's own update (``ShardedModel._wait_gather``).  Only when no
+            # peer reads our shards (shard group of 1) -- otherwise the cross-GPU step barrier orders everything.
+            eng.s_opt.wait_stream(eng.s_compute)
+            with torch.cuda.stream(eng.s_opt):
+                update_all()
+        else:
+            update_all()
         eng._clip_coef = None
         eng.step_count = self._step
         return loss
