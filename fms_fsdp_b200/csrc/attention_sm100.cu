@@ -435,24 +435,21 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tm, __nv_bfloat16* __restri
       tmem_ld_32x32b_x32(tS + 64, *reinterpret_cast<uint32_t(*)[32]>(&v[64]));
       tmem_ld_32x32b_x32(tS + 96, *reinterpret_cast<uint32_t(*)[32]>(&v[96]));
       tmem_ld_wait();
-      float mx = -INFINITY;
+      // row max on the RAW scores (scale > 0 commutes with max); masking only on the diagonal / ragged last tile
       if (diag || kv0 + 128 > S) {
 #pragma unroll
         for (int i = 0; i < 128; ++i) {
           const int kv = kv0 + i;
-          float x = __uint_as_float(v[i]) * scale_log2;
-          if (kv > q_idx || kv >= S) x = -INFINITY;
-          v[i] = __float_as_uint(x);
-          mx = fmaxf(mx, x);
-        }
-      } else {
-#pragma unroll
-        for (int i = 0; i < 128; ++i) {
-          const float x = __uint_as_float(v[i]) * scale_log2;
-          v[i] = __float_as_uint(x);
-          mx = fmaxf(mx, x);
+          if (kv > q_idx || kv >= S) v[i] = 0xff800000u;  // -inf
         }
       }
+      float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+      for (int i = 0; i < 128; i += 2) {
+        mx0 = fmaxf(mx0, __uint_as_float(v[i]));
+        mx1 = fmaxf(mx1, __uint_as_float(v[i + 1]));
+      }
+      const float mx = fmaxf(mx0, mx1) * scale_log2;
       const float m_new = fmaxf(m_ref, mx);
       const bool grow = (m_new - m_ref) > 8.f;
       if (j == 0) {
@@ -484,8 +481,8 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tm, __nv_bfloat16* __restri
         uint32_t w[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-          const float p0 = exp2f(__uint_as_float(v[c * 32 + 2 * i]) - m_ref);
-          const float p1 = exp2f(__uint_as_float(v[c * 32 + 2 * i + 1]) - m_ref);
+          const float p0 = exp2f(fmaf(__uint_as_float(v[c * 32 + 2 * i]), scale_log2, -m_ref));
+          const float p1 = exp2f(fmaf(__uint_as_float(v[c * 32 + 2 * i + 1]), scale_log2, -m_ref));
           l_sum += p0 + p1;
           w[i] = pack_bf16x2(p0, p1);
         }
@@ -532,7 +529,8 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tm, __nv_bfloat16* __restri
 // ===================================================================================== backward prep
 // delta[b,h,s] = sum_d dO[b,s,h,d] * O[b,s,h,d]      (one warp per (row, head))
 __global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16* __restrict__ o,
-                                  float* __restrict__ delta, int B, int S, int H, int HD) {
+                                  float* __restrict__ delta, const float* __restrict__ lse, float* __restrict__ lse2,
+                                  int B, int S, int H, int HD, int ld) {
   const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (gw >= B * S * H) return;
   const int h = gw % H;
@@ -548,7 +546,8 @@ __global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ dout, const 
   s = warp_sum(s);
   if (lane == 0) {
     const int b = (int)(bs / S), sq = (int)(bs % S);
-    delta[((size_t)b * H + h) * S + sq] = s;
+    delta[((size_t)b * H + h) * ld + sq] = s;
+    if (lse2) lse2[((size_t)b * H + h) * ld + sq] = lse[((size_t)b * H + h) * S + sq] * LOG2E;  // log2-domain copy
   }
 }
 
@@ -854,6 +853,12 @@ static int g_attn_bwd_version = 2;
 // (WG p owns T[p] and its own P^T/dS^T smem tiles), the streamed (Q,dO)/(K,V) ring is 3 deep and the score GEMMs
 // run two iterations ahead of the accumulate GEMMs, so neither the tensor pipe nor the row owners wait on a
 // single-buffered hand-off.  384 threads: warp 0 TMA, warp 1 MMA, warps 4-7 WG0, warps 8-11 WG1.
+B200_DEVINL void bulk_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
 template <int HD>
 struct Bwd2Cfg {
   static constexpr int NCH = HD / 64;
@@ -862,24 +867,57 @@ struct Bwd2Cfg {
   static constexpr int Y_CHUNK = 64 * 128;
   static constexpr int W_BYTES = 128 * 64 * 2;
   static constexpr int STAGES = 3;
-  static constexpr int SMEM = 2 * X_BYTES + STAGES * 2 * Y_BYTES + 4 * W_BYTES + 2 * 128 * 4 + 1024 + 256;
+  static constexpr int STAT_BYTES = 128 * 4;   // per stage: lse2[64] | delta[64] of the streamed q rows (DKDV)
+  static constexpr int SMEM = 2 * X_BYTES + STAGES * 2 * Y_BYTES + STAGES * STAT_BYTES + 1024 + 256;
 };
+
+// one 32-column chunk of the row owner's work: (S or S^T, dP or dP^T) fp32 -> P, dS as packed bf16 pairs written
+// back into TENSOR MEMORY over the first 16 of the 32 columns just read (row per lane): they become the TMEM-A
+// operands of the accumulate GEMMs, so neither P nor dS ever touches shared memory.
+template <int MODE, bool MASK>
+B200_DEVINL void bwd_chunk(const uint32_t (&a)[32], const uint32_t (&d)[32], uint32_t tP, uint32_t tdS, int c,
+                           int x_idx, int y0, int S, const float* stat, float row_lse2, float row_delta,
+                           float scale_log2, float scale) {
+  uint32_t pk[16], dk[16];
+#pragma unroll
+  for (int i = 0; i < 32; i += 2) {
+    float pv[2], dv[2];
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      float l2, dl;
+      if constexpr (MODE == MODE_DKDV) { l2 = stat[c + i + e]; dl = stat[64 + c + i + e]; }
+      else { l2 = row_lse2; dl = row_delta; }
+      float p = exp2f(fmaf(__uint_as_float(a[i + e]), scale_log2, -l2));
+      if constexpr (MASK) {
+        const int y_idx = y0 + c + i + e;
+        const bool masked = (MODE == MODE_DKDV) ? ((x_idx > y_idx) || (y_idx >= S) || (x_idx >= S))
+                                                : ((y_idx > x_idx) || (y_idx >= S) || (x_idx >= S));
+        if (masked) p = 0.f;
+      }
+      pv[e] = p;
+      dv[e] = p * (__uint_as_float(d[i + e]) - dl) * scale;
+    }
+    pk[i >> 1] = pack_bf16x2(pv[0], pv[1]);
+    dk[i >> 1] = pack_bf16x2(dv[0], dv[1]);
+  }
+  if constexpr (MODE == MODE_DKDV) tmem_st_32x32b_x16(tP, pk);
+  tmem_st_32x32b_x16(tdS, dk);
+}
 
 template <int HD, int MODE>
 __global__ void __launch_bounds__(ATT2_THREADS, 1)
 attn_bwd2_kernel(const __grid_constant__ CUtensorMap tm_qkv128, const __grid_constant__ CUtensorMap tm_qkv64,
                  const __grid_constant__ CUtensorMap tm_do128, const __grid_constant__ CUtensorMap tm_do64,
-                 const float* __restrict__ lse, const float* __restrict__ delta, __nv_bfloat16* __restrict__ dqkv,
-                 int S, int H, int KVH, float scale, int n_t128) {
+                 const float* __restrict__ lse2g, const float* __restrict__ delta, __nv_bfloat16* __restrict__ dqkv,
+                 int S, int H, int KVH, float scale, int n_t128, int ld) {
   using C = Bwd2Cfg<HD>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sX1 = smem;
   uint8_t* sX2 = sX1 + C::X_BYTES;
   uint8_t* sY = sX2 + C::X_BYTES;                          // [stage][Y1 | Y2]
-  uint8_t* sW = sY + C::STAGES * 2 * C::Y_BYTES;           // [parity][W1 | W2]
-  float* sStat = reinterpret_cast<float*>(sW + 4 * C::W_BYTES);   // [parity][lse2 64 | delta 64]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sStat) + 2 * 128 * 4);
+  float* sStat = reinterpret_cast<float*>(sY + C::STAGES * 2 * C::Y_BYTES);   // [stage][lse2 64 | delta 64]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sStat) + C::STAGES * C::STAT_BYTES);
   uint64_t* x_full = bars;
   uint64_t* y_full = bars + 1;     // [3]
   uint64_t* y_empty = bars + 4;    // [3]
@@ -904,13 +942,14 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tm_qkv128, const __grid_con
   const int per_head = s_hi - s_lo;
   const int n_iter = per_head * head_n;
   const int xrow0 = b * S + t128 * 128;
+  constexpr uint32_t Y_TX = 2 * C::Y_BYTES + (MODE == MODE_DKDV ? C::STAT_BYTES : 0);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_qkv128); tma_prefetch_desc(&tm_qkv64);
     tma_prefetch_desc(&tm_do128); tma_prefetch_desc(&tm_do64);
     mbar_init(x_full, 1);
     for (int i = 0; i < 3; ++i) { mbar_init(&y_full[i], 1); mbar_init(&y_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&t_full[i], 1); mbar_init(&w_full[i], 4); mbar_init(&acc_done[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&t_full[i], 1); mbar_init(&w_full[i], 8); mbar_init(&acc_done[i], 1); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
@@ -941,7 +980,7 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tm_qkv128, const __grid_con
         uint8_t* y1 = sY + st * 2 * C::Y_BYTES;
         uint8_t* y2 = y1 + C::Y_BYTES;
         mbar_wait(&y_empty[st], ph ^ 1);
-        mbar_arrive_expect_tx(&y_full[st], 2 * C::Y_BYTES);
+        mbar_arrive_expect_tx(&y_full[st], Y_TX);
         for (int c = 0; c < C::NCH; ++c) {
           if constexpr (MODE == MODE_DKDV) {
             tma_load_2d(y1 + c * C::Y_CHUNK, &tm_qkv64, &y_full[st], hh * HD + 64 * c, yrow);
@@ -950,6 +989,12 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tm_qkv128, const __grid_con
             tma_load_2d(y1 + c * C::Y_CHUNK, &tm_qkv64, &y_full[st], (H + kvh) * HD + 64 * c, yrow);
             tma_load_2d(y2 + c * C::Y_CHUNK, &tm_qkv64, &y_full[st], (H + KVH + kvh) * HD + 64 * c, yrow);
           }
+        }
+        if constexpr (MODE == MODE_DKDV) {
+          // per-column softmax statistics of the streamed q rows ride on the same barrier (two 256 B bulk copies)
+          const size_t so = ((size_t)b * H + hh) * ld + (size_t)t64 * 64;
+          bulk_load_1d(sStat + st * 128, lse2g + so, 256, &y_full[st]);
+          bulk_load_1d(sStat + st * 128 + 64, delta + so, 256, &y_full[st]);
         }
         if (++st == 3) { st = 0; ph ^= 1; }
       }
@@ -983,100 +1028,66 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tm_qkv128, const __grid_con
     };
     mbar_wait(x_full, 0);
     if (n_iter > 0) issue_scores(0);
-    if (n_iter > 1) issue_scores(1);
     for (int it = 0; it < n_iter; ++it) {
       const int p = it & 1, st = it % 3;
+      if (it + 1 < n_iter) issue_scores(it + 1);   // T[(it+1)&1] was drained before w_full(it-1) was signalled
       mbar_wait(&w_full[p], (it >> 1) & 1);
       tc_fence_after();
       if (lane == 0) {
         const uint32_t y1 = smem_u32(sY + st * 2 * C::Y_BYTES), y2 = y1 + C::Y_BYTES;
-        const uint32_t w1 = smem_u32(sW + p * 2 * C::W_BYTES), w2 = w1 + C::W_BYTES;
+        // P^T / dS^T (or dS) sit in TMEM over the score columns: warpgroup g wrote the 16 packed columns of its
+        // 32-column half at column offset 32*g  ->  K-step t (16 streamed rows) = 8 columns at 32*(t/2) + 8*(t%2)
+        const uint32_t tP = tmem + p * 128, tdS = tP + 64;
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
+          const uint32_t co = 32 * (t >> 1) + 8 * (t & 1);
           if constexpr (MODE == MODE_DKDV)
-            umma_bf16_ss(tmem_acc1, make_smem_desc(w1 + t * 32, 0, 1024),
-                         make_smem_desc(y2 + t * 2048, C::Y_CHUNK, 1024), idesc_a, (it | t) != 0);
-          umma_bf16_ss(tmem_acc2, make_smem_desc(w2 + t * 32, 0, 1024),
-                       make_smem_desc(y1 + t * 2048, C::Y_CHUNK, 1024), idesc_a, (it | t) != 0);
+            umma_bf16_ts(tmem_acc1, tP + co, make_smem_desc(y2 + t * 2048, C::Y_CHUNK, 1024), idesc_a, (it | t) != 0);
+          umma_bf16_ts(tmem_acc2, tdS + co, make_smem_desc(y1 + t * 2048, C::Y_CHUNK, 1024), idesc_a, (it | t) != 0);
         }
         umma_commit(&y_empty[st]);
         umma_commit(&acc_done[p]);
       }
       __syncwarp();
-      if (it + 2 < n_iter) issue_scores(it + 2);
     }
   } else if (warp >= 4) {
-    const int p = (warp - 4) >> 2;            // warpgroup parity
+    // 8 row-owner warps; warpgroup g owns columns [32g, 32g+32) of EVERY iteration's 128 x 64 score tiles
+    const int g = (warp - 4) >> 2;
+    const int p = g;                          // (epilogue split below)
     const int q4 = warp & 3;
     const int r = q4 * 32 + lane;
-    const int tid128 = (warp & 3) * 32 + lane;
     const uint32_t lane_addr = static_cast<uint32_t>(q4 * 32) << 16;
     const int x_idx = t128 * 128 + r;
-    uint8_t* sW1 = sW + p * 2 * C::W_BYTES;
-    uint8_t* sW2 = sW1 + C::W_BYTES;
-    float* stat = sStat + p * 128;
     float row_lse2 = 0.f, row_delta = 0.f;
     if constexpr (MODE == MODE_DQ) {
-      const size_t sidx = ((size_t)b * H + head_lo) * S + min(x_idx, S - 1);
-      row_lse2 = lse[sidx] * LOG2E;
+      const size_t sidx = ((size_t)b * H + head_lo) * ld + min(x_idx, S - 1);
+      row_lse2 = lse2g[sidx];
       row_delta = delta[sidx];
     }
-    for (int it = p; it < n_iter; it += 2) {
-      const int hh = head_lo + it / per_head;
+    for (int it = 0; it < n_iter; ++it) {
+      const int par = it & 1;
       const int t64 = s_lo + it % per_head;
       const int y0 = t64 * 64;
-      if constexpr (MODE == MODE_DKDV) {
-        named_bar_sync(1 + p, 128);  // previous iteration's readers of stat[p] are done
-        const int qi = y0 + (tid128 & 63);
-        const size_t sidx = ((size_t)b * H + hh) * S + min(qi, S - 1);
-        stat[tid128] = (tid128 < 64) ? lse[sidx] * LOG2E : delta[sidx];
-        named_bar_sync(1 + p, 128);
-      }
-      mbar_wait(&t_full[p], (it >> 1) & 1);
+      const int st = it % 3;
+      const float* stat = sStat + st * 128;
+      if constexpr (MODE == MODE_DKDV) mbar_wait(&y_full[st], (it / 3) & 1);   // the stats landed (TMA -> generic visibility)
+      mbar_wait(&t_full[par], (it >> 1) & 1);
       tc_fence_after();
-      if (it >= 2) mbar_wait(&acc_done[p], ((it >> 1) - 1) & 1);  // W[p] free again
-      const uint32_t t1 = tmem + p * 128 + lane_addr, t2 = t1 + 64;
-#pragma unroll 1
-      for (int c = 0; c < 64; c += 32) {
-        uint32_t a[32], d[32];
-        tmem_ld_32x32b_x32(t1 + c, a);
-        tmem_ld_32x32b_x32(t2 + c, d);
-        tmem_ld_wait();
-        float pr[32], ds[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const int y_idx = y0 + c + i;
-          float l2, dl;
-          bool masked;
-          if constexpr (MODE == MODE_DKDV) {
-            l2 = stat[c + i]; dl = stat[64 + c + i];
-            masked = (x_idx > y_idx) || (y_idx >= S) || (x_idx >= S);
-          } else {
-            l2 = row_lse2; dl = row_delta;
-            masked = (y_idx > x_idx) || (y_idx >= S) || (x_idx >= S);
-          }
-          const float pv = masked ? 0.f : exp2f(__uint_as_float(a[i]) * scale_log2 - l2);
-          pr[i] = pv;
-          ds[i] = pv * (__uint_as_float(d[i]) - dl) * scale;
-        }
-        const int cb = c >> 3;
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          uint4 u;
-          if constexpr (MODE == MODE_DKDV) {
-            u.x = pack_bf16x2(pr[g * 8 + 0], pr[g * 8 + 1]); u.y = pack_bf16x2(pr[g * 8 + 2], pr[g * 8 + 3]);
-            u.z = pack_bf16x2(pr[g * 8 + 4], pr[g * 8 + 5]); u.w = pack_bf16x2(pr[g * 8 + 6], pr[g * 8 + 7]);
-            st_swz128(sW1, r, cb + g, u);
-          }
-          u.x = pack_bf16x2(ds[g * 8 + 0], ds[g * 8 + 1]); u.y = pack_bf16x2(ds[g * 8 + 2], ds[g * 8 + 3]);
-          u.z = pack_bf16x2(ds[g * 8 + 4], ds[g * 8 + 5]); u.w = pack_bf16x2(ds[g * 8 + 6], ds[g * 8 + 7]);
-          st_swz128(sW2, r, cb + g, u);
-        }
-      }
-      fence_proxy_async_smem();
+      const uint32_t t1 = tmem + par * 128 + lane_addr + 32 * g, t2 = t1 + 64;
+      uint32_t a0[32], d0[32];
+      tmem_ld_32x32b_x32(t1, a0);
+      tmem_ld_32x32b_x32(t2, d0);
+      tmem_ld_wait();
+      // only tiles touching the causal diagonal or the sequence end need per-element masking
+      const bool need_mask = (y0 < t128 * 128 + 128 && y0 + 64 > t128 * 128) || (y0 + 64 > S) || (t128 * 128 + 128 > S);
+      if (need_mask)
+        bwd_chunk<MODE, true>(a0, d0, t1, t2, 32 * g, x_idx, y0, S, stat, row_lse2, row_delta, scale_log2, scale);
+      else
+        bwd_chunk<MODE, false>(a0, d0, t1, t2, 32 * g, x_idx, y0, S, stat, row_lse2, row_delta, scale_log2, scale);
+      tmem_st_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&w_full[p]);
+      if (lane == 0) mbar_arrive(&w_full[par]);
     }
     // epilogue: WG0 stores acc2 (dK | dQ), WG1 stores acc1 (dV); in DQ mode the two groups split acc2's columns
     if (n_iter > 0) mbar_wait(&acc_done[(n_iter - 1) & 1], ((n_iter - 1) >> 1) & 1);
@@ -1174,8 +1185,11 @@ static int launch_bwd(const void* dout, const void* qkv, const void* o, const fl
     const long long warps = (long long)B * S * H;
     const int threads = 256;
     const long long blocks = (warps * 32 + threads - 1) / threads;
+    // v2: rows padded to a multiple of 64 so a 64-float TMA bulk copy never leaves the row; plane 1 = lse * log2(e)
+    const int ld = (g_attn_bwd_version == 2) ? ((S + 63) / 64) * 64 : S;
+    float* lse2 = (g_attn_bwd_version == 2) ? delta + (size_t)B * H * ld : nullptr;
     attn_delta_kernel<<<(unsigned)blocks, threads, 0, st>>>((const __nv_bfloat16*)dout, (const __nv_bfloat16*)o, delta,
-                                                            B, S, H, HD);
+                                                            lse, lse2, B, S, H, HD, ld);
   }
   const int n_t = (S + 127) / 128;
   if (g_attn_bwd_version == 2) {
@@ -1190,10 +1204,12 @@ static int launch_bwd(const void* dout, const void* qkv, const void* o, const fl
       if (e != cudaSuccess) return (int)e;
       configured2 = true;
     }
-    j1<<<dim3(n_t, KVH, B), ATT2_THREADS, C2::SMEM, st>>>(q128, q64, d128, d64, lse, delta, (__nv_bfloat16*)dqkv, S, H,
-                                                         KVH, scale, n_t);
-    j2<<<dim3(n_t, H, B), ATT2_THREADS, C2::SMEM, st>>>(q128, q64, d128, d64, lse, delta, (__nv_bfloat16*)dqkv, S, H, KVH,
-                                                       scale, n_t);
+    const int ld2 = ((S + 63) / 64) * 64;
+    const float* lse2p = delta + (size_t)B * H * ld2;
+    j1<<<dim3(n_t, KVH, B), ATT2_THREADS, C2::SMEM, st>>>(q128, q64, d128, d64, lse2p, delta, (__nv_bfloat16*)dqkv, S, H,
+                                                         KVH, scale, n_t, ld2);
+    j2<<<dim3(n_t, H, B), ATT2_THREADS, C2::SMEM, st>>>(q128, q64, d128, d64, lse2p, delta, (__nv_bfloat16*)dqkv, S, H, KVH,
+                                                       scale, n_t, ld2);
     return (int)cudaGetLastError();
   }
   auto k1 = attn_bwd_kernel<HD, MODE_DKDV>;

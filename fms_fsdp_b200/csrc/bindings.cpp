@@ -23,6 +23,8 @@ DECL int b200_rmsnorm_bwd(const void*, const void*, const void*, const float*, v
                           cudaStream_t);
 DECL int b200_add_rmsnorm_fwd(const void*, const float*, const void*, void*, float*, float*, int, int, float, cudaStream_t);
 DECL int b200_rmsnorm_bwd_f32(const void*, const float*, const void*, const float*, float*, float*, float*, int, int, cudaStream_t);
+DECL int b200_rmsnorm_gated_fwd(const void*, const void*, const void*, void*, float*, int, int, float, cudaStream_t);
+DECL int b200_rmsnorm_gated_bwd(const void*, const void*, const void*, const void*, const float*, void*, void*, float*, float*, int, int, cudaStream_t);
 DECL int b200_rope(void*, const float*, int, int, int, int, int, int, int, int, int, cudaStream_t);
 DECL int b200_swiglu_fwd(const void*, void*, long long, int, int, cudaStream_t);
 DECL int b200_swiglu_bwd(const void*, const void*, void*, long long, int, int, cudaStream_t);
@@ -170,6 +172,36 @@ std::vector<at::Tensor> rmsnorm_bwd_f32(const at::Tensor& dy, const at::Tensor& 
                              part.data_ptr<float>(), dw.data_ptr<float>(), M, D, cur_stream()), "rmsnorm_bwd_f32", 2);
   return {dx, dw};
 }
+std::vector<at::Tensor> rmsnorm_gated_fwd(const at::Tensor& x, const at::Tensor& z, const at::Tensor& w, double eps) {
+  c10::cuda::CUDAGuard guard(x.device());
+  need(x, "x", at::kBFloat16);
+  need(z, "z", at::kBFloat16);
+  need(w, "w", at::kBFloat16);
+  TORCH_CHECK(x.is_contiguous() && z.is_contiguous());
+  const int D = x.size(-1), M = x.numel() / D;
+  auto y = at::empty_like(x);
+  auto rstd = at::empty({M}, x.options().dtype(at::kFloat));
+  check(b200_rmsnorm_gated_fwd(x.data_ptr(), z.data_ptr(), w.data_ptr(), y.data_ptr(), rstd.data_ptr<float>(), M, D,
+                               (float)eps, cur_stream()), "rmsnorm_gated_fwd");
+  return {y, rstd};
+}
+std::vector<at::Tensor> rmsnorm_gated_bwd(const at::Tensor& dy, const at::Tensor& x, const at::Tensor& z,
+                                          const at::Tensor& w, const at::Tensor& rstd) {
+  c10::cuda::CUDAGuard guard(x.device());
+  need(dy, "dy", at::kBFloat16);
+  need(x, "x", at::kBFloat16);
+  need(z, "z", at::kBFloat16);
+  TORCH_CHECK(dy.is_contiguous() && x.is_contiguous() && z.is_contiguous());
+  const int D = x.size(-1), M = x.numel() / D;
+  auto dx = at::empty_like(x);
+  auto dz = at::empty_like(z);
+  auto part = at::empty({b200_rmsnorm_bwd_grid(M), D}, x.options().dtype(at::kFloat));
+  auto dw = at::empty({D}, x.options().dtype(at::kFloat));
+  check(b200_rmsnorm_gated_bwd(dy.data_ptr(), x.data_ptr(), z.data_ptr(), w.data_ptr(), rstd.data_ptr<float>(),
+                               dx.data_ptr(), dz.data_ptr(), part.data_ptr<float>(), dw.data_ptr<float>(), M, D, cur_stream()),
+        "rmsnorm_gated_bwd", 2);
+  return {dx, dz, dw};
+}
 void rope(at::Tensor& qkv, const at::Tensor& table, int64_t seq_len, int64_t nrot_heads, int64_t hd, int64_t rot,
           bool inverse, int64_t pos_offset, bool interleaved) {
   c10::cuda::CUDAGuard guard(qkv.device());
@@ -290,7 +322,8 @@ at::Tensor attn_bwd(const at::Tensor& dout, const at::Tensor& qkv, const at::Ten
   need(lse, "lse", at::kFloat);
   TORCH_CHECK(qkv.is_contiguous() && dout.is_contiguous() && o.is_contiguous() && lse.is_contiguous());
   auto dqkv = at::empty_like(qkv);
-  auto delta = at::empty({B, H, S}, qkv.options().dtype(at::kFloat));
+  // [2 planes: delta | lse*log2e][B][H][S padded to 64]
+  auto delta = at::empty({2, B, H, ((S + 63) / 64) * 64}, qkv.options().dtype(at::kFloat));
   check(b200_attn_bwd(dout.data_ptr(), qkv.data_ptr(), o.data_ptr(), lse.data_ptr<float>(), dqkv.data_ptr(),
                       delta.data_ptr<float>(), B, S, H, KVH, hd, (float)scale, cur_stream()), "attn_bwd", 3);
   return dqkv;
@@ -413,6 +446,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("rmsnorm_bwd", &rmsnorm_bwd);
   m.def("add_rmsnorm_fwd", &add_rmsnorm_fwd);
   m.def("rmsnorm_bwd_f32", &rmsnorm_bwd_f32);
+  m.def("rmsnorm_gated_fwd", &rmsnorm_gated_fwd);
+  m.def("rmsnorm_gated_bwd", &rmsnorm_gated_bwd);
   m.def("rope", &rope);
   m.def("swiglu_fwd", &swiglu_fwd);
   m.def("swiglu_bwd", &swiglu_bwd);

@@ -258,6 +258,117 @@ __global__ void __launch_bounds__(NT) rmsnorm_bwd_f32_kernel(const __nv_bfloat16
   }
 }
 
+// ----------------------------------------------------- gated RMSNorm (Mamba2 RMSNormGated, norm_before_gate=False)
+// y = rmsnorm(x * silu(z)) * w over the whole row (ngroups = 1).  SURVEY.md M5.
+__global__ void __launch_bounds__(NT) rmsnorm_gated_fwd_kernel(const __nv_bfloat16* __restrict__ x,
+                                                               const __nv_bfloat16* __restrict__ z,
+                                                               const __nv_bfloat16* __restrict__ w,
+                                                               __nv_bfloat16* __restrict__ y, float* __restrict__ rstd,
+                                                               int M, int D, float eps) {
+  __shared__ float sh[32];
+  for (int row = blockIdx.x; row < M; row += gridDim.x) {
+    float u[MAXC][8];
+    float ss = 0.f;
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c) {
+      const int col = (c * NT + threadIdx.x) * 8;
+      if (col < D) {
+        float a[8], g[8];
+        load8(x + (size_t)row * D + col, a);
+        load8(z + (size_t)row * D + col, g);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          u[c][i] = a[i] * g[i] / (1.f + __expf(-g[i]));
+          ss += u[c][i] * u[c][i];
+        }
+      }
+    }
+    ss = block_sum(ss, sh);
+    const float r = rsqrtf(ss / (float)D + eps);
+    if (threadIdx.x == 0) rstd[row] = r;
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c) {
+      const int col = (c * NT + threadIdx.x) * 8;
+      if (col < D) {
+        float wv[8], o[8];
+        load8(w + col, wv);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] = u[c][i] * r * wv[i];
+        store8(y + (size_t)row * D + col, o);
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(NT) rmsnorm_gated_bwd_kernel(const __nv_bfloat16* __restrict__ dy,
+                                                               const __nv_bfloat16* __restrict__ x,
+                                                               const __nv_bfloat16* __restrict__ z,
+                                                               const __nv_bfloat16* __restrict__ w,
+                                                               const float* __restrict__ rstd,
+                                                               __nv_bfloat16* __restrict__ dx, __nv_bfloat16* __restrict__ dz,
+                                                               float* __restrict__ dw_part, int M, int D) {
+  __shared__ float sh[32];
+  float dwacc[MAXC][8], wv[MAXC][8];
+#pragma unroll
+  for (int c = 0; c < MAXC; ++c) {
+    const int col = (c * NT + threadIdx.x) * 8;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) dwacc[c][i] = 0.f;
+    if (col < D) load8(w + col, wv[c]);
+  }
+  for (int row = blockIdx.x; row < M; row += gridDim.x) {
+    const float r = rstd[row];
+    float g[MAXC][8], uh[MAXC][8], xs[MAXC][8], zs[MAXC][8];
+    float dot = 0.f;
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c) {
+      const int col = (c * NT + threadIdx.x) * 8;
+      if (col < D) {
+        float a[8];
+        load8(dy + (size_t)row * D + col, a);
+        load8(x + (size_t)row * D + col, xs[c]);
+        load8(z + (size_t)row * D + col, zs[c]);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float sig = 1.f / (1.f + __expf(-zs[c][i]));
+          const float uu = xs[c][i] * zs[c][i] * sig;
+          uh[c][i] = uu * r;
+          g[c][i] = a[i] * wv[c][i];
+          dot += g[c][i] * uh[c][i];
+          dwacc[c][i] += a[i] * uh[c][i];
+        }
+      }
+    }
+    dot = block_sum(dot, sh) / (float)D;
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c) {
+      const int col = (c * NT + threadIdx.x) * 8;
+      if (col < D) {
+        float ox[8], oz[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float du = r * (g[c][i] - uh[c][i] * dot);
+          const float zz = zs[c][i];
+          const float sig = 1.f / (1.f + __expf(-zz));
+          ox[i] = du * zz * sig;
+          oz[i] = du * xs[c][i] * sig * (1.f + zz * (1.f - sig));
+        }
+        store8(dx + (size_t)row * D + col, ox);
+        store8(dz + (size_t)row * D + col, oz);
+      }
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < MAXC; ++c) {
+    const int col = (c * NT + threadIdx.x) * 8;
+    if (col < D) {
+      float4* o = reinterpret_cast<float4*>(dw_part + (size_t)blockIdx.x * D + col);
+      o[0] = make_float4(dwacc[c][0], dwacc[c][1], dwacc[c][2], dwacc[c][3]);
+      o[1] = make_float4(dwacc[c][4], dwacc[c][5], dwacc[c][6], dwacc[c][7]);
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------- RoPE
 // In place on heads [0, nrot) of a fused [M, nheads_total*hd] projection; pairs (2i, 2i+1);
 // table [S, rot/2, 2] fp32 (cos, sin).  One thread = 8 elements = 4 pairs.
@@ -565,6 +676,23 @@ extern "C" int b200_rmsnorm_bwd_f32(const void* dy, const float* x, const void* 
   if (D % 8 || D > NT * 8 * MAXC) return -1;
   const int grid = b200_rmsnorm_bwd_grid(M);
   rmsnorm_bwd_f32_kernel<<<grid, NT, 0, s>>>((const __nv_bfloat16*)dy, x, (const __nv_bfloat16*)w, rstd, dx, dw_part, M, D);
+  colsum_kernel<<<(D + 255) / 256, 256, 0, s>>>(dw_part, dw, grid, D);
+  CK();
+}
+extern "C" int b200_rmsnorm_gated_fwd(const void* x, const void* z, const void* w, void* y, float* rstd, int M, int D,
+                                      float eps, cudaStream_t s) {
+  if (D % 8 || D > NT * 8 * MAXC) return -1;
+  rmsnorm_gated_fwd_kernel<<<M < 148 * 8 ? M : 148 * 8, NT, 0, s>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)z,
+                                                                   (const __nv_bfloat16*)w, (__nv_bfloat16*)y, rstd, M, D, eps);
+  CK();
+}
+extern "C" int b200_rmsnorm_gated_bwd(const void* dy, const void* x, const void* z, const void* w, const float* rstd,
+                                      void* dx, void* dz, float* dw_part, float* dw, int M, int D, cudaStream_t s) {
+  if (D % 8 || D > NT * 8 * MAXC) return -1;
+  const int grid = b200_rmsnorm_bwd_grid(M);
+  rmsnorm_gated_bwd_kernel<<<grid, NT, 0, s>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, (const __nv_bfloat16*)z,
+                                               (const __nv_bfloat16*)w, rstd, (__nv_bfloat16*)dx, (__nv_bfloat16*)dz, dw_part,
+                                               M, D);
   colsum_kernel<<<(D + 255) / 256, 256, 0, s>>>(dw_part, dw, grid, D);
   CK();
 }

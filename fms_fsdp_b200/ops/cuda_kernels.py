@@ -149,8 +149,20 @@ def add_rmsnorm_fwd(x, res, w, eps):
     return y, res_out, rstd
 
 
-rmsnorm_gated_fwd = torch_kernels.rmsnorm_gated_fwd
-rmsnorm_gated_bwd = torch_kernels.rmsnorm_gated_bwd
+def rmsnorm_gated_fwd(x, z, w, eps, group_size):
+    D = x.shape[-1]
+    if x.dtype != torch.bfloat16 or group_size != D or D % 8 or D > 8192:
+        return torch_kernels.rmsnorm_gated_fwd(x, z, w, eps, group_size)
+    y, rstd = _C.rmsnorm_gated_fwd(x.contiguous(), z.contiguous(), _bf16c(w), float(eps))
+    return y, rstd.view(-1, 1)
+
+
+def rmsnorm_gated_bwd(dy, x, z, w, rstd, group_size):
+    D = x.shape[-1]
+    if x.dtype != torch.bfloat16 or group_size != D or D % 8 or D > 8192:
+        return torch_kernels.rmsnorm_gated_bwd(dy, x, z, w, rstd, group_size)
+    dx, dz, dw = _C.rmsnorm_gated_bwd(dy.contiguous(), x.contiguous(), z.contiguous(), _bf16c(w), rstd.reshape(-1))
+    return dx, dz, dw
 
 # ------------------------------------------------------------------------------------------ RoPE
 rope_table = torch_kernels.rope_table

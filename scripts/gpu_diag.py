@@ -172,6 +172,14 @@ def main(groups):
             rec("add_rmsnorm", y=relerr(y1, y0), res=relerr(ro1, ro0), rstd=relerr(r1, r0), dx=relerr(dx1, dx0), dw=relerr(dw1, dw0))
         chk("add_rmsnorm", t_addnorm)
 
+        def t_gated():
+            x = torch.randn(M, D, device=dev).bfloat16(); z = torch.randn(M, D, device=dev).bfloat16(); w = (1 + 0.1 * torch.randn(D, device=dev)).bfloat16()
+            dy = torch.randn(M, D, device=dev).bfloat16()
+            y0, r0 = TK.rmsnorm_gated_fwd(x, z, w, 1e-5, D); y1, r1 = CK.rmsnorm_gated_fwd(x, z, w, 1e-5, D)
+            g0 = TK.rmsnorm_gated_bwd(dy, x, z, w, r0, D); g1 = CK.rmsnorm_gated_bwd(dy, x, z, w, r1, D)
+            rec("rmsnorm_gated", y=relerr(y1, y0), dx=relerr(g1[0], g0[0]), dz=relerr(g1[1], g0[1]), dw=relerr(g1[2], g0[2]))
+        chk("rmsnorm_gated", t_gated)
+
         def t_rope():
             S, H, KVH, hd = 256, 8, 4, 128
             tab = TK.rope_table(S, hd, device=dev)
