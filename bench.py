@@ -15,6 +15,7 @@ host->device copy of that step's tokens/labels from pinned memory and a device->
 from __future__ import annotations
 
 import argparse
+import contextlib
 import json
 import os
 import subprocess
@@ -42,6 +43,7 @@ def _args():
     p.add_argument("--collective_impl", default="auto")
     p.add_argument("--ac", default="0", help="selective activation checkpointing fraction, e.g. 0, 1/2, 1")
     p.add_argument("--nlayers", type=int, default=0, help="debug only: override depth (result is flagged invalid)")
+    p.add_argument("--profile", default="", help="write a per-kernel device-time table of 2 extra steps to this path")
     return p.parse_args()
 
 
@@ -227,6 +229,18 @@ def run_ours(a):
         if a.nlayers:
             out["invalid"] = "debug depth override"
         print(json.dumps(out), flush=True)
+    if a.profile:
+        # per-kernel device-time table of two more steps (never part of a reported number)
+        from torch.profiler import ProfilerActivity, profile
+        ctx = profile(activities=[ProfilerActivity.CUDA]) if rank == 0 else contextlib.nullcontext()
+        with ctx as prof:
+            for i in range(2):
+                step_device(dev_tok[i % 4], dev_lab[i % 4])
+            sync_all()
+        if rank == 0:
+            os.makedirs(os.path.dirname(a.profile) or ".", exist_ok=True)
+            with open(a.profile, "w") as f:
+                f.write(prof.key_averages().table(sort_by="cuda_time_total", row_limit=60, max_name_column_width=90))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

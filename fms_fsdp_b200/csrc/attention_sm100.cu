@@ -904,6 +904,20 @@ B200_DEVINL void bwd_chunk(const uint32_t (&a)[32], const uint32_t (&d)[32], uin
   tmem_st_32x32b_x16(tdS, dk);
 }
 
+#ifdef B200_ATTN_TRACE
+// timeline instrumentation (scripts/attn_trace.cu only): clock64 stamps of one CTA, [iteration][16 slots]
+__device__ long long* g_attn_trace = nullptr;
+__device__ int g_attn_trace_cta = 0;
+__device__ int g_attn_trace_mode = 0;
+#define ATRACE(it, slot)                                                                                   \
+  do {                                                                                                     \
+    if (g_attn_trace && MODE == g_attn_trace_mode && (int)blockIdx.x == g_attn_trace_cta && blockIdx.y == 0 && blockIdx.z == 0 && (it) < 64) \
+      g_attn_trace[(it) * 16 + (slot)] = clock64();                                                        \
+  } while (0)
+#else
+#define ATRACE(it, slot) do {} while (0)
+#endif
+
 template <int HD, int MODE>
 __global__ void __launch_bounds__(ATT2_THREADS, 1)
 attn_bwd2_kernel(const __grid_constant__ CUtensorMap tm_qkv128, const __grid_constant__ CUtensorMap tm_qkv64,
@@ -980,6 +994,7 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tm_qkv128, const __grid_con
         uint8_t* y1 = sY + st * 2 * C::Y_BYTES;
         uint8_t* y2 = y1 + C::Y_BYTES;
         mbar_wait(&y_empty[st], ph ^ 1);
+        ATRACE(it, 13);
         mbar_arrive_expect_tx(&y_full[st], Y_TX);
         for (int c = 0; c < C::NCH; ++c) {
           if constexpr (MODE == MODE_DKDV) {
@@ -1004,9 +1019,11 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tm_qkv128, const __grid_con
     constexpr uint32_t idesc_a = make_idesc_bf16(128, HD, false, true);
     auto issue_scores = [&](int it) {
       const int st = it % 3;
+      if (lane == 0) ATRACE(it, 10);
       mbar_wait(&y_full[st], (it / 3) & 1);
       tc_fence_after();
       if (lane == 0) {
+        ATRACE(it, 0);
         const uint32_t x1 = smem_u32(sX1), x2 = smem_u32(sX2);
         const uint32_t y1 = smem_u32(sY + st * 2 * C::Y_BYTES), y2 = y1 + C::Y_BYTES;
         const uint32_t t1 = tmem + (it & 1) * 128, t2 = t1 + 64;
@@ -1023,6 +1040,7 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tm_qkv128, const __grid_con
           umma_bf16_ss(t2, make_smem_desc(x2 + xo, 0, 1024), make_smem_desc(y2 + yo, 0, 1024), idesc_t, kk != 0);
         }
         umma_commit(&t_full[it & 1]);
+        ATRACE(it, 11);
       }
       __syncwarp();
     };
@@ -1034,6 +1052,7 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tm_qkv128, const __grid_con
       mbar_wait(&w_full[p], (it >> 1) & 1);
       tc_fence_after();
       if (lane == 0) {
+        ATRACE(it, 1);
         const uint32_t y1 = smem_u32(sY + st * 2 * C::Y_BYTES), y2 = y1 + C::Y_BYTES;
         // P^T / dS^T (or dS) sit in TMEM over the score columns: warpgroup g wrote the 16 packed columns of its
         // 32-column half at column offset 32*g  ->  K-step t (16 streamed rows) = 8 columns at 32*(t/2) + 8*(t%2)
@@ -1047,6 +1066,7 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tm_qkv128, const __grid_con
         }
         umma_commit(&y_empty[st]);
         umma_commit(&acc_done[p]);
+        ATRACE(it, 12);
       }
       __syncwarp();
     }
@@ -1071,13 +1091,16 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tm_qkv128, const __grid_con
       const int st = it % 3;
       const float* stat = sStat + st * 128;
       if constexpr (MODE == MODE_DKDV) mbar_wait(&y_full[st], (it / 3) & 1);   // the stats landed (TMA -> generic visibility)
+      if (lane == 0 && q4 == 0) ATRACE(it, 2 + 4 * g);
       mbar_wait(&t_full[par], (it >> 1) & 1);
       tc_fence_after();
+      if (lane == 0 && q4 == 0) ATRACE(it, 3 + 4 * g);
       const uint32_t t1 = tmem + par * 128 + lane_addr + 32 * g, t2 = t1 + 64;
       uint32_t a0[32], d0[32];
       tmem_ld_32x32b_x32(t1, a0);
       tmem_ld_32x32b_x32(t2, d0);
       tmem_ld_wait();
+      if (lane == 0 && q4 == 0) ATRACE(it, 4 + 4 * g);
       // only tiles touching the causal diagonal or the sequence end need per-element masking
       const bool need_mask = (y0 < t128 * 128 + 128 && y0 + 64 > t128 * 128) || (y0 + 64 > S) || (t128 * 128 + 128 > S);
       if (need_mask)
@@ -1088,6 +1111,7 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tm_qkv128, const __grid_con
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&w_full[par]);
+      if (lane == 0 && q4 == 0) ATRACE(it, 5 + 4 * g);
     }
     // epilogue: WG0 stores acc2 (dK | dQ), WG1 stores acc1 (dV); in DQ mode the two groups split acc2's columns
     if (n_iter > 0) mbar_wait(&acc_done[(n_iter - 1) & 1], ((n_iter - 1) >> 1) & 1);

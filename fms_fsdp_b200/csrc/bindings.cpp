@@ -19,7 +19,7 @@ DECL int b200_p2p_gather_range(const void* const*, void*, long long, long long, 
 DECL int b200_ts_mma_probe(const void*, const void*, float*, cudaStream_t);
 DECL int b200_rmsnorm_fwd(const void*, const void*, void*, float*, int, int, float, cudaStream_t);
 DECL int b200_rmsnorm_bwd_grid(int);
-DECL int b200_rmsnorm_bwd(const void*, const void*, const void*, const float*, void*, float*, float*, int, int,
+DECL int b200_rmsnorm_bwd(const void*, const void*, const void*, const float*, const void*, void*, float*, float*, int, int,
                           cudaStream_t);
 DECL int b200_add_rmsnorm_fwd(const void*, const float*, const void*, void*, float*, float*, int, int, float, cudaStream_t);
 DECL int b200_rmsnorm_bwd_f32(const void*, const float*, const void*, const float*, float*, float*, float*, int, int, cudaStream_t);
@@ -128,7 +128,7 @@ std::vector<at::Tensor> rmsnorm_fwd(const at::Tensor& x, const at::Tensor& w, do
   return {y, rstd};
 }
 std::vector<at::Tensor> rmsnorm_bwd(const at::Tensor& dy, const at::Tensor& x, const at::Tensor& w,
-                                    const at::Tensor& rstd) {
+                                    const at::Tensor& rstd, const c10::optional<at::Tensor>& dres) {
   c10::cuda::CUDAGuard guard(x.device());
   need(dy, "dy", at::kBFloat16);
   need(x, "x", at::kBFloat16);
@@ -139,7 +139,13 @@ std::vector<at::Tensor> rmsnorm_bwd(const at::Tensor& dy, const at::Tensor& x, c
   auto dx = at::empty_like(x);
   auto part = at::empty({b200_rmsnorm_bwd_grid(M), D}, x.options().dtype(at::kFloat));
   auto dw = at::empty({D}, x.options().dtype(at::kFloat));
-  check(b200_rmsnorm_bwd(dy.data_ptr(), x.data_ptr(), w.data_ptr(), rstd.data_ptr<float>(), dx.data_ptr(),
+  const void* dres_p = nullptr;
+  if (dres.has_value() && dres->defined()) {
+    need(*dres, "dres", at::kBFloat16);
+    TORCH_CHECK(dres->is_contiguous() && dres->numel() == x.numel(), "rmsnorm_bwd: dres shape");
+    dres_p = dres->data_ptr();
+  }
+  check(b200_rmsnorm_bwd(dy.data_ptr(), x.data_ptr(), w.data_ptr(), rstd.data_ptr<float>(), dres_p, dx.data_ptr(),
                          part.data_ptr<float>(), dw.data_ptr<float>(), M, D, cur_stream()), "rmsnorm_bwd", 2);
   return {dx, dw};
 }
@@ -443,7 +449,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.doc() = "fms_fsdp_b200 sm_100a kernels";
   m.def("gemm", &gemm);
   m.def("rmsnorm_fwd", &rmsnorm_fwd);
-  m.def("rmsnorm_bwd", &rmsnorm_bwd);
+  m.def("rmsnorm_bwd", &rmsnorm_bwd, py::arg("dy"), py::arg("x"), py::arg("w"), py::arg("rstd"), py::arg("dres") = py::none());
   m.def("add_rmsnorm_fwd", &add_rmsnorm_fwd);
   m.def("rmsnorm_bwd_f32", &rmsnorm_bwd_f32);
   m.def("rmsnorm_gated_fwd", &rmsnorm_gated_fwd);

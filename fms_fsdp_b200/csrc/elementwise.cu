@@ -45,36 +45,54 @@ B200_DEVINL void store8(__nv_bfloat16* p, const float (&f)[8]) {
 // One CTA per row (grid-stride).  Row cached in registers: D <= NT*8*MAXC.
 constexpr int MAXC = 4;
 
-__global__ void __launch_bounds__(NT) rmsnorm_fwd_kernel(const __nv_bfloat16* __restrict__ x,
-                                                         const __nv_bfloat16* __restrict__ w,
-                                                         __nv_bfloat16* __restrict__ y, float* __restrict__ rstd,
-                                                         int M, int D, float eps) {
+B200_DEVINL void unpack8(const uint4& u, float (&f)[8]) {
+  float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+  f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
+}
+
+// NC = ceil(D / (NT*8)) 16-byte vectors per thread.  Rows stay in registers as PACKED bf16 (4 regs per vector) so
+// 6-8 CTAs are resident per SM and every thread has all of its row's loads in flight before the reduction.
+template <int NC>
+__global__ void __launch_bounds__(NT, 6) rmsnorm_fwd_kernel(const __nv_bfloat16* __restrict__ x,
+                                                            const __nv_bfloat16* __restrict__ w,
+                                                            __nv_bfloat16* __restrict__ y, float* __restrict__ rstd,
+                                                            int M, int D, float eps) {
   __shared__ float sh[32];
+  uint4 wq[NC];
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
+    const int col = (c * NT + threadIdx.x) * 8;
+    wq[c] = (col < D) ? *reinterpret_cast<const uint4*>(w + col) : make_uint4(0, 0, 0, 0);
+  }
   for (int row = blockIdx.x; row < M; row += gridDim.x) {
     const __nv_bfloat16* xr = x + (size_t)row * D;
-    float v[MAXC][8];
+    uint4 xq[NC];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      const int col = (c * NT + threadIdx.x) * 8;
+      xq[c] = (col < D) ? *reinterpret_cast<const uint4*>(xr + col) : make_uint4(0, 0, 0, 0);
+    }
     float ss = 0.f;
 #pragma unroll
-    for (int c = 0; c < MAXC; ++c) {
-      const int col = (c * NT + threadIdx.x) * 8;
-      if (col < D) {
-        load8(xr + col, v[c]);
+    for (int c = 0; c < NC; ++c) {
+      float v[8];
+      unpack8(xq[c], v);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) ss += v[c][i] * v[c][i];
-      }
+      for (int i = 0; i < 8; ++i) ss += v[i] * v[i];
     }
     ss = block_sum(ss, sh);
     const float r = rsqrtf(ss / (float)D + eps);
     if (threadIdx.x == 0) rstd[row] = r;
     __nv_bfloat16* yr = y + (size_t)row * D;
 #pragma unroll
-    for (int c = 0; c < MAXC; ++c) {
+    for (int c = 0; c < NC; ++c) {
       const int col = (c * NT + threadIdx.x) * 8;
       if (col < D) {
-        float wv[8], o[8];
-        load8(w + col, wv);
+        float v[8], wv[8], o[8];
+        unpack8(xq[c], v);
+        unpack8(wq[c], wv);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) o[i] = v[c][i] * r * wv[i];
+        for (int i = 0; i < 8; ++i) o[i] = v[i] * r * wv[i];
         store8(yr + col, o);
       }
     }
@@ -82,58 +100,73 @@ __global__ void __launch_bounds__(NT) rmsnorm_fwd_kernel(const __nv_bfloat16* __
 }
 
 // dx = r * (g - xhat * mean(g*xhat)),  g = dy*w,  xhat = x*r ;  dw_partial[cta] += dy*xhat
-__global__ void __launch_bounds__(NT) rmsnorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy,
+template <int NC>
+__global__ void __launch_bounds__(NT, (NC <= 2 ? 4 : 2)) rmsnorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy,
                                                          const __nv_bfloat16* __restrict__ x,
                                                          const __nv_bfloat16* __restrict__ w,
                                                          const float* __restrict__ rstd,
+                                                         const __nv_bfloat16* __restrict__ dres,
                                                          __nv_bfloat16* __restrict__ dx, float* __restrict__ dw_part,
                                                          int M, int D) {
+  // dres (optional): gradient arriving on the residual branch that forked off x; summed into dx here so autograd
+  // never runs a separate accumulate kernel
   __shared__ float sh[32];
-  float dwacc[MAXC][8];
+  float dwacc[NC][8];
+  uint4 wq[NC];
 #pragma unroll
-  for (int c = 0; c < MAXC; ++c)
+  for (int c = 0; c < NC; ++c) {
+    const int col = (c * NT + threadIdx.x) * 8;
 #pragma unroll
     for (int i = 0; i < 8; ++i) dwacc[c][i] = 0.f;
-  float wv[MAXC][8];
-#pragma unroll
-  for (int c = 0; c < MAXC; ++c) {
-    const int col = (c * NT + threadIdx.x) * 8;
-    if (col < D) load8(w + col, wv[c]);
+    wq[c] = (col < D) ? *reinterpret_cast<const uint4*>(w + col) : make_uint4(0, 0, 0, 0);
   }
   for (int row = blockIdx.x; row < M; row += gridDim.x) {
+    uint4 dq[NC], xq[NC];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      const int col = (c * NT + threadIdx.x) * 8;
+      const bool ok = col < D;
+      dq[c] = ok ? *reinterpret_cast<const uint4*>(dy + (size_t)row * D + col) : make_uint4(0, 0, 0, 0);
+      xq[c] = ok ? *reinterpret_cast<const uint4*>(x + (size_t)row * D + col) : make_uint4(0, 0, 0, 0);
+    }
     const float r = rstd[row];
-    float g[MAXC][8], xh[MAXC][8];
     float dot = 0.f;
 #pragma unroll
-    for (int c = 0; c < MAXC; ++c) {
-      const int col = (c * NT + threadIdx.x) * 8;
-      if (col < D) {
-        float a[8], b[8];
-        load8(dy + (size_t)row * D + col, a);
-        load8(x + (size_t)row * D + col, b);
+    for (int c = 0; c < NC; ++c) {
+      float a[8], b[8], wv[8];
+      unpack8(dq[c], a);
+      unpack8(xq[c], b);
+      unpack8(wq[c], wv);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          xh[c][i] = b[i] * r;
-          g[c][i] = a[i] * wv[c][i];
-          dot += g[c][i] * xh[c][i];
-          dwacc[c][i] += a[i] * xh[c][i];
-        }
+      for (int i = 0; i < 8; ++i) {
+        const float xh = b[i] * r;
+        dot += a[i] * wv[i] * xh;
+        dwacc[c][i] += a[i] * xh;
       }
     }
     dot = block_sum(dot, sh) / (float)D;
 #pragma unroll
-    for (int c = 0; c < MAXC; ++c) {
+    for (int c = 0; c < NC; ++c) {
       const int col = (c * NT + threadIdx.x) * 8;
       if (col < D) {
-        float o[8];
+        float a[8], b[8], wv[8], o[8];
+        unpack8(dq[c], a);
+        unpack8(xq[c], b);
+        unpack8(wq[c], wv);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) o[i] = r * (g[c][i] - xh[c][i] * dot);
+        for (int i = 0; i < 8; ++i) o[i] = r * (a[i] * wv[i] - b[i] * r * dot);
+        if (dres) {
+          float e[8];
+          load8(dres + (size_t)row * D + col, e);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) o[i] += e[i];
+        }
         store8(dx + (size_t)row * D + col, o);
       }
     }
   }
 #pragma unroll
-  for (int c = 0; c < MAXC; ++c) {
+  for (int c = 0; c < NC; ++c) {
     const int col = (c * NT + threadIdx.x) * 8;
     if (col < D) {
       float4* o = reinterpret_cast<float4*>(dw_part + (size_t)blockIdx.x * D + col);
@@ -143,13 +176,22 @@ __global__ void __launch_bounds__(NT) rmsnorm_bwd_kernel(const __nv_bfloat16* __
   }
 }
 
-// out[d] = sum_p part[p, d]
-__global__ void colsum_kernel(const float* __restrict__ part, float* __restrict__ out, int P, int D) {
-  const int d = blockIdx.x * blockDim.x + threadIdx.x;
-  if (d >= D) return;
+// out[d] = sum_p part[p, d]   (CTA = 32 columns x 8 row slices)
+__global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ part, float* __restrict__ out, int P, int D) {
+  __shared__ float sh[8][33];
+  const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
+  const int d = blockIdx.x * 32 + lane;
   float s = 0.f;
-  for (int p = 0; p < P; ++p) s += part[(size_t)p * D + d];
-  out[d] = s;
+  if (d < D)
+    for (int p = slice; p < P; p += 8) s += part[(size_t)p * D + d];
+  sh[slice][lane] = s;
+  __syncthreads();
+  if (slice == 0 && d < D) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += sh[k][lane];
+    out[d] = t;
+  }
 }
 
 // ------------------------------------------------------------- fused add + RMSNorm (fp32 residual stream)
@@ -403,31 +445,59 @@ __global__ void rope_halfsplit_kernel(__nv_bfloat16* __restrict__ qkv, const flo
   }
 }
 
-__global__ void rope_kernel(__nv_bfloat16* __restrict__ qkv, const float* __restrict__ table, int M, int seq_len,
-                            int row_stride, int nrot_heads, int hd, int rot, float sign, int pos_offset) {
-  const int vec_per_head = rot / 8;
-  const size_t total = (size_t)M * nrot_heads * vec_per_head;
-  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-       idx += (size_t)gridDim.x * blockDim.x) {
-    const int vi = (int)(idx % vec_per_head);
-    const size_t t = idx / vec_per_head;
-    const int head = (int)(t % nrot_heads);
-    const size_t row = t / nrot_heads;
-    const int pos = (int)(row % seq_len) + pos_offset;
-    __nv_bfloat16* p = qkv + row * row_stride + head * hd + vi * 8;
-    float f[8];
-    load8(p, f);
-    const float4* cs = reinterpret_cast<const float4*>(table + ((size_t)pos * (rot / 2) + vi * 4) * 2);
-    const float4 c0 = cs[0], c1 = cs[1];
-    const float cosv[4] = {c0.x, c0.z, c1.x, c1.z};
-    const float sinv[4] = {c0.y * sign, c0.w * sign, c1.y * sign, c1.w * sign};
-    float o[8];
+__global__ void __launch_bounds__(256) rope_kernel(__nv_bfloat16* __restrict__ qkv, const float* __restrict__ table,
+                                                   int M, int seq_len, int row_stride, int nrot_heads, int hd, int rot,
+                                                   float sign, int pos_offset) {
+  // one CTA per row (grid-stride); 4 independent 16-byte vectors in flight per thread
+  const int vph = rot / 8;
+  const int per_row = nrot_heads * vph;
+  for (int row = blockIdx.x; row < M; row += gridDim.x) {
+    const int pos = row % seq_len + pos_offset;
+    __nv_bfloat16* base = qkv + (size_t)row * row_stride;
+    const float* trow = table + (size_t)pos * rot;          // [rot/2][cos, sin]
+    const bool same_vi = (256 % vph) == 0;                    // then v0 + k*256 has the same vi for every k
+    for (int v0 = threadIdx.x; v0 < per_row; v0 += 4 * 256) {
+      uint4 q[4];
+      float4 c0[4], c1[4];
+      if (same_vi) {
+        const float4* cs = reinterpret_cast<const float4*>(trow + (v0 % vph) * 8);
+        c0[0] = cs[0];
+        c1[0] = cs[1];
+      }
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      o[2 * i] = f[2 * i] * cosv[i] - f[2 * i + 1] * sinv[i];
-      o[2 * i + 1] = f[2 * i] * sinv[i] + f[2 * i + 1] * cosv[i];
+      for (int k = 0; k < 4; ++k) {
+        const int v = v0 + k * 256;
+        if (v < per_row) {
+          const int head = v / vph, vi = v - head * vph;
+          q[k] = *reinterpret_cast<const uint4*>(base + head * hd + vi * 8);
+          if (!same_vi) {
+            const float4* cs = reinterpret_cast<const float4*>(trow + vi * 8);
+            c0[k] = cs[0];
+            c1[k] = cs[1];
+          } else if (k > 0) {
+            c0[k] = c0[0];
+            c1[k] = c1[0];
+          }
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int v = v0 + k * 256;
+        if (v < per_row) {
+          const int head = v / vph, vi = v - head * vph;
+          float f[8], o[8];
+          unpack8(q[k], f);
+          const float cosv[4] = {c0[k].x, c0[k].z, c1[k].x, c1[k].z};
+          const float sinv[4] = {c0[k].y * sign, c0[k].w * sign, c1[k].y * sign, c1[k].w * sign};
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            o[2 * i] = f[2 * i] * cosv[i] - f[2 * i + 1] * sinv[i];
+            o[2 * i + 1] = f[2 * i] * sinv[i] + f[2 * i + 1] * cosv[i];
+          }
+          store8(base + head * hd + vi * 8, o);
+        }
+      }
     }
-    store8(p, o);
   }
 }
 
@@ -620,17 +690,34 @@ __global__ void adamw_kernel(float* __restrict__ master, const GradT* __restrict
 template <typename T>
 __global__ void sumsq_kernel(const T* __restrict__ x, size_t n, float* __restrict__ out) {
   __shared__ float sh[32];
-  float s = 0.f;
-  for (size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < n;
-       i += (size_t)gridDim.x * blockDim.x * 4) {
+  constexpr int EPV = 16 / sizeof(T);      // elements per 16-byte vector
+  constexpr int UNR = 4;                   // vectors in flight per thread
+  const size_t nvec = n / EPV;
+  const uint4* xv = reinterpret_cast<const uint4*>(x);
+  auto acc = [](const uint4& u) -> float {
     if constexpr (sizeof(T) == 2) {
-      uint2 u = *reinterpret_cast<const uint2*>(x + i);
-      float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y);
-      s += a.x * a.x + a.y * a.y + b.x * b.x + b.y * b.y;
+      float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+      return a.x * a.x + a.y * a.y + b.x * b.x + b.y * b.y + c.x * c.x + c.y * c.y + d.x * d.x + d.y * d.y;
     } else {
-      float4 f = *reinterpret_cast<const float4*>(x + i);
-      s += f.x * f.x + f.y * f.y + f.z * f.z + f.w * f.w;
+      const float f0 = __uint_as_float(u.x), f1 = __uint_as_float(u.y), f2 = __uint_as_float(u.z), f3 = __uint_as_float(u.w);
+      return f0 * f0 + f1 * f1 + f2 * f2 + f3 * f3;
     }
+  };
+  float s = 0.f;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (; i + (UNR - 1) * stride < nvec; i += UNR * stride) {
+    uint4 u[UNR];
+#pragma unroll
+    for (int k = 0; k < UNR; ++k) u[k] = xv[i + k * stride];
+#pragma unroll
+    for (int k = 0; k < UNR; ++k) s += acc(u[k]);
+  }
+  for (; i < nvec; i += stride) s += acc(xv[i]);
+  // tail (n not a multiple of the vector width)
+  if (blockIdx.x == 0 && threadIdx.x < (int)(n - nvec * EPV)) {
+    const float t = (float)x[nvec * EPV + threadIdx.x];
+    s += t * t;
   }
   s = block_sum(s, sh);
   if (threadIdx.x == 0) atomicAdd(out, s);
@@ -650,18 +737,28 @@ using namespace b200;
 extern "C" int b200_rmsnorm_fwd(const void* x, const void* w, void* y, float* rstd, int M, int D, float eps,
                                 cudaStream_t s) {
   if (D % 8 || D > NT * 8 * MAXC) return -1;
-  rmsnorm_fwd_kernel<<<M < 148 * 8 ? M : 148 * 8, NT, 0, s>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)w,
-                                                             (__nv_bfloat16*)y, rstd, M, D, eps);
+  const int grid = M < 148 * 6 ? M : 148 * 6;
+  const int nc = (D + NT * 8 - 1) / (NT * 8);
+#define B200_RMS_FWD(NCV)                                                                                     \
+  rmsnorm_fwd_kernel<NCV><<<grid, NT, 0, s>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)w, (__nv_bfloat16*)y, \
+                                              rstd, M, D, eps)
+  if (nc == 1) B200_RMS_FWD(1); else if (nc == 2) B200_RMS_FWD(2); else if (nc == 3) B200_RMS_FWD(3); else B200_RMS_FWD(4);
+#undef B200_RMS_FWD
   CK();
 }
 extern "C" int b200_rmsnorm_bwd_grid(int M) { return M < 148 * 4 ? M : 148 * 4; }
-extern "C" int b200_rmsnorm_bwd(const void* dy, const void* x, const void* w, const float* rstd, void* dx,
-                                float* dw_part, float* dw, int M, int D, cudaStream_t s) {
+extern "C" int b200_rmsnorm_bwd(const void* dy, const void* x, const void* w, const float* rstd, const void* dres,
+                                void* dx, float* dw_part, float* dw, int M, int D, cudaStream_t s) {
   if (D % 8 || D > NT * 8 * MAXC) return -1;
   const int grid = b200_rmsnorm_bwd_grid(M);
-  rmsnorm_bwd_kernel<<<grid, NT, 0, s>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, (const __nv_bfloat16*)w,
-                                         rstd, (__nv_bfloat16*)dx, dw_part, M, D);
-  colsum_kernel<<<(D + 255) / 256, 256, 0, s>>>(dw_part, dw, grid, D);
+  const int nc = (D + NT * 8 - 1) / (NT * 8);
+#define B200_RMS_BWD(NCV)                                                                                       \
+  rmsnorm_bwd_kernel<NCV><<<grid, NT, 0, s>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x,                 \
+                                              (const __nv_bfloat16*)w, rstd, (const __nv_bfloat16*)dres,     \
+                                              (__nv_bfloat16*)dx, dw_part, M, D)
+  if (nc == 1) B200_RMS_BWD(1); else if (nc == 2) B200_RMS_BWD(2); else if (nc == 3) B200_RMS_BWD(3); else B200_RMS_BWD(4);
+#undef B200_RMS_BWD
+  colsum_kernel<<<(D + 31) / 32, 256, 0, s>>>(dw_part, dw, grid, D);
   CK();
 }
 extern "C" int b200_add_rmsnorm_fwd(const void* x, const float* res, const void* w, void* y, float* res_out, float* rstd,
@@ -676,7 +773,7 @@ extern "C" int b200_rmsnorm_bwd_f32(const void* dy, const float* x, const void* 
   if (D % 8 || D > NT * 8 * MAXC) return -1;
   const int grid = b200_rmsnorm_bwd_grid(M);
   rmsnorm_bwd_f32_kernel<<<grid, NT, 0, s>>>((const __nv_bfloat16*)dy, x, (const __nv_bfloat16*)w, rstd, dx, dw_part, M, D);
-  colsum_kernel<<<(D + 255) / 256, 256, 0, s>>>(dw_part, dw, grid, D);
+  colsum_kernel<<<(D + 31) / 32, 256, 0, s>>>(dw_part, dw, grid, D);
   CK();
 }
 extern "C" int b200_rmsnorm_gated_fwd(const void* x, const void* z, const void* w, void* y, float* rstd, int M, int D,
@@ -693,15 +790,14 @@ extern "C" int b200_rmsnorm_gated_bwd(const void* dy, const void* x, const void*
   rmsnorm_gated_bwd_kernel<<<grid, NT, 0, s>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, (const __nv_bfloat16*)z,
                                                (const __nv_bfloat16*)w, rstd, (__nv_bfloat16*)dx, (__nv_bfloat16*)dz, dw_part,
                                                M, D);
-  colsum_kernel<<<(D + 255) / 256, 256, 0, s>>>(dw_part, dw, grid, D);
+  colsum_kernel<<<(D + 31) / 32, 256, 0, s>>>(dw_part, dw, grid, D);
   CK();
 }
 extern "C" int b200_rope(void* qkv, const float* table, int M, int seq_len, int row_stride, int nrot_heads, int hd,
                          int rot, int inverse, int pos_offset, int interleaved, cudaStream_t s) {
   if (rot % 16 || hd % 8 || row_stride % 8) return -1;
   if (interleaved) {
-    size_t total = (size_t)M * nrot_heads * (rot / 8);
-    rope_kernel<<<grid_for(total, 256), 256, 0, s>>>((__nv_bfloat16*)qkv, table, M, seq_len, row_stride, nrot_heads,
+    rope_kernel<<<(M < 148 * 8 ? M : 148 * 8), 256, 0, s>>>((__nv_bfloat16*)qkv, table, M, seq_len, row_stride, nrot_heads,
                                                      hd, rot, inverse ? -1.f : 1.f, pos_offset);
   } else {
     size_t total = (size_t)M * nrot_heads * (rot / 16);
@@ -784,8 +880,8 @@ extern "C" int b200_adamw(float* master, const void* grad, int grad_is_bf16, flo
   CK();
 }
 extern "C" int b200_sumsq(const void* x, int is_bf16, long long n, float* out, cudaStream_t s) {
-  if (n % 4) return -1;
-  int g = grid_for((size_t)n / 4, 256, 148 * 8);
+  if (reinterpret_cast<uintptr_t>(x) & 15) return -1;
+  int g = grid_for((size_t)n / 16, 256, 148 * 8);
   if (is_bf16) sumsq_kernel<__nv_bfloat16><<<g, 256, 0, s>>>((const __nv_bfloat16*)x, (size_t)n, out);
   else sumsq_kernel<float><<<g, 256, 0, s>>>((const float*)x, (size_t)n, out);
   CK();

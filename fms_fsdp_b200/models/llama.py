@@ -85,6 +85,10 @@ class RMSNorm(nn.Module):
     def forward(self, x):
         return ops.rmsnorm(x, self.weight, self.eps)
 
+    def fork(self, x):
+        """(norm(x), x) with the residual-branch gradient folded into the norm's backward kernel."""
+        return ops.rmsnorm_fork(x, self.weight, self.eps)
+
 
 class RotaryEmbedding(nn.Module):
     """cos/sin table cache; attrs mirror what the reference exporter reads
@@ -191,12 +195,12 @@ class LLaMABlock(nn.Module):
     def forward(self, x):
         a, cfg = self.attn, self.config
         B, S, _ = x.shape
-        h = self.ln(x)
+        h, x = self.ln.fork(x)
         qkv = a.in_proj.qkv_fused(h)
         qkv = ops.rope_(qkv, self._rot.table(x.device, S), S, a.nheads, a.kvheads, a.head_dim)
         ctx = ops.attention(qkv, a.nheads, a.kvheads, a.head_dim)
         x = a.dense(ctx, residual=x)
-        h = self.ff_ln(x)
+        h, x = self.ff_ln.fork(x)
         gu = self.ff_sub_layer.wg1_fused(h)
         x = self.ff_sub_layer.w2(ops.swiglu(gu), residual=x)
         return x

@@ -132,13 +132,18 @@ def rmsnorm_fwd(x, w, eps):
     return y, rstd
 
 
-def rmsnorm_bwd(dy, x, w, rstd):
+def rmsnorm_bwd(dy, x, w, rstd, dres=None):
+    """``dres``: optional gradient of the residual branch that forked off ``x``; summed into dx inside the kernel."""
+    if dres is not None and (x.dtype != torch.bfloat16 or dres.dtype != torch.bfloat16 or x.shape[-1] % 8 or x.shape[-1] > 8192):
+        dx, dw = rmsnorm_bwd(dy, x, w, rstd)
+        return dx + dres.reshape(dx.shape).to(dx.dtype), dw
     if x.dtype == torch.float32 and dy.dtype == torch.bfloat16 and x.shape[-1] % 8 == 0 and x.shape[-1] <= 8192:
         dx, dw = _C.rmsnorm_bwd_f32(dy.contiguous(), x.contiguous(), _bf16c(w), rstd)   # fp32 residual stream
         return dx, dw
     if x.dtype != torch.bfloat16 or x.shape[-1] % 8 or x.shape[-1] > 8192:
         return torch_kernels.rmsnorm_bwd(dy, x, w, rstd)
-    dx, dw = _C.rmsnorm_bwd(dy.contiguous(), x.contiguous(), _bf16c(w), rstd)
+    dx, dw = _C.rmsnorm_bwd(dy.contiguous(), x.contiguous(), _bf16c(w), rstd,
+                            None if dres is None else dres.reshape(x.shape).contiguous())
     return dx, dw
 
 
@@ -279,7 +284,7 @@ def cross_entropy_fwd_bwd(logits, labels, ignore_index=-100):
 def sumsq(x, out=None):
     if out is None:
         out = torch.zeros((), dtype=torch.float32, device=x.device)
-    if x.dtype not in (torch.bfloat16, torch.float32) or x.numel() % 4 or not x.is_contiguous():
+    if x.dtype not in (torch.bfloat16, torch.float32) or x.data_ptr() % 16 or not x.is_contiguous():
         return torch_kernels.sumsq(x, out)
     _C.sumsq(x, out)
     return out

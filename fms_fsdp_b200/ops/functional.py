@@ -130,6 +130,43 @@ def rmsnorm(x, w, eps=1e-5):
     return _RMSNorm.apply(x, w, eps)
 
 
+class _RMSNormFork(torch.autograd.Function):
+    """(rmsnorm(x), x): the pre-norm residual fork as ONE node, so the gradient of the residual branch is summed into
+    the norm's dx inside the backward kernel instead of by a separate autograd accumulate."""
+
+    @staticmethod
+    def forward(ctx, x, w, eps):
+        K = kernels_for(x)
+        y, rstd = K.rmsnorm_fwd(x.reshape(-1, x.shape[-1]), _wdata(w), eps)
+        ctx.K, ctx.w = K, w
+        ctx.save_for_backward(x, rstd)
+        return y.view_as(x), x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, dy, dres):
+        x, rstd = ctx.saved_tensors
+        K, w = ctx.K, ctx.w
+        D = x.shape[-1]
+        if dy is None:
+            return dres, None, None
+        dx, dw32 = K.rmsnorm_bwd(dy.reshape(-1, D).contiguous(), x.reshape(-1, D), _wdata(w), rstd,
+                                 None if dres is None else dres.reshape(-1, D))
+        dw = None
+        if ctx.needs_input_grad[1]:
+            def put(out, acc):
+                if acc:
+                    out.add_(dw32.to(out.dtype))
+                else:
+                    out.copy_(dw32)
+            dw = _deliver_wgrad(w, put)
+        return dx.view_as(x), dw, None
+
+
+def rmsnorm_fork(x, w, eps=1e-5):
+    """Returns ``(rmsnorm(x) * w, x)``; use the second output as the residual."""
+    return _RMSNormFork.apply(x, w, eps)
+
+
 class _RMSNormGated(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, z, w, eps, group_size):

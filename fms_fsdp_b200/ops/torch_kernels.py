@@ -50,12 +50,14 @@ def rmsnorm_fwd(x, w, eps):
     return y, rstd.squeeze(-1)
 
 
-def rmsnorm_bwd(dy, x, w, rstd):
+def rmsnorm_bwd(dy, x, w, rstd, dres=None):
     xf, dyf, wf = x.float(), dy.float(), w.float()
     r = rstd.unsqueeze(-1)
     xhat = xf * r
     g = dyf * wf
     dx = r * (g - xhat * (g * xhat).mean(-1, keepdim=True))
+    if dres is not None:
+        dx = dx + dres.reshape(dx.shape).float()
     dw = (dyf * xhat).reshape(-1, x.shape[-1]).sum(0)
     return dx.to(x.dtype), dw
 

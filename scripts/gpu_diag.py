@@ -160,8 +160,18 @@ def main(groups):
             dx0, dw0 = TK.rmsnorm_bwd(dy, x, w, r0); dx1, dw1 = CK.rmsnorm_bwd(dy, x, w, r1)
             xb = torch.randn(8192, 4096, device=dev).bfloat16()
             ms = time_ms(lambda: CK.rmsnorm_fwd(xb, w, 1e-5))
-            rec("rmsnorm", y=relerr(y1, y0), rstd=relerr(r1, r0), dx=relerr(dx1, dx0), dw=relerr(dw1, dw0),
-                fwd_ms_8192x4096=ms, fwd_gbs=2 * xb.numel() * 2 / ms / 1e6)
+            dres = torch.randn(M, D, device=dev).bfloat16()
+            dxr = relerr(CK.rmsnorm_bwd(dy, x, w, r1, dres)[0], TK.rmsnorm_bwd(dy, x, w, r0, dres)[0])
+            dyb = torch.randn(8192, 4096, device=dev).bfloat16(); _, rb = CK.rmsnorm_fwd(xb, w, 1e-5)
+            msb = time_ms(lambda: CK.rmsnorm_bwd(dyb, xb, w, rb, dyb))
+            q = torch.randn(8192, 12288, device=dev).bfloat16(); tab = TK.rope_table(4096, 128, device=dev)
+            msr = time_ms(lambda: CK.rope_(q, tab, 4096, 32, 32, 128))
+            g = torch.randn(202383360, device=dev).bfloat16()
+            mss = time_ms(lambda: CK.sumsq(g))
+            rec("rmsnorm", y=relerr(y1, y0), rstd=relerr(r1, r0), dx=relerr(dx1, dx0), dw=relerr(dw1, dw0), dx_dres=dxr,
+                fwd_ms_8192x4096=ms, fwd_gbs=2 * xb.numel() * 2 / ms / 1e6, bwd_dres_ms=msb,
+                bwd_gbs=4 * xb.numel() * 2 / msb / 1e6, rope_ms=msr, rope_gbs=2 * 8192 * 8192 * 2 / msr / 1e6,
+                sumsq_ms=mss, sumsq_gbs=g.numel() * 2 / mss / 1e6)
         chk("rmsnorm", t_rms)
 
         def t_addnorm():

@@ -65,6 +65,16 @@ def test_rmsnorm_rope_swiglu_embedding(K):
     assert rel(y1, y0) < 1e-2 and rel(r1, r0) < 1e-4
     dx0, dw0 = TK.rmsnorm_bwd(dy, x, w, r0); dx1, dw1 = CK.rmsnorm_bwd(dy, x, w, r1)
     assert rel(dx1, dx0) < 1e-2 and rel(dw1, dw0) < 1e-3
+    dres = torch.randn(M, D, device=DEV).bfloat16()     # residual-branch gradient folded into the kernel
+    dx2, _ = CK.rmsnorm_bwd(dy, x, w, r1, dres)
+    assert rel(dx2, TK.rmsnorm_bwd(dy, x, w, r0, dres)[0]) < 1e-2
+    for D2 in (1024, 5120, 8192):                       # other chunk-count instantiations
+        x2 = torch.randn(64, D2, device=DEV).bfloat16(); w2 = (1 + 0.1 * torch.randn(D2, device=DEV)).bfloat16()
+        d2 = torch.randn(64, D2, device=DEV).bfloat16()
+        ya, ra = TK.rmsnorm_fwd(x2, w2, 1e-5); yb, rb = CK.rmsnorm_fwd(x2, w2, 1e-5)
+        assert rel(yb, ya) < 1e-2 and rel(rb, ra) < 1e-4
+        da, wa = TK.rmsnorm_bwd(d2, x2, w2, ra); db, wb = CK.rmsnorm_bwd(d2, x2, w2, rb)
+        assert rel(db, da) < 1e-2 and rel(wb, wa) < 1e-3
     S, H, KVH, hd = 128, 8, 4, 128
     tab = TK.rope_table(S, hd, device=DEV)
     q = torch.randn(2 * S, (H + 2 * KVH) * hd, device=DEV).bfloat16()

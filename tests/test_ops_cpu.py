@@ -30,6 +30,21 @@ def test_rmsnorm():
     _close(y, y2); _close(x.grad, x2.grad); _close(w.grad, w2.grad)
 
 
+def test_rmsnorm_fork_sums_residual_gradient():
+    x = torch.randn(7, 32, requires_grad=True); w = torch.nn.Parameter(torch.rand(32) + 0.5)
+    h, r = ops.rmsnorm_fork(x, w, 1e-5)
+    (r + torch.tanh(h) * 3).pow(2).sum().backward()
+    x2 = x.detach().requires_grad_(); w2 = w.detach().requires_grad_()
+    h2 = x2 * torch.rsqrt(x2.pow(2).mean(-1, keepdim=True) + 1e-5) * w2
+    (x2 + torch.tanh(h2) * 3).pow(2).sum().backward()
+    _close(x.grad, x2.grad); _close(w.grad, w2.grad)
+    # only the residual branch used
+    x3 = x.detach().requires_grad_()
+    _, r3 = ops.rmsnorm_fork(x3, w, 1e-5)
+    r3.sum().backward()
+    _close(x3.grad, torch.ones_like(x3))
+
+
 def test_rmsnorm_gated():
     x = torch.randn(6, 32, requires_grad=True); z = torch.randn(6, 32, requires_grad=True); w = torch.nn.Parameter(torch.rand(32) + 0.5)
     y = ops.rmsnorm_gated(x, z, w, 1e-5, 16); (y * torch.arange(32.)).sum().backward()
