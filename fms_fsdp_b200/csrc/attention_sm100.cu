@@ -365,19 +365,22 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tm, __nv_bfloat16* __restri
     // Tensor-pipe issue order (the pipe executes in issue order, which is what makes the S/P aliasing safe):
     //   QK0_0 QK1_0 | PV0_0 QK0_1 PV1_0 QK1_1 | PV0_1 QK0_2 PV1_1 QK1_2 | ...
     // QK_t(j+1) overwrites S_t only after PV_t(j) -- which reads P_t from the same TMEM columns -- was issued.
+    // every MMA batch is issued by ONE elected lane of the converged warp (elect.sync): back-to-back UTCHMMA with
+    // descriptors = base + constant, no per-MMA ELECT loop / descriptor rebuild
+    const uint64_t qd0 = make_smem_desc(smem_u32(sQ), 0, 1024), kd0 = make_smem_desc(smem_u32(sK), 0, 1024);
+    const uint64_t vd0 = make_smem_desc(smem_u32(sV), 16384, 1024);
+    constexpr uint64_t TILE16 = C::TILE_BYTES >> 4;   // second tile / stage: start-address field + TILE_BYTES/16
     auto qk = [&](int t, int j) {
-      const uint32_t qa = smem_u32(sQ + t * C::TILE_BYTES), ka = smem_u32(sK + (j & 1) * C::TILE_BYTES);
 #pragma unroll
       for (int kk = 0; kk < HD / 16; ++kk) {
-        const uint32_t off = (kk >> 2) * 16384 + (kk & 3) * 32;
-        umma_bf16_ss(tmem + t * 128, make_smem_desc(qa + off, 0, 1024), make_smem_desc(ka + off, 0, 1024), idesc_qk,
-                     kk != 0);
+        const uint32_t off = ((kk >> 2) * 16384 + (kk & 3) * 32) >> 4;
+        umma_bf16_ss(tmem + t * 128, qd0 + t * TILE16 + off, kd0 + (j & 1) * TILE16 + off, idesc_qk, kk != 0);
       }
       umma_commit(&s_full[t]);
     };
     mbar_wait(&k_full[0], 0);
     tc_fence_after();
-    if (lane == 0) {
+    if (elect_one()) {
       if (0 < n_kv[0]) qk(0, 0);
       if (0 < n_kv[1]) qk(1, 0);
       umma_commit(&k_empty[0]);
@@ -392,22 +395,21 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tm, __nv_bfloat16* __restri
         if (j < n_kv[t]) {
           mbar_wait(&p_full[t], j & 1);
           tc_fence_after();
-          if (lane == 0) {
-            const uint32_t va = smem_u32(sV + st * C::TILE_BYTES);
+          if (elect_one()) {
 #pragma unroll
             for (int k = 0; k < 8; ++k)  // 16 kv rows per step; P: 8 packed TMEM columns per step
-              umma_bf16_ts(tmem + 256 + t * 128, tmem + t * 128 + k * 8, make_smem_desc(va + k * 2048, 16384, 1024),
-                           idesc_pv, (j | k) != 0);
+              umma_bf16_ts(tmem + 256 + t * 128, tmem + t * 128 + k * 8, vd0 + st * TILE16 + ((k * 2048) >> 4), idesc_pv,
+                           (j | k) != 0);
             umma_commit(&pv_done[t]);
+            if (next && j + 1 < n_kv[t]) qk(t, j + 1);
           }
           __syncwarp();
-        }
-        if (next && j + 1 < n_kv[t]) {
-          if (lane == 0) qk(t, j + 1);
+        } else if (next && j + 1 < n_kv[t]) {
+          if (elect_one()) qk(t, j + 1);
           __syncwarp();
         }
       }
-      if (lane == 0) {
+      if (elect_one()) {
         umma_commit(&v_empty[st]);
         if (next) umma_commit(&k_empty[(j + 1) & 1]);
       }
@@ -846,7 +848,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv128, const __grid_cons
 }
 
 static int g_attn_fwd_version = 2;
-static int g_attn_bwd_version = 2;
+static int g_attn_bwd_version = 3;
 
 // ============================================================================================ backward v2
 // Same math / operand layouts as attn_bwd_kernel, re-pipelined: two row-owner warpgroups alternate iterations
@@ -909,12 +911,15 @@ B200_DEVINL void bwd_chunk(const uint32_t (&a)[32], const uint32_t (&d)[32], uin
 __device__ long long* g_attn_trace = nullptr;
 __device__ int g_attn_trace_cta = 0;
 __device__ int g_attn_trace_mode = 0;
+#define ATRACE_INIT()                                                                                      \
+  long long* const atrace_ptr = (MODE == g_attn_trace_mode && (int)blockIdx.x == g_attn_trace_cta &&      \
+                                 blockIdx.y == 0 && blockIdx.z == 0) ? g_attn_trace : nullptr
 #define ATRACE(it, slot)                                                                                   \
   do {                                                                                                     \
-    if (g_attn_trace && MODE == g_attn_trace_mode && (int)blockIdx.x == g_attn_trace_cta && blockIdx.y == 0 && blockIdx.z == 0 && (it) < 64) \
-      g_attn_trace[(it) * 16 + (slot)] = clock64();                                                        \
+    if (atrace_ptr && (it) < 64) atrace_ptr[(it) * 16 + (slot)] = clock64();                               \
   } while (0)
 #else
+#define ATRACE_INIT() do {} while (0)
 #define ATRACE(it, slot) do {} while (0)
 #endif
 
@@ -994,7 +999,6 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tm_qkv128, const __grid_con
         uint8_t* y1 = sY + st * 2 * C::Y_BYTES;
         uint8_t* y2 = y1 + C::Y_BYTES;
         mbar_wait(&y_empty[st], ph ^ 1);
-        ATRACE(it, 13);
         mbar_arrive_expect_tx(&y_full[st], Y_TX);
         for (int c = 0; c < C::NCH; ++c) {
           if constexpr (MODE == MODE_DKDV) {
@@ -1019,11 +1023,9 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tm_qkv128, const __grid_con
     constexpr uint32_t idesc_a = make_idesc_bf16(128, HD, false, true);
     auto issue_scores = [&](int it) {
       const int st = it % 3;
-      if (lane == 0) ATRACE(it, 10);
       mbar_wait(&y_full[st], (it / 3) & 1);
       tc_fence_after();
       if (lane == 0) {
-        ATRACE(it, 0);
         const uint32_t x1 = smem_u32(sX1), x2 = smem_u32(sX2);
         const uint32_t y1 = smem_u32(sY + st * 2 * C::Y_BYTES), y2 = y1 + C::Y_BYTES;
         const uint32_t t1 = tmem + (it & 1) * 128, t2 = t1 + 64;
@@ -1040,7 +1042,6 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tm_qkv128, const __grid_con
           umma_bf16_ss(t2, make_smem_desc(x2 + xo, 0, 1024), make_smem_desc(y2 + yo, 0, 1024), idesc_t, kk != 0);
         }
         umma_commit(&t_full[it & 1]);
-        ATRACE(it, 11);
       }
       __syncwarp();
     };
@@ -1052,7 +1053,6 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tm_qkv128, const __grid_con
       mbar_wait(&w_full[p], (it >> 1) & 1);
       tc_fence_after();
       if (lane == 0) {
-        ATRACE(it, 1);
         const uint32_t y1 = smem_u32(sY + st * 2 * C::Y_BYTES), y2 = y1 + C::Y_BYTES;
         // P^T / dS^T (or dS) sit in TMEM over the score columns: warpgroup g wrote the 16 packed columns of its
         // 32-column half at column offset 32*g  ->  K-step t (16 streamed rows) = 8 columns at 32*(t/2) + 8*(t%2)
@@ -1066,7 +1066,6 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tm_qkv128, const __grid_con
         }
         umma_commit(&y_empty[st]);
         umma_commit(&acc_done[p]);
-        ATRACE(it, 12);
       }
       __syncwarp();
     }
@@ -1091,16 +1090,13 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tm_qkv128, const __grid_con
       const int st = it % 3;
       const float* stat = sStat + st * 128;
       if constexpr (MODE == MODE_DKDV) mbar_wait(&y_full[st], (it / 3) & 1);   // the stats landed (TMA -> generic visibility)
-      if (lane == 0 && q4 == 0) ATRACE(it, 2 + 4 * g);
       mbar_wait(&t_full[par], (it >> 1) & 1);
       tc_fence_after();
-      if (lane == 0 && q4 == 0) ATRACE(it, 3 + 4 * g);
       const uint32_t t1 = tmem + par * 128 + lane_addr + 32 * g, t2 = t1 + 64;
       uint32_t a0[32], d0[32];
       tmem_ld_32x32b_x32(t1, a0);
       tmem_ld_32x32b_x32(t2, d0);
       tmem_ld_wait();
-      if (lane == 0 && q4 == 0) ATRACE(it, 4 + 4 * g);
       // only tiles touching the causal diagonal or the sequence end need per-element masking
       const bool need_mask = (y0 < t128 * 128 + 128 && y0 + 64 > t128 * 128) || (y0 + 64 > S) || (t128 * 128 + 128 > S);
       if (need_mask)
@@ -1111,7 +1107,6 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tm_qkv128, const __grid_con
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&w_full[par]);
-      if (lane == 0 && q4 == 0) ATRACE(it, 5 + 4 * g);
     }
     // epilogue: WG0 stores acc2 (dK | dQ), WG1 stores acc1 (dV); in DQ mode the two groups split acc2's columns
     if (n_iter > 0) mbar_wait(&acc_done[(n_iter - 1) & 1], ((n_iter - 1) >> 1) & 1);
@@ -1143,6 +1138,365 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tm_qkv128, const __grid_con
       } else {
         if (p == 0) store_acc(tmem_acc2, head_lo * HD, 0, HD / 2);
         else        store_acc(tmem_acc2, head_lo * HD, HD / 2, HD);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
+// ================================================================================ backward, version 3
+// Measured on the v2 kernel (scripts/attn_trace.cu, profiles/attn_bwd2_pipeline_trace_r1.txt): the tensor pipe idled
+// ~60% of every iteration because the softmax-gradient warps (TMEM load -> exp2 -> pack -> TMEM store, ~1.8k cycles)
+// sat between "scores done" and "accumulate GEMMs may start" with only ONE other GEMM pair to overlap with, and the
+// N=64 score MMAs run at 48 instead of 32 cycles.  v3 streams 128-row tiles (all MMAs N=128: 64 cycles, at the floor)
+// and splits the row-owner work into two phases that each hide behind a different GEMM pair:
+//
+//   tensor pipe :  acc1(k)   S(k+1)      acc2(k)   dP(k+1)      acc1(k+1)  S(k+2) ...
+//   row owners  :  ......D(k)......|.......E(k+1)........|......D(k+1)......|.....
+//
+//   E(k): S(k) -> P (exp2, mask) -> packed bf16 back into the S columns (TMEM A operand of acc1)
+//   D(k): dP(k), P -> dS = P * (dP - delta) -> packed bf16 into the dP columns (TMEM A operand of acc2)
+//
+// TMEM: S | dP | acc1 | acc2 = 4 x 128 columns.  The streamed pair is released in two halves (Y2 after acc1, Y1 after
+// acc2) so the next TMA loads start as early as the data dependencies allow with only two stages of shared memory.
+// The softmax scale of dS is applied once in the epilogue (dK, dQ are linear in dS).
+template <int HD>
+struct Bwd3Cfg {
+  static constexpr int NCH = HD / 64;
+  static constexpr int T_BYTES = 128 * HD * 2;   // one 128-row operand tile
+  static constexpr int CHUNK = 128 * 128;        // one 64-column 128B-swizzled chunk of a tile
+  static constexpr int STAT_BYTES = 256 * 4;     // per stage: lse2[128] | delta[128] of the streamed q rows (DKDV)
+  static constexpr int SMEM = 2 * T_BYTES + 2 * 2 * T_BYTES + 2 * STAT_BYTES + 1024 + 256;
+};
+
+B200_DEVINL float4 lds128(const float* p) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(smem_u32(p)));
+  return v;
+}
+
+// E phase of one row owner: 64 fp32 scores -> P = exp2(s * scale_log2 - lse2) (masked), packed bf16 pairs
+template <int MODE, bool MASK>
+B200_DEVINL void bwd3_exp(const uint32_t (&a)[64], uint32_t (&pk)[32], const float* stat, float row_lse2,
+                          float scale_log2, int x_idx, int yb, int S) {
+#pragma unroll
+  for (int i = 0; i < 64; i += 4) {
+    float l2[4];
+    if constexpr (MODE == MODE_DKDV) {
+      const float4 v = lds128(stat + i);
+      l2[0] = v.x; l2[1] = v.y; l2[2] = v.z; l2[3] = v.w;
+    } else {
+      l2[0] = l2[1] = l2[2] = l2[3] = row_lse2;
+    }
+    float p[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      p[e] = exp2f(fmaf(__uint_as_float(a[i + e]), scale_log2, -l2[e]));
+      if constexpr (MASK) {
+        const int y_idx = yb + i + e;
+        const bool masked = (MODE == MODE_DKDV) ? ((x_idx > y_idx) || (y_idx >= S) || (x_idx >= S))
+                                                : ((y_idx > x_idx) || (y_idx >= S) || (x_idx >= S));
+        if (masked) p[e] = 0.f;
+      }
+    }
+    pk[i >> 1] = pack_bf16x2(p[0], p[1]);
+    pk[(i >> 1) + 1] = pack_bf16x2(p[2], p[3]);
+  }
+}
+
+template <int HD, int MODE>
+__global__ void __launch_bounds__(ATT2_THREADS, 1)
+attn_bwd3_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do,
+                 const float* __restrict__ lse2g, const float* __restrict__ delta, __nv_bfloat16* __restrict__ dqkv,
+                 int S, int H, int KVH, float scale, int n_t128, int ld) {
+  using C = Bwd3Cfg<HD>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sX1 = smem;
+  uint8_t* sX2 = sX1 + C::T_BYTES;
+  uint8_t* sY = sX2 + C::T_BYTES;                           // [stage][Y1 | Y2]
+  float* sStat = reinterpret_cast<float*>(sY + 4 * C::T_BYTES);   // [stage][lse2 128 | delta 128]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sStat) + 2 * C::STAT_BYTES);
+  uint64_t* x_full = bars;
+  uint64_t* y1_full = bars + 1;    // [2]
+  uint64_t* y2_full = bars + 3;    // [2]
+  uint64_t* y1_empty = bars + 5;   // [2]
+  uint64_t* y2_empty = bars + 7;   // [2]
+  uint64_t* s_full = bars + 9;
+  uint64_t* dp_full = bars + 10;
+  uint64_t* p_full = bars + 11;
+  uint64_t* ds_full = bars + 12;
+  uint64_t* acc_done = bars + 13;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+  ATRACE_INIT();
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int G = H / KVH;
+  const int b = blockIdx.z;
+  const float scale_log2 = scale * LOG2E;
+  int t128, head_lo, head_n, kvh;
+  if constexpr (MODE == MODE_DKDV) {
+    t128 = blockIdx.x; kvh = blockIdx.y; head_lo = kvh * G; head_n = G;
+  } else {
+    t128 = n_t128 - 1 - blockIdx.x; head_lo = blockIdx.y; head_n = 1; kvh = blockIdx.y / G;
+  }
+  const int s_lo = (MODE == MODE_DKDV) ? t128 : 0;
+  const int s_hi = (MODE == MODE_DKDV) ? n_t128 : t128 + 1;
+  const int per_head = s_hi - s_lo;
+  const int n_iter = per_head * head_n;
+  const int xrow0 = b * S + t128 * 128;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_qkv); tma_prefetch_desc(&tm_do);
+    mbar_init(x_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&y1_full[i], 1); mbar_init(&y2_full[i], 1); mbar_init(&y1_empty[i], 1); mbar_init(&y2_empty[i], 1);
+    }
+    mbar_init(s_full, 1); mbar_init(dp_full, 1); mbar_init(p_full, 8); mbar_init(ds_full, 8); mbar_init(acc_done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t tmem_s = tmem, tmem_dp = tmem + 128, tmem_acc1 = tmem + 256, tmem_acc2 = tmem + 384;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(x_full, 2 * C::T_BYTES);
+      for (int c = 0; c < C::NCH; ++c) {
+        if constexpr (MODE == MODE_DKDV) {
+          tma_load_2d(sX1 + c * C::CHUNK, &tm_qkv, x_full, (H + kvh) * HD + 64 * c, xrow0);
+          tma_load_2d(sX2 + c * C::CHUNK, &tm_qkv, x_full, (H + KVH + kvh) * HD + 64 * c, xrow0);
+        } else {
+          tma_load_2d(sX1 + c * C::CHUNK, &tm_qkv, x_full, head_lo * HD + 64 * c, xrow0);
+          tma_load_2d(sX2 + c * C::CHUNK, &tm_do, x_full, head_lo * HD + 64 * c, xrow0);
+        }
+      }
+      for (int it = 0; it < n_iter; ++it) {
+        const int st = it & 1;
+        const uint32_t free_par = ((it >> 1) & 1) ^ 1;
+        const int hh = head_lo + it / per_head;
+        const int t = s_lo + it % per_head;
+        const int yrow = b * S + t * 128;
+        uint8_t* y1 = sY + st * 2 * C::T_BYTES;
+        uint8_t* y2 = y1 + C::T_BYTES;
+        mbar_wait(&y1_empty[st], free_par);
+        mbar_arrive_expect_tx(&y1_full[st], C::T_BYTES + (MODE == MODE_DKDV ? C::STAT_BYTES : 0));
+        for (int c = 0; c < C::NCH; ++c) {
+          if constexpr (MODE == MODE_DKDV) tma_load_2d(y1 + c * C::CHUNK, &tm_qkv, &y1_full[st], hh * HD + 64 * c, yrow);
+          else tma_load_2d(y1 + c * C::CHUNK, &tm_qkv, &y1_full[st], (H + kvh) * HD + 64 * c, yrow);
+        }
+        if constexpr (MODE == MODE_DKDV) {
+          // per-column softmax statistics of the streamed q rows ride on the Y1 barrier (two 512 B bulk copies)
+          const size_t so = ((size_t)b * H + hh) * ld + (size_t)t * 128;
+          bulk_load_1d(sStat + st * 256, lse2g + so, 512, &y1_full[st]);
+          bulk_load_1d(sStat + st * 256 + 128, delta + so, 512, &y1_full[st]);
+        }
+        mbar_wait(&y2_empty[st], free_par);
+        mbar_arrive_expect_tx(&y2_full[st], C::T_BYTES);
+        for (int c = 0; c < C::NCH; ++c) {
+          if constexpr (MODE == MODE_DKDV) tma_load_2d(y2 + c * C::CHUNK, &tm_do, &y2_full[st], hh * HD + 64 * c, yrow);
+          else tma_load_2d(y2 + c * C::CHUNK, &tm_qkv, &y2_full[st], (H + KVH + kvh) * HD + 64 * c, yrow);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t idesc_t = make_idesc_bf16(128, 128, false, false);
+    constexpr uint32_t idesc_a = make_idesc_bf16(128, HD, false, true);
+    const uint32_t x1 = smem_u32(sX1), x2 = smem_u32(sX2), y0 = smem_u32(sY);
+    // descriptors are built once; per-MMA operands are base + constant (the start-address field counts 16-byte units)
+    const uint64_t x1d = make_smem_desc(x1, 0, 1024), x2d = make_smem_desc(x2, 0, 1024);
+    // scores: T = X * Y^T (both operands K-major, 128 x 128 x HD)
+    auto issue_scores = [&](uint32_t tdst, uint64_t xd, uint32_t ya, uint64_t* done) {
+      if (elect_one()) {
+        const uint64_t yd = make_smem_desc(ya, 0, 1024);
+#pragma unroll
+        for (int kk = 0; kk < HD / 16; ++kk) {
+          const uint32_t o = ((kk >> 2) * C::CHUNK + (kk & 3) * 32) >> 4;
+          umma_bf16_ss(tdst, xd + o, yd + o, idesc_t, kk != 0);
+        }
+        umma_commit(done);
+      }
+      __syncwarp();
+    };
+    // accumulate: acc += W(TMEM, packed bf16 [128 x 128 streamed]) * Y (MN-major [128 streamed x HD])
+    auto issue_acc = [&](uint32_t tacc, uint32_t tw, uint32_t ya, bool first, uint64_t* release, uint64_t* done) {
+      if (elect_one()) {
+        const uint64_t yd = make_smem_desc(ya, C::CHUNK, 1024);
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+          const uint32_t co = 64 * (t >> 2) + 8 * (t & 3);   // warpgroup g packs its 64 columns into [64g, 64g+32)
+          umma_bf16_ts(tacc, tw + co, yd + ((t * 2048) >> 4), idesc_a, !(first && t == 0));
+        }
+        umma_commit(release);
+        if (done) umma_commit(done);
+      }
+      __syncwarp();
+    };
+    mbar_wait(x_full, 0);
+    if (n_iter > 0) {
+      mbar_wait(&y1_full[0], 0);
+      tc_fence_after();
+      issue_scores(tmem_s, x1d, y0, s_full);
+      mbar_wait(&y2_full[0], 0);
+      tc_fence_after();
+      issue_scores(tmem_dp, x2d, y0 + C::T_BYTES, dp_full);
+      if constexpr (MODE == MODE_DQ) { if (elect_one()) umma_commit(&y2_empty[0]); __syncwarp(); }
+    }
+    for (int it = 0; it < n_iter; ++it) {
+      const int st = it & 1, nst = st ^ 1;
+      const uint32_t ph = it & 1;
+      const uint32_t ya1 = y0 + st * 2 * C::T_BYTES, ya2 = ya1 + C::T_BYTES;
+      const uint32_t nya1 = y0 + nst * 2 * C::T_BYTES, nya2 = nya1 + C::T_BYTES;
+      const bool last = (it + 1 == n_iter);
+      mbar_wait(p_full, ph);                       // P(it) is in the S columns (and S(it) has been consumed)
+      tc_fence_after();
+      if (lane == 0) ATRACE(it, 0);
+      if constexpr (MODE == MODE_DKDV) issue_acc(tmem_acc1, tmem_s, ya2, it == 0, &y2_empty[st], nullptr);
+      if (!last) {
+        mbar_wait(&y1_full[nst], ((it + 1) >> 1) & 1);
+        tc_fence_after();
+        issue_scores(tmem_s, x1d, nya1, s_full);
+      }
+      if (lane == 0) ATRACE(it, 1);
+      mbar_wait(ds_full, ph);                      // dS(it) is in the dP columns
+      tc_fence_after();
+      if (lane == 0) ATRACE(it, 2);
+      issue_acc(tmem_acc2, tmem_dp, ya1, it == 0, &y1_empty[st], last ? acc_done : nullptr);
+      if (!last) {
+        mbar_wait(&y2_full[nst], ((it + 1) >> 1) & 1);
+        tc_fence_after();
+        issue_scores(tmem_dp, x2d, nya2, dp_full);
+        if constexpr (MODE == MODE_DQ) { if (elect_one()) umma_commit(&y2_empty[nst]); __syncwarp(); }
+      }
+      if (lane == 0) ATRACE(it, 3);
+    }
+  } else if (warp >= 4) {
+    // 8 row-owner warps; warpgroup g owns columns [64g, 64g+64) of every 128 x 128 tile, thread <-> row
+    const int g = (warp - 4) >> 2;
+    const int q4 = warp & 3;
+    const int r = q4 * 32 + lane;
+    const uint32_t lane_addr = static_cast<uint32_t>(q4 * 32) << 16;
+    const int x_idx = t128 * 128 + r;
+    float row_lse2 = 0.f, row_delta = 0.f;
+    if constexpr (MODE == MODE_DQ) {
+      const size_t sidx = ((size_t)b * H + head_lo) * ld + min(x_idx, S - 1);
+      row_lse2 = lse2g[sidx];
+      row_delta = delta[sidx];
+    }
+    const uint32_t ts = tmem_s + lane_addr + 64 * g, td = tmem_dp + lane_addr + 64 * g;
+    int t_in_head = 0;
+    for (int it = 0; it < n_iter; ++it) {
+      const int st = it & 1;
+      const uint32_t ph = it & 1;
+      const int t = s_lo + t_in_head;
+      if (++t_in_head == per_head) t_in_head = 0;
+      const int yb = t * 128 + 64 * g;             // first streamed index of this warpgroup's columns
+      const float* stat = sStat + st * 256 + 64 * g;
+      // only tiles on the causal diagonal or crossing the sequence end need per-element masking
+      const bool need_mask = (t == t128) || (t * 128 + 128 > S) || (t128 * 128 + 128 > S);
+      uint32_t pk[32];                             // P of this thread's 64 columns, packed bf16 (kept for the dS phase)
+      // ---------------- E phase: S -> P
+      if constexpr (MODE == MODE_DKDV) mbar_wait(&y1_full[st], (it >> 1) & 1);   // column statistics have landed
+      if (lane == 0 && q4 == 0) ATRACE(it, 4 + 5 * g);
+      mbar_wait(s_full, ph);
+      tc_fence_after();
+      if (lane == 0 && q4 == 0) ATRACE(it, 5 + 5 * g);
+      {
+        uint32_t a[64];
+        tmem_ld_32x32b_x32(ts, *reinterpret_cast<uint32_t(*)[32]>(&a[0]));
+        tmem_ld_32x32b_x32(ts + 32, *reinterpret_cast<uint32_t(*)[32]>(&a[32]));
+        tmem_ld_wait();
+        if (need_mask) bwd3_exp<MODE, true>(a, pk, stat, row_lse2, scale_log2, x_idx, yb, S);
+        else           bwd3_exp<MODE, false>(a, pk, stat, row_lse2, scale_log2, x_idx, yb, S);
+      }
+      if constexpr (MODE == MODE_DKDV) {
+        tmem_st_32x32b_x16(ts, *reinterpret_cast<uint32_t(*)[16]>(&pk[0]));
+        tmem_st_32x32b_x16(ts + 16, *reinterpret_cast<uint32_t(*)[16]>(&pk[16]));
+        tmem_st_wait();
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_full);
+      if (lane == 0 && q4 == 0) ATRACE(it, 6 + 5 * g);
+      // ---------------- D phase: dP, P -> dS (unscaled)
+      mbar_wait(dp_full, ph);
+      tc_fence_after();
+      if (lane == 0 && q4 == 0) ATRACE(it, 7 + 5 * g);
+      {
+        uint32_t d[64];
+        tmem_ld_32x32b_x32(td, *reinterpret_cast<uint32_t(*)[32]>(&d[0]));
+        tmem_ld_32x32b_x32(td + 32, *reinterpret_cast<uint32_t(*)[32]>(&d[32]));
+        tmem_ld_wait();
+        uint32_t dk[32];
+#pragma unroll
+        for (int i = 0; i < 64; i += 4) {
+          float dl[4];
+          if constexpr (MODE == MODE_DKDV) {
+            const float4 v = lds128(stat + 128 + i);
+            dl[0] = v.x; dl[1] = v.y; dl[2] = v.z; dl[3] = v.w;
+          } else {
+            dl[0] = dl[1] = dl[2] = dl[3] = row_delta;
+          }
+          const float2 p01 = unpack_bf16x2(pk[i >> 1]), p23 = unpack_bf16x2(pk[(i >> 1) + 1]);
+          const float pp[4] = {p01.x, p01.y, p23.x, p23.y};
+          float dv[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            float v = pp[e] * (__uint_as_float(d[i + e]) - dl[e]);
+            if (need_mask && pp[e] == 0.f) v = 0.f;   // masked / padded entries: statistics may be garbage (NaN * 0)
+            dv[e] = v;
+          }
+          dk[i >> 1] = pack_bf16x2(dv[0], dv[1]);
+          dk[(i >> 1) + 1] = pack_bf16x2(dv[2], dv[3]);
+        }
+        tmem_st_32x32b_x16(td, *reinterpret_cast<uint32_t(*)[16]>(&dk[0]));
+        tmem_st_32x32b_x16(td + 16, *reinterpret_cast<uint32_t(*)[16]>(&dk[16]));
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(ds_full);
+      if (lane == 0 && q4 == 0) ATRACE(it, 8 + 5 * g);
+    }
+    // epilogue: warpgroup 0 stores acc2 (dK | dQ, times the softmax scale), warpgroup 1 acc1 (dV); in DQ mode the two
+    // groups split acc2's columns
+    if (n_iter > 0) mbar_wait(acc_done, 0);
+    tc_fence_after();
+    if (x_idx < S && n_iter > 0) {
+      const size_t row = (size_t)b * S + x_idx;
+      const int Wd = (H + 2 * KVH) * HD;
+      auto store_acc = [&](uint32_t tacc, int col0, int c_lo, int c_hi, float mul) {
+        __nv_bfloat16* dst = dqkv + row * Wd + col0;
+#pragma unroll 1
+        for (int c = c_lo; c < c_hi; c += 32) {
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(tacc + lane_addr + c, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            uint4 u;
+            u.x = pack_bf16x2(__uint_as_float(v[q * 8 + 0]) * mul, __uint_as_float(v[q * 8 + 1]) * mul);
+            u.y = pack_bf16x2(__uint_as_float(v[q * 8 + 2]) * mul, __uint_as_float(v[q * 8 + 3]) * mul);
+            u.z = pack_bf16x2(__uint_as_float(v[q * 8 + 4]) * mul, __uint_as_float(v[q * 8 + 5]) * mul);
+            u.w = pack_bf16x2(__uint_as_float(v[q * 8 + 6]) * mul, __uint_as_float(v[q * 8 + 7]) * mul);
+            *reinterpret_cast<uint4*>(dst + c + q * 8) = u;
+          }
+        }
+      };
+      if constexpr (MODE == MODE_DKDV) {
+        if (g == 0) store_acc(tmem_acc2, (H + kvh) * HD, 0, HD, scale);
+        else        store_acc(tmem_acc1, (H + KVH + kvh) * HD, 0, HD, 1.f);
+      } else {
+        if (g == 0) store_acc(tmem_acc2, head_lo * HD, 0, HD / 2, scale);
+        else        store_acc(tmem_acc2, head_lo * HD, HD / 2, HD, scale);
       }
     }
   }
@@ -1210,12 +1564,32 @@ static int launch_bwd(const void* dout, const void* qkv, const void* o, const fl
     const int threads = 256;
     const long long blocks = (warps * 32 + threads - 1) / threads;
     // v2: rows padded to a multiple of 64 so a 64-float TMA bulk copy never leaves the row; plane 1 = lse * log2(e)
-    const int ld = (g_attn_bwd_version == 2) ? ((S + 63) / 64) * 64 : S;
-    float* lse2 = (g_attn_bwd_version == 2) ? delta + (size_t)B * H * ld : nullptr;
+    const int ld = (g_attn_bwd_version >= 2) ? ((S + 127) / 128) * 128 : S;
+    float* lse2 = (g_attn_bwd_version >= 2) ? delta + (size_t)B * H * ld : nullptr;
     attn_delta_kernel<<<(unsigned)blocks, threads, 0, st>>>((const __nv_bfloat16*)dout, (const __nv_bfloat16*)o, delta,
                                                             lse, lse2, B, S, H, HD, ld);
   }
   const int n_t = (S + 127) / 128;
+  if (g_attn_bwd_version == 3) {
+    using C3 = Bwd3Cfg<HD>;
+    auto j1 = attn_bwd3_kernel<HD, MODE_DKDV>;
+    auto j2 = attn_bwd3_kernel<HD, MODE_DQ>;
+    static bool configured3 = false;
+    if (!configured3) {
+      cudaError_t e = cudaFuncSetAttribute(j1, cudaFuncAttributeMaxDynamicSharedMemorySize, C3::SMEM);
+      if (e != cudaSuccess) return (int)e;
+      e = cudaFuncSetAttribute(j2, cudaFuncAttributeMaxDynamicSharedMemorySize, C3::SMEM);
+      if (e != cudaSuccess) return (int)e;
+      configured3 = true;
+    }
+    const int ld3 = ((S + 127) / 128) * 128;
+    const float* lse2p = delta + (size_t)B * H * ld3;
+    j1<<<dim3(n_t, KVH, B), ATT2_THREADS, C3::SMEM, st>>>(q128, d128, lse2p, delta, (__nv_bfloat16*)dqkv, S, H, KVH, scale,
+                                                         n_t, ld3);
+    j2<<<dim3(n_t, H, B), ATT2_THREADS, C3::SMEM, st>>>(q128, d128, lse2p, delta, (__nv_bfloat16*)dqkv, S, H, KVH, scale,
+                                                       n_t, ld3);
+    return (int)cudaGetLastError();
+  }
   if (g_attn_bwd_version == 2) {
     using C2 = Bwd2Cfg<HD>;
     auto j1 = attn_bwd2_kernel<HD, MODE_DKDV>;
@@ -1228,7 +1602,7 @@ static int launch_bwd(const void* dout, const void* qkv, const void* o, const fl
       if (e != cudaSuccess) return (int)e;
       configured2 = true;
     }
-    const int ld2 = ((S + 63) / 64) * 64;
+    const int ld2 = ((S + 127) / 128) * 128;
     const float* lse2p = delta + (size_t)B * H * ld2;
     j1<<<dim3(n_t, KVH, B), ATT2_THREADS, C2::SMEM, st>>>(q128, q64, d128, d64, lse2p, delta, (__nv_bfloat16*)dqkv, S, H,
                                                          KVH, scale, n_t, ld2);

@@ -328,8 +328,8 @@ at::Tensor attn_bwd(const at::Tensor& dout, const at::Tensor& qkv, const at::Ten
   need(lse, "lse", at::kFloat);
   TORCH_CHECK(qkv.is_contiguous() && dout.is_contiguous() && o.is_contiguous() && lse.is_contiguous());
   auto dqkv = at::empty_like(qkv);
-  // [2 planes: delta | lse*log2e][B][H][S padded to 64]
-  auto delta = at::empty({2, B, H, ((S + 63) / 64) * 64}, qkv.options().dtype(at::kFloat));
+  // [2 planes: delta | lse*log2e][B][H][S padded to 128]
+  auto delta = at::empty({2, B, H, ((S + 127) / 128) * 128}, qkv.options().dtype(at::kFloat));
   check(b200_attn_bwd(dout.data_ptr(), qkv.data_ptr(), o.data_ptr(), lse.data_ptr<float>(), dqkv.data_ptr(),
                       delta.data_ptr<float>(), B, S, H, KVH, hd, (float)scale, cur_stream()), "attn_bwd", 3);
   return dqkv;

@@ -135,6 +135,16 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, bool a_mn_m
          (static_cast<uint32_t>(M >> 4) << 24);
 }
 
+// One lane of a CONVERGED warp.  Issue tcgen05.mma behind this instead of `lane == 0`: the compiler then knows a single
+// thread is active and emits back-to-back UTCHMMA with hoisted descriptors; a `lane == 0` branch makes it wrap every
+// UTCHMMA in an ELECT / BRA.U.ANY waterfall loop plus per-MMA descriptor rebuilds (~14 instructions per MMA, which
+// starves the tensor pipe when the issuing warp shares its scheduler with busy softmax/epilogue warps).
+B200_DEVINL bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+
 // D[tmem] (+)= A[smem] * B[smem]; issued by ONE thread on behalf of the CTA.
 B200_DEVINL void umma_bf16_ss(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(

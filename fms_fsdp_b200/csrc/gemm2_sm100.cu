@@ -205,16 +205,15 @@ gemm2_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          if (lane == 0) {
+          if (elect_one()) {   // single elected lane: back-to-back UTCHMMA, descriptors = per-stage base + constant
             const uint32_t sa = smem_u32(smem + stage * P_STAGE_BYTES);
             const uint32_t sb = sa + PA_BYTES;
+            const uint64_t a0 = make_smem_desc(sa, A_MN ? 64 * P_BK * 2 : 0, 1024);
+            const uint64_t b0 = make_smem_desc(sb, B_MN ? 64 * P_BK * 2 : 0, 1024);
 #pragma unroll
             for (int k = 0; k < P_BK / 16; ++k) {
-              uint64_t adesc, bdesc;
-              if constexpr (!A_MN) adesc = make_smem_desc(sa + k * 32, 0, 1024);
-              else                 adesc = make_smem_desc(sa + k * 2048, 64 * P_BK * 2, 1024);
-              if constexpr (!B_MN) bdesc = make_smem_desc(sb + k * 32, 0, 1024);
-              else                 bdesc = make_smem_desc(sb + k * 2048, 64 * P_BK * 2, 1024);
+              const uint64_t adesc = a0 + ((A_MN ? k * 2048 : k * 32) >> 4);
+              const uint64_t bdesc = b0 + ((B_MN ? k * 2048 : k * 32) >> 4);
               umma_bf16_ss_2cta(tmem_d, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
             }
             umma_commit_2cta_mcast(&empty_bar[stage], 0x3);

@@ -133,16 +133,15 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
-        if (lane == 0) {
+        if (elect_one()) {   // single elected lane: back-to-back UTCHMMA, descriptors = per-stage base + constant
           const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
           const uint32_t sb = sa + A_STAGE_BYTES;
+          const uint64_t a0 = make_smem_desc(sa, A_MN ? 64 * BK * 2 : 0, 1024);
+          const uint64_t b0 = make_smem_desc(sb, B_MN ? 64 * BK * 2 : 0, 1024);
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
-            uint64_t adesc, bdesc;
-            if constexpr (!A_MN) adesc = make_smem_desc(sa + k * (UMMA_K * 2), 0, 1024);
-            else                 adesc = make_smem_desc(sa + k * (UMMA_K * 128), 64 * BK * 2, 1024);
-            if constexpr (!B_MN) bdesc = make_smem_desc(sb + k * (UMMA_K * 2), 0, 1024);
-            else                 bdesc = make_smem_desc(sb + k * (UMMA_K * 128), 64 * BK * 2, 1024);
+            const uint64_t adesc = a0 + ((A_MN ? k * (UMMA_K * 128) : k * (UMMA_K * 2)) >> 4);
+            const uint64_t bdesc = b0 + ((B_MN ? k * (UMMA_K * 128) : k * (UMMA_K * 2)) >> 4);
             umma_bf16_ss(tmem_d, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
           }
           umma_commit(&empty_bar[stage]);                 // smem slot reusable once these MMAs retire

@@ -22,7 +22,7 @@ _LAYOUT = {"nt": 0, "nn": 1, "tn": 2}
 ATTN_IMPL = os.environ.get("FMS_B200_ATTN_IMPL", "tcgen05")
 GEMM_IMPL = os.environ.get("FMS_B200_GEMM_IMPL", "tcgen05")  # "cublas" = library fallback, debugging only
 _C.set_attn_fwd_version(int(os.environ.get("FMS_B200_ATTN_FWD", "2")))  # 2 = two Q tiles/CTA, P in TMEM
-_C.set_attn_bwd_version(int(os.environ.get("FMS_B200_ATTN_BWD", "2")))  # 2 = two row-owner warpgroups, 3-stage ring
+_C.set_attn_bwd_version(int(os.environ.get("FMS_B200_ATTN_BWD", "3")))  # 3 = 128-row streamed tiles, two-phase row owners (2 = 64-row tiles)
 _C.set_gemm_2cta(os.environ.get("FMS_B200_GEMM_2CTA", "1") == "1")  # CTA-pair (cta_group::2) GEMM for M >= 256
 
 

@@ -18,10 +18,10 @@ int main(int argc, char** argv) {
   float *lse, *delta;
   cudaMalloc(&qkv, M * W * 2); cudaMalloc(&dqkv, M * W * 2);
   cudaMalloc(&o, M * H * HD * 2); cudaMalloc(&dout, M * H * HD * 2);
-  cudaMalloc(&lse, (size_t)B * H * S * 4); cudaMalloc(&delta, (size_t)2 * B * H * (S + 64) * 4);
+  cudaMalloc(&lse, (size_t)B * H * S * 4); cudaMalloc(&delta, (size_t)2 * B * H * (S + 128) * 4);
   cudaMemcpy(qkv, h.data(), M * W * 2, cudaMemcpyHostToDevice);
   cudaMemcpy(dout, h.data(), M * H * HD * 2, cudaMemcpyHostToDevice);
-  b200_attn_set_fwd_version(2); b200_attn_set_bwd_version(2);
+  b200_attn_set_fwd_version(2); b200_attn_set_bwd_version(3);
   int rc = b200_attn_fwd(qkv, o, lse, B, S, H, KVH, HD, 0.0884f, 0);
   printf("fwd rc %d\n", rc);
   long long* tr;
@@ -37,7 +37,7 @@ int main(int argc, char** argv) {
   std::vector<long long> t(64 * 16);
   cudaMemcpy(t.data(), tr, 64 * 16 * 8, cudaMemcpyDeviceToHost);
   long long t0 = t[0];
-  printf("it | S_issue  A_issue | wg0: wait_start t_full ld_done arrive | wg1: wait_start t_full ld_done arrive | S_prewait S_issued A_issued TMA_issue  (cycles since first score issue)\n");
+  printf("v3 kernel mode %d.  mma: p_full seen | acc1+S(k+1) issued | ds_full seen | acc2+dP(k+1) issued || wg0: E wait, s_full, E done(p arrive), dp_full, D done || wg1: same\n", mode);
   for (int it = 0; it < 24; ++it) {
     printf("%2d |", it);
     for (int s = 0; s < 14; ++s) printf(" %7lld", t[it * 16 + s] ? t[it * 16 + s] - t0 : -1);

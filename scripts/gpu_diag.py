@@ -251,13 +251,14 @@ def main(groups):
 
     if "attn" in groups:
         for ver in ([int(x) for x in os.environ.get("DIAG_ATTN_VERS", "2").split(",")]):
-          CK._C.set_attn_fwd_version(ver); CK._C.set_attn_bwd_version(ver)
+          bver = int(os.environ.get("DIAG_ATTN_BWD", "3" if ver == 2 else str(ver)))
+          CK._C.set_attn_fwd_version(ver); CK._C.set_attn_bwd_version(bver)
           for (B, S, H, KVH, hd) in [(1, 128, 1, 1, 128), (2, 256, 4, 2, 128), (1, 384, 2, 1, 128), (1, 512, 2, 2, 64), (2, 4096, 32, 32, 128)]:
             try:
                 qkv = torch.randn(B * S, (H + 2 * KVH) * hd, device=dev).bfloat16()
                 do = torch.randn(B * S, H * hd, device=dev).bfloat16()
                 sc = hd ** -0.5
-                r = dict(B=B, S=S, H=H, KVH=KVH, hd=hd, fwd_version=ver)
+                r = dict(B=B, S=S, H=H, KVH=KVH, hd=hd, fwd_version=ver, bwd_version=bver)
                 o1, l1 = CK.attn_fwd(qkv, B, S, H, KVH, hd, sc)
                 torch.cuda.synchronize()
                 if S <= 1024:
