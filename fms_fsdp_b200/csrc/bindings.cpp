@@ -15,6 +15,24 @@ DECL int b200_gemm2_bf16(const void*, const void*, void*, const void*, int, int,
 DECL int b200_gemm2_ag_bf16(const void*, const void*, void*, const void*, int, int, int, int, int, int, int, int, int, int,
                             const void* const*, void*, unsigned long long, unsigned long long, unsigned long long, int, int,
                             uint32_t*, uint32_t, int, cudaStream_t);
+DECL int b200_bgemm_bf16(const void*, const void*, void*, int, int, int, int, int, int, int, int, long long, long long,
+                         long long, long long, long long, long long, int, int, int, int, cudaStream_t);
+DECL int b200_ssd_prep(const void*, const float*, const float*, float*, float*, float*, int, int, int, cudaStream_t);
+DECL int b200_ssd_mask(const void*, const float*, const float*, void*, int, int, int, cudaStream_t);
+DECL int b200_ssd_xs(const void*, const float*, const float*, const float*, void*, long long, int, int, cudaStream_t);
+DECL int b200_ssd_state_pass(const float*, const float*, void*, int, int, int, int, int, cudaStream_t);
+DECL int b200_ssd_combine(const void*, const void*, const void*, const float*, const float*, void*, long long, int, int,
+                          cudaStream_t);
+DECL int b200_ssd_dyoff(const void*, const void*, const void*, const float*, void*, float*, float*, long long, int,
+                        cudaStream_t);
+DECL int b200_ssd_mask_bwd(const void*, const void*, const float*, const float*, void*, float*, float*, int, int, int,
+                           cudaStream_t);
+DECL int b200_ssd_state_pass_bwd(const float*, const void*, const float*, void*, float*, int, int, int, int, int,
+                                 cudaStream_t);
+DECL int b200_ssd_dx(const void*, const void*, const void*, const void*, const float*, const float*, const float*,
+                     const float*, void*, float*, float*, float*, long long, int, int, cudaStream_t);
+DECL int b200_ssd_dt_bwd(const void*, const float*, const float*, const float*, const float*, const float*, const float*,
+                         void*, float*, float*, int, int, int, cudaStream_t);
 DECL int b200_p2p_gather_range(const void* const*, void*, long long, long long, long long, cudaStream_t);
 DECL int b200_ts_mma_probe(const void*, const void*, float*, cudaStream_t);
 DECL int b200_rmsnorm_fwd(const void*, const void*, void*, float*, int, int, float, cudaStream_t);
@@ -445,6 +463,169 @@ void reset_launch_count() { g_launches = 0; }
 
 }  // namespace
 
+
+// ------------------------------------------------------------------------------ Mamba2 SSD chunk scan (csrc/ssd.cu)
+// Orchestration of the batched tcgen05 GEMMs and the glue kernels.  Internal chunk length is 128 tokens whatever
+// the model's chunk_size (the chunked form is exact for every chunking).
+namespace {
+constexpr int kL = 128;
+struct SsdDims {
+  long long M; int H, P, G, Nd, Hg, HP, GN, nbc, batch, nc;
+};
+struct SsdFwd {
+  at::Tensor dtv, acs, aL, CB, Mh, xs, states, prev, yd, yoff;
+};
+SsdDims ssd_dims(const at::Tensor& x, const at::Tensor& Bm, int64_t seq_len) {
+  SsdDims d;
+  d.M = x.size(0); d.H = x.size(1); d.P = x.size(2); d.G = Bm.size(1); d.Nd = Bm.size(2);
+  TORCH_CHECK(seq_len % kL == 0 && d.M % seq_len == 0, "ssd: seq_len must be a multiple of 128");
+  TORCH_CHECK(d.H % d.G == 0 && d.P % 32 == 0 && d.Nd % 8 == 0, "ssd: unsupported head/state dims");
+  d.Hg = d.H / d.G; d.HP = d.H * d.P; d.GN = d.G * d.Nd; d.nbc = (int)(d.M / kL);
+  d.batch = (int)(d.M / seq_len); d.nc = (int)(seq_len / kL);
+  return d;
+}
+void bg(const void* A, const void* B, void* C, int M, int N, int K, int lda, int ldb, int ldc, int nb0, int nb1,
+        long long sa0, long long sa1, long long sb0, long long sb1, long long sc0, long long sc1, int a_mn, int b_mn, int epi,
+        int f32, const char* what) {
+  check(b200_bgemm_bf16(A, B, C, M, N, K, lda, ldb, ldc, nb0, nb1, sa0, sa1, sb0, sb1, sc0, sc1, a_mn, b_mn, epi, f32,
+                        cur_stream()), what);
+}
+SsdFwd ssd_forward_internals(const SsdDims& d, const at::Tensor& x, const at::Tensor& dt, const at::Tensor& A,
+                             const at::Tensor& Bm, const at::Tensor& Cm, const float* bias, bool softplus) {
+  SsdFwd f;
+  auto f32 = x.options().dtype(at::kFloat);
+  auto bf = x.options();
+  const long long LL = (long long)kL * kL;
+  f.dtv = at::empty({d.M, d.H}, f32); f.acs = at::empty({d.M, d.H}, f32); f.aL = at::empty({d.nbc, d.H}, f32);
+  check(b200_ssd_prep(dt.data_ptr(), A.data_ptr<float>(), bias, f.dtv.data_ptr<float>(), f.acs.data_ptr<float>(),
+                      f.aL.data_ptr<float>(), d.nbc, d.H, softplus ? 1 : 0, cur_stream()), "ssd_prep");
+  f.CB = at::empty({d.nbc, d.G, kL, kL}, bf);
+  bg(Cm.data_ptr(), Bm.data_ptr(), f.CB.data_ptr(), kL, kL, d.Nd, d.GN, d.GN, kL, d.G, d.nbc, d.Nd, (long long)kL * d.GN,
+     d.Nd, (long long)kL * d.GN, LL, d.G * LL, 0, 0, 0, 0, "ssd_bgemm_CB");
+  f.Mh = at::empty({d.nbc, d.H, kL, kL}, bf);
+  check(b200_ssd_mask(f.CB.data_ptr(), f.acs.data_ptr<float>(), f.dtv.data_ptr<float>(), f.Mh.data_ptr(), d.nbc, d.H, d.G,
+                      cur_stream()), "ssd_mask");
+  f.yd = at::empty({d.M, d.H, d.P}, bf);
+  bg(f.Mh.data_ptr(), x.data_ptr(), f.yd.data_ptr(), kL, d.P, kL, kL, d.HP, d.HP, d.H, d.nbc, LL, d.H * LL, d.P,
+     (long long)kL * d.HP, d.P, (long long)kL * d.HP, 0, 1, 0, 0, "ssd_bgemm_Ydiag");
+  f.xs = at::empty({d.M, d.H, d.P}, bf);
+  check(b200_ssd_xs(x.data_ptr(), f.dtv.data_ptr<float>(), f.acs.data_ptr<float>(), f.aL.data_ptr<float>(), f.xs.data_ptr(),
+                    d.M, d.H, d.P, cur_stream()), "ssd_xs");
+  f.states = at::empty({d.nbc, d.Nd, d.HP}, f32);
+  bg(Bm.data_ptr(), f.xs.data_ptr(), f.states.data_ptr(), d.Nd, d.Hg * d.P, kL, d.GN, d.HP, d.HP, d.G, d.nbc, d.Nd,
+     (long long)kL * d.GN, (long long)d.Hg * d.P, (long long)kL * d.HP, (long long)d.Hg * d.P, (long long)d.Nd * d.HP, 1, 1, 0, 1,
+     "ssd_bgemm_states");
+  f.prev = at::empty({d.nbc, d.Nd, d.HP}, bf);
+  check(b200_ssd_state_pass(f.states.data_ptr<float>(), f.aL.data_ptr<float>(), f.prev.data_ptr(), d.batch, d.nc, d.Nd, d.H,
+                            d.P, cur_stream()), "ssd_state_pass");
+  f.yoff = at::empty({d.M, d.H, d.P}, bf);
+  bg(Cm.data_ptr(), f.prev.data_ptr(), f.yoff.data_ptr(), kL, d.Hg * d.P, d.Nd, d.GN, d.HP, d.HP, d.G, d.nbc, d.Nd,
+     (long long)kL * d.GN, (long long)d.Hg * d.P, (long long)d.Nd * d.HP, (long long)d.Hg * d.P, (long long)kL * d.HP, 0, 1, 0, 0,
+     "ssd_bgemm_Yoff");
+  return f;
+}
+void ssd_check_inputs(const at::Tensor& x, const at::Tensor& dt, const at::Tensor& A, const at::Tensor& Bm,
+                      const at::Tensor& Cm) {
+  need(x, "x", at::kBFloat16); need(dt, "dt", at::kBFloat16); need(Bm, "B", at::kBFloat16); need(Cm, "C", at::kBFloat16);
+  need(A, "A", at::kFloat);
+  TORCH_CHECK(x.dim() == 3 && dt.dim() == 2 && Bm.dim() == 3 && Cm.dim() == 3, "ssd: x [M,H,P], dt [M,H], B/C [M,G,N]");
+  TORCH_CHECK(x.is_contiguous() && dt.is_contiguous() && Bm.is_contiguous() && Cm.is_contiguous() && A.is_contiguous(),
+              "ssd: inputs must be contiguous");
+}
+}  // namespace
+
+at::Tensor ssd_scan_fwd(const at::Tensor& x, const at::Tensor& dt, const at::Tensor& A, const at::Tensor& Bm,
+                        const at::Tensor& Cm, const c10::optional<at::Tensor>& D, const c10::optional<at::Tensor>& dt_bias,
+                        int64_t seq_len, bool softplus) {
+  c10::cuda::CUDAGuard guard(x.device());
+  ssd_check_inputs(x, dt, A, Bm, Cm);
+  const SsdDims d = ssd_dims(x, Bm, seq_len);
+  const float* bias = dt_bias.has_value() ? dt_bias->data_ptr<float>() : nullptr;
+  SsdFwd f = ssd_forward_internals(d, x, dt, A, Bm, Cm, bias, softplus);
+  auto y = at::empty_like(x);
+  check(b200_ssd_combine(f.yd.data_ptr(), f.yoff.data_ptr(), x.data_ptr(), f.acs.data_ptr<float>(),
+                         D.has_value() ? D->data_ptr<float>() : nullptr, y.data_ptr(), d.M, d.H, d.P, cur_stream()),
+        "ssd_combine");
+  return y;
+}
+
+// returns dx, ddt (bf16), dA, dB, dC (B/C dtype), dD, ddt_bias (fp32; undefined tensors when the input was absent)
+std::vector<at::Tensor> ssd_scan_bwd(const at::Tensor& dy, const at::Tensor& x, const at::Tensor& dt, const at::Tensor& A,
+                                     const at::Tensor& Bm, const at::Tensor& Cm, const c10::optional<at::Tensor>& D,
+                                     const c10::optional<at::Tensor>& dt_bias, int64_t seq_len, bool softplus) {
+  c10::cuda::CUDAGuard guard(x.device());
+  ssd_check_inputs(x, dt, A, Bm, Cm);
+  need(dy, "dy", at::kBFloat16);
+  TORCH_CHECK(dy.is_contiguous() && dy.sizes() == x.sizes(), "ssd: dy must match x");
+  const SsdDims d = ssd_dims(x, Bm, seq_len);
+  const float* bias = dt_bias.has_value() ? dt_bias->data_ptr<float>() : nullptr;
+  const float* Dp = D.has_value() ? D->data_ptr<float>() : nullptr;
+  SsdFwd f = ssd_forward_internals(d, x, dt, A, Bm, Cm, bias, softplus);   // recompute (nothing but inputs is saved)
+  auto f32 = x.options().dtype(at::kFloat);
+  auto bf = x.options();
+  const long long LL = (long long)kL * kL;
+  const long long MH = d.M * d.H;
+  // output branch: dYs = dy * exp(acs); dacs, dD partials
+  auto dys = at::empty_like(x);
+  auto dacs = at::empty({d.M, d.H}, f32), dDrow = at::empty({d.M, d.H}, f32);
+  check(b200_ssd_dyoff(dy.data_ptr(), f.yoff.data_ptr(), x.data_ptr(), f.acs.data_ptr<float>(), dys.data_ptr(),
+                       dacs.data_ptr<float>(), dDrow.data_ptr<float>(), MH, d.P, cur_stream()), "ssd_dyoff");
+  // intra-chunk: dMh = dy x^T ; dx_diag = Mh^T dy
+  auto dMh = at::empty({d.nbc, d.H, kL, kL}, bf);
+  bg(dy.data_ptr(), x.data_ptr(), dMh.data_ptr(), kL, kL, d.P, d.HP, d.HP, kL, d.H, d.nbc, d.P, (long long)kL * d.HP, d.P,
+     (long long)kL * d.HP, LL, d.H * LL, 0, 0, 0, 0, "ssd_bgemm_dMh");
+  auto dxd = at::empty_like(x);
+  bg(f.Mh.data_ptr(), dy.data_ptr(), dxd.data_ptr(), kL, d.P, kL, kL, d.HP, d.HP, d.H, d.nbc, LL, d.H * LL, d.P,
+     (long long)kL * d.HP, d.P, (long long)kL * d.HP, 1, 1, 0, 0, "ssd_bgemm_dxdiag");
+  f.Mh = at::Tensor();
+  auto ddtv = at::zeros({d.M, d.H}, f32);
+  auto dCB = at::empty({d.nbc, d.G, kL, kL}, bf);
+  check(b200_ssd_mask_bwd(dMh.data_ptr(), f.CB.data_ptr(), f.acs.data_ptr<float>(), f.dtv.data_ptr<float>(), dCB.data_ptr(),
+                          dacs.data_ptr<float>(), ddtv.data_ptr<float>(), d.nbc, d.H, d.G, cur_stream()), "ssd_mask_bwd");
+  dMh = at::Tensor();
+  auto dC32 = at::empty({d.M, d.G, d.Nd}, f32), dB32 = at::empty({d.M, d.G, d.Nd}, f32);
+  bg(dCB.data_ptr(), Bm.data_ptr(), dC32.data_ptr(), kL, d.Nd, kL, kL, d.GN, d.GN, d.G, d.nbc, LL, d.G * LL, d.Nd,
+     (long long)kL * d.GN, d.Nd, (long long)kL * d.GN, 0, 1, 0, 1, "ssd_bgemm_dC_diag");
+  bg(dCB.data_ptr(), Cm.data_ptr(), dB32.data_ptr(), kL, d.Nd, kL, kL, d.GN, d.GN, d.G, d.nbc, LL, d.G * LL, d.Nd,
+     (long long)kL * d.GN, d.Nd, (long long)kL * d.GN, 1, 1, 0, 1, "ssd_bgemm_dB_diag");
+  // inter-chunk: dprev = C^T dYs ; dC += dYs prev^T
+  auto dprev = at::empty({d.nbc, d.Nd, d.HP}, f32);
+  bg(Cm.data_ptr(), dys.data_ptr(), dprev.data_ptr(), d.Nd, d.Hg * d.P, kL, d.GN, d.HP, d.HP, d.G, d.nbc, d.Nd,
+     (long long)kL * d.GN, (long long)d.Hg * d.P, (long long)kL * d.HP, (long long)d.Hg * d.P, (long long)d.Nd * d.HP, 1, 1, 0, 1,
+     "ssd_bgemm_dprev");
+  bg(dys.data_ptr(), f.prev.data_ptr(), dC32.data_ptr(), kL, d.Nd, d.Hg * d.P, d.HP, d.HP, d.GN, d.G, d.nbc,
+     (long long)d.Hg * d.P, (long long)kL * d.HP, (long long)d.Hg * d.P, (long long)d.Nd * d.HP, d.Nd, (long long)kL * d.GN, 0, 0, 2,
+     1, "ssd_bgemm_dC_off");
+  auto dstates = at::empty({d.nbc, d.Nd, d.HP}, bf);
+  auto daL = at::zeros({d.nbc, d.H}, f32);
+  check(b200_ssd_state_pass_bwd(dprev.data_ptr<float>(), f.prev.data_ptr(), f.aL.data_ptr<float>(), dstates.data_ptr(),
+                                daL.data_ptr<float>(), d.batch, d.nc, d.Nd, d.H, d.P, cur_stream()), "ssd_state_pass_bwd");
+  dprev = at::Tensor();
+  // chunk states: dXs = B dS ; dB += Xs dS^T
+  auto dxs = at::empty_like(x);
+  bg(Bm.data_ptr(), dstates.data_ptr(), dxs.data_ptr(), kL, d.Hg * d.P, d.Nd, d.GN, d.HP, d.HP, d.G, d.nbc, d.Nd,
+     (long long)kL * d.GN, (long long)d.Hg * d.P, (long long)d.Nd * d.HP, (long long)d.Hg * d.P, (long long)kL * d.HP, 0, 1, 0, 0,
+     "ssd_bgemm_dXs");
+  bg(f.xs.data_ptr(), dstates.data_ptr(), dB32.data_ptr(), kL, d.Nd, d.Hg * d.P, d.HP, d.HP, d.GN, d.G, d.nbc,
+     (long long)d.Hg * d.P, (long long)kL * d.HP, (long long)d.Hg * d.P, (long long)d.Nd * d.HP, d.Nd, (long long)kL * d.GN, 0, 0, 2,
+     1, "ssd_bgemm_dB_states");
+  auto dx = at::empty_like(x);
+  check(b200_ssd_dx(dxd.data_ptr(), dxs.data_ptr(), dy.data_ptr(), x.data_ptr(), f.dtv.data_ptr<float>(),
+                    f.acs.data_ptr<float>(), f.aL.data_ptr<float>(), Dp, dx.data_ptr(), ddtv.data_ptr<float>(),
+                    dacs.data_ptr<float>(), daL.data_ptr<float>(), MH, d.H, d.P, cur_stream()), "ssd_dx");
+  auto ddt = at::empty_like(dt);
+  auto dA = at::zeros({d.H}, f32);
+  at::Tensor dbias;
+  if (dt_bias.has_value()) dbias = at::zeros({d.H}, f32);
+  check(b200_ssd_dt_bwd(dt.data_ptr(), A.data_ptr<float>(), bias, f.dtv.data_ptr<float>(), dacs.data_ptr<float>(),
+                        ddtv.data_ptr<float>(), daL.data_ptr<float>(), ddt.data_ptr(), dA.data_ptr<float>(),
+                        dbias.defined() ? dbias.data_ptr<float>() : nullptr, d.nbc, d.H, softplus ? 1 : 0, cur_stream()),
+        "ssd_dt_bwd");
+  at::Tensor dD;
+  if (D.has_value()) dD = dDrow.sum(0);
+  return {dx, ddt, dA, dB32.to(Bm.scalar_type()), dC32.to(Cm.scalar_type()), dD, dbias};
+}
+
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.doc() = "fms_fsdp_b200 sm_100a kernels";
   m.def("gemm", &gemm);
@@ -471,6 +652,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("signal_barrier", &signal_barrier);
   m.def("causal_conv1d_fwd", &causal_conv1d_fwd);
   m.def("causal_conv1d_bwd", &causal_conv1d_bwd);
+  m.def("ssd_scan_fwd", &ssd_scan_fwd);
+  m.def("ssd_scan_bwd", &ssd_scan_bwd);
   m.def("set_attn_fwd_version", &set_attn_fwd_version);
   m.def("set_attn_bwd_version", &set_attn_bwd_version);
   m.def("set_gemm_2cta", &set_gemm_2cta);

@@ -49,9 +49,15 @@ struct GemmParams {
   void* C;
   const void* R;        // residual (bf16) or nullptr
   int m_tiles, n_tiles;
+  // batched mode (BATCH = true): nb0 x nb1 independent problems; operands come through rank-4 tensor maps
+  // {inner, outer, b0, b1}; C (and R) of problem (b0, b1) start at b0 * sc0 + b1 * sc1 elements
+  int nb0, nb1;
+  long long sc0, sc1;
 };
 
-template <bool A_MN, bool B_MN, int EPI, typename OutT>
+// BATCH: many small independent GEMMs in one persistent launch (Mamba2 SSD chunk products: C_c B_c^T, masked-score x X,
+// chunk states ...).  The tile loop runs over (problem, m-tile, n-tile); TMA coordinates get the two batch indices.
+template <bool A_MN, bool B_MN, int EPI, typename OutT, bool BATCH = false>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -67,7 +73,8 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int num_kb = (p.K + BK - 1) / BK;
-  const int num_tiles = p.m_tiles * p.n_tiles;
+  const int tiles_per_problem = p.m_tiles * p.n_tiles;
+  const int num_tiles = BATCH ? tiles_per_problem * p.nb0 * p.nb1 : tiles_per_problem;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -94,9 +101,19 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       int stage = 0;
       uint32_t phase = 0;
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-        int mt, nt;
-        tile_coords(t, p.m_tiles, p.n_tiles, mt, nt);
+        int mt, nt, b0 = 0, b1 = 0;
+        if constexpr (BATCH) {
+          const int prob = t / tiles_per_problem;
+          b0 = prob % p.nb0; b1 = prob / p.nb0;
+          tile_coords(t - prob * tiles_per_problem, p.m_tiles, p.n_tiles, mt, nt);
+        } else {
+          tile_coords(t, p.m_tiles, p.n_tiles, mt, nt);
+        }
         const int m0 = mt * BM, n0 = nt * BN;
+        auto load = [&](void* dst, const CUtensorMap* tm, int c0, int c1) {
+          if constexpr (BATCH) tma_load_4d(dst, tm, &full_bar[stage], c0, c1, b0, b1);
+          else tma_load_2d(dst, tm, &full_bar[stage], c0, c1);
+        };
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * STAGE_BYTES;
@@ -104,18 +121,18 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
           const int k0 = kb * BK;
           if constexpr (!A_MN) {
-            tma_load_2d(sa, &tmA, &full_bar[stage], k0, m0);          // box {64 k, 128 rows}
+            load(sa, &tmA, k0, m0);                                    // box {64 k, 128 rows}
           } else {
 #pragma unroll
             for (int j = 0; j < BM / 64; ++j)                          // boxes {64 m, 64 k-rows}
-              tma_load_2d(sa + j * (64 * BK * 2), &tmA, &full_bar[stage], m0 + 64 * j, k0);
+              load(sa + j * (64 * BK * 2), &tmA, m0 + 64 * j, k0);
           }
           if constexpr (!B_MN) {
-            tma_load_2d(sb, &tmB, &full_bar[stage], k0, n0);          // box {64 k, 256 rows}
+            load(sb, &tmB, k0, n0);                                    // box {64 k, 256 rows}
           } else {
 #pragma unroll
             for (int j = 0; j < BN / 64; ++j)
-              tma_load_2d(sb + j * (64 * BK * 2), &tmB, &full_bar[stage], n0 + 64 * j, k0);
+              load(sb + j * (64 * BK * 2), &tmB, n0 + 64 * j, k0);
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -159,14 +176,21 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     uint32_t acc_phase = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
       int mt, nt;
-      tile_coords(t, p.m_tiles, p.n_tiles, mt, nt);
+      size_t boff = 0;
+      if constexpr (BATCH) {
+        const int prob = t / tiles_per_problem;
+        boff = (size_t)(prob % p.nb0) * p.sc0 + (size_t)(prob / p.nb0) * p.sc1;
+        tile_coords(t - prob * tiles_per_problem, p.m_tiles, p.n_tiles, mt, nt);
+      } else {
+        tile_coords(t, p.m_tiles, p.n_tiles, mt, nt);
+      }
       const int m0 = mt * BM, n0 = nt * BN;
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const int row = m0 + q * 32 + lane;
       const bool row_ok = row < p.M;
-      OutT* crow = reinterpret_cast<OutT*>(p.C) + static_cast<size_t>(row) * p.ldc;
-      const __nv_bfloat16* rrow = reinterpret_cast<const __nv_bfloat16*>(p.R) + static_cast<size_t>(row) * p.ldr;
+      OutT* crow = reinterpret_cast<OutT*>(p.C) + boff + static_cast<size_t>(row) * p.ldc;
+      const __nv_bfloat16* rrow = reinterpret_cast<const __nv_bfloat16*>(p.R) + boff + static_cast<size_t>(row) * p.ldr;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
 #pragma unroll 1
       for (int c = 0; c < BN; c += 64) {
@@ -238,17 +262,17 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   }
 }
 
-template <bool A_MN, bool B_MN, int EPI, typename OutT>
+template <bool A_MN, bool B_MN, int EPI, typename OutT, bool BATCH = false>
 static int launch_one(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream) {
-  auto kern = gemm_bf16_tcgen05<A_MN, B_MN, EPI, OutT>;
+  auto kern = gemm_bf16_tcgen05<A_MN, B_MN, EPI, OutT, BATCH>;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
     if (e != cudaSuccess) return (int)e;
     configured = true;
   }
-  int tiles = p.m_tiles * p.n_tiles;
-  int grid = tiles < sm_count() ? tiles : sm_count();
+  long long tiles = (long long)p.m_tiles * p.n_tiles * (BATCH ? (long long)p.nb0 * p.nb1 : 1);
+  int grid = tiles < sm_count() ? (int)tiles : sm_count();
   kern<<<grid, GEMM_THREADS, SMEM_BYTES, stream>>>(tmA, tmB, p);
   return (int)cudaGetLastError();
 }
@@ -266,7 +290,56 @@ static int dispatch_epi(const CUtensorMap& a, const CUtensorMap& b, const GemmPa
   return launch_one<A_MN, B_MN, EPI_ACCUM, __nv_bfloat16>(a, b, p, s);
 }
 
+// batched dispatch: store / accumulate epilogues, bf16 or fp32 output
+template <bool A_MN, bool B_MN>
+static int dispatch_batched(const CUtensorMap& a, const CUtensorMap& b, const GemmParams& p, int epi, int out_fp32,
+                            cudaStream_t s) {
+  if (out_fp32) {
+    if (epi == EPI_ACCUM) return launch_one<A_MN, B_MN, EPI_ACCUM, float, true>(a, b, p, s);
+    return launch_one<A_MN, B_MN, EPI_STORE, float, true>(a, b, p, s);
+  }
+  if (epi == EPI_ACCUM) return launch_one<A_MN, B_MN, EPI_ACCUM, __nv_bfloat16, true>(a, b, p, s);
+  return launch_one<A_MN, B_MN, EPI_STORE, __nv_bfloat16, true>(a, b, p, s);
+}
+
+inline int make_tmap_4d_bf16(CUtensorMap* m, const void* ptr, uint64_t inner, uint64_t outer, uint64_t nb0, uint64_t nb1,
+                             uint64_t ld, uint64_t s0, uint64_t s1, uint32_t box_inner, uint32_t box_outer) {
+  uint64_t dims[4] = {inner, outer, nb0, nb1};
+  uint64_t strides[3] = {ld * 2, s0 * 2, s1 * 2};
+  uint32_t box[4] = {box_inner, box_outer, 1, 1};
+  return make_tmap(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, ptr, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+}
+
 }  // namespace b200
+
+// Batched C[b0,b1] = op(A[b0,b1]) op(B[b0,b1]) (+C): nb0 x nb1 problems of identical shape; sa*/sb*/sc* are the element
+// strides of the two batch indices (each a multiple of 8 elements; use any valid stride when the count is 1).
+extern "C" int b200_bgemm_bf16(const void* A, const void* B, void* C, int M, int N, int K, int lda, int ldb, int ldc,
+                               int nb0, int nb1, long long sa0, long long sa1, long long sb0, long long sb1,
+                               long long sc0, long long sc1, int a_mn, int b_mn, int epi, int out_fp32,
+                               cudaStream_t stream) {
+  using namespace b200;
+  if (epi == EPI_RESIDUAL) return -1;
+  CUtensorMap tmA, tmB;
+  int rc;
+  if (!a_mn) rc = make_tmap_4d_bf16(&tmA, A, K, M, nb0, nb1, lda, sa0, sa1, BK, BM);
+  else       rc = make_tmap_4d_bf16(&tmA, A, M, K, nb0, nb1, lda, sa0, sa1, 64, BK);
+  if (rc) return 1000 - rc;
+  if (!b_mn) rc = make_tmap_4d_bf16(&tmB, B, K, N, nb0, nb1, ldb, sb0, sb1, BK, BN);
+  else       rc = make_tmap_4d_bf16(&tmB, B, N, K, nb0, nb1, ldb, sb0, sb1, 64, BK);
+  if (rc) return 2000 - rc;
+  GemmParams p;
+  p.M = M; p.N = N; p.K = K; p.ldc = ldc; p.ldr = 0; p.C = C; p.R = nullptr;
+  p.m_tiles = (M + BM - 1) / BM;
+  p.n_tiles = (N + BN - 1) / BN;
+  p.nb0 = nb0; p.nb1 = nb1; p.sc0 = sc0; p.sc1 = sc1;
+  if (a_mn) {
+    if (b_mn) return dispatch_batched<true, true>(tmA, tmB, p, epi, out_fp32, stream);
+    return dispatch_batched<true, false>(tmA, tmB, p, epi, out_fp32, stream);
+  }
+  if (b_mn) return dispatch_batched<false, true>(tmA, tmB, p, epi, out_fp32, stream);
+  return dispatch_batched<false, false>(tmA, tmB, p, epi, out_fp32, stream);
+}
 
 // C[M,N] = op(A) op(B) (+R | +C).  a_mn: A is stored [K,M] (M contiguous) else [M,K];  b_mn: B is stored [K,N]
 // (N contiguous) else [N,K].  lda/ldb/ldc/ldr are row strides in elements.  Returns 0 or a CUDA error code.
@@ -286,6 +359,7 @@ extern "C" int b200_gemm_bf16(const void* A, const void* B, void* C, const void*
   p.M = M; p.N = N; p.K = K; p.ldc = ldc; p.ldr = ldr; p.C = C; p.R = R;
   p.m_tiles = (M + BM - 1) / BM;
   p.n_tiles = (N + BN - 1) / BN;
+  p.nb0 = p.nb1 = 1; p.sc0 = p.sc1 = 0;
   if (a_mn) {
     if (b_mn) return dispatch_epi<true, true>(tmA, tmB, p, epi, out_fp32, stream);
     return dispatch_epi<true, false>(tmA, tmB, p, epi, out_fp32, stream);

@@ -335,5 +335,31 @@ def causal_conv1d_bwd(dy, x, w, b, seq_len, activation=True):
     return dx, dw, (None if b is None else db)
 
 
-ssd_scan_fwd = torch_kernels.ssd_scan_chunked   # matmul (chunked SSD) form in ATen until ssd.cu lands
+# ------------------------------------------------------------------------------ Mamba2 SSD scan
+def _ssd_native_ok(x, dt, Bm, Cm, seq_len):
+    return (x.is_cuda and x.dtype == dt.dtype == Bm.dtype == Cm.dtype == torch.bfloat16 and x.dim() == 3
+            and seq_len % 128 == 0 and x.shape[2] % 32 == 0 and Bm.shape[2] % 8 == 0 and x.shape[1] % Bm.shape[1] == 0)
+
+
+def _f32c(t):
+    return None if t is None else t.detach().float().contiguous()
+
+
+def ssd_scan_fwd(x, dt, A, Bm, Cm, D, dt_bias, seq_len, chunk_size, dt_softplus=True):
+    """Mamba2 SSD scan (csrc/ssd.cu + batched tcgen05 GEMMs); 128-token internal chunks whatever ``chunk_size``."""
+    if not _ssd_native_ok(x, dt, Bm, Cm, seq_len):
+        return torch_kernels.ssd_scan_chunked(x, dt, A, Bm, Cm, D, dt_bias, seq_len, chunk_size, dt_softplus)
+    return _C.ssd_scan_fwd(x.contiguous(), dt.contiguous(), _f32c(A), Bm.contiguous(), Cm.contiguous(), _f32c(D),
+                           _f32c(dt_bias), int(seq_len), bool(dt_softplus))
+
+
+def ssd_scan_bwd(dy, x, dt, A, Bm, Cm, D, dt_bias, seq_len, chunk_size, dt_softplus=True):
+    if not _ssd_native_ok(x, dt, Bm, Cm, seq_len):
+        return None                                   # caller differentiates the ATen chunked form instead
+    dx, ddt, dA, dB, dC, dD, dbias = _C.ssd_scan_bwd(dy.contiguous(), x.contiguous(), dt.contiguous(), _f32c(A),
+                                                     Bm.contiguous(), Cm.contiguous(), _f32c(D), _f32c(dt_bias),
+                                                     int(seq_len), bool(dt_softplus))
+    return dx, ddt, dA, dB, dC, dD, dbias
+
+
 selective_scan_fwd = torch_kernels.selective_scan_fwd

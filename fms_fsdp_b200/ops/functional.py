@@ -436,10 +436,12 @@ class _SSDScan(torch.autograd.Function):
         A, D, dt_bias = ctx.params
         seq_len, chunk_size = ctx.args
         K = ctx.K
+        native = None
         if hasattr(K, "ssd_scan_bwd"):
-            dx, ddt, dA, dB, dC, dD, ddtb = K.ssd_scan_bwd(
-                dy.contiguous(), x, dt, _wdata(A), Bm, Cm, None if D is None else _wdata(D),
-                None if dt_bias is None else _wdata(dt_bias), seq_len, chunk_size)
+            native = K.ssd_scan_bwd(dy.contiguous(), x, dt, _wdata(A), Bm, Cm, None if D is None else _wdata(D),
+                                    None if dt_bias is None else _wdata(dt_bias), seq_len, chunk_size)
+        if native is not None:
+            dx, ddt, dA, dB, dC, dD, ddtb = native
         else:
             with torch.enable_grad():
                 leaves = [t.detach().float().requires_grad_() for t in (x, dt, _wdata(A), Bm, Cm)]

@@ -249,6 +249,39 @@ def main(groups):
             rec("conv1d", fwd=relerr(y1, y0), dx=relerr(g1[0], g0[0]), dw=relerr(g1[1], g0[1]), db=relerr(g1[2], g0[2]))
         chk("conv1d", t_conv)
 
+    if "ssd" in groups:
+        def t_ssd():
+            for (Bs, S, H, P, G, N) in [(2, 256, 8, 64, 1, 128), (1, 384, 8, 64, 2, 64), (2, 4096, 128, 64, 1, 128)]:
+                M = Bs * S
+                x = torch.randn(M, H, P, device=dev).bfloat16().requires_grad_()
+                dt = (torch.randn(M, H, device=dev) * 0.5 - 1.0).bfloat16().requires_grad_()
+                A = -(torch.rand(H, device=dev) * 4 + 0.5)
+                Bm = (torch.randn(M, G, N, device=dev) * 0.3).bfloat16().requires_grad_()
+                Cm = (torch.randn(M, G, N, device=dev) * 0.3).bfloat16().requires_grad_()
+                D = torch.randn(H, device=dev); bias = torch.randn(H, device=dev) * 0.2
+                dy = torch.randn(M, H, P, device=dev).bfloat16()
+                r = dict(B=Bs, S=S, H=H, P=P, G=G, N=N)
+                y1 = CK.ssd_scan_fwd(x.detach(), dt.detach(), A, Bm.detach(), Cm.detach(), D, bias, S, 256)
+                g1 = CK.ssd_scan_bwd(dy, x.detach(), dt.detach(), A, Bm.detach(), Cm.detach(), D, bias, S, 256)
+                torch.cuda.synchronize()
+                if M <= 4096:
+                    Al, Dl, bl = A.clone().requires_grad_(), D.clone().requires_grad_(), bias.clone().requires_grad_()
+                    y0 = TK.ssd_scan_chunked(x, dt, Al, Bm, Cm, Dl, bl, S, 128)
+                    g0 = torch.autograd.grad(y0, [x, dt, Al, Bm, Cm, Dl, bl], dy.float())
+                    r.update(y=relerr(y1, y0))
+                    for nm, a, b in zip(["dx", "ddt", "dA", "dB", "dC", "dD", "dbias"], g1, g0):
+                        r[nm] = relerr(a, b)
+                else:
+                    r["fwd_ms"] = time_ms(lambda: CK.ssd_scan_fwd(x.detach(), dt.detach(), A, Bm.detach(), Cm.detach(), D, bias, S, 256))
+                    r["bwd_ms"] = time_ms(lambda: CK.ssd_scan_bwd(dy, x.detach(), dt.detach(), A, Bm.detach(), Cm.detach(), D, bias, S, 256))
+                    r["aten_fwd_ms"] = time_ms(lambda: TK.ssd_scan_chunked(x.detach(), dt.detach(), A, Bm.detach(), Cm.detach(), D, bias, S, 256), iters=3)
+                    r["finite"] = bool(torch.isfinite(y1).all()) and all(bool(torch.isfinite(t).all()) for t in g1)
+                rec("ssd", **r)
+        try:
+            t_ssd()
+        except Exception as ex:
+            rec("ssd", ok=False, error=repr(ex)[:500], tb=traceback.format_exc()[-900:])
+
     if "attn" in groups:
         for ver in ([int(x) for x in os.environ.get("DIAG_ATTN_VERS", "2").split(",")]):
           bver = int(os.environ.get("DIAG_ATTN_BWD", "3" if ver == 2 else str(ver)))

@@ -200,3 +200,28 @@ def test_fused_collectives_two_gpus():
     assert out["allgather_equal"] and out["reduce_scatter_maxdiff"] < 1e-3
     f, t = out["engine_fsdp"]["fused"], out["engine_fsdp"]["torch"]
     assert all(abs(a[1] - b[1]) < 2e-2 * b[1] for a, b in zip(f, t))
+
+
+@pytest.mark.parametrize("shape", [(2, 256, 8, 64, 1, 128), (1, 384, 8, 64, 2, 64)])
+def test_ssd_scan_native_vs_chunked_oracle(K, shape):
+    """Mamba2 SSD scan: batched tcgen05 GEMMs + csrc/ssd.cu glue against the fp32 ATen chunked formulation."""
+    CK, TK = K
+    Bs, S, H, P, G, N = shape
+    M = Bs * S
+    x = torch.randn(M, H, P, device=DEV).bfloat16().requires_grad_()
+    dt = (torch.randn(M, H, device=DEV) * 0.5 - 1.0).bfloat16().requires_grad_()
+    A = (-(torch.rand(H, device=DEV) * 4 + 0.5)).requires_grad_()
+    Bm = (torch.randn(M, G, N, device=DEV) * 0.3).bfloat16().requires_grad_()
+    Cm = (torch.randn(M, G, N, device=DEV) * 0.3).bfloat16().requires_grad_()
+    D = torch.randn(H, device=DEV).requires_grad_()
+    bias = (torch.randn(H, device=DEV) * 0.2).requires_grad_()
+    dy = torch.randn(M, H, P, device=DEV).bfloat16()
+    y0 = TK.ssd_scan_chunked(x, dt, A, Bm, Cm, D, bias, S, 128)
+    g0 = torch.autograd.grad(y0, [x, dt, A, Bm, Cm, D, bias], dy.float())
+    d = lambda t: t.detach()
+    y1 = CK.ssd_scan_fwd(d(x), d(dt), d(A), d(Bm), d(Cm), d(D), d(bias), S, 256)
+    g1 = CK.ssd_scan_bwd(dy, d(x), d(dt), d(A), d(Bm), d(Cm), d(D), d(bias), S, 256)
+    assert g1 is not None, "native SSD path was not taken"
+    assert rel(y1, y0) < 2e-2
+    for name, a, b in zip(["dx", "ddt", "dA", "dB", "dC", "dD", "dbias"], g1, g0):
+        assert rel(a, b) < 3e-2, name
