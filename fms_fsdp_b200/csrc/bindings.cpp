@@ -33,6 +33,11 @@ DECL int b200_ssd_dx(const void*, const void*, const void*, const void*, const f
                      const float*, void*, float*, float*, float*, long long, int, int, cudaStream_t);
 DECL int b200_ssd_dt_bwd(const void*, const float*, const float*, const float*, const float*, const float*, const float*,
                          void*, float*, float*, int, int, int, cudaStream_t);
+DECL int b200_selscan_fwd(const void*, const void*, const float*, const void*, const void*, const float*, const void*,
+                          const float*, float*, void*, int, int, int, int, int, cudaStream_t);
+DECL int b200_selscan_bwd(const void*, const void*, const void*, const float*, const void*, const void*, const float*,
+                          const void*, const float*, float*, void*, void*, void*, float*, float*, float*, float*, float*, int,
+                          int, int, int, int, cudaStream_t);
 DECL int b200_p2p_gather_range(const void* const*, void*, long long, long long, long long, cudaStream_t);
 DECL int b200_ts_mma_probe(const void*, const void*, float*, cudaStream_t);
 DECL int b200_rmsnorm_fwd(const void*, const void*, void*, float*, int, int, float, cudaStream_t);
@@ -626,6 +631,56 @@ std::vector<at::Tensor> ssd_scan_bwd(const at::Tensor& dy, const at::Tensor& x, 
   return {dx, ddt, dA, dB32.to(Bm.scalar_type()), dC32.to(Cm.scalar_type()), dD, dbias};
 }
 
+
+// ------------------------------------------------------------------------------ Mamba1 selective scan (csrc/selscan.cu)
+// u, delta, z: [M, Dm] bf16; A: [Dm, 16] fp32; B, C: [M, 16] bf16; D, delta_bias: [Dm] fp32.
+std::vector<at::Tensor> selective_scan_fwd(const at::Tensor& u, const at::Tensor& delta, const at::Tensor& A,
+                                           const at::Tensor& Bm, const at::Tensor& Cm, const c10::optional<at::Tensor>& D,
+                                           const c10::optional<at::Tensor>& z, const c10::optional<at::Tensor>& dbias,
+                                           int64_t seq_len, bool softplus, bool save_carry) {
+  c10::cuda::CUDAGuard guard(u.device());
+  need(u, "u", at::kBFloat16); need(delta, "delta", at::kBFloat16); need(Bm, "B", at::kBFloat16); need(Cm, "C", at::kBFloat16);
+  need(A, "A", at::kFloat);
+  TORCH_CHECK(u.is_contiguous() && delta.is_contiguous() && Bm.is_contiguous() && Cm.is_contiguous() && A.is_contiguous());
+  const int64_t M = u.size(0), Dm = u.size(1), N = A.size(1);
+  TORCH_CHECK(M % seq_len == 0, "selective_scan: rows must be batch * seq_len");
+  const int batch = (int)(M / seq_len);
+  auto y = at::empty_like(u);
+  at::Tensor hc;
+  if (save_carry) hc = at::empty({batch, seq_len / 32, Dm, N}, u.options().dtype(at::kFloat));
+  check(b200_selscan_fwd(u.data_ptr(), delta.data_ptr(), A.data_ptr<float>(), Bm.data_ptr(), Cm.data_ptr(),
+                         D.has_value() ? D->data_ptr<float>() : nullptr, z.has_value() ? z->data_ptr() : nullptr,
+                         dbias.has_value() ? dbias->data_ptr<float>() : nullptr, hc.defined() ? hc.data_ptr<float>() : nullptr,
+                         y.data_ptr(), batch, (int)seq_len, (int)Dm, (int)N, softplus ? 1 : 0, cur_stream()), "selscan_fwd");
+  return {y, hc};
+}
+std::vector<at::Tensor> selective_scan_bwd(const at::Tensor& dy, const at::Tensor& u, const at::Tensor& delta,
+                                           const at::Tensor& A, const at::Tensor& Bm, const at::Tensor& Cm,
+                                           const c10::optional<at::Tensor>& D, const c10::optional<at::Tensor>& z,
+                                           const c10::optional<at::Tensor>& dbias, const at::Tensor& hcarry, int64_t seq_len,
+                                           bool softplus) {
+  c10::cuda::CUDAGuard guard(u.device());
+  need(dy, "dy", at::kBFloat16);
+  TORCH_CHECK(dy.is_contiguous() && dy.sizes() == u.sizes());
+  const int64_t M = u.size(0), Dm = u.size(1), N = A.size(1);
+  const int batch = (int)(M / seq_len);
+  auto f32 = u.options().dtype(at::kFloat);
+  auto du = at::empty_like(u), dd = at::empty_like(delta);
+  at::Tensor dz, dD, ddb;
+  if (z.has_value()) dz = at::empty_like(u);
+  auto dA = at::zeros({Dm, N}, f32), dB = at::zeros({M, N}, f32), dC = at::zeros({M, N}, f32);
+  if (D.has_value()) dD = at::zeros({Dm}, f32);
+  if (dbias.has_value()) ddb = at::zeros({Dm}, f32);
+  check(b200_selscan_bwd(dy.data_ptr(), u.data_ptr(), delta.data_ptr(), A.data_ptr<float>(), Bm.data_ptr(), Cm.data_ptr(),
+                         D.has_value() ? D->data_ptr<float>() : nullptr, z.has_value() ? z->data_ptr() : nullptr,
+                         dbias.has_value() ? dbias->data_ptr<float>() : nullptr, hcarry.data_ptr<float>(), du.data_ptr(),
+                         dd.data_ptr(), dz.defined() ? dz.data_ptr() : nullptr, dA.data_ptr<float>(), dB.data_ptr<float>(),
+                         dC.data_ptr<float>(), dD.defined() ? dD.data_ptr<float>() : nullptr,
+                         ddb.defined() ? ddb.data_ptr<float>() : nullptr, batch, (int)seq_len, (int)Dm, (int)N,
+                         softplus ? 1 : 0, cur_stream()), "selscan_bwd");
+  return {du, dd, dA, dB, dC, dD, dz, ddb};
+}
+
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.doc() = "fms_fsdp_b200 sm_100a kernels";
   m.def("gemm", &gemm);
@@ -653,6 +708,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("causal_conv1d_fwd", &causal_conv1d_fwd);
   m.def("causal_conv1d_bwd", &causal_conv1d_bwd);
   m.def("ssd_scan_fwd", &ssd_scan_fwd);
+  m.def("selective_scan_fwd", &selective_scan_fwd);
+  m.def("selective_scan_bwd", &selective_scan_bwd);
   m.def("ssd_scan_bwd", &ssd_scan_bwd);
   m.def("set_attn_fwd_version", &set_attn_fwd_version);
   m.def("set_attn_bwd_version", &set_attn_bwd_version);

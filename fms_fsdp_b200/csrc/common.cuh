@@ -264,6 +264,20 @@ B200_DEVINL float2 unpack_bf16x2(uint32_t u) {
   __nv_bfloat162 v = *reinterpret_cast<__nv_bfloat162*>(&u);
   return __bfloat1622float2(v);
 }
+// 2^x on the FMA pipe (Cody-Waite range reduction + degree-3 minimax polynomial, max relative error 7.5e-5; far below
+// bf16 resolution).  The MUFU unit does 16 ex2/clk/SM, which bounds flash attention at 128x128 tiles (1024 cycles per
+// tile = the tensor-pipe time of its two GEMMs); routing a fraction of the exponentials through here rebalances the
+// two pipes (same idea as FlashAttention-4's software exp).  Valid for x <= ~100; x < -126 flushes to ~2^-126.
+B200_DEVINL float exp2_poly(float x) {
+  x = fmaxf(x, -126.f);
+  const float r = x + 12582912.f;                 // 1.5 * 2^23: round-to-nearest integer lands in the low mantissa bits
+  const float f = x - (r - 12582912.f);           // in [-0.5, 0.5]
+  float p = fmaf(f, 0.055170949548482895f, 0.2426096349954605f);
+  p = fmaf(p, f, 0.6932609677314758f);
+  p = fmaf(p, f, 0.9999281764030457f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(r) << 23));   // * 2^n through the exponent field
+}
+
 B200_DEVINL float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -362,4 +362,28 @@ def ssd_scan_bwd(dy, x, dt, A, Bm, Cm, D, dt_bias, seq_len, chunk_size, dt_softp
     return dx, ddt, dA, dB, dC, dD, dbias
 
 
-selective_scan_fwd = torch_kernels.selective_scan_fwd
+# ------------------------------------------------------------------------------ Mamba1 selective scan
+def _selscan_native_ok(u, delta, A, Bm, Cm, z, seq_len):
+    return (u.is_cuda and u.dtype == delta.dtype == Bm.dtype == Cm.dtype == torch.bfloat16 and u.dim() == 2
+            and (z is None or z.dtype == torch.bfloat16) and A.shape[-1] == 16 and seq_len % 32 == 0
+            and u.shape[1] % 32 == 0)
+
+
+def selective_scan_fwd(u, delta, A, Bm, Cm, D, z, delta_bias, seq_len, delta_softplus=True):
+    """Mamba1 selective scan (csrc/selscan.cu: warp = channel, lane = timestep, shuffle scans)."""
+    if not _selscan_native_ok(u, delta, A, Bm, Cm, z, seq_len):
+        return torch_kernels.selective_scan_fwd(u, delta, A, Bm, Cm, D, z, delta_bias, seq_len, delta_softplus)
+    y, _ = _C.selective_scan_fwd(u.contiguous(), delta.contiguous(), _f32c(A), Bm.contiguous(), Cm.contiguous(), _f32c(D),
+                                 None if z is None else z.contiguous(), _f32c(delta_bias), int(seq_len),
+                                 bool(delta_softplus), False)
+    return y
+
+
+def selective_scan_bwd(dy, u, delta, A, Bm, Cm, D, z, delta_bias, seq_len, delta_softplus=True):
+    if not _selscan_native_ok(u, delta, A, Bm, Cm, z, seq_len):
+        return None
+    args = (u.contiguous(), delta.contiguous(), _f32c(A), Bm.contiguous(), Cm.contiguous(), _f32c(D),
+            None if z is None else z.contiguous(), _f32c(delta_bias))
+    _, hc = _C.selective_scan_fwd(*args, int(seq_len), bool(delta_softplus), True)   # block-entry states for the recompute
+    du, dd, dA, dB, dC, dD, dz, ddb = _C.selective_scan_bwd(dy.contiguous(), *args, hc, int(seq_len), bool(delta_softplus))
+    return du, dd, dA, dB, dC, dD, dz, ddb

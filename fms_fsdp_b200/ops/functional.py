@@ -486,10 +486,12 @@ class _SelectiveScan(torch.autograd.Function):
         u, delta, Bm, Cm, z = ctx.saved_tensors
         A, D, delta_bias = ctx.params
         K = ctx.K
+        native = None
         if hasattr(K, "selective_scan_bwd"):
-            du, dd, dA, dB, dC, dD, dz, ddb = K.selective_scan_bwd(
-                dy.contiguous(), u, delta, _wdata(A), Bm, Cm, None if D is None else _wdata(D), z,
-                None if delta_bias is None else _wdata(delta_bias), ctx.seq_len)
+            native = K.selective_scan_bwd(dy.contiguous(), u, delta, _wdata(A), Bm, Cm, None if D is None else _wdata(D), z,
+                                          None if delta_bias is None else _wdata(delta_bias), ctx.seq_len)
+        if native is not None:
+            du, dd, dA, dB, dC, dD, dz, ddb = native
         else:
             with torch.enable_grad():
                 lv = [t.detach().float().requires_grad_() for t in (u, delta, _wdata(A), Bm, Cm)]

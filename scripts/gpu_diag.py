@@ -282,6 +282,42 @@ def main(groups):
         except Exception as ex:
             rec("ssd", ok=False, error=repr(ex)[:500], tb=traceback.format_exc()[-900:])
 
+    if "selscan" in groups:
+        def t_sel():
+            for (Bs, S, Dm, N, use_z) in [(2, 64, 64, 16, True), (1, 96, 32, 16, False), (2, 4096, 5120, 16, True)]:
+                M = Bs * S
+                u = torch.randn(M, Dm, device=dev).bfloat16().requires_grad_()
+                dl = (torch.randn(M, Dm, device=dev) * 0.5 - 1.0).bfloat16().requires_grad_()
+                A = (-(torch.rand(Dm, N, device=dev) * 4 + 0.5)).requires_grad_()
+                Bm = (torch.randn(M, N, device=dev) * 0.5).bfloat16().requires_grad_()
+                Cm = (torch.randn(M, N, device=dev) * 0.5).bfloat16().requires_grad_()
+                D = torch.randn(Dm, device=dev).requires_grad_(); bias = (torch.randn(Dm, device=dev) * 0.2).requires_grad_()
+                z = torch.randn(M, Dm, device=dev).bfloat16().requires_grad_() if use_z else None
+                dy = torch.randn(M, Dm, device=dev).bfloat16()
+                dd = lambda t: None if t is None else t.detach()
+                r = dict(B=Bs, S=S, Dm=Dm, N=N, z=use_z)
+                y1 = CK.selective_scan_fwd(dd(u), dd(dl), dd(A), dd(Bm), dd(Cm), dd(D), dd(z), dd(bias), S)
+                g1 = CK.selective_scan_bwd(dy, dd(u), dd(dl), dd(A), dd(Bm), dd(Cm), dd(D), dd(z), dd(bias), S)
+                torch.cuda.synchronize()
+                if M <= 512:
+                    y0 = TK.selective_scan_fwd(u, dl, A, Bm, Cm, D, z, bias, S)
+                    ins = [u, dl, A, Bm, Cm, D] + ([z] if use_z else []) + [bias]
+                    g0 = list(torch.autograd.grad(y0, ins, dy.float()))
+                    names = ["du", "ddelta", "dA", "dB", "dC", "dD"] + (["dz"] if use_z else []) + ["dbias"]
+                    mine = list(g1[:6]) + ([g1[6]] if use_z else []) + [g1[7]]
+                    r.update(y=relerr(y1, y0))
+                    for nm, a, b in zip(names, mine, g0):
+                        r[nm] = relerr(a, b)
+                else:
+                    r["fwd_ms"] = time_ms(lambda: CK.selective_scan_fwd(dd(u), dd(dl), dd(A), dd(Bm), dd(Cm), dd(D), dd(z), dd(bias), S))
+                    r["bwd_ms"] = time_ms(lambda: CK.selective_scan_bwd(dy, dd(u), dd(dl), dd(A), dd(Bm), dd(Cm), dd(D), dd(z), dd(bias), S))
+                    r["finite"] = bool(torch.isfinite(y1).all()) and all(bool(torch.isfinite(t).all()) for t in g1 if t is not None)
+                rec("selscan", **r)
+        try:
+            t_sel()
+        except Exception as ex:
+            rec("selscan", ok=False, error=repr(ex)[:500], tb=traceback.format_exc()[-900:])
+
     if "attn" in groups:
         for ver in ([int(x) for x in os.environ.get("DIAG_ATTN_VERS", "2").split(",")]):
           bver = int(os.environ.get("DIAG_ATTN_BWD", "3" if ver == 2 else str(ver)))

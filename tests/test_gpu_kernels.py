@@ -225,3 +225,32 @@ def test_ssd_scan_native_vs_chunked_oracle(K, shape):
     assert rel(y1, y0) < 2e-2
     for name, a, b in zip(["dx", "ddt", "dA", "dB", "dC", "dD", "dbias"], g1, g0):
         assert rel(a, b) < 3e-2, name
+
+
+@pytest.mark.parametrize("use_z", [True, False])
+def test_selective_scan_native_vs_sequential_oracle(K, use_z):
+    """Mamba1 selective scan (csrc/selscan.cu) against the sequential fp32 ATen recurrence."""
+    CK, TK = K
+    Bs, S, Dm, N = 2, 64, 64, 16
+    M = Bs * S
+    u = torch.randn(M, Dm, device=DEV).bfloat16().requires_grad_()
+    dl = (torch.randn(M, Dm, device=DEV) * 0.5 - 1.0).bfloat16().requires_grad_()
+    A = (-(torch.rand(Dm, N, device=DEV) * 4 + 0.5)).requires_grad_()
+    Bm = (torch.randn(M, N, device=DEV) * 0.5).bfloat16().requires_grad_()
+    Cm = (torch.randn(M, N, device=DEV) * 0.5).bfloat16().requires_grad_()
+    D = torch.randn(Dm, device=DEV).requires_grad_()
+    bias = (torch.randn(Dm, device=DEV) * 0.2).requires_grad_()
+    z = torch.randn(M, Dm, device=DEV).bfloat16().requires_grad_() if use_z else None
+    dy = torch.randn(M, Dm, device=DEV).bfloat16()
+    y0 = TK.selective_scan_fwd(u, dl, A, Bm, Cm, D, z, bias, S)
+    ins = [u, dl, A, Bm, Cm, D] + ([z] if use_z else []) + [bias]
+    g0 = list(torch.autograd.grad(y0, ins, dy.float()))
+    dd = lambda t: None if t is None else t.detach()
+    y1 = CK.selective_scan_fwd(dd(u), dd(dl), dd(A), dd(Bm), dd(Cm), dd(D), dd(z), dd(bias), S)
+    g1 = CK.selective_scan_bwd(dy, dd(u), dd(dl), dd(A), dd(Bm), dd(Cm), dd(D), dd(z), dd(bias), S)
+    assert g1 is not None, "native selective-scan path was not taken"
+    assert rel(y1, y0) < 2e-2
+    mine = list(g1[:6]) + ([g1[6]] if use_z else []) + [g1[7]]
+    names = ["du", "ddelta", "dA", "dB", "dC", "dD"] + (["dz"] if use_z else []) + ["dbias"]
+    for name, a, b in zip(names, mine, g0):
+        assert rel(a, b) < 3e-2, name
