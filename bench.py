@@ -27,6 +27,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 BASELINE_TOK_S_GPU = 9600.0  # Llama2-7B on 96x H100, reference README.md:16 (best published)
+# best published tokens/s/GPU per model (BASELINE.md section 1, H100 column); models without a published number -> null
+PUBLISHED_TOK_S_GPU = {"llama2_7b": 9600.0, "llama2_13b": 4850.0, "llama2_34b": 1830.0, "llama2_70b": 890.0}
 
 
 def _args():
@@ -229,7 +231,7 @@ def run_ours(a):
             "value": round(value, 1), "unit": "tokens/s",
             "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": round(ms_step, 3),
             "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": round(value / world / BASELINE_TOK_S_GPU, 4),
+            "vs_baseline": (round(value / world / PUBLISHED_TOK_S_GPU[a.model], 4) if a.model in PUBLISHED_TOK_S_GPU else None),
             "dtype": "bf16", "data": "synthetic (reference dummy stream, random-init weights)",
             "impl": "ours",
             "tokens_per_sec_per_gpu": round(value / world, 1), "mfu_vs_measured_bf16_peak": round(mfu, 4),

@@ -40,7 +40,7 @@ int main(int argc, char** argv) {
   printf("v3 kernel mode %d.  mma: p_full seen | acc1+S(k+1) issued | ds_full seen | acc2+dP(k+1) issued || wg0: E wait, s_full, E done(p arrive), dp_full, D done || wg1: same\n", mode);
   for (int it = 0; it < 24; ++it) {
     printf("%2d |", it);
-    for (int s = 0; s < 14; ++s) printf(" %7lld", t[it * 16 + s] ? t[it * 16 + s] - t0 : -1);
+    for (int s = 0; s < 16; ++s) printf(" %7lld", t[it * 16 + s] ? t[it * 16 + s] - t0 : -1);
     printf("\n");
   }
   }
