@@ -45,6 +45,7 @@ def _args():
     p.add_argument("--collective_impl", default="auto")
     p.add_argument("--ac", default="0", help="selective activation checkpointing fraction, e.g. 0, 1/2, 1")
     p.add_argument("--nlayers", type=int, default=0, help="debug only: override depth (result is flagged invalid)")
+    p.add_argument("--trace", default="", help="with --profile: also export the chrome trace of the 2 profiled steps")
     p.add_argument("--profile", default="", help="write a per-kernel device-time table of 2 extra steps to this path")
     return p.parse_args()
 
@@ -263,6 +264,8 @@ def run_ours(a):
             os.makedirs(os.path.dirname(a.profile) or ".", exist_ok=True)
             with open(a.profile, "w") as f:
                 f.write(prof.key_averages().table(sort_by="cuda_time_total", row_limit=60, max_name_column_width=90))
+            if a.trace:
+                prof.export_chrome_trace(a.trace)     # timeline for scripts/trace_gaps.py
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -38,6 +38,7 @@ DECL int b200_selscan_fwd(const void*, const void*, const float*, const void*, c
 DECL int b200_selscan_bwd(const void*, const void*, const void*, const float*, const void*, const void*, const float*,
                           const void*, const float*, float*, void*, void*, void*, float*, float*, float*, float*, float*, int,
                           int, int, int, int, cudaStream_t);
+DECL void b200_comm_set_reduce_ctas(int);
 DECL int b200_p2p_gather_range(const void* const*, void*, long long, long long, long long, cudaStream_t);
 DECL int b200_ts_mma_probe(const void*, const void*, float*, cudaStream_t);
 DECL int b200_rmsnorm_fwd(const void*, const void*, void*, float*, int, int, float, cudaStream_t);
@@ -707,6 +708,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("signal_barrier", &signal_barrier);
   m.def("causal_conv1d_fwd", &causal_conv1d_fwd);
   m.def("causal_conv1d_bwd", &causal_conv1d_bwd);
+  m.def("set_reduce_ctas", [](int64_t n) { b200_comm_set_reduce_ctas((int)n); });
   m.def("ssd_scan_fwd", &ssd_scan_fwd);
   m.def("selective_scan_fwd", &selective_scan_fwd);
   m.def("selective_scan_bwd", &selective_scan_bwd);

@@ -245,6 +245,13 @@ extern "C" int b200_p2p_gather_range(const void* const* shard_ptrs, void* full, 
   return (int)cudaGetLastError();
 }
 
+// Upper bound on the CTAs of the overlapped reduce kernels.  They run on a side stream UNDER the backward GEMMs (which
+// also carry the next unit's all-gather in their comm warps): a full-chip burst steals SM issue slots and NVLink
+// ingress exactly when those comm warps need it (measured at 8 GPUs: ag-GEMMs 760 -> 1080 us).  A unit's reduce only
+// has to finish within one block's backward (~5 ms), so a few dozen CTAs are enough.
+static int g_reduce_max_ctas = 148 * 2;
+extern "C" void b200_comm_set_reduce_ctas(int n) { g_reduce_max_ctas = n < 1 ? 1 : n; }
+
 #define RS_CASE(BF, WW) \
   case WW: reduce_scatter_kernel<BF, WW><<<grid, 256, 0, s>>>(srcs, out, (size_t)n, (size_t)off, rank, scale, sumsq); break;
 
@@ -254,7 +261,7 @@ extern "C" int b200_reduce_scatter(const void* const* srcs, float* out, long lon
   if (n % vec || off % vec) return -1;
   long long nvec = n / vec;
   int grid = (int)((nvec + 255) / 256);
-  if (grid > 148 * 2) grid = 148 * 2;
+  if (grid > g_reduce_max_ctas) grid = g_reduce_max_ctas;
   if (grid < 1) grid = 1;
   if (src_bf16) {
     switch (world) { RS_CASE(true, 1) RS_CASE(true, 2) RS_CASE(true, 4) RS_CASE(true, 8) default: return -2; }

@@ -92,9 +92,10 @@ def _try_fused_gather(a, b, layout, out, epi, residual) -> bool:
         return False
     begin, end = req["begin"], req["end"]
     hi = end
-    if AG_SPLIT > 0 and not req["dependent"]:
+    split = req.get("split", AG_SPLIT)
+    if split > 0 and not req["dependent"]:
         w = out if layout == "tn" else b                       # the weight-shaped operand of this GEMM
-        take = int(w.numel() * w.element_size() * AG_SPLIT)
+        take = int(w.numel() * w.element_size() * split)
         take = max(_AG_CHUNK, (take + _AG_CHUNK - 1) // _AG_CHUNK * _AG_CHUNK)
         hi = min(end, begin + take)
     _C.gemm_ag(a, b, out, _LAYOUT[layout], epi, residual, req["table"], req["full"], req["shard_bytes"], begin,

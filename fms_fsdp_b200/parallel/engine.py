@@ -22,6 +22,8 @@ Collectives are pluggable (``comm.py``): c10d baseline or fused NVLink peer kern
 """
 from __future__ import annotations
 
+import os
+
 import contextlib
 from typing import Dict, Iterable, List, Optional, Sequence, Tuple
 
@@ -157,6 +159,12 @@ class ShardedModel(nn.Module):
         # pools
         self._full_pool: Dict[Tuple, List[_Buf]] = {}
         self._grad_pool: Dict[Tuple, List[_Buf]] = {}
+        self._pool_made: Dict[Tuple, int] = {}
+        self._bwd_gather_split = float(os.environ.get("FMS_B200_AG_SPLIT_BWD", "1.0"))
+        # backward knobs (measured in profiles/README.md): gradient-buffer pool depth (1 = the block's backward waits for
+        # the previous unit's reduce, 2 = they overlap) and whether backward re-gathers ride inside the GEMMs
+        self._grad_pool_depth = int(os.environ.get("FMS_B200_GRAD_POOL", "1"))
+        self._fuse_gather_bwd = os.environ.get("FMS_B200_FUSED_GATHER_BWD", "1") != "0"
         self._gnorm_sq = torch.zeros((), dtype=torch.float32, device=self.device)
         self._clip_coef: Optional[torch.Tensor] = None
         self._saved = None
@@ -245,20 +253,27 @@ class ShardedModel(nn.Module):
         return u
 
     # --------------------------------------------------------------------------------- buffers
-    def _acquire(self, pool, unit: ShardUnit, dtype, symmetric: bool) -> _Buf:
+    def _acquire(self, pool, unit: ShardUnit, dtype, symmetric: bool, min_depth: int = 1) -> _Buf:
+        """Oldest pooled buffer of this shape once ``min_depth`` buffers exist.  Gradient buffers need depth 2: a unit's buffer goes back to the pool the moment its
+        reduce-scatter is ENQUEUED, so the next block would otherwise pick the same buffer and stall the compute
+        stream for the whole reduce (measured: 0.58 ms idle per block at 2 GPUs, ~1.1 ms at 8)."""
         key = (unit.layout.signature(), dtype)
         lst = pool.setdefault(key, [])
-        if lst:
+        made = self._pool_made.setdefault((id(pool), key), 0)
+        # (the decision must not depend on timing: symmetric-heap allocations are collective across ranks)
+        if lst and made >= min_depth:
             return lst.pop(0)
         # gradient buffers are read by peers (symmetric heap); gathered parameters are local
         t = self.coll.alloc_full(unit.layout.total, dtype, symmetric=symmetric)
+        self._pool_made[(id(pool), key)] = made + 1
         return _Buf(t, self._event())
 
     def _give_back(self, pool, unit: ShardUnit, buf: _Buf, dtype):
         pool.setdefault((unit.layout.signature(), dtype), []).append(buf)
 
     # ---------------------------------------------------------------------------------- gather
-    def _start_gather(self, u: ShardUnit, dependent: bool = False, fuse: Optional[bool] = None):
+    def _start_gather(self, u: ShardUnit, dependent: bool = False, fuse: Optional[bool] = None,
+                      split: Optional[float] = None):
         if self.mesh.shard_size == 1 or u.full is not None:
             return
         buf = self._acquire(self._full_pool, u, self.mp.param_dtype, False)
@@ -274,6 +289,8 @@ class ShardedModel(nn.Module):
             u.ag_req = None
             if total > mb:
                 u.ag_req = self.coll.ag_request(u.lowp, buf.t, mb, total, dependent)
+                if split is not None:
+                    u.ag_req["split"] = split
                 CK.push_ag_request(u.ag_req)
             u.full = buf
             u.gather_pending = True
@@ -320,7 +337,7 @@ class ShardedModel(nn.Module):
     # ------------------------------------------------------------------------------- gradients
     def _prepare_grads(self, u: ShardUnit):
         if u.full_grad is None:
-            buf = self._acquire(self._grad_pool, u, self.mp.reduce_dtype, True)
+            buf = self._acquire(self._grad_pool, u, self.mp.reduce_dtype, True, min_depth=self._grad_pool_depth)
             u.full_grad = buf
         if self.is_cuda:
             self.s_compute.wait_event(u.full_grad.free_event)
@@ -427,7 +444,7 @@ class ShardedModel(nn.Module):
         if sv is None:
             raise RuntimeError("backward without a recorded forward")
         self._saved = None
-        fuse = self._fuse_gather
+        fuse = self._fuse_gather and self._fuse_gather_bwd
         depth = 1 if fuse else self.prefetch_depth
         n = len(blocks)
         # re-gather ahead (the last block is still resident from forward)
@@ -448,7 +465,8 @@ class ShardedModel(nn.Module):
             self._wait_gather(u)
             nxt = i - depth
             if nxt >= 0:
-                self._start_gather(blocks[nxt], fuse=fuse)   # fused: rides inside block i's backward GEMMs
+                # fused: rides inside block i's backward GEMMs (FMS_B200_AG_SPLIT_BWD < 1 spreads it over more of them)
+                self._start_gather(blocks[nxt], fuse=fuse, split=self._bwd_gather_split)
             x_in, y = sv["blocks"][i]
             self._prepare_grads(u)
             if y is None:  # selective recompute with the weights that are resident for backward anyway
