@@ -1215,7 +1215,7 @@ template <int HD, int MODE>
 __global__ void __launch_bounds__(ATT2_THREADS, 1)
 attn_bwd3_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do,
                  const float* __restrict__ lse2g, const float* __restrict__ delta, __nv_bfloat16* __restrict__ dqkv,
-                 int S, int H, int KVH, float scale, int n_t128, int ld) {
+                 int S, int H, int KVH, float scale, int n_t128, int ld, const float* __restrict__ rope) {
   using C = Bwd3Cfg<HD>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -1475,8 +1475,11 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_consta
     if (x_idx < S && n_iter > 0) {
       const size_t row = (size_t)b * S + x_idx;
       const int Wd = (H + 2 * KVH) * HD;
-      auto store_acc = [&](uint32_t tacc, int col0, int c_lo, int c_hi, float mul) {
+      // rot: apply the INVERSE rotary embedding of this row's position (the forward RoPE lives in the QKV GEMM epilogue,
+      // so what leaves here is the gradient of the un-rotated projection); table [S][HD/2][cos, sin]
+      auto store_acc = [&](uint32_t tacc, int col0, int c_lo, int c_hi, float mul, bool rot) {
         __nv_bfloat16* dst = dqkv + row * Wd + col0;
+        const float* trow = rope + (size_t)x_idx * HD;
 #pragma unroll 1
         for (int c = c_lo; c < c_hi; c += 32) {
           uint32_t v[32];
@@ -1484,21 +1487,34 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_consta
           tmem_ld_wait();
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
+            float f[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(v[q * 8 + i]) * mul;
+            if (rot) {
+              const float4* tp = reinterpret_cast<const float4*>(trow + c + q * 8);
+              const float4 t0 = tp[0], t1 = tp[1];
+              const float cs[4] = {t0.x, t0.z, t1.x, t1.z}, sn[4] = {t0.y, t0.w, t1.y, t1.w};
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float a0 = f[2 * i], a1 = f[2 * i + 1];
+                f[2 * i] = a0 * cs[i] + a1 * sn[i];
+                f[2 * i + 1] = a1 * cs[i] - a0 * sn[i];
+              }
+            }
             uint4 u;
-            u.x = pack_bf16x2(__uint_as_float(v[q * 8 + 0]) * mul, __uint_as_float(v[q * 8 + 1]) * mul);
-            u.y = pack_bf16x2(__uint_as_float(v[q * 8 + 2]) * mul, __uint_as_float(v[q * 8 + 3]) * mul);
-            u.z = pack_bf16x2(__uint_as_float(v[q * 8 + 4]) * mul, __uint_as_float(v[q * 8 + 5]) * mul);
-            u.w = pack_bf16x2(__uint_as_float(v[q * 8 + 6]) * mul, __uint_as_float(v[q * 8 + 7]) * mul);
+            u.x = pack_bf16x2(f[0], f[1]); u.y = pack_bf16x2(f[2], f[3]);
+            u.z = pack_bf16x2(f[4], f[5]); u.w = pack_bf16x2(f[6], f[7]);
             *reinterpret_cast<uint4*>(dst + c + q * 8) = u;
           }
         }
       };
+      const bool rot = rope != nullptr;
       if constexpr (MODE == MODE_DKDV) {
-        if (g == 0) store_acc(tmem_acc2, (H + kvh) * HD, 0, HD, scale);
-        else        store_acc(tmem_acc1, (H + KVH + kvh) * HD, 0, HD, 1.f);
+        if (g == 0) store_acc(tmem_acc2, (H + kvh) * HD, 0, HD, scale, rot);
+        else        store_acc(tmem_acc1, (H + KVH + kvh) * HD, 0, HD, 1.f, false);
       } else {
-        if (g == 0) store_acc(tmem_acc2, head_lo * HD, 0, HD / 2, scale);
-        else        store_acc(tmem_acc2, head_lo * HD, HD / 2, HD, scale);
+        if (g == 0) store_acc(tmem_acc2, head_lo * HD, 0, HD / 2, scale, rot);
+        else        store_acc(tmem_acc2, head_lo * HD, HD / 2, HD, scale, rot);
       }
     }
   }
@@ -1553,7 +1569,7 @@ static int launch_fwd(const void* qkv, void* o, float* lse, int B, int S, int H,
 
 template <int HD>
 static int launch_bwd(const void* dout, const void* qkv, const void* o, const float* lse, void* dqkv, float* delta,
-                      int B, int S, int H, int KVH, float scale, cudaStream_t st) {
+                      int B, int S, int H, int KVH, float scale, const float* rope, cudaStream_t st) {
   using C = BwdCfg<HD>;
   const int W = (H + 2 * KVH) * HD;
   CUtensorMap q128, q64, d128, d64;
@@ -1587,11 +1603,12 @@ static int launch_bwd(const void* dout, const void* qkv, const void* o, const fl
     const int ld3 = ((S + 127) / 128) * 128;
     const float* lse2p = delta + (size_t)B * H * ld3;
     j1<<<dim3(n_t, KVH, B), ATT2_THREADS, C3::SMEM, st>>>(q128, d128, lse2p, delta, (__nv_bfloat16*)dqkv, S, H, KVH, scale,
-                                                         n_t, ld3);
+                                                         n_t, ld3, rope);
     j2<<<dim3(n_t, H, B), ATT2_THREADS, C3::SMEM, st>>>(q128, d128, lse2p, delta, (__nv_bfloat16*)dqkv, S, H, KVH, scale,
-                                                       n_t, ld3);
+                                                       n_t, ld3, rope);
     return (int)cudaGetLastError();
   }
+  if (rope) return -9;   // only the v3 kernels fuse the inverse RoPE
   if (g_attn_bwd_version == 2) {
     using C2 = Bwd2Cfg<HD>;
     auto j1 = attn_bwd2_kernel<HD, MODE_DKDV>;
@@ -1640,10 +1657,12 @@ extern "C" int b200_attn_fwd(const void* qkv, void* o, float* lse, int B, int S,
   if (HD == 64) return b200::launch_fwd<64>(qkv, o, lse, B, S, H, KVH, scale, st);
   return -2;
 }
+// rope (optional): [S][HD/2][cos, sin] table; dq and dk leave the kernel with the inverse rotation applied
 extern "C" int b200_attn_bwd(const void* dout, const void* qkv, const void* o, const float* lse, void* dqkv,
-                             float* delta, int B, int S, int H, int KVH, int HD, float scale, cudaStream_t st) {
+                             float* delta, int B, int S, int H, int KVH, int HD, float scale, const float* rope,
+                             cudaStream_t st) {
   if (H % KVH) return -1;
-  if (HD == 128) return b200::launch_bwd<128>(dout, qkv, o, lse, dqkv, delta, B, S, H, KVH, scale, st);
-  if (HD == 64) return b200::launch_bwd<64>(dout, qkv, o, lse, dqkv, delta, B, S, H, KVH, scale, st);
+  if (HD == 128) return b200::launch_bwd<128>(dout, qkv, o, lse, dqkv, delta, B, S, H, KVH, scale, rope, st);
+  if (HD == 64) return b200::launch_bwd<64>(dout, qkv, o, lse, dqkv, delta, B, S, H, KVH, scale, rope, st);
   return -2;
 }

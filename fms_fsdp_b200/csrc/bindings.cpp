@@ -63,7 +63,8 @@ DECL void b200_attn_set_fwd_version(int);
 DECL void b200_attn_set_bwd_version(int);
 DECL int b200_attn_fwd(const void*, void*, float*, int, int, int, int, int, float, cudaStream_t);
 DECL int b200_attn_bwd(const void*, const void*, const void*, const float*, void*, float*, int, int, int, int, int,
-                       float, cudaStream_t);
+                       float, const float*, cudaStream_t);
+DECL void b200_gemm2_set_rope(const float*, int, int, int);
 DECL int b200_p2p_allgather(const void* const*, void*, long long, int, int, cudaStream_t);
 DECL int b200_reduce_scatter(const void* const*, float*, long long, long long, int, int, int, float, float*,
                              cudaStream_t);
@@ -127,6 +128,8 @@ void gemm(const at::Tensor& a, const at::Tensor& b, at::Tensor& c, int64_t layou
     r = residual->data_ptr();
     ldr = residual->stride(0);
   }
+  TORCH_CHECK(epi != 3 || (g_gemm_2cta && M >= 256 && layout == 0 && c.scalar_type() == at::kBFloat16),
+              "RoPE epilogue: CTA-pair kernel, nt layout, bf16 output only (call set_gemm_rope first)");
   // CTA-pair kernel (cta_group::2, 256x256 tiles) for anything with at least one full pair tile of rows
   if (g_gemm_2cta && M >= 256) {
     check(b200_gemm2_bf16(a.data_ptr(), b.data_ptr(), c.data_ptr(), r, M, N, K, a.stride(0), b.stride(0), c.stride(0),
@@ -344,7 +347,8 @@ std::vector<at::Tensor> attn_fwd(const at::Tensor& qkv, int64_t B, int64_t S, in
   return {o, lse};
 }
 at::Tensor attn_bwd(const at::Tensor& dout, const at::Tensor& qkv, const at::Tensor& o, const at::Tensor& lse,
-                    int64_t B, int64_t S, int64_t H, int64_t KVH, int64_t hd, double scale) {
+                    int64_t B, int64_t S, int64_t H, int64_t KVH, int64_t hd, double scale,
+                    const c10::optional<at::Tensor>& rope) {
   c10::cuda::CUDAGuard guard(qkv.device());
   need(qkv, "qkv", at::kBFloat16);
   need(dout, "do", at::kBFloat16);
@@ -354,8 +358,14 @@ at::Tensor attn_bwd(const at::Tensor& dout, const at::Tensor& qkv, const at::Ten
   auto dqkv = at::empty_like(qkv);
   // [2 planes: delta | lse*log2e][B][H][S padded to 128]
   auto delta = at::empty({2, B, H, ((S + 127) / 128) * 128}, qkv.options().dtype(at::kFloat));
+  const float* rope_p = nullptr;
+  if (rope.has_value() && rope->defined()) {   // inverse RoPE of dq, dk fused into the epilogue
+    need(*rope, "rope", at::kFloat);
+    TORCH_CHECK(rope->is_contiguous() && rope->numel() >= S * hd, "attn_bwd: rope table must be [S, hd/2, 2] fp32");
+    rope_p = rope->data_ptr<float>();
+  }
   check(b200_attn_bwd(dout.data_ptr(), qkv.data_ptr(), o.data_ptr(), lse.data_ptr<float>(), dqkv.data_ptr(),
-                      delta.data_ptr<float>(), B, S, H, KVH, hd, (float)scale, cur_stream()), "attn_bwd", 3);
+                      delta.data_ptr<float>(), B, S, H, KVH, hd, (float)scale, rope_p, cur_stream()), "attn_bwd", 3);
   return dqkv;
 }
 
@@ -701,7 +711,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("adamw", &adamw);
   m.def("sumsq", &sumsq);
   m.def("attn_fwd", &attn_fwd);
-  m.def("attn_bwd", &attn_bwd);
+  m.def("attn_bwd", &attn_bwd, py::arg("dout"), py::arg("qkv"), py::arg("o"), py::arg("lse"), py::arg("B"), py::arg("S"),
+        py::arg("H"), py::arg("KVH"), py::arg("hd"), py::arg("scale"), py::arg("rope") = py::none());
   m.def("p2p_allgather", &p2p_allgather);
   m.def("reduce_scatter", &reduce_scatter);
   m.def("allreduce_inplace", &allreduce_inplace);
@@ -709,6 +720,11 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("causal_conv1d_fwd", &causal_conv1d_fwd);
   m.def("causal_conv1d_bwd", &causal_conv1d_bwd);
   m.def("set_reduce_ctas", [](int64_t n) { b200_comm_set_reduce_ctas((int)n); });
+  m.def("set_gemm_rope", [](const at::Tensor& table, int64_t S, int64_t hd, int64_t cols) {
+    need(table, "rope table", at::kFloat);
+    TORCH_CHECK(table.is_contiguous() && table.numel() >= S * hd, "rope table must be [S, hd/2, 2] fp32");
+    b200_gemm2_set_rope(table.data_ptr<float>(), (int)S, (int)hd, (int)cols);
+  });
   m.def("ssd_scan_fwd", &ssd_scan_fwd);
   m.def("selective_scan_fwd", &selective_scan_fwd);
   m.def("selective_scan_bwd", &selective_scan_bwd);

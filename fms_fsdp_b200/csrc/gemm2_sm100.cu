@@ -26,7 +26,7 @@ constexpr int P_STAGE_BYTES = PA_BYTES + PB_BYTES;
 constexpr int P_THREADS = 192;
 constexpr int P_SMEM = P_STAGES * P_STAGE_BYTES + 1024 + 256;
 
-enum { P_EPI_STORE = 0, P_EPI_RESIDUAL = 1, P_EPI_ACCUM = 2 };
+enum { P_EPI_STORE = 0, P_EPI_RESIDUAL = 1, P_EPI_ACCUM = 2, P_EPI_ROPE = 3 };
 
 
 // L2-friendly rasterisation: sweep all n-tiles for a band of GROUP_M m-tiles before moving to the next band, so the
@@ -103,6 +103,10 @@ struct Gemm2Params {
   void* C;
   const void* R;
   int m_tiles, n_tiles;  // in units of 256 x 256
+  // P_EPI_ROPE (QKV projection): rotate adjacent column pairs of the first rope_cols columns by the angle of
+  // (row % rope_S, (col % rope_hd) / 2) before the bf16 store; table is [S][hd/2][cos, sin] fp32
+  const float* rope;
+  int rope_S, rope_hd, rope_cols;
 };
 
 template <bool A_MN, bool B_MN, int EPI, typename OutT, bool AG>
@@ -304,7 +308,21 @@ gemm2_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                 float f[8];
 #pragma unroll
                 for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(v[g * 8 + i]);
-                if constexpr (EPI != P_EPI_STORE) {
+                if constexpr (EPI == P_EPI_ROPE) {
+                  const int c8 = cb + g * 8;
+                  if (c8 < p.rope_cols) {
+                    const float4* tp = reinterpret_cast<const float4*>(
+                        p.rope + ((size_t)(row % p.rope_S) * (p.rope_hd >> 1) + ((c8 % p.rope_hd) >> 1)) * 2);
+                    const float4 t0 = tp[0], t1 = tp[1];
+                    const float cs[4] = {t0.x, t0.z, t1.x, t1.z}, sn[4] = {t0.y, t0.w, t1.y, t1.w};
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                      const float a0 = f[2 * i], a1 = f[2 * i + 1];
+                      f[2 * i] = a0 * cs[i] - a1 * sn[i];
+                      f[2 * i + 1] = a0 * sn[i] + a1 * cs[i];
+                    }
+                  }
+                } else if constexpr (EPI != P_EPI_STORE) {
                   const __nv_bfloat16* src = (EPI == P_EPI_RESIDUAL) ? (rrow + cb + g * 8)
                                                                      : (reinterpret_cast<const __nv_bfloat16*>(crow) + cb + g * 8);
                   uint4 r = *reinterpret_cast<const uint4*>(src);
@@ -398,7 +416,16 @@ static int dispatch2(const CUtensorMap& a, const CUtensorMap& b, const Gemm2Para
   return launch2<A_MN, B_MN, P_EPI_ACCUM, __nv_bfloat16>(a, b, p, s);
 }
 
+// RoPE epilogue parameters of the NEXT epi == P_EPI_ROPE launch (set immediately before it by the single host thread
+// that owns the stream; keeps the two launcher signatures unchanged)
+static const float* g_rope_table = nullptr;
+static int g_rope_S = 1, g_rope_hd = 2, g_rope_cols = 0;
+
 }  // namespace b200
+
+extern "C" void b200_gemm2_set_rope(const float* table, int S, int hd, int cols) {
+  b200::g_rope_table = table; b200::g_rope_S = S; b200::g_rope_hd = hd; b200::g_rope_cols = cols;
+}
 
 extern "C" int b200_gemm2_bf16(const void* A, const void* B, void* C, const void* R, int M, int N, int K, int lda,
                                int ldb, int ldc, int ldr, int a_mn, int b_mn, int epi, int out_fp32,
@@ -416,6 +443,11 @@ extern "C" int b200_gemm2_bf16(const void* A, const void* B, void* C, const void
   p.M = M; p.N = N; p.K = K; p.ldc = ldc; p.ldr = ldr; p.C = C; p.R = R;
   p.m_tiles = (M + P_BM - 1) / P_BM;
   p.n_tiles = (N + P_BN - 1) / P_BN;
+  p.rope = g_rope_table; p.rope_S = g_rope_S; p.rope_hd = g_rope_hd; p.rope_cols = g_rope_cols;
+  if (epi == P_EPI_ROPE) {
+    if (a_mn || b_mn || out_fp32 || !p.rope || (p.rope_hd % 8) || (p.rope_cols % 8)) return -8;
+    return launch2<false, false, P_EPI_ROPE, __nv_bfloat16>(tmA, tmB, p, stream);
+  }
   if (a_mn) {
     if (b_mn) return dispatch2<true, true>(tmA, tmB, p, epi, out_fp32, stream);
     return dispatch2<true, false>(tmA, tmB, p, epi, out_fp32, stream);
@@ -445,6 +477,7 @@ extern "C" int b200_gemm2_ag_bf16(const void* A, const void* B, void* C, const v
   p.M = M; p.N = N; p.K = K; p.ldc = ldc; p.ldr = ldr; p.C = C; p.R = R;
   p.m_tiles = (M + P_BM - 1) / P_BM;
   p.n_tiles = (N + P_BN - 1) / P_BN;
+  p.rope = g_rope_table; p.rope_S = g_rope_S; p.rope_hd = g_rope_hd; p.rope_cols = g_rope_cols;
   AgParams ag;
   ag.peer_shards = peer_shards; ag.full = (uint8_t*)full; ag.shard_bytes = shard_bytes; ag.begin = begin; ag.end = end;
   ag.world = world; ag.rank = rank; ag.flags = flags; ag.epoch = epoch; ag.dependent = dependent;
@@ -452,6 +485,10 @@ extern "C" int b200_gemm2_ag_bf16(const void* A, const void* B, void* C, const v
   ag.b_row_bytes = (unsigned long long)ldb * 2;
   if (dependent && ((const uint8_t*)B < (const uint8_t*)full)) return -6;
 #define AGL(AM, BM_, E) return launch2_ag<AM, BM_, E, __nv_bfloat16>(tmA, tmB, p, ag, stream)
+  if (epi == P_EPI_ROPE) {
+    if (a_mn || b_mn || !p.rope || (p.rope_hd % 8) || (p.rope_cols % 8)) return -8;
+    AGL(false, false, P_EPI_ROPE);
+  }
   if (!a_mn && !b_mn) { if (epi == P_EPI_RESIDUAL) AGL(false, false, P_EPI_RESIDUAL); AGL(false, false, P_EPI_STORE); }
   if (!a_mn && b_mn)  { if (epi == P_EPI_RESIDUAL) AGL(false, true, P_EPI_RESIDUAL);  AGL(false, true, P_EPI_STORE); }
   if (a_mn && b_mn)   { if (epi == P_EPI_ACCUM) AGL(true, true, P_EPI_ACCUM);        AGL(true, true, P_EPI_STORE); }

@@ -196,9 +196,9 @@ class LLaMABlock(nn.Module):
         a, cfg = self.attn, self.config
         B, S, _ = x.shape
         h, x = self.ln.fork(x)
-        qkv = a.in_proj.qkv_fused(h)
-        qkv = ops.rope_(qkv, self._rot.table(x.device, S), S, a.nheads, a.kvheads, a.head_dim)
-        ctx = ops.attention(qkv, a.nheads, a.kvheads, a.head_dim)
+        # projection + RoPE + attention: one node, RoPE fused into the GEMM / dq-dk epilogues
+        ctx = ops.qkv_attention(h, a.in_proj.qkv_fused.weight, self._rot.table(x.device, S), a.nheads, a.kvheads,
+                                a.head_dim)
         x = a.dense(ctx, residual=x)
         h, x = self.ff_ln.fork(x)
         gu = self.ff_sub_layer.wg1_fused(h)

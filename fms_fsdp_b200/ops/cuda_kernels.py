@@ -22,7 +22,8 @@ _LAYOUT = {"nt": 0, "nn": 1, "tn": 2}
 ATTN_IMPL = os.environ.get("FMS_B200_ATTN_IMPL", "tcgen05")
 GEMM_IMPL = os.environ.get("FMS_B200_GEMM_IMPL", "tcgen05")  # "cublas" = library fallback, debugging only
 _C.set_attn_fwd_version(int(os.environ.get("FMS_B200_ATTN_FWD", "2")))  # 2 = two Q tiles/CTA, P in TMEM
-_C.set_attn_bwd_version(int(os.environ.get("FMS_B200_ATTN_BWD", "3")))  # 3 = 128-row streamed tiles, two-phase row owners (2 = 64-row tiles)
+_ATTN_BWD_VERSION = int(os.environ.get("FMS_B200_ATTN_BWD", "3"))
+_C.set_attn_bwd_version(_ATTN_BWD_VERSION)  # 3 = 128-row streamed tiles, two-phase row owners (2 = 64-row tiles)
 _C.set_gemm_2cta(os.environ.get("FMS_B200_GEMM_2CTA", "1") == "1")  # CTA-pair (cta_group::2) GEMM for M >= 256
 
 
@@ -81,7 +82,8 @@ def _try_fused_gather(a, b, layout, out, epi, residual) -> bool:
     req = _AG_QUEUE[0]
     M = a.shape[1] if layout == "tn" else a.shape[0]
     ok = (M >= 256 and out.dtype == torch.bfloat16 and _C.get_gemm_2cta()
-          and ((layout in ("nt", "nn") and epi in (0, 1)) or (layout == "tn" and epi in (0, 2))))
+          and ((layout in ("nt", "nn") and epi in (0, 1)) or (layout == "tn" and epi in (0, 2))
+               or (layout == "nt" and epi == 3)))
     if ok and req["dependent"]:
         lo = req["full"].data_ptr() + req["begin"]
         ok = lo <= b.data_ptr() < req["full"].data_ptr() + req["end"]
@@ -111,7 +113,19 @@ def _try_fused_gather(a, b, layout, out, epi, residual) -> bool:
 
 
 # ------------------------------------------------------------------------------------------ GEMM
-def gemm(a, b, layout="nt", out=None, accumulate=False, residual=None, out_dtype=None):
+def gemm(a, b, layout="nt", out=None, accumulate=False, residual=None, out_dtype=None, rope=None):
+    """``rope=(table [S, hd/2, 2] fp32, S, hd, H, KVH)``: rotary embedding of the q and k heads (the first
+    ``(H + KVH) * hd`` output columns) fused into the GEMM epilogue (QKV projection; nt layout)."""
+    if rope is not None:
+        M0 = a.shape[0]
+        ok = (GEMM_IMPL == "tcgen05" and layout == "nt" and a.dtype == b.dtype == torch.bfloat16 and residual is None
+              and not accumulate and M0 >= 256 and M0 % 8 == 0 and _C.get_gemm_2cta() and rope[2] % 8 == 0
+              and a.shape[1] % 8 == 0 and b.shape[0] % 8 == 0 and out_dtype in (None, torch.bfloat16)
+              and (out is None or out.dtype == torch.bfloat16))
+        if not ok:   # unfused: GEMM, then the in-place RoPE kernel
+            y = gemm(a, b, layout, out=out, accumulate=accumulate, residual=residual, out_dtype=out_dtype)
+            table, S, hd, H, KVH = rope
+            return rope_(y, table, S, H, KVH, hd)
     if GEMM_IMPL != "tcgen05" or a.dtype != torch.bfloat16 or b.dtype != torch.bfloat16:
         return torch_kernels.gemm(a, b, layout, out=out, accumulate=accumulate, residual=residual, out_dtype=out_dtype)
     if layout == "nt":
@@ -136,6 +150,9 @@ def gemm(a, b, layout="nt", out=None, accumulate=False, residual=None, out_dtype
         epi = 1
     elif accumulate:
         epi = 2
+    if rope is not None:
+        epi = 3
+        _C.set_gemm_rope(rope[0], int(rope[1]), int(rope[2]), int((rope[3] + rope[4]) * rope[2]))   # for the launch below
     if _AG_QUEUE and _try_fused_gather(a, b, layout, out, epi, residual):
         return out
     _C.gemm(a, b, out, _LAYOUT[layout], epi, residual)
@@ -217,9 +234,19 @@ def attn_fwd(qkv, B, S, H, KVH, hd, scale, causal=True):
     return torch_kernels.attn_fwd(qkv, B, S, H, KVH, hd, scale, causal)
 
 
-def attn_bwd(do, qkv, o, lse, B, S, H, KVH, hd, scale, causal=True):
+def attn_bwd(do, qkv, o, lse, B, S, H, KVH, hd, scale, causal=True, rope_table=None):
+    """``rope_table``: the forward applied RoPE (full head_dim, interleaved) to q, k before this attention; return the
+    gradient of the UN-rotated projection (inverse rotation fused into the dq / dk epilogues)."""
     if ATTN_IMPL == "tcgen05" and qkv.dtype == torch.bfloat16 and hd in (64, 128) and causal:
-        return _C.attn_bwd(do.contiguous(), qkv.contiguous(), o, lse, B, S, H, KVH, hd, float(scale))
+        fused = rope_table is not None and _ATTN_BWD_VERSION == 3
+        g = _C.attn_bwd(do.contiguous(), qkv.contiguous(), o, lse, B, S, H, KVH, hd, float(scale),
+                        rope_table if fused else None)
+        if rope_table is not None and not fused:
+            rope_(g, rope_table, S, H, KVH, hd, inverse=True)
+        return g
+    if rope_table is not None:
+        g = attn_bwd(do, qkv, o, lse, B, S, H, KVH, hd, scale, causal)
+        return rope_(g, rope_table, S, H, KVH, hd, inverse=True)
     if ATTN_IMPL == "sdpa":
         with torch.enable_grad():
             leaf = qkv.detach().requires_grad_(True)

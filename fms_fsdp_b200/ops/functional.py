@@ -241,6 +241,44 @@ class _Attention(torch.autograd.Function):
         return dqkv.view_as(qkv), None, None, None, None, None, None
 
 
+class _QKVAttention(torch.autograd.Function):
+    """QKV projection + RoPE + causal attention as ONE autograd node: the rotary embedding is the epilogue of the
+    projection GEMM in forward and of the dq / dk kernels in backward, so no standalone RoPE pass touches HBM
+    (reference path: fms MultiHeadAttention.in_proj -> RotaryEmbedding.adjusted_qk -> SDPA)."""
+
+    @staticmethod
+    def forward(ctx, h, w, table, S, H, KVH, hd, scale):
+        K = kernels_for(h)
+        B = h.shape[0]
+        h2 = h.reshape(-1, h.shape[-1])
+        qkv = K.gemm(h2, _wdata(w), "nt", rope=(table, S, hd, H, KVH))
+        o, lse = K.attn_fwd(qkv, B, S, H, KVH, hd, scale)
+        ctx.K, ctx.w, ctx.args = K, w, (B, S, H, KVH, hd, scale)
+        ctx.save_for_backward(h, qkv, o, lse, table)
+        return o.view(B, S, H * hd)
+
+    @staticmethod
+    def backward(ctx, do):
+        h, qkv, o, lse, table = ctx.saved_tensors
+        B, S, H, KVH, hd, scale = ctx.args
+        K, w = ctx.K, ctx.w
+        dqkv = K.attn_bwd(do.reshape(B * S, H * hd).contiguous(), qkv, o, lse, B, S, H, KVH, hd, scale,
+                          rope_table=table)
+        h2 = h.reshape(-1, h.shape[-1])
+        dh = K.gemm(dqkv, _wdata(w), "nn").view_as(h) if ctx.needs_input_grad[0] else None
+        dw = None
+        if ctx.needs_input_grad[1]:
+            dw = _deliver_wgrad(w, lambda out, acc: K.gemm(dqkv, h2, "tn", out=out, accumulate=acc))
+        return dh, dw, None, None, None, None, None, None
+
+
+def qkv_attention(h, w, table, nheads, kvheads, head_dim, scale=None):
+    """attention(rope(h @ w^T)) for a fused [(H + 2 KVH) * hd, D] projection weight; h: [B, S, D]."""
+    S = h.shape[1]
+    scale = (head_dim ** -0.5) if scale is None else scale
+    return _QKVAttention.apply(h, w, table, S, nheads, kvheads, head_dim, scale)
+
+
 def attention(qkv, nheads, kvheads, head_dim, scale=None):
     """Causal GQA flash attention on a fused (roped) projection [B, S, (H+2KVH)*hd] -> [B, S, H*hd]."""
     B, S, _ = qkv.shape

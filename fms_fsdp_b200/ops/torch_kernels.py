@@ -20,7 +20,11 @@ NAME = "torch"
 # GEMM family.  layout: "nt": C[M,N] = A[M,K] B[N,K]^T ; "nn": C[M,N] = A[M,K] B[K,N] ;
 #                        "tn": C[M,N] = A[K,M]^T B[K,N].  fp32 accumulate, output dtype of `out`/a.
 # ----------------------------------------------------------------------------------------------
-def gemm(a, b, layout="nt", out=None, accumulate=False, residual=None, out_dtype=None):
+def gemm(a, b, layout="nt", out=None, accumulate=False, residual=None, out_dtype=None, rope=None):
+    if rope is not None:   # (table, S, head_dim, H, KVH): RoPE on the q and k heads of a fused QKV product
+        y = gemm(a, b, layout, out=out, accumulate=accumulate, residual=residual, out_dtype=out_dtype)
+        table, S, hd, H, KVH = rope
+        return rope_(y, table, S, H, KVH, hd)
     if layout == "nt":
         c = a @ b.t()
     elif layout == "nn":
@@ -156,7 +160,10 @@ def attn_fwd(qkv, B, S, H, KVH, hd, scale, causal=True):
     return o, lse
 
 
-def attn_bwd(do, qkv, o, lse, B, S, H, KVH, hd, scale, causal=True):
+def attn_bwd(do, qkv, o, lse, B, S, H, KVH, hd, scale, causal=True, rope_table=None):
+    if rope_table is not None:   # gradient of the un-rotated projection
+        g = attn_bwd(do, qkv, o, lse, B, S, H, KVH, hd, scale, causal)
+        return rope_(g, rope_table, S, H, KVH, hd, inverse=True)
     q, k, v = _split_qkv(qkv, B, S, H, KVH, hd)
     qf, kf, vf = (t.permute(0, 2, 1, 3).float() for t in (q, k, v))
     rep = H // KVH

@@ -31,7 +31,7 @@ int main(int argc, char** argv) {
     cudaMemcpyToSymbol(b200::g_attn_trace, &tr, sizeof(tr));
     cudaMemcpyToSymbol(b200::g_attn_trace_cta, &cta, sizeof(int));
     cudaMemcpyToSymbol(b200::g_attn_trace_mode, &mode, sizeof(int));
-    rc = b200_attn_bwd(dout, qkv, o, lse, dqkv, delta, B, S, H, KVH, HD, 0.0884f, 0);
+    rc = b200_attn_bwd(dout, qkv, o, lse, dqkv, delta, B, S, H, KVH, HD, 0.0884f, nullptr, 0);
     cudaError_t e = cudaDeviceSynchronize();
     printf("bwd rc %d sync %s\n", rc, cudaGetErrorString(e));
   std::vector<long long> t(64 * 16);

@@ -254,3 +254,24 @@ def test_selective_scan_native_vs_sequential_oracle(K, use_z):
     names = ["du", "ddelta", "dA", "dB", "dC", "dD"] + (["dz"] if use_z else []) + ["dbias"]
     for name, a, b in zip(names, mine, g0):
         assert rel(a, b) < 3e-2, name
+
+
+def test_qkv_attention_rope_fused_in_gemm_and_bwd_epilogues(K):
+    """RoPE as the epilogue of the CTA-pair QKV GEMM (forward) and of the dq/dk kernels (backward) against the
+    unfused CUDA path (GEMM, in-place RoPE kernel, attention) and its autograd."""
+    from fms_fsdp_b200 import ops
+    CK, TK = K
+    torch.manual_seed(0)
+    B, S, D, H, KVH, hd = 2, 256, 512, 4, 2, 128
+    tab = TK.rope_table(S, hd, device=DEV)
+    h = (torch.randn(B, S, D, device=DEV) * 0.5).bfloat16().requires_grad_()
+    w = torch.nn.Parameter((torch.randn((H + 2 * KVH) * hd, D, device=DEV) * 0.05).bfloat16())
+    dy = torch.randn(B, S, H * hd, device=DEV).bfloat16()
+    y = ops.qkv_attention(h, w, tab, H, KVH, hd)
+    y.backward(dy)
+    h2 = h.detach().requires_grad_(); w2 = torch.nn.Parameter(w.detach().clone())
+    qkv = ops.rope_(ops.linear(h2, w2), tab, S, H, KVH, hd)
+    y2 = ops.attention(qkv, H, KVH, hd)
+    y2.backward(dy)
+    assert rel(y, y2) < 2e-2
+    assert rel(h.grad, h2.grad) < 3e-2 and rel(w.grad, w2.grad) < 3e-2

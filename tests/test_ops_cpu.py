@@ -136,3 +136,19 @@ def test_ssd_scan_matches_chunked_reference():
     CB = torch.einsum("tgn,sgn->ts", Cm, Bm)
     y2 = torch.einsum("ts,tsh,sh,shp->thp", CB, L, dt, x) + x * D[None, :, None]
     _close(y, y2, 1e-3)
+
+
+def test_qkv_attention_fused_node_matches_separate_ops():
+    """qkv_attention (projection + RoPE + attention as one node) == linear -> rope_ -> attention, values and grads."""
+    torch.manual_seed(0)
+    B, S, D, H, KVH, hd = 2, 16, 24, 4, 2, 8
+    tab = TK.rope_table(S, hd)
+    h = torch.randn(B, S, D, requires_grad=True)
+    w = torch.nn.Parameter(torch.randn((H + 2 * KVH) * hd, D) * 0.2)
+    y = ops.qkv_attention(h, w, tab, H, KVH, hd)
+    (y * torch.arange(y.shape[-1]).float()).sum().backward()
+    h2 = h.detach().requires_grad_(); w2 = torch.nn.Parameter(w.detach().clone())
+    qkv = ops.rope_(ops.linear(h2, w2), tab, S, H, KVH, hd)
+    y2 = ops.attention(qkv, H, KVH, hd)
+    (y2 * torch.arange(y2.shape[-1]).float()).sum().backward()
+    _close(y, y2); _close(h.grad, h2.grad); _close(w.grad, w2.grad)
