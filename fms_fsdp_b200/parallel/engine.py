@@ -164,6 +164,7 @@ class ShardedModel(nn.Module):
         # backward knobs (measured in profiles/README.md): gradient-buffer pool depth (1 = the block's backward waits for
         # the previous unit's reduce, 2 = they overlap) and whether backward re-gathers ride inside the GEMMs
         self._grad_pool_depth = int(os.environ.get("FMS_B200_GRAD_POOL", "1"))
+        self.poison_released_params = os.environ.get("FMS_B200_POISON", "0") == "1"
         self._fuse_gather_bwd = os.environ.get("FMS_B200_FUSED_GATHER_BWD", "1") != "0"
         self._gnorm_sq = torch.zeros((), dtype=torch.float32, device=self.device)
         self._clip_coef: Optional[torch.Tensor] = None
@@ -328,6 +329,10 @@ class ShardedModel(nn.Module):
     def _release(self, u: ShardUnit):
         if self.mesh.shard_size == 1 or u.full is None:
             return
+        if self.poison_released_params:
+            # debug trap: any kernel that still reads this unit's gathered parameters after release
+            # now sees NaN instead of silently-stale weights
+            u.full.t.fill_(float("nan"))
         if self.is_cuda:
             u.full.free_event.record(self.s_compute)
         u.unbind_params(self._placeholder)

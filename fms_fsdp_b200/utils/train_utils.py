@@ -238,6 +238,15 @@ def train(cfg, model, local_rank, rank, train_loader, optimizer, scheduler, prof
                 dist.all_reduce(ddp_stats, op=dist.ReduceOp.SUM)
             train_loss = ddp_stats[0] / ddp_stats[2]
             g_norm = ddp_stats[1] / ddp_stats[2]
+            # failure detection the reference lacks: a non-finite loss / grad norm is surfaced at the
+            # report step (already a sync point, so it costs nothing) and can stop the job so that restart + auto-resume
+            # rolls back to the last checkpoint instead of training on garbage
+            if not bool(torch.isfinite(train_loss)) or not bool(torch.isfinite(g_norm)):
+                msg = f"[non-finite] step {batch_idx}: loss {train_loss.item()} gradient norm {g_norm.item()}"
+                if getattr(cfg, "nonfinite_action", "warn") == "halt":
+                    raise FloatingPointError(msg + " -- halting (nonfinite_action=halt); restart resumes from the last checkpoint")
+                if rank == 0:
+                    print(msg, flush=True)
             elapsed_time = time.time() - loop_start
             if rank == 0:
                 total_tokens_seen = tokens_seen + new_tokens_seen

@@ -93,6 +93,7 @@ def main(**kwargs):
         param_init_fn=param_init_fn,
         local_world=(torch.cuda.device_count() if use_cuda else None),
     )
+    model.poison_released_params = bool(cfg.poison_released_params) or model.poison_released_params
     model.module.rot_emb.compute_freqs_cis(device, model.module.config.max_expected_seq_len)
     if rank == 0:
         print(f"--> sharded runtime: {model.extra_repr()}")

@@ -87,6 +87,7 @@ def main(**kwargs):
         param_init_fn=param_init_fn,
         local_world=(torch.cuda.device_count() if use_cuda else None),
     )
+    model.poison_released_params = bool(cfg.poison_released_params) or model.poison_released_params
     if rank == 0:
         print(f"--> sharded runtime: {model.extra_repr()}")
 

@@ -25,7 +25,14 @@ def rec(name, **kw):
         json.dump(records, f, indent=1)
 
 
+SMALL = os.environ.get("DIAG_SMALL") == "1"   # under compute-sanitizer: numerics on small shapes only, no timing loops
+
+
 def time_ms(fn, iters=10, warmup=3):
+    if SMALL:
+        fn()
+        torch.cuda.synchronize()
+        return 0.0
     for _ in range(warmup):
         fn()
     torch.cuda.synchronize()
@@ -102,7 +109,7 @@ def main(groups):
 
     if "gemm" in groups:
         shapes = [(128, 256, 64), (256, 512, 256), (384, 768, 192), (8, 8, 8), (1000, 520, 72),
-                  (2048, 4096, 4096), (8192, 12288, 4096)]
+                  (2048, 4096, 4096), (8192, 12288, 4096)][:(2 if SMALL else None)]
         for layout in ("nt", "nn", "tn"):
             for (M, N, K) in shapes:
                 try:
@@ -158,15 +165,15 @@ def main(groups):
             dy = torch.randn(M, D, device=dev).bfloat16()
             y0, r0 = TK.rmsnorm_fwd(x, w, 1e-5); y1, r1 = CK.rmsnorm_fwd(x, w, 1e-5)
             dx0, dw0 = TK.rmsnorm_bwd(dy, x, w, r0); dx1, dw1 = CK.rmsnorm_bwd(dy, x, w, r1)
-            xb = torch.randn(8192, 4096, device=dev).bfloat16()
+            xb = torch.randn(256 if SMALL else 8192, 4096, device=dev).bfloat16()
             ms = time_ms(lambda: CK.rmsnorm_fwd(xb, w, 1e-5))
             dres = torch.randn(M, D, device=dev).bfloat16()
             dxr = relerr(CK.rmsnorm_bwd(dy, x, w, r1, dres)[0], TK.rmsnorm_bwd(dy, x, w, r0, dres)[0])
-            dyb = torch.randn(8192, 4096, device=dev).bfloat16(); _, rb = CK.rmsnorm_fwd(xb, w, 1e-5)
+            dyb = torch.randn(xb.shape[0], 4096, device=dev).bfloat16(); _, rb = CK.rmsnorm_fwd(xb, w, 1e-5)
             msb = time_ms(lambda: CK.rmsnorm_bwd(dyb, xb, w, rb, dyb))
-            q = torch.randn(8192, 12288, device=dev).bfloat16(); tab = TK.rope_table(4096, 128, device=dev)
+            q = torch.randn(256 if SMALL else 8192, 12288, device=dev).bfloat16(); tab = TK.rope_table(4096, 128, device=dev)
             msr = time_ms(lambda: CK.rope_(q, tab, 4096, 32, 32, 128))
-            g = torch.randn(202383360, device=dev).bfloat16()
+            g = torch.randn(1 << 20 if SMALL else 202383360, device=dev).bfloat16()
             mss = time_ms(lambda: CK.sumsq(g))
             rec("rmsnorm", y=relerr(y1, y0), rstd=relerr(r1, r0), dx=relerr(dx1, dx0), dw=relerr(dw1, dw0), dx_dres=dxr,
                 fwd_ms_8192x4096=ms, fwd_gbs=2 * xb.numel() * 2 / ms / 1e6, bwd_dres_ms=msb,
@@ -322,7 +329,7 @@ def main(groups):
         for ver in ([int(x) for x in os.environ.get("DIAG_ATTN_VERS", "2").split(",")]):
           bver = int(os.environ.get("DIAG_ATTN_BWD", "3" if ver == 2 else str(ver)))
           CK._C.set_attn_fwd_version(ver); CK._C.set_attn_bwd_version(bver)
-          for (B, S, H, KVH, hd) in [(1, 128, 1, 1, 128), (2, 256, 4, 2, 128), (1, 384, 2, 1, 128), (1, 512, 2, 2, 64), (2, 4096, 32, 32, 128)]:
+          for (B, S, H, KVH, hd) in [(1, 128, 1, 1, 128), (2, 256, 4, 2, 128), (1, 384, 2, 1, 128), (1, 512, 2, 2, 64), (2, 4096, 32, 32, 128)][:(4 if SMALL else None)]:
             try:
                 qkv = torch.randn(B * S, (H + 2 * KVH) * hd, device=dev).bfloat16()
                 do = torch.randn(B * S, H * hd, device=dev).bfloat16()

@@ -95,6 +95,13 @@ def test_world2_matches_oracle(strategy, shard, ac):
     _check(_run(2, strategy, shard, ac), 2)
 
 
+def test_world2_poisoned_release_still_matches_oracle(monkeypatch):
+    """Debug trap of SURVEY 5.2: gathered parameters are NaN-filled the moment a unit is released; the schedule
+    (incl. selective recompute) must never read them afterwards, so the run still equals the oracle."""
+    monkeypatch.setenv("FMS_B200_POISON", "1")
+    _check(_run(2, "fsdp", 0, "1/2"), 2)
+
+
 def test_hsdp_2x2_matches_oracle():
     _check(_run(4, "hsdp", 2), 4)
 
