@@ -22,12 +22,14 @@ Collectives are pluggable (``comm.py``): c10d baseline or fused NVLink peer kern
 """
 from __future__ import annotations
 
+import hashlib
 import os
 
 import contextlib
 from typing import Dict, Iterable, List, Optional, Sequence, Tuple
 
 import torch
+import torch.distributed as dist
 import torch.nn as nn
 
 from fms_fsdp_b200.ops.functional import kernels_for
@@ -110,9 +112,12 @@ class ShardedModel(nn.Module):
                  mixed_precision: Optional[MixedPrecision] = None, device: Optional[torch.device] = None,
                  collective_impl: str = "auto", prefetch_depth: int = 2, param_init_fn=None,
                  mesh: Optional[DPMesh] = None, local_world: Optional[int] = None,
-                 reshard_after_forward: bool = True):
+                 reshard_after_forward: bool = True, sync_module_states: bool = False):
+        """``sync_module_states``: broadcast global rank 0's initial parameters to every rank before sharding (torch
+        FSDP's flag of the same name; the reference sets it for the speculator, ``train_speculator.py:205``)."""
         super().__init__()
         self.module = model
+        self._sync_module_states = bool(sync_module_states)
         self.device = torch.device(device) if device is not None else (
             torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else torch.device("cpu"))
         self.is_cuda = self.device.type == "cuda"
@@ -142,6 +147,8 @@ class ShardedModel(nn.Module):
 
         blocks, root_modules = model.engine_units()
         self.blocks: List[ShardUnit] = []
+        if self.mesh.world > 1:
+            self._validate_same_everywhere("number of shard units", len(blocks) + 1)
         self.root = self._make_unit("root", root_modules, param_init_fn, prefix_of=model)
         for i, blk in enumerate(blocks):
             u = self._make_unit(f"block{i}", [blk], param_init_fn, prefix_of=model)
@@ -186,6 +193,26 @@ class ShardedModel(nn.Module):
                 if b is not None and b.device != self.device:
                     m._buffers[k] = b.to(self.device)
 
+    def _validate_layout(self, name: str, layout: UnitLayout):
+        """Every rank must shard the same unit the same way (cf. torch FSDP's exec-order validation):
+        a model that differs across ranks would otherwise deadlock or silently mix shards.  One small object
+        all-gather per unit at construction; on by default, ``FMS_B200_VALIDATE=0`` skips it."""
+        if os.environ.get("FMS_B200_VALIDATE", "1") == "0":
+            return
+        mine = (name, layout.total, tuple((s.name, tuple(s.shape), s.offset) for s in layout.slots))
+        self._validate_same_everywhere(f"shard unit '{name}' (parameter names / shapes / order)", mine)
+
+    def _validate_same_everywhere(self, what: str, value):
+        if os.environ.get("FMS_B200_VALIDATE", "1") == "0":
+            return
+        digest = int.from_bytes(hashlib.sha1(repr(value).encode()).digest()[:6], "big")   # same on every rank
+        t = torch.tensor([digest], dtype=torch.int64, device=self.device)
+        lo, hi = t.clone(), t.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        if int(lo) != int(hi):
+            raise RuntimeError(f"{what} differs across ranks (rank {self.mesh.rank}: {str(value)[:200]})")
+
     def _make_unit(self, name, modules, param_init_fn, prefix_of) -> ShardUnit:
         # materialise (meta -> device) one unit at a time: allocate the whole unit, then run the init
         # functions children-first so a parent's reset_parameters has the last word on its children
@@ -209,6 +236,13 @@ class ShardedModel(nn.Module):
                     params.append((fqn[id(p)], p))
         params.sort(key=lambda np_: np_[1].dim() > 1)  # stable: vectors (norm gains, biases) first, matrices after
         layout = build_layout(name, [(n, tuple(p.shape)) for n, p in params], self.mesh.shard_size)
+        if self.mesh.world > 1:
+            self._validate_layout(name, layout)
+            if self._sync_module_states:
+                for _, p in params:   # rank 0's initial values win everywhere (before the unit is cut into shards)
+                    t = p.data.to(self.device).contiguous()
+                    dist.broadcast(t, src=0)
+                    p.data = t
         u = ShardUnit(name, modules, params, layout)
         n = layout.shard_numel
         lo, _ = layout.shard_range(self.mesh.shard_rank)

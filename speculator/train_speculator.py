@@ -149,7 +149,8 @@ def main(**kwargs):
 
     from fms_fsdp_b200.policies import bfSixteen, fp32_policy
     speculator = ShardedModel(speculator, sharding_strategy="ddp", mixed_precision=bfSixteen if use_cuda else fp32_policy,
-                              device=device, collective_impl=cfg.collective_impl)
+                              device=device, collective_impl=cfg.collective_impl,
+                              sync_module_states=True)   # rank 0's init everywhere (reference train_speculator.py:205)
     optimizer = ShardedAdamW(speculator, lr=cfg.learning_rate, betas=(0.9, 0.95), weight_decay=0.1)
 
     checkpointer = Checkpointer(cfg.ckpt_save_path, 1000, "ddp", rank, local_rank)

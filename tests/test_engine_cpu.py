@@ -158,3 +158,51 @@ def test_layout_math():
     assert [dim0_chunk(10, 4, r) for r in range(4)] == [(0, 3), (3, 6), (6, 9), (9, 10)]
     assert resolve_shard_size("hsdp", 8, 4) == 4 and resolve_shard_size("ddp", 8) == 1
     assert resolve_shard_size("whatever", 8) == 8  # unknown -> full shard, like the reference
+
+
+def _sync_worker(rank, world, port, outdir, mismatch):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        torch.manual_seed(100 + rank)                     # deliberately different initial weights per rank
+        cfg = get_model_config("llama2_tiny")
+        if mismatch == "depth" and rank == 1:
+            cfg.nlayers += 1                              # a model that differs across ranks must be rejected
+        if mismatch == "width" and rank == 1:
+            cfg.hidden_grow_factor = cfg.hidden_grow_factor * 2
+        m = LLaMA(cfg); m.reset_parameters()
+        err = None
+        try:
+            eng = ShardedModel(m, sharding_strategy="fsdp", mixed_precision=fp32_policy, device="cpu",
+                               collective_impl="torch", sync_module_states=True)
+            sd = eng.full_state_dict()
+        except RuntimeError as ex:
+            err, sd = str(ex), None
+        if rank == 0:
+            torch.manual_seed(100)
+            ref = LLaMA(get_model_config("llama2_tiny")); ref.reset_parameters()
+            torch.save(dict(err=err, sd=sd, ref=ref.state_dict()), os.path.join(outdir, "out.pt"))
+    finally:
+        try:
+            dist.barrier()
+        except Exception:
+            pass
+        dist.destroy_process_group()
+
+
+def test_sync_module_states_broadcasts_rank0_init():
+    outdir = tempfile.mkdtemp()
+    mp.spawn(_sync_worker, args=(2, free_port(), outdir, False), nprocs=2, join=True)
+    out = torch.load(os.path.join(outdir, "out.pt"), weights_only=False)
+    assert out["err"] is None
+    for k, v in out["ref"].items():
+        assert torch.equal(out["sd"][k], v), k
+
+
+@pytest.mark.parametrize("kind", ["depth", "width"])
+def test_models_that_differ_across_ranks_are_rejected(kind):
+    outdir = tempfile.mkdtemp()
+    mp.spawn(_sync_worker, args=(2, free_port(), outdir, kind), nprocs=2, join=True)
+    out = torch.load(os.path.join(outdir, "out.pt"), weights_only=False)
+    assert out["err"] is not None and "differs across ranks" in out["err"]
