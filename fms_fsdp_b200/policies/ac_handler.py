@@ -35,6 +35,14 @@ def selection_mask(n_blocks: int, p: Union[int, float, str]):
     return mask
 
 
+def non_reentrant_wrapper(module: nn.Module) -> nn.Module:
+    """Counterpart of the reference's module-level ``non_reentrant_wrapper`` (``ac_handler.py:10-13``, a partial of
+    torch's ``checkpoint_wrapper``): marks ONE block for recompute and returns it (no wrapper module is inserted, so
+    state-dict keys do not change)."""
+    setattr(module, _FLAG, True)
+    return module
+
+
 def is_checkpointed(module: nn.Module) -> bool:
     return bool(getattr(module, _FLAG, False))
 

@@ -28,3 +28,11 @@ def test_fraction_parser_is_not_eval():
     assert parse_fraction(0.5) == 0.5
     with pytest.raises(Exception):
         parse_fraction("__import__('os').system('true')")
+
+
+def test_non_reentrant_wrapper_marks_a_single_block():
+    import torch.nn as nn
+    from fms_fsdp_b200.policies.ac_handler import is_checkpointed, non_reentrant_wrapper
+    blk = nn.Linear(2, 2)
+    assert not is_checkpointed(blk)
+    assert non_reentrant_wrapper(blk) is blk and is_checkpointed(blk)
