@@ -60,13 +60,15 @@ def get_mixed_precision_policy(cfg, rank):
     if not cfg.mixed_precision:
         return None
     bf16_ready = (not torch.cuda.is_available()) or torch.cuda.is_bf16_supported()
-    if bf16_ready:
-        if rank == 0:
-            print("bFloat16 enabled for mixed precision - using bfSixteen policy")
-        return bfSixteen
+    policy = bfSixteen if bf16_ready else fpSixteen
     if rank == 0:
-        print("FP16 enabled")
-    return fpSixteen
+        print("bFloat16 enabled for mixed precision - using bfSixteen policy" if bf16_ready else "FP16 enabled")
+    if getattr(cfg, "grad_dtype", "bf16") == "fp32":
+        # extension: keep the unsharded gradient buffer (what the wgrad GEMMs write and the reduce-scatter reads) in
+        # fp32 instead of the reference's reduce_dtype = bf16
+        import dataclasses
+        policy = dataclasses.replace(policy, reduce_dtype=torch.float32)
+    return policy
 
 
 _STRATEGIES = {"fsdp": "fsdp", "hsdp": "hsdp", "ddp": "ddp"}

@@ -45,3 +45,19 @@ def test_param_counts():
     with torch.device("meta"):
         m = LLaMA(get_model_config("llama2_7b"))
     assert sum(p.numel() for p in m.parameters()) == 6738415616
+
+
+def test_grad_dtype_and_precision_switches():
+    import torch
+    from fms_fsdp_b200.config import train_config
+    from fms_fsdp_b200.models.llama import LLaMABlock
+    from fms_fsdp_b200.utils.train_utils import get_policies
+    cfg = train_config()
+    assert get_policies(cfg, 1, LLaMABlock)[0].reduce_dtype == torch.bfloat16
+    cfg.grad_dtype = "fp32"
+    mp = get_policies(cfg, 1, LLaMABlock)[0]
+    assert mp.reduce_dtype == torch.float32 and mp.param_dtype == torch.bfloat16
+    cfg.precision = "mxfp8"
+    import pytest
+    with pytest.raises(NotImplementedError):
+        get_policies(cfg, 1, LLaMABlock)
