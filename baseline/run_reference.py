@@ -109,11 +109,23 @@ def main():
         else:
             raise
     dist.barrier(); torch.cuda.synchronize()
+    sampler = None
+    if rank == 0:   # same nvidia-smi clock / throttle sampling as the other arm, during the timed region only
+        try:
+            root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+            if root not in sys.path:
+                sys.path.insert(0, root)
+            from bench import ClockSampler
+            sampler = ClockSampler(local_rank)
+            sampler.start()
+        except Exception:
+            sampler = None
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     loss = run_train(a.warmup, a.warmup + a.steps)
     e1.record()
     dist.barrier(); torch.cuda.synchronize()
+    clocks = sampler.stop() if sampler is not None else None
     ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
     dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_step = ms.item() / a.steps
@@ -131,6 +143,8 @@ def main():
             "e2e": {"value": round(value, 1), "unit": "tokens/s",
                     "note": "the reference train() loop is inherently end-to-end (per-step H2D of the batch, loss.item())",
                     "h2d_bytes_per_step": a.batch * a.seq * 4 * 2, "d2h_bytes_per_step": 8},
+            "gpu_launches": 0,   # none of this repo's kernels run in the reference arm (library / inductor kernels only)
+            "clocks": clocks,
             "loss": float(loss) if loss is not None else None,
             "mem_gb": round(torch.cuda.max_memory_allocated() / 2 ** 30, 2),
         }), flush=True)
