@@ -16,6 +16,8 @@ from __future__ import annotations
 
 from typing import Optional
 
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -100,7 +102,14 @@ class TorchCollectives:
 def make_collectives(impl: str, mesh: DPMesh, device: torch.device):
     impl = (impl or "auto").lower()
     if impl == "auto":
-        impl = "fused" if (device.type == "cuda" and mesh.world > 1) else "torch"
+        # the peer-memory collectives need every rank of the job on one NVSwitch domain; a multi-node job (the
+        # reference's 96-128 GPU runs) takes the c10d/NCCL implementation of the same interface
+        local_world = int(os.environ.get("LOCAL_WORLD_SIZE", mesh.world))
+        single_node = local_world >= mesh.world
+        impl = "fused" if (device.type == "cuda" and mesh.world > 1 and single_node) else "torch"
+        if device.type == "cuda" and mesh.world > 1 and not single_node and mesh.rank == 0:
+            print(f"[fms_fsdp_b200] {mesh.world} ranks over {mesh.world // max(local_world, 1)} nodes: "
+                  "collective_impl=torch (NCCL); the NVLink peer-memory collectives are single-node")
     if impl == "fused":
         if device.type != "cuda":
             raise ValueError("collective_impl=fused needs CUDA devices")
