@@ -1,0 +1,50 @@
+"""Tensor-parallel frozen base model of speculator training (reference: fms TP strategy, `train_speculator.py:133-160`):
+slicing a loaded LLaMA over 2 ranks (gloo) must reproduce the unsharded logits, embeds and KV-cache decode."""
+import os
+import tempfile
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from conftest import free_port
+from fms_fsdp_b200.parallel.tensor_parallel import shard_llama_for_tp
+from fms_fsdp_b200.utils.config_utils import get_model_config
+
+
+def _worker(rank, world, port, outdir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import sys
+        sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "speculator"))
+        from train_speculator_utils import EmbedLLaMA
+        torch.manual_seed(0)
+        m = EmbedLLaMA(get_model_config("llama2_tiny")); m.reset_parameters(); m.eval()
+        x = torch.randint(0, m.config.src_vocab_size, (2, 12))
+        with torch.no_grad():
+            ref_logits, ref_embeds = m(x, include_embeds=True)
+            # prefill + one cached decode step, unsharded
+            l0, cache = m(x[:, :-1], use_cache=True)
+            l1, _ = m(x[:, -1:], past_key_value_states=cache, use_cache=True)
+            shard_llama_for_tp(m, dist.group.WORLD)
+            tp_logits, tp_embeds = m(x, include_embeds=True)
+            t0, tcache = m(x[:, :-1], use_cache=True)
+            t1, _ = m(x[:, -1:], past_key_value_states=tcache, use_cache=True)
+        ok = dict(logits=(tp_logits - ref_logits).abs().max().item(), embeds=(tp_embeds - ref_embeds).abs().max().item(),
+                  prefill=(t0 - l0).abs().max().item(), decode=(t1 - l1).abs().max().item(),
+                  scale=ref_logits.abs().max().item())
+        if rank == 0:
+            torch.save(ok, os.path.join(outdir, "out.pt"))
+    finally:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def test_tp2_base_model_matches_unsharded():
+    outdir = tempfile.mkdtemp()
+    mp.spawn(_worker, args=(2, free_port(), outdir), nprocs=2, join=True)
+    r = torch.load(os.path.join(outdir, "out.pt"), weights_only=False)
+    tol = 1e-4 * max(1.0, r["scale"])
+    assert r["logits"] < tol and r["embeds"] < tol and r["prefill"] < tol and r["decode"] < tol, r
