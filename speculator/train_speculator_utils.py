@@ -172,6 +172,9 @@ class EmbedMixtral(EmbedLLaMA):
 
 
 _REGISTRY = {
+    # 2-layer toy for CPU drills and tests (not a reference variant)
+    ("embedllama", "tiny"): lambda: EmbedLLaMA(LLaMAConfig(src_vocab_size=512, emb_dim=64, nheads=4, kvheads=2, nlayers=2,
+                                                           multiple_of=16, max_expected_seq_len=256)),
     ("embedllama", "7b"): lambda: EmbedLLaMA(LLaMAConfig(hidden_grow_factor=11008 / 4096, kvheads=32)),
     ("embedllama", "8b"): lambda: EmbedLLaMA(LLaMAConfig(src_vocab_size=128256, emb_dim=4096, nheads=32, kvheads=8,
                                                          nlayers=32, hidden_grow_factor=3.5, max_expected_seq_len=8192,

@@ -48,3 +48,23 @@ def test_tp2_base_model_matches_unsharded():
     r = torch.load(os.path.join(outdir, "out.pt"), weights_only=False)
     tol = 1e-4 * max(1.0, r["scale"])
     assert r["logits"] < tol and r["embeds"] < tol and r["prefill"] < tol and r["decode"] < tol, r
+
+
+def test_speculator_entrypoint_tp2_two_stages(tmp_path):
+    """`speculator/train_speculator.py` end to end on 2 gloo ranks: (dp, tp) = (1, 2) mesh, TP-sharded frozen base model,
+    DDP speculator on the engine, stage 1 -> stage 2 (generated continuations), final checkpoint."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", str(free_port()), os.path.join(root, "speculator", "train_speculator.py"),
+           "--model_arch=embedllama", "--model_variant=tiny", "--model_path=/nonexistent", "--sharding_strategy=tp",
+           "--tp_size=2", "--use_dummy_dataset=True", "--num_steps=4", "--report_interval=2", "--stage2_start_step=3",
+           "--stage2_batch_size=4", "--stage2_prompt_length=4", "--stage2_seq_length=8", "--n_speculator_heads=2",
+           "--speculator_width=32", "--seq_length=16", "--vocab_size=512", "--batch_size=2",
+           f"--ckpt_save_path={tmp_path}", f"--ckpt_load_path={tmp_path}", "--checkpoint_interval=100",
+           "--comm_backend=gloo", "--use_torch_compile=False"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=root, env=dict(os.environ, OMP_NUM_THREADS="1"))
+    assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-1500:]
+    assert "step: 4" in r.stdout and "loss 2:" in r.stdout and "Checkpoint saved" in r.stdout
+    assert os.path.isdir(os.path.join(tmp_path, "checkpoints", "step_4_ckp"))
