@@ -65,6 +65,7 @@ DECL int b200_attn_fwd(const void*, void*, float*, int, int, int, int, int, floa
 DECL int b200_attn_bwd(const void*, const void*, const void*, const float*, void*, float*, int, int, int, int, int,
                        float, const float*, cudaStream_t);
 DECL void b200_gemm2_set_rope(const float*, int, int, int);
+DECL void b200_gemm2_set_push(void* const*, long long, long long, int);
 DECL int b200_p2p_allgather(const void* const*, void*, long long, int, int, cudaStream_t);
 DECL int b200_reduce_scatter(const void* const*, float*, long long, long long, int, int, int, float, float*,
                              cudaStream_t);
@@ -130,6 +131,8 @@ void gemm(const at::Tensor& a, const at::Tensor& b, at::Tensor& c, int64_t layou
   }
   TORCH_CHECK(epi != 3 || (g_gemm_2cta && M >= 256 && layout == 0 && c.scalar_type() == at::kBFloat16),
               "RoPE epilogue: CTA-pair kernel, nt layout, bf16 output only (call set_gemm_rope first)");
+  TORCH_CHECK(epi != 4 || (g_gemm_2cta && M >= 256 && layout == 2 && c.scalar_type() == at::kBFloat16),
+              "push epilogue (experimental): CTA-pair kernel, tn layout, bf16 only (call set_gemm_push first)");
   // CTA-pair kernel (cta_group::2, 256x256 tiles) for anything with at least one full pair tile of rows
   if (g_gemm_2cta && M >= 256) {
     check(b200_gemm2_bf16(a.data_ptr(), b.data_ptr(), c.data_ptr(), r, M, N, K, a.stride(0), b.stride(0), c.stride(0),
@@ -724,6 +727,11 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     need(table, "rope table", at::kFloat);
     TORCH_CHECK(table.is_contiguous() && table.numel() >= S * hd, "rope table must be [S, hd/2, 2] fp32");
     b200_gemm2_set_rope(table.data_ptr<float>(), (int)S, (int)hd, (int)cols);
+  });
+  m.def("set_gemm_push", [](const at::Tensor& bases, int64_t n, int64_t off, int64_t rank) {
+    // EXPERIMENTAL (docs/next_steps.md 2): int64 device table of every rank's staging-buffer base address
+    TORCH_CHECK(bases.is_cuda() && bases.scalar_type() == at::kLong && bases.is_contiguous(), "push table: int64 CUDA tensor");
+    b200_gemm2_set_push((void* const*)bases.data_ptr(), n, off, (int)rank);
   });
   m.def("ssd_scan_fwd", &ssd_scan_fwd);
   m.def("selective_scan_fwd", &selective_scan_fwd);

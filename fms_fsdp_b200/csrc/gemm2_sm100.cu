@@ -26,7 +26,7 @@ constexpr int P_STAGE_BYTES = PA_BYTES + PB_BYTES;
 constexpr int P_THREADS = 192;
 constexpr int P_SMEM = P_STAGES * P_STAGE_BYTES + 1024 + 256;
 
-enum { P_EPI_STORE = 0, P_EPI_RESIDUAL = 1, P_EPI_ACCUM = 2, P_EPI_ROPE = 3 };
+enum { P_EPI_STORE = 0, P_EPI_RESIDUAL = 1, P_EPI_ACCUM = 2, P_EPI_ROPE = 3, P_EPI_PUSH = 4 };
 
 
 // L2-friendly rasterisation: sweep all n-tiles for a band of GROUP_M m-tiles before moving to the next band, so the
@@ -107,6 +107,13 @@ struct Gemm2Params {
   // (row % rope_S, (col % rope_hd) / 2) before the bf16 store; table is [S][hd/2][cos, sin] fp32
   const float* rope;
   int rope_S, rope_hd, rope_cols;
+  // P_EPI_PUSH (EXPERIMENTAL, not used by the engine yet; docs/next_steps.md section 2): the wgrad tile is not stored to C
+  // but pushed over NVLink into the staging buffer of the rank that OWNS that slice of the unit's flat gradient:
+  //   e = push_off + row * ldc + col ; owner = e / push_n ; dst = push_bases[owner] + push_rank * push_n + (e - owner * push_n)
+  // so that after a barrier each owner reduces `world` local slots (reduce-scatter with no NVLink traffic of its own).
+  void* const* push_bases;
+  long long push_n, push_off;
+  int push_rank;
 };
 
 template <bool A_MN, bool B_MN, int EPI, typename OutT, bool AG>
@@ -308,6 +315,17 @@ gemm2_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                 float f[8];
 #pragma unroll
                 for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(v[g * 8 + i]);
+                if constexpr (EPI == P_EPI_PUSH) {
+                  const long long e = p.push_off + (long long)row * p.ldc + (cb + g * 8);
+                  const long long owner = e / p.push_n;
+                  __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.push_bases[owner]) +
+                                       ((long long)p.push_rank * p.push_n + (e - owner * p.push_n));
+                  uint4 o;
+                  o.x = pack_bf16x2(f[0], f[1]); o.y = pack_bf16x2(f[2], f[3]);
+                  o.z = pack_bf16x2(f[4], f[5]); o.w = pack_bf16x2(f[6], f[7]);
+                  *reinterpret_cast<uint4*>(dst) = o;     // peer (or local) store; made visible by the barrier that follows
+                  continue;
+                }
                 if constexpr (EPI == P_EPI_ROPE) {
                   const int c8 = cb + g * 8;
                   if (c8 < p.rope_cols) {
@@ -420,11 +438,19 @@ static int dispatch2(const CUtensorMap& a, const CUtensorMap& b, const Gemm2Para
 // that owns the stream; keeps the two launcher signatures unchanged)
 static const float* g_rope_table = nullptr;
 static int g_rope_S = 1, g_rope_hd = 2, g_rope_cols = 0;
+// same convention for the (experimental) push epilogue
+static void* const* g_push_bases = nullptr;
+static long long g_push_n = 1, g_push_off = 0;
+static int g_push_rank = 0;
 
 }  // namespace b200
 
 extern "C" void b200_gemm2_set_rope(const float* table, int S, int hd, int cols) {
   b200::g_rope_table = table; b200::g_rope_S = S; b200::g_rope_hd = hd; b200::g_rope_cols = cols;
+}
+
+extern "C" void b200_gemm2_set_push(void* const* bases, long long n, long long off, int rank) {
+  b200::g_push_bases = bases; b200::g_push_n = n; b200::g_push_off = off; b200::g_push_rank = rank;
 }
 
 extern "C" int b200_gemm2_bf16(const void* A, const void* B, void* C, const void* R, int M, int N, int K, int lda,
@@ -444,9 +470,15 @@ extern "C" int b200_gemm2_bf16(const void* A, const void* B, void* C, const void
   p.m_tiles = (M + P_BM - 1) / P_BM;
   p.n_tiles = (N + P_BN - 1) / P_BN;
   p.rope = g_rope_table; p.rope_S = g_rope_S; p.rope_hd = g_rope_hd; p.rope_cols = g_rope_cols;
+  p.push_bases = g_push_bases; p.push_n = g_push_n; p.push_off = g_push_off; p.push_rank = g_push_rank;
   if (epi == P_EPI_ROPE) {
     if (a_mn || b_mn || out_fp32 || !p.rope || (p.rope_hd % 8) || (p.rope_cols % 8)) return -8;
     return launch2<false, false, P_EPI_ROPE, __nv_bfloat16>(tmA, tmB, p, stream);
+  }
+  if (epi == P_EPI_PUSH) {   // wgrad (tn) only; every 8-element vector must stay inside one owner's slice
+    if (!a_mn || !b_mn || out_fp32 || !p.push_bases || p.push_n <= 0 || (p.push_n % 8) || (p.push_off % 8) || (ldc % 8))
+      return -9;
+    return launch2<true, true, P_EPI_PUSH, __nv_bfloat16>(tmA, tmB, p, stream);
   }
   if (a_mn) {
     if (b_mn) return dispatch2<true, true>(tmA, tmB, p, epi, out_fp32, stream);
@@ -478,6 +510,7 @@ extern "C" int b200_gemm2_ag_bf16(const void* A, const void* B, void* C, const v
   p.m_tiles = (M + P_BM - 1) / P_BM;
   p.n_tiles = (N + P_BN - 1) / P_BN;
   p.rope = g_rope_table; p.rope_S = g_rope_S; p.rope_hd = g_rope_hd; p.rope_cols = g_rope_cols;
+  p.push_bases = nullptr; p.push_n = 1; p.push_off = 0; p.push_rank = 0;
   AgParams ag;
   ag.peer_shards = peer_shards; ag.full = (uint8_t*)full; ag.shard_bytes = shard_bytes; ag.begin = begin; ag.end = end;
   ag.world = world; ag.rank = rank; ag.flags = flags; ag.epoch = epoch; ag.dependent = dependent;
