@@ -206,11 +206,17 @@ class ShardedModel(nn.Module):
         if os.environ.get("FMS_B200_VALIDATE", "1") == "0":
             return
         digest = int.from_bytes(hashlib.sha1(repr(value).encode()).digest()[:6], "big")   # same on every rank
-        t = torch.tensor([digest], dtype=torch.int64, device=self.device)
-        lo, hi = t.clone(), t.clone()
-        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
-        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
-        if int(lo) != int(hi):
+        try:
+            t = torch.tensor([digest], dtype=torch.int64, device=self.device)
+            lo, hi = t.clone(), t.clone()
+            dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+            dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+            lo, hi = int(lo), int(hi)
+        except Exception as ex:   # a debugging aid must never take a healthy job down
+            if self.mesh.rank == 0:
+                print(f"[fms_fsdp_b200] cross-rank validation of {what} skipped: {ex!r}")
+            return
+        if lo != hi:
             raise RuntimeError(f"{what} differs across ranks (rank {self.mesh.rank}: {str(value)[:200]})")
 
     def _make_unit(self, name, modules, param_init_fn, prefix_of) -> ShardUnit:
