@@ -66,6 +66,7 @@ DECL int b200_attn_bwd(const void*, const void*, const void*, const float*, void
                        float, const float*, cudaStream_t);
 DECL void b200_gemm2_set_rope(const float*, int, int, int);
 DECL void b200_gemm2_set_push(void* const*, long long, long long, int);
+DECL int b200_p2p_push_range(const void*, void* const*, long long, long long, long long, int, cudaStream_t);
 DECL int b200_p2p_allgather(const void* const*, void*, long long, int, int, cudaStream_t);
 DECL int b200_reduce_scatter(const void* const*, float*, long long, long long, int, int, int, float, float*,
                              cudaStream_t);
@@ -727,6 +728,14 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     need(table, "rope table", at::kFloat);
     TORCH_CHECK(table.is_contiguous() && table.numel() >= S * hd, "rope table must be [S, hd/2, 2] fp32");
     b200_gemm2_set_rope(table.data_ptr<float>(), (int)S, (int)hd, (int)cols);
+  });
+  m.def("push_range", [](const at::Tensor& src, const at::Tensor& bases, int64_t n, int64_t off, int64_t rank) {
+    // EXPERIMENTAL: this rank's gradient elements [off, off + src.numel()) -> the owners' staging slots
+    c10::cuda::CUDAGuard guard(src.device());
+    need(src, "src", at::kBFloat16);
+    TORCH_CHECK(src.is_contiguous() && bases.scalar_type() == at::kLong && bases.is_cuda());
+    check(b200_p2p_push_range(src.data_ptr(), (void* const*)bases.data_ptr(), n, off, src.numel(), (int)rank, cur_stream()),
+          "p2p_push_range");
   });
   m.def("set_gemm_push", [](const at::Tensor& bases, int64_t n, int64_t off, int64_t rank) {
     // EXPERIMENTAL (docs/next_steps.md 2): int64 device table of every rank's staging-buffer base address

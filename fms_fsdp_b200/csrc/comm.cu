@@ -98,6 +98,20 @@ __global__ void __launch_bounds__(512) p2p_gather_range_kernel(const void* const
   }
 }
 
+// EXPERIMENTAL (docs/next_steps.md 2): the inverse of gather_range for gradients -- element range [off, off + len) of this
+// rank's contribution to a unit's flat gradient is written into the OWNERS' staging slots
+//   owner = e / n ;  dst = bases[owner] + rank * n + (e - owner * n)        (bf16 elements, 16-byte vectors)
+__global__ void __launch_bounds__(256) p2p_push_range_kernel(const __nv_bfloat16* __restrict__ src, void* const* bases,
+                                                             size_t n, size_t off, size_t len, int rank) {
+  const size_t nvec = len / 8;
+  for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += (size_t)gridDim.x * blockDim.x) {
+    const size_t e = off + v * 8;
+    const size_t owner = e / n;
+    __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(bases[owner]) + ((size_t)rank * n + (e - owner * n));
+    *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(src + v * 8);
+  }
+}
+
 B200_DEVINL float block_sum256(float v, float* sh) {
   v = warp_sum(v);
   const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
@@ -242,6 +256,16 @@ extern "C" int b200_p2p_gather_range(const void* const* shard_ptrs, void* full, 
   int grid = (int)((nvec + 511) / 512);
   if (grid > 64) grid = 64;
   p2p_gather_range_kernel<<<grid, 512, 0, s>>>(shard_ptrs, (uint8_t*)full, (size_t)shard_bytes, (size_t)begin, (size_t)end);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int b200_p2p_push_range(const void* src, void* const* bases, long long n, long long off, long long len, int rank,
+                                   cudaStream_t s) {
+  if ((n % 8) || (off % 8) || (len % 8) || len < 0) return -1;
+  if (len == 0) return 0;
+  int grid = (int)((len / 8 + 255) / 256);
+  if (grid > 64) grid = 64;
+  p2p_push_range_kernel<<<grid, 256, 0, s>>>((const __nv_bfloat16*)src, bases, (size_t)n, (size_t)off, (size_t)len, rank);
   return (int)cudaGetLastError();
 }
 

@@ -112,10 +112,36 @@ def _try_fused_gather(a, b, layout, out, epi, residual) -> bool:
     return True
 
 
+class PushTarget:
+    """EXPERIMENTAL (docs/next_steps.md 2, FMS_B200_PUSH_RS=1): "output" of a wgrad GEMM whose epilogue writes every
+    tile into the staging slots of the rank that owns that slice of the unit's flat gradient (fused GEMM ->
+    reduce-scatter).  ``table``: int64 device tensor of the ranks' staging-buffer addresses; ``n``: elements per shard;
+    ``off``: element offset of this weight inside the flat unit."""
+    __slots__ = ("table", "n", "off", "rank", "shape", "_dummy")
+
+    def __init__(self, table, n, off, rank, shape, device):
+        self.table, self.n, self.off, self.rank, self.shape = table, int(n), int(off), int(rank), tuple(shape)
+        self._dummy = torch.empty(8, dtype=torch.bfloat16, device=device).as_strided(self.shape, (self.shape[1], 1))
+
+
+def _gemm_push(a, b, tgt: PushTarget):
+    M, N = a.shape[1], b.shape[1]
+    if (a.dtype != torch.bfloat16 or b.dtype != torch.bfloat16 or (M, N) != tgt.shape or M < 256 or not _C.get_gemm_2cta()
+            or M % 8 or N % 8 or a.shape[0] % 8):
+        raise RuntimeError(f"wgrad {tuple(a.shape)}^T x {tuple(b.shape)} cannot use the push epilogue")
+    _C.set_gemm_push(tgt.table, tgt.n, tgt.off, tgt.rank)
+    _C.gemm(a if a.stride(-1) == 1 else a.contiguous(), b if b.stride(-1) == 1 else b.contiguous(), tgt._dummy, 2, 4, None)
+    return tgt
+
+
 # ------------------------------------------------------------------------------------------ GEMM
 def gemm(a, b, layout="nt", out=None, accumulate=False, residual=None, out_dtype=None, rope=None):
     """``rope=(table [S, hd/2, 2] fp32, S, hd, H, KVH)``: rotary embedding of the q and k heads (the first
     ``(H + KVH) * hd`` output columns) fused into the GEMM epilogue (QKV projection; nt layout)."""
+    if isinstance(out, PushTarget):
+        if layout != "tn" or accumulate or residual is not None:
+            raise RuntimeError("the push epilogue is a plain tn (wgrad) store")
+        return _gemm_push(a, b, out)
     if rope is not None:
         M0 = a.shape[0]
         ok = (GEMM_IMPL == "tcgen05" and layout == "nt" and a.dtype == b.dtype == torch.bfloat16 and residual is None

@@ -49,6 +49,13 @@ def _wdata(w):
 
 def _deliver_wgrad(w, compute):
     """Run ``compute(out, accumulate)`` into the runtime grad buffer if present, else return a grad."""
+    push = getattr(w, "_grad_push", None)
+    if push is not None:   # experimental fused GEMM -> reduce-scatter: the wgrad goes straight to the owning ranks
+        if getattr(w, "_grad_ready", False):
+            raise RuntimeError("push reduce-scatter: a second gradient contribution to the same weight is not supported")
+        compute(push, False)
+        w._grad_ready = True
+        return None
     buf = getattr(w, "_grad_buf", None)
     if buf is not None:
         acc = bool(getattr(w, "_grad_ready", False))

@@ -84,10 +84,25 @@ class ShardUnit:
             p._grad_ready = False
             p.grad = None
 
+    def bind_grads_push(self, vec: torch.Tensor, make_target):
+        """EXPERIMENTAL push path: 1-D parameters write into the local vector buffer ``vec`` (flat elements
+        [0, matrix_begin)), weight matrices get a push target instead of a buffer view."""
+        for (_, p), s in zip(self.params, self.layout.slots):
+            p._grad_ready = False
+            p.grad = None
+            if p.dim() == 1:
+                p._grad_buf, p._grad_push = vec[s.offset:s.offset + s.numel].view(s.shape), None
+            else:
+                p._grad_buf, p._grad_push = None, make_target(s)
+
     def collect_grads(self):
         """Fold autograd-produced .grad (ops that did not write into the buffer) and zero the slots
         of parameters that received no gradient at all."""
         for _, p in self.params:
+            if getattr(p, "_grad_push", None) is not None:
+                if p.grad is not None or not p._grad_ready:
+                    raise RuntimeError("push reduce-scatter: every weight matrix must receive exactly one wgrad GEMM")
+                continue
             buf = p._grad_buf
             if p.grad is not None:
                 if p._grad_ready:
@@ -102,6 +117,7 @@ class ShardUnit:
     def unbind_grads(self):
         for _, p in self.params:
             p._grad_buf = None
+            p._grad_push = None
             p._grad_ready = False
 
 
@@ -172,6 +188,10 @@ class ShardedModel(nn.Module):
         # the previous unit's reduce, 2 = they overlap) and whether backward re-gathers ride inside the GEMMs
         self._grad_pool_depth = int(os.environ.get("FMS_B200_GRAD_POOL", "1"))
         self.poison_released_params = os.environ.get("FMS_B200_POISON", "0") == "1"
+        # EXPERIMENTAL, off by default and not yet validated on hardware (docs/next_steps.md 2): wgrad GEMMs push their
+        # tiles to the owning ranks (fused GEMM -> reduce-scatter), the reduce becomes a local slot sum
+        self._push_rs = (os.environ.get("FMS_B200_PUSH_RS", "0") == "1" and self.coll.name == "fused"
+                         and self.mesh.shard_size > 1 and self.mp.reduce_dtype == torch.bfloat16)
         self._fuse_gather_bwd = os.environ.get("FMS_B200_FUSED_GATHER_BWD", "1") != "0"
         self._gnorm_sq = torch.zeros((), dtype=torch.float32, device=self.device)
         self._clip_coef: Optional[torch.Tensor] = None
@@ -386,7 +406,29 @@ class ShardedModel(nn.Module):
             u.full_grad = buf
         if self.is_cuda:
             self.s_compute.wait_event(u.full_grad.free_event)
+        if self._push_rs and self._push_eligible(u):
+            from fms_fsdp_b200.ops.cuda_kernels import PushTarget
+            staging = u.full_grad.t                       # same buffer, now laid out [src rank][shard elements]
+            if getattr(u, "vec_grad", None) is None:
+                u.vec_grad = torch.zeros(u.layout.matrix_begin, dtype=staging.dtype, device=self.device)
+            table, n, r = self.coll.push_table(staging), u.layout.shard_numel, self.mesh.shard_rank
+            u.bind_grads_push(u.vec_grad, lambda s: PushTarget(table, n, s.offset, r, s.shape, self.device))
+            u.pushed = True
+            return
+        u.pushed = False
         u.bind_grads(u.full_grad.t)
+
+    def _push_eligible(self, u: ShardUnit) -> bool:
+        """Block units whose every parameter is a norm-style vector or a weight matrix large enough for the CTA-pair
+        wgrad GEMM (LLaMA blocks); the root unit (embedding / tied or chunk-accumulated head) keeps the pull path."""
+        if u is self.root or u.recompute:
+            return False
+        ok = getattr(u, "_push_ok", None)
+        if ok is None:
+            ok = all(p.dim() == 1 or (p.dim() == 2 and p.shape[0] >= 256 and p.shape[0] % 8 == 0 and p.shape[1] % 8 == 0)
+                     for _, p in u.params) and u.layout.matrix_begin % 8 == 0
+            u._push_ok = ok
+        return ok
 
     def _reduce(self, u: ShardUnit):
         u.collect_grads()
@@ -398,6 +440,9 @@ class ShardedModel(nn.Module):
         with ctx:
             if m.shard_size == 1:
                 self.coll.all_reduce_full(u.full_grad.t, 1.0 / W, self._gnorm_sq)
+            elif getattr(u, "pushed", False):
+                self.coll.push_vectors(u.vec_grad, u.full_grad.t)
+                self.coll.reduce_pushed(u.full_grad.t, u.grad_shard, 1.0 / W, self._gnorm_sq)
             else:
                 self.coll.reduce_scatter(u.full_grad.t, u.grad_shard, 1.0 / W, self._gnorm_sq)
             if self.is_cuda:

@@ -169,6 +169,33 @@ class FusedCollectives:
         if hsdp:
             self._allreduce(self.replica, shard32, 1.0, sumsq)
 
+    # ---- EXPERIMENTAL push path (FMS_B200_PUSH_RS=1; docs/next_steps.md 2) -------------------------------------------
+    def push_table(self, staging: torch.Tensor) -> torch.Tensor:
+        """Addresses of every shard-rank's copy of ``staging`` (layout [src_rank][shard elements])."""
+        return self.shard.table_of(staging)
+
+    def push_vectors(self, vec: torch.Tensor, staging: torch.Tensor):
+        """The non-GEMM gradients of a unit (norm gains: flat elements [0, vec.numel())) -> the owners' slots."""
+        g = self.shard
+        self.C.push_range(vec, g.table_of(staging), staging.numel() // g.size, 0, g.index)
+
+    def reduce_pushed(self, staging: torch.Tensor, shard32: torch.Tensor, scale: float, sumsq: Optional[torch.Tensor]):
+        """After every rank pushed its wgrad tiles: barrier, LOCAL sum of the `world` slots, barrier (buffer reusable)."""
+        g = self.shard
+        n = shard32.numel()
+        g.barrier(self.C, self._anchor)   # all tiles of all ranks have landed in my slots
+        key = ("slots", staging.data_ptr())
+        tab = self._slice_tables.get(key)
+        if tab is None:
+            tab = torch.tensor([staging.data_ptr() + s_ * n * staging.element_size() for s_ in range(g.size)],
+                               dtype=torch.int64, device=self.device)
+            self._slice_tables[key] = tab
+        hsdp = self.replica is not None
+        self.C.reduce_scatter(tab, shard32, 0, g.size, 0, staging.dtype == torch.bfloat16, float(scale), None if hsdp else sumsq)
+        g.barrier(self.C, self._anchor)   # nobody pushes into a buffer another rank is still reducing
+        if hsdp:
+            self._allreduce(self.replica, shard32, 1.0, sumsq)
+
     def all_reduce_full(self, full: torch.Tensor, scale: float, sumsq: Optional[torch.Tensor]):
         if self.replica is None:
             if sumsq is not None:
