@@ -65,13 +65,15 @@ DECL int b200_attn_fwd(const void*, void*, float*, int, int, int, int, int, floa
 DECL int b200_attn_bwd(const void*, const void*, const void*, const float*, void*, float*, int, int, int, int, int,
                        float, const float*, cudaStream_t);
 DECL void b200_gemm2_set_rope(const float*, int, int, int);
-DECL void b200_gemm2_set_push(void* const*, long long, long long, int);
+DECL void b200_gemm2_set_push(void* const*, long long, long long, int, int);
 DECL int b200_p2p_push_range(const void*, void* const*, long long, long long, long long, int, cudaStream_t);
 DECL int b200_p2p_allgather(const void* const*, void*, long long, int, int, cudaStream_t);
 DECL int b200_reduce_scatter(const void* const*, float*, long long, long long, int, int, int, float, float*,
                              cudaStream_t);
 DECL int b200_allreduce_inplace(void* const*, long long, int, int, int, float, float*, cudaStream_t);
-DECL int b200_signal_barrier(uint32_t* const*, int, int, uint32_t, cudaStream_t);
+DECL int b200_signal_barrier(uint32_t* const*, int, int, uint32_t, int, int, cudaStream_t);
+DECL int b200_scalar_allreduce_bytes();
+DECL int b200_scalar_allreduce(uint8_t* const*, int, int, uint32_t, float*, int, cudaStream_t);
 DECL int b200_causal_conv1d_fwd(const void*, const void*, const void*, void*, int, int, int, int, int, cudaStream_t);
 DECL int b200_causal_conv1d_bwd(const void*, const void*, const void*, const void*, void*, float*, float*, int, int,
                                 int, int, int, cudaStream_t);
@@ -132,8 +134,7 @@ void gemm(const at::Tensor& a, const at::Tensor& b, at::Tensor& c, int64_t layou
   }
   TORCH_CHECK(epi != 3 || (g_gemm_2cta && M >= 256 && layout == 0 && c.scalar_type() == at::kBFloat16),
               "RoPE epilogue: CTA-pair kernel, nt layout, bf16 output only (call set_gemm_rope first)");
-  TORCH_CHECK(epi != 4 || (g_gemm_2cta && M >= 256 && layout == 2 && c.scalar_type() == at::kBFloat16),
-              "push epilogue (experimental): CTA-pair kernel, tn layout, bf16 only (call set_gemm_push first)");
+  TORCH_CHECK(epi != 4, "push epilogue: use gemm_push (no output tensor)");
   // CTA-pair kernel (cta_group::2, 256x256 tiles) for anything with at least one full pair tile of rows
   if (g_gemm_2cta && M >= 256) {
     check(b200_gemm2_bf16(a.data_ptr(), b.data_ptr(), c.data_ptr(), r, M, N, K, a.stride(0), b.stride(0), c.stride(0),
@@ -395,10 +396,20 @@ void allreduce_inplace(const at::Tensor& peer_ptrs, int64_t numel, int64_t world
                                sumsq_out.has_value() ? sumsq_out->data_ptr<float>() : nullptr, cur_stream()),
         "allreduce_inplace");
 }
-void signal_barrier(const at::Tensor& pad_ptrs, int64_t world, int64_t rank, int64_t epoch, const at::Tensor& anchor) {
+// mode 0 = barrier, 1 = post only, 2 = wait only; slot_base selects the 32-slot channel of the signal pad
+void signal_barrier(const at::Tensor& pad_ptrs, int64_t world, int64_t rank, int64_t epoch, const at::Tensor& anchor,
+                    int64_t slot_base, int64_t mode) {
   c10::cuda::CUDAGuard guard(anchor.device());
-  check(b200_signal_barrier((uint32_t* const*)pad_ptrs.data_ptr(), world, rank, (uint32_t)epoch, cur_stream()),
-        "signal_barrier");
+  check(b200_signal_barrier((uint32_t* const*)pad_ptrs.data_ptr(), world, rank, (uint32_t)epoch, (int)slot_base, (int)mode,
+                            cur_stream()), "signal_barrier");
+}
+// one-shot sum of a few fp32 scalars across the group (in place), every rank gets the identical result
+void scalar_allreduce(const at::Tensor& buf_ptrs, int64_t world, int64_t rank, int64_t epoch, at::Tensor& inout) {
+  c10::cuda::CUDAGuard guard(inout.device());
+  need(inout, "inout", at::kFloat);
+  TORCH_CHECK(inout.is_contiguous());
+  check(b200_scalar_allreduce((uint8_t* const*)buf_ptrs.data_ptr(), (int)world, (int)rank, (uint32_t)epoch,
+                              inout.data_ptr<float>(), (int)inout.numel(), cur_stream()), "scalar_allreduce");
 }
 
 at::Tensor causal_conv1d_fwd(const at::Tensor& x, const at::Tensor& w, const c10::optional<at::Tensor>& b,
@@ -432,17 +443,30 @@ void set_attn_bwd_version(int64_t v) { b200_attn_set_bwd_version((int)v); }
 void set_gemm_2cta(bool on) { g_gemm_2cta = on; }
 bool get_gemm_2cta() { return g_gemm_2cta; }
 // GEMM with the all-gather of a unit's parameters fused in (comm warps over NVLink peer memory)
-void gemm_ag(const at::Tensor& a, const at::Tensor& b, at::Tensor& c, int64_t layout, int64_t epi,
+void gemm_ag(const at::Tensor& a, const at::Tensor& b, const c10::optional<at::Tensor>& c_opt, int64_t layout, int64_t epi,
              const c10::optional<at::Tensor>& residual, const at::Tensor& peer_ptrs, at::Tensor& full,
              int64_t shard_bytes, int64_t begin, int64_t end, int64_t world, int64_t rank, at::Tensor& flags,
              int64_t epoch, bool dependent) {
   c10::cuda::CUDAGuard guard(a.device());
   need(a, "a", at::kBFloat16);
   need(b, "b", at::kBFloat16);
-  need(c, "c", at::kBFloat16);
   need(flags, "flags", at::kInt);
   need_rowmajor2d(a, "a");
   need_rowmajor2d(b, "b");
+  if (epi == 4) {   // push epilogue: the output goes to the owners' staging slots (set_gemm_push), there is no C
+    TORCH_CHECK(layout == 2 && !c_opt.has_value(), "push epilogue: tn layout, no output tensor");
+    const int K = a.size(0), M = a.size(1), N = b.size(1);
+    TORCH_CHECK(b.size(0) == K && M >= 256 && K % 8 == 0 && N % 8 == 0 && M % 8 == 0);
+    check(b200_gemm2_ag_bf16(a.data_ptr(), b.data_ptr(), nullptr, nullptr, M, N, K, a.stride(0), b.stride(0), N, 0, 1, 1, 4,
+                             (const void* const*)peer_ptrs.data_ptr(), full.data_ptr(), (unsigned long long)shard_bytes,
+                             (unsigned long long)begin, (unsigned long long)end, (int)world, (int)rank,
+                             (uint32_t*)flags.data_ptr(), (uint32_t)epoch, dependent ? 1 : 0, cur_stream()),
+          "gemm2_ag_push_bf16_tcgen05");
+    return;
+  }
+  TORCH_CHECK(c_opt.has_value(), "gemm_ag: output tensor required");
+  at::Tensor c = *c_opt;
+  need(c, "c", at::kBFloat16);
   need_rowmajor2d(c, "c");
   int M, N, K, a_mn = 0, b_mn = 0;
   if (layout == 0) { M = a.size(0); K = a.size(1); N = b.size(0); TORCH_CHECK(b.size(1) == K); }
@@ -462,6 +486,19 @@ void gemm_ag(const at::Tensor& a, const at::Tensor& b, at::Tensor& c, int64_t la
                            (unsigned long long)shard_bytes, (unsigned long long)begin, (unsigned long long)end, (int)world,
                            (int)rank, (uint32_t*)flags.data_ptr(), (uint32_t)epoch, dependent ? 1 : 0, cur_stream()),
         "gemm2_ag_bf16_tcgen05");
+}
+// wgrad GEMM (tn: dW[M,N] = a[K,M]^T b[K,N]) whose epilogue pushes every tile to the owning rank's staging slot
+void gemm_push(const at::Tensor& a, const at::Tensor& b) {
+  c10::cuda::CUDAGuard guard(a.device());
+  need(a, "a", at::kBFloat16);
+  need(b, "b", at::kBFloat16);
+  need_rowmajor2d(a, "a");
+  need_rowmajor2d(b, "b");
+  const int K = a.size(0), M = a.size(1), N = b.size(1);
+  TORCH_CHECK(b.size(0) == K && g_gemm_2cta && M >= 256 && K % 8 == 0 && N % 8 == 0 && M % 8 == 0,
+              "push epilogue: CTA-pair kernel (M >= 256), dims multiples of 8");
+  check(b200_gemm2_bf16(a.data_ptr(), b.data_ptr(), nullptr, nullptr, M, N, K, a.stride(0), b.stride(0), N, 0, 1, 1, 4, 0,
+                        cur_stream()), "gemm2_push_bf16_tcgen05");
 }
 void p2p_gather_range(const at::Tensor& peer_ptrs, at::Tensor& full, int64_t shard_bytes, int64_t begin, int64_t end) {
   c10::cuda::CUDAGuard guard(full.device());
@@ -720,7 +757,10 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("p2p_allgather", &p2p_allgather);
   m.def("reduce_scatter", &reduce_scatter);
   m.def("allreduce_inplace", &allreduce_inplace);
-  m.def("signal_barrier", &signal_barrier);
+  m.def("signal_barrier", &signal_barrier, py::arg("pad_ptrs"), py::arg("world"), py::arg("rank"), py::arg("epoch"),
+        py::arg("anchor"), py::arg("slot_base") = 0, py::arg("mode") = 0);
+  m.def("scalar_allreduce", &scalar_allreduce);
+  m.def("scalar_allreduce_bytes", []() { return (int64_t)b200_scalar_allreduce_bytes(); });
   m.def("causal_conv1d_fwd", &causal_conv1d_fwd);
   m.def("causal_conv1d_bwd", &causal_conv1d_bwd);
   m.def("set_reduce_ctas", [](int64_t n) { b200_comm_set_reduce_ctas((int)n); });
@@ -730,18 +770,18 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     b200_gemm2_set_rope(table.data_ptr<float>(), (int)S, (int)hd, (int)cols);
   });
   m.def("push_range", [](const at::Tensor& src, const at::Tensor& bases, int64_t n, int64_t off, int64_t rank) {
-    // EXPERIMENTAL: this rank's gradient elements [off, off + src.numel()) -> the owners' staging slots
+    // this rank's gradient elements [off, off + src.numel()) -> the owners' staging slots (norm gains / biases)
     c10::cuda::CUDAGuard guard(src.device());
     need(src, "src", at::kBFloat16);
     TORCH_CHECK(src.is_contiguous() && bases.scalar_type() == at::kLong && bases.is_cuda());
     check(b200_p2p_push_range(src.data_ptr(), (void* const*)bases.data_ptr(), n, off, src.numel(), (int)rank, cur_stream()),
           "p2p_push_range");
   });
-  m.def("set_gemm_push", [](const at::Tensor& bases, int64_t n, int64_t off, int64_t rank) {
-    // EXPERIMENTAL (docs/next_steps.md 2): int64 device table of every rank's staging-buffer base address
+  m.def("set_gemm_push", [](const at::Tensor& bases, int64_t n, int64_t off, int64_t rank, bool bulk) {
+    // int64 device table of every rank's staging-buffer base address (fused wgrad GEMM -> reduce-scatter)
     TORCH_CHECK(bases.is_cuda() && bases.scalar_type() == at::kLong && bases.is_contiguous(), "push table: int64 CUDA tensor");
-    b200_gemm2_set_push((void* const*)bases.data_ptr(), n, off, (int)rank);
-  });
+    b200_gemm2_set_push((void* const*)bases.data_ptr(), n, off, (int)rank, bulk ? 1 : 0);
+  }, py::arg("bases"), py::arg("n"), py::arg("off"), py::arg("rank"), py::arg("bulk") = true);
   m.def("ssd_scan_fwd", &ssd_scan_fwd);
   m.def("selective_scan_fwd", &selective_scan_fwd);
   m.def("selective_scan_bwd", &selective_scan_bwd);
@@ -751,6 +791,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("set_gemm_2cta", &set_gemm_2cta);
   m.def("get_gemm_2cta", &get_gemm_2cta);
   m.def("gemm_ag", &gemm_ag);
+  m.def("gemm_push", &gemm_push);
   m.def("p2p_gather_range", &p2p_gather_range);
   m.def("ts_mma_probe", &ts_mma_probe);
   m.def("launch_count", &launch_count);

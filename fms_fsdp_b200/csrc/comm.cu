@@ -39,23 +39,66 @@ B200_DEVINL uint4 ld_relaxed_v4(const void* p) {
   return r;
 }
 
-// pads[r] -> uint32[W] on rank r.  Rank `rank` posts `epoch` into slot [rank] of every peer's pad, then waits
-// until all W slots of its own pad have reached `epoch`.
-__global__ void signal_barrier_kernel(uint32_t* const* pads, int world, int rank, uint32_t epoch) {
+// pads[r] -> uint32 signal pad on rank r, organised as channels of 32 slots.  Rank `rank` posts `epoch` into slot
+// [slot_base + rank] of every peer's pad, then waits until slots [slot_base, slot_base + W) of its own pad have reached
+// `epoch`.  Channels keep barriers that are enqueued on different streams from observing each other's epochs.
+B200_DEVINL void spin_until(const uint32_t* flag, uint32_t epoch) {
+  uint64_t t0 = 0;
+  uint32_t spins = 0;
+  while ((int32_t)(ld_acquire_sys(flag) - epoch) < 0) {
+    if ((++spins & 0x3ff) == 0) {
+      uint64_t now = global_timer_ns();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 20000000000ull) __trap();  // 20 s: a peer died
+    }
+  }
+}
+
+__global__ void signal_barrier_kernel(uint32_t* const* pads, int world, int rank, uint32_t epoch, int slot_base) {
   const int p = threadIdx.x;
   if (p < world) {
     __threadfence_system();
-    st_release_sys(pads[p] + rank, epoch);
-    const uint32_t* mine = pads[rank] + p;
-    uint64_t t0 = 0;
-    uint32_t spins = 0;
-    while ((int32_t)(ld_acquire_sys(mine) - epoch) < 0) {
-      if ((++spins & 0x3ff) == 0) {
-        uint64_t now = global_timer_ns();
-        if (t0 == 0) t0 = now;
-        else if (now - t0 > 20000000000ull) __trap();  // 20 s: a peer died
-      }
-    }
+    st_release_sys(pads[p] + slot_base + rank, epoch);
+    spin_until(pads[rank] + slot_base + p, epoch);
+  }
+}
+
+// One-sided halves of the barrier: "my work up to here is visible" / "wait until every rank has posted".  Used for the
+// per-unit optimizer flags: rank r posts (unit u, step t) after its AdamW of unit u; whoever gathers unit u waits.
+__global__ void signal_post_kernel(uint32_t* const* pads, int world, int rank, uint32_t epoch, int slot_base) {
+  const int p = threadIdx.x;
+  if (p < world) {
+    __threadfence_system();
+    st_release_sys(pads[p] + slot_base + rank, epoch);
+  }
+}
+__global__ void signal_wait_kernel(uint32_t* const* pads, int world, int rank, uint32_t epoch, int slot_base) {
+  const int p = threadIdx.x;
+  if (p < world) spin_until(pads[rank] + slot_base + p, epoch);
+}
+
+// One-shot all-reduce (sum) of a few fp32 scalars over the signal pads (grad-norm: SURVEY.md N11 / section 5.8 item 5).
+// bufs[r] -> on rank r: float vals[2][32][MAXV] followed by uint32 flags[2][32]; parity = epoch & 1 double-buffers
+// the slots (a rank can only be one call ahead of the slowest peer).  Every rank sums in rank order, so all ranks
+// get bit-identical results.
+constexpr int SAR_MAXV = 8;
+__global__ void scalar_allreduce_kernel(uint8_t* const* bufs, int world, int rank, uint32_t epoch, float* inout, int nvals) {
+  const int p = threadIdx.x;
+  const int par = epoch & 1;
+  const size_t flags_off = (size_t)2 * 32 * SAR_MAXV * sizeof(float);
+  if (p < world) {
+    float* vals = reinterpret_cast<float*>(bufs[p]) + ((size_t)par * 32 + rank) * SAR_MAXV;
+    for (int i = 0; i < nvals; ++i) vals[i] = inout[i];
+    __threadfence_system();
+    st_release_sys(reinterpret_cast<uint32_t*>(bufs[p] + flags_off) + par * 32 + rank, epoch);
+    spin_until(reinterpret_cast<const uint32_t*>(bufs[rank] + flags_off) + par * 32 + p, epoch);
+  }
+  __syncthreads();
+  if (p < nvals) {
+    const float* mine = reinterpret_cast<const float*>(bufs[rank]) + (size_t)par * 32 * SAR_MAXV;
+    float acc = 0.f;
+    for (int r = 0; r < world; ++r) acc += *reinterpret_cast<const volatile float*>(mine + r * SAR_MAXV + p);
+    inout[p] = acc;
   }
 }
 
@@ -168,6 +211,45 @@ __global__ void __launch_bounds__(256) reduce_scatter_kernel(const void* const* 
   }
 }
 
+// Any group size (HSDP 2x3, 6-GPU jobs ...): peer table read per iteration instead of W unrolled base registers.
+template <bool SRC_BF16>
+__global__ void __launch_bounds__(256) reduce_scatter_dyn_kernel(const void* const* srcs, float* out, size_t n, size_t off,
+                                                                 int world, int rank, float scale, float* sumsq) {
+  __shared__ float sh[32];
+  constexpr int VEC = SRC_BF16 ? 8 : 4;
+  float ss = 0.f;
+  const size_t nvec = n / VEC;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (size_t)gridDim.x * blockDim.x) {
+    float acc[VEC];
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) acc[k] = 0.f;
+    for (int r = 0; r < world; ++r) {
+      const uint8_t* b = reinterpret_cast<const uint8_t*>(srcs[(rank + r) % world]) + off * (SRC_BF16 ? 2 : 4);
+      const uint4 v = ld_relaxed_v4(b + i * 16);
+      if constexpr (SRC_BF16) {
+        float2 a = unpack_bf16x2(v.x), bb = unpack_bf16x2(v.y), c = unpack_bf16x2(v.z), d = unpack_bf16x2(v.w);
+        acc[0] += a.x; acc[1] += a.y; acc[2] += bb.x; acc[3] += bb.y;
+        acc[4] += c.x; acc[5] += c.y; acc[6] += d.x; acc[7] += d.y;
+      } else {
+        acc[0] += __uint_as_float(v.x); acc[1] += __uint_as_float(v.y);
+        acc[2] += __uint_as_float(v.z); acc[3] += __uint_as_float(v.w);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) {
+      acc[k] *= scale;
+      ss += acc[k] * acc[k];
+    }
+    float4* o = reinterpret_cast<float4*>(out + i * VEC);
+    o[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    if constexpr (SRC_BF16) o[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+  }
+  if (sumsq) {
+    ss = block_sum256(ss, sh);
+    if (threadIdx.x == 0) atomicAdd(sumsq, ss);
+  }
+}
+
 // In-place reduction of this rank's slice [rank*n_slice, (rank+1)*n_slice) of a symmetric buffer (phase 1 of
 // a two-phase all-reduce; phase 2 is p2p_allgather on the same buffers after a barrier).
 template <bool IS_BF16, int W>
@@ -227,13 +309,75 @@ __global__ void __launch_bounds__(256) reduce_slice_inplace_kernel(void* const* 
   }
 }
 
+template <bool IS_BF16>
+__global__ void __launch_bounds__(256) reduce_slice_inplace_dyn_kernel(void* const* bufs, size_t n_slice, int world, int rank,
+                                                                      float scale, float* sumsq) {
+  __shared__ float sh[32];
+  constexpr int VEC = IS_BF16 ? 8 : 4;
+  constexpr int ES = IS_BF16 ? 2 : 4;
+  uint8_t* mine = reinterpret_cast<uint8_t*>(bufs[rank]) + (size_t)rank * n_slice * ES;
+  float ss = 0.f;
+  const size_t nvec = n_slice / VEC;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (size_t)gridDim.x * blockDim.x) {
+    float acc[VEC];
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) acc[k] = 0.f;
+    for (int r = 0; r < world; ++r) {
+      const uint8_t* b = reinterpret_cast<const uint8_t*>(bufs[(rank + r) % world]) + (size_t)rank * n_slice * ES;
+      const uint4 v = ld_relaxed_v4(b + i * 16);
+      if constexpr (IS_BF16) {
+        float2 a = unpack_bf16x2(v.x), bb = unpack_bf16x2(v.y), c = unpack_bf16x2(v.z), d = unpack_bf16x2(v.w);
+        acc[0] += a.x; acc[1] += a.y; acc[2] += bb.x; acc[3] += bb.y;
+        acc[4] += c.x; acc[5] += c.y; acc[6] += d.x; acc[7] += d.y;
+      } else {
+        acc[0] += __uint_as_float(v.x); acc[1] += __uint_as_float(v.y);
+        acc[2] += __uint_as_float(v.z); acc[3] += __uint_as_float(v.w);
+      }
+    }
+    uint4 o;
+    if constexpr (IS_BF16) {
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) acc[k] *= scale;
+      o.x = pack_bf16x2(acc[0], acc[1]); o.y = pack_bf16x2(acc[2], acc[3]);
+      o.z = pack_bf16x2(acc[4], acc[5]); o.w = pack_bf16x2(acc[6], acc[7]);
+      float2 a = unpack_bf16x2(o.x), bb = unpack_bf16x2(o.y), c = unpack_bf16x2(o.z), d = unpack_bf16x2(o.w);
+      ss += a.x * a.x + a.y * a.y + bb.x * bb.x + bb.y * bb.y + c.x * c.x + c.y * c.y + d.x * d.x + d.y * d.y;
+    } else {
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) {
+        acc[k] *= scale;
+        ss += acc[k] * acc[k];
+      }
+      o.x = __float_as_uint(acc[0]); o.y = __float_as_uint(acc[1]);
+      o.z = __float_as_uint(acc[2]); o.w = __float_as_uint(acc[3]);
+    }
+    *reinterpret_cast<uint4*>(mine + i * 16) = o;
+  }
+  if (sumsq) {
+    ss = block_sum256(ss, sh);
+    if (threadIdx.x == 0) atomicAdd(sumsq, ss);
+  }
+}
+
 }  // namespace b200
 
 using namespace b200;
 
-extern "C" int b200_signal_barrier(uint32_t* const* pads, int world, int rank, uint32_t epoch, cudaStream_t s) {
-  if (world > 32) return -1;
-  signal_barrier_kernel<<<1, 32, 0, s>>>(pads, world, rank, epoch);
+// mode: 0 = barrier (post + wait), 1 = post only, 2 = wait only
+extern "C" int b200_signal_barrier(uint32_t* const* pads, int world, int rank, uint32_t epoch, int slot_base, int mode,
+                                   cudaStream_t s) {
+  if (world > 32 || slot_base < 0) return -1;
+  if (mode == 0) signal_barrier_kernel<<<1, 32, 0, s>>>(pads, world, rank, epoch, slot_base);
+  else if (mode == 1) signal_post_kernel<<<1, 32, 0, s>>>(pads, world, rank, epoch, slot_base);
+  else signal_wait_kernel<<<1, 32, 0, s>>>(pads, world, rank, epoch, slot_base);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int b200_scalar_allreduce_bytes() { return 2 * 32 * SAR_MAXV * (int)sizeof(float) + 2 * 32 * (int)sizeof(uint32_t); }
+extern "C" int b200_scalar_allreduce(uint8_t* const* bufs, int world, int rank, uint32_t epoch, float* inout, int nvals,
+                                     cudaStream_t s) {
+  if (world > 32 || nvals < 1 || nvals > SAR_MAXV) return -1;
+  scalar_allreduce_kernel<<<1, 32, 0, s>>>(bufs, world, rank, epoch, inout, nvals);
   return (int)cudaGetLastError();
 }
 
@@ -288,9 +432,11 @@ extern "C" int b200_reduce_scatter(const void* const* srcs, float* out, long lon
   if (grid > g_reduce_max_ctas) grid = g_reduce_max_ctas;
   if (grid < 1) grid = 1;
   if (src_bf16) {
-    switch (world) { RS_CASE(true, 1) RS_CASE(true, 2) RS_CASE(true, 4) RS_CASE(true, 8) default: return -2; }
+    switch (world) { RS_CASE(true, 1) RS_CASE(true, 2) RS_CASE(true, 4) RS_CASE(true, 8)
+      default: reduce_scatter_dyn_kernel<true><<<grid, 256, 0, s>>>(srcs, out, (size_t)n, (size_t)off, world, rank, scale, sumsq); }
   } else {
-    switch (world) { RS_CASE(false, 1) RS_CASE(false, 2) RS_CASE(false, 4) RS_CASE(false, 8) default: return -2; }
+    switch (world) { RS_CASE(false, 1) RS_CASE(false, 2) RS_CASE(false, 4) RS_CASE(false, 8)
+      default: reduce_scatter_dyn_kernel<false><<<grid, 256, 0, s>>>(srcs, out, (size_t)n, (size_t)off, world, rank, scale, sumsq); }
   }
   return (int)cudaGetLastError();
 }
@@ -308,9 +454,11 @@ extern "C" int b200_allreduce_inplace(void* const* bufs, long long numel, int wo
   if (grid > 148 * 2) grid = 148 * 2;
   if (grid < 1) grid = 1;
   if (is_bf16) {
-    switch (world) { AR_CASE(true, 1) AR_CASE(true, 2) AR_CASE(true, 4) AR_CASE(true, 8) default: return -2; }
+    switch (world) { AR_CASE(true, 1) AR_CASE(true, 2) AR_CASE(true, 4) AR_CASE(true, 8)
+      default: reduce_slice_inplace_dyn_kernel<true><<<grid, 256, 0, s>>>(bufs, (size_t)n_slice, world, rank, scale, sumsq); }
   } else {
-    switch (world) { AR_CASE(false, 1) AR_CASE(false, 2) AR_CASE(false, 4) AR_CASE(false, 8) default: return -2; }
+    switch (world) { AR_CASE(false, 1) AR_CASE(false, 2) AR_CASE(false, 4) AR_CASE(false, 8)
+      default: reduce_slice_inplace_dyn_kernel<false><<<grid, 256, 0, s>>>(bufs, (size_t)n_slice, world, rank, scale, sumsq); }
   }
   return (int)cudaGetLastError();
 }

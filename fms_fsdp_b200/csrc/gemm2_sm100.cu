@@ -25,6 +25,10 @@ constexpr int PB_BYTES = C_BN * P_BK * 2;   // 16 KiB
 constexpr int P_STAGE_BYTES = PA_BYTES + PB_BYTES;
 constexpr int P_THREADS = 192;
 constexpr int P_SMEM = P_STAGES * P_STAGE_BYTES + 1024 + 256;
+// push epilogue: each epilogue warp stages 32 rows x 64 bf16 columns (128 B, row pitch 144 B: 16-byte accesses of a
+// quarter-warp hit 32 distinct banks) so that every row leaves the SM as ONE 128-byte bulk store over NVLink
+constexpr int PUSH_ROW_PITCH = 144;
+constexpr int PUSH_STAGE_BYTES = 4 * 32 * PUSH_ROW_PITCH;   // 18 KiB per CTA
 
 enum { P_EPI_STORE = 0, P_EPI_RESIDUAL = 1, P_EPI_ACCUM = 2, P_EPI_ROPE = 3, P_EPI_PUSH = 4 };
 
@@ -107,14 +111,21 @@ struct Gemm2Params {
   // (row % rope_S, (col % rope_hd) / 2) before the bf16 store; table is [S][hd/2][cos, sin] fp32
   const float* rope;
   int rope_S, rope_hd, rope_cols;
-  // P_EPI_PUSH (EXPERIMENTAL, not used by the engine yet; docs/next_steps.md section 2): the wgrad tile is not stored to C
-  // but pushed over NVLink into the staging buffer of the rank that OWNS that slice of the unit's flat gradient:
+  // P_EPI_PUSH (fused wgrad GEMM -> reduce-scatter): the wgrad tile is not stored to C but pushed over
+  // NVLink into the staging buffer of the rank that OWNS that slice of the unit's flat gradient:
   //   e = push_off + row * ldc + col ; owner = e / push_n ; dst = push_bases[owner] + push_rank * push_n + (e - owner * push_n)
-  // so that after a barrier each owner reduces `world` local slots (reduce-scatter with no NVLink traffic of its own).
+  // so that after one cross-rank flag round each owner sums `world` LOCAL slots (no NVLink traffic of its own).
+  // push_bulk = 1: rows are staged in shared memory and leave as 128-byte cp.async.bulk stores (one per row and
+  // 64-column chunk); 0: 16-byte st.global per lane (kept as the reference path for the numerics test).
   void* const* push_bases;
   long long push_n, push_off;
-  int push_rank;
+  int push_rank, push_bulk;
 };
+
+B200_DEVINL void bulk_store_s2g(void* gdst, const void* ssrc, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+               ::"l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes) : "memory");
+}
 
 template <bool A_MN, bool B_MN, int EPI, typename OutT, bool AG>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(P_THREADS + (AG ? 32 * AG_WARPS : 0), 1)
@@ -302,6 +313,42 @@ gemm2_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         tmem_ld_32x32b_x32(taddr + c + 32, v1);
         tmem_ld_wait();
         const int col = n0 + c;
+        if constexpr (EPI == P_EPI_PUSH) {
+          if (p.push_bulk) {
+            uint8_t* stg = bar_base + 256 + (q * 32 + lane) * PUSH_ROW_PITCH;
+            // the bulk store issued from this staging row two chunks ago has finished READING it
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            if (row_ok && col < p.N) {
+              const int ncols = min(64, p.N - col);            // multiple of 8
+#pragma unroll
+              for (int g = 0; g < 8; ++g) {
+                const uint32_t* v = (g < 4) ? (v0 + g * 8) : (v1 + (g - 4) * 8);
+                uint4 o;
+                o.x = pack_bf16x2(__uint_as_float(v[0]), __uint_as_float(v[1]));
+                o.y = pack_bf16x2(__uint_as_float(v[2]), __uint_as_float(v[3]));
+                o.z = pack_bf16x2(__uint_as_float(v[4]), __uint_as_float(v[5]));
+                o.w = pack_bf16x2(__uint_as_float(v[6]), __uint_as_float(v[7]));
+                *reinterpret_cast<uint4*>(stg + g * 16) = o;
+              }
+              asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic smem writes -> async-proxy reads
+              const long long e = p.push_off + (long long)row * p.ldc + col;
+              if (ncols == 64 && (e & 63) == 0 && (p.push_n & 63) == 0) {
+                const long long owner = e / p.push_n;
+                bulk_store_s2g(reinterpret_cast<__nv_bfloat16*>(p.push_bases[owner]) +
+                                   ((long long)p.push_rank * p.push_n + (e - owner * p.push_n)), stg, 128);
+              } else {   // a chunk that may straddle two owners / a ragged right edge: one 16-byte store per vector
+                for (int g = 0; g * 8 < ncols; ++g) {
+                  const long long e8 = e + g * 8;
+                  const long long owner = e8 / p.push_n;
+                  bulk_store_s2g(reinterpret_cast<__nv_bfloat16*>(p.push_bases[owner]) +
+                                     ((long long)p.push_rank * p.push_n + (e8 - owner * p.push_n)), stg + g * 16, 16);
+                }
+              }
+              asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+            continue;
+          }
+        }
         if (row_ok && col < p.N) {
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
@@ -323,7 +370,7 @@ gemm2_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                   uint4 o;
                   o.x = pack_bf16x2(f[0], f[1]); o.y = pack_bf16x2(f[2], f[3]);
                   o.z = pack_bf16x2(f[4], f[5]); o.w = pack_bf16x2(f[6], f[7]);
-                  *reinterpret_cast<uint4*>(dst) = o;     // peer (or local) store; made visible by the barrier that follows
+                  *reinterpret_cast<uint4*>(dst) = o;     // peer (or local) store; made visible by the flag round that follows
                   continue;
                 }
                 if constexpr (EPI == P_EPI_ROPE) {
@@ -378,6 +425,7 @@ gemm2_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       if (lane == 0) mbar_arrive_leader(&tempty_bar[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
+    if constexpr (EPI == P_EPI_PUSH) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all pushed rows are out
   }
 
   tc_fence_before();
@@ -393,31 +441,33 @@ template <bool A_MN, bool B_MN, int EPI, typename OutT>
 static int launch2_ag(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gemm2Params& p, const AgParams& ag,
                       cudaStream_t stream) {
   auto kern = gemm2_bf16_tcgen05<A_MN, B_MN, EPI, OutT, true>;
+  constexpr int smem = P_SMEM + (EPI == P_EPI_PUSH ? PUSH_STAGE_BYTES : 0);
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return (int)e;
     configured = true;
   }
   // the comm warps of ALL SMs carry the gather, so always launch the full machine even for few tiles
   int pairs = sm_count() / 2;
-  kern<<<pairs * 2, P_THREADS + 32 * AG_WARPS, P_SMEM, stream>>>(tmA, tmB, p, ag);
+  kern<<<pairs * 2, P_THREADS + 32 * AG_WARPS, smem, stream>>>(tmA, tmB, p, ag);
   return (int)cudaGetLastError();
 }
 
 template <bool A_MN, bool B_MN, int EPI, typename OutT>
 static int launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gemm2Params& p, cudaStream_t stream) {
   auto kern = gemm2_bf16_tcgen05<A_MN, B_MN, EPI, OutT, false>;
+  constexpr int smem = P_SMEM + (EPI == P_EPI_PUSH ? PUSH_STAGE_BYTES : 0);
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return (int)e;
     configured = true;
   }
   int tiles = p.m_tiles * p.n_tiles;
   int pairs = sm_count() / 2;
   if (tiles < pairs) pairs = tiles;
-  kern<<<pairs * 2, P_THREADS, P_SMEM, stream>>>(tmA, tmB, p, AgParams{});
+  kern<<<pairs * 2, P_THREADS, smem, stream>>>(tmA, tmB, p, AgParams{});
   return (int)cudaGetLastError();
 }
 
@@ -438,10 +488,10 @@ static int dispatch2(const CUtensorMap& a, const CUtensorMap& b, const Gemm2Para
 // that owns the stream; keeps the two launcher signatures unchanged)
 static const float* g_rope_table = nullptr;
 static int g_rope_S = 1, g_rope_hd = 2, g_rope_cols = 0;
-// same convention for the (experimental) push epilogue
+// same convention for the push epilogue
 static void* const* g_push_bases = nullptr;
 static long long g_push_n = 1, g_push_off = 0;
-static int g_push_rank = 0;
+static int g_push_rank = 0, g_push_bulk = 1;
 
 }  // namespace b200
 
@@ -449,8 +499,8 @@ extern "C" void b200_gemm2_set_rope(const float* table, int S, int hd, int cols)
   b200::g_rope_table = table; b200::g_rope_S = S; b200::g_rope_hd = hd; b200::g_rope_cols = cols;
 }
 
-extern "C" void b200_gemm2_set_push(void* const* bases, long long n, long long off, int rank) {
-  b200::g_push_bases = bases; b200::g_push_n = n; b200::g_push_off = off; b200::g_push_rank = rank;
+extern "C" void b200_gemm2_set_push(void* const* bases, long long n, long long off, int rank, int bulk) {
+  b200::g_push_bases = bases; b200::g_push_n = n; b200::g_push_off = off; b200::g_push_rank = rank; b200::g_push_bulk = bulk;
 }
 
 extern "C" int b200_gemm2_bf16(const void* A, const void* B, void* C, const void* R, int M, int N, int K, int lda,
@@ -471,6 +521,7 @@ extern "C" int b200_gemm2_bf16(const void* A, const void* B, void* C, const void
   p.n_tiles = (N + P_BN - 1) / P_BN;
   p.rope = g_rope_table; p.rope_S = g_rope_S; p.rope_hd = g_rope_hd; p.rope_cols = g_rope_cols;
   p.push_bases = g_push_bases; p.push_n = g_push_n; p.push_off = g_push_off; p.push_rank = g_push_rank;
+  p.push_bulk = g_push_bulk;
   if (epi == P_EPI_ROPE) {
     if (a_mn || b_mn || out_fp32 || !p.rope || (p.rope_hd % 8) || (p.rope_cols % 8)) return -8;
     return launch2<false, false, P_EPI_ROPE, __nv_bfloat16>(tmA, tmB, p, stream);
@@ -510,7 +561,8 @@ extern "C" int b200_gemm2_ag_bf16(const void* A, const void* B, void* C, const v
   p.m_tiles = (M + P_BM - 1) / P_BM;
   p.n_tiles = (N + P_BN - 1) / P_BN;
   p.rope = g_rope_table; p.rope_S = g_rope_S; p.rope_hd = g_rope_hd; p.rope_cols = g_rope_cols;
-  p.push_bases = nullptr; p.push_n = 1; p.push_off = 0; p.push_rank = 0;
+  p.push_bases = g_push_bases; p.push_n = g_push_n; p.push_off = g_push_off; p.push_rank = g_push_rank;
+  p.push_bulk = g_push_bulk;
   AgParams ag;
   ag.peer_shards = peer_shards; ag.full = (uint8_t*)full; ag.shard_bytes = shard_bytes; ag.begin = begin; ag.end = end;
   ag.world = world; ag.rank = rank; ag.flags = flags; ag.epoch = epoch; ag.dependent = dependent;
@@ -524,7 +576,14 @@ extern "C" int b200_gemm2_ag_bf16(const void* A, const void* B, void* C, const v
   }
   if (!a_mn && !b_mn) { if (epi == P_EPI_RESIDUAL) AGL(false, false, P_EPI_RESIDUAL); AGL(false, false, P_EPI_STORE); }
   if (!a_mn && b_mn)  { if (epi == P_EPI_RESIDUAL) AGL(false, true, P_EPI_RESIDUAL);  AGL(false, true, P_EPI_STORE); }
-  if (a_mn && b_mn)   { if (epi == P_EPI_ACCUM) AGL(true, true, P_EPI_ACCUM);        AGL(true, true, P_EPI_STORE); }
+  if (a_mn && b_mn) {
+    if (epi == P_EPI_PUSH) {   // wgrad that pushes its tiles to the owners AND carries the next unit's all-gather
+      if (!p.push_bases || p.push_n <= 0 || (p.push_n % 8) || (p.push_off % 8) || (ldc % 8)) return -9;
+      AGL(true, true, P_EPI_PUSH);
+    }
+    if (epi == P_EPI_ACCUM) AGL(true, true, P_EPI_ACCUM);
+    AGL(true, true, P_EPI_STORE);
+  }
 #undef AGL
   return -7;
 }

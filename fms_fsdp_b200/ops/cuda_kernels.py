@@ -82,7 +82,7 @@ def _try_fused_gather(a, b, layout, out, epi, residual) -> bool:
     req = _AG_QUEUE[0]
     M = a.shape[1] if layout == "tn" else a.shape[0]
     ok = (M >= 256 and out.dtype == torch.bfloat16 and _C.get_gemm_2cta()
-          and ((layout in ("nt", "nn") and epi in (0, 1)) or (layout == "tn" and epi in (0, 2))
+          and ((layout in ("nt", "nn") and epi in (0, 1)) or (layout == "tn" and epi in (0, 2, 4))
                or (layout == "nt" and epi == 3)))
     if ok and req["dependent"]:
         lo = req["full"].data_ptr() + req["begin"]
@@ -100,7 +100,7 @@ def _try_fused_gather(a, b, layout, out, epi, residual) -> bool:
         take = int(w.numel() * w.element_size() * split)
         take = max(_AG_CHUNK, (take + _AG_CHUNK - 1) // _AG_CHUNK * _AG_CHUNK)
         hi = min(end, begin + take)
-    _C.gemm_ag(a, b, out, _LAYOUT[layout], epi, residual, req["table"], req["full"], req["shard_bytes"], begin,
+    _C.gemm_ag(a, b, None if epi == 4 else out, _LAYOUT[layout], epi, residual, req["table"], req["full"], req["shard_bytes"], begin,
                hi, req["world"], req["rank"], req["flags"], req["epoch"], bool(req["dependent"]))
     AG_STATS["carrier_gemms"] += 1
     if hi >= end:
@@ -113,24 +113,46 @@ def _try_fused_gather(a, b, layout, out, epi, residual) -> bool:
 
 
 class PushTarget:
-    """EXPERIMENTAL (docs/next_steps.md 2, FMS_B200_PUSH_RS=1): "output" of a wgrad GEMM whose epilogue writes every
-    tile into the staging slots of the rank that owns that slice of the unit's flat gradient (fused GEMM ->
-    reduce-scatter).  ``table``: int64 device tensor of the ranks' staging-buffer addresses; ``n``: elements per shard;
-    ``off``: element offset of this weight inside the flat unit."""
-    __slots__ = ("table", "n", "off", "rank", "shape", "_dummy")
+    """"Output" of a wgrad GEMM whose epilogue writes every tile into the staging slots of the rank that owns that
+    slice of the unit's flat gradient (fused GEMM -> reduce-scatter; ``csrc/gemm2_sm100.cu`` P_EPI_PUSH).
+    ``table``: int64 device tensor of the ranks' staging-buffer addresses; ``n``: elements per shard; ``off``: element
+    offset of this weight inside the flat unit."""
+    __slots__ = ("table", "n", "off", "rank", "shape", "dtype")
 
-    def __init__(self, table, n, off, rank, shape, device):
+    def __init__(self, table, n, off, rank, shape, device=None):
         self.table, self.n, self.off, self.rank, self.shape = table, int(n), int(off), int(rank), tuple(shape)
-        self._dummy = torch.empty(8, dtype=torch.bfloat16, device=device).as_strided(self.shape, (self.shape[1], 1))
+        self.dtype = torch.bfloat16
+
+    def numel(self):
+        return self.shape[0] * self.shape[1]
+
+    def element_size(self):
+        return 2
+
+
+# 1 = rows leave the SM as 128-byte cp.async.bulk stores staged through shared memory; 0 = 16-byte st.global per lane
+PUSH_BULK = os.environ.get("FMS_B200_PUSH_BULK", "1") == "1"
+PUSH_STATS = {"gemms": 0, "with_gather": 0}
+
+
+def push_eligible_shape(shape) -> bool:
+    """Weight shapes the push epilogue handles (CTA-pair wgrad GEMM, 16-byte vectors never straddle an owner)."""
+    return len(shape) == 2 and shape[0] >= 256 and shape[0] % 8 == 0 and shape[1] % 8 == 0
 
 
 def _gemm_push(a, b, tgt: PushTarget):
     M, N = a.shape[1], b.shape[1]
-    if (a.dtype != torch.bfloat16 or b.dtype != torch.bfloat16 or (M, N) != tgt.shape or M < 256 or not _C.get_gemm_2cta()
-            or M % 8 or N % 8 or a.shape[0] % 8):
+    if (a.dtype != torch.bfloat16 or b.dtype != torch.bfloat16 or (M, N) != tgt.shape or not push_eligible_shape((M, N))
+            or not _C.get_gemm_2cta() or a.shape[0] % 8):
         raise RuntimeError(f"wgrad {tuple(a.shape)}^T x {tuple(b.shape)} cannot use the push epilogue")
-    _C.set_gemm_push(tgt.table, tgt.n, tgt.off, tgt.rank)
-    _C.gemm(a if a.stride(-1) == 1 else a.contiguous(), b if b.stride(-1) == 1 else b.contiguous(), tgt._dummy, 2, 4, None)
+    a = a if a.stride(-1) == 1 else a.contiguous()
+    b = b if b.stride(-1) == 1 else b.contiguous()
+    _C.set_gemm_push(tgt.table, tgt.n, tgt.off, tgt.rank, PUSH_BULK)
+    PUSH_STATS["gemms"] += 1
+    if _AG_QUEUE and _try_fused_gather(a, b, "tn", tgt, 4, None):
+        PUSH_STATS["with_gather"] += 1      # the same kernel pushes its tiles out and pulls the next unit's weights in
+        return tgt
+    _C.gemm_push(a, b)
     return tgt
 
 

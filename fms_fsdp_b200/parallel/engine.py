@@ -157,9 +157,16 @@ class ShardedModel(nn.Module):
             self.s_opt = torch.cuda.Stream(self.device)
         else:
             self.s_compute = self.s_gather = self.s_reduce = self.s_opt = None
-        import os as _os0
-        self.async_optimizer = (self.is_cuda and self.mesh.shard_size == 1
-                                and _os0.environ.get("FMS_B200_ASYNC_OPT", "1") == "1")
+        # asynchronous optimizer: the (bandwidth-bound) AdamW of step t runs on ``s_opt`` under the forward GEMMs of step
+        # t+1; each unit's forward / gather waits only for that unit's own update.  Sharded runs additionally need every
+        # PEER's shard of the unit to be updated before it is gathered: per-unit cross-rank flags on the signal pads
+        # (fused collectives) replace the step barrier.
+        self.async_optimizer = (self.is_cuda and os.environ.get("FMS_B200_ASYNC_OPT", "1") == "1"
+                                and (self.mesh.shard_size == 1
+                                     or (self.coll.name == "fused" and os.environ.get("FMS_B200_ASYNC_OPT_SHARDED", "1") == "1")))
+        self._async_sharded = self.async_optimizer and self.mesh.shard_size > 1
+        self._opt_epoch = 0            # number of optimizer steps whose per-unit flags have been posted
+        self._nvtx_on = os.environ.get("FMS_B200_NVTX", "0") == "1"
 
         blocks, root_modules = model.engine_units()
         self.blocks: List[ShardUnit] = []
@@ -169,6 +176,10 @@ class ShardedModel(nn.Module):
         for i, blk in enumerate(blocks):
             u = self._make_unit(f"block{i}", [blk], param_init_fn, prefix_of=model)
             self.blocks.append(u)
+        for idx, u in enumerate(self.units):
+            u.index = idx
+        if self._async_sharded and len(self.units) > self.coll.max_units:
+            self.async_optimizer = self._async_sharded = False   # more units than flag channels: keep the step barrier
         # anything not covered by a unit is a bug in the model's protocol
         covered = {id(p) for u in self.units for _, p in u.params}
         missing = [n for n, p in model.named_parameters() if id(p) not in covered]
@@ -188,10 +199,15 @@ class ShardedModel(nn.Module):
         # the previous unit's reduce, 2 = they overlap) and whether backward re-gathers ride inside the GEMMs
         self._grad_pool_depth = int(os.environ.get("FMS_B200_GRAD_POOL", "1"))
         self.poison_released_params = os.environ.get("FMS_B200_POISON", "0") == "1"
-        # EXPERIMENTAL, off by default and not yet validated on hardware (docs/next_steps.md 2): wgrad GEMMs push their
-        # tiles to the owning ranks (fused GEMM -> reduce-scatter), the reduce becomes a local slot sum
-        self._push_rs = (os.environ.get("FMS_B200_PUSH_RS", "0") == "1" and self.coll.name == "fused"
+        # fused wgrad GEMM -> reduce-scatter: wgrad epilogues push their tiles straight into the owning
+        # rank's staging slots over NVLink; after one flag round per unit the owner sums `world` local slots.  Staging
+        # buffers rotate through a pool of ``_push_pool_depth`` (>= 2): buffer X of unit j may be pushed into again once
+        # the flag round of unit j+1 has completed on the reduce stream (=> every rank has summed X).
+        self._push_rs = (os.environ.get("FMS_B200_PUSH_RS", "1") == "1" and self.coll.name == "fused"
                          and self.mesh.shard_size > 1 and self.mp.reduce_dtype == torch.bfloat16)
+        self._push_pool_depth = max(2, int(os.environ.get("FMS_B200_PUSH_POOL", "3")))
+        self._push_pool: Dict[Tuple, List[_Buf]] = {}
+        self._push_pending: Optional[_Buf] = None     # summed locally, waiting for the next flag round to become reusable
         self._fuse_gather_bwd = os.environ.get("FMS_B200_FUSED_GATHER_BWD", "1") != "0"
         self._gnorm_sq = torch.zeros((), dtype=torch.float32, device=self.device)
         self._clip_coef: Optional[torch.Tensor] = None
@@ -343,6 +359,7 @@ class ShardedModel(nn.Module):
             # compute-stream gather: the small vector prefix now, the matrices inside the next GEMM kernel
             from fms_fsdp_b200.ops import cuda_kernels as CK
             self.s_compute.wait_event(buf.free_event)
+            self._wait_unit_updated(u, self.s_compute)
             es = u.lowp.element_size()
             mb, total = u.layout.matrix_begin * es, u.layout.total * es
             if mb > 0:
@@ -363,6 +380,7 @@ class ShardedModel(nn.Module):
         if self.is_cuda:
             with torch.cuda.stream(self.s_gather):
                 self.s_gather.wait_event(buf.free_event)
+                self._wait_unit_updated(u, self.s_gather)
                 self.coll.all_gather(u.lowp, buf.t)
                 u.ev_gathered.record(self.s_gather)
         else:
@@ -370,10 +388,23 @@ class ShardedModel(nn.Module):
         u.full = buf
         u.gather_pending = True
 
+    def _wait_unit_updated(self, u: ShardUnit, stream):
+        """Asynchronous sharded optimizer: the gather of ``u`` enqueued on ``stream`` (the current stream) must see this
+        rank's AND every peer's AdamW update of the unit (own: CUDA event; peers: cross-rank flags)."""
+        if self._async_sharded and self._opt_epoch > 0 and getattr(u, "_seen_epoch", 0) != self._opt_epoch:
+            stream.wait_event(u.ev_updated)
+            self.coll.wait_unit_updated(u.index, self._opt_epoch)
+            u._seen_epoch = self._opt_epoch   # the backward re-gather of the same step needs no second wait
+
+    def _nvtx(self, name: str):
+        if not self._nvtx_on:
+            return contextlib.nullcontext()
+        return torch.cuda.nvtx.range(name)
+
     def _wait_gather(self, u: ShardUnit, allow_pending_dependent: bool = False):
         if u.full is None:
             self._start_gather(u)
-        if self.async_optimizer:
+        if self.async_optimizer and not self._async_sharded:
             self.s_compute.wait_event(u.ev_updated)   # this unit's (asynchronous) AdamW update has landed
         if u.gather_pending:
             if getattr(u, "gather_fused", False):
@@ -401,34 +432,48 @@ class ShardedModel(nn.Module):
 
     # ------------------------------------------------------------------------------- gradients
     def _prepare_grads(self, u: ShardUnit):
-        if u.full_grad is None:
-            buf = self._acquire(self._grad_pool, u, self.mp.reduce_dtype, True, min_depth=self._grad_pool_depth)
-            u.full_grad = buf
-        if self.is_cuda:
-            self.s_compute.wait_event(u.full_grad.free_event)
         if self._push_rs and self._push_eligible(u):
             from fms_fsdp_b200.ops.cuda_kernels import PushTarget
-            staging = u.full_grad.t                       # same buffer, now laid out [src rank][shard elements]
+            if u.full_grad is None:
+                # staging buffer, laid out [src rank][shard elements]; symmetric (peers write into it)
+                u.full_grad = self._acquire(self._push_pool, u, self.mp.reduce_dtype, True, min_depth=self._push_pool_depth)
+            self.s_compute.wait_event(u.full_grad.free_event)   # every rank has finished summing its previous contents
+            staging = u.full_grad.t
             if getattr(u, "vec_grad", None) is None:
                 u.vec_grad = torch.zeros(u.layout.matrix_begin, dtype=staging.dtype, device=self.device)
             table, n, r = self.coll.push_table(staging), u.layout.shard_numel, self.mesh.shard_rank
             u.bind_grads_push(u.vec_grad, lambda s: PushTarget(table, n, s.offset, r, s.shape, self.device))
             u.pushed = True
             return
+        if u.full_grad is None:
+            buf = self._acquire(self._grad_pool, u, self.mp.reduce_dtype, True, min_depth=self._grad_pool_depth)
+            u.full_grad = buf
+        if self.is_cuda:
+            self.s_compute.wait_event(u.full_grad.free_event)
         u.pushed = False
         u.bind_grads(u.full_grad.t)
 
     def _push_eligible(self, u: ShardUnit) -> bool:
         """Block units whose every parameter is a norm-style vector or a weight matrix large enough for the CTA-pair
-        wgrad GEMM (LLaMA blocks); the root unit (embedding / tied or chunk-accumulated head) keeps the pull path."""
-        if u is self.root or u.recompute:
+        wgrad GEMM (LLaMA blocks); the root unit (embedding / tied or chunk-accumulated head) and units with other
+        parameter kinds (Mamba conv / SSM tensors) keep the pull path."""
+        if u is self.root:
             return False
         ok = getattr(u, "_push_ok", None)
         if ok is None:
-            ok = all(p.dim() == 1 or (p.dim() == 2 and p.shape[0] >= 256 and p.shape[0] % 8 == 0 and p.shape[1] % 8 == 0)
-                     for _, p in u.params) and u.layout.matrix_begin % 8 == 0
+            from fms_fsdp_b200.ops.cuda_kernels import push_eligible_shape
+            ok = (all(p.dim() == 1 or push_eligible_shape(tuple(p.shape)) for _, p in u.params)
+                  and u.layout.matrix_begin % 8 == 0 and u.layout.shard_numel % 8 == 0
+                  and getattr(u.modules[0], "engine_push_wgrad", True))
             u._push_ok = ok
         return ok
+
+    def _on_reduce_barrier(self):
+        """Called right after a flag round has been enqueued on the reduce stream: once it completes, every rank has
+        finished the slot sum that preceded it, so that staging buffer may be pushed into again."""
+        if self._push_pending is not None:
+            self._push_pending.free_event.record(self.s_reduce)
+            self._push_pending = None
 
     def _reduce(self, u: ShardUnit):
         u.collect_grads()
@@ -441,14 +486,21 @@ class ShardedModel(nn.Module):
             if m.shard_size == 1:
                 self.coll.all_reduce_full(u.full_grad.t, 1.0 / W, self._gnorm_sq)
             elif getattr(u, "pushed", False):
-                self.coll.push_vectors(u.vec_grad, u.full_grad.t)
-                self.coll.reduce_pushed(u.full_grad.t, u.grad_shard, 1.0 / W, self._gnorm_sq)
+                if u.layout.matrix_begin:
+                    self.coll.push_vectors(u.vec_grad, u.full_grad.t)
+                self.coll.reduce_pushed(u.full_grad.t, u.grad_shard, 1.0 / W, self._gnorm_sq,
+                                        on_barrier=self._on_reduce_barrier)
+                self._push_pending = u.full_grad      # reusable after the NEXT flag round on this stream
+            elif self._push_rs:
+                self.coll.reduce_scatter(u.full_grad.t, u.grad_shard, 1.0 / W, self._gnorm_sq,
+                                         on_barrier=self._on_reduce_barrier)
             else:
                 self.coll.reduce_scatter(u.full_grad.t, u.grad_shard, 1.0 / W, self._gnorm_sq)
-            if self.is_cuda:
+            if self.is_cuda and not getattr(u, "pushed", False):
                 u.full_grad.free_event.record(self.s_reduce)
         if m.shard_size > 1:
-            self._give_back(self._grad_pool, u, u.full_grad, self.mp.reduce_dtype)
+            self._give_back(self._push_pool if getattr(u, "pushed", False) else self._grad_pool, u, u.full_grad,
+                            self.mp.reduce_dtype)
             u.full_grad = None
 
     # ------------------------------------------------------------------------ forward / backward
@@ -474,10 +526,12 @@ class ShardedModel(nn.Module):
         fuse = self._fuse_gather and torch.is_grad_enabled()
         depth = 1 if fuse else self.prefetch_depth
         if self.is_cuda:
-            if fuse:
+            if self._async_sharded and self._opt_epoch > 0:
+                pass    # per-unit optimizer flags order every gather (``_wait_unit_updated``); no step barrier
+            elif fuse:
                 self.coll.begin_step()                 # cross-GPU barrier on the compute stream
             self.s_gather.wait_stream(self.s_compute)  # shards were just written by the optimizer
-            if not fuse:
+            if not fuse and not (self._async_sharded and self._opt_epoch > 0):
                 with torch.cuda.stream(self.s_gather):
                     self.coll.begin_step()             # ... on every rank (cross-GPU barrier, fused path)
         else:
@@ -601,7 +655,7 @@ class ShardedModel(nn.Module):
             self.coll.begin_step()
         self._gnorm_sq.zero_()
         self._clip_coef = None
-        self._start_gather(self.root)
+        self._start_gather(self.root, fuse=False)   # the step barrier above sits on the gather stream
         self._wait_gather(self.root)
         self._prepare_grads(self.root)
         with torch.enable_grad():
@@ -637,7 +691,12 @@ class ShardedModel(nn.Module):
         total = self._gnorm_sq.clone()
         self.coll.all_reduce_scalar(total, over="shard")
         norm = total.sqrt()
-        self._clip_coef = torch.clamp(max_norm / (norm + 1e-6), max=1.0)
+        # engine-owned scalar: the asynchronous optimizer's kernels on ``s_opt`` read it after this call returns, so it
+        # must not be a temporary the caching allocator could hand to the next step's compute-stream allocations
+        if getattr(self, "_clip_coef_buf", None) is None:
+            self._clip_coef_buf = torch.ones((), dtype=torch.float32, device=self.device)
+        torch.clamp(max_norm / (norm + 1e-6), max=1.0, out=self._clip_coef_buf)
+        self._clip_coef = self._clip_coef_buf
         self.last_grad_norm = norm
         return norm
 

@@ -6,12 +6,18 @@ parameter / gradient paths (SURVEY.md §5.8 "B200-native design").
   table of the W peer addresses;
 * ``all_gather``      = pull kernel (``csrc/comm.cu::p2p_allgather_kernel``): every rank copies the 7 remote
   shards with 16-byte peer loads, rotated start so all inbound NVLink flows are busy;
-* ``reduce_scatter``  = one-shot pull-reduce: rank r sums slice r of all W gradient buffers in fp32, scales by
-  1/world, writes the fp32 shard and accumulates ||g||^2 in the same pass (K11 folded into N8);
+* gradients of LLaMA-style blocks never exist unsharded: the wgrad GEMM epilogue PUSHES each tile into the owning
+  rank's staging slot ``[src rank][shard]`` (``csrc/gemm2_sm100.cu`` ``P_EPI_PUSH``); after ONE cross-rank flag round
+  per unit the owner sums its ``world`` local slots in fp32, scales by 1/world, writes the fp32 shard and accumulates
+  ||g||^2 in the same pass (``reduce_pushed``; K11 folded into N8) -- no NVLink traffic outside the GEMMs;
+* ``reduce_scatter``  = one-shot pull-reduce for everything else (root unit, Mamba blocks): rank r sums slice r of all
+  W gradient buffers;
 * HSDP replica all-reduce / DDP all-reduce = two-phase (reduce own slice in place, barrier, gather slices);
-* ordering = signal-pad barriers (``st.release.sys`` / ``ld.acquire.sys``) enqueued on the same streams.
+* ordering = signal-pad flags (``st.release.sys`` / ``ld.acquire.sys``) enqueued on the same streams; the pad has
+  32-slot channels so flag rounds of different streams never see each other's epochs;
+* the grad-norm scalar = a one-shot all-reduce kernel over the same pads (``scalar_allreduce``).
 
-Only scalars (grad-norm) and checkpoint metadata still travel through c10d.
+Only checkpoint metadata and the report-interval statistics still travel through c10d.
 """
 from __future__ import annotations
 
@@ -30,6 +36,11 @@ from fms_fsdp_b200.parallel.mesh import DPMesh
 class _SymGroup:
     """Symmetric allocations + barrier state for one process group."""
 
+    # signal-pad channels (32 slots each): 0 = step / stream-ordered barriers on the compute or gather stream,
+    # 1 = reduce stream, 2 = replica all-reduce, UNIT_CH0 + i = "optimizer updated unit i" flags
+    N_CHANNELS = 512
+    CH_STEP, CH_REDUCE, CH_AUX, UNIT_CH0 = 0, 1, 2, 8
+
     def __init__(self, group, size: int, my_index: int, device: torch.device):
         import torch.distributed._symmetric_memory as symm_mem
         self.symm_mem = symm_mem
@@ -37,10 +48,13 @@ class _SymGroup:
         self.tables: Dict[int, Tuple[torch.Tensor, list]] = {}  # data_ptr -> (device ptr table, host ptr list)
         self.regions = []  # (base address, bytes, peer base addresses)
         self._keep = []
-        self.epoch = 0
-        pad = self.alloc(64, torch.int32)
+        self.epochs: Dict[int, int] = {}
+        pad = self.alloc(32 * self.N_CHANNELS, torch.int32)
         pad.zero_()
         self.pad_table = self.tables[pad.data_ptr()][0]
+        self._sar_buf = self.alloc(1024, torch.int32)   # scalar all-reduce slots (csrc/comm.cu: 2304 bytes)
+        self._sar_buf.zero_()
+        self._sar_epoch = 0
         torch.cuda.synchronize(device)
         dist.barrier(group=group)
 
@@ -74,9 +88,24 @@ class _SymGroup:
         return torch.tensor([p + off + byte_offset_per_peer(i) for i, p in enumerate(ptrs)], dtype=torch.int64,
                             device=self.device)
 
-    def barrier(self, C, anchor: torch.Tensor):
-        self.epoch += 1
-        C.signal_barrier(self.pad_table, self.size, self.index, self.epoch, anchor)
+    def barrier(self, C, anchor: torch.Tensor, channel: int = 0):
+        """All ranks of the group have reached this point of the current stream (flag round on ``channel``)."""
+        e = self.epochs.get(channel, 0) + 1
+        self.epochs[channel] = e
+        C.signal_barrier(self.pad_table, self.size, self.index, e, anchor, 32 * channel, 0)
+
+    def post(self, C, anchor: torch.Tensor, channel: int, epoch: int):
+        """One-sided: everything this rank enqueued before is visible to whoever ``wait``s for (channel, epoch)."""
+        C.signal_barrier(self.pad_table, self.size, self.index, int(epoch), anchor, 32 * channel, 1)
+
+    def wait(self, C, anchor: torch.Tensor, channel: int, epoch: int):
+        C.signal_barrier(self.pad_table, self.size, self.index, int(epoch), anchor, 32 * channel, 2)
+
+    def scalar_allreduce(self, C, t: torch.Tensor):
+        """In-place sum of up to 8 fp32 scalars over the group: one tiny kernel, identical result on every rank."""
+        assert int(C.scalar_allreduce_bytes()) <= self._sar_buf.numel() * 4
+        self._sar_epoch += 1
+        C.scalar_allreduce(self.tables[self._sar_buf.data_ptr()][0], self.size, self.index, self._sar_epoch, t)
 
 
 class FusedCollectives:
@@ -93,6 +122,7 @@ class FusedCollectives:
         self._ag_state: Dict[int, list] = {}
         # CTA cap of the reduce kernels (csrc/comm.cu); throttling them was measured slower (2 GPUs: 354 -> 361 ms/step)
         self.C.set_reduce_ctas(int(os.environ.get("FMS_B200_REDUCE_CTAS", "296")))
+        self._own_scalar = os.environ.get("FMS_B200_OWN_SCALAR_ALLREDUCE", "1") == "1"
 
     # ---- allocation ---------------------------------------------------------------------------
     def alloc_shard(self, numel: int, dtype: torch.dtype) -> torch.Tensor:
@@ -126,7 +156,21 @@ class FusedCollectives:
     def begin_step(self):
         """All ranks' optimizer updates are visible before anyone gathers (enqueue on the gather stream)."""
         if self.shard is not None:
-            self.shard.barrier(self.C, self._anchor)
+            self.shard.barrier(self.C, self._anchor, _SymGroup.CH_STEP)
+
+    # per-unit optimizer flags (asynchronous sharded AdamW): rank r posts (unit, step) after updating its shard of the
+    # unit; a gather of that unit waits until every shard rank has posted
+    def post_unit_updated(self, unit_index: int, step: int):
+        if self.shard is not None:
+            self.shard.post(self.C, self._anchor, _SymGroup.UNIT_CH0 + unit_index, step)
+
+    def wait_unit_updated(self, unit_index: int, step: int):
+        if self.shard is not None:
+            self.shard.wait(self.C, self._anchor, _SymGroup.UNIT_CH0 + unit_index, step)
+
+    @property
+    def max_units(self) -> int:
+        return _SymGroup.N_CHANNELS - _SymGroup.UNIT_CH0
 
     def all_gather(self, shard: torch.Tensor, full: torch.Tensor):
         if self.shard is None:
@@ -159,17 +203,20 @@ class FusedCollectives:
                     dependent=bool(dependent))
 
     # ---- gradient path ------------------------------------------------------------------------
-    def reduce_scatter(self, full: torch.Tensor, shard32: torch.Tensor, scale: float, sumsq: Optional[torch.Tensor]):
+    def reduce_scatter(self, full: torch.Tensor, shard32: torch.Tensor, scale: float, sumsq: Optional[torch.Tensor],
+                       on_barrier=None):
         g = self.shard
-        g.barrier(self.C, self._anchor)  # every rank's wgrads for this unit are complete
+        g.barrier(self.C, self._anchor, _SymGroup.CH_REDUCE)  # every rank's wgrads for this unit are complete
+        if on_barrier is not None:
+            on_barrier()
         hsdp = self.replica is not None
         self.C.reduce_scatter(g.table_of(full), shard32, g.index * shard32.numel(), g.size, g.index,
                               full.dtype == torch.bfloat16, float(scale), None if hsdp else sumsq)
-        g.barrier(self.C, self._anchor)  # peers are done reading my buffer before it is rewritten
+        g.barrier(self.C, self._anchor, _SymGroup.CH_REDUCE)  # peers are done reading my buffer before it is rewritten
         if hsdp:
             self._allreduce(self.replica, shard32, 1.0, sumsq)
 
-    # ---- EXPERIMENTAL push path (FMS_B200_PUSH_RS=1; docs/next_steps.md 2) -------------------------------------------
+    # ---- fused wgrad GEMM -> reduce-scatter (push) ----------------------------------------------------------------
     def push_table(self, staging: torch.Tensor) -> torch.Tensor:
         """Addresses of every shard-rank's copy of ``staging`` (layout [src_rank][shard elements])."""
         return self.shard.table_of(staging)
@@ -179,11 +226,17 @@ class FusedCollectives:
         g = self.shard
         self.C.push_range(vec, g.table_of(staging), staging.numel() // g.size, 0, g.index)
 
-    def reduce_pushed(self, staging: torch.Tensor, shard32: torch.Tensor, scale: float, sumsq: Optional[torch.Tensor]):
-        """After every rank pushed its wgrad tiles: barrier, LOCAL sum of the `world` slots, barrier (buffer reusable)."""
+    def reduce_pushed(self, staging: torch.Tensor, shard32: torch.Tensor, scale: float, sumsq: Optional[torch.Tensor],
+                      on_barrier=None):
+        """After every rank pushed its wgrad tiles: ONE flag round (all tiles of all ranks have landed in my slots),
+        then a LOCAL sum of the ``world`` slots.  There is no trailing barrier: a staging buffer is handed out again
+        only after a LATER flag round on this stream has completed (``on_barrier`` lets the engine record that), which
+        implies every rank has finished summing it."""
         g = self.shard
         n = shard32.numel()
-        g.barrier(self.C, self._anchor)   # all tiles of all ranks have landed in my slots
+        g.barrier(self.C, self._anchor, _SymGroup.CH_REDUCE)
+        if on_barrier is not None:
+            on_barrier()
         key = ("slots", staging.data_ptr())
         tab = self._slice_tables.get(key)
         if tab is None:
@@ -192,7 +245,6 @@ class FusedCollectives:
             self._slice_tables[key] = tab
         hsdp = self.replica is not None
         self.C.reduce_scatter(tab, shard32, 0, g.size, 0, staging.dtype == torch.bfloat16, float(scale), None if hsdp else sumsq)
-        g.barrier(self.C, self._anchor)   # nobody pushes into a buffer another rank is still reducing
         if hsdp:
             self._allreduce(self.replica, shard32, 1.0, sumsq)
 
@@ -211,24 +263,30 @@ class FusedCollectives:
             raise RuntimeError(f"all-reduce buffer of {n} elements is not a multiple of {unit}")
         es = buf.element_size()
         slice_bytes = n // g.size * es
-        g.barrier(self.C, self._anchor)
+        ch = _SymGroup.CH_AUX
+        g.barrier(self.C, self._anchor, ch)
         self.C.allreduce_inplace(g.table_of(buf), n, g.size, g.index, is_bf16, float(scale), None, self._anchor)
-        g.barrier(self.C, self._anchor)
+        g.barrier(self.C, self._anchor, ch)
         key = (buf.data_ptr(), g.size)
         tab = self._slice_tables.get(key)
         if tab is None:
             tab = g.table_of(buf, byte_offset_per_peer=lambda i: i * slice_bytes)
             self._slice_tables[key] = tab
         self.C.p2p_allgather(tab, buf, slice_bytes, g.size, g.index)
-        g.barrier(self.C, self._anchor)
+        g.barrier(self.C, self._anchor, ch)
         if sumsq is not None:
             kernels_for(buf).sumsq(buf, out=sumsq)
 
     def all_reduce_scalar(self, t: torch.Tensor, over: str = "shard"):
+        """Sum of one fp32 scalar (the squared grad-norm) over the shard group -- one-shot kernel over the signal pads
+        instead of an NCCL ring (measured 3.7 ms of launch + ring latency per step at 8 GPUs)."""
         m = self.mesh
         if over == "shard":
             if m.shard_size > 1:
-                dist.all_reduce(t, group=m.shard_group)
+                if self._own_scalar and t.dtype == torch.float32 and t.is_contiguous():
+                    self.shard.scalar_allreduce(self.C, t.view(-1))
+                else:
+                    dist.all_reduce(t, group=m.shard_group)
         elif m.world > 1:
             dist.all_reduce(t)
         return t

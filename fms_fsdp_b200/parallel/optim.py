@@ -36,21 +36,34 @@ class ShardedAdamW(torch.optim.Optimizer):
         eng = self.engine
         coef = eng._clip_coef
 
+        sharded_async = eng.async_optimizer and getattr(eng, "_async_sharded", False)
+        epoch = eng._opt_epoch + 1 if sharded_async else 0
+
         def update_all():
+            nvtx = eng._nvtx("optimizer") if hasattr(eng, "_nvtx") else None
+            if nvtx is not None:
+                nvtx.__enter__()
             for u in eng.units:  # root first, then blocks in forward order: the order the next forward needs them
                 K = kernels_for(u.master)
                 K.adamw_step(u.master, u.grad_shard, u.exp_avg, u.exp_avg_sq,
                              None if u.lowp is u.master else u.lowp, lr, b1, b2, eps, wd, self._step, coef)
                 if eng.async_optimizer:
                     u.ev_updated.record(eng.s_opt)
+                    if sharded_async:   # tell every shard rank that my slice of this unit is updated
+                        eng.coll.post_unit_updated(u.index, epoch)
+            if nvtx is not None:
+                nvtx.__exit__(None, None, None)
 
         if eng.async_optimizer:
             # Bandwidth-bound update on a side stream: it overlaps the next forward's (compute-bound) GEMMs; each
-            # unit's forward waits only for that unit's own update (``ShardedModel._wait_gather``).  Only when no
-            # peer reads our shards (shard group of 1) -- otherwise the cross-GPU step barrier orders everything.
+            # unit's forward waits only for that unit's own update (``ShardedModel._wait_gather``).  When peers read our
+            # shards (shard group > 1) each unit's update is followed by a cross-rank flag that the peers' gathers of that
+            # unit wait for (``ShardedModel._wait_unit_updated``) -- no step barrier.
             eng.s_opt.wait_stream(eng.s_compute)
             with torch.cuda.stream(eng.s_opt):
                 update_all()
+            if sharded_async:
+                eng._opt_epoch = epoch
         else:
             update_all()
         eng._clip_coef = None

@@ -98,38 +98,44 @@ if mode in ("all", "ag"):
     out["ag_gemm"] = res
     del fc
 
-if mode in ("push",):
-    # EXPERIMENTAL (docs/next_steps.md 2): wgrad GEMM whose epilogue pushes every tile into the OWNER rank's staging slot
-    # over NVLink, then a LOCAL slot reduction == reduce-scatter of the per-rank wgrads.  Not used by the engine yet.
+if mode in ("all", "push"):
+    # fused wgrad GEMM -> reduce-scatter: the GEMM epilogue pushes every tile into the OWNER rank's staging slot over
+    # NVLink (128-byte bulk stores, or 16-byte st.global as the reference), then a LOCAL slot sum == reduce-scatter.
     from fms_fsdp_b200.ops import cuda_kernels as CK
     mesh = build_mesh("fsdp")
     fc = FusedCollectives(mesh, dev)
     C = fc.C
-    T, N, Kd = 8192, 4096, 4096                      # dW [N, Kd] = dy^T x
-    total = N * Kd
+    T, N, Kd = 8192, 4096, 11008                     # dW [N, Kd] = dy^T x  (the down projection of Llama2-7B)
+    total = N * Kd // (world * 64) * (world * 64)
     n = total // world
     torch.manual_seed(100 + rank)
     dy = (torch.randn(T, N, device=dev) * 0.05).bfloat16(); x = (torch.randn(T, Kd, device=dev) * 0.05).bfloat16()
     staging = fc.shard.alloc(world * n, torch.bfloat16); staging.zero_()
     table = fc.shard.table_of(staging)               # base address of every rank's staging buffer
-    dummy = torch.empty(8, dtype=torch.bfloat16, device=dev).as_strided((N, Kd), (Kd, 1))
-    fc.shard.barrier(C, fc._anchor)
-    def push():
-        C.set_gemm_push(table, n, 0, rank)
-        C.gemm(dy, x, dummy, 2, 4, None)             # layout tn, epilogue 4 = push
-    push()
-    fc.shard.barrier(C, fc._anchor)                  # every rank's tiles have landed in my slots
     slots = torch.tensor([staging.data_ptr() + s_ * n * 2 for s_ in range(world)], dtype=torch.int64, device=dev)
     mine = torch.empty(n, dtype=torch.float32, device=dev)
-    C.reduce_scatter(slots, mine, 0, world, 0, True, 1.0, None)     # local 'world'-way sum of the slots
-    torch.cuda.synchronize()
     ref_local = CK.gemm(dy, x, "tn").float().reshape(-1)             # this rank's full wgrad (bf16-rounded like the push)
     dist.all_reduce(ref_local)
     ref = ref_local[rank * n:(rank + 1) * n]
-    res = dict(maxdiff=(mine - ref).abs().max().item(), absmax=ref.abs().max().item())
-    res["push_gemm_ms"] = timed(push)
+    res = {}
+    for bulk in (True, False):
+        staging.zero_()
+        fc.shard.barrier(C, fc._anchor)
+        def push():
+            C.set_gemm_push(table, n, 0, rank, bulk)
+            C.gemm_push(dy, x)                           # layout tn, push epilogue
+        push()
+        fc.shard.barrier(C, fc._anchor)                  # every rank's tiles have landed in my slots
+        C.reduce_scatter(slots, mine, 0, world, 0, True, 1.0, None)     # local 'world'-way sum of the slots
+        torch.cuda.synchronize()
+        key = "bulk" if bulk else "direct"
+        res[key] = dict(maxdiff=(mine - ref).abs().max().item(), absmax=ref.abs().max().item(), push_gemm_ms=timed(push))
     res["plain_gemm_ms"] = timed(lambda: CK.gemm(dy, x, "tn"))
-    res["local_reduce_ms"] = timed(lambda: C.reduce_scatter(slots, mine, 0, world, 0, True, 1.0, None))
+    res["local_slot_sum_ms"] = timed(lambda: C.reduce_scatter(slots, mine, 0, world, 0, True, 1.0, None))
+    res["pushed_MB_out"] = total * 2 * (world - 1) / world / 1e6
+    sc = torch.tensor([float(rank + 1)], device=dev)
+    fc.shard.scalar_allreduce(C, sc); torch.cuda.synchronize()
+    res["scalar_allreduce"] = [sc.item(), world * (world + 1) / 2]
     out["push_wgrad"] = res
     del fc
 
@@ -192,6 +198,10 @@ if mode in ("all", "engine", "gn"):
         a, ca = run("fused", strat, shard); b, cb = run("torch", strat, shard)
         out[f"engine_{strat}"] = dict(fused=a, torch=b, param_checksum=[ca, cb])
         if strat == "fsdp":
+            os.environ["FMS_B200_PUSH_RS"] = "0"; os.environ["FMS_B200_ASYNC_OPT_SHARDED"] = "0"
+            d_, cd = run("fused", strat, shard)
+            os.environ["FMS_B200_PUSH_RS"] = "1"; os.environ["FMS_B200_ASYNC_OPT_SHARDED"] = "1"
+            out["engine_fsdp_fused_pull_syncopt"] = dict(res=d_, checksum=cd)
             c, cc = run("fused", strat, shard, fused_gather="0")
             from fms_fsdp_b200.ops import cuda_kernels as CK
             out["engine_fsdp_fused_nogemmgather"] = dict(res=c, checksum=cc, ag_stats=dict(CK.AG_STATS))
