@@ -209,6 +209,8 @@ class ShardedModel(nn.Module):
         self._push_pool: Dict[Tuple, List[_Buf]] = {}
         self._push_pending: Optional[_Buf] = None     # summed locally, waiting for the next flag round to become reusable
         self._fuse_gather_bwd = os.environ.get("FMS_B200_FUSED_GATHER_BWD", "1") != "0"
+        if self._push_rs:
+            self._warm_push_pool()
         self._gnorm_sq = torch.zeros((), dtype=torch.float32, device=self.device)
         self._clip_coef: Optional[torch.Tensor] = None
         self._saved = None
@@ -467,6 +469,28 @@ class ShardedModel(nn.Module):
                   and getattr(u.modules[0], "engine_push_wgrad", True))
             u._push_ok = ok
         return ok
+
+    def _warm_push_pool(self):
+        """Allocate (and zero) every staging buffer of the push path NOW, followed by a cross-rank barrier.  Peers
+        write into these buffers, so a lazily allocated buffer's zero-fill on this rank's stream could land AFTER a
+        faster peer's first pushed tiles (found by the 2-GPU gradient check: every freshly allocated buffer of the
+        first backward lost part of the peer's contribution)."""
+        made = False
+        for u in self.blocks:
+            if not self._push_eligible(u):
+                continue
+            key = (u.layout.signature(), self.mp.reduce_dtype)
+            lst = self._push_pool.setdefault(key, [])
+            while len(lst) < self._push_pool_depth:
+                t = self.coll.alloc_full(u.layout.total, self.mp.reduce_dtype, symmetric=True)
+                self._pool_made[(id(self._push_pool), key)] = self._pool_made.get((id(self._push_pool), key), 0) + 1
+                lst.append(_Buf(t, self._event()))
+                made = True
+            if getattr(u, "vec_grad", None) is None:
+                u.vec_grad = torch.zeros(u.layout.matrix_begin, dtype=self.mp.reduce_dtype, device=self.device)
+        if made:
+            torch.cuda.synchronize(self.device)
+            self.coll.barrier()
 
     def _on_reduce_barrier(self):
         """Called right after a flag round has been enqueued on the reduce stream: once it completes, every rank has
