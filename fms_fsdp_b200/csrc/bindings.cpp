@@ -65,7 +65,7 @@ DECL int b200_attn_fwd(const void*, void*, float*, int, int, int, int, int, floa
 DECL int b200_attn_bwd(const void*, const void*, const void*, const float*, void*, float*, int, int, int, int, int,
                        float, const float*, cudaStream_t);
 DECL void b200_gemm2_set_rope(const float*, int, int, int);
-DECL void b200_gemm2_set_push(void* const*, long long, long long, int, int);
+DECL void b200_gemm2_set_push(void* const*, long long, long long, int, int, int);
 DECL int b200_p2p_push_range(const void*, void* const*, long long, long long, long long, int, cudaStream_t);
 DECL int b200_p2p_allgather(const void* const*, void*, long long, int, int, cudaStream_t);
 DECL int b200_reduce_scatter(const void* const*, float*, long long, long long, int, int, int, float, float*,
@@ -81,6 +81,7 @@ DECL int b200_causal_conv1d_bwd(const void*, const void*, const void*, const voi
 namespace {
 
 static int64_t g_launches = 0;
+static int g_reduce_ctas_default = 296;
 static bool g_gemm_2cta = true;
 
 inline cudaStream_t cur_stream() { return at::cuda::getCurrentCUDAStream().stream(); }
@@ -381,9 +382,10 @@ void p2p_allgather(const at::Tensor& peer_ptrs, at::Tensor& full, int64_t shard_
                            cur_stream()), "p2p_allgather");
 }
 void reduce_scatter(const at::Tensor& peer_ptrs, at::Tensor& out32, int64_t elem_offset, int64_t world, int64_t rank,
-                    bool src_bf16, double scale, const c10::optional<at::Tensor>& sumsq_out) {
+                    bool src_bf16, double scale, const c10::optional<at::Tensor>& sumsq_out, int64_t max_ctas) {
   c10::cuda::CUDAGuard guard(out32.device());
   need(out32, "out", at::kFloat);
+  b200_comm_set_reduce_ctas(max_ctas > 0 ? (int)max_ctas : g_reduce_ctas_default);
   check(b200_reduce_scatter((const void* const*)peer_ptrs.data_ptr(), out32.data_ptr<float>(), out32.numel(),
                             elem_offset, world, rank, src_bf16, (float)scale,
                             sumsq_out.has_value() ? sumsq_out->data_ptr<float>() : nullptr, cur_stream()),
@@ -755,7 +757,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("attn_bwd", &attn_bwd, py::arg("dout"), py::arg("qkv"), py::arg("o"), py::arg("lse"), py::arg("B"), py::arg("S"),
         py::arg("H"), py::arg("KVH"), py::arg("hd"), py::arg("scale"), py::arg("rope") = py::none());
   m.def("p2p_allgather", &p2p_allgather);
-  m.def("reduce_scatter", &reduce_scatter);
+  m.def("reduce_scatter", &reduce_scatter, py::arg("peer_ptrs"), py::arg("out32"), py::arg("elem_offset"), py::arg("world"),
+        py::arg("rank"), py::arg("src_bf16"), py::arg("scale"), py::arg("sumsq_out"), py::arg("max_ctas") = 0);
   m.def("allreduce_inplace", &allreduce_inplace);
   m.def("signal_barrier", &signal_barrier, py::arg("pad_ptrs"), py::arg("world"), py::arg("rank"), py::arg("epoch"),
         py::arg("anchor"), py::arg("slot_base") = 0, py::arg("mode") = 0);
@@ -763,7 +766,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("scalar_allreduce_bytes", []() { return (int64_t)b200_scalar_allreduce_bytes(); });
   m.def("causal_conv1d_fwd", &causal_conv1d_fwd);
   m.def("causal_conv1d_bwd", &causal_conv1d_bwd);
-  m.def("set_reduce_ctas", [](int64_t n) { b200_comm_set_reduce_ctas((int)n); });
+  m.def("set_reduce_ctas", [](int64_t n) { g_reduce_ctas_default = n < 1 ? 1 : (int)n; b200_comm_set_reduce_ctas((int)n); });
   m.def("set_gemm_rope", [](const at::Tensor& table, int64_t S, int64_t hd, int64_t cols) {
     need(table, "rope table", at::kFloat);
     TORCH_CHECK(table.is_contiguous() && table.numel() >= S * hd, "rope table must be [S, hd/2, 2] fp32");
@@ -777,11 +780,12 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     check(b200_p2p_push_range(src.data_ptr(), (void* const*)bases.data_ptr(), n, off, src.numel(), (int)rank, cur_stream()),
           "p2p_push_range");
   });
-  m.def("set_gemm_push", [](const at::Tensor& bases, int64_t n, int64_t off, int64_t rank, bool bulk) {
-    // int64 device table of every rank's staging-buffer base address (fused wgrad GEMM -> reduce-scatter)
+  m.def("set_gemm_push", [](const at::Tensor& bases, int64_t n, int64_t off, int64_t rank, bool bulk, int64_t rot_world) {
+    // int64 device table of every rank's staging-buffer base address (fused wgrad GEMM -> reduce-scatter);
+    // rot_world > 1 rotates the tile raster by rank / rot_world of a sweep (spreads the pushes over all owners)
     TORCH_CHECK(bases.is_cuda() && bases.scalar_type() == at::kLong && bases.is_contiguous(), "push table: int64 CUDA tensor");
-    b200_gemm2_set_push((void* const*)bases.data_ptr(), n, off, (int)rank, bulk ? 1 : 0);
-  }, py::arg("bases"), py::arg("n"), py::arg("off"), py::arg("rank"), py::arg("bulk") = true);
+    b200_gemm2_set_push((void* const*)bases.data_ptr(), n, off, (int)rank, bulk ? 1 : 0, (int)rot_world);
+  }, py::arg("bases"), py::arg("n"), py::arg("off"), py::arg("rank"), py::arg("bulk") = true, py::arg("rot_world") = 1);
   m.def("ssd_scan_fwd", &ssd_scan_fwd);
   m.def("selective_scan_fwd", &selective_scan_fwd);
   m.def("selective_scan_bwd", &selective_scan_bwd);

@@ -120,6 +120,11 @@ struct Gemm2Params {
   void* const* push_bases;
   long long push_n, push_off;
   int push_rank, push_bulk;
+  // every CTA pair starts its sweep `tile_rot` tiles into the raster (wraps around).  The push epilogue sets it to
+  // rank * tiles / world: all ranks run the same wgrad GEMM at the same time with the same raster, so without the
+  // rotation all W ranks write into the SAME owner's staging buffer at once (W -> 1 incast on that GPU's NVLink ingress,
+  // ~7 x 175 GB/s) while the other owners' links idle.
+  int tile_rot;
 };
 
 B200_DEVINL void bulk_store_s2g(void* gdst, const void* ssrc, uint32_t bytes) {
@@ -174,7 +179,7 @@ gemm2_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       uint32_t phase = 0;
       for (int t = pair; t < num_tiles; t += n_pairs) {
         int mt, nt;
-        tile_coords2(t, p.m_tiles, p.n_tiles, mt, nt);
+        tile_coords2((t + p.tile_rot) % num_tiles, p.m_tiles, p.n_tiles, mt, nt);
         const int m0 = mt * P_BM + (int)rank * C_BM;
         const int n0 = nt * P_BN + (int)rank * C_BN;
         for (int kb = 0; kb < num_kb; ++kb) {
@@ -296,7 +301,7 @@ gemm2_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     uint32_t acc_phase = 0;
     for (int t = pair; t < num_tiles; t += n_pairs) {
       int mt, nt;
-      tile_coords2(t, p.m_tiles, p.n_tiles, mt, nt);
+      tile_coords2((t + p.tile_rot) % num_tiles, p.m_tiles, p.n_tiles, mt, nt);
       const int m0 = mt * P_BM + (int)rank * C_BM;
       const int n0 = nt * P_BN;
       mbar_wait(&tfull_bar[acc], acc_phase);
@@ -491,7 +496,7 @@ static int g_rope_S = 1, g_rope_hd = 2, g_rope_cols = 0;
 // same convention for the push epilogue
 static void* const* g_push_bases = nullptr;
 static long long g_push_n = 1, g_push_off = 0;
-static int g_push_rank = 0, g_push_bulk = 1;
+static int g_push_rank = 0, g_push_bulk = 1, g_push_world = 1;
 
 }  // namespace b200
 
@@ -499,8 +504,10 @@ extern "C" void b200_gemm2_set_rope(const float* table, int S, int hd, int cols)
   b200::g_rope_table = table; b200::g_rope_S = S; b200::g_rope_hd = hd; b200::g_rope_cols = cols;
 }
 
-extern "C" void b200_gemm2_set_push(void* const* bases, long long n, long long off, int rank, int bulk) {
+// world > 1: rotate the tile raster by rank * tiles / world (0 / 1 = no rotation)
+extern "C" void b200_gemm2_set_push(void* const* bases, long long n, long long off, int rank, int bulk, int world) {
   b200::g_push_bases = bases; b200::g_push_n = n; b200::g_push_off = off; b200::g_push_rank = rank; b200::g_push_bulk = bulk;
+  b200::g_push_world = world < 1 ? 1 : world;
 }
 
 extern "C" int b200_gemm2_bf16(const void* A, const void* B, void* C, const void* R, int M, int N, int K, int lda,
@@ -522,6 +529,12 @@ extern "C" int b200_gemm2_bf16(const void* A, const void* B, void* C, const void
   p.rope = g_rope_table; p.rope_S = g_rope_S; p.rope_hd = g_rope_hd; p.rope_cols = g_rope_cols;
   p.push_bases = g_push_bases; p.push_n = g_push_n; p.push_off = g_push_off; p.push_rank = g_push_rank;
   p.push_bulk = g_push_bulk;
+  p.tile_rot = 0;
+  if (epi == P_EPI_PUSH && g_push_world > 1) {
+    const int per_band = P_GROUP_M * p.n_tiles, tiles = p.m_tiles * p.n_tiles;
+    const int bands = (tiles + per_band - 1) / per_band;
+    p.tile_rot = (int)(((long long)(g_push_rank % g_push_world) * bands / g_push_world) * per_band) % tiles;
+  }
   if (epi == P_EPI_ROPE) {
     if (a_mn || b_mn || out_fp32 || !p.rope || (p.rope_hd % 8) || (p.rope_cols % 8)) return -8;
     return launch2<false, false, P_EPI_ROPE, __nv_bfloat16>(tmA, tmB, p, stream);
@@ -563,6 +576,12 @@ extern "C" int b200_gemm2_ag_bf16(const void* A, const void* B, void* C, const v
   p.rope = g_rope_table; p.rope_S = g_rope_S; p.rope_hd = g_rope_hd; p.rope_cols = g_rope_cols;
   p.push_bases = g_push_bases; p.push_n = g_push_n; p.push_off = g_push_off; p.push_rank = g_push_rank;
   p.push_bulk = g_push_bulk;
+  p.tile_rot = 0;
+  if (epi == P_EPI_PUSH && g_push_world > 1) {
+    const int per_band = P_GROUP_M * p.n_tiles, tiles = p.m_tiles * p.n_tiles;
+    const int bands = (tiles + per_band - 1) / per_band;
+    p.tile_rot = (int)(((long long)(g_push_rank % g_push_world) * bands / g_push_world) * per_band) % tiles;
+  }
   AgParams ag;
   ag.peer_shards = peer_shards; ag.full = (uint8_t*)full; ag.shard_bytes = shard_bytes; ag.begin = begin; ag.end = end;
   ag.world = world; ag.rank = rank; ag.flags = flags; ag.epoch = epoch; ag.dependent = dependent;

@@ -117,11 +117,11 @@ class PushTarget:
     slice of the unit's flat gradient (fused GEMM -> reduce-scatter; ``csrc/gemm2_sm100.cu`` P_EPI_PUSH).
     ``table``: int64 device tensor of the ranks' staging-buffer addresses; ``n``: elements per shard; ``off``: element
     offset of this weight inside the flat unit."""
-    __slots__ = ("table", "n", "off", "rank", "shape", "dtype")
+    __slots__ = ("table", "n", "off", "rank", "shape", "dtype", "world")
 
-    def __init__(self, table, n, off, rank, shape, device=None):
+    def __init__(self, table, n, off, rank, shape, device=None, world=1):
         self.table, self.n, self.off, self.rank, self.shape = table, int(n), int(off), int(rank), tuple(shape)
-        self.dtype = torch.bfloat16
+        self.dtype, self.world = torch.bfloat16, int(world)
 
     def numel(self):
         return self.shape[0] * self.shape[1]
@@ -132,6 +132,8 @@ class PushTarget:
 
 # 1 = rows leave the SM as 128-byte cp.async.bulk stores staged through shared memory; 0 = 16-byte st.global per lane
 PUSH_BULK = os.environ.get("FMS_B200_PUSH_BULK", "1") == "1"
+# every rank starts its tile sweep rank/world of the way into the raster, so the ranks push to different owners at any time
+PUSH_ROTATE = os.environ.get("FMS_B200_PUSH_ROTATE", "1") == "1"
 PUSH_STATS = {"gemms": 0, "with_gather": 0}
 
 
@@ -147,7 +149,7 @@ def _gemm_push(a, b, tgt: PushTarget):
         raise RuntimeError(f"wgrad {tuple(a.shape)}^T x {tuple(b.shape)} cannot use the push epilogue")
     a = a if a.stride(-1) == 1 else a.contiguous()
     b = b if b.stride(-1) == 1 else b.contiguous()
-    _C.set_gemm_push(tgt.table, tgt.n, tgt.off, tgt.rank, PUSH_BULK)
+    _C.set_gemm_push(tgt.table, tgt.n, tgt.off, tgt.rank, PUSH_BULK, tgt.world if PUSH_ROTATE else 1)
     PUSH_STATS["gemms"] += 1
     if _AG_QUEUE and _try_fused_gather(a, b, "tn", tgt, 4, None):
         PUSH_STATS["with_gather"] += 1      # the same kernel pushes its tiles out and pulls the next unit's weights in

@@ -444,7 +444,8 @@ class ShardedModel(nn.Module):
             if getattr(u, "vec_grad", None) is None:
                 u.vec_grad = torch.zeros(u.layout.matrix_begin, dtype=staging.dtype, device=self.device)
             table, n, r = self.coll.push_table(staging), u.layout.shard_numel, self.mesh.shard_rank
-            u.bind_grads_push(u.vec_grad, lambda s: PushTarget(table, n, s.offset, r, s.shape, self.device))
+            W = self.mesh.shard_size
+            u.bind_grads_push(u.vec_grad, lambda s: PushTarget(table, n, s.offset, r, s.shape, self.device, world=W))
             u.pushed = True
             return
         if u.full_grad is None:
@@ -656,7 +657,14 @@ class ShardedModel(nn.Module):
         self._reduce(self.root)
         self._release(self.root)
         if self.is_cuda:
-            self.s_compute.wait_stream(self.s_reduce)
+            ev = getattr(self.coll, "last_reduce_done", None)
+            if ev is not None:
+                # the root's fp32 shard and ||g||^2 are complete; the trailing "peers are done reading my buffer" flag
+                # round stays on the reduce stream (it only gates the buffer's reuse, ``_Buf.free_event``)
+                self.s_compute.wait_event(ev)
+                self.coll.last_reduce_done = None
+            else:
+                self.s_compute.wait_stream(self.s_reduce)
 
     def forward_backward(self, tokens, labels, **head_kwargs) -> torch.Tensor:
         """One training micro-step: returns the (detached) mean loss; gradients end up reduced,

@@ -123,6 +123,9 @@ class FusedCollectives:
         # CTA cap of the reduce kernels (csrc/comm.cu); throttling them was measured slower (2 GPUs: 354 -> 361 ms/step)
         self.C.set_reduce_ctas(int(os.environ.get("FMS_B200_REDUCE_CTAS", "296")))
         self._own_scalar = os.environ.get("FMS_B200_OWN_SCALAR_ALLREDUCE", "1") == "1"
+        # CTA cap of the local slot sum (runs under the backward GEMMs; 0 = same as the pull kernels)
+        self._slotsum_ctas = int(os.environ.get("FMS_B200_SLOTSUM_CTAS", "0"))
+        self.last_reduce_done = None
 
     # ---- allocation ---------------------------------------------------------------------------
     def alloc_shard(self, numel: int, dtype: torch.dtype) -> torch.Tensor:
@@ -212,9 +215,14 @@ class FusedCollectives:
         hsdp = self.replica is not None
         self.C.reduce_scatter(g.table_of(full), shard32, g.index * shard32.numel(), g.size, g.index,
                               full.dtype == torch.bfloat16, float(scale), None if hsdp else sumsq)
+        if not hsdp:
+            # results of this unit are final here; consumers need not wait for the trailing flag round
+            self.last_reduce_done = torch.cuda.Event()
+            self.last_reduce_done.record(torch.cuda.current_stream(self.device))
         g.barrier(self.C, self._anchor, _SymGroup.CH_REDUCE)  # peers are done reading my buffer before it is rewritten
         if hsdp:
             self._allreduce(self.replica, shard32, 1.0, sumsq)
+            self.last_reduce_done = None
 
     # ---- fused wgrad GEMM -> reduce-scatter (push) ----------------------------------------------------------------
     def push_table(self, staging: torch.Tensor) -> torch.Tensor:
@@ -244,7 +252,9 @@ class FusedCollectives:
                                dtype=torch.int64, device=self.device)
             self._slice_tables[key] = tab
         hsdp = self.replica is not None
-        self.C.reduce_scatter(tab, shard32, 0, g.size, 0, staging.dtype == torch.bfloat16, float(scale), None if hsdp else sumsq)
+        self.C.reduce_scatter(tab, shard32, 0, g.size, 0, staging.dtype == torch.bfloat16, float(scale),
+                              None if hsdp else sumsq, self._slotsum_ctas)
+        self.last_reduce_done = None
         if hsdp:
             self._allreduce(self.replica, shard32, 1.0, sumsq)
 

@@ -118,17 +118,17 @@ if mode in ("all", "push"):
     dist.all_reduce(ref_local)
     ref = ref_local[rank * n:(rank + 1) * n]
     res = {}
-    for bulk in (True, False):
+    for bulk, rotate in ((True, True), (True, False), (False, True)):
         staging.zero_()
         fc.shard.barrier(C, fc._anchor)
         def push():
-            C.set_gemm_push(table, n, 0, rank, bulk)
+            C.set_gemm_push(table, n, 0, rank, bulk, world if rotate else 1)
             C.gemm_push(dy, x)                           # layout tn, push epilogue
         push()
         fc.shard.barrier(C, fc._anchor)                  # every rank's tiles have landed in my slots
         C.reduce_scatter(slots, mine, 0, world, 0, True, 1.0, None)     # local 'world'-way sum of the slots
         torch.cuda.synchronize()
-        key = "bulk" if bulk else "direct"
+        key = ("bulk" if bulk else "direct") + ("_rot" if rotate else "")
         res[key] = dict(maxdiff=(mine - ref).abs().max().item(), absmax=ref.abs().max().item(), push_gemm_ms=timed(push))
     res["plain_gemm_ms"] = timed(lambda: CK.gemm(dy, x, "tn"))
     res["local_slot_sum_ms"] = timed(lambda: C.reduce_scatter(slots, mine, 0, world, 0, True, 1.0, None))

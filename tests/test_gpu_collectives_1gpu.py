@@ -170,7 +170,7 @@ def test_wgrad_push_epilogue_then_slot_sum_is_reduce_scatter(C, shape, bulk):
     for r in range(W):
         dy = (torch.randn(T, Nw, device=DEV) * 0.1).bfloat16()
         x = (torch.randn(T, Kd, device=DEV) * 0.1).bfloat16()
-        C.set_gemm_push(tab, n, off, r, bulk)
+        C.set_gemm_push(tab, n, off, r, bulk, W if Nw != 512 else 1)   # rank-rotated tile raster (and one case without)
         C.gemm_push(dy, x)
         ref[off:off + Nw * Kd] += (dy.float().t() @ x.float()).bfloat16().float().reshape(-1)
     torch.cuda.synchronize()
