@@ -63,7 +63,8 @@ def main():
 
     cfg = config.train_config()
     update_config(cfg, model_variant=a.model, use_dummy_dataset=True, sharding_strategy="fsdp", seq_length=a.seq,
-                  batch_size=a.batch, low_cpu_fsdp=True, use_torch_compile=not a.no_compile, report_interval=1,
+                  batch_size=a.batch, low_cpu_fsdp=True, use_torch_compile=not a.no_compile,
+                  report_interval=max(a.steps, a.warmup),   # one report per train() call, never per step
                   num_steps=a.warmup, vocab_size=32000, fsdp_activation_checkpointing=False,
                   checkpoint_interval=10 ** 9)
     torch.cuda.manual_seed(cfg.seed); torch.manual_seed(cfg.seed)
@@ -95,6 +96,8 @@ def main():
 
     def run_train(start, stop):
         cfg.num_steps = stop
+        cfg.report_interval = stop   # stock loop; the only multiple of `stop` in (start, stop] is the last step, so there
+        #                              is exactly one report, at the end: loss = mean over the steps of this call
         sink = io.StringIO()
         with contextlib.redirect_stdout(sink):
             return train(cfg, model, local_rank, rank, train_loader, optimizer, scheduler, None, _NoCkpt(), start, 0)
@@ -120,6 +123,12 @@ def main():
             sampler.start()
         except Exception:
             sampler = None
+    try:
+        from bench import DATA_NOTE, bench_config
+    except Exception:
+        root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+        sys.path.insert(0, root)
+        from bench import DATA_NOTE, bench_config
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     loss = run_train(a.warmup, a.warmup + a.steps)
@@ -135,11 +144,12 @@ def main():
             "metric": "tokens/sec (Llama2-7B FSDP seq4k bs2)", "value": round(value, 1), "unit": "tokens/s",
             "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": round(ms_step, 3),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": round(value / world / 9600.0, 4),
-            "dtype": "bf16", "data": "synthetic (reference dummy stream, random-init weights)", "impl": "reference",
+            "dtype": "bf16", "data": DATA_NOTE, "impl": "reference",
             "tokens_per_sec_per_gpu": round(value / world, 1),
-            "config": {"model": a.model, "global_batch": a.batch * world, "seq_len": a.seq, "parallelism": f"fsdp{world}",
-                       "torch_compile": compiled, "stack": "torch FSDP1 + cuBLAS + SDPA + NCCL",
-                       "deps": "ibm-fms/fire absent offline -> plain-torch stand-ins in baseline/fms_shim; reference code unmodified"},
+            "config": bench_config(a.model, a.batch * world, a.seq, f"fsdp{world}", "0"),
+            "details": {"torch_compile": compiled, "stack": "torch FSDP1 + cuBLAS + SDPA + NCCL",
+                        "deps": "ibm-fms/fire absent offline -> plain-torch stand-ins in baseline/fms_shim; reference code unmodified"},
+            "loss_steps": [a.warmup + 1, a.warmup + a.steps],
             "e2e": {"value": round(value, 1), "unit": "tokens/s",
                     "note": "the reference train() loop is inherently end-to-end (per-step H2D of the batch, loss.item())",
                     "h2d_bytes_per_step": a.batch * a.seq * 4 * 2, "d2h_bytes_per_step": 8},

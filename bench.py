@@ -50,6 +50,16 @@ def _args():
     return p.parse_args()
 
 
+DATA_NOTE = "synthetic (reference get_dummy_loader stream, random-init weights)"
+
+
+def bench_config(model, global_batch, seq, parallelism, ac):
+    """The SAME keys (and, for the same run, values) in both arms."""
+    return {"model": model, "global_batch": global_batch, "seq_len": seq, "parallelism": parallelism,
+            "selective_ac": str(ac), "data_stream": "get_dummy_loader (arange windows mod vocab, label == input)",
+            "l2": "per-step working set (>=13.5 GB of weights+activations) >> 126 MB L2; no explicit flush"}
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
 
@@ -149,14 +159,16 @@ def run_ours(a):
     if not is_mamba:
         model.rot_emb.compute_freqs_cis(dev, mcfg.max_expected_seq_len)
     opt = ShardedAdamW(eng, lr=cfg.learning_rate, betas=(0.9, 0.95), weight_decay=0.1)
-    sched = torch.optim.lr_scheduler.LambdaLR(opt, lr_schedule_fn(cfg))
+    import copy
+    sched = torch.optim.lr_scheduler.LambdaLR(opt, lr_schedule_fn(copy.copy(cfg)))   # frozen 1M-step schedule
 
     from fms_fsdp_b200.ops import cuda_kernels as CK
+    from fms_fsdp_b200.utils.dataloader_utils import get_dummy_loader
+    from fms_fsdp_b200.utils.train_utils import train
 
-    # the reference's dummy stream: every rank yields arange(i, i+S) % V, label == input
-    def host_batch(i):
-        t = torch.stack([(torch.arange(i * a.batch + b, i * a.batch + b + a.seq) % cfg.vocab_size) for b in range(a.batch)])
-        return t.int().pin_memory()
+    # BOTH arms read the reference's dummy stream through the same call: get_dummy_loader(cfg, rank, world)
+    # (reference dataloader_utils.py:36-57: sample k = arange(k*S, (k+1)*S) % V, label == input, same on every rank)
+    loader = get_dummy_loader(cfg, rank, world)
 
     def step_device(tok, lab):
         loss = eng.forward_backward(tok, lab)
@@ -165,17 +177,11 @@ def run_ours(a):
         sched.step()
         return loss, gn
 
-    def step_e2e(i):
-        """The call a user makes per step (same ops as fms_fsdp_b200.utils.train_utils.train's loop body)."""
-        h = host_batch_cache[i % len(host_batch_cache)]
-        tok = h.to(dev, non_blocking=True)
-        lab = tok.long()
-        loss, gn = step_device(tok, lab)
-        return float(loss)  # device->host read of the step's result
-
-    host_batch_cache = [host_batch(i) for i in range(4)]
-    dev_tok = [h.to(dev) for h in host_batch_cache]
-    dev_lab = [t.long() for t in dev_tok]
+    # device-resident copies of the batches of the warm-up and of the device-timed region (a different batch every step)
+    dev_batches = []
+    for _ in range(a.warmup + a.steps):
+        tok, lab = next(loader)
+        dev_batches.append((tok.to(dev), lab.to(dev).long()))
 
     def sync_all():
         if world > 1:
@@ -183,33 +189,51 @@ def run_ours(a):
         torch.cuda.synchronize()
 
     for i in range(a.warmup):
-        loss, _ = step_device(dev_tok[i % 4], dev_lab[i % 4])
+        loss, _ = step_device(*dev_batches[i])
     sync_all()
 
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
     CK.reset_launch_count()
+    CK.reset_fallback_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sync_all()
     e0.record()
+    loss_sum = torch.zeros((), device=dev)
     for i in range(a.steps):
-        loss, gn = step_device(dev_tok[i % 4], dev_lab[i % 4])
+        loss, gn = step_device(*dev_batches[a.warmup + i])
+        loss_sum += loss
     e1.record()
     sync_all()
     launches = CK.launch_count()
+    fallbacks = CK.fallback_count()
+    loss_timed = float(loss_sum) / a.steps      # mean loss of steps W+1 .. W+K (what the reference arm prints too)
     ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_step = ms.item() / a.steps
 
-    # ---- end-to-end: pinned H2D of inputs + D2H of the loss every step
+    # ---- end-to-end: K more steps through the PUBLIC training loop, fms_fsdp_b200.utils.train_utils.train()
+    # (the call main_training_llama.main() makes): every step it copies that step's batch host -> device from pinned
+    # staging memory and reads the step's loss back device -> host (4-byte async read-back, checked one step later).
+    class _NoCkpt:   # train() insists on saving at the final step; a 7B checkpoint is not part of the metric
+        def save(self, *args, **kw):
+            return None
+
+    del dev_batches
+    cfg.checkpoint_interval = 10 ** 9
+    cfg.use_dummy_dataset = True
+    start_step = a.warmup + a.steps
+    # the LR lambda above keeps the 1M-step schedule: num_steps only ends the loop from here on
+    cfg.num_steps = start_step + a.steps
+    cfg.report_interval = cfg.num_steps     # exactly one report (and its stats all-reduce), at the last of the K steps
     sync_all()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     f0.record()
-    last = 0.0
-    for i in range(a.steps):
-        last = step_e2e(i)
+    sink = contextlib.nullcontext() if os.environ.get("FMS_B200_BENCH_VERBOSE") else contextlib.redirect_stdout(open(os.devnull, "w"))
+    with sink:
+        last = train(cfg, eng, local_rank, rank, loader, opt, sched, None, _NoCkpt(), start_step, 0)
     f1.record()
     sync_all()
     ms2 = torch.tensor([f0.elapsed_time(f1)], device=dev)
@@ -233,22 +257,29 @@ def run_ours(a):
             "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": round(ms_step, 3),
             "higher_is_better": True, "scaling": "weak",
             "vs_baseline": (round(value / world / PUBLISHED_TOK_S_GPU[a.model], 4) if a.model in PUBLISHED_TOK_S_GPU else None),
-            "dtype": "bf16", "data": "synthetic (reference dummy stream, random-init weights)",
+            "dtype": "bf16", "data": DATA_NOTE,
             "impl": "ours",
             "tokens_per_sec_per_gpu": round(value / world, 1), "mfu_vs_measured_bf16_peak": round(mfu, 4),
-            "loss": round(float(last), 4), "grad_norm": round(float(gn), 4),
-            "config": {"model": a.model, "global_batch": a.batch * world, "seq_len": a.seq, "parallelism": par,
-                       "selective_ac": a.ac, "n_params": n_params, "collectives": eng.coll.name,
-                       "l2": "per-step working set (>=13.5 GB of weights+activations) >> 126 MB L2; no explicit flush",
-                       "attn_impl": CK.ATTN_IMPL, "gemm_impl": CK.GEMM_IMPL},
+            # mean loss over the K device-timed steps (optimizer steps W+1..W+K): directly comparable with the other arm
+            "loss": round(loss_timed, 4), "loss_steps": [a.warmup + 1, a.warmup + a.steps],
+            "loss_e2e": round(float(last), 4), "grad_norm": round(float(gn), 4),
+            "config": bench_config(a.model, a.batch * world, a.seq, par, a.ac),
+            "details": {"n_params": n_params, "collectives": eng.coll.name, "attn_impl": CK.ATTN_IMPL,
+                        "gemm_impl": CK.GEMM_IMPL, "push_reduce_scatter": bool(getattr(eng, "_push_rs", False)),
+                        "async_sharded_optimizer": bool(getattr(eng, "_async_sharded", False))},
             "e2e": {"value": round(e2e, 1), "unit": "tokens/s", "ms_per_step": round(ms_step_e2e, 3),
-                    "h2d_bytes_per_step": a.batch * a.seq * 4, "d2h_bytes_per_step": 4},
+                    "api": "fms_fsdp_b200.utils.train_utils.train (the loop of main_training_llama.main)",
+                    # tokens + labels, int32, copied from pinned staging memory every step; loss read back every step
+                    "h2d_bytes_per_step": 2 * a.batch * a.seq * 4, "d2h_bytes_per_step": 4},
             "gpu_launches": int(launches),
+            "aten_fallbacks": int(fallbacks),
             "clocks": clocks,
             "mem_gb": round(torch.cuda.max_memory_allocated(dev) / 2**30, 2),
         }
         if a.nlayers:
             out["invalid"] = "debug depth override"
+        if fallbacks:
+            out["invalid"] = f"{fallbacks} ops of the timed region ran on the ATen fallback: {dict(CK.FALLBACKS)}"
         if a.model != "llama2_7b" or a.seq != 4096 or a.batch != 2:
             out["note"] = "secondary configuration, not the BASELINE headline"
         print(json.dumps(out), flush=True)
@@ -258,7 +289,8 @@ def run_ours(a):
         ctx = profile(activities=[ProfilerActivity.CUDA]) if rank == 0 else contextlib.nullcontext()
         with ctx as prof:
             for i in range(2):
-                step_device(dev_tok[i % 4], dev_lab[i % 4])
+                tok, lab = next(loader)
+                step_device(tok.to(dev), lab.to(dev).long())
             sync_all()
         if rank == 0:
             os.makedirs(os.path.dirname(a.profile) or ".", exist_ok=True)

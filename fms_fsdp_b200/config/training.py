@@ -103,5 +103,6 @@ class train_config:
     fused_cross_entropy: bool = True         # linear+CE without materialising logits
     fault_inject_step: int = 0               # >0: rank 1 exits at that step (resume drill)
     nonfinite_action: str = "warn"           # NaN/Inf loss or grad norm at a report step: warn | halt (restart + auto-resume)
+    loss_readback: bool = True               # every step: async 4-byte D2H of the loss into pinned memory, checked one step later
     poison_released_params: bool = False     # debug: NaN-fill a unit's gathered parameters on release (use-after-free trap)
     grad_dtype: str = "bf16"                 # dtype of the unsharded gradient buffer (reference reduce_dtype=bf16)

@@ -31,6 +31,29 @@ def launch_count() -> int:
     return int(_C.launch_count())
 
 
+# Calls that did NOT run one of our kernels but the ATen oracle (unsupported dtype / alignment).  Never silent: the
+# first fallback of each op prints one line, every one is counted; bench.py reports the count of its timed region and
+# flags a non-zero value.
+FALLBACKS: dict = {}
+
+
+def _fallback(op: str, why: str = ""):
+    n = FALLBACKS.get(op, 0)
+    FALLBACKS[op] = n + 1
+    if n == 0 and os.environ.get("FMS_B200_QUIET_FALLBACK", "0") != "1":
+        print(f"[fms_fsdp_b200] '{op}' ran on the ATen fallback{(' (' + why + ')') if why else ''}; "
+              "counted in cuda_kernels.FALLBACKS", flush=True)
+    return torch_kernels
+
+
+def fallback_count() -> int:
+    return sum(FALLBACKS.values())
+
+
+def reset_fallback_count():
+    FALLBACKS.clear()
+
+
 def reset_launch_count():
     _C.reset_launch_count()
 
@@ -177,7 +200,7 @@ def gemm(a, b, layout="nt", out=None, accumulate=False, residual=None, out_dtype
             table, S, hd, H, KVH = rope
             return rope_(y, table, S, H, KVH, hd)
     if GEMM_IMPL != "tcgen05" or a.dtype != torch.bfloat16 or b.dtype != torch.bfloat16:
-        return torch_kernels.gemm(a, b, layout, out=out, accumulate=accumulate, residual=residual, out_dtype=out_dtype)
+        return _fallback("gemm").gemm(a, b, layout, out=out, accumulate=accumulate, residual=residual, out_dtype=out_dtype)
     if layout == "nt":
         M, N = a.shape[0], b.shape[0]
     elif layout == "nn":
@@ -186,7 +209,7 @@ def gemm(a, b, layout="nt", out=None, accumulate=False, residual=None, out_dtype
         M, N = a.shape[1], b.shape[1]
     K = a.shape[1] if layout != "tn" else a.shape[0]
     if (M % 8) or (N % 8) or (K % 8):
-        return torch_kernels.gemm(a, b, layout, out=out, accumulate=accumulate, residual=residual, out_dtype=out_dtype)
+        return _fallback("gemm").gemm(a, b, layout, out=out, accumulate=accumulate, residual=residual, out_dtype=out_dtype)
     if a.stride(-1) != 1:
         a = a.contiguous()
     if b.stride(-1) != 1:
@@ -212,7 +235,7 @@ def gemm(a, b, layout="nt", out=None, accumulate=False, residual=None, out_dtype
 # --------------------------------------------------------------------------------------- RMSNorm
 def rmsnorm_fwd(x, w, eps):
     if x.dtype != torch.bfloat16 or x.shape[-1] % 8 or x.shape[-1] > 8192:
-        return torch_kernels.rmsnorm_fwd(x, w, eps)
+        return _fallback("rmsnorm_fwd").rmsnorm_fwd(x, w, eps)
     y, rstd = _C.rmsnorm_fwd(x.contiguous(), _bf16c(w), float(eps))
     return y, rstd
 
@@ -226,7 +249,7 @@ def rmsnorm_bwd(dy, x, w, rstd, dres=None):
         dx, dw = _C.rmsnorm_bwd_f32(dy.contiguous(), x.contiguous(), _bf16c(w), rstd)   # fp32 residual stream
         return dx, dw
     if x.dtype != torch.bfloat16 or x.shape[-1] % 8 or x.shape[-1] > 8192:
-        return torch_kernels.rmsnorm_bwd(dy, x, w, rstd)
+        return _fallback("rmsnorm_bwd").rmsnorm_bwd(dy, x, w, rstd)
     dx, dw = _C.rmsnorm_bwd(dy.contiguous(), x.contiguous(), _bf16c(w), rstd,
                             None if dres is None else dres.reshape(x.shape).contiguous())
     return dx, dw
@@ -234,7 +257,7 @@ def rmsnorm_bwd(dy, x, w, rstd, dres=None):
 
 def add_rmsnorm_fwd(x, res, w, eps):
     if x.dtype != torch.bfloat16 or res.dtype != torch.float32 or x.shape[-1] % 8 or x.shape[-1] > 8192:
-        return torch_kernels.add_rmsnorm_fwd(x, res, w, eps)
+        return _fallback("add_rmsnorm_fwd").add_rmsnorm_fwd(x, res, w, eps)
     y, res_out, rstd = _C.add_rmsnorm_fwd(x.contiguous(), res.contiguous(), _bf16c(w), float(eps))
     return y, res_out, rstd
 
@@ -242,7 +265,7 @@ def add_rmsnorm_fwd(x, res, w, eps):
 def rmsnorm_gated_fwd(x, z, w, eps, group_size):
     D = x.shape[-1]
     if x.dtype != torch.bfloat16 or group_size != D or D % 8 or D > 8192:
-        return torch_kernels.rmsnorm_gated_fwd(x, z, w, eps, group_size)
+        return _fallback("rmsnorm_gated_fwd").rmsnorm_gated_fwd(x, z, w, eps, group_size)
     y, rstd = _C.rmsnorm_gated_fwd(x.contiguous(), z.contiguous(), _bf16c(w), float(eps))
     return y, rstd.view(-1, 1)
 
@@ -250,7 +273,7 @@ def rmsnorm_gated_fwd(x, z, w, eps, group_size):
 def rmsnorm_gated_bwd(dy, x, z, w, rstd, group_size):
     D = x.shape[-1]
     if x.dtype != torch.bfloat16 or group_size != D or D % 8 or D > 8192:
-        return torch_kernels.rmsnorm_gated_bwd(dy, x, z, w, rstd, group_size)
+        return _fallback("rmsnorm_gated_bwd").rmsnorm_gated_bwd(dy, x, z, w, rstd, group_size)
     dx, dz, dw = _C.rmsnorm_gated_bwd(dy.contiguous(), x.contiguous(), z.contiguous(), _bf16c(w), rstd.reshape(-1))
     return dx, dz, dw
 
@@ -261,7 +284,7 @@ rope_table = torch_kernels.rope_table
 def rope_(qkv, table, seq_len, nheads, kvheads, head_dim, rot_dim=None, inverse=False, pos_offset=0, interleaved=True):
     rot_dim = head_dim if rot_dim is None else rot_dim
     if qkv.dtype != torch.bfloat16 or rot_dim % 16 or head_dim % 8:
-        return torch_kernels.rope_(qkv, table, seq_len, nheads, kvheads, head_dim, rot_dim, inverse, pos_offset,
+        return _fallback("rope_").rope_(qkv, table, seq_len, nheads, kvheads, head_dim, rot_dim, inverse, pos_offset,
                                    interleaved)
     _C.rope(qkv, table, seq_len, nheads + kvheads, head_dim, rot_dim, bool(inverse), pos_offset, bool(interleaved))
     return qkv
@@ -281,7 +304,7 @@ def attn_fwd(qkv, B, S, H, KVH, hd, scale, causal=True):
         return o, lse
     if ATTN_IMPL == "sdpa":
         return _sdpa_fwd(qkv, B, S, H, KVH, hd, scale), torch.empty(0, device=qkv.device)
-    return torch_kernels.attn_fwd(qkv, B, S, H, KVH, hd, scale, causal)
+    return _fallback("attn_fwd").attn_fwd(qkv, B, S, H, KVH, hd, scale, causal)
 
 
 def attn_bwd(do, qkv, o, lse, B, S, H, KVH, hd, scale, causal=True, rope_table=None):
@@ -303,32 +326,32 @@ def attn_bwd(do, qkv, o, lse, B, S, H, KVH, hd, scale, causal=True, rope_table=N
             out = _sdpa_fwd(leaf, B, S, H, KVH, hd, scale)
             (g,) = torch.autograd.grad(out, leaf, do)
         return g
-    return torch_kernels.attn_bwd(do, qkv, o, lse, B, S, H, KVH, hd, scale, causal)
+    return _fallback("attn_bwd").attn_bwd(do, qkv, o, lse, B, S, H, KVH, hd, scale, causal)
 
 
 # ---------------------------------------------------------------------------------------- SwiGLU
 def swiglu_fwd(gu, gate_first=True):
     if gu.dtype != torch.bfloat16 or (gu.shape[-1] // 2) % 8:
-        return torch_kernels.swiglu_fwd(gu, gate_first)
+        return _fallback("swiglu_fwd").swiglu_fwd(gu, gate_first)
     return _C.swiglu_fwd(gu.contiguous(), bool(gate_first))
 
 
 def swiglu_bwd(ds, gu, gate_first=True):
     if gu.dtype != torch.bfloat16 or (gu.shape[-1] // 2) % 8:
-        return torch_kernels.swiglu_bwd(ds, gu, gate_first)
+        return _fallback("swiglu_bwd").swiglu_bwd(ds, gu, gate_first)
     return _C.swiglu_bwd(ds.contiguous(), gu.contiguous(), bool(gate_first))
 
 
 # ------------------------------------------------------------------------------------- embedding
 def embedding_fwd(tokens, w):
     if w.dtype != torch.bfloat16 or w.shape[1] % 8:
-        return torch_kernels.embedding_fwd(tokens, w)
+        return _fallback("embedding_fwd").embedding_fwd(tokens, w)
     return _C.embedding_fwd(tokens.contiguous(), w)
 
 
 def embedding_bwd(dx, tokens, out, accumulate=False):
     if dx.dtype != torch.bfloat16 or dx.shape[-1] % 2 or out.dtype not in (torch.bfloat16, torch.float32):
-        return torch_kernels.embedding_bwd(dx, tokens, out, accumulate)
+        return _fallback("embedding_bwd").embedding_bwd(dx, tokens, out, accumulate)
     if not accumulate:
         out.zero_()
     _C.embedding_bwd(dx.contiguous(), tokens.contiguous(), out)
@@ -340,7 +363,7 @@ def linear_ce_fwd_bwd(h, w, labels, dw_out, ignore_index=-100, chunk_rows=4096, 
     M, D = h.shape
     V = w.shape[0]
     if h.dtype != torch.bfloat16 or V % 8 or D % 8 or M % 8:
-        return torch_kernels.linear_ce_fwd_bwd(h, w, labels, dw_out, ignore_index, chunk_rows, accumulate)
+        return _fallback("linear_ce_fwd_bwd").linear_ce_fwd_bwd(h, w, labels, dw_out, ignore_index, chunk_rows, accumulate)
     labels = labels.reshape(-1)
     if labels.dtype != torch.long:
         labels = labels.long()
@@ -365,7 +388,7 @@ def linear_ce_fwd_bwd(h, w, labels, dw_out, ignore_index=-100, chunk_rows=4096, 
 def cross_entropy_fwd_bwd(logits, labels, ignore_index=-100):
     V = logits.shape[-1]
     if logits.dtype != torch.bfloat16 or V % 8:
-        return torch_kernels.cross_entropy_fwd_bwd(logits, labels, ignore_index)
+        return _fallback("cross_entropy_fwd_bwd").cross_entropy_fwd_bwd(logits, labels, ignore_index)
     labels = labels.reshape(-1).long()
     n_valid = torch.zeros((), dtype=torch.float32, device=logits.device)
     loss_sum = torch.zeros((), dtype=torch.float32, device=logits.device)
@@ -380,7 +403,7 @@ def sumsq(x, out=None):
     if out is None:
         out = torch.zeros((), dtype=torch.float32, device=x.device)
     if x.dtype not in (torch.bfloat16, torch.float32) or x.data_ptr() % 16 or not x.is_contiguous():
-        return torch_kernels.sumsq(x, out)
+        return _fallback("sumsq").sumsq(x, out)
     _C.sumsq(x, out)
     return out
 
@@ -390,7 +413,7 @@ def adamw_step(master, grad, exp_avg, exp_avg_sq, lowp_out, lr, beta1, beta2, ep
     ok = (master.numel() % 4 == 0 and grad.dtype in (torch.bfloat16, torch.float32)
           and (lowp_out is None or lowp_out.dtype == torch.bfloat16))
     if not ok:
-        return torch_kernels.adamw_step(master, grad, exp_avg, exp_avg_sq, lowp_out, lr, beta1, beta2, eps,
+        return _fallback("adamw_step").adamw_step(master, grad, exp_avg, exp_avg_sq, lowp_out, lr, beta1, beta2, eps,
                                         weight_decay, step, grad_scale)
     if grad_scale is not None and grad_scale.dtype != torch.float32:
         grad_scale = grad_scale.float()
@@ -401,13 +424,13 @@ def adamw_step(master, grad, exp_avg, exp_avg_sq, lowp_out, lr, beta1, beta2, ep
 # ----------------------------------------------------------------------------------------- mamba
 def causal_conv1d_fwd(x, w, b, seq_len, activation=True):
     if x.dtype != torch.bfloat16 or x.shape[1] % 8 or w.shape[1] > 4:
-        return torch_kernels.causal_conv1d_fwd(x, w, b, seq_len, activation)
+        return _fallback("causal_conv1d_fwd").causal_conv1d_fwd(x, w, b, seq_len, activation)
     return _C.causal_conv1d_fwd(x.contiguous(), _bf16c(w), None if b is None else _bf16c(b), seq_len, activation)
 
 
 def causal_conv1d_bwd(dy, x, w, b, seq_len, activation=True):
     if x.dtype != torch.bfloat16 or x.shape[1] % 8 or w.shape[1] > 4:
-        return torch_kernels.causal_conv1d_bwd(dy, x, w, b, seq_len, activation)
+        return _fallback("causal_conv1d_bwd").causal_conv1d_bwd(dy, x, w, b, seq_len, activation)
     dx, dw, db = _C.causal_conv1d_bwd(dy.contiguous(), x.contiguous(), _bf16c(w), None if b is None else _bf16c(b),
                                       seq_len, activation)
     return dx, dw, (None if b is None else db)
@@ -426,7 +449,7 @@ def _f32c(t):
 def ssd_scan_fwd(x, dt, A, Bm, Cm, D, dt_bias, seq_len, chunk_size, dt_softplus=True):
     """Mamba2 SSD scan (csrc/ssd.cu + batched tcgen05 GEMMs); 128-token internal chunks whatever ``chunk_size``."""
     if not _ssd_native_ok(x, dt, Bm, Cm, seq_len):
-        return torch_kernels.ssd_scan_chunked(x, dt, A, Bm, Cm, D, dt_bias, seq_len, chunk_size, dt_softplus)
+        return _fallback("ssd_scan_chunked").ssd_scan_chunked(x, dt, A, Bm, Cm, D, dt_bias, seq_len, chunk_size, dt_softplus)
     return _C.ssd_scan_fwd(x.contiguous(), dt.contiguous(), _f32c(A), Bm.contiguous(), Cm.contiguous(), _f32c(D),
                            _f32c(dt_bias), int(seq_len), bool(dt_softplus))
 
@@ -450,7 +473,7 @@ def _selscan_native_ok(u, delta, A, Bm, Cm, z, seq_len):
 def selective_scan_fwd(u, delta, A, Bm, Cm, D, z, delta_bias, seq_len, delta_softplus=True):
     """Mamba1 selective scan (csrc/selscan.cu: warp = channel, lane = timestep, shuffle scans)."""
     if not _selscan_native_ok(u, delta, A, Bm, Cm, z, seq_len):
-        return torch_kernels.selective_scan_fwd(u, delta, A, Bm, Cm, D, z, delta_bias, seq_len, delta_softplus)
+        return _fallback("selective_scan_fwd").selective_scan_fwd(u, delta, A, Bm, Cm, D, z, delta_bias, seq_len, delta_softplus)
     y, _ = _C.selective_scan_fwd(u.contiguous(), delta.contiguous(), _f32c(A), Bm.contiguous(), Cm.contiguous(), _f32c(D),
                                  None if z is None else z.contiguous(), _f32c(delta_bias), int(seq_len),
                                  bool(delta_softplus), False)

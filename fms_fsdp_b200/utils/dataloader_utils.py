@@ -28,18 +28,19 @@ def causal_lm(data_seq, prompt_len: int = 1):
 
 
 class _SteadyCounter(torch.utils.data.IterableDataset):
-    """Every rank yields ``arange(i, i+seq) % vocab`` for i = 0,1,2,...; input == label (unshifted),
-    exactly the reference's benchmarking stream (``dataloader_utils.py:36-57``)."""
+    """The reference's benchmarking stream (``dataloader_utils.py:36-57``): sample k is the k-th window of
+    ``seq_len`` consecutive integers modulo the vocabulary -- ``arange(k*seq, (k+1)*seq) % vocab`` -- so the stream
+    sweeps the whole vocabulary; every rank yields the same samples and input == label (unshifted)."""
 
     def __init__(self, seq_len: int, vocab_size: int):
         self.seq_len, self.vocab_size = seq_len, vocab_size
+        self.i = 0
 
     def __iter__(self):
-        i = 0
         while True:
-            t = (torch.arange(i, i + self.seq_len) % self.vocab_size).int()
+            t = (torch.arange(self.i, self.i + self.seq_len) % self.vocab_size).int()
             yield t, t
-            i += 1
+            self.i += self.seq_len
 
 
 def get_dummy_loader(cfg, rank, world_size):

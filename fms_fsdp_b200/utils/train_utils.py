@@ -168,12 +168,58 @@ def _init_tracker(cfg, rank):
 
 
 # --------------------------------------------------------------------------------------------- train
-def _to_device(t, device):
-    if device.type == "cuda":
-        if not t.is_pinned():
-            t = t.pin_memory()
-        return t.to(device, non_blocking=True)
-    return t.to(device)
+class _H2DStager:
+    """Host -> device path of the training loop: the loader's (pageable) batch is copied into a small ring of PINNED
+    staging buffers and sent with an asynchronous copy, so the step's input transfer overlaps the previous step's
+    compute instead of pinning fresh memory every step (cudaHostAlloc) or taking the synchronous pageable path."""
+
+    def __init__(self, device, depth: int = 4):
+        self.device, self.depth, self.slots, self.k = device, depth, {}, 0
+
+    def __call__(self, t: torch.Tensor) -> torch.Tensor:
+        if self.device.type != "cuda":
+            return t.to(self.device)
+        if t.is_cuda:
+            return t
+        key = (tuple(t.shape), t.dtype)
+        ring = self.slots.get(key)
+        if ring is None:
+            ring = [(torch.empty(t.shape, dtype=t.dtype).pin_memory(), torch.cuda.Event()) for _ in range(self.depth)]
+            self.slots[key] = ring
+        buf, ev = ring[self.k % self.depth]
+        self.k += 1
+        ev.synchronize()                 # the copy that last used this pinned slot has left the host
+        buf.copy_(t)
+        out = buf.to(self.device, non_blocking=True)
+        ev.record(torch.cuda.current_stream(self.device))
+        return out
+
+
+class _LossReadback:
+    """Every step: 4-byte asynchronous device -> host copy of the step's loss into pinned memory; the value is looked
+    at ONE step later (non-finite guard without stalling the launch pipeline)."""
+
+    def __init__(self, device, depth: int = 4):
+        self.on = device.type == "cuda"
+        if self.on:
+            self.ring = [(torch.zeros(1, dtype=torch.float32).pin_memory(), torch.cuda.Event(), [None]) for _ in range(depth)]
+        self.k, self.depth, self.device, self.last = 0, depth, device, None
+
+    def push(self, loss: torch.Tensor, step: int):
+        """Returns (step, value) of the oldest completed read-back, or None."""
+        if not self.on:
+            return None
+        buf, ev, tag = self.ring[self.k % self.depth]
+        done = None
+        if tag[0] is not None:
+            ev.synchronize()
+            done = (tag[0], float(buf[0]))
+            self.last = done
+        buf.copy_(loss.detach().reshape(1).float(), non_blocking=True)
+        ev.record(torch.cuda.current_stream(self.device))
+        tag[0] = step
+        self.k += 1
+        return done
 
 
 def train(cfg, model, local_rank, rank, train_loader, optimizer, scheduler, profiler, checkpointer,
@@ -185,6 +231,8 @@ def train(cfg, model, local_rank, rank, train_loader, optimizer, scheduler, prof
     engine_mode = hasattr(model, "forward_backward")
     model.train()
     ddp_stats = torch.zeros(3, device=device)  # [sum loss, sum gnorm, steps]
+    to_device = _H2DStager(device)
+    readback = _LossReadback(device) if getattr(cfg, "loss_readback", True) else None
 
     n_params = model.param_count() if hasattr(model, "param_count") else sum(p.numel() for p in model.parameters())
     mcfg = getattr(getattr(model, "module", model), "config", None)
@@ -205,8 +253,8 @@ def train(cfg, model, local_rank, rank, train_loader, optimizer, scheduler, prof
         if cfg.fault_inject_step and batch_idx == cfg.fault_inject_step and rank == min(1, world_size - 1):
             print(f"[fault-inject] rank {rank} exiting at step {batch_idx}", flush=True)
             os._exit(17)
-        input = _to_device(input, device)
-        label = _to_device(label, device)
+        input = to_device(input)
+        label = to_device(label)
 
         optimizer.zero_grad()
         if engine_mode and cfg.fused_cross_entropy:
@@ -225,6 +273,14 @@ def train(cfg, model, local_rank, rank, train_loader, optimizer, scheduler, prof
         ddp_stats[0] += loss
         ddp_stats[1] += gnorm
         ddp_stats[2] += 1
+        if readback is not None:
+            seen = readback.push(loss, batch_idx)
+            if seen is not None and not math.isfinite(seen[1]):
+                msg = f"[non-finite] step {seen[0]}: loss {seen[1]}"
+                if getattr(cfg, "nonfinite_action", "warn") == "halt":
+                    raise FloatingPointError(msg + " -- halting (nonfinite_action=halt); restart resumes from the last checkpoint")
+                if rank == 0:
+                    print(msg, flush=True)
 
         if profiler:
             profiler.step()
