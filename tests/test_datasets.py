@@ -273,8 +273,12 @@ def test_dummy_loader_and_causal_lm():
     from fms_fsdp_b200.config import train_config
     from fms_fsdp_b200.utils.dataloader_utils import causal_lm, get_dummy_loader, parse_data_args
     cfg = train_config(); cfg.seq_length, cfg.vocab_size, cfg.batch_size = 8, 5, 2
-    x, y = next(get_dummy_loader(cfg, 0, 1))
-    assert x.shape == (2, 8) and torch.equal(x, y) and x.dtype == torch.int32 and x[1, 0] == 1
+    loader = get_dummy_loader(cfg, 0, 1)
+    x, y = next(loader)
+    # the reference stream: sample k = arange(k*seq, (k+1)*seq) % vocab (SteadyCounter advances by seq_len per sample)
+    assert x.shape == (2, 8) and torch.equal(x, y) and x.dtype == torch.int32
+    assert x[0].tolist() == [0, 1, 2, 3, 4, 0, 1, 2] and x[1].tolist() == [3, 4, 0, 1, 2, 3, 4, 0]
+    assert next(loader)[0][0].tolist() == [(16 + j) % 5 for j in range(8)]
     i, t = causal_lm(torch.arange(6))
     assert i.tolist() == [0, 1, 2, 3, 4] and t.tolist() == [-100, 2, 3, 4, 5]
     assert parse_data_args("a,b", "1,2.5") == (["a", "b"], [1.0, 2.5])
