@@ -128,9 +128,14 @@ class ShardedModel(nn.Module):
                  mixed_precision: Optional[MixedPrecision] = None, device: Optional[torch.device] = None,
                  collective_impl: str = "auto", prefetch_depth: int = 2, param_init_fn=None,
                  mesh: Optional[DPMesh] = None, local_world: Optional[int] = None,
-                 reshard_after_forward: bool = True, sync_module_states: bool = False):
+                 reshard_after_forward: bool = True, sync_module_states: bool = False, auto_wrap_policy=None):
         """``sync_module_states``: broadcast global rank 0's initial parameters to every rank before sharding (torch
-        FSDP's flag of the same name; the reference sets it for the speculator, ``train_speculator.py:205``)."""
+        FSDP's flag of the same name; the reference sets it for the speculator, ``train_speculator.py:205``).
+
+        ``auto_wrap_policy``: predicate over the model's chain of blocks (``policies.get_wrapper(block_cls)``, the
+        reference's ``wrapping.py:6-14`` contract): a block for which it is true becomes a shard unit of its own (gathered
+        just in time, released after use); a block for which it is false stays in the ROOT unit next to embedding / head
+        / final norm -- resident for the whole step, reduced with the root.  ``None`` = every block is a unit."""
         super().__init__()
         self.module = model
         self._sync_module_states = bool(sync_module_states)
@@ -169,13 +174,21 @@ class ShardedModel(nn.Module):
         self._nvtx_on = os.environ.get("FMS_B200_NVTX", "0") == "1"
 
         blocks, root_modules = model.engine_units()
+        wrapped = [True if auto_wrap_policy is None else bool(auto_wrap_policy(b)) for b in blocks]
         self.blocks: List[ShardUnit] = []
         if self.mesh.world > 1:
-            self._validate_same_everywhere("number of shard units", len(blocks) + 1)
-        self.root = self._make_unit("root", root_modules, param_init_fn, prefix_of=model)
-        for i, blk in enumerate(blocks):
-            u = self._make_unit(f"block{i}", [blk], param_init_fn, prefix_of=model)
-            self.blocks.append(u)
+            self._validate_same_everywhere("number of shard units", sum(wrapped) + 1)
+        resident = [b for b, w in zip(blocks, wrapped) if not w]
+        self.root = self._make_unit("root", list(root_modules) + resident, param_init_fn, prefix_of=model)
+        # the forward chain: (block module, its own unit | None when its parameters live in the root unit)
+        self._chain: List[Tuple[nn.Module, Optional[ShardUnit]]] = []
+        for i, (blk, w) in enumerate(zip(blocks, wrapped)):
+            u = None
+            if w:
+                u = self._make_unit(f"block{i}", [blk], param_init_fn, prefix_of=model)
+                u.chain_pos = len(self._chain)
+                self.blocks.append(u)
+            self._chain.append((blk, u))
         for idx, u in enumerate(self.units):
             u.index = idx
         if self._async_sharded and len(self.units) > self.coll.max_units:
@@ -576,27 +589,34 @@ class ShardedModel(nn.Module):
             emb_out = self._as_tuple(model.engine_embed(tokens))
         saved = []
         state = emb_out
-        for i, u in enumerate(blocks):
-            self._wait_gather(u, allow_pending_dependent=True)
-            nxt = i + depth
-            if nxt < len(blocks):
-                self._start_gather(blocks[nxt], fuse=fuse)   # fused: rides in one of block i's GEMMs
-            u.recompute = is_checkpointed(u.modules[0])
-            if not grad_on:
-                with torch.no_grad():
-                    state = self._run_block(u.modules[0], self._detach_state(state, False))
-            elif u.recompute:
-                x_in = self._detach_state(state)
-                with torch.no_grad():
-                    state = self._run_block(u.modules[0], x_in)
-                saved.append((x_in, None))
-            else:
-                x_in = self._detach_state(state)
-                state = self._run_block(u.modules[0], x_in)
-                saved.append((x_in, state))
-            keep = (not self.reshard_after_forward) or (grad_on and i >= len(blocks) - 1)
-            if not keep:
-                self._release(u)
+        i = -1                                  # index of the current unit among ``blocks``
+        for blk, u in self._chain:
+            if u is not None:
+                i += 1
+                self._wait_gather(u, allow_pending_dependent=True)
+                nxt = i + depth
+                if nxt < len(blocks):
+                    self._start_gather(blocks[nxt], fuse=fuse)   # fused: rides in one of block i's GEMMs
+            recompute = is_checkpointed(blk)
+            if u is not None:
+                u.recompute = recompute
+            with self._nvtx(f"fwd {u.name if u is not None else 'root-resident block'}"):
+                if not grad_on:
+                    with torch.no_grad():
+                        state = self._run_block(blk, self._detach_state(state, False))
+                elif recompute:
+                    x_in = self._detach_state(state)
+                    with torch.no_grad():
+                        state = self._run_block(blk, x_in)
+                    saved.append((x_in, None))
+                else:
+                    x_in = self._detach_state(state)
+                    state = self._run_block(blk, x_in)
+                    saved.append((x_in, state))
+            if u is not None:
+                keep = (not self.reshard_after_forward) or (grad_on and i >= len(blocks) - 1)
+                if not keep:
+                    self._release(u)
         head_in = self._detach_state(state, grad_on)
         with torch.enable_grad() if grad_on else torch.no_grad():
             out = model.engine_head(*head_in, labels=labels, **head_kwargs) if labels is not None \
@@ -629,27 +649,33 @@ class ShardedModel(nn.Module):
         del out
         sv["head_out"] = None
         # ---- blocks in reverse, re-gathering ahead
-        for i in range(n - 1, -1, -1):
-            u = blocks[i]
-            self._wait_gather(u)
-            nxt = i - depth
-            if nxt >= 0:
-                # fused: rides inside block i's backward GEMMs (FMS_B200_AG_SPLIT_BWD < 1 spreads it over more of them)
-                self._start_gather(blocks[nxt], fuse=fuse, split=self._bwd_gather_split)
-            x_in, y = sv["blocks"][i]
-            self._prepare_grads(u)
-            if y is None:  # selective recompute with the weights that are resident for backward anyway
-                with torch.enable_grad():
-                    y = self._run_block(u.modules[0], x_in)
-            pairs = [(a, g) for a, g in zip(y, dstate) if g is not None and a.requires_grad]
-            torch.autograd.backward([a for a, _ in pairs], [g for _, g in pairs])
+        i = n                                   # index of the current unit among ``blocks``
+        for pos in range(len(self._chain) - 1, -1, -1):
+            blk, u = self._chain[pos]
+            if u is not None:
+                i -= 1
+                self._wait_gather(u)
+                nxt = i - depth
+                if nxt >= 0:
+                    # fused: rides inside block i's backward GEMMs (FMS_B200_AG_SPLIT_BWD < 1 spreads it over more of them)
+                    self._start_gather(blocks[nxt], fuse=fuse, split=self._bwd_gather_split)
+                self._prepare_grads(u)
+            x_in, y = sv["blocks"][pos]
+            with self._nvtx(f"bwd {u.name if u is not None else 'root-resident block'}"):
+                if y is None:  # selective recompute with the weights that are resident for backward anyway
+                    with torch.enable_grad():
+                        y = self._run_block(blk, x_in)
+                pairs = [(a, g) for a, g in zip(y, dstate) if g is not None and a.requires_grad]
+                torch.autograd.backward([a for a, _ in pairs], [g for _, g in pairs])
             dstate = tuple(t.grad for t in x_in)
             for t in x_in:
                 t.grad = None
-            sv["blocks"][i] = None
+            sv["blocks"][pos] = None
             del y, pairs
-            self._reduce(u)
-            self._release(u)
+            if u is not None:
+                with self._nvtx(f"reduce {u.name}"):
+                    self._reduce(u)
+                self._release(u)
         # ---- embedding stage
         pairs = [(a, g) for a, g in zip(sv["emb_out"], dstate) if g is not None and a.requires_grad]
         if pairs:

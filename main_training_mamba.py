@@ -85,6 +85,7 @@ def main(**kwargs):
         collective_impl=cfg.collective_impl,
         prefetch_depth=cfg.prefetch_depth,
         param_init_fn=param_init_fn,
+        auto_wrap_policy=wrapping_policy,
         local_world=(torch.cuda.device_count() if use_cuda else None),
     )
     model.poison_released_params = bool(cfg.poison_released_params) or model.poison_released_params

@@ -217,105 +217,133 @@ def get_model(arch: str, variant: str, model_path: Optional[str] = None, device_
 
 
 # ---------------------------------------------------------------------------------- generation
+class _DecodeSession:
+    """One autoregressive decode: owns the growing token matrix (pre-allocated once -- no O(n^2) re-concatenation), the
+    KV cache handle and the per-step hidden states of the frozen base model."""
+
+    def __init__(self, model, prompt: torch.Tensor, n_new: int, window: int, use_cache: bool, want_embeds: bool):
+        self.model, self.window, self.use_cache, self.want_embeds = model, window, use_cache, want_embeds
+        B, P = prompt.shape
+        self.tokens = torch.empty(B, P + n_new, dtype=prompt.dtype, device=prompt.device)
+        self.tokens[:, :P] = prompt
+        self.filled = P
+        self.cache = None
+        self.hidden = []          # one [B, steps, D] block per model call
+
+    def _model_input(self) -> torch.Tensor:
+        if self.use_cache and self.cache is not None:
+            return self.tokens[:, self.filled - 1: self.filled]          # only the newest token; the rest is cached
+        return self.tokens[:, max(0, self.filled - self.window): self.filled]
+
+    def next_logits(self) -> torch.Tensor:
+        out = self.model(self._model_input(), past_key_value_states=self.cache, use_cache=self.use_cache,
+                         include_embeds=self.want_embeds)
+        if not (self.use_cache or self.want_embeds):
+            return out[:, -1]
+        if self.use_cache:
+            self.cache = out[1]
+        if self.want_embeds:
+            self.hidden.append(out[-1])
+        return out[0][:, -1]
+
+    def append(self, next_tokens: torch.Tensor):
+        self.tokens[:, self.filled] = next_tokens.reshape(-1)
+        self.filled += 1
+
+
+def _sample(logits: torch.Tensor, temperature: float, top_k: int) -> torch.Tensor:
+    scores = logits.float() / temperature
+    if top_k:
+        kth = torch.topk(scores, top_k).values[:, -1:]
+        scores = scores.masked_fill(scores < kth, float("-inf"))
+    return torch.multinomial(torch.softmax(scores, dim=-1), 1)
+
+
 def generate(model: Union[Callable, nn.Module], input_ids: torch.Tensor, max_seq_len: int = 2048,
              max_new_tokens: int = 256, temperature: float = 1.0, top_k: int = 10, do_sample: bool = True,
              num_beams: int = 1, use_cache: bool = False, contiguous_cache: bool = False, include_embeds: bool = True):
-    """Autoregressive decoding that can also return the embedding vector of every produced position
-    (reference ``:28-118``)."""
+    """Decode ``max_new_tokens`` tokens after ``input_ids`` (greedy, or temperature / top-k sampling) and, with
+    ``include_embeds``, also return the base model's final hidden state of every position it computed -- the
+    training signal of stage 2 (same call contract as the reference's ``generate``, ``:28-118``)."""
     if num_beams != 1:
-        raise NotImplementedError("generate() does yet not support beam search")
-    if not isinstance(input_ids, torch.Tensor):
-        raise RuntimeError("generate() requires a tensor of token ids as the prefix")
-    batched = input_ids.dim() != 1
-    if not batched:
-        input_ids = input_ids.unsqueeze(0)
-    result, next_input, embeds = input_ids, input_ids, None
-    kwargs: MutableMapping[str, Any] = dict(past_key_value_states=None, use_cache=use_cache, include_embeds=include_embeds)
+        raise NotImplementedError("beam search is not supported by generate()")
+    if not torch.is_tensor(input_ids):
+        raise RuntimeError("generate() needs the prompt as a tensor of token ids")
+    single = input_ids.dim() == 1
+    session = _DecodeSession(model, input_ids[None] if single else input_ids, max_new_tokens, max_seq_len,
+                             use_cache, include_embeds)
     for _ in range(max_new_tokens):
-        out = model(next_input[:, -max_seq_len:], **kwargs)
-        if not use_cache and not include_embeds:
-            logits = out
-        else:
-            logits = out[0]
-            if include_embeds:
-                z = out[-1]
-            if use_cache:
-                kwargs["past_key_value_states"] = out[1]
-        logits = logits[:, -1, :]
-        if do_sample:
-            logits = logits.float() / temperature
-            if top_k:
-                v, _ = torch.topk(logits, top_k)
-                logits[logits < v[:, [-1]]] = -float("inf")
-            next_val = torch.multinomial(F.softmax(logits, dim=-1), num_samples=1)
-        else:
-            next_val = torch.argmax(logits, dim=-1, keepdim=True)
-        result = torch.cat((result, next_val), dim=-1)
-        next_input = next_val if use_cache else result
-        if include_embeds:
-            embeds = z if embeds is None else torch.cat((embeds, z), dim=-2)
-    if not batched:
-        result = result[0]
-    return (result, embeds) if include_embeds else result
+        logits = session.next_logits()
+        session.append(_sample(logits, temperature, top_k) if do_sample else logits.argmax(dim=-1))
+    tokens = session.tokens[0] if single else session.tokens
+    if not include_embeds:
+        return tokens
+    return tokens, (torch.cat(session.hidden, dim=-2) if session.hidden else None)
 
 
 # -------------------------------------------------------------------------------------- losses
-def _tp_chunk(cfg, t, mesh):
-    if cfg.sharding_strategy == "tp" and mesh is not None:
-        return t.chunk(mesh["tp"].size())[mesh["tp"].get_local_rank()]
-    return t
+def _my_tp_slice(cfg, t, mesh):
+    """Under TP every rank of the TP group ran the base model on the gathered batch; keep this rank's rows."""
+    if cfg.sharding_strategy != "tp" or mesh is None:
+        return t
+    tp = mesh["tp"]
+    return t.chunk(tp.size())[tp.get_local_rank()]
 
 
-def _head_losses(preds, targets_of, loss_fn, ddp_stats):
-    losses = []
-    for i in range(preds.size(0)):
-        targ = targets_of(i, preds.size(2))
-        l = loss_fn(preds[i].reshape(-1, preds.size(3)).float(), targ.long().reshape(-1))
-        losses.append(l)
-        ddp_stats[2 + i] += l.detach()
-    return sum(losses)
+def _per_head_loss(preds: torch.Tensor, tokens: torch.Tensor, first_target: int, loss_fn, ddp_stats) -> torch.Tensor:
+    """``preds`` [n_heads, B, N, V]; head i at position t is scored against ``tokens[:, first_target + i + t]``.  Adds
+    each head's loss to ``ddp_stats[2 + i]`` and returns the sum over heads."""
+    n_heads, _, width, vocab = preds.shape
+    windows = tokens.unfold(1, width, 1)                      # [B, n_windows, width]; window j starts at token j
+    total = preds.new_zeros((), dtype=torch.float32)
+    for head in range(n_heads):
+        target = windows[:, first_target + head]
+        head_loss = loss_fn(preds[head].reshape(-1, vocab).float(), target.reshape(-1).long())
+        ddp_stats[2 + head] += head_loss.detach()
+        total = total + head_loss
+    return total
 
 
 def stage1_loss(cfg, model, speculator, base_model_input, input, loss_fn, ddp_stats, base_model_mesh):
-    """Stage 1: embeddings from ONE parallel forward of the frozen base model on ground-truth text; head i
-    predicts token n+2+i (reference ``:122-171``)."""
+    """Stage 1 (reference ``:122-171``): ONE parallel forward of the frozen base model over ground-truth text gives
+    the hidden states; from the state at position t and the true tokens t+1.., head i predicts token t+2+i."""
+    n = speculator.n_predict
     with torch.no_grad():
-        _, embeds = model(base_model_input[:, : -speculator.n_predict - 1], include_embeds=True, use_cache=False)
-    embeds = _tp_chunk(cfg, embeds, base_model_mesh)
-    preds = speculator(embeds.detach(), input[:, 1:])
-    loss = _head_losses(preds, lambda i, n: input[:, i + 2: n + i + 2], loss_fn, ddp_stats)
-    return loss, ddp_stats, input.numel()
+        _, hidden = model(base_model_input[:, : -(n + 1)], include_embeds=True, use_cache=False)
+    hidden = _my_tp_slice(cfg, hidden, base_model_mesh).detach()
+    preds = speculator(hidden, input[:, 1:])
+    return _per_head_loss(preds, input, 2, loss_fn, ddp_stats), ddp_stats, input.numel()
 
 
 def stage2_loss(cfg, model, speculator, base_model_input, input, loss_fn, ddp_stats, base_model_mesh):
-    """Stage 2: the base model *generates* (sampling, KV cache) from short prompts and the speculator is
-    trained to match the generated continuation (reference ``:175-242``)."""
+    """Stage 2 (reference ``:175-242``): the batch is re-cut into many short prompts, the base model CONTINUES them
+    (sampling, KV cache) and the speculator learns to predict the base model's own continuation."""
+    n = speculator.n_predict
     with torch.no_grad():
-        grow = cfg.stage2_batch_size // cfg.batch_size
-        assert cfg.stage2_prompt_length * grow <= cfg.seq_length, "Error: batch is too small for specified partition"
-        prompts = base_model_input[:, : cfg.stage2_prompt_length * grow].reshape(
-            base_model_input.size(0) * grow, cfg.stage2_prompt_length)
-        targs, embeds = generate(model, prompts, cfg.seq_length, cfg.stage2_seq_length, do_sample=True, use_cache=True,
-                                 include_embeds=True)
-        targs, embeds = _tp_chunk(cfg, targs, base_model_mesh), _tp_chunk(cfg, embeds, base_model_mesh)
-        targs = targs[:, -cfg.stage2_seq_length:]
-        embeds = embeds[:, -cfg.stage2_seq_length: -speculator.n_predict]
-    preds = speculator(embeds.detach(), targs[:, :-1].detach())
-    loss = _head_losses(preds, lambda i, n: targs[:, i + 1: n + i + 1], loss_fn, ddp_stats)
-    return loss, ddp_stats, targs.numel()
+        fan_out = cfg.stage2_batch_size // cfg.batch_size
+        used = cfg.stage2_prompt_length * fan_out
+        assert used <= cfg.seq_length, "Error: batch is too small for specified partition"
+        prompts = base_model_input[:, :used].reshape(-1, cfg.stage2_prompt_length)
+        text, hidden = generate(model, prompts, cfg.seq_length, cfg.stage2_seq_length, do_sample=True, use_cache=True,
+                                include_embeds=True)
+        text = _my_tp_slice(cfg, text, base_model_mesh)[:, -cfg.stage2_seq_length:]
+        hidden = _my_tp_slice(cfg, hidden, base_model_mesh)[:, -cfg.stage2_seq_length: -n]
+    preds = speculator(hidden.detach(), text[:, :-1].detach())
+    return _per_head_loss(preds, text, 1, loss_fn, ddp_stats), ddp_stats, text.numel()
 
 
 def do_ckpt(ckpt_save_path, reset=False):
-    """On-demand checkpoint trigger: ``echo 1 > <ckpt_save_path>/do_ckpt``."""
-    cmd = ckpt_save_path + "/do_ckpt"
-    if not os.path.exists(cmd):
+    """Operator-triggered checkpoint: writing ``1`` into ``<ckpt_save_path>/do_ckpt`` asks the loop for a checkpoint at
+    the next step; the loop acknowledges with ``reset=True``, which writes ``0`` back."""
+    flag = os.path.join(ckpt_save_path, "do_ckpt")
+    if not os.path.isfile(flag):
         return False
     if reset:
-        with open(cmd, "w") as fd:
-            fd.write("0")
+        with open(flag, "w") as fh:
+            fh.write("0")
         return False
-    with open(cmd) as fd:
-        return fd.read().strip() == "1"
+    with open(flag) as fh:
+        return fh.read().strip() == "1"
 
 
 # ---------------------------------------------------------------------------------------- loop

@@ -206,3 +206,48 @@ def test_models_that_differ_across_ranks_are_rejected(kind):
     mp.spawn(_sync_worker, args=(2, free_port(), outdir, kind), nprocs=2, join=True)
     out = torch.load(os.path.join(outdir, "out.pt"), weights_only=False)
     assert out["err"] is not None and "differs across ranks" in out["err"]
+
+
+def test_wrapping_policy_decides_the_shard_units():
+    """``get_wrapper(block)`` is consumed by the engine (reference ``policies/wrapping.py:6-14`` contract): blocks the
+    predicate accepts become units of their own, the others stay resident in the root unit -- same training result."""
+    from fms_fsdp_b200.policies import get_wrapper
+    ref_losses, ref_norms, _ = _oracle(1)
+
+    def run(policy):
+        torch.manual_seed(0)
+        m = LLaMA(get_model_config("llama2_tiny")); m.reset_parameters()
+        eng = ShardedModel(m, sharding_strategy="fsdp", mixed_precision=fp32_policy, device="cpu",
+                           collective_impl="torch", auto_wrap_policy=policy)
+        opt = ShardedAdamW(eng, lr=1e-3)
+        out = []
+        for st in range(STEPS):
+            x = _batch(0, st)
+            loss = eng.forward_backward(x, x)
+            out.append((loss.item(), eng.clip_grad_norm_(1.0).item()))
+            opt.step()
+        return eng, out
+
+    eng, out = run(get_wrapper(LLaMABlock))
+    n_layers = get_model_config("llama2_tiny").nlayers
+    assert len(eng.blocks) == n_layers and all(u is not None for _, u in eng._chain)
+    layers = None
+
+    def only_first(module):            # a policy that wraps just the first block
+        return module is layers[0]
+    torch.manual_seed(0)
+    m = LLaMA(get_model_config("llama2_tiny")); m.reset_parameters()
+    layers = list(m.layers)
+    eng2 = ShardedModel(m, sharding_strategy="fsdp", mixed_precision=fp32_policy, device="cpu", collective_impl="torch",
+                        auto_wrap_policy=only_first)
+    assert len(eng2.blocks) == 1 and [u is not None for _, u in eng2._chain] == [True] + [False] * (n_layers - 1)
+    root_names = {n for n, _ in eng2.root.params}
+    assert any(n.startswith("layers.1.") for n in root_names) and not any(n.startswith("layers.0.") for n in root_names)
+    opt2 = ShardedAdamW(eng2, lr=1e-3)
+    for st in range(STEPS):
+        x = _batch(0, st)
+        loss = eng2.forward_backward(x, x)
+        gn = eng2.clip_grad_norm_(1.0).item()
+        opt2.step()
+        assert abs(loss.item() - out[st][0]) < 1e-5 and abs(gn - out[st][1]) < 1e-4
+        assert abs(loss.item() - ref_losses[st]) < 1e-4
