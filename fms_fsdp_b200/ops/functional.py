@@ -371,17 +371,33 @@ def embedding(tokens, w):
 
 
 # ------------------------------------------------------------------------- fused linear + CE loss
+# The engine's own schedule always differentiates the loss with an upstream gradient of exactly 1 (``_backward(None)``);
+# it says so here, and ``_LinearCE.backward`` then skips the multiplication.  Every other caller (``loss.backward()`` on a
+# scaled loss, gradient accumulation with loss / k, ...) gets the upstream gradient applied ON DEVICE -- never a host
+# read, never silently dropped.
+_UNIT_UPSTREAM = False
+
+
+def set_unit_upstream(flag: bool):
+    global _UNIT_UPSTREAM
+    _UNIT_UPSTREAM = bool(flag)
+
+
 class _LinearCE(torch.autograd.Function):
     @staticmethod
     def forward(ctx, h, w, labels, ignore_index):
         K = kernels_for(h)
         h2 = h.reshape(-1, h.shape[-1])
         buf = getattr(w, "_grad_buf", None)
+        ctx.buf = None
         if buf is not None:
+            # the runtime bound the root unit's gradient buffer before the head: dW lands there directly (no [V, D]
+            # temporary, no copy in collect_grads)
             acc = bool(getattr(w, "_grad_ready", False))
             loss, dh = K.linear_ce_fwd_bwd(h2, _wdata(w), labels, buf, ignore_index, accumulate=acc)
             w._grad_ready = True
             ctx.dw = None
+            ctx.buf, ctx.buf_accumulated = buf, acc
         else:
             dw = torch.zeros_like(_wdata(w))
             loss, dh = K.linear_ce_fwd_bwd(h2, _wdata(w), labels, dw, ignore_index)
@@ -394,16 +410,17 @@ class _LinearCE(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dloss):
         (dh,) = ctx.saved_tensors
-        # gradients were produced in forward for dloss == 1 (the engine always calls backward with 1)
-        scale_is_one = True
-        try:
-            scale_is_one = bool(dloss.numel() == 1 and float(dloss) == 1.0) if not dloss.is_cuda else True
-        except Exception:
-            pass
-        if not scale_is_one:
-            dh = dh * dloss
+        # dh / dW were produced in forward for an upstream gradient of 1
+        if not _UNIT_UPSTREAM:
+            g = dloss.reshape(()).to(dh.device)
+            dh = dh * g.to(dh.dtype)
             if ctx.dw is not None:
-                ctx.dw.mul_(dloss)
+                ctx.dw.mul_(g.to(ctx.dw.dtype))
+            elif ctx.buf is not None:
+                if ctx.buf_accumulated:
+                    raise RuntimeError("a scaled loss cannot be applied to a head gradient that was accumulated into "
+                                       "an existing buffer; scale the loss before the fused linear-cross-entropy instead")
+                ctx.buf.mul_(g.to(ctx.buf.dtype))
         return dh.view(ctx.shape), ctx.dw, None, None
 
 

@@ -115,6 +115,12 @@ def make_collectives(impl: str, mesh: DPMesh, device: torch.device):
             raise ValueError("collective_impl=fused needs CUDA devices")
         if mesh.world == 1:
             return TorchCollectives(mesh, device)
+        if max(mesh.shard_size, mesh.replica_size) > 32:
+            # the signal pads hold 32 ranks per channel (csrc/comm.cu); the reduce kernels themselves take any group size
+            if mesh.rank == 0:
+                print(f"[fms_fsdp_b200] group of {max(mesh.shard_size, mesh.replica_size)} ranks exceeds the 32-rank "
+                      "signal pad: collective_impl=torch (NCCL)")
+            return TorchCollectives(mesh, device)
         from fms_fsdp_b200.parallel.fused_comm import FusedCollectives
         return FusedCollectives(mesh, device)
     return TorchCollectives(mesh, device)

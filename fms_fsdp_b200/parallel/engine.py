@@ -446,7 +446,13 @@ class ShardedModel(nn.Module):
         u.full = None
 
     # ------------------------------------------------------------------------------- gradients
-    def _prepare_grads(self, u: ShardUnit):
+    def _prepare_grads(self, u: ShardUnit, rebind: bool = True):
+        """Bind the unit's parameters to their gradient destination for this step.  ``rebind=False``: keep an existing
+        binding (the root unit is bound before the head stage of the forward, where the fused linear-cross-entropy
+        already writes the head's dW; the backward must not reset that)."""
+        if not rebind and getattr(u, "_grads_bound", False):
+            return
+        u._grads_bound = True
         if self._push_rs and self._push_eligible(u):
             from fms_fsdp_b200.ops.cuda_kernels import PushTarget
             if u.full_grad is None:
@@ -516,6 +522,7 @@ class ShardedModel(nn.Module):
     def _reduce(self, u: ShardUnit):
         u.collect_grads()
         u.unbind_grads()
+        u._grads_bound = False
         m, W = self.mesh, self.mesh.world
         ctx = torch.cuda.stream(self.s_reduce) if self.is_cuda else contextlib.nullcontext()
         if self.is_cuda:
@@ -618,6 +625,8 @@ class ShardedModel(nn.Module):
                 if not keep:
                     self._release(u)
         head_in = self._detach_state(state, grad_on)
+        if grad_on:
+            self._prepare_grads(self.root)      # the head's dW is produced by the fused linear-CE of the forward
         with torch.enable_grad() if grad_on else torch.no_grad():
             out = model.engine_head(*head_in, labels=labels, **head_kwargs) if labels is not None \
                 else model.engine_head(*head_in, **head_kwargs)
@@ -640,9 +649,14 @@ class ShardedModel(nn.Module):
         for j in range(n - 1, max(-1, n - 1 - depth), -1):
             self._start_gather(blocks[j], fuse=fuse)
         # ---- head stage (root unit weights are still gathered)
-        self._prepare_grads(self.root)
+        self._prepare_grads(self.root, rebind=False)
         out = sv["head_out"]
-        torch.autograd.backward(out, dout if dout is not None else torch.ones_like(out))
+        from fms_fsdp_b200.ops import functional as _F
+        _F.set_unit_upstream(dout is None)      # our own schedule differentiates with an upstream gradient of 1
+        try:
+            torch.autograd.backward(out, dout if dout is not None else torch.ones_like(out))
+        finally:
+            _F.set_unit_upstream(False)
         dstate = tuple(t.grad for t in sv["head_in"])
         for t in sv["head_in"]:
             t.grad = None

@@ -152,3 +152,18 @@ def test_qkv_attention_fused_node_matches_separate_ops():
     y2 = ops.attention(qkv, H, KVH, hd)
     (y2 * torch.arange(y2.shape[-1]).float()).sum().backward()
     _close(y, y2); _close(h.grad, h2.grad); _close(w.grad, w2.grad)
+
+
+def test_linear_ce_applies_the_upstream_gradient():
+    """(loss / k).backward() through the fused linear-cross-entropy scales dh and dW (grad accumulation, weighted
+    losses); only the engine's own schedule (upstream == 1, declared via set_unit_upstream) skips the multiply."""
+    import torch
+    from fms_fsdp_b200 import ops
+    torch.manual_seed(0)
+    h = torch.randn(6, 16, requires_grad=True)
+    w = torch.nn.Parameter(torch.randn(32, 16) * 0.1)
+    y = torch.randint(0, 32, (6,))
+    (ops.linear_cross_entropy(h, w, y) * 0.25).backward()
+    h2 = h.detach().clone().requires_grad_(); w2 = torch.nn.Parameter(w.detach().clone())
+    (torch.nn.functional.cross_entropy(h2 @ w2.t(), y) * 0.25).backward()
+    assert torch.allclose(h.grad, h2.grad, atol=1e-6) and torch.allclose(w.grad, w2.grad, atol=1e-6)
