@@ -36,242 +36,69 @@ B200_DEVINL void st_swz128(uint8_t* tile, int row, int chunk16, uint4 v) {
   *reinterpret_cast<uint4*>(tile + row * 128 + ((chunk16 ^ (row & 7)) << 4)) = v;
 }
 
-// ============================================================================================ forward
-template <int HD>
-struct FwdCfg {
-  static constexpr int NCH = HD / 64;              // 64-column chunks of the head dim
-  static constexpr int TILE_BYTES = 128 * HD * 2;  // a 128-row Q/K/V tile
-  static constexpr int KV_STAGES = 2;
-  static constexpr int P_BYTES = 128 * 128 * 2;
-  static constexpr int SMEM = TILE_BYTES * (1 + 2 * KV_STAGES) + P_BYTES + 1024 + 256;
-};
-
-template <int HD>
-__global__ void __launch_bounds__(ATT_THREADS, 1)
-attn_fwd_kernel(const __grid_constant__ CUtensorMap tm, __nv_bfloat16* __restrict__ o, float* __restrict__ lse,
-                int S, int H, int KVH, float scale_log2, int n_qt) {
-  using C = FwdCfg<HD>;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sQ = smem;
-  uint8_t* sK = sQ + C::TILE_BYTES;
-  uint8_t* sV = sK + C::KV_STAGES * C::TILE_BYTES;
-  uint8_t* sP = sV + C::KV_STAGES * C::TILE_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + C::P_BYTES);
-  uint64_t* q_full = bars;
-  uint64_t* k_full = bars + 1;      // [2]
-  uint64_t* k_empty = bars + 3;     // [2]
-  uint64_t* v_full = bars + 5;      // [2]
-  uint64_t* v_empty = bars + 7;     // [2]
-  uint64_t* s_full = bars + 9;      // [2]
-  uint64_t* p_full = bars + 11;
-  uint64_t* pv_done = bars + 12;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // heavy (late) q tiles first
-  const int qt = n_qt - 1 - blockIdx.x;
-  const int h = blockIdx.y, b = blockIdx.z;
-  const int kvh = h / (H / KVH);
-  const int n_kv = qt + 1;  // causal: kv tiles 0..qt
-  const int row0 = b * S + qt * 128;
-
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tm);
-    mbar_init(q_full, 1);
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1);
-      mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1);
-      mbar_init(&s_full[i], 1);
-    }
-    mbar_init(p_full, 4);
-    mbar_init(pv_done, 1);
-    fence_barrier_init();
-  }
-  if (warp == 1) tmem_alloc(tmem_slot, 512);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem = *tmem_slot;
-  const uint32_t tmem_S[2] = {tmem, tmem + 128};
-  const uint32_t tmem_O = tmem + 256;
-
-  if (warp == 0) {
-    if (lane == 0) {
-      mbar_arrive_expect_tx(q_full, C::TILE_BYTES);
-      for (int c = 0; c < C::NCH; ++c) tma_load_2d(sQ + c * 16384, &tm, q_full, h * HD + 64 * c, row0);
-      for (int j = 0; j < n_kv; ++j) {
-        const int st = j & 1;
-        const uint32_t ph = (j >> 1) & 1;
-        const int krow = b * S + j * 128;
-        mbar_wait(&k_empty[st], ph ^ 1);
-        mbar_arrive_expect_tx(&k_full[st], C::TILE_BYTES);
-        for (int c = 0; c < C::NCH; ++c)
-          tma_load_2d(sK + st * C::TILE_BYTES + c * 16384, &tm, &k_full[st], (H + kvh) * HD + 64 * c, krow);
-        mbar_wait(&v_empty[st], ph ^ 1);
-        mbar_arrive_expect_tx(&v_full[st], C::TILE_BYTES);
-        for (int c = 0; c < C::NCH; ++c)
-          tma_load_2d(sV + st * C::TILE_BYTES + c * 16384, &tm, &v_full[st], (H + KVH + kvh) * HD + 64 * c, krow);
-      }
-    }
-  } else if (warp == 1) {
-    constexpr uint32_t idesc_qk = make_idesc_bf16(128, 128, false, false);
-    constexpr uint32_t idesc_pv = make_idesc_bf16(128, HD, false, true);
-    auto issue_qk = [&](int j) {
-      const int st = j & 1;
-      mbar_wait(&k_full[st], (j >> 1) & 1);
-      tc_fence_after();
-      if (lane == 0) {
-        const uint32_t qa = smem_u32(sQ), ka = smem_u32(sK + st * C::TILE_BYTES);
+// ---- packed fp32x2 arithmetic (FFMA2 / FADD2 / FMUL2: two fp32 lanes per issue slot) and an exponential that runs on
+// the FMA pipe.  Measured (ncu source page of the round-1 kernels, profiles/ncu_attention_r1.txt): the softmax /
+// softmax-gradient warps stall on MUFU.EX2 behind the MIO queue -- one 128 x 128 tile costs ~2.1k cycles of exponentials
+// against 1k (forward) / 2k (backward) cycles of tensor-core work, so the tensor pipe idles at ~45 %.  Moving a
+// compile-time fraction of every group of 8 exponentials onto the FMA pipe (Cody-Waite range reduction + degree-3
+// minimax polynomial, 7.5e-5 relative error -- 50x below bf16 rounding of P) lets both pipes work in parallel.
+typedef unsigned long long f32x2_t;
+B200_DEVINL f32x2_t f2_pack(float lo, float hi) {
+  f32x2_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+B200_DEVINL void f2_unpack(f32x2_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+B200_DEVINL f32x2_t f2_fma(f32x2_t a, f32x2_t b, f32x2_t c) {
+  f32x2_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+B200_DEVINL f32x2_t f2_add(f32x2_t a, f32x2_t b) {
+  f32x2_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+B200_DEVINL f32x2_t f2_mul(f32x2_t a, f32x2_t b) {
+  f32x2_t d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+// 2^x for two values, FMA + ALU pipes only.  x is clamped at -126 (result ~1e-38, i.e. 0 after the bf16 pack).
+B200_DEVINL f32x2_t exp2_fma2(f32x2_t x) {
+  float x0, x1;
+  f2_unpack(x, x0, x1);
+  x = f2_pack(fmaxf(x0, -126.f), fmaxf(x1, -126.f));
+  const f32x2_t t = f2_add(x, f2_pack(12582912.f, 12582912.f));      // 1.5 * 2^23: round(x) lands in the low mantissa bits
+  const f32x2_t r = f2_add(t, f2_pack(-12582912.f, -12582912.f));    // round(x)
+  const f32x2_t f = f2_fma(r, f2_pack(-1.f, -1.f), x);               // in [-0.5, 0.5]
+  f32x2_t p = f2_fma(f, f2_pack(0.05517159402370453f, 0.05517159402370453f), f2_pack(0.2426111400127411f, 0.2426111400127411f));
+  p = f2_fma(p, f, f2_pack(0.6932610273361206f, 0.6932610273361206f));
+  p = f2_fma(p, f, f2_pack(0.9999280571937561f, 0.9999280571937561f));
+  float p0, p1, t0, t1;
+  f2_unpack(p, p0, p1);
+  f2_unpack(t, t0, t1);
+  return f2_pack(__int_as_float(__float_as_int(p0) + (__float_as_int(t0) << 23)),     // * 2^round(x) through the exponent
+                 __int_as_float(__float_as_int(p1) + (__float_as_int(t1) << 23)));
+}
+// exponentials of 8 values (4 packed pairs): the first PP pairs on the FMA pipe, the others on the MUFU
+template <int PP>
+B200_DEVINL void exp2_group8(const f32x2_t (&x)[4], f32x2_t (&y)[4]) {
 #pragma unroll
-        for (int kk = 0; kk < HD / 16; ++kk) {
-          const uint32_t off = (kk >> 2) * 16384 + (kk & 3) * 32;
-          umma_bf16_ss(tmem_S[j & 1], make_smem_desc(qa + off, 0, 1024), make_smem_desc(ka + off, 0, 1024), idesc_qk,
-                       kk != 0);
-        }
-        umma_commit(&k_empty[st]);
-        umma_commit(&s_full[j & 1]);
-      }
-      __syncwarp();
-    };
-    mbar_wait(q_full, 0);
-    issue_qk(0);
-    for (int j = 0; j < n_kv; ++j) {
-      if (j + 1 < n_kv) issue_qk(j + 1);
-      const int st = j & 1;
-      mbar_wait(p_full, j & 1);
-      mbar_wait(&v_full[st], (j >> 1) & 1);
-      tc_fence_after();
-      if (lane == 0) {
-        const uint32_t pa = smem_u32(sP), va = smem_u32(sV + st * C::TILE_BYTES);
-#pragma unroll
-        for (int t = 0; t < 8; ++t) {  // 16 kv rows per step
-          const uint32_t poff = (t >> 2) * 16384 + (t & 3) * 32;
-          umma_bf16_ss(tmem_O, make_smem_desc(pa + poff, 0, 1024), make_smem_desc(va + t * 2048, 16384, 1024),
-                       idesc_pv, (j | t) != 0);
-        }
-        umma_commit(&v_empty[st]);
-        umma_commit(pv_done);
-      }
-      __syncwarp();
-    }
-  } else {
-    // ------------------------------------------------ row owners: online softmax, O rescale, epilogue
-    const int q4 = warp & 3;
-    const int r = q4 * 32 + lane;         // row within the q tile == TMEM lane
-    const int q_idx = qt * 128 + r;       // position in the sequence
-    const uint32_t lane_addr = static_cast<uint32_t>(q4 * 32) << 16;
-    float m_ref = -INFINITY, l_sum = 0.f;
-    for (int j = 0; j < n_kv; ++j) {
-      mbar_wait(&s_full[j & 1], (j >> 1) & 1);
-      tc_fence_after();
-      const uint32_t ts = tmem_S[j & 1] + lane_addr;
-      const bool diag = (j == qt);
-      const int kv0 = j * 128;
-      // pass 1: row max (scaled log2 domain)
-      float mx = -INFINITY;
-#pragma unroll 1
-      for (int c = 0; c < 128; c += 32) {
-        uint32_t v[32];
-        tmem_ld_32x32b_x32(ts + c, v);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          float x = __uint_as_float(v[i]) * scale_log2;
-          const int kv = kv0 + c + i;
-          if ((diag && kv > q_idx) || kv >= S) x = -INFINITY;
-          mx = fmaxf(mx, x);
-        }
-      }
-      const float m_new = fmaxf(m_ref, mx);
-      // P buffer and O are free only once PV_{j-1} has retired
-      if (j > 0) mbar_wait(pv_done, (j - 1) & 1);
-      tc_fence_after();
-      const bool grow = (m_new - m_ref) > 8.f;  // lazy rescale threshold (values stay < 2^8 above the reference)
-      if (j == 0) {
-        m_ref = m_new;
-      } else if (__any_sync(0xffffffffu, grow)) {
-        const float f = exp2f(m_ref - m_new);
-        l_sum *= f;
-        m_ref = m_new;
-#pragma unroll 1
-        for (int c = 0; c < HD; c += 32) {
-          uint32_t v[32];
-          tmem_ld_32x32b_x32(tmem_O + lane_addr + c, v);
-          tmem_ld_wait();
-          uint32_t w0[16], w1[16];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            w0[i] = __float_as_uint(__uint_as_float(v[i]) * f);
-            w1[i] = __float_as_uint(__uint_as_float(v[16 + i]) * f);
-          }
-          tmem_st_32x32b_x16(tmem_O + lane_addr + c, w0);
-          tmem_st_32x32b_x16(tmem_O + lane_addr + c + 16, w1);
-        }
-        tmem_st_wait();
-      }
-      // pass 2: p = 2^(x - m_ref) -> bf16 -> swizzled smem (A operand of the PV GEMM)
-#pragma unroll 1
-      for (int c = 0; c < 128; c += 32) {
-        uint32_t v[32];
-        tmem_ld_32x32b_x32(ts + c, v);
-        tmem_ld_wait();
-        float p[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          float x = __uint_as_float(v[i]) * scale_log2;
-          const int kv = kv0 + c + i;
-          if ((diag && kv > q_idx) || kv >= S) x = -INFINITY;
-          p[i] = exp2f(x - m_ref);
-          l_sum += p[i];
-        }
-        uint8_t* tile = sP + (c >> 6) * 16384;
-        const int cb = (c & 63) >> 3;  // first 16-byte chunk of this group within the 128 B row
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          uint4 u;
-          u.x = pack_bf16x2(p[g * 8 + 0], p[g * 8 + 1]); u.y = pack_bf16x2(p[g * 8 + 2], p[g * 8 + 3]);
-          u.z = pack_bf16x2(p[g * 8 + 4], p[g * 8 + 5]); u.w = pack_bf16x2(p[g * 8 + 6], p[g * 8 + 7]);
-          st_swz128(tile, r, cb + g, u);
-        }
-      }
-      fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(p_full);
-    }
-    // epilogue: O / l -> bf16 ; lse
-    mbar_wait(pv_done, (n_kv - 1) & 1);
-    tc_fence_after();
-    const float inv_l = 1.f / l_sum;
-    if (q_idx < S) {
-      __nv_bfloat16* orow = o + (static_cast<size_t>(b) * S + q_idx) * (H * HD) + h * HD;
-#pragma unroll 1
-      for (int c = 0; c < HD; c += 32) {
-        uint32_t v[32];
-        tmem_ld_32x32b_x32(tmem_O + lane_addr + c, v);
-        tmem_ld_wait();
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          uint4 u;
-          u.x = pack_bf16x2(__uint_as_float(v[g * 8 + 0]) * inv_l, __uint_as_float(v[g * 8 + 1]) * inv_l);
-          u.y = pack_bf16x2(__uint_as_float(v[g * 8 + 2]) * inv_l, __uint_as_float(v[g * 8 + 3]) * inv_l);
-          u.z = pack_bf16x2(__uint_as_float(v[g * 8 + 4]) * inv_l, __uint_as_float(v[g * 8 + 5]) * inv_l);
-          u.w = pack_bf16x2(__uint_as_float(v[g * 8 + 6]) * inv_l, __uint_as_float(v[g * 8 + 7]) * inv_l);
-          *reinterpret_cast<uint4*>(orow + c + g * 8) = u;
-        }
-      }
-      lse[(static_cast<size_t>(b) * H + h) * S + q_idx] = (m_ref + log2f(l_sum)) * LN2;
+  for (int q = 0; q < 4; ++q) {
+    if (q < PP) {
+      y[q] = exp2_fma2(x[q]);
     } else {
-      // still drain TMEM reads are not required; nothing to store
+      float a, b;
+      f2_unpack(x[q], a, b);
+      y[q] = f2_pack(exp2f(a), exp2f(b));
     }
   }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) {
-    tc_fence_after();
-    tmem_dealloc(tmem, 512);
-  }
+}
+B200_DEVINL float fmax3(float a, float b, float c) {
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
 }
 
 // ===================================================================================== forward v2
@@ -291,7 +118,7 @@ struct Fwd2Cfg {
   static constexpr int SMEM = TILE_BYTES * (2 + 2 + 2) + 1024 + 256;
 };
 
-template <int HD>
+template <int HD, int PP>
 __global__ void __launch_bounds__(ATT2_THREADS, 1)
 attn_fwd2_kernel(const __grid_constant__ CUtensorMap tm, __nv_bfloat16* __restrict__ o, float* __restrict__ lse,
                  int S, int H, int KVH, float scale_log2, int n_pt) {
@@ -447,9 +274,9 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tm, __nv_bfloat16* __restri
       }
       float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
-      for (int i = 0; i < 128; i += 2) {
-        mx0 = fmaxf(mx0, __uint_as_float(v[i]));
-        mx1 = fmaxf(mx1, __uint_as_float(v[i + 1]));
+      for (int i = 0; i < 128; i += 4) {   // 3-input max: two elements per instruction
+        mx0 = fmax3(mx0, __uint_as_float(v[i]), __uint_as_float(v[i + 1]));
+        mx1 = fmax3(mx1, __uint_as_float(v[i + 2]), __uint_as_float(v[i + 3]));
       }
       const float mx = fmaxf(mx0, mx1) * scale_log2;
       const float m_new = fmaxf(m_ref, mx);
@@ -477,18 +304,35 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tm, __nv_bfloat16* __restri
           tmem_st_32x32b_x16(tO + c + 16, w1);
         }
       }
-      // P = 2^(x - m_ref) packed two bf16 per column, written over S's own columns (in order => no hazard)
+      // P = 2^(x - m_ref) packed two bf16 per column, written over S's own columns (in order => no hazard).
+      // Packed FFMA2 for the scale / shift, PP of every 4 pairs exponentiated on the FMA pipe, the rest on the MUFU.
+      {
+        const f32x2_t sc2 = f2_pack(scale_log2, scale_log2), nm2 = f2_pack(-m_ref, -m_ref);
+        f32x2_t ls2 = f2_pack(0.f, 0.f);
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        uint32_t w[16];
+        for (int c = 0; c < 4; ++c) {
+          uint32_t w[16];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const float p0 = exp2f(fmaf(__uint_as_float(v[c * 32 + 2 * i]), scale_log2, -m_ref));
-          const float p1 = exp2f(fmaf(__uint_as_float(v[c * 32 + 2 * i + 1]), scale_log2, -m_ref));
-          l_sum += p0 + p1;
-          w[i] = pack_bf16x2(p0, p1);
+          for (int g8 = 0; g8 < 4; ++g8) {
+            f32x2_t x[4], y[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              x[q] = f2_fma(f2_pack(__uint_as_float(v[c * 32 + g8 * 8 + 2 * q]), __uint_as_float(v[c * 32 + g8 * 8 + 2 * q + 1])),
+                            sc2, nm2);
+            exp2_group8<PP>(x, y);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              ls2 = f2_add(ls2, y[q]);
+              float p0, p1;
+              f2_unpack(y[q], p0, p1);
+              w[g8 * 4 + q] = pack_bf16x2(p0, p1);
+            }
+          }
+          tmem_st_32x32b_x16(tS + c * 16, w);
         }
-        tmem_st_32x32b_x16(tS + c * 16, w);
+        float s0, s1;
+        f2_unpack(ls2, s0, s1);
+        l_sum += s0 + s1;
       }
       tmem_st_wait();
       tc_fence_before();
@@ -529,381 +373,47 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tm, __nv_bfloat16* __restri
 }
 
 // ===================================================================================== backward prep
-// delta[b,h,s] = sum_d dO[b,s,h,d] * O[b,s,h,d]      (one warp per (row, head))
-__global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16* __restrict__ o,
-                                  float* __restrict__ delta, const float* __restrict__ lse, float* __restrict__ lse2,
-                                  int B, int S, int H, int HD, int ld) {
-  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (gw >= B * S * H) return;
-  const int h = gw % H;
-  const size_t bs = gw / H;
-  const __nv_bfloat16* a = dout + (bs * H + h) * HD;
-  const __nv_bfloat16* c = o + (bs * H + h) * HD;
-  float s = 0.f;
-  for (int d = lane * 2; d < HD; d += 64) {
-    float2 x = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(a + d));
-    float2 y = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(c + d));
-    s += x.x * y.x + x.y * y.y;
+// -delta[b,h,s] = -sum_d dO[b,s,h,d] * O[b,s,h,d]  and  -lse * log2(e)  (both planes NEGATED: the backward kernels use
+// them as the addend of a packed FFMA2 / FADD2).  HD/8 lanes per (row, head), one 16-byte load of dO and of O per lane
+// (the round-1 kernel issued 4-byte loads from one warp per row: 78 us for 134 MB, now bandwidth-bound).
+template <int HD>
+__global__ void __launch_bounds__(256) attn_delta_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16* __restrict__ o,
+                                                         float* __restrict__ delta, const float* __restrict__ lse,
+                                                         float* __restrict__ lse2, int B, int S, int H, int ld) {
+  constexpr int G = HD / 8;                              // lanes per (row, head)
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long item = gid / G;                        // (b*S + s) * H + h
+  const int sub = (int)(gid % G);
+  const bool live = item < (long long)B * S * H;
+  float acc = 0.f;
+  if (live) {
+    const uint4 x = *reinterpret_cast<const uint4*>(dout + item * HD + sub * 8);
+    const uint4 y = *reinterpret_cast<const uint4*>(o + item * HD + sub * 8);
+    const uint32_t xs[4] = {x.x, x.y, x.z, x.w}, ys[4] = {y.x, y.y, y.z, y.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 a = unpack_bf16x2(xs[i]), c = unpack_bf16x2(ys[i]);
+      acc = fmaf(a.x, c.x, fmaf(a.y, c.y, acc));
+    }
   }
-  s = warp_sum(s);
-  if (lane == 0) {
+#pragma unroll
+  for (int m = G / 2; m > 0; m >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, m);
+  if (live && sub == 0) {
+    const int h = (int)(item % H);
+    const long long bs = item / H;
     const int b = (int)(bs / S), sq = (int)(bs % S);
-    delta[((size_t)b * H + h) * ld + sq] = s;
-    if (lse2) lse2[((size_t)b * H + h) * ld + sq] = lse[((size_t)b * H + h) * S + sq] * LOG2E;  // log2-domain copy
+    delta[((size_t)b * H + h) * ld + sq] = -acc;
+    if (lse2) lse2[((size_t)b * H + h) * ld + sq] = -lse[((size_t)b * H + h) * S + sq] * LOG2E;
   }
 }
 
 // ============================================================================================ backward
-// Skeleton shared by both kernels:
-//   resident pair (X1, X2): 128 rows x HD        streamed pair (Y1, Y2): 64 rows x HD, 2 stages
-//   T1 = X1 Y1^T, T2 = X2 Y2^T   (128 x 64 fp32 in TMEM, double buffered)
-//   row owners turn (T1, T2) into bf16 tiles W1 (and W2) of shape [128 x 64] in smem
-//   DKDV: X=(K_j, V_j), Y=(Q_i, dO_i): W1 = P^T, W2 = dS^T; acc1(dV) += W1 Y2, acc2(dK) += W2 Y1
-//   DQ  : X=(Q_i, dO_i), Y=(K_j, V_j): W2 = dS;             acc2(dQ) += W2 Y1
 enum { MODE_DKDV = 0, MODE_DQ = 1 };
 
-template <int HD>
-struct BwdCfg {
-  static constexpr int NCH = HD / 64;
-  static constexpr int X_BYTES = 128 * HD * 2;   // one resident operand
-  static constexpr int Y_BYTES = 64 * HD * 2;    // one streamed operand
-  static constexpr int Y_CHUNK = 64 * 128;       // bytes of one 64-row x 64-col chunk
-  static constexpr int W_BYTES = 128 * 64 * 2;
-  static constexpr int STAGES = 2;
-  static constexpr int SMEM = 2 * X_BYTES + STAGES * 2 * Y_BYTES + 2 * W_BYTES + 64 * 2 * 4 * 2 + 1024 + 256;
-};
-
-template <int HD, int MODE>
-__global__ void __launch_bounds__(ATT_THREADS, 1)
-attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv128, const __grid_constant__ CUtensorMap tm_qkv64,
-                const __grid_constant__ CUtensorMap tm_do128, const __grid_constant__ CUtensorMap tm_do64,
-                const float* __restrict__ lse, const float* __restrict__ delta, __nv_bfloat16* __restrict__ dqkv,
-                int S, int H, int KVH, float scale, int n_t128) {
-  using C = BwdCfg<HD>;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sX1 = smem;
-  uint8_t* sX2 = sX1 + C::X_BYTES;
-  uint8_t* sY = sX2 + C::X_BYTES;                       // [stage][Y1 | Y2]
-  uint8_t* sW1 = sY + C::STAGES * 2 * C::Y_BYTES;
-  uint8_t* sW2 = sW1 + C::W_BYTES;
-  float* sStat = reinterpret_cast<float*>(sW2 + C::W_BYTES);  // [2 buffers][lse2 64 | delta 64]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sStat) + 64 * 2 * 4 * 2);
-  uint64_t* x_full = bars;
-  uint64_t* y_full = bars + 1;     // [2]
-  uint64_t* y_empty = bars + 3;    // [2]
-  uint64_t* t_full = bars + 5;     // [2]
-  uint64_t* w_full = bars + 7;
-  uint64_t* acc_done = bars + 8;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int G = H / KVH;
-  const int b = blockIdx.z;
-  const float scale_log2 = scale * LOG2E;
-
-  // iteration space of the streamed (64-row) tiles
-  int t128, head_lo, head_n, kvh;
-  if constexpr (MODE == MODE_DKDV) {
-    t128 = blockIdx.x;                 // kv tile; small index = most work, scheduled first
-    kvh = blockIdx.y;
-    head_lo = kvh * G;
-    head_n = G;
-  } else {
-    t128 = n_t128 - 1 - blockIdx.x;    // q tile; large index = most work
-    head_lo = blockIdx.y;
-    head_n = 1;
-    kvh = blockIdx.y / G;
-  }
-  const int n64 = (S + 63) / 64;
-  // DKDV: q tiles i64 in [2*t128, n64) ; DQ: kv tiles j64 in [0, 2*t128+2) clipped
-  const int s_lo = (MODE == MODE_DKDV) ? 2 * t128 : 0;
-  const int s_hi = (MODE == MODE_DKDV) ? n64 : min(n64, 2 * t128 + 2);
-  const int per_head = s_hi - s_lo;
-  const int n_iter = per_head * head_n;
-  const int xrow0 = b * S + t128 * 128;
-
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tm_qkv128); tma_prefetch_desc(&tm_qkv64);
-    tma_prefetch_desc(&tm_do128); tma_prefetch_desc(&tm_do64);
-    mbar_init(x_full, 1);
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&y_full[i], 1); mbar_init(&y_empty[i], 1); mbar_init(&t_full[i], 1);
-    }
-    mbar_init(w_full, 4);
-    mbar_init(acc_done, 1);
-    fence_barrier_init();
-  }
-  if (warp == 1) tmem_alloc(tmem_slot, 512);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem = *tmem_slot;
-  // TMEM columns: T1[0] 0..63, T2[0] 64..127, T1[1] 128..191, T2[1] 192..255, acc1 256.., acc2 384..
-  const uint32_t tmem_acc1 = tmem + 256, tmem_acc2 = tmem + 384;
-
-  if (warp == 0) {
-    if (lane == 0) {
-      // resident operands.  DKDV: per-CTA constant (K_j, V_j).  DQ: (Q_i, dO_i) of this head.
-      if constexpr (MODE == MODE_DKDV) {
-        mbar_arrive_expect_tx(x_full, 2 * C::X_BYTES);
-        for (int c = 0; c < C::NCH; ++c) {
-          tma_load_2d(sX1 + c * 16384, &tm_qkv128, x_full, (H + kvh) * HD + 64 * c, xrow0);
-          tma_load_2d(sX2 + c * 16384, &tm_qkv128, x_full, (H + KVH + kvh) * HD + 64 * c, xrow0);
-        }
-      } else {
-        mbar_arrive_expect_tx(x_full, 2 * C::X_BYTES);
-        for (int c = 0; c < C::NCH; ++c) {
-          tma_load_2d(sX1 + c * 16384, &tm_qkv128, x_full, head_lo * HD + 64 * c, xrow0);
-          tma_load_2d(sX2 + c * 16384, &tm_do128, x_full, head_lo * HD + 64 * c, xrow0);
-        }
-      }
-      for (int it = 0; it < n_iter; ++it) {
-        const int st = it & 1;
-        const uint32_t ph = (it >> 1) & 1;
-        const int hh = head_lo + it / per_head;
-        const int t64 = s_lo + it % per_head;
-        const int yrow = b * S + t64 * 64;
-        uint8_t* y1 = sY + st * 2 * C::Y_BYTES;
-        uint8_t* y2 = y1 + C::Y_BYTES;
-        mbar_wait(&y_empty[st], ph ^ 1);
-        mbar_arrive_expect_tx(&y_full[st], 2 * C::Y_BYTES);
-        for (int c = 0; c < C::NCH; ++c) {
-          if constexpr (MODE == MODE_DKDV) {
-            tma_load_2d(y1 + c * C::Y_CHUNK, &tm_qkv64, &y_full[st], hh * HD + 64 * c, yrow);   // Q_i
-            tma_load_2d(y2 + c * C::Y_CHUNK, &tm_do64, &y_full[st], hh * HD + 64 * c, yrow);    // dO_i
-          } else {
-            tma_load_2d(y1 + c * C::Y_CHUNK, &tm_qkv64, &y_full[st], (H + kvh) * HD + 64 * c, yrow);        // K_j
-            tma_load_2d(y2 + c * C::Y_CHUNK, &tm_qkv64, &y_full[st], (H + KVH + kvh) * HD + 64 * c, yrow);  // V_j
-          }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    constexpr uint32_t idesc_t = make_idesc_bf16(128, 64, false, false);   // scores: both K-major over HD
-    constexpr uint32_t idesc_a = make_idesc_bf16(128, HD, false, true);    // accumulate: A K-major, B MN-major
-    auto issue_scores = [&](int it) {
-      const int st = it & 1;
-      mbar_wait(&y_full[st], (it >> 1) & 1);
-      tc_fence_after();
-      if (lane == 0) {
-        const uint32_t x1 = smem_u32(sX1), x2 = smem_u32(sX2);
-        const uint32_t y1 = smem_u32(sY + st * 2 * C::Y_BYTES), y2 = y1 + C::Y_BYTES;
-        const uint32_t t1 = tmem + (it & 1) * 128, t2 = t1 + 64;
-#pragma unroll
-        for (int kk = 0; kk < HD / 16; ++kk) {
-          const uint32_t xo = (kk >> 2) * 16384 + (kk & 3) * 32;
-          const uint32_t yo = (kk >> 2) * C::Y_CHUNK + (kk & 3) * 32;
-          umma_bf16_ss(t1, make_smem_desc(x1 + xo, 0, 1024), make_smem_desc(y1 + yo, 0, 1024), idesc_t, kk != 0);
-        }
-#pragma unroll
-        for (int kk = 0; kk < HD / 16; ++kk) {
-          const uint32_t xo = (kk >> 2) * 16384 + (kk & 3) * 32;
-          const uint32_t yo = (kk >> 2) * C::Y_CHUNK + (kk & 3) * 32;
-          umma_bf16_ss(t2, make_smem_desc(x2 + xo, 0, 1024), make_smem_desc(y2 + yo, 0, 1024), idesc_t, kk != 0);
-        }
-        umma_commit(&t_full[it & 1]);
-      }
-      __syncwarp();
-    };
-    mbar_wait(x_full, 0);
-    if (n_iter > 0) issue_scores(0);
-    for (int it = 0; it < n_iter; ++it) {
-      if (it + 1 < n_iter) issue_scores(it + 1);
-      const int st = it & 1;
-      mbar_wait(w_full, it & 1);
-      tc_fence_after();
-      if (lane == 0) {
-        const uint32_t y1 = smem_u32(sY + st * 2 * C::Y_BYTES), y2 = y1 + C::Y_BYTES;
-        const uint32_t w1 = smem_u32(sW1), w2 = smem_u32(sW2);
-        // reduction over the 64 streamed rows: 4 steps of 16; Y as MN-major B: LBO = chunk stride, SBO = 1024
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          if constexpr (MODE == MODE_DKDV) {
-            umma_bf16_ss(tmem_acc1, make_smem_desc(w1 + t * 32, 0, 1024),
-                         make_smem_desc(y2 + t * 2048, C::Y_CHUNK, 1024), idesc_a, (it | t) != 0);   // dV += P^T dO
-          }
-          umma_bf16_ss(tmem_acc2, make_smem_desc(w2 + t * 32, 0, 1024),
-                       make_smem_desc(y1 + t * 2048, C::Y_CHUNK, 1024), idesc_a, (it | t) != 0);     // dK += dS^T Q | dQ += dS K
-        }
-        umma_commit(&y_empty[st]);
-        umma_commit(acc_done);
-      }
-      __syncwarp();
-    }
-  } else {
-    // ------------------------------------------------------------------- row owners
-    const int q4 = warp & 3;
-    const int r = q4 * 32 + lane;
-    const int tid128 = (warp - 2) * 32 + lane;
-    const uint32_t lane_addr = static_cast<uint32_t>(q4 * 32) << 16;
-    const int x_idx = t128 * 128 + r;  // sequence position of this thread's resident row
-    float row_lse2 = 0.f, row_delta = 0.f;
-    for (int it = 0; it < n_iter; ++it) {
-      const int hh = head_lo + it / per_head;
-      const int t64 = s_lo + it % per_head;
-      const int y0 = t64 * 64;
-      float* stat = sStat + (it & 1) * 128;
-      if constexpr (MODE == MODE_DKDV) {
-        // per-column statistics of the streamed q rows
-        const int qi = y0 + (tid128 & 63);
-        const size_t sidx = ((size_t)b * H + hh) * S + min(qi, S - 1);
-        stat[tid128] = (tid128 < 64) ? lse[sidx] * LOG2E : delta[sidx];
-        named_bar_sync(1, 128);
-      } else if (it == 0) {
-        const size_t sidx = ((size_t)b * H + hh) * S + min(x_idx, S - 1);
-        row_lse2 = lse[sidx] * LOG2E;
-        row_delta = delta[sidx];
-      }
-      mbar_wait(&t_full[it & 1], (it >> 1) & 1);
-      tc_fence_after();
-      // W tiles are free once the accumulate GEMMs of the previous iteration retired
-      if (it > 0) mbar_wait(acc_done, (it - 1) & 1);
-      const uint32_t t1 = tmem + (it & 1) * 128 + lane_addr, t2 = t1 + 64;
-#pragma unroll 1
-      for (int c = 0; c < 64; c += 32) {
-        uint32_t a[32], d[32];
-        tmem_ld_32x32b_x32(t1 + c, a);
-        tmem_ld_32x32b_x32(t2 + c, d);
-        tmem_ld_wait();
-        float p[32], ds[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const int y_idx = y0 + c + i;
-          float l2, dl;
-          bool masked;
-          if constexpr (MODE == MODE_DKDV) {
-            l2 = stat[c + i]; dl = stat[64 + c + i];
-            masked = (x_idx > y_idx) || (y_idx >= S) || (x_idx >= S);     // kv > q
-          } else {
-            l2 = row_lse2; dl = row_delta;
-            masked = (y_idx > x_idx) || (y_idx >= S) || (x_idx >= S);
-          }
-          const float pv = masked ? 0.f : exp2f(__uint_as_float(a[i]) * scale_log2 - l2);
-          p[i] = pv;
-          ds[i] = pv * (__uint_as_float(d[i]) - dl) * scale;
-        }
-        const int cb = c >> 3;
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          uint4 u;
-          if constexpr (MODE == MODE_DKDV) {
-            u.x = pack_bf16x2(p[g * 8 + 0], p[g * 8 + 1]); u.y = pack_bf16x2(p[g * 8 + 2], p[g * 8 + 3]);
-            u.z = pack_bf16x2(p[g * 8 + 4], p[g * 8 + 5]); u.w = pack_bf16x2(p[g * 8 + 6], p[g * 8 + 7]);
-            st_swz128(sW1, r, cb + g, u);
-          }
-          u.x = pack_bf16x2(ds[g * 8 + 0], ds[g * 8 + 1]); u.y = pack_bf16x2(ds[g * 8 + 2], ds[g * 8 + 3]);
-          u.z = pack_bf16x2(ds[g * 8 + 4], ds[g * 8 + 5]); u.w = pack_bf16x2(ds[g * 8 + 6], ds[g * 8 + 7]);
-          st_swz128(sW2, r, cb + g, u);
-        }
-      }
-      fence_proxy_async_smem();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(w_full);
-    }
-    // epilogue: accumulators -> bf16 -> dqkv sections
-    if (n_iter > 0) mbar_wait(acc_done, (n_iter - 1) & 1);
-    tc_fence_after();
-    if (x_idx < S) {
-      const size_t row = (size_t)b * S + x_idx;
-      const int W = (H + 2 * KVH) * HD;
-      auto store_acc = [&](uint32_t tacc, int col0) {
-        __nv_bfloat16* dst = dqkv + row * W + col0;
-#pragma unroll 1
-        for (int c = 0; c < HD; c += 32) {
-          uint32_t v[32];
-          if (n_iter > 0) {
-            tmem_ld_32x32b_x32(tacc + lane_addr + c, v);
-            tmem_ld_wait();
-          } else {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = 0u;
-          }
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            uint4 u;
-            u.x = pack_bf16x2(__uint_as_float(v[g * 8 + 0]), __uint_as_float(v[g * 8 + 1]));
-            u.y = pack_bf16x2(__uint_as_float(v[g * 8 + 2]), __uint_as_float(v[g * 8 + 3]));
-            u.z = pack_bf16x2(__uint_as_float(v[g * 8 + 4]), __uint_as_float(v[g * 8 + 5]));
-            u.w = pack_bf16x2(__uint_as_float(v[g * 8 + 6]), __uint_as_float(v[g * 8 + 7]));
-            *reinterpret_cast<uint4*>(dst + c + g * 8) = u;
-          }
-        }
-      };
-      if constexpr (MODE == MODE_DKDV) {
-        store_acc(tmem_acc2, (H + kvh) * HD);         // dK
-        store_acc(tmem_acc1, (H + KVH + kvh) * HD);   // dV
-      } else {
-        store_acc(tmem_acc2, head_lo * HD);           // dQ
-      }
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) {
-    tc_fence_after();
-    tmem_dealloc(tmem, 512);
-  }
-}
-
-static int g_attn_fwd_version = 2;
-static int g_attn_bwd_version = 3;
-
-// ============================================================================================ backward v2
-// Same math / operand layouts as attn_bwd_kernel, re-pipelined: two row-owner warpgroups alternate iterations
-// (WG p owns T[p] and its own P^T/dS^T smem tiles), the streamed (Q,dO)/(K,V) ring is 3 deep and the score GEMMs
-// run two iterations ahead of the accumulate GEMMs, so neither the tensor pipe nor the row owners wait on a
-// single-buffered hand-off.  384 threads: warp 0 TMA, warp 1 MMA, warps 4-7 WG0, warps 8-11 WG1.
 B200_DEVINL void bulk_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
-}
-
-template <int HD>
-struct Bwd2Cfg {
-  static constexpr int NCH = HD / 64;
-  static constexpr int X_BYTES = 128 * HD * 2;
-  static constexpr int Y_BYTES = 64 * HD * 2;
-  static constexpr int Y_CHUNK = 64 * 128;
-  static constexpr int W_BYTES = 128 * 64 * 2;
-  static constexpr int STAGES = 3;
-  static constexpr int STAT_BYTES = 128 * 4;   // per stage: lse2[64] | delta[64] of the streamed q rows (DKDV)
-  static constexpr int SMEM = 2 * X_BYTES + STAGES * 2 * Y_BYTES + STAGES * STAT_BYTES + 1024 + 256;
-};
-
-// one 32-column chunk of the row owner's work: (S or S^T, dP or dP^T) fp32 -> P, dS as packed bf16 pairs written
-// back into TENSOR MEMORY over the first 16 of the 32 columns just read (row per lane): they become the TMEM-A
-// operands of the accumulate GEMMs, so neither P nor dS ever touches shared memory.
-template <int MODE, bool MASK>
-B200_DEVINL void bwd_chunk(const uint32_t (&a)[32], const uint32_t (&d)[32], uint32_t tP, uint32_t tdS, int c,
-                           int x_idx, int y0, int S, const float* stat, float row_lse2, float row_delta,
-                           float scale_log2, float scale) {
-  uint32_t pk[16], dk[16];
-#pragma unroll
-  for (int i = 0; i < 32; i += 2) {
-    float pv[2], dv[2];
-#pragma unroll
-    for (int e = 0; e < 2; ++e) {
-      float l2, dl;
-      if constexpr (MODE == MODE_DKDV) { l2 = stat[c + i + e]; dl = stat[64 + c + i + e]; }
-      else { l2 = row_lse2; dl = row_delta; }
-      float p = exp2f(fmaf(__uint_as_float(a[i + e]), scale_log2, -l2));
-      if constexpr (MASK) {
-        const int y_idx = y0 + c + i + e;
-        const bool masked = (MODE == MODE_DKDV) ? ((x_idx > y_idx) || (y_idx >= S) || (x_idx >= S))
-                                                : ((y_idx > x_idx) || (y_idx >= S) || (x_idx >= S));
-        if (masked) p = 0.f;
-      }
-      pv[e] = p;
-      dv[e] = p * (__uint_as_float(d[i + e]) - dl) * scale;
-    }
-    pk[i >> 1] = pack_bf16x2(pv[0], pv[1]);
-    dk[i >> 1] = pack_bf16x2(dv[0], dv[1]);
-  }
-  if constexpr (MODE == MODE_DKDV) tmem_st_32x32b_x16(tP, pk);
-  tmem_st_32x32b_x16(tdS, dk);
 }
 
 #ifdef B200_ATTN_TRACE
@@ -922,232 +432,6 @@ __device__ int g_attn_trace_mode = 0;
 #define ATRACE_INIT() do {} while (0)
 #define ATRACE(it, slot) do {} while (0)
 #endif
-
-template <int HD, int MODE>
-__global__ void __launch_bounds__(ATT2_THREADS, 1)
-attn_bwd2_kernel(const __grid_constant__ CUtensorMap tm_qkv128, const __grid_constant__ CUtensorMap tm_qkv64,
-                 const __grid_constant__ CUtensorMap tm_do128, const __grid_constant__ CUtensorMap tm_do64,
-                 const float* __restrict__ lse2g, const float* __restrict__ delta, __nv_bfloat16* __restrict__ dqkv,
-                 int S, int H, int KVH, float scale, int n_t128, int ld) {
-  using C = Bwd2Cfg<HD>;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sX1 = smem;
-  uint8_t* sX2 = sX1 + C::X_BYTES;
-  uint8_t* sY = sX2 + C::X_BYTES;                          // [stage][Y1 | Y2]
-  float* sStat = reinterpret_cast<float*>(sY + C::STAGES * 2 * C::Y_BYTES);   // [stage][lse2 64 | delta 64]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sStat) + C::STAGES * C::STAT_BYTES);
-  uint64_t* x_full = bars;
-  uint64_t* y_full = bars + 1;     // [3]
-  uint64_t* y_empty = bars + 4;    // [3]
-  uint64_t* t_full = bars + 7;     // [2]
-  uint64_t* w_full = bars + 9;     // [2]
-  uint64_t* acc_done = bars + 11;  // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int G = H / KVH;
-  const int b = blockIdx.z;
-  const float scale_log2 = scale * LOG2E;
-  int t128, head_lo, head_n, kvh;
-  if constexpr (MODE == MODE_DKDV) {
-    t128 = blockIdx.x; kvh = blockIdx.y; head_lo = kvh * G; head_n = G;
-  } else {
-    t128 = n_t128 - 1 - blockIdx.x; head_lo = blockIdx.y; head_n = 1; kvh = blockIdx.y / G;
-  }
-  const int n64 = (S + 63) / 64;
-  const int s_lo = (MODE == MODE_DKDV) ? 2 * t128 : 0;
-  const int s_hi = (MODE == MODE_DKDV) ? n64 : min(n64, 2 * t128 + 2);
-  const int per_head = s_hi - s_lo;
-  const int n_iter = per_head * head_n;
-  const int xrow0 = b * S + t128 * 128;
-  constexpr uint32_t Y_TX = 2 * C::Y_BYTES + (MODE == MODE_DKDV ? C::STAT_BYTES : 0);
-
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tm_qkv128); tma_prefetch_desc(&tm_qkv64);
-    tma_prefetch_desc(&tm_do128); tma_prefetch_desc(&tm_do64);
-    mbar_init(x_full, 1);
-    for (int i = 0; i < 3; ++i) { mbar_init(&y_full[i], 1); mbar_init(&y_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&t_full[i], 1); mbar_init(&w_full[i], 8); mbar_init(&acc_done[i], 1); }
-    fence_barrier_init();
-  }
-  if (warp == 1) tmem_alloc(tmem_slot, 512);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem = *tmem_slot;
-  const uint32_t tmem_acc1 = tmem + 256, tmem_acc2 = tmem + 384;
-
-  if (warp == 0) {
-    if (lane == 0) {
-      mbar_arrive_expect_tx(x_full, 2 * C::X_BYTES);
-      for (int c = 0; c < C::NCH; ++c) {
-        if constexpr (MODE == MODE_DKDV) {
-          tma_load_2d(sX1 + c * 16384, &tm_qkv128, x_full, (H + kvh) * HD + 64 * c, xrow0);
-          tma_load_2d(sX2 + c * 16384, &tm_qkv128, x_full, (H + KVH + kvh) * HD + 64 * c, xrow0);
-        } else {
-          tma_load_2d(sX1 + c * 16384, &tm_qkv128, x_full, head_lo * HD + 64 * c, xrow0);
-          tma_load_2d(sX2 + c * 16384, &tm_do128, x_full, head_lo * HD + 64 * c, xrow0);
-        }
-      }
-      int st = 0;
-      uint32_t ph = 0;
-      for (int it = 0; it < n_iter; ++it) {
-        const int hh = head_lo + it / per_head;
-        const int t64 = s_lo + it % per_head;
-        const int yrow = b * S + t64 * 64;
-        uint8_t* y1 = sY + st * 2 * C::Y_BYTES;
-        uint8_t* y2 = y1 + C::Y_BYTES;
-        mbar_wait(&y_empty[st], ph ^ 1);
-        mbar_arrive_expect_tx(&y_full[st], Y_TX);
-        for (int c = 0; c < C::NCH; ++c) {
-          if constexpr (MODE == MODE_DKDV) {
-            tma_load_2d(y1 + c * C::Y_CHUNK, &tm_qkv64, &y_full[st], hh * HD + 64 * c, yrow);
-            tma_load_2d(y2 + c * C::Y_CHUNK, &tm_do64, &y_full[st], hh * HD + 64 * c, yrow);
-          } else {
-            tma_load_2d(y1 + c * C::Y_CHUNK, &tm_qkv64, &y_full[st], (H + kvh) * HD + 64 * c, yrow);
-            tma_load_2d(y2 + c * C::Y_CHUNK, &tm_qkv64, &y_full[st], (H + KVH + kvh) * HD + 64 * c, yrow);
-          }
-        }
-        if constexpr (MODE == MODE_DKDV) {
-          // per-column softmax statistics of the streamed q rows ride on the same barrier (two 256 B bulk copies)
-          const size_t so = ((size_t)b * H + hh) * ld + (size_t)t64 * 64;
-          bulk_load_1d(sStat + st * 128, lse2g + so, 256, &y_full[st]);
-          bulk_load_1d(sStat + st * 128 + 64, delta + so, 256, &y_full[st]);
-        }
-        if (++st == 3) { st = 0; ph ^= 1; }
-      }
-    }
-  } else if (warp == 1) {
-    constexpr uint32_t idesc_t = make_idesc_bf16(128, 64, false, false);
-    constexpr uint32_t idesc_a = make_idesc_bf16(128, HD, false, true);
-    auto issue_scores = [&](int it) {
-      const int st = it % 3;
-      mbar_wait(&y_full[st], (it / 3) & 1);
-      tc_fence_after();
-      if (lane == 0) {
-        const uint32_t x1 = smem_u32(sX1), x2 = smem_u32(sX2);
-        const uint32_t y1 = smem_u32(sY + st * 2 * C::Y_BYTES), y2 = y1 + C::Y_BYTES;
-        const uint32_t t1 = tmem + (it & 1) * 128, t2 = t1 + 64;
-#pragma unroll
-        for (int kk = 0; kk < HD / 16; ++kk) {
-          const uint32_t xo = (kk >> 2) * 16384 + (kk & 3) * 32;
-          const uint32_t yo = (kk >> 2) * C::Y_CHUNK + (kk & 3) * 32;
-          umma_bf16_ss(t1, make_smem_desc(x1 + xo, 0, 1024), make_smem_desc(y1 + yo, 0, 1024), idesc_t, kk != 0);
-        }
-#pragma unroll
-        for (int kk = 0; kk < HD / 16; ++kk) {
-          const uint32_t xo = (kk >> 2) * 16384 + (kk & 3) * 32;
-          const uint32_t yo = (kk >> 2) * C::Y_CHUNK + (kk & 3) * 32;
-          umma_bf16_ss(t2, make_smem_desc(x2 + xo, 0, 1024), make_smem_desc(y2 + yo, 0, 1024), idesc_t, kk != 0);
-        }
-        umma_commit(&t_full[it & 1]);
-      }
-      __syncwarp();
-    };
-    mbar_wait(x_full, 0);
-    if (n_iter > 0) issue_scores(0);
-    for (int it = 0; it < n_iter; ++it) {
-      const int p = it & 1, st = it % 3;
-      if (it + 1 < n_iter) issue_scores(it + 1);   // T[(it+1)&1] was drained before w_full(it-1) was signalled
-      mbar_wait(&w_full[p], (it >> 1) & 1);
-      tc_fence_after();
-      if (lane == 0) {
-        const uint32_t y1 = smem_u32(sY + st * 2 * C::Y_BYTES), y2 = y1 + C::Y_BYTES;
-        // P^T / dS^T (or dS) sit in TMEM over the score columns: warpgroup g wrote the 16 packed columns of its
-        // 32-column half at column offset 32*g  ->  K-step t (16 streamed rows) = 8 columns at 32*(t/2) + 8*(t%2)
-        const uint32_t tP = tmem + p * 128, tdS = tP + 64;
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          const uint32_t co = 32 * (t >> 1) + 8 * (t & 1);
-          if constexpr (MODE == MODE_DKDV)
-            umma_bf16_ts(tmem_acc1, tP + co, make_smem_desc(y2 + t * 2048, C::Y_CHUNK, 1024), idesc_a, (it | t) != 0);
-          umma_bf16_ts(tmem_acc2, tdS + co, make_smem_desc(y1 + t * 2048, C::Y_CHUNK, 1024), idesc_a, (it | t) != 0);
-        }
-        umma_commit(&y_empty[st]);
-        umma_commit(&acc_done[p]);
-      }
-      __syncwarp();
-    }
-  } else if (warp >= 4) {
-    // 8 row-owner warps; warpgroup g owns columns [32g, 32g+32) of EVERY iteration's 128 x 64 score tiles
-    const int g = (warp - 4) >> 2;
-    const int p = g;                          // (epilogue split below)
-    const int q4 = warp & 3;
-    const int r = q4 * 32 + lane;
-    const uint32_t lane_addr = static_cast<uint32_t>(q4 * 32) << 16;
-    const int x_idx = t128 * 128 + r;
-    float row_lse2 = 0.f, row_delta = 0.f;
-    if constexpr (MODE == MODE_DQ) {
-      const size_t sidx = ((size_t)b * H + head_lo) * ld + min(x_idx, S - 1);
-      row_lse2 = lse2g[sidx];
-      row_delta = delta[sidx];
-    }
-    for (int it = 0; it < n_iter; ++it) {
-      const int par = it & 1;
-      const int t64 = s_lo + it % per_head;
-      const int y0 = t64 * 64;
-      const int st = it % 3;
-      const float* stat = sStat + st * 128;
-      if constexpr (MODE == MODE_DKDV) mbar_wait(&y_full[st], (it / 3) & 1);   // the stats landed (TMA -> generic visibility)
-      mbar_wait(&t_full[par], (it >> 1) & 1);
-      tc_fence_after();
-      const uint32_t t1 = tmem + par * 128 + lane_addr + 32 * g, t2 = t1 + 64;
-      uint32_t a0[32], d0[32];
-      tmem_ld_32x32b_x32(t1, a0);
-      tmem_ld_32x32b_x32(t2, d0);
-      tmem_ld_wait();
-      // only tiles touching the causal diagonal or the sequence end need per-element masking
-      const bool need_mask = (y0 < t128 * 128 + 128 && y0 + 64 > t128 * 128) || (y0 + 64 > S) || (t128 * 128 + 128 > S);
-      if (need_mask)
-        bwd_chunk<MODE, true>(a0, d0, t1, t2, 32 * g, x_idx, y0, S, stat, row_lse2, row_delta, scale_log2, scale);
-      else
-        bwd_chunk<MODE, false>(a0, d0, t1, t2, 32 * g, x_idx, y0, S, stat, row_lse2, row_delta, scale_log2, scale);
-      tmem_st_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&w_full[par]);
-    }
-    // epilogue: WG0 stores acc2 (dK | dQ), WG1 stores acc1 (dV); in DQ mode the two groups split acc2's columns
-    if (n_iter > 0) mbar_wait(&acc_done[(n_iter - 1) & 1], ((n_iter - 1) >> 1) & 1);
-    tc_fence_after();
-    if (x_idx < S) {
-      const size_t row = (size_t)b * S + x_idx;
-      const int Wd = (H + 2 * KVH) * HD;
-      auto store_acc = [&](uint32_t tacc, int col0, int c_lo, int c_hi) {
-        __nv_bfloat16* dst = dqkv + row * Wd + col0;
-#pragma unroll 1
-        for (int c = c_lo; c < c_hi; c += 32) {
-          uint32_t v[32];
-          tmem_ld_32x32b_x32(tacc + lane_addr + c, v);
-          tmem_ld_wait();
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            uint4 u;
-            u.x = pack_bf16x2(__uint_as_float(v[g * 8 + 0]), __uint_as_float(v[g * 8 + 1]));
-            u.y = pack_bf16x2(__uint_as_float(v[g * 8 + 2]), __uint_as_float(v[g * 8 + 3]));
-            u.z = pack_bf16x2(__uint_as_float(v[g * 8 + 4]), __uint_as_float(v[g * 8 + 5]));
-            u.w = pack_bf16x2(__uint_as_float(v[g * 8 + 6]), __uint_as_float(v[g * 8 + 7]));
-            *reinterpret_cast<uint4*>(dst + c + g * 8) = u;
-          }
-        }
-      };
-      if constexpr (MODE == MODE_DKDV) {
-        if (p == 0) store_acc(tmem_acc2, (H + kvh) * HD, 0, HD);
-        else        store_acc(tmem_acc1, (H + KVH + kvh) * HD, 0, HD);
-      } else {
-        if (p == 0) store_acc(tmem_acc2, head_lo * HD, 0, HD / 2);
-        else        store_acc(tmem_acc2, head_lo * HD, HD / 2, HD);
-      }
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) {
-    tc_fence_after();
-    tmem_dealloc(tmem, 512);
-  }
-}
 
 // ================================================================================ backward, version 3
 // Measured on the v2 kernel (scripts/attn_trace.cu, profiles/attn_bwd2_pipeline_trace_r1.txt): the tensor pipe idled
@@ -1180,38 +464,75 @@ B200_DEVINL float4 lds128(const float* p) {
   return v;
 }
 
-// E phase of one row owner: 64 fp32 scores -> P = exp2(s * scale_log2 - lse2) (masked), packed bf16 pairs
-template <int MODE, bool MASK>
-B200_DEVINL void bwd3_exp(const uint32_t (&a)[64], uint32_t (&pk)[32], const float* stat, float row_lse2,
+// E phase of one row owner: 64 fp32 scores -> P = exp2(s * scale_log2 - lse2) (masked), packed bf16 pairs.
+// ``nstat`` / ``row_nlse2`` hold -lse2 (attn_delta_kernel stores the statistics negated).
+template <int MODE, bool MASK, int PP>
+B200_DEVINL void bwd3_exp(const uint32_t (&a)[64], uint32_t (&pk)[32], const float* nstat, float row_nlse2,
                           float scale_log2, int x_idx, int yb, int S) {
+  const f32x2_t sc2 = f2_pack(scale_log2, scale_log2), rn2 = f2_pack(row_nlse2, row_nlse2);
 #pragma unroll
-  for (int i = 0; i < 64; i += 4) {
-    float l2[4];
+  for (int i = 0; i < 64; i += 8) {
+    f32x2_t nl[4];
     if constexpr (MODE == MODE_DKDV) {
-      const float4 v = lds128(stat + i);
-      l2[0] = v.x; l2[1] = v.y; l2[2] = v.z; l2[3] = v.w;
+      const float4 u = lds128(nstat + i), w = lds128(nstat + i + 4);
+      nl[0] = f2_pack(u.x, u.y); nl[1] = f2_pack(u.z, u.w); nl[2] = f2_pack(w.x, w.y); nl[3] = f2_pack(w.z, w.w);
     } else {
-      l2[0] = l2[1] = l2[2] = l2[3] = row_lse2;
+      nl[0] = nl[1] = nl[2] = nl[3] = rn2;
     }
-    float p[4];
+    f32x2_t x[4], y[4];
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      // (measured: routing 1/4 of these through exp2_poly -- FMA-pipe exponential -- was 2 % SLOWER; the row owners are
-      // issue/latency bound here, not MUFU bound)
-      p[e] = exp2f(fmaf(__uint_as_float(a[i + e]), scale_log2, -l2[e]));
+    for (int q = 0; q < 4; ++q)
+      x[q] = f2_fma(f2_pack(__uint_as_float(a[i + 2 * q]), __uint_as_float(a[i + 2 * q + 1])), sc2, nl[q]);
+    exp2_group8<PP>(x, y);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      float p[2];
+      f2_unpack(y[q], p[0], p[1]);
       if constexpr (MASK) {
-        const int y_idx = yb + i + e;
-        const bool masked = (MODE == MODE_DKDV) ? ((x_idx > y_idx) || (y_idx >= S) || (x_idx >= S))
-                                                : ((y_idx > x_idx) || (y_idx >= S) || (x_idx >= S));
-        if (masked) p[e] = 0.f;
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int y_idx = yb + i + 2 * q + e;
+          const bool masked = (MODE == MODE_DKDV) ? ((x_idx > y_idx) || (y_idx >= S) || (x_idx >= S))
+                                                  : ((y_idx > x_idx) || (y_idx >= S) || (x_idx >= S));
+          if (masked) p[e] = 0.f;
+        }
       }
+      pk[(i >> 1) + q] = pack_bf16x2(p[0], p[1]);
     }
-    pk[i >> 1] = pack_bf16x2(p[0], p[1]);
-    pk[(i >> 1) + 1] = pack_bf16x2(p[2], p[3]);
   }
 }
 
-template <int HD, int MODE>
+// D phase: dS = P * (dP - delta) (unscaled), packed bf16 pairs.  ``nstat`` / ``row_ndelta`` hold -delta.
+template <int MODE, bool MASK>
+B200_DEVINL void bwd3_ds(const uint32_t (&d)[64], const uint32_t (&pk)[32], uint32_t (&dk)[32], const float* nstat,
+                         float row_ndelta) {
+  const f32x2_t rd2 = f2_pack(row_ndelta, row_ndelta);
+#pragma unroll
+  for (int i = 0; i < 64; i += 8) {
+    f32x2_t nd[4];
+    if constexpr (MODE == MODE_DKDV) {
+      const float4 u = lds128(nstat + i), w = lds128(nstat + i + 4);
+      nd[0] = f2_pack(u.x, u.y); nd[1] = f2_pack(u.z, u.w); nd[2] = f2_pack(w.x, w.y); nd[3] = f2_pack(w.z, w.w);
+    } else {
+      nd[0] = nd[1] = nd[2] = nd[3] = rd2;
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const uint32_t pp = pk[(i >> 1) + q];
+      const f32x2_t p2 = f2_pack(__uint_as_float(pp << 16), __uint_as_float(pp & 0xffff0000u));
+      const f32x2_t v2 = f2_mul(p2, f2_add(f2_pack(__uint_as_float(d[i + 2 * q]), __uint_as_float(d[i + 2 * q + 1])), nd[q]));
+      float v0, v1;
+      f2_unpack(v2, v0, v1);
+      if constexpr (MASK) {   // masked / padded entries: the statistics may be garbage (NaN * 0)
+        if ((pp & 0xffffu) == 0) v0 = 0.f;
+        if ((pp >> 16) == 0) v1 = 0.f;
+      }
+      dk[(i >> 1) + q] = pack_bf16x2(v0, v1);
+    }
+  }
+}
+
+template <int HD, int MODE, int PP>
 __global__ void __launch_bounds__(ATT2_THREADS, 1)
 attn_bwd3_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do,
                  const float* __restrict__ lse2g, const float* __restrict__ delta, __nv_bfloat16* __restrict__ dqkv,
@@ -1407,18 +728,23 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_consta
       uint32_t pk[32];                             // P of this thread's 64 columns, packed bf16 (kept for the dS phase)
       // ---------------- E phase: S -> P
       if constexpr (MODE == MODE_DKDV) mbar_wait(&y1_full[st], (it >> 1) & 1);   // column statistics have landed
-      if (lane == 0 && q4 == 0) ATRACE(it, 4 + 5 * g);
+      if (lane == 0 && q4 == 0 && g == 0) ATRACE(it, 4);
       mbar_wait(s_full, ph);
       tc_fence_after();
-      if (lane == 0 && q4 == 0) ATRACE(it, 5 + 5 * g);
+      if (lane == 0 && q4 == 0 && g == 0) ATRACE(it, 5);
       {
         uint32_t a[64];
         tmem_ld_32x32b_x32(ts, *reinterpret_cast<uint32_t(*)[32]>(&a[0]));
         tmem_ld_32x32b_x32(ts + 32, *reinterpret_cast<uint32_t(*)[32]>(&a[32]));
         tmem_ld_wait();
-        if (need_mask) bwd3_exp<MODE, true>(a, pk, stat, row_lse2, scale_log2, x_idx, yb, S);
-        else           bwd3_exp<MODE, false>(a, pk, stat, row_lse2, scale_log2, x_idx, yb, S);
+        if (lane == 0 && q4 == 0 && g == 0) ATRACE(it, 9);
+        if (need_mask) bwd3_exp<MODE, true, PP>(a, pk, stat, row_lse2, scale_log2, x_idx, yb, S);
+        else           bwd3_exp<MODE, false, PP>(a, pk, stat, row_lse2, scale_log2, x_idx, yb, S);
       }
+#ifdef B200_ATTN_TRACE
+      asm volatile("" ::"r"(pk[0]), "r"(pk[31]) : "memory");   // the exponentials are done before the stamp
+#endif
+      if (lane == 0 && q4 == 0 && g == 0) ATRACE(it, 10);
       if constexpr (MODE == MODE_DKDV) {
         tmem_st_32x32b_x16(ts, *reinterpret_cast<uint32_t(*)[16]>(&pk[0]));
         tmem_st_32x32b_x16(ts + 16, *reinterpret_cast<uint32_t(*)[16]>(&pk[16]));
@@ -1427,38 +753,20 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_consta
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(p_full);
-      if (lane == 0 && q4 == 0) ATRACE(it, 6 + 5 * g);
+      if (lane == 0 && q4 == 0 && g == 0) ATRACE(it, 6);
       // ---------------- D phase: dP, P -> dS (unscaled)
       mbar_wait(dp_full, ph);
       tc_fence_after();
-      if (lane == 0 && q4 == 0) ATRACE(it, 7 + 5 * g);
+      if (lane == 0 && q4 == 0 && g == 0) ATRACE(it, 7);
       {
         uint32_t d[64];
         tmem_ld_32x32b_x32(td, *reinterpret_cast<uint32_t(*)[32]>(&d[0]));
         tmem_ld_32x32b_x32(td + 32, *reinterpret_cast<uint32_t(*)[32]>(&d[32]));
         tmem_ld_wait();
+        if (lane == 0 && q4 == 0 && g == 0) ATRACE(it, 11);
         uint32_t dk[32];
-#pragma unroll
-        for (int i = 0; i < 64; i += 4) {
-          float dl[4];
-          if constexpr (MODE == MODE_DKDV) {
-            const float4 v = lds128(stat + 128 + i);
-            dl[0] = v.x; dl[1] = v.y; dl[2] = v.z; dl[3] = v.w;
-          } else {
-            dl[0] = dl[1] = dl[2] = dl[3] = row_delta;
-          }
-          const float2 p01 = unpack_bf16x2(pk[i >> 1]), p23 = unpack_bf16x2(pk[(i >> 1) + 1]);
-          const float pp[4] = {p01.x, p01.y, p23.x, p23.y};
-          float dv[4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            float v = pp[e] * (__uint_as_float(d[i + e]) - dl[e]);
-            if (need_mask && pp[e] == 0.f) v = 0.f;   // masked / padded entries: statistics may be garbage (NaN * 0)
-            dv[e] = v;
-          }
-          dk[i >> 1] = pack_bf16x2(dv[0], dv[1]);
-          dk[(i >> 1) + 1] = pack_bf16x2(dv[2], dv[3]);
-        }
+        if (need_mask) bwd3_ds<MODE, true>(d, pk, dk, stat + 128, row_delta);
+        else           bwd3_ds<MODE, false>(d, pk, dk, stat + 128, row_delta);
         tmem_st_32x32b_x16(td, *reinterpret_cast<uint32_t(*)[16]>(&dk[0]));
         tmem_st_32x32b_x16(td + 16, *reinterpret_cast<uint32_t(*)[16]>(&dk[16]));
       }
@@ -1466,7 +774,7 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_consta
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(ds_full);
-      if (lane == 0 && q4 == 0) ATRACE(it, 8 + 5 * g);
+      if (lane == 0 && q4 == 0 && g == 0) ATRACE(it, 8);
     }
     // epilogue: warpgroup 0 stores acc2 (dK | dQ, times the softmax scale), warpgroup 1 acc1 (dV); in DQ mode the two
     // groups split acc2's columns
@@ -1526,14 +834,18 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_consta
   }
 }
 
-template <int HD>
+// pairs (of every 4) whose exponential runs on the FMA pipe instead of the MUFU: 0 = all MUFU (round-1 behaviour)
+static int g_attn_poly_fwd = 0;
+static int g_attn_poly_bwd = 1;
+
+template <int HD, int PP>
 static int launch_fwd2(const void* qkv, void* o, float* lse, int B, int S, int H, int KVH, float scale,
                        cudaStream_t st) {
   using C = Fwd2Cfg<HD>;
   CUtensorMap tm;
   const int W = (H + 2 * KVH) * HD;
   if (make_tmap_2d_bf16(&tm, qkv, (uint64_t)W, (uint64_t)B * S, (uint64_t)W, 64, 128)) return -3;
-  auto kern = attn_fwd2_kernel<HD>;
+  auto kern = attn_fwd2_kernel<HD, PP>;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
@@ -1549,107 +861,71 @@ static int launch_fwd2(const void* qkv, void* o, float* lse, int B, int S, int H
 template <int HD>
 static int launch_fwd(const void* qkv, void* o, float* lse, int B, int S, int H, int KVH, float scale,
                       cudaStream_t st) {
-  if (g_attn_fwd_version == 2) return launch_fwd2<HD>(qkv, o, lse, B, S, H, KVH, scale, st);
-  using C = FwdCfg<HD>;
-  CUtensorMap tm;
-  const int W = (H + 2 * KVH) * HD;
-  if (make_tmap_2d_bf16(&tm, qkv, (uint64_t)W, (uint64_t)B * S, (uint64_t)W, 64, 128)) return -3;
-  auto kern = attn_fwd_kernel<HD>;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
-    if (e != cudaSuccess) return (int)e;
-    configured = true;
+  switch (g_attn_poly_fwd) {
+    case 0: return launch_fwd2<HD, 0>(qkv, o, lse, B, S, H, KVH, scale, st);
+    case 1: return launch_fwd2<HD, 1>(qkv, o, lse, B, S, H, KVH, scale, st);
+    case 3: return launch_fwd2<HD, 3>(qkv, o, lse, B, S, H, KVH, scale, st);
+    default: return launch_fwd2<HD, 2>(qkv, o, lse, B, S, H, KVH, scale, st);
   }
-  const int n_qt = (S + 127) / 128;
-  dim3 grid(n_qt, H, B);
-  kern<<<grid, ATT_THREADS, C::SMEM, st>>>(tm, (__nv_bfloat16*)o, lse, S, H, KVH, scale * LOG2E, n_qt);
+}
+
+template <int HD, int PP>
+static int launch_bwd3(const CUtensorMap& q128, const CUtensorMap& d128, const float* lse2p, const float* delta, void* dqkv,
+                       int B, int S, int H, int KVH, float scale, int n_t, int ld3, const float* rope, cudaStream_t st) {
+  using C3 = Bwd3Cfg<HD>;
+  auto j1 = attn_bwd3_kernel<HD, MODE_DKDV, PP>;
+  auto j2 = attn_bwd3_kernel<HD, MODE_DQ, PP>;
+  static bool configured3 = false;
+  if (!configured3) {
+    cudaError_t e = cudaFuncSetAttribute(j1, cudaFuncAttributeMaxDynamicSharedMemorySize, C3::SMEM);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute(j2, cudaFuncAttributeMaxDynamicSharedMemorySize, C3::SMEM);
+    if (e != cudaSuccess) return (int)e;
+    configured3 = true;
+  }
+  j1<<<dim3(n_t, KVH, B), ATT2_THREADS, C3::SMEM, st>>>(q128, d128, lse2p, delta, (__nv_bfloat16*)dqkv, S, H, KVH, scale,
+                                                       n_t, ld3, rope);
+  j2<<<dim3(n_t, H, B), ATT2_THREADS, C3::SMEM, st>>>(q128, d128, lse2p, delta, (__nv_bfloat16*)dqkv, S, H, KVH, scale,
+                                                     n_t, ld3, rope);
   return (int)cudaGetLastError();
 }
 
 template <int HD>
 static int launch_bwd(const void* dout, const void* qkv, const void* o, const float* lse, void* dqkv, float* delta,
                       int B, int S, int H, int KVH, float scale, const float* rope, cudaStream_t st) {
-  using C = BwdCfg<HD>;
   const int W = (H + 2 * KVH) * HD;
-  CUtensorMap q128, q64, d128, d64;
+  CUtensorMap q128, d128;
   if (make_tmap_2d_bf16(&q128, qkv, (uint64_t)W, (uint64_t)B * S, (uint64_t)W, 64, 128)) return -3;
-  if (make_tmap_2d_bf16(&q64, qkv, (uint64_t)W, (uint64_t)B * S, (uint64_t)W, 64, 64)) return -3;
   if (make_tmap_2d_bf16(&d128, dout, (uint64_t)H * HD, (uint64_t)B * S, (uint64_t)H * HD, 64, 128)) return -3;
-  if (make_tmap_2d_bf16(&d64, dout, (uint64_t)H * HD, (uint64_t)B * S, (uint64_t)H * HD, 64, 64)) return -3;
+  // rows padded to a multiple of 128 so a 128-float TMA bulk copy never leaves the row; plane 0 = -delta,
+  // plane 1 = -lse * log2(e)
+  const int ld = ((S + 127) / 128) * 128;
   {
-    const long long warps = (long long)B * S * H;
-    const int threads = 256;
-    const long long blocks = (warps * 32 + threads - 1) / threads;
-    // v2: rows padded to a multiple of 64 so a 64-float TMA bulk copy never leaves the row; plane 1 = lse * log2(e)
-    const int ld = (g_attn_bwd_version >= 2) ? ((S + 127) / 128) * 128 : S;
-    float* lse2 = (g_attn_bwd_version >= 2) ? delta + (size_t)B * H * ld : nullptr;
-    attn_delta_kernel<<<(unsigned)blocks, threads, 0, st>>>((const __nv_bfloat16*)dout, (const __nv_bfloat16*)o, delta,
-                                                            lse, lse2, B, S, H, HD, ld);
+    const long long lanes = (long long)B * S * H * (HD / 8);
+    const long long blocks = (lanes + 255) / 256;
+    float* lse2 = delta + (size_t)B * H * ld;
+    attn_delta_kernel<HD><<<(unsigned)blocks, 256, 0, st>>>((const __nv_bfloat16*)dout, (const __nv_bfloat16*)o, delta,
+                                                            lse, lse2, B, S, H, ld);
   }
   const int n_t = (S + 127) / 128;
-  if (g_attn_bwd_version == 3) {
-    using C3 = Bwd3Cfg<HD>;
-    auto j1 = attn_bwd3_kernel<HD, MODE_DKDV>;
-    auto j2 = attn_bwd3_kernel<HD, MODE_DQ>;
-    static bool configured3 = false;
-    if (!configured3) {
-      cudaError_t e = cudaFuncSetAttribute(j1, cudaFuncAttributeMaxDynamicSharedMemorySize, C3::SMEM);
-      if (e != cudaSuccess) return (int)e;
-      e = cudaFuncSetAttribute(j2, cudaFuncAttributeMaxDynamicSharedMemorySize, C3::SMEM);
-      if (e != cudaSuccess) return (int)e;
-      configured3 = true;
-    }
-    const int ld3 = ((S + 127) / 128) * 128;
-    const float* lse2p = delta + (size_t)B * H * ld3;
-    j1<<<dim3(n_t, KVH, B), ATT2_THREADS, C3::SMEM, st>>>(q128, d128, lse2p, delta, (__nv_bfloat16*)dqkv, S, H, KVH, scale,
-                                                         n_t, ld3, rope);
-    j2<<<dim3(n_t, H, B), ATT2_THREADS, C3::SMEM, st>>>(q128, d128, lse2p, delta, (__nv_bfloat16*)dqkv, S, H, KVH, scale,
-                                                       n_t, ld3, rope);
-    return (int)cudaGetLastError();
+  const float* lse2p = delta + (size_t)B * H * ld;
+  switch (g_attn_poly_bwd) {
+    case 0: return launch_bwd3<HD, 0>(q128, d128, lse2p, delta, dqkv, B, S, H, KVH, scale, n_t, ld, rope, st);
+    case 1: return launch_bwd3<HD, 1>(q128, d128, lse2p, delta, dqkv, B, S, H, KVH, scale, n_t, ld, rope, st);
+    case 3: return launch_bwd3<HD, 3>(q128, d128, lse2p, delta, dqkv, B, S, H, KVH, scale, n_t, ld, rope, st);
+    default: return launch_bwd3<HD, 2>(q128, d128, lse2p, delta, dqkv, B, S, H, KVH, scale, n_t, ld, rope, st);
   }
-  if (rope) return -9;   // only the v3 kernels fuse the inverse RoPE
-  if (g_attn_bwd_version == 2) {
-    using C2 = Bwd2Cfg<HD>;
-    auto j1 = attn_bwd2_kernel<HD, MODE_DKDV>;
-    auto j2 = attn_bwd2_kernel<HD, MODE_DQ>;
-    static bool configured2 = false;
-    if (!configured2) {
-      cudaError_t e = cudaFuncSetAttribute(j1, cudaFuncAttributeMaxDynamicSharedMemorySize, C2::SMEM);
-      if (e != cudaSuccess) return (int)e;
-      e = cudaFuncSetAttribute(j2, cudaFuncAttributeMaxDynamicSharedMemorySize, C2::SMEM);
-      if (e != cudaSuccess) return (int)e;
-      configured2 = true;
-    }
-    const int ld2 = ((S + 127) / 128) * 128;
-    const float* lse2p = delta + (size_t)B * H * ld2;
-    j1<<<dim3(n_t, KVH, B), ATT2_THREADS, C2::SMEM, st>>>(q128, q64, d128, d64, lse2p, delta, (__nv_bfloat16*)dqkv, S, H,
-                                                         KVH, scale, n_t, ld2);
-    j2<<<dim3(n_t, H, B), ATT2_THREADS, C2::SMEM, st>>>(q128, q64, d128, d64, lse2p, delta, (__nv_bfloat16*)dqkv, S, H, KVH,
-                                                       scale, n_t, ld2);
-    return (int)cudaGetLastError();
-  }
-  auto k1 = attn_bwd_kernel<HD, MODE_DKDV>;
-  auto k2 = attn_bwd_kernel<HD, MODE_DQ>;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
-    if (e != cudaSuccess) return (int)e;
-    e = cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
-    if (e != cudaSuccess) return (int)e;
-    configured = true;
-  }
-  k1<<<dim3(n_t, KVH, B), ATT_THREADS, C::SMEM, st>>>(q128, q64, d128, d64, lse, delta, (__nv_bfloat16*)dqkv, S, H, KVH,
-                                                     scale, n_t);
-  k2<<<dim3(n_t, H, B), ATT_THREADS, C::SMEM, st>>>(q128, q64, d128, d64, lse, delta, (__nv_bfloat16*)dqkv, S, H, KVH,
-                                                   scale, n_t);
-  return (int)cudaGetLastError();
 }
 
 }  // namespace b200
 
-extern "C" void b200_attn_set_fwd_version(int v) { b200::g_attn_fwd_version = v; }
-extern "C" void b200_attn_set_bwd_version(int v) { b200::g_attn_bwd_version = v; }
+// (superseded kernel generations were removed in round 2; the selectors are kept as no-ops for old scripts)
+extern "C" void b200_attn_set_fwd_version(int) {}
+extern "C" void b200_attn_set_bwd_version(int) {}
+extern "C" void b200_attn_set_poly(int fwd_pairs, int bwd_pairs) {
+  if (fwd_pairs >= 0 && fwd_pairs <= 3) b200::g_attn_poly_fwd = fwd_pairs;
+  if (bwd_pairs >= 0 && bwd_pairs <= 3) b200::g_attn_poly_bwd = bwd_pairs;
+}
 extern "C" int b200_attn_fwd(const void* qkv, void* o, float* lse, int B, int S, int H, int KVH, int HD, float scale,
                              cudaStream_t st) {
   if (H % KVH) return -1;

@@ -61,6 +61,7 @@ DECL int b200_adamw(float*, const void*, int, float*, float*, void*, long long, 
 DECL int b200_sumsq(const void*, int, long long, float*, cudaStream_t);
 DECL void b200_attn_set_fwd_version(int);
 DECL void b200_attn_set_bwd_version(int);
+DECL void b200_attn_set_poly(int, int);
 DECL int b200_attn_fwd(const void*, void*, float*, int, int, int, int, int, float, cudaStream_t);
 DECL int b200_attn_bwd(const void*, const void*, const void*, const float*, void*, float*, int, int, int, int, int,
                        float, const float*, cudaStream_t);
@@ -790,6 +791,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("selective_scan_fwd", &selective_scan_fwd);
   m.def("selective_scan_bwd", &selective_scan_bwd);
   m.def("ssd_scan_bwd", &ssd_scan_bwd);
+  m.def("set_attn_poly", [](int64_t f, int64_t b) { b200_attn_set_poly((int)f, (int)b); });
   m.def("set_attn_fwd_version", &set_attn_fwd_version);
   m.def("set_attn_bwd_version", &set_attn_bwd_version);
   m.def("set_gemm_2cta", &set_gemm_2cta);

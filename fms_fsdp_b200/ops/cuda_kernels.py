@@ -21,9 +21,10 @@ _LAYOUT = {"nt": 0, "nn": 1, "tn": 2}
 # attention implementation: "tcgen05" (ours) | "sdpa" (library fallback, debugging only)
 ATTN_IMPL = os.environ.get("FMS_B200_ATTN_IMPL", "tcgen05")
 GEMM_IMPL = os.environ.get("FMS_B200_GEMM_IMPL", "tcgen05")  # "cublas" = library fallback, debugging only
-_C.set_attn_fwd_version(int(os.environ.get("FMS_B200_ATTN_FWD", "2")))  # 2 = two Q tiles/CTA, P in TMEM
-_ATTN_BWD_VERSION = int(os.environ.get("FMS_B200_ATTN_BWD", "3"))
-_C.set_attn_bwd_version(_ATTN_BWD_VERSION)  # 3 = 128-row streamed tiles, two-phase row owners (2 = 64-row tiles)
+# pairs (of every 4) of softmax exponentials computed on the FMA pipe (packed FFMA2 polynomial) instead of the MUFU
+# (measured, profiles/attn_bench_r2.json: the split is performance-neutral -- the row owners are bound by the dependency
+# chain S -> exp -> P -> next MMA, not by MUFU throughput -- so the defaults stay at 0 / 1)
+_C.set_attn_poly(int(os.environ.get("FMS_B200_ATTN_POLY_FWD", "0")), int(os.environ.get("FMS_B200_ATTN_POLY_BWD", "1")))
 _C.set_gemm_2cta(os.environ.get("FMS_B200_GEMM_2CTA", "1") == "1")  # CTA-pair (cta_group::2) GEMM for M >= 256
 
 
@@ -311,12 +312,7 @@ def attn_bwd(do, qkv, o, lse, B, S, H, KVH, hd, scale, causal=True, rope_table=N
     """``rope_table``: the forward applied RoPE (full head_dim, interleaved) to q, k before this attention; return the
     gradient of the UN-rotated projection (inverse rotation fused into the dq / dk epilogues)."""
     if ATTN_IMPL == "tcgen05" and qkv.dtype == torch.bfloat16 and hd in (64, 128) and causal:
-        fused = rope_table is not None and _ATTN_BWD_VERSION == 3
-        g = _C.attn_bwd(do.contiguous(), qkv.contiguous(), o, lse, B, S, H, KVH, hd, float(scale),
-                        rope_table if fused else None)
-        if rope_table is not None and not fused:
-            rope_(g, rope_table, S, H, KVH, hd, inverse=True)
-        return g
+        return _C.attn_bwd(do.contiguous(), qkv.contiguous(), o, lse, B, S, H, KVH, hd, float(scale), rope_table)
     if rope_table is not None:
         g = attn_bwd(do, qkv, o, lse, B, S, H, KVH, hd, scale, causal)
         return rope_(g, rope_table, S, H, KVH, hd, inverse=True)

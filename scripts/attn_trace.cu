@@ -21,7 +21,7 @@ int main(int argc, char** argv) {
   cudaMalloc(&lse, (size_t)B * H * S * 4); cudaMalloc(&delta, (size_t)2 * B * H * (S + 128) * 4);
   cudaMemcpy(qkv, h.data(), M * W * 2, cudaMemcpyHostToDevice);
   cudaMemcpy(dout, h.data(), M * H * HD * 2, cudaMemcpyHostToDevice);
-  b200_attn_set_fwd_version(2); b200_attn_set_bwd_version(3);
+  b200_attn_set_poly(argc > 2 ? atoi(argv[2]) : 2, argc > 2 ? atoi(argv[2]) : 2);
   int rc = b200_attn_fwd(qkv, o, lse, B, S, H, KVH, HD, 0.0884f, 0);
   printf("fwd rc %d\n", rc);
   long long* tr;
@@ -37,10 +37,10 @@ int main(int argc, char** argv) {
   std::vector<long long> t(64 * 16);
   cudaMemcpy(t.data(), tr, 64 * 16 * 8, cudaMemcpyDeviceToHost);
   long long t0 = t[0];
-  printf("v3 kernel mode %d.  mma: p_full seen | acc1+S(k+1) issued | ds_full seen | acc2+dP(k+1) issued || wg0: E wait, s_full, E done(p arrive), dp_full, D done || wg1: same\n", mode);
+  printf("v3 kernel mode %d.  slots 0-3 mma: p_full seen | acc1+S(k+1) issued | ds_full seen | acc2+dP(k+1) issued || wg0: 4 E wait, 5 s_full, 6 E done(p arrive), 7 dp_full, 8 D done, 9 S loaded, 10 exp done, 11 dP loaded\n", mode);
   for (int it = 0; it < 24; ++it) {
     printf("%2d |", it);
-    for (int s = 0; s < 16; ++s) printf(" %7lld", t[it * 16 + s] ? t[it * 16 + s] - t0 : -1);
+    for (int s = 0; s < 12; ++s) printf(" %7lld", t[it * 16 + s] ? t[it * 16 + s] - t0 : -1);
     printf("\n");
   }
   }
