@@ -454,8 +454,16 @@ struct Bwd3Cfg {
   static constexpr int NCH = HD / 64;
   static constexpr int T_BYTES = 128 * HD * 2;   // one 128-row operand tile
   static constexpr int CHUNK = 128 * 128;        // one 64-column 128B-swizzled chunk of a tile
-  static constexpr int STAT_BYTES = 256 * 4;     // per stage: lse2[128] | delta[128] of the streamed q rows (DKDV)
-  static constexpr int SMEM = 2 * T_BYTES + 2 * 2 * T_BYTES + 2 * STAT_BYTES + 1024 + 256;
+  static constexpr int STAT_BYTES = 256 * 4;     // per stage: -lse2[128] | -delta[128] of the streamed q rows (DKDV)
+  // Y1 (K in the dQ kernel, Q in the dK/dV kernel) is held from the score GEMM of an iteration until its LAST accumulate
+  // GEMM, so with two stages the refill of a stage (global -> smem, ~1.7k cycles measured) sat on the critical path of
+  // every second iteration (profiles/attn_bwd3_pipeline_trace_r2.txt: 2.7k cycles per iteration against 1.5k of tensor
+  // work in the dQ kernel).  Y1 gets a third stage; Y2 (released early) keeps two.  At HD = 128 that is 7 x 32 KiB of
+  // tiles: the carve-up only fits the 227 KiB of the SM without the usual 1 KiB alignment slack, so the kernel asks for
+  // the maximum and traps if the (in practice 1 KiB-aligned) dynamic base leaves too little room.
+  static constexpr int Y1_STAGES = 3;
+  static constexpr int NEED = (2 + Y1_STAGES + 2) * T_BYTES + 2 * STAT_BYTES + 256;
+  static constexpr int SMEM = (NEED + 1024 <= 232448) ? NEED + 1024 : 232448;
 };
 
 B200_DEVINL float4 lds128(const float* p) {
@@ -542,20 +550,24 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_consta
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sX1 = smem;
   uint8_t* sX2 = sX1 + C::T_BYTES;
-  uint8_t* sY = sX2 + C::T_BYTES;                           // [stage][Y1 | Y2]
-  float* sStat = reinterpret_cast<float*>(sY + 4 * C::T_BYTES);   // [stage][lse2 128 | delta 128]
+  uint8_t* sY1 = sX2 + C::T_BYTES;                          // [3 stages]
+  uint8_t* sY2 = sY1 + C::Y1_STAGES * C::T_BYTES;           // [2 stages]
+  float* sStat = reinterpret_cast<float*>(sY2 + 2 * C::T_BYTES);   // [2 stages][-lse2 128 | -delta 128]
   uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sStat) + 2 * C::STAT_BYTES);
+  if (reinterpret_cast<uint8_t*>(bars) + 256 > smem_raw + C::SMEM) __trap();   // dynamic smem base less aligned than assumed
   uint64_t* x_full = bars;
-  uint64_t* y1_full = bars + 1;    // [2]
-  uint64_t* y2_full = bars + 3;    // [2]
-  uint64_t* y1_empty = bars + 5;   // [2]
-  uint64_t* y2_empty = bars + 7;   // [2]
-  uint64_t* s_full = bars + 9;
-  uint64_t* dp_full = bars + 10;
-  uint64_t* p_full = bars + 11;
-  uint64_t* ds_full = bars + 12;
-  uint64_t* acc_done = bars + 13;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+  uint64_t* y1_full = bars + 1;    // [3]
+  uint64_t* y1_empty = bars + 4;   // [3]
+  uint64_t* y2_full = bars + 7;    // [2]
+  uint64_t* y2_empty = bars + 9;   // [2]
+  uint64_t* s_full = bars + 11;
+  uint64_t* dp_full = bars + 12;
+  uint64_t* p_full = bars + 13;
+  uint64_t* ds_full = bars + 14;
+  uint64_t* acc_done = bars + 15;
+  uint64_t* stat_full = bars + 16;   // [2]  (dK/dV kernel: column statistics of the streamed q rows)
+  uint64_t* stat_empty = bars + 18;  // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
   ATRACE_INIT();
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -577,8 +589,10 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_consta
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_qkv); tma_prefetch_desc(&tm_do);
     mbar_init(x_full, 1);
+    for (int i = 0; i < C::Y1_STAGES; ++i) { mbar_init(&y1_full[i], 1); mbar_init(&y1_empty[i], 1); }
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&y1_full[i], 1); mbar_init(&y2_full[i], 1); mbar_init(&y1_empty[i], 1); mbar_init(&y2_empty[i], 1);
+      mbar_init(&y2_full[i], 1); mbar_init(&y2_empty[i], 1);
+      mbar_init(&stat_full[i], 1); mbar_init(&stat_empty[i], 8);   // 8 row-owner warps release a statistics stage
     }
     mbar_init(s_full, 1); mbar_init(dp_full, 1); mbar_init(p_full, 8); mbar_init(ds_full, 8); mbar_init(acc_done, 1);
     fence_barrier_init();
@@ -603,37 +617,40 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_consta
         }
       }
       for (int it = 0; it < n_iter; ++it) {
-        const int st = it & 1;
-        const uint32_t free_par = ((it >> 1) & 1) ^ 1;
+        const int s1 = it % C::Y1_STAGES, s2 = it & 1;
+        const uint32_t free1 = ((it / C::Y1_STAGES) & 1) ^ 1, free2 = ((it >> 1) & 1) ^ 1;
         const int hh = head_lo + it / per_head;
         const int t = s_lo + it % per_head;
         const int yrow = b * S + t * 128;
-        uint8_t* y1 = sY + st * 2 * C::T_BYTES;
-        uint8_t* y2 = y1 + C::T_BYTES;
-        mbar_wait(&y1_empty[st], free_par);
-        mbar_arrive_expect_tx(&y1_full[st], C::T_BYTES + (MODE == MODE_DKDV ? C::STAT_BYTES : 0));
+        uint8_t* y1 = sY1 + s1 * C::T_BYTES;
+        uint8_t* y2 = sY2 + s2 * C::T_BYTES;
+        mbar_wait(&y1_empty[s1], free1);
+        mbar_arrive_expect_tx(&y1_full[s1], C::T_BYTES);
         for (int c = 0; c < C::NCH; ++c) {
-          if constexpr (MODE == MODE_DKDV) tma_load_2d(y1 + c * C::CHUNK, &tm_qkv, &y1_full[st], hh * HD + 64 * c, yrow);
-          else tma_load_2d(y1 + c * C::CHUNK, &tm_qkv, &y1_full[st], (H + kvh) * HD + 64 * c, yrow);
+          if constexpr (MODE == MODE_DKDV) tma_load_2d(y1 + c * C::CHUNK, &tm_qkv, &y1_full[s1], hh * HD + 64 * c, yrow);
+          else tma_load_2d(y1 + c * C::CHUNK, &tm_qkv, &y1_full[s1], (H + kvh) * HD + 64 * c, yrow);
         }
         if constexpr (MODE == MODE_DKDV) {
-          // per-column softmax statistics of the streamed q rows ride on the Y1 barrier (two 512 B bulk copies)
+          // per-column softmax statistics of the streamed q rows: two 512 B bulk copies, own 2-stage ring (a stage is
+          // released by the row owners after the dS phase has read it)
           const size_t so = ((size_t)b * H + hh) * ld + (size_t)t * 128;
-          bulk_load_1d(sStat + st * 256, lse2g + so, 512, &y1_full[st]);
-          bulk_load_1d(sStat + st * 256 + 128, delta + so, 512, &y1_full[st]);
+          mbar_wait(&stat_empty[s2], free2);
+          mbar_arrive_expect_tx(&stat_full[s2], C::STAT_BYTES);
+          bulk_load_1d(sStat + s2 * 256, lse2g + so, 512, &stat_full[s2]);
+          bulk_load_1d(sStat + s2 * 256 + 128, delta + so, 512, &stat_full[s2]);
         }
-        mbar_wait(&y2_empty[st], free_par);
-        mbar_arrive_expect_tx(&y2_full[st], C::T_BYTES);
+        mbar_wait(&y2_empty[s2], free2);
+        mbar_arrive_expect_tx(&y2_full[s2], C::T_BYTES);
         for (int c = 0; c < C::NCH; ++c) {
-          if constexpr (MODE == MODE_DKDV) tma_load_2d(y2 + c * C::CHUNK, &tm_do, &y2_full[st], hh * HD + 64 * c, yrow);
-          else tma_load_2d(y2 + c * C::CHUNK, &tm_qkv, &y2_full[st], (H + KVH + kvh) * HD + 64 * c, yrow);
+          if constexpr (MODE == MODE_DKDV) tma_load_2d(y2 + c * C::CHUNK, &tm_do, &y2_full[s2], hh * HD + 64 * c, yrow);
+          else tma_load_2d(y2 + c * C::CHUNK, &tm_qkv, &y2_full[s2], (H + KVH + kvh) * HD + 64 * c, yrow);
         }
       }
     }
   } else if (warp == 1) {
     constexpr uint32_t idesc_t = make_idesc_bf16(128, 128, false, false);
     constexpr uint32_t idesc_a = make_idesc_bf16(128, HD, false, true);
-    const uint32_t x1 = smem_u32(sX1), x2 = smem_u32(sX2), y0 = smem_u32(sY);
+    const uint32_t x1 = smem_u32(sX1), x2 = smem_u32(sX2), y1b = smem_u32(sY1), y2b = smem_u32(sY2);
     // descriptors are built once; per-MMA operands are base + constant (the start-address field counts 16-byte units)
     const uint64_t x1d = make_smem_desc(x1, 0, 1024), x2d = make_smem_desc(x2, 0, 1024);
     // scores: T = X * Y^T (both operands K-major, 128 x 128 x HD)
@@ -667,24 +684,24 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_consta
     if (n_iter > 0) {
       mbar_wait(&y1_full[0], 0);
       tc_fence_after();
-      issue_scores(tmem_s, x1d, y0, s_full);
+      issue_scores(tmem_s, x1d, y1b, s_full);
       mbar_wait(&y2_full[0], 0);
       tc_fence_after();
-      issue_scores(tmem_dp, x2d, y0 + C::T_BYTES, dp_full);
+      issue_scores(tmem_dp, x2d, y2b, dp_full);
       if constexpr (MODE == MODE_DQ) { if (elect_one()) umma_commit(&y2_empty[0]); __syncwarp(); }
     }
     for (int it = 0; it < n_iter; ++it) {
-      const int st = it & 1, nst = st ^ 1;
+      const int s1 = it % C::Y1_STAGES, s2 = it & 1, ns1 = (it + 1) % C::Y1_STAGES, ns2 = s2 ^ 1;
       const uint32_t ph = it & 1;
-      const uint32_t ya1 = y0 + st * 2 * C::T_BYTES, ya2 = ya1 + C::T_BYTES;
-      const uint32_t nya1 = y0 + nst * 2 * C::T_BYTES, nya2 = nya1 + C::T_BYTES;
+      const uint32_t ya1 = y1b + s1 * C::T_BYTES, ya2 = y2b + s2 * C::T_BYTES;
+      const uint32_t nya1 = y1b + ns1 * C::T_BYTES, nya2 = y2b + ns2 * C::T_BYTES;
       const bool last = (it + 1 == n_iter);
       mbar_wait(p_full, ph);                       // P(it) is in the S columns (and S(it) has been consumed)
       tc_fence_after();
       if (lane == 0) ATRACE(it, 0);
-      if constexpr (MODE == MODE_DKDV) issue_acc(tmem_acc1, tmem_s, ya2, it == 0, &y2_empty[st], nullptr);
+      if constexpr (MODE == MODE_DKDV) issue_acc(tmem_acc1, tmem_s, ya2, it == 0, &y2_empty[s2], nullptr);
       if (!last) {
-        mbar_wait(&y1_full[nst], ((it + 1) >> 1) & 1);
+        mbar_wait(&y1_full[ns1], ((it + 1) / C::Y1_STAGES) & 1);
         tc_fence_after();
         issue_scores(tmem_s, x1d, nya1, s_full);
       }
@@ -692,12 +709,12 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_consta
       mbar_wait(ds_full, ph);                      // dS(it) is in the dP columns
       tc_fence_after();
       if (lane == 0) ATRACE(it, 2);
-      issue_acc(tmem_acc2, tmem_dp, ya1, it == 0, &y1_empty[st], last ? acc_done : nullptr);
+      issue_acc(tmem_acc2, tmem_dp, ya1, it == 0, &y1_empty[s1], last ? acc_done : nullptr);
       if (!last) {
-        mbar_wait(&y2_full[nst], ((it + 1) >> 1) & 1);
+        mbar_wait(&y2_full[ns2], ((it + 1) >> 1) & 1);
         tc_fence_after();
         issue_scores(tmem_dp, x2d, nya2, dp_full);
-        if constexpr (MODE == MODE_DQ) { if (elect_one()) umma_commit(&y2_empty[nst]); __syncwarp(); }
+        if constexpr (MODE == MODE_DQ) { if (elect_one()) umma_commit(&y2_empty[ns2]); __syncwarp(); }
       }
       if (lane == 0) ATRACE(it, 3);
     }
@@ -727,7 +744,7 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_consta
       const bool need_mask = (t == t128) || (t * 128 + 128 > S) || (t128 * 128 + 128 > S);
       uint32_t pk[32];                             // P of this thread's 64 columns, packed bf16 (kept for the dS phase)
       // ---------------- E phase: S -> P
-      if constexpr (MODE == MODE_DKDV) mbar_wait(&y1_full[st], (it >> 1) & 1);   // column statistics have landed
+      if constexpr (MODE == MODE_DKDV) mbar_wait(&stat_full[st], (it >> 1) & 1);   // column statistics have landed
       if (lane == 0 && q4 == 0 && g == 0) ATRACE(it, 4);
       mbar_wait(s_full, ph);
       tc_fence_after();
@@ -773,7 +790,10 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_consta
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(ds_full);
+      if (lane == 0) {
+        mbar_arrive(ds_full);
+        if constexpr (MODE == MODE_DKDV) mbar_arrive(&stat_empty[st]);   // this warp is done with the stage's statistics
+      }
       if (lane == 0 && q4 == 0 && g == 0) ATRACE(it, 8);
     }
     // epilogue: warpgroup 0 stores acc2 (dK | dQ, times the softmax scale), warpgroup 1 acc1 (dV); in DQ mode the two
