@@ -66,6 +66,7 @@ DECL int b200_attn_fwd(const void*, void*, float*, int, int, int, int, int, floa
 DECL int b200_attn_bwd(const void*, const void*, const void*, const float*, void*, float*, int, int, int, int, int,
                        float, const float*, cudaStream_t);
 DECL void b200_gemm2_set_rope(const float*, int, int, int);
+DECL void b200_gemm2_set_swiglu(void*, int, int, int);
 DECL void b200_gemm2_set_push(void* const*, long long, long long, int, int, int);
 DECL int b200_p2p_push_range(const void*, void* const*, long long, long long, long long, int, cudaStream_t);
 DECL int b200_p2p_allgather(const void* const*, void*, long long, int, int, cudaStream_t);
@@ -123,8 +124,10 @@ void gemm(const at::Tensor& a, const at::Tensor& b, at::Tensor& c, int64_t layou
     K = a.size(0); M = a.size(1); N = b.size(1); a_mn = b_mn = 1;
     TORCH_CHECK(b.size(0) == K, "tn: K mismatch");
   }
-  TORCH_CHECK(c.size(0) == M && c.size(1) == N, "c shape mismatch");
+  TORCH_CHECK(c.size(0) == M && c.size(1) == (epi == 6 ? 2 * N : N), "c shape mismatch");
   TORCH_CHECK(K % 8 == 0 && N % 8 == 0 && M % 8 == 0, "M, N, K must be multiples of 8");
+  TORCH_CHECK((epi != 5 && epi != 6) || (g_gemm_2cta && M >= 256 && c.scalar_type() == at::kBFloat16),
+              "SwiGLU epilogues: CTA-pair kernel, bf16 output (call set_gemm_swiglu first)");
   const void* r = nullptr;
   int ldr = 0;
   if (epi == 1) {
@@ -475,7 +478,7 @@ void gemm_ag(const at::Tensor& a, const at::Tensor& b, const c10::optional<at::T
   if (layout == 0) { M = a.size(0); K = a.size(1); N = b.size(0); TORCH_CHECK(b.size(1) == K); }
   else if (layout == 1) { M = a.size(0); K = a.size(1); N = b.size(1); b_mn = 1; TORCH_CHECK(b.size(0) == K); }
   else { K = a.size(0); M = a.size(1); N = b.size(1); a_mn = b_mn = 1; TORCH_CHECK(b.size(0) == K); }
-  TORCH_CHECK(c.size(0) == M && c.size(1) == N && M >= 256 && K % 8 == 0 && N % 8 == 0 && M % 8 == 0);
+  TORCH_CHECK(c.size(0) == M && c.size(1) == (epi == 6 ? 2 * N : N) && M >= 256 && K % 8 == 0 && N % 8 == 0 && M % 8 == 0);
   const void* r = nullptr;
   int ldr = 0;
   if (epi == 1) {
@@ -780,6 +783,12 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     TORCH_CHECK(src.is_contiguous() && bases.scalar_type() == at::kLong && bases.is_cuda());
     check(b200_p2p_push_range(src.data_ptr(), (void* const*)bases.data_ptr(), n, off, src.numel(), (int)rank, cur_stream()),
           "p2p_push_range");
+  });
+  m.def("set_gemm_swiglu", [](const at::Tensor& aux, int64_t F, bool gate_first) {
+    // aux: activation output [M, F] (epi 5, forward) or the saved bf16 projection [M, 2F] (epi 6, backward)
+    need(aux, "aux", at::kBFloat16);
+    TORCH_CHECK(aux.dim() == 2 && aux.stride(1) == 1 && (aux.size(1) == F || aux.size(1) == 2 * F));
+    b200_gemm2_set_swiglu(aux.data_ptr(), (int)aux.stride(0), (int)F, gate_first ? 1 : 0);
   });
   m.def("set_gemm_push", [](const at::Tensor& bases, int64_t n, int64_t off, int64_t rank, bool bulk, int64_t rot_world) {
     // int64 device table of every rank's staging-buffer base address (fused wgrad GEMM -> reduce-scatter);

@@ -30,7 +30,8 @@ constexpr int P_SMEM = P_STAGES * P_STAGE_BYTES + 1024 + 256;
 constexpr int PUSH_ROW_PITCH = 144;
 constexpr int PUSH_STAGE_BYTES = 4 * 32 * PUSH_ROW_PITCH;   // 18 KiB per CTA
 
-enum { P_EPI_STORE = 0, P_EPI_RESIDUAL = 1, P_EPI_ACCUM = 2, P_EPI_ROPE = 3, P_EPI_PUSH = 4 };
+enum { P_EPI_STORE = 0, P_EPI_RESIDUAL = 1, P_EPI_ACCUM = 2, P_EPI_ROPE = 3, P_EPI_PUSH = 4, P_EPI_SWIGLU = 5,
+       P_EPI_SWIGLU_BWD = 6 };
 
 
 // L2-friendly rasterisation: sweep all n-tiles for a band of GROUP_M m-tiles before moving to the next band, so the
@@ -125,7 +126,18 @@ struct Gemm2Params {
   // rotation all W ranks write into the SAME owner's staging buffer at once (W -> 1 incast on that GPU's NVLink ingress,
   // ~7 x 175 GB/s) while the other owners' links idle.
   int tile_rot;
+  // P_EPI_SWIGLU (gate/up projection, nt): B is the fused [2F, K] weight.  The CTA pair's 256-wide
+  // accumulator holds rows [n0, n0+128) of the FIRST half of the weight in columns [0,128) and the same features of the
+  // SECOND half in columns [128,256) (CTA rank r stages weight rows n0 + r*F), so every epilogue lane has gate and up of
+  // the same feature: it stores the bf16 projection to C [M, 2F] (needed by the backward) AND silu(gate) * up to
+  // aux [M, F].  N of the launch = F.
+  // P_EPI_SWIGLU_BWD (down-projection dgrad, nn): the accumulator is dS [M, F]; the epilogue reads gate / up from
+  // aux = the saved projection [M, 2F] and stores d(gate) | d(up) to C [M, 2F] -- dS itself never reaches memory.
+  void* aux;
+  int ld_aux, swi_F, swi_gate_first;
 };
+
+B200_DEVINL float sigmoidf_fast(float x) { return __frcp_rn(1.f + exp2f(-1.4426950408889634f * x)); }
 
 B200_DEVINL void bulk_store_s2g(void* gdst, const void* ssrc, uint32_t bytes) {
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
@@ -181,7 +193,7 @@ gemm2_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         int mt, nt;
         tile_coords2((t + p.tile_rot) % num_tiles, p.m_tiles, p.n_tiles, mt, nt);
         const int m0 = mt * P_BM + (int)rank * C_BM;
-        const int n0 = nt * P_BN + (int)rank * C_BN;
+        const int n0 = (EPI == P_EPI_SWIGLU) ? nt * C_BN + (int)rank * p.swi_F : nt * P_BN + (int)rank * C_BN;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * P_STAGE_BYTES;
@@ -311,6 +323,76 @@ gemm2_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       OutT* crow = reinterpret_cast<OutT*>(p.C) + static_cast<size_t>(row) * p.ldc;
       const __nv_bfloat16* rrow = reinterpret_cast<const __nv_bfloat16*>(p.R) + static_cast<size_t>(row) * p.ldr;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * P_BN;
+      if constexpr (EPI == P_EPI_SWIGLU) {
+        // columns [0,128) = first half of the fused projection, [128,256) = second half, same 128 features
+        const int f0 = nt * C_BN;
+        __nv_bfloat16* arow = reinterpret_cast<__nv_bfloat16*>(p.aux) + static_cast<size_t>(row) * p.ld_aux;
+#pragma unroll 1
+        for (int c = 0; c < C_BN; c += 32) {
+          uint32_t a[32], b[32];
+          tmem_ld_32x32b_x32(taddr + c, a);
+          tmem_ld_32x32b_x32(taddr + C_BN + c, b);
+          tmem_ld_wait();
+          if (row_ok && f0 + c < p.swi_F) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              uint4 o1, o2, oa;
+              uint32_t* w1 = reinterpret_cast<uint32_t*>(&o1);
+              uint32_t* w2 = reinterpret_cast<uint32_t*>(&o2);
+              uint32_t* wa = reinterpret_cast<uint32_t*>(&oa);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                w1[i] = pack_bf16x2(__uint_as_float(a[g * 8 + 2 * i]), __uint_as_float(a[g * 8 + 2 * i + 1]));
+                w2[i] = pack_bf16x2(__uint_as_float(b[g * 8 + 2 * i]), __uint_as_float(b[g * 8 + 2 * i + 1]));
+                // activation from the ROUNDED projection: forward and backward see the same gate / up values
+                const float2 x1 = unpack_bf16x2(w1[i]), x2 = unpack_bf16x2(w2[i]);
+                const float2 gt = p.swi_gate_first ? x1 : x2, up = p.swi_gate_first ? x2 : x1;
+                wa[i] = pack_bf16x2(gt.x * sigmoidf_fast(gt.x) * up.x, gt.y * sigmoidf_fast(gt.y) * up.y);
+              }
+              const int col = f0 + c + g * 8;
+              *reinterpret_cast<uint4*>(crow + col) = o1;
+              *reinterpret_cast<uint4*>(crow + p.swi_F + col) = o2;
+              *reinterpret_cast<uint4*>(arow + col) = oa;
+            }
+          }
+        }
+      } else if constexpr (EPI == P_EPI_SWIGLU_BWD) {
+        const __nv_bfloat16* grow = reinterpret_cast<const __nv_bfloat16*>(p.aux) + static_cast<size_t>(row) * p.ld_aux;
+#pragma unroll 1
+        for (int c = 0; c < P_BN; c += 32) {
+          uint32_t d[32];
+          tmem_ld_32x32b_x32(taddr + c, d);
+          tmem_ld_wait();
+          const int col = n0 + c;
+          if (row_ok && col < p.N) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              if (col + g * 8 >= p.N) break;
+              const uint4 r1 = *reinterpret_cast<const uint4*>(grow + col + g * 8);
+              const uint4 r2 = *reinterpret_cast<const uint4*>(grow + p.swi_F + col + g * 8);
+              const uint32_t* q1 = reinterpret_cast<const uint32_t*>(&r1);
+              const uint32_t* q2 = reinterpret_cast<const uint32_t*>(&r2);
+              uint4 o1, o2;
+              uint32_t* w1 = reinterpret_cast<uint32_t*>(&o1);
+              uint32_t* w2 = reinterpret_cast<uint32_t*>(&o2);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float2 x1 = unpack_bf16x2(q1[i]), x2 = unpack_bf16x2(q2[i]);
+                const float2 gt = p.swi_gate_first ? x1 : x2, up = p.swi_gate_first ? x2 : x1;
+                const float ds0 = __uint_as_float(d[g * 8 + 2 * i]), ds1 = __uint_as_float(d[g * 8 + 2 * i + 1]);
+                const float s0 = sigmoidf_fast(gt.x), s1 = sigmoidf_fast(gt.y);
+                const float dg0 = ds0 * up.x * s0 * (1.f + gt.x * (1.f - s0)), dg1 = ds1 * up.y * s1 * (1.f + gt.y * (1.f - s1));
+                const float du0 = ds0 * gt.x * s0, du1 = ds1 * gt.y * s1;
+                const uint32_t pg = pack_bf16x2(dg0, dg1), pu = pack_bf16x2(du0, du1);
+                w1[i] = p.swi_gate_first ? pg : pu;
+                w2[i] = p.swi_gate_first ? pu : pg;
+              }
+              *reinterpret_cast<uint4*>(crow + col + g * 8) = o1;
+              *reinterpret_cast<uint4*>(crow + p.swi_F + col + g * 8) = o2;
+            }
+          }
+        }
+      } else {
 #pragma unroll 1
       for (int c = 0; c < P_BN; c += 64) {
         uint32_t v0[32], v1[32];
@@ -425,6 +507,7 @@ gemm2_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           }
         }
       }
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_leader(&tempty_bar[acc]);
@@ -497,6 +580,9 @@ static int g_rope_S = 1, g_rope_hd = 2, g_rope_cols = 0;
 static void* const* g_push_bases = nullptr;
 static long long g_push_n = 1, g_push_off = 0;
 static int g_push_rank = 0, g_push_bulk = 1, g_push_world = 1;
+// same convention for the SwiGLU epilogues: aux = activation output (forward) / saved projection (backward)
+static void* g_swi_aux = nullptr;
+static int g_swi_ld = 0, g_swi_F = 0, g_swi_gate_first = 1;
 
 }  // namespace b200
 
@@ -508,6 +594,10 @@ extern "C" void b200_gemm2_set_rope(const float* table, int S, int hd, int cols)
 extern "C" void b200_gemm2_set_push(void* const* bases, long long n, long long off, int rank, int bulk, int world) {
   b200::g_push_bases = bases; b200::g_push_n = n; b200::g_push_off = off; b200::g_push_rank = rank; b200::g_push_bulk = bulk;
   b200::g_push_world = world < 1 ? 1 : world;
+}
+
+extern "C" void b200_gemm2_set_swiglu(void* aux, int ld_aux, int F, int gate_first) {
+  b200::g_swi_aux = aux; b200::g_swi_ld = ld_aux; b200::g_swi_F = F; b200::g_swi_gate_first = gate_first;
 }
 
 extern "C" int b200_gemm2_bf16(const void* A, const void* B, void* C, const void* R, int M, int N, int K, int lda,
@@ -530,10 +620,21 @@ extern "C" int b200_gemm2_bf16(const void* A, const void* B, void* C, const void
   p.push_bases = g_push_bases; p.push_n = g_push_n; p.push_off = g_push_off; p.push_rank = g_push_rank;
   p.push_bulk = g_push_bulk;
   p.tile_rot = 0;
+  p.aux = g_swi_aux; p.ld_aux = g_swi_ld; p.swi_F = g_swi_F; p.swi_gate_first = g_swi_gate_first;
   if (epi == P_EPI_PUSH && g_push_world > 1) {
     const int per_band = P_GROUP_M * p.n_tiles, tiles = p.m_tiles * p.n_tiles;
     const int bands = (tiles + per_band - 1) / per_band;
     p.tile_rot = (int)(((long long)(g_push_rank % g_push_world) * bands / g_push_world) * per_band) % tiles;
+  }
+  if (epi == P_EPI_SWIGLU) {   // nt; N = 2F rows of the fused weight, tiles of 128 features
+    if (a_mn || b_mn || out_fp32 || !p.aux || p.swi_F <= 0 || N != 2 * p.swi_F || (p.swi_F % C_BN) || (p.ld_aux % 8)) return -11;
+    p.N = p.swi_F;
+    p.n_tiles = p.swi_F / C_BN;
+    return launch2<false, false, P_EPI_SWIGLU, __nv_bfloat16>(tmA, tmB, p, stream);
+  }
+  if (epi == P_EPI_SWIGLU_BWD) {   // nn; N = F columns of dS, output [M, 2F]
+    if (a_mn || !b_mn || out_fp32 || !p.aux || p.swi_F != N || (N % 8) || (p.ld_aux % 8)) return -12;
+    return launch2<false, true, P_EPI_SWIGLU_BWD, __nv_bfloat16>(tmA, tmB, p, stream);
   }
   if (epi == P_EPI_ROPE) {
     if (a_mn || b_mn || out_fp32 || !p.rope || (p.rope_hd % 8) || (p.rope_cols % 8)) return -8;
@@ -577,11 +678,18 @@ extern "C" int b200_gemm2_ag_bf16(const void* A, const void* B, void* C, const v
   p.push_bases = g_push_bases; p.push_n = g_push_n; p.push_off = g_push_off; p.push_rank = g_push_rank;
   p.push_bulk = g_push_bulk;
   p.tile_rot = 0;
+  p.aux = g_swi_aux; p.ld_aux = g_swi_ld; p.swi_F = g_swi_F; p.swi_gate_first = g_swi_gate_first;
   if (epi == P_EPI_PUSH && g_push_world > 1) {
     const int per_band = P_GROUP_M * p.n_tiles, tiles = p.m_tiles * p.n_tiles;
     const int bands = (tiles + per_band - 1) / per_band;
     p.tile_rot = (int)(((long long)(g_push_rank % g_push_world) * bands / g_push_world) * per_band) % tiles;
   }
+  if (epi == P_EPI_SWIGLU) {
+    if (a_mn || b_mn || !p.aux || p.swi_F <= 0 || N != 2 * p.swi_F || (p.swi_F % C_BN) || (p.ld_aux % 8) || dependent) return -11;
+    p.N = p.swi_F;
+    p.n_tiles = p.swi_F / C_BN;
+  }
+  if (epi == P_EPI_SWIGLU_BWD && (a_mn || !b_mn || !p.aux || p.swi_F != N || (N % 8) || (p.ld_aux % 8))) return -12;
   AgParams ag;
   ag.peer_shards = peer_shards; ag.full = (uint8_t*)full; ag.shard_bytes = shard_bytes; ag.begin = begin; ag.end = end;
   ag.world = world; ag.rank = rank; ag.flags = flags; ag.epoch = epoch; ag.dependent = dependent;
@@ -593,8 +701,16 @@ extern "C" int b200_gemm2_ag_bf16(const void* A, const void* B, void* C, const v
     if (a_mn || b_mn || !p.rope || (p.rope_hd % 8) || (p.rope_cols % 8)) return -8;
     AGL(false, false, P_EPI_ROPE);
   }
-  if (!a_mn && !b_mn) { if (epi == P_EPI_RESIDUAL) AGL(false, false, P_EPI_RESIDUAL); AGL(false, false, P_EPI_STORE); }
-  if (!a_mn && b_mn)  { if (epi == P_EPI_RESIDUAL) AGL(false, true, P_EPI_RESIDUAL);  AGL(false, true, P_EPI_STORE); }
+  if (!a_mn && !b_mn) {
+    if (epi == P_EPI_SWIGLU) AGL(false, false, P_EPI_SWIGLU);
+    if (epi == P_EPI_RESIDUAL) AGL(false, false, P_EPI_RESIDUAL);
+    AGL(false, false, P_EPI_STORE);
+  }
+  if (!a_mn && b_mn) {
+    if (epi == P_EPI_SWIGLU_BWD) AGL(false, true, P_EPI_SWIGLU_BWD);
+    if (epi == P_EPI_RESIDUAL) AGL(false, true, P_EPI_RESIDUAL);
+    AGL(false, true, P_EPI_STORE);
+  }
   if (a_mn && b_mn) {
     if (epi == P_EPI_PUSH) {   // wgrad that pushes its tiles to the owners AND carries the next unit's all-gather
       if (!p.push_bases || p.push_n <= 0 || (p.push_n % 8) || (p.push_off % 8) || (ldc % 8)) return -9;

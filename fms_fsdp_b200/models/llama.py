@@ -201,9 +201,9 @@ class LLaMABlock(nn.Module):
                                 a.head_dim)
         x = a.dense(ctx, residual=x)
         h, x = self.ff_ln.fork(x)
-        gu = self.ff_sub_layer.wg1_fused(h)
-        x = self.ff_sub_layer.w2(ops.swiglu(gu), residual=x)
-        return x
+        ff = self.ff_sub_layer
+        # gate/up GEMM with the SwiGLU epilogue, down projection with the residual epilogue: one autograd node
+        return ops.gated_mlp(h, ff.wg1_fused.weight, ff.w2.weight, residual=x)
 
 
 class LLaMA(nn.Module):

@@ -271,7 +271,7 @@ class GatedMLP(nn.Module):
         self.fc2.reset_parameters()
 
     def forward(self, x):
-        return self.fc2(ops.swiglu(self.fc1(x), gate_first=False))
+        return ops.gated_mlp(x, self.fc1.weight, self.fc2.weight, gate_first=False)
 
 
 class Block(nn.Module):

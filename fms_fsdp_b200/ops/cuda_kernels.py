@@ -107,6 +107,7 @@ def _try_fused_gather(a, b, layout, out, epi, residual) -> bool:
     M = a.shape[1] if layout == "tn" else a.shape[0]
     ok = (M >= 256 and out.dtype == torch.bfloat16 and _C.get_gemm_2cta()
           and ((layout in ("nt", "nn") and epi in (0, 1)) or (layout == "tn" and epi in (0, 2, 4))
+               or (layout == "nt" and epi == 5 and not req["dependent"]) or (layout == "nn" and epi == 6)
                or (layout == "nt" and epi == 3)))
     if ok and req["dependent"]:
         lo = req["full"].data_ptr() + req["begin"]
@@ -231,6 +232,50 @@ def gemm(a, b, layout="nt", out=None, accumulate=False, residual=None, out_dtype
         return out
     _C.gemm(a, b, out, _LAYOUT[layout], epi, residual)
     return out
+
+
+# -------------------------------------------------------- gate/up GEMM + SwiGLU, down-proj dgrad + SwiGLU backward
+FUSE_SWIGLU = os.environ.get("FMS_B200_FUSE_SWIGLU", "1") == "1"
+
+
+def _swiglu_fusable(x, F):
+    return (FUSE_SWIGLU and GEMM_IMPL == "tcgen05" and x.dtype == torch.bfloat16 and x.shape[0] >= 256 and x.shape[0] % 8 == 0
+            and _C.get_gemm_2cta())
+
+
+def gated_up_fwd(x, w, gate_first=True):
+    """(gu [M, 2F] bf16, silu(gate) * up [M, F]): the activation is the EPILOGUE of the gate/up GEMM -- a CTA pair's
+    accumulator holds gate and up of the same 128 features side by side (csrc/gemm2_sm100.cu P_EPI_SWIGLU)."""
+    F = w.shape[0] // 2
+    if not (_swiglu_fusable(x, F) and w.dtype == torch.bfloat16 and F % 128 == 0 and x.shape[1] % 8 == 0):
+        gu = gemm(x, w, "nt")
+        return gu, swiglu_fwd(gu, gate_first)
+    x = x if x.stride(-1) == 1 else x.contiguous()
+    w = w if w.stride(-1) == 1 else w.contiguous()
+    gu = torch.empty(x.shape[0], 2 * F, dtype=torch.bfloat16, device=x.device)
+    act = torch.empty(x.shape[0], F, dtype=torch.bfloat16, device=x.device)
+    _C.set_gemm_swiglu(act, F, bool(gate_first))
+    if _AG_QUEUE and _try_fused_gather(x, w, "nt", gu, 5, None):
+        return gu, act
+    _C.gemm(x, w, gu, 0, 5, None)
+    return gu, act
+
+
+def gated_down_bwd(dy, w2, gu, gate_first=True):
+    """d(gu) [M, 2F] = swiglu_bwd(dy @ w2, gu) with the SwiGLU backward as the epilogue of the dgrad GEMM: dS = dy @ w2
+    never reaches memory (csrc/gemm2_sm100.cu P_EPI_SWIGLU_BWD)."""
+    F = w2.shape[1]
+    if not (_swiglu_fusable(dy, F) and w2.dtype == gu.dtype == torch.bfloat16 and F % 8 == 0 and dy.shape[1] % 8 == 0
+            and gu.is_contiguous()):
+        return swiglu_bwd(gemm(dy, w2, "nn"), gu, gate_first)
+    dy = dy if dy.stride(-1) == 1 else dy.contiguous()
+    w2 = w2 if w2.stride(-1) == 1 else w2.contiguous()
+    dgu = torch.empty_like(gu)
+    _C.set_gemm_swiglu(gu, F, bool(gate_first))
+    if _AG_QUEUE and _try_fused_gather(dy, w2, "nn", dgu, 6, None):
+        return dgu
+    _C.gemm(dy, w2, dgu, 1, 6, None)
+    return dgu
 
 
 # --------------------------------------------------------------------------------------- RMSNorm

@@ -313,6 +313,47 @@ def swiglu(gu, gate_first=True):
     return _SwiGLU.apply(gu, gate_first)
 
 
+class _GatedMLP(torch.autograd.Function):
+    """y = (silu(gate) * up) @ w2^T (+ residual) with [gate | up] = x @ wg1^T as ONE node, so that the activation can be
+    the epilogue of the gate/up GEMM and its backward the epilogue of the down-projection dgrad GEMM (SURVEY.md K6-K8;
+    reference op: fms GatedLinearUnit, weights ``ff_sub_layer.wg1_fused`` / ``w2``, ``fms_to_hf_llama.py:89-96``)."""
+
+    @staticmethod
+    def forward(ctx, x, wg1, w2, residual, gate_first):
+        K = kernels_for(x)
+        x2 = x.reshape(-1, x.shape[-1])
+        gu, act = K.gated_up_fwd(x2, _wdata(wg1), gate_first)
+        w2d = _wdata(w2)
+        y = torch.empty(*x.shape[:-1], w2d.shape[0], dtype=x.dtype, device=x.device)
+        r2 = None if residual is None else residual.reshape(-1, residual.shape[-1])
+        K.gemm(act, w2d, "nt", out=y.view(-1, w2d.shape[0]), residual=r2)
+        ctx.K, ctx.wg1, ctx.w2, ctx.gate_first, ctx.has_res = K, wg1, w2, gate_first, residual is not None
+        ctx.save_for_backward(x, gu, act)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, gu, act = ctx.saved_tensors
+        K, wg1, w2 = ctx.K, ctx.wg1, ctx.w2
+        dy2 = dy.reshape(-1, dy.shape[-1])
+        if not dy2.is_contiguous():
+            dy2 = dy2.contiguous()
+        x2 = x.reshape(-1, x.shape[-1])
+        dgu = K.gated_down_bwd(dy2, _wdata(w2), gu, ctx.gate_first)
+        dw2 = _deliver_wgrad(w2, lambda out, acc: K.gemm(dy2, act, "tn", out=out, accumulate=acc)) \
+            if ctx.needs_input_grad[2] else None
+        dx = K.gemm(dgu, _wdata(wg1), "nn").view_as(x) if ctx.needs_input_grad[0] else None
+        dwg1 = _deliver_wgrad(wg1, lambda out, acc: K.gemm(dgu, x2, "tn", out=out, accumulate=acc)) \
+            if ctx.needs_input_grad[1] else None
+        return dx, dwg1, dw2, (dy if ctx.has_res else None), None
+
+
+def gated_mlp(x, wg1, w2, residual: Optional[torch.Tensor] = None, gate_first: bool = True):
+    """SwiGLU MLP: ``(silu(g) * u) @ w2^T (+ residual)`` with ``[g | u] = x @ wg1^T`` (``gate_first=False``: ``[u | g]``,
+    the mamba_ssm GatedMLP order)."""
+    return _GatedMLP.apply(x, wg1, w2, residual, gate_first)
+
+
 class _AddRMSNorm(torch.autograd.Function):
     """residual_out = residual + x (kept in the residual stream dtype, fp32 for Mamba);
     y = rmsnorm(residual_out) in x.dtype.  (mamba_ssm fused_add_norm)"""

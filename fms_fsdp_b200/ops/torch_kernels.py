@@ -203,6 +203,17 @@ def swiglu_fwd(gu, gate_first=True):
     return (F.silu(g) * u).to(gu.dtype)
 
 
+def gated_up_fwd(x, w, gate_first=True):
+    """Gate/up projection with the SwiGLU activation: returns (gu [M, 2F], silu(gate) * up [M, F])  (SURVEY.md K6/K7)."""
+    gu = gemm(x, w, "nt")
+    return gu, swiglu_fwd(gu, gate_first)
+
+
+def gated_down_bwd(dy, w2, gu, gate_first=True):
+    """d(gu) of  y = (silu(gate) * up) @ w2^T :  swiglu_bwd(dy @ w2, gu)  (the CUDA path fuses the two)."""
+    return swiglu_bwd(gemm(dy, w2, "nn"), gu, gate_first)
+
+
 def swiglu_bwd(ds, gu, gate_first=True):
     F_ = gu.shape[-1] // 2
     a, b, d = gu[..., :F_].float(), gu[..., F_:].float(), ds.float()

@@ -278,3 +278,46 @@ def test_qkv_attention_rope_fused_in_gemm_and_bwd_epilogues(K):
     y2.backward(dy)
     assert rel(y, y2) < 2e-2
     assert rel(h.grad, h2.grad) < 3e-2 and rel(w.grad, w2.grad) < 3e-2
+
+
+@pytest.mark.parametrize("gate_first", [True, False])
+@pytest.mark.parametrize("shape", [(512, 256, 384), (1024, 512, 2816), (8192, 4096, 11008)])
+def test_swiglu_fused_into_gemm_epilogues(K, shape, gate_first):
+    """SwiGLU as the epilogue of the gate/up GEMM (forward) and of the down-projection dgrad GEMM (backward) against
+    the fp32 oracle; the last shape is the Llama2-7B MLP at the benchmark token count."""
+    CK, TK = K
+    M, D, F = shape
+    torch.manual_seed(1)
+    x = (torch.randn(M, D, device=DEV) * 0.5).bfloat16()
+    w = (torch.randn(2 * F, D, device=DEV) * (D ** -0.5)).bfloat16()
+    w2 = (torch.randn(D, F, device=DEV) * (F ** -0.5)).bfloat16()
+    dy = (torch.randn(M, D, device=DEV) * 0.5).bfloat16()
+    n0 = CK.launch_count()
+    gu, act = CK.gated_up_fwd(x, w, gate_first)
+    assert CK.launch_count() == n0 + 1, "the fused epilogue was not taken"
+    gu0 = x.float() @ w.float().t()
+    assert rel(gu, gu0) < 1e-2
+    act0 = TK.swiglu_fwd(gu.float(), gate_first)          # activation of the bf16-rounded projection, as the kernel does
+    assert rel(act, act0) < 1e-2
+    n0 = CK.launch_count()
+    dgu = CK.gated_down_bwd(dy, w2, gu, gate_first)
+    assert CK.launch_count() == n0 + 1
+    dgu0 = TK.swiglu_bwd(dy.float() @ w2.float(), gu.float(), gate_first)
+    assert rel(dgu[:, :F], dgu0[:, :F]) < 2e-2 and rel(dgu[:, F:], dgu0[:, F:]) < 2e-2
+
+
+def test_gated_mlp_node_matches_unfused_ops(K):
+    from fms_fsdp_b200 import ops
+    torch.manual_seed(2)
+    B, S, D, F = 2, 256, 512, 1408                          # F % 128 == 0
+    x = (torch.randn(B, S, D, device=DEV) * 0.5).bfloat16().requires_grad_()
+    w1 = torch.nn.Parameter((torch.randn(2 * F, D, device=DEV) * 0.04).bfloat16())
+    w2 = torch.nn.Parameter((torch.randn(D, F, device=DEV) * 0.03).bfloat16())
+    dy = torch.randn(B, S, D, device=DEV).bfloat16()
+    y = ops.gated_mlp(x, w1, w2, residual=x)
+    y.backward(dy)
+    x2 = x.detach().requires_grad_(); a1 = torch.nn.Parameter(w1.detach().clone()); a2 = torch.nn.Parameter(w2.detach().clone())
+    y2 = ops.linear(ops.swiglu(ops.linear(x2, a1)), a2, residual=x2)
+    y2.backward(dy)
+    assert rel(y, y2) < 1e-2
+    assert rel(x.grad, x2.grad) < 2e-2 and rel(w1.grad, a1.grad) < 2e-2 and rel(w2.grad, a2.grad) < 2e-2

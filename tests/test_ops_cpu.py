@@ -167,3 +167,22 @@ def test_linear_ce_applies_the_upstream_gradient():
     h2 = h.detach().clone().requires_grad_(); w2 = torch.nn.Parameter(w.detach().clone())
     (torch.nn.functional.cross_entropy(h2 @ w2.t(), y) * 0.25).backward()
     assert torch.allclose(h.grad, h2.grad, atol=1e-6) and torch.allclose(w.grad, w2.grad, atol=1e-6)
+
+
+def test_gated_mlp_matches_autograd():
+    import torch
+    from fms_fsdp_b200 import ops
+    torch.manual_seed(0)
+    for gate_first in (True, False):
+        x = torch.randn(3, 5, 16, requires_grad=True)
+        w1 = torch.nn.Parameter(torch.randn(24, 16) * 0.2); w2 = torch.nn.Parameter(torch.randn(16, 12) * 0.2)
+        y = ops.gated_mlp(x, w1, w2, residual=x, gate_first=gate_first)
+        y.pow(2).sum().backward()
+        x2 = x.detach().clone().requires_grad_(); a1 = torch.nn.Parameter(w1.detach().clone()); a2 = torch.nn.Parameter(w2.detach().clone())
+        gu = x2 @ a1.t()
+        g, u = (gu[..., :12], gu[..., 12:]) if gate_first else (gu[..., 12:], gu[..., :12])
+        y2 = (torch.nn.functional.silu(g) * u) @ a2.t() + x2
+        y2.pow(2).sum().backward()
+        assert torch.allclose(y, y2, atol=1e-5)
+        for a, b in ((x.grad, x2.grad), (w1.grad, a1.grad), (w2.grad, a2.grad)):
+            assert torch.allclose(a, b, atol=1e-4)
