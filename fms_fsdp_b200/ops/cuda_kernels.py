@@ -236,6 +236,12 @@ def gemm(a, b, layout="nt", out=None, accumulate=False, residual=None, out_dtype
 
 # -------------------------------------------------------- gate/up GEMM + SwiGLU, down-proj dgrad + SwiGLU backward
 FUSE_SWIGLU = os.environ.get("FMS_B200_FUSE_SWIGLU", "1") == "1"
+# Measured on Llama2-7B, 1 GPU, same box (profiles/step_kernel_table_1gpu_swiglu_{fused,unfused}_r2.txt): the forward fusion
+# costs +97 us in the gate/up GEMM and removes the 112 us activation kernel (kept on); the BACKWARD fusion turns the 560 us
+# down-projection dgrad into 904 us (its epilogue reads gate/up with one 16-byte load per row and lane, 32 cache lines per
+# warp instruction) and only removes a 155 us kernel -- so it is off by default until that epilogue reads through shared
+# memory.
+FUSE_SWIGLU_BWD = os.environ.get("FMS_B200_FUSE_SWIGLU_BWD", "0") == "1"
 
 
 def _swiglu_fusable(x, F):
@@ -265,7 +271,7 @@ def gated_down_bwd(dy, w2, gu, gate_first=True):
     """d(gu) [M, 2F] = swiglu_bwd(dy @ w2, gu) with the SwiGLU backward as the epilogue of the dgrad GEMM: dS = dy @ w2
     never reaches memory (csrc/gemm2_sm100.cu P_EPI_SWIGLU_BWD)."""
     F = w2.shape[1]
-    if not (_swiglu_fusable(dy, F) and w2.dtype == gu.dtype == torch.bfloat16 and F % 8 == 0 and dy.shape[1] % 8 == 0
+    if not (FUSE_SWIGLU_BWD and _swiglu_fusable(dy, F) and w2.dtype == gu.dtype == torch.bfloat16 and F % 8 == 0 and dy.shape[1] % 8 == 0
             and gu.is_contiguous()):
         return swiglu_bwd(gemm(dy, w2, "nn"), gu, gate_first)
     dy = dy if dy.stride(-1) == 1 else dy.contiguous()
