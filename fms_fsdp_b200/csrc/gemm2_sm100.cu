@@ -358,20 +358,32 @@ gemm2_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         }
       } else if constexpr (EPI == P_EPI_SWIGLU_BWD) {
         const __nv_bfloat16* grow = reinterpret_cast<const __nv_bfloat16*>(p.aux) + static_cast<size_t>(row) * p.ld_aux;
+        // 64 columns per step: every lane reads whole 128-byte lines of its row's gate and up values (all 16 loads are
+        // issued before the TMEM wait, so their latency overlaps it) -- 32-column steps fetched every line twice
 #pragma unroll 1
-        for (int c = 0; c < P_BN; c += 32) {
-          uint32_t d[32];
-          tmem_ld_32x32b_x32(taddr + c, d);
-          tmem_ld_wait();
+        for (int c = 0; c < P_BN; c += 64) {
           const int col = n0 + c;
-          if (row_ok && col < p.N) {
+          const bool live = row_ok && col < p.N;
+          uint4 r1[8], r2[8];
+          if (live) {
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
+            for (int g = 0; g < 8; ++g) {
+              if (col + g * 8 < p.N) {
+                r1[g] = *reinterpret_cast<const uint4*>(grow + col + g * 8);
+                r2[g] = *reinterpret_cast<const uint4*>(grow + p.swi_F + col + g * 8);
+              }
+            }
+          }
+          uint32_t d[64];
+          tmem_ld_32x32b_x32(taddr + c, *reinterpret_cast<uint32_t(*)[32]>(&d[0]));
+          tmem_ld_32x32b_x32(taddr + c + 32, *reinterpret_cast<uint32_t(*)[32]>(&d[32]));
+          tmem_ld_wait();
+          if (live) {
+#pragma unroll
+            for (int g = 0; g < 8; ++g) {
               if (col + g * 8 >= p.N) break;
-              const uint4 r1 = *reinterpret_cast<const uint4*>(grow + col + g * 8);
-              const uint4 r2 = *reinterpret_cast<const uint4*>(grow + p.swi_F + col + g * 8);
-              const uint32_t* q1 = reinterpret_cast<const uint32_t*>(&r1);
-              const uint32_t* q2 = reinterpret_cast<const uint32_t*>(&r2);
+              const uint32_t* q1 = reinterpret_cast<const uint32_t*>(&r1[g]);
+              const uint32_t* q2 = reinterpret_cast<const uint32_t*>(&r2[g]);
               uint4 o1, o2;
               uint32_t* w1 = reinterpret_cast<uint32_t*>(&o1);
               uint32_t* w2 = reinterpret_cast<uint32_t*>(&o2);

@@ -32,10 +32,25 @@ inline int make_tmap(CUtensorMap* m, CUtensorMapDataType dt, int rank, const voi
                      const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle swz) {
   PFN_encodeTiled fn = get_encode_fn();
   if (!fn) return -1;
+  // The encode call is a DRIVER API call and needs a context current in the calling thread.  PyTorch's autograd worker
+  // threads only get one lazily, on their first runtime-API call -- a backward node whose first CUDA action is a GEMM
+  // (tensor-map encode, output served from the caching allocator) got CUDA_ERROR_INVALID_CONTEXT.  cudaFree(0) binds the
+  // primary context of the current device to this thread; once per thread.
+  static thread_local bool ctx_bound = false;
+  if (!ctx_bound) {
+    cudaFree(0);
+    ctx_bound = true;
+  }
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
   CUresult r = fn(m, dt, (cuuint32_t)rank, const_cast<void*>(ptr), (const cuuint64_t*)dims,
                   (const cuuint64_t*)strides_bytes, (const cuuint32_t*)box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r == CUDA_ERROR_INVALID_CONTEXT) {   // e.g. the thread switched devices: bind again and retry once
+    cudaFree(0);
+    r = fn(m, dt, (cuuint32_t)rank, const_cast<void*>(ptr), (const cuuint64_t*)dims, (const cuuint64_t*)strides_bytes,
+           (const cuuint32_t*)box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  }
   if (r != CUDA_SUCCESS) {
     fprintf(stderr, "[b200] cuTensorMapEncodeTiled failed: %d (rank %d dims %llu %llu box %u %u stride %llu)\n", (int)r,
             rank, (unsigned long long)dims[0], (unsigned long long)(rank > 1 ? dims[1] : 0), box[0],

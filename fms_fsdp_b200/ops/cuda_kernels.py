@@ -236,12 +236,12 @@ def gemm(a, b, layout="nt", out=None, accumulate=False, residual=None, out_dtype
 
 # -------------------------------------------------------- gate/up GEMM + SwiGLU, down-proj dgrad + SwiGLU backward
 FUSE_SWIGLU = os.environ.get("FMS_B200_FUSE_SWIGLU", "1") == "1"
-# Measured on Llama2-7B, 1 GPU, same box (profiles/step_kernel_table_1gpu_swiglu_{fused,unfused}_r2.txt): the forward fusion
-# costs +97 us in the gate/up GEMM and removes the 112 us activation kernel (kept on); the BACKWARD fusion turns the 560 us
-# down-projection dgrad into 904 us (its epilogue reads gate/up with one 16-byte load per row and lane, 32 cache lines per
-# warp instruction) and only removes a 155 us kernel -- so it is off by default until that epilogue reads through shared
-# memory.
-FUSE_SWIGLU_BWD = os.environ.get("FMS_B200_FUSE_SWIGLU_BWD", "0") == "1"
+# Measured on Llama2-7B, 1 GPU, same box (profiles/step_kernel_table_1gpu_swiglu_{fused,unfused}_r2.txt, ab_1gpu_swiglu_*):
+# forward fusion +97 us in the gate/up GEMM, -112 us activation kernel.  The first backward epilogue read gate/up in
+# 32-column steps (every 128-byte line fetched twice, loads issued after the TMEM wait): 904 us vs 560 + 155 us unfused;
+# with 64-column steps and the loads issued before the TMEM wait the step time equals the unfused one (329.7 vs 329.4 ms)
+# while dS [M, F] never reaches memory -- on by default.
+FUSE_SWIGLU_BWD = os.environ.get("FMS_B200_FUSE_SWIGLU_BWD", "1") == "1"
 
 
 def _swiglu_fusable(x, F):

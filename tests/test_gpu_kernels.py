@@ -300,11 +300,7 @@ def test_swiglu_fused_into_gemm_epilogues(K, shape, gate_first):
     act0 = TK.swiglu_fwd(gu.float(), gate_first)          # activation of the bf16-rounded projection, as the kernel does
     assert rel(act, act0) < 1e-2
     n0 = CK.launch_count()
-    CK.FUSE_SWIGLU_BWD = True            # the backward epilogue is off by default (slower than the unfused pair)
-    try:
-        dgu = CK.gated_down_bwd(dy, w2, gu, gate_first)
-    finally:
-        CK.FUSE_SWIGLU_BWD = False
+    dgu = CK.gated_down_bwd(dy, w2, gu, gate_first)
     assert CK.launch_count() == n0 + 1
     dgu0 = TK.swiglu_bwd(dy.float() @ w2.float(), gu.float(), gate_first)
     assert rel(dgu[:, :F], dgu0[:, :F]) < 2e-2 and rel(dgu[:, F:], dgu0[:, F:]) < 2e-2
