@@ -192,13 +192,23 @@ def register_model(arch: str, variant: str, factory: Callable[[], nn.Module]):
 
 def get_model(arch: str, variant: str, model_path: Optional[str] = None, device_type="cuda", source="hf",
               distributed_strategy=None, group=None, dtype=torch.bfloat16):
-    """Stand-in for ``fms.models.get_model``: build a registered base model and (for ``source='hf'`` Llama
-    checkpoints) load weights; ``distributed_strategy='tp'`` shards it over ``group``."""
+    """Stand-in for ``fms.models.get_model``: build a registered base model and, when ``model_path`` holds an HF
+    checkpoint (``source='hf'``), load its weights -- Llama, GPT-BigCode and Mixtral (reference adapters
+    ``train_speculator_utils.py:526-569``); without a checkpoint the registered variant is built with random weights and
+    that is said out loud.  ``distributed_strategy='tp'`` shards a Llama base over ``group``."""
     dev = torch.device(device_type, torch.cuda.current_device()) if device_type == "cuda" else torch.device("cpu")
-    if model_path and arch == "embedllama" and os.path.exists(os.path.join(model_path, "config.json")):
-        from fms_fsdp_b200.models.hf_loader import load_hf_llama
-        model = load_hf_llama(model_path, "cpu", dtype, EmbedLLaMA)
+    has_ckpt = bool(model_path) and os.path.exists(os.path.join(model_path, "config.json"))
+    if has_ckpt and arch in ("embedllama", "embedgpt_bigcode", "embedmixtral"):
+        from fms_fsdp_b200.models import hf_loader
+        if arch == "embedllama":
+            model = hf_loader.load_hf_llama(model_path, "cpu", dtype, EmbedLLaMA)
+        elif arch == "embedgpt_bigcode":
+            model = hf_loader.load_hf_gpt_bigcode(model_path, EmbedGPTBigCode, "cpu", dtype)
+        else:
+            model = hf_loader.load_hf_mixtral(model_path, EmbedMixtral, "cpu", dtype)
     else:
+        if int(os.environ.get("RANK", 0)) == 0:
+            print(f"[get_model] no HF checkpoint at {model_path!r}: {arch}.{variant} is built with RANDOM weights")
         if (arch, variant) not in _REGISTRY:
             raise KeyError(f"unknown model {arch}.{variant}; registered: {sorted(_REGISTRY)}")
         with torch.device("meta"):

@@ -106,3 +106,27 @@ def test_hf_loader_roundtrip():
     back = load_hf_llama(d, dtype=torch.float32)
     x = torch.randint(0, 40, (2, 11))
     assert torch.allclose(m(x), back(x), atol=1e-5)
+
+
+def test_hf_gpt_bigcode_and_mixtral_checkpoints_load_with_equal_logits():
+    """``get_model(..., model_path=<HF dir>)`` loads GPT-BigCode and Mixtral weights (reference adapters
+    ``train_speculator_utils.py:526-569``): logits equal the ``transformers`` implementation on the same checkpoint."""
+    from transformers import GPTBigCodeConfig, GPTBigCodeForCausalLM, MixtralConfig, MixtralForCausalLM
+    from speculator.train_speculator_utils import get_model
+    torch.manual_seed(5)
+    x = torch.randint(0, 50, (2, 13))
+    d1 = tempfile.mkdtemp()
+    hf = GPTBigCodeForCausalLM(GPTBigCodeConfig(vocab_size=50, n_positions=64, n_embd=32, n_layer=2, n_head=4, n_inner=128,
+                                                multi_query=True, attn_pdrop=0.0, resid_pdrop=0.0, embd_pdrop=0.0)).eval()
+    hf.save_pretrained(d1)
+    ours = get_model("embedgpt_bigcode", "20b", model_path=d1, device_type="cpu", dtype=torch.float32)
+    with torch.no_grad():
+        assert torch.allclose(ours(x), hf(x).logits, atol=2e-4)
+    d2 = tempfile.mkdtemp()
+    hf2 = MixtralForCausalLM(MixtralConfig(vocab_size=50, hidden_size=32, intermediate_size=48, num_hidden_layers=2,
+                                           num_attention_heads=4, num_key_value_heads=2, num_local_experts=4,
+                                           num_experts_per_tok=2, max_position_embeddings=64)).eval()
+    hf2.save_pretrained(d2)
+    ours2 = get_model("embedmixtral", "8x7b", model_path=d2, device_type="cpu", dtype=torch.float32)
+    with torch.no_grad():
+        assert torch.allclose(ours2(x), hf2(x).logits, atol=2e-4)
