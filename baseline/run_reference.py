@@ -36,6 +36,7 @@ def main():
     ap.add_argument("--seq", type=int, default=4096)
     ap.add_argument("--batch", type=int, default=2)
     ap.add_argument("--no_compile", action="store_true")
+    ap.add_argument("--ac", default="0", help="selective activation checkpointing fraction (reference --selective_checkpointing)")
     a = ap.parse_args()
 
     import torch
@@ -65,8 +66,8 @@ def main():
     update_config(cfg, model_variant=a.model, use_dummy_dataset=True, sharding_strategy="fsdp", seq_length=a.seq,
                   batch_size=a.batch, low_cpu_fsdp=True, use_torch_compile=not a.no_compile,
                   report_interval=max(a.steps, a.warmup),   # one report per train() call, never per step
-                  num_steps=a.warmup, vocab_size=32000, fsdp_activation_checkpointing=False,
-                  checkpoint_interval=10 ** 9)
+                  num_steps=a.warmup, vocab_size=32000, fsdp_activation_checkpointing=(a.ac not in ("0", "0.0", "")),
+                  selective_checkpointing=a.ac, checkpoint_interval=10 ** 9)
     torch.cuda.manual_seed(cfg.seed); torch.manual_seed(cfg.seed)
     setup()
     torch.cuda.set_device(local_rank); torch.cuda.empty_cache()
@@ -80,6 +81,8 @@ def main():
                  use_orig_params=cfg.use_torch_compile, device_id=torch.cuda.current_device(), limit_all_gathers=True,
                  param_init_fn=param_init_fn)
     model.rot_emb.compute_freqs_cis(torch.device("cuda", torch.cuda.current_device()), model.config.max_expected_seq_len)
+    if cfg.fsdp_activation_checkpointing:      # reference main_training_llama.py:99-102
+        apply_ac(model, p=cfg.selective_checkpointing)
     compiled = False
     if cfg.use_torch_compile:
         torch._dynamo.config.accumulated_cache_size_limit = 128
@@ -129,6 +132,10 @@ def main():
         root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
         sys.path.insert(0, root)
         from bench import DATA_NOTE, bench_config
+    try:
+        from bench import PUBLISHED_TOK_S_GPU as PUB
+    except Exception:
+        PUB = {"llama2_7b": 9600.0}
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     loss = run_train(a.warmup, a.warmup + a.steps)
@@ -141,12 +148,13 @@ def main():
     value = a.batch * a.seq * world / (ms_step / 1e3)
     if rank == 0:
         print(json.dumps({
-            "metric": "tokens/sec (Llama2-7B FSDP seq4k bs2)", "value": round(value, 1), "unit": "tokens/s",
+            "metric": "tokens/sec (Llama2-7B FSDP seq4k bs2)" if a.model == "llama2_7b" else f"tokens/sec ({a.model})",
+            "value": round(value, 1), "unit": "tokens/s",
             "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": round(ms_step, 3),
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": round(value / world / 9600.0, 4),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": (round(value / world / PUB[a.model], 4) if a.model in PUB else None),
             "dtype": "bf16", "data": DATA_NOTE, "impl": "reference",
             "tokens_per_sec_per_gpu": round(value / world, 1),
-            "config": bench_config(a.model, a.batch * world, a.seq, f"fsdp{world}", "0"),
+            "config": bench_config(a.model, a.batch * world, a.seq, f"fsdp{world}", a.ac),
             "details": {"torch_compile": compiled, "stack": "torch FSDP1 + cuBLAS + SDPA + NCCL",
                         "deps": "ibm-fms/fire absent offline -> plain-torch stand-ins in baseline/fms_shim; reference code unmodified"},
             "loss_steps": [a.warmup + 1, a.warmup + a.steps],

@@ -312,7 +312,7 @@ def run_reference(a):
             print(json.dumps({"impl": "reference", "unavailable": "baseline/_ref not installed (pip --target failed or not run)"}))
         return
     sys.argv = [runner, "--gpus", str(a.gpus), "--steps", str(a.steps), "--warmup", str(a.warmup),
-                "--model", a.model, "--seq", str(a.seq), "--batch", str(a.batch)]
+                "--model", a.model, "--seq", str(a.seq), "--batch", str(a.batch), "--ac", str(a.ac)]
     import runpy
     runpy.run_path(runner, run_name="__main__")
 
