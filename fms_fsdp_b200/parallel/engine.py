@@ -90,7 +90,7 @@ class ShardUnit:
         for (_, p), s in zip(self.params, self.layout.slots):
             p._grad_ready = False
             p.grad = None
-            if p.dim() == 1:
+            if len(s.shape) == 1:
                 p._grad_buf, p._grad_push = vec[s.offset:s.offset + s.numel].view(s.shape), None
             else:
                 p._grad_buf, p._grad_push = None, make_target(s)
@@ -98,10 +98,12 @@ class ShardUnit:
     def collect_grads(self):
         """Fold autograd-produced .grad (ops that did not write into the buffer) and zero the slots
         of parameters that received no gradient at all."""
-        for _, p in self.params:
+        for pname, p in self.params:
             if getattr(p, "_grad_push", None) is not None:
                 if p.grad is not None or not p._grad_ready:
-                    raise RuntimeError("push reduce-scatter: every weight matrix must receive exactly one wgrad GEMM")
+                    raise RuntimeError(f"push reduce-scatter ({self.name}): weight {pname} {tuple(p.shape)} must receive exactly "
+                                       f"one wgrad GEMM (autograd .grad present: {p.grad is not None}, wgrad delivered: "
+                                       f"{bool(p._grad_ready)}); set engine_push_wgrad = False on the block to use the pull path")
                 continue
             buf = p._grad_buf
             if p.grad is not None:
@@ -484,7 +486,8 @@ class ShardedModel(nn.Module):
         ok = getattr(u, "_push_ok", None)
         if ok is None:
             from fms_fsdp_b200.ops.cuda_kernels import push_eligible_shape
-            ok = (all(p.dim() == 1 or push_eligible_shape(tuple(p.shape)) for _, p in u.params)
+            # (slot shapes, not p.shape: released parameters point at an empty placeholder)
+            ok = (all(len(sl.shape) == 1 or push_eligible_shape(tuple(sl.shape)) for sl in u.layout.slots)
                   and u.layout.matrix_begin % 8 == 0 and u.layout.shard_numel % 8 == 0
                   and getattr(u.modules[0], "engine_push_wgrad", True))
             u._push_ok = ok

@@ -168,6 +168,28 @@ def _init_tracker(cfg, rank):
 
 
 # --------------------------------------------------------------------------------------------- train
+# One page-locked arena per process for the loop's staging slots.  cudaHostAlloc maps the block into every visible device
+# and takes the driver lock: with 8 GPUs visible each call cost tens of milliseconds (the first train() call of an 8-GPU
+# job spent ~0.4 s in eight of them), so the slots are carved out of ONE allocation that later train() calls reuse.
+_ARENA = {"buf": None, "used": 0}
+
+
+def _pinned_slot(shape, dtype) -> torch.Tensor:
+    n = 1
+    for d in shape:
+        n *= int(d)
+    nbytes = (n * torch.empty((), dtype=dtype).element_size() + 255) // 256 * 256
+    if _ARENA["buf"] is None or _ARENA["used"] + nbytes > _ARENA["buf"].numel():
+        if _ARENA["buf"] is not None and nbytes <= _ARENA["buf"].numel():
+            _ARENA["used"] = 0           # wrap: old slots belong to loops that have finished
+        else:
+            _ARENA["buf"] = torch.empty(max(4 << 20, 2 * nbytes), dtype=torch.uint8).pin_memory()
+            _ARENA["used"] = 0
+    off = _ARENA["used"]
+    _ARENA["used"] += nbytes
+    return _ARENA["buf"][off:off + n * torch.empty((), dtype=dtype).element_size()].view(dtype).view(shape)
+
+
 class _H2DStager:
     """Host -> device path of the training loop: the loader's (pageable) batch is copied into a small ring of PINNED
     staging buffers and sent with an asynchronous copy, so the step's input transfer overlaps the previous step's
@@ -184,7 +206,7 @@ class _H2DStager:
         key = (tuple(t.shape), t.dtype)
         ring = self.slots.get(key)
         if ring is None:
-            ring = [(torch.empty(t.shape, dtype=t.dtype).pin_memory(), torch.cuda.Event()) for _ in range(self.depth)]
+            ring = [(_pinned_slot(t.shape, t.dtype), torch.cuda.Event()) for _ in range(self.depth)]
             self.slots[key] = ring
         buf, ev = ring[self.k % self.depth]
         self.k += 1
@@ -202,7 +224,7 @@ class _LossReadback:
     def __init__(self, device, depth: int = 4):
         self.on = device.type == "cuda"
         if self.on:
-            self.ring = [(torch.zeros(1, dtype=torch.float32).pin_memory(), torch.cuda.Event(), [None]) for _ in range(depth)]
+            self.ring = [(_pinned_slot((1,), torch.float32), torch.cuda.Event(), [None]) for _ in range(depth)]
         self.k, self.depth, self.device, self.last = 0, depth, device, None
 
     def push(self, loss: torch.Tensor, step: int):
