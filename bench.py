@@ -197,7 +197,7 @@ def run_ours(a):
         cfg.checkpoint_interval = 10 ** 9
         cfg.use_dummy_dataset = True
         cfg.num_steps = start_step + n_steps
-        cfg.report_interval = cfg.num_steps     # exactly one report (and its stats all-reduce), at the last step
+        cfg.report_interval = max(1, cfg.num_steps)     # exactly one report (and its stats all-reduce), at the last step
         sink = contextlib.nullcontext() if os.environ.get("FMS_B200_BENCH_VERBOSE") \
             else contextlib.redirect_stdout(open(os.devnull, "w"))
         with sink:
@@ -207,7 +207,8 @@ def run_ours(a):
     # staging arena, events, tracker init -- belong to warm-up exactly like the kernels' first launches)
     for i in range(a.warmup - 1):
         loss, _ = step_device(*dev_batches[i])
-    run_train(a.warmup - 1, 1, iter([tuple(t.cpu() for t in (dev_batches[a.warmup - 1][0], dev_batches[a.warmup - 1][1].int()))]))
+    if a.warmup >= 1:
+        run_train(a.warmup - 1, 1, iter([tuple(t.cpu() for t in (dev_batches[a.warmup - 1][0], dev_batches[a.warmup - 1][1].int()))]))
     sync_all()
 
     sampler = ClockSampler(local_rank)
