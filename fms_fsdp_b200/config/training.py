@@ -98,7 +98,7 @@ class train_config:
     collective_impl: str = "auto"            # auto | fused (NVLink peer kernels) | torch (c10d collectives)
     hsdp_shard_size: int = 0                 # 0 = local device count (reference behaviour); 4 -> 2x4 on one box
     kernel_path: str = "auto"                # auto | fused (sm_100a kernels) | torch (ATen oracle)
-    precision: str = "bf16"                  # GEMM operand precision; only bf16 exists (mxfp8 is rejected at start-up)
+    precision: str = "bf16"                  # bf16 | fp8 (opt-in: row-wise scaled e4m3 forward GEMMs, bf16 backward)
     prefetch_depth: int = 2                  # gathered-unit buffers in flight (reference limiter = 2)
     fused_cross_entropy: bool = True         # linear+CE without materialising logits
     fault_inject_step: int = 0               # >0: rank 1 exits at that step (resume drill)

@@ -67,6 +67,8 @@ DECL int b200_attn_bwd(const void*, const void*, const void*, const float*, void
                        float, const float*, cudaStream_t);
 DECL void b200_gemm2_set_rope(const float*, int, int, int);
 DECL void b200_gemm2_set_swiglu(void*, int, int, int);
+DECL int b200_gemm2_fp8(const void*, const void*, void*, const float*, const float*, int, int, int, int, int, int, cudaStream_t);
+DECL int b200_quant_rowwise_e4m3(const void*, void*, float*, int, int, int, int, cudaStream_t);
 DECL void b200_gemm2_set_push(void* const*, long long, long long, int, int, int);
 DECL int b200_p2p_push_range(const void*, void* const*, long long, long long, long long, int, cudaStream_t);
 DECL int b200_p2p_allgather(const void* const*, void*, long long, int, int, cudaStream_t);
@@ -506,6 +508,29 @@ void gemm_push(const at::Tensor& a, const at::Tensor& b) {
   check(b200_gemm2_bf16(a.data_ptr(), b.data_ptr(), nullptr, nullptr, M, N, K, a.stride(0), b.stride(0), N, 0, 1, 1, 4, 0,
                         cur_stream()), "gemm2_push_bf16_tcgen05");
 }
+// optional fp8 forward path: row-wise e4m3 quantisation and the e4m3 x e4m3 -> bf16 GEMM (kind::f8f6f4)
+std::vector<at::Tensor> quant_rowwise_e4m3(const at::Tensor& x) {
+  c10::cuda::CUDAGuard guard(x.device());
+  need(x, "x", at::kBFloat16);
+  need_rowmajor2d(x, "x");
+  TORCH_CHECK(x.size(1) % 16 == 0, "quant_rowwise_e4m3: K must be a multiple of 16");
+  auto q = at::empty({x.size(0), x.size(1)}, x.options().dtype(at::kByte));
+  auto sc = at::empty({x.size(0)}, x.options().dtype(at::kFloat));
+  check(b200_quant_rowwise_e4m3(x.data_ptr(), q.data_ptr(), sc.data_ptr<float>(), (int)x.size(0), (int)x.size(1),
+                                (int)x.stride(0), (int)q.stride(0), cur_stream()), "quant_rowwise_e4m3");
+  return {q, sc};
+}
+void gemm_fp8(const at::Tensor& aq, const at::Tensor& bq, const at::Tensor& sa, const at::Tensor& sb, at::Tensor& c) {
+  c10::cuda::CUDAGuard guard(aq.device());
+  need(aq, "a_q", at::kByte); need(bq, "b_q", at::kByte); need(sa, "scale_a", at::kFloat); need(sb, "scale_b", at::kFloat);
+  need(c, "c", at::kBFloat16);
+  need_rowmajor2d(aq, "a_q"); need_rowmajor2d(bq, "b_q"); need_rowmajor2d(c, "c");
+  const int M = aq.size(0), K = aq.size(1), N = bq.size(0);
+  TORCH_CHECK(bq.size(1) == K && c.size(0) == M && c.size(1) == N && sa.numel() == M && sb.numel() == N &&
+              sa.is_contiguous() && sb.is_contiguous(), "gemm_fp8: shape mismatch");
+  check(b200_gemm2_fp8(aq.data_ptr(), bq.data_ptr(), c.data_ptr(), sa.data_ptr<float>(), sb.data_ptr<float>(), M, N, K,
+                       (int)aq.stride(0), (int)bq.stride(0), (int)c.stride(0), cur_stream()), "gemm2_fp8_tcgen05");
+}
 void p2p_gather_range(const at::Tensor& peer_ptrs, at::Tensor& full, int64_t shard_bytes, int64_t begin, int64_t end) {
   c10::cuda::CUDAGuard guard(full.device());
   check(b200_p2p_gather_range((const void* const*)peer_ptrs.data_ptr(), full.data_ptr(), shard_bytes, begin, end, cur_stream()),
@@ -807,6 +832,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("get_gemm_2cta", &get_gemm_2cta);
   m.def("gemm_ag", &gemm_ag);
   m.def("gemm_push", &gemm_push);
+  m.def("quant_rowwise_e4m3", &quant_rowwise_e4m3);
+  m.def("gemm_fp8", &gemm_fp8);
   m.def("p2p_gather_range", &p2p_gather_range);
   m.def("ts_mma_probe", &ts_mma_probe);
   m.def("launch_count", &launch_count);

@@ -135,6 +135,11 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, bool a_mn_m
          (static_cast<uint32_t>(M >> 4) << 24);
 }
 
+// Instruction descriptor for kind::f8f6f4 with e4m3 inputs (format code 0) and fp32 accumulation, both operands K-major.
+__host__ __device__ constexpr uint32_t make_idesc_e4m3(int M, int N) {
+  return (1u << 4) | (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
+}
+
 // One lane of a CONVERGED warp.  Issue tcgen05.mma behind this instead of `lane == 0`: the compiler then knows a single
 // thread is active and emits back-to-back UTCHMMA with hoisted descriptors; a `lane == 0` branch makes it wrap every
 // UTCHMMA in an ELECT / BRA.U.ANY waterfall loop plus per-MMA descriptor rebuilds (~14 instructions per MMA, which
@@ -240,6 +245,16 @@ B200_DEVINL void umma_bf16_ss_2cta(uint32_t tmem_d, uint64_t adesc, uint64_t bde
       "{\n\t.reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// 8-bit operands (e4m3): K = 32 elements (= 32 bytes, the same descriptor step as bf16's K = 16) per instruction
+B200_DEVINL void umma_e4m3_ss_2cta(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                   uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }

@@ -886,3 +886,52 @@ extern "C" int b200_sumsq(const void* x, int is_bf16, long long n, float* out, c
   else sumsq_kernel<float><<<g, 256, 0, s>>>((const float*)x, (size_t)n, out);
   CK();
 }
+
+// ------------------------------------------------------------------------------------------------------------------
+// Row-wise e4m3 quantisation for the optional fp8 forward GEMMs: one warp per row; scale[row] = amax(row) / 448 (the
+// largest finite e4m3 value), q = x / scale rounded to nearest, saturating.  The second pass re-reads the row from L1/L2.
+namespace b200 {
+B200_DEVINL uint32_t cvt_e4m3x4(float a, float b, float c, float d) {
+  uint16_t lo, hi;
+  asm("cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2;" : "=h"(lo) : "f"(b), "f"(a));   // {second operand -> low byte}
+  asm("cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2;" : "=h"(hi) : "f"(d), "f"(c));
+  return (uint32_t)lo | ((uint32_t)hi << 16);
+}
+__global__ void __launch_bounds__(256) quant_rowwise_e4m3_kernel(const __nv_bfloat16* __restrict__ x, uint8_t* __restrict__ q,
+                                                                 float* __restrict__ scale, int rows, int K, int ldx, int ldq) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const __nv_bfloat16* xr = x + (size_t)row * ldx;
+  float amax = 0.f;
+  for (int c = lane * 8; c < K; c += 256) {
+    const uint4 v = *reinterpret_cast<const uint4*>(xr + c);
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 f = unpack_bf16x2(w[i]);
+      amax = fmaxf(amax, fmaxf(fabsf(f.x), fabsf(f.y)));
+    }
+  }
+  amax = warp_max(amax);
+  const float sc = amax > 0.f ? amax * (1.f / 448.f) : 1.f;
+  const float inv = 1.f / sc;
+  if (lane == 0) scale[row] = sc;
+  uint8_t* qr = q + (size_t)row * ldq;
+  for (int c = lane * 8; c < K; c += 256) {
+    const uint4 v = *reinterpret_cast<const uint4*>(xr + c);
+    const float2 a = unpack_bf16x2(v.x), b = unpack_bf16x2(v.y), e = unpack_bf16x2(v.z), f = unpack_bf16x2(v.w);
+    uint2 o;
+    o.x = cvt_e4m3x4(a.x * inv, a.y * inv, b.x * inv, b.y * inv);
+    o.y = cvt_e4m3x4(e.x * inv, e.y * inv, f.x * inv, f.y * inv);
+    *reinterpret_cast<uint2*>(qr + c) = o;
+  }
+}
+}  // namespace b200
+
+extern "C" int b200_quant_rowwise_e4m3(const void* x, void* q, float* scale, int rows, int K, int ldx, int ldq, cudaStream_t s) {
+  if ((K % 8) || (ldx % 8) || (ldq % 8)) return -1;
+  const int warps = 8;
+  b200::quant_rowwise_e4m3_kernel<<<(rows + warps - 1) / warps, warps * 32, 0, s>>>((const __nv_bfloat16*)x, (uint8_t*)q, scale,
+                                                                                   rows, K, ldx, ldq);
+  return (int)cudaGetLastError();
+}

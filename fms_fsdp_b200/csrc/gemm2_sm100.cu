@@ -31,7 +31,7 @@ constexpr int PUSH_ROW_PITCH = 144;
 constexpr int PUSH_STAGE_BYTES = 4 * 32 * PUSH_ROW_PITCH;   // 18 KiB per CTA
 
 enum { P_EPI_STORE = 0, P_EPI_RESIDUAL = 1, P_EPI_ACCUM = 2, P_EPI_ROPE = 3, P_EPI_PUSH = 4, P_EPI_SWIGLU = 5,
-       P_EPI_SWIGLU_BWD = 6 };
+       P_EPI_SWIGLU_BWD = 6, P_EPI_SCALE = 7 };
 
 
 // L2-friendly rasterisation: sweep all n-tiles for a band of GROUP_M m-tiles before moving to the next band, so the
@@ -135,6 +135,10 @@ struct Gemm2Params {
   // aux = the saved projection [M, 2F] and stores d(gate) | d(up) to C [M, 2F] -- dS itself never reaches memory.
   void* aux;
   int ld_aux, swi_F, swi_gate_first;
+  // P_EPI_SCALE (fp8 e4m3 operands, FP8 = true): C = acc * scale_a[row] * scale_b[col]  (row-wise scales of both
+  // quantised operands; the optional reduced-precision forward path, default off)
+  const float* scale_a;
+  const float* scale_b;
 };
 
 B200_DEVINL float sigmoidf_fast(float x) { return __frcp_rn(1.f + exp2f(-1.4426950408889634f * x)); }
@@ -144,7 +148,7 @@ B200_DEVINL void bulk_store_s2g(void* gdst, const void* ssrc, uint32_t bytes) {
                ::"l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes) : "memory");
 }
 
-template <bool A_MN, bool B_MN, int EPI, typename OutT, bool AG>
+template <bool A_MN, bool B_MN, int EPI, typename OutT, bool AG, bool FP8 = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(P_THREADS + (AG ? 32 * AG_WARPS : 0), 1)
 gemm2_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, Gemm2Params p,
                    AgParams ag) {
@@ -161,7 +165,10 @@ gemm2_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   const uint32_t rank = cluster_ctarank();
   const bool leader = rank == 0;
   const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
-  const int num_kb = (p.K + P_BK - 1) / P_BK;
+  // elements per k-block: one 128-byte swizzle atom per row = 64 bf16 or 128 e4m3
+  constexpr int BKE = FP8 ? 2 * P_BK : P_BK;
+  static_assert(!FP8 || (!A_MN && !B_MN && !AG), "fp8 operands: K-major (nt) only, no fused gather");
+  const int num_kb = (p.K + BKE - 1) / BKE;
   const int num_tiles = p.m_tiles * p.n_tiles;
 
   if (warp == 0 && lane == 0) {
@@ -199,7 +206,7 @@ gemm2_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           uint8_t* sa = smem + stage * P_STAGE_BYTES;
           uint8_t* sb = sa + PA_BYTES;
           if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * P_STAGE_BYTES);
-          const int k0 = kb * P_BK;
+          const int k0 = kb * BKE;
           if constexpr (AG) {
             if (ag.dependent) {
               // stored rows of B under this CTA's loads: K-major -> rows [n0, n0+128) (once per tile);
@@ -234,7 +241,7 @@ gemm2_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA only) =====================
     if (leader) {
-      constexpr uint32_t idesc = make_idesc_bf16(P_BM, P_BN, A_MN, B_MN);
+      constexpr uint32_t idesc = FP8 ? make_idesc_e4m3(P_BM, P_BN) : make_idesc_bf16(P_BM, P_BN, A_MN, B_MN);
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
       for (int t = pair; t < num_tiles; t += n_pairs) {
@@ -253,7 +260,8 @@ gemm2_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             for (int k = 0; k < P_BK / 16; ++k) {
               const uint64_t adesc = a0 + ((A_MN ? k * 2048 : k * 32) >> 4);
               const uint64_t bdesc = b0 + ((B_MN ? k * 2048 : k * 32) >> 4);
-              umma_bf16_ss_2cta(tmem_d, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+              if constexpr (FP8) umma_e4m3_ss_2cta(tmem_d, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+              else umma_bf16_ss_2cta(tmem_d, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
             }
             umma_commit_2cta_mcast(&empty_bar[stage], 0x3);
             if (kb == num_kb - 1) umma_commit_2cta_mcast(&tfull_bar[acc], 0x3);
@@ -472,7 +480,13 @@ gemm2_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                   *reinterpret_cast<uint4*>(dst) = o;     // peer (or local) store; made visible by the flag round that follows
                   continue;
                 }
-                if constexpr (EPI == P_EPI_ROPE) {
+                if constexpr (EPI == P_EPI_SCALE) {
+                  const float sa = p.scale_a[row];
+                  const float4 b0 = *reinterpret_cast<const float4*>(p.scale_b + cb + g * 8);
+                  const float4 b1 = *reinterpret_cast<const float4*>(p.scale_b + cb + g * 8 + 4);
+                  f[0] *= sa * b0.x; f[1] *= sa * b0.y; f[2] *= sa * b0.z; f[3] *= sa * b0.w;
+                  f[4] *= sa * b1.x; f[5] *= sa * b1.y; f[6] *= sa * b1.z; f[7] *= sa * b1.w;
+                } else if constexpr (EPI == P_EPI_ROPE) {
                   const int c8 = cb + g * 8;
                   if (c8 < p.rope_cols) {
                     const float4* tp = reinterpret_cast<const float4*>(
@@ -486,7 +500,7 @@ gemm2_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                       f[2 * i + 1] = a0 * sn[i] + a1 * cs[i];
                     }
                   }
-                } else if constexpr (EPI != P_EPI_STORE) {
+                } else if constexpr (EPI != P_EPI_STORE && EPI != P_EPI_SCALE) {
                   const __nv_bfloat16* src = (EPI == P_EPI_RESIDUAL) ? (rrow + cb + g * 8)
                                                                      : (reinterpret_cast<const __nv_bfloat16*>(crow) + cb + g * 8);
                   uint4 r = *reinterpret_cast<const uint4*>(src);
@@ -568,6 +582,21 @@ static int launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gemm2Pa
   int pairs = sm_count() / 2;
   if (tiles < pairs) pairs = tiles;
   kern<<<pairs * 2, P_THREADS, smem, stream>>>(tmA, tmB, p, AgParams{});
+  return (int)cudaGetLastError();
+}
+
+static int launch2_fp8(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gemm2Params& p, cudaStream_t stream) {
+  auto kern = gemm2_bf16_tcgen05<false, false, P_EPI_SCALE, __nv_bfloat16, false, true>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM);
+    if (e != cudaSuccess) return (int)e;
+    configured = true;
+  }
+  int tiles = p.m_tiles * p.n_tiles;
+  int pairs = sm_count() / 2;
+  if (tiles < pairs) pairs = tiles;
+  kern<<<pairs * 2, P_THREADS, P_SMEM, stream>>>(tmA, tmB, p, AgParams{});
   return (int)cudaGetLastError();
 }
 
@@ -733,4 +762,22 @@ extern "C" int b200_gemm2_ag_bf16(const void* A, const void* B, void* C, const v
   }
 #undef AGL
   return -7;
+}
+
+// C[M, N] (bf16) = (A_q[M, K] x B_q[N, K]^T) * scale_a[M] * scale_b[N]  with e4m3 operands on the tensor cores
+// (tcgen05.mma kind::f8f6f4, fp32 accumulate).  K (bytes = elements) must be a multiple of 16; rows 16-byte aligned.
+extern "C" int b200_gemm2_fp8(const void* A, const void* B, void* C, const float* scale_a, const float* scale_b, int M, int N,
+                              int K, int lda, int ldb, int ldc, cudaStream_t stream) {
+  using namespace b200;
+  if ((K % 16) || (lda % 16) || (ldb % 16) || (N % 8) || (ldc % 8) || M < 1) return -13;
+  CUtensorMap tmA, tmB;
+  if (make_tmap_2d_u8(&tmA, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, 2 * P_BK, C_BM)) return 1001;
+  if (make_tmap_2d_u8(&tmB, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, 2 * P_BK, C_BN)) return 2001;
+  Gemm2Params p{};
+  p.M = M; p.N = N; p.K = K; p.ldc = ldc; p.ldr = 0; p.C = C; p.R = nullptr;
+  p.m_tiles = (M + P_BM - 1) / P_BM;
+  p.n_tiles = (N + P_BN - 1) / P_BN;
+  p.tile_rot = 0;
+  p.scale_a = scale_a; p.scale_b = scale_b;
+  return launch2_fp8(tmA, tmB, p, stream);
 }

@@ -68,6 +68,15 @@ inline int make_tmap_2d_bf16(CUtensorMap* m, const void* ptr, uint64_t inner, ui
   return make_tmap(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, ptr, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
+// e4m3 / uint8 operand tiles: one element = one byte, 128-byte swizzle atoms hold 128 elements along K
+inline int make_tmap_2d_u8(CUtensorMap* m, const void* ptr, uint64_t inner, uint64_t outer, uint64_t ld_bytes,
+                           uint32_t box_inner, uint32_t box_outer) {
+  uint64_t dims[2] = {inner, outer};
+  uint64_t strides[1] = {ld_bytes};
+  uint32_t box[2] = {box_inner, box_outer};
+  return make_tmap(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, ptr, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+}
+
 inline int sm_count() {
   static int n = 0;
   if (!n) {

@@ -284,6 +284,26 @@ def gated_down_bwd(dy, w2, gu, gate_first=True):
     return dgu
 
 
+# ------------------------------------------------------------------------ optional fp8 (e4m3) forward GEMMs
+def quant_rowwise_e4m3(x):
+    if x.dtype != torch.bfloat16 or x.dim() != 2 or x.shape[1] % 16 or x.stride(-1) != 1:
+        return _fallback("quant_rowwise_e4m3").quant_rowwise_e4m3(x)
+    q, sc = _C.quant_rowwise_e4m3(x)
+    return q, sc
+
+
+def gemm_fp8(aq, bq, sa, sb, out=None):
+    """e4m3 x e4m3 -> bf16 on the tensor cores (tcgen05.mma kind::f8f6f4, CTA pair), row / column scales in the epilogue."""
+    M, K = aq.shape
+    N = bq.shape[0]
+    if out is None:
+        out = torch.empty(M, N, dtype=torch.bfloat16, device=aq.device)
+    if K % 16 or N % 8 or not _C.get_gemm_2cta():
+        return _fallback("gemm_fp8").gemm_fp8(aq, bq, sa, sb, out)
+    _C.gemm_fp8(aq, bq, sa, sb, out)
+    return out
+
+
 # --------------------------------------------------------------------------------------- RMSNorm
 def rmsnorm_fwd(x, w, eps):
     if x.dtype != torch.bfloat16 or x.shape[-1] % 8 or x.shape[-1] > 8192:

@@ -100,8 +100,48 @@ class _Linear(torch.autograd.Function):
         return dx, dw, (dy if ctx.has_res else None)
 
 
+# ---- optional reduced-precision forward GEMMs (default "bf16"; "fp8" is opt-in and never used for the headline metric)
+_GEMM_PRECISION = os.environ.get("FMS_B200_PRECISION", "bf16")
+
+
+def set_gemm_precision(p: str):
+    global _GEMM_PRECISION
+    if p not in ("bf16", "fp8"):
+        raise ValueError(f"precision must be bf16|fp8, got {p}")
+    _GEMM_PRECISION = p
+
+
+def get_gemm_precision() -> str:
+    return _GEMM_PRECISION
+
+
+class _LinearFP8(torch.autograd.Function):
+    """y = x @ w^T with BOTH operands quantised row-wise to e4m3 on the fly (scale = row amax / 448) and multiplied on the
+    fp8 tensor cores with fp32 accumulation; the backward is the bf16 backward of ``_Linear`` (fp8 forward / bf16
+    backward recipe).  Activations and weights stay bf16 in memory."""
+
+    @staticmethod
+    def forward(ctx, x, w, residual):
+        K = kernels_for(x)
+        x2 = x.reshape(-1, x.shape[-1])
+        wd = _wdata(w)
+        xq, sx = K.quant_rowwise_e4m3(x2 if x2.is_contiguous() else x2.contiguous())
+        wq, sw = K.quant_rowwise_e4m3(wd if wd.is_contiguous() else wd.contiguous())
+        y = torch.empty(*x.shape[:-1], wd.shape[0], dtype=x.dtype, device=x.device)
+        K.gemm_fp8(xq, wq, sx, sw, out=y.view(-1, wd.shape[0]))
+        if residual is not None:
+            y += residual
+        ctx.K, ctx.w, ctx.has_res = K, w, residual is not None
+        ctx.save_for_backward(x)
+        return y
+
+    backward = _Linear.backward
+
+
 def linear(x, w, residual: Optional[torch.Tensor] = None):
     """y = x @ w^T (+ residual, fused in the GEMM epilogue)."""
+    if _GEMM_PRECISION == "fp8" and x.dtype == torch.bfloat16 and x.shape[-1] % 16 == 0:
+        return _LinearFP8.apply(x, w, residual)
     return _Linear.apply(x, w, residual)
 
 
@@ -283,6 +323,8 @@ def qkv_attention(h, w, table, nheads, kvheads, head_dim, scale=None):
     """attention(rope(h @ w^T)) for a fused [(H + 2 KVH) * hd, D] projection weight; h: [B, S, D]."""
     S = h.shape[1]
     scale = (head_dim ** -0.5) if scale is None else scale
+    if _GEMM_PRECISION == "fp8":     # fp8 projection, then the stand-alone RoPE kernel and attention
+        return attention(rope_(linear(h, w), table, S, nheads, kvheads, head_dim), nheads, kvheads, head_dim, scale)
     return _QKVAttention.apply(h, w, table, S, nheads, kvheads, head_dim, scale)
 
 
@@ -351,6 +393,8 @@ class _GatedMLP(torch.autograd.Function):
 def gated_mlp(x, wg1, w2, residual: Optional[torch.Tensor] = None, gate_first: bool = True):
     """SwiGLU MLP: ``(silu(g) * u) @ w2^T (+ residual)`` with ``[g | u] = x @ wg1^T`` (``gate_first=False``: ``[u | g]``,
     the mamba_ssm GatedMLP order)."""
+    if _GEMM_PRECISION == "fp8":
+        return linear(swiglu(linear(x, wg1), gate_first), w2, residual)
     return _GatedMLP.apply(x, wg1, w2, residual, gate_first)
 
 

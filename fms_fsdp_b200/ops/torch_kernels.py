@@ -194,6 +194,32 @@ def attn_bwd(do, qkv, o, lse, B, S, H, KVH, hd, scale, causal=True, rope_table=N
 
 
 # ----------------------------------------------------------------------------------------------
+# Optional fp8 forward path (default off): row-wise scaled e4m3 operands, fp32 accumulation.
+# ----------------------------------------------------------------------------------------------
+E4M3_MAX = 448.0
+
+
+def quant_rowwise_e4m3(x):
+    """(q uint8 view of float8_e4m3fn [R, K], scale fp32 [R]) with scale = amax(row) / 448."""
+    xf = x.float()
+    amax = xf.abs().amax(dim=1)
+    sc = torch.where(amax > 0, amax / E4M3_MAX, torch.ones_like(amax))
+    q = (xf / sc[:, None]).clamp(-E4M3_MAX, E4M3_MAX).to(torch.float8_e4m3fn)
+    return q.view(torch.uint8), sc
+
+
+def gemm_fp8(aq, bq, sa, sb, out=None):
+    """C = (A_q B_q^T) * sa[:, None] * sb[None, :] in bf16 (oracle of csrc/gemm2_sm100.cu b200_gemm2_fp8)."""
+    a = aq.view(torch.float8_e4m3fn).float()
+    b = bq.view(torch.float8_e4m3fn).float()
+    y = ((a @ b.t()) * sa[:, None] * sb[None, :]).to(torch.bfloat16)
+    if out is not None:
+        out.copy_(y)
+        return out
+    return y
+
+
+# ----------------------------------------------------------------------------------------------
 # SwiGLU on the fused gate/up projection gu = [gate | up] (FMS wg1_fused row order).
 # ----------------------------------------------------------------------------------------------
 def swiglu_fwd(gu, gate_first=True):

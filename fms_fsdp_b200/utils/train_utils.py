@@ -76,9 +76,14 @@ _STRATEGIES = {"fsdp": "fsdp", "hsdp": "hsdp", "ddp": "ddp"}
 
 def get_policies(cfg, rank, block):
     """(mixed_precision_policy, wrapping_policy, sharding_strategy, apply_selective_ac, param_init_fn)."""
-    if getattr(cfg, "precision", "bf16") != "bf16":
-        raise NotImplementedError(f"precision={cfg.precision!r}: only the bf16 GEMM path exists (block-scaled fp8 "
-                                  "operands are future work, see DESIGN.md section 6)")
+    precision = getattr(cfg, "precision", "bf16")
+    if precision not in ("bf16", "fp8"):
+        raise NotImplementedError(f"precision={precision!r}: bf16 (default) and fp8 (row-wise scaled e4m3 forward GEMMs, bf16 "
+                                  "backward) exist; block-scaled mxfp8 operands are future work, see DESIGN.md section 6")
+    from fms_fsdp_b200.ops.functional import set_gemm_precision
+    set_gemm_precision(precision)
+    if precision != "bf16" and rank == 0:
+        print("--> forward GEMMs run on e4m3 operands (row-wise scales, fp32 accumulation); backward stays bf16")
     mixed_precision_policy = get_mixed_precision_policy(cfg, rank)
     wrapping_policy = get_wrapper(block)
     sharding_strategy = _STRATEGIES.get(cfg.sharding_strategy, "fsdp")  # unknown -> full shard, like the reference

@@ -321,3 +321,46 @@ def test_gated_mlp_node_matches_unfused_ops(K):
     y2.backward(dy)
     assert rel(y, y2) < 1e-2
     assert rel(x.grad, x2.grad) < 2e-2 and rel(w1.grad, a1.grad) < 2e-2 and rel(w2.grad, a2.grad) < 2e-2
+
+
+def test_fp8_rowwise_quant_and_e4m3_gemm(K):
+    """Opt-in fp8 forward path: row-wise e4m3 quantisation kernel and the kind::f8f6f4 CTA-pair GEMM against the torch
+    float8_e4m3fn oracle (the GEMM is exact on the quantised values up to fp32 summation order and bf16 rounding)."""
+    CK, TK = K
+    torch.manual_seed(4)
+    M, N, Kd = 1024, 768, 512
+    x = (torch.randn(M, Kd, device=DEV) * 0.7).bfloat16()
+    w = (torch.randn(N, Kd, device=DEV) * 0.05).bfloat16()
+    n0 = CK.launch_count()
+    xq, sx = CK.quant_rowwise_e4m3(x)
+    wq, sw = CK.quant_rowwise_e4m3(w)
+    xq0, sx0 = TK.quant_rowwise_e4m3(x)
+    assert torch.allclose(sx, sx0, rtol=1e-6)
+    dq = xq.view(torch.float8_e4m3fn).float() * sx[:, None]
+    assert rel(dq, x) < 0.07                                              # e4m3: 3 mantissa bits
+    assert (xq.view(torch.float8_e4m3fn).float() - xq0.view(torch.float8_e4m3fn).float()).abs().max() <= 32  # <= 1 ulp at the top
+    y = CK.gemm_fp8(xq, wq, sx, sw)
+    assert CK.launch_count() == n0 + 3
+    y0 = TK.gemm_fp8(xq, wq, sx, sw)
+    assert rel(y, y0) < 1e-2
+    assert rel(y, x.float() @ w.float().t()) < 0.08
+
+
+def test_fp8_linear_trains_like_bf16(K):
+    from fms_fsdp_b200 import ops
+    from fms_fsdp_b200.ops import functional as Fn
+    torch.manual_seed(5)
+    x = (torch.randn(2, 256, 512, device=DEV) * 0.5).bfloat16().requires_grad_()
+    w = torch.nn.Parameter((torch.randn(1024, 512, device=DEV) * 0.04).bfloat16())
+    dy = torch.randn(2, 256, 1024, device=DEV).bfloat16()
+    y_ref = ops.linear(x, w)
+    Fn.set_gemm_precision("fp8")
+    try:
+        y = ops.linear(x, w)
+        y.backward(dy)
+    finally:
+        Fn.set_gemm_precision("bf16")
+    assert rel(y, y_ref) < 0.08
+    x2 = x.detach().requires_grad_(); w2 = torch.nn.Parameter(w.detach().clone())
+    ops.linear(x2, w2).backward(dy)
+    assert rel(x.grad, x2.grad) < 1e-2 and rel(w.grad, w2.grad) < 1e-2     # the backward is the bf16 backward

@@ -186,3 +186,29 @@ def test_gated_mlp_matches_autograd():
         assert torch.allclose(y, y2, atol=1e-5)
         for a, b in ((x.grad, x2.grad), (w1.grad, a1.grad), (w2.grad, a2.grad)):
             assert torch.allclose(a, b, atol=1e-4)
+
+
+def test_fp8_precision_switch_cpu_oracle():
+    """precision=fp8: linear / qkv_attention / gated_mlp run their forward GEMMs on row-wise e4m3 operands (torch oracle on
+    CPU), gradients come from the bf16 backward; default precision is untouched afterwards."""
+    import torch
+    from fms_fsdp_b200 import ops
+    from fms_fsdp_b200.ops import functional as Fn
+    from fms_fsdp_b200.ops import torch_kernels as TK
+    torch.manual_seed(0)
+    x = (torch.randn(4, 8, 32) * 0.5).bfloat16().requires_grad_()
+    w1 = torch.nn.Parameter((torch.randn(64, 32) * 0.2).bfloat16()); w2 = torch.nn.Parameter((torch.randn(32, 32) * 0.2).bfloat16())
+    ref = ops.gated_mlp(x, w1, w2, residual=x)
+    Fn.set_gemm_precision("fp8")
+    try:
+        assert Fn.get_gemm_precision() == "fp8"
+        y = ops.gated_mlp(x, w1, w2, residual=x)
+        y.float().sum().backward()
+    finally:
+        Fn.set_gemm_precision("bf16")
+    err = ((y.float() - ref.float()).abs().max() / ref.float().abs().max()).item()
+    assert 0 < err < 0.1, err                       # really quantised, and close
+    assert x.grad is not None and w1.grad is not None and w2.grad is not None
+    q, s = TK.quant_rowwise_e4m3(x.detach().reshape(-1, 32))
+    assert q.dtype == torch.uint8 and torch.all(s > 0)
+    assert (q.view(torch.float8_e4m3fn).float().abs().amax(1) - 448).abs().max() < 1e-3   # every row uses the full range
