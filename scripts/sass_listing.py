@@ -19,6 +19,8 @@ HOT = [
     ("gemm2_nn_dgrad_ag", r"gemm2_bf16_tcgen05<false, true, 0, __nv_bfloat16, true>"),
     ("gemm2_tn_wgrad_push_ag", r"gemm2_bf16_tcgen05<true, true, 4, __nv_bfloat16, true>"),
     ("gemm2_tn_wgrad_push", r"gemm2_bf16_tcgen05<true, true, 4, __nv_bfloat16, false>"),
+    ("gemm2_fp8_e4m3", r"gemm2_bf16_tcgen05<false, false, 7, __nv_bfloat16, false, true>"),
+    ("quant_rowwise_e4m3", r"quant_rowwise_e4m3_kernel"),
     ("attn_fwd2", r"attn_fwd2_kernel<128, 0>"),
     ("attn_bwd3_dkdv", r"attn_bwd3_kernel<128, 0, 1>"),
     ("attn_bwd3_dq", r"attn_bwd3_kernel<128, 1, 1>"),
