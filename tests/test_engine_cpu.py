@@ -251,3 +251,40 @@ def test_wrapping_policy_decides_the_shard_units():
         opt2.step()
         assert abs(loss.item() - out[st][0]) < 1e-5 and abs(gn - out[st][1]) < 1e-4
         assert abs(loss.item() - ref_losses[st]) < 1e-4
+
+
+def _reload_worker(rank, world, port, ckpt_dir, outdir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from fms_fsdp_b200.utils.checkpointing_utils import Checkpointer
+        torch.manual_seed(7)                                   # different weights than the checkpoint's
+        m = LLaMA(get_model_config("llama2_tiny")); m.reset_parameters()
+        eng = ShardedModel(m, sharding_strategy="fsdp", mixed_precision=fp32_policy, device="cpu", collective_impl="torch")
+        opt = ShardedAdamW(eng, lr=1e-3)
+        _, _, _, step, ntok, resuming = Checkpointer(ckpt_dir, 5, "fsdp", rank, rank).load(eng, opt, None, path="")
+        sd = eng.full_state_dict()
+        x = _batch(rank, STEPS)
+        loss = eng.forward_backward(x, x); gn = eng.clip_grad_norm_(1.0); opt.step()     # and training continues
+        if rank == 0:
+            torch.save(dict(sd=sd, step=step, ntok=ntok, resuming=resuming, opt_step=opt._step, loss=loss.item(),
+                            gn=gn.item()), os.path.join(outdir, "reload.pt"))
+    finally:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("save_world,load_world", [(2, 4), (4, 2)])
+def test_checkpoint_reshards_across_world_sizes(save_world, load_world):
+    """A sharded checkpoint written by W ranks loads into a job of a different size (the DCP chunks are per-parameter
+    dim-0 shards of the CURRENT world size; reference behaviour: resharding-on-load), model + optimizer + step."""
+    ck = tempfile.mkdtemp()
+    out = _run(save_world, "fsdp", ckpt_dir=ck)
+    outdir = tempfile.mkdtemp()
+    mp.spawn(_reload_worker, args=(load_world, free_port(), ck, outdir), nprocs=load_world, join=True)
+    r = torch.load(os.path.join(outdir, "reload.pt"), weights_only=False)
+    assert (r["step"], r["ntok"], r["resuming"], r["opt_step"]) == (STEPS, 123, True, STEPS + 1)
+    for k, v in out["sd"].items():
+        assert torch.equal(r["sd"][k], v), k
+    assert r["loss"] == r["loss"] and r["gn"] > 0
