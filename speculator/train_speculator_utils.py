@@ -70,7 +70,8 @@ class EmbedLLaMA(LLaMA):
 class _GPTBigCodeBlock(nn.Module):
     def __init__(self, d, nheads, hidden, eps):
         super().__init__()
-        self.nheads, self.hd = nheads, d // nheads
+        self.nheads, self.hd = nheads, d // nheads   # nheads becomes the LOCAL head count under tensor parallelism
+        self.tp_group = None
         self.ln = nn.LayerNorm(d, eps=eps)
         self.ff_ln = nn.LayerNorm(d, eps=eps)
         self.qkv = nn.Linear(d, d + 2 * self.hd)  # multi-query attention: one shared k/v head
@@ -78,14 +79,16 @@ class _GPTBigCodeBlock(nn.Module):
         self.w1, self.w2 = nn.Linear(d, hidden), nn.Linear(hidden, d)
 
     def forward(self, h, past=None, use_cache=False):
-        B, S, D = h.shape
-        q, k, v = self.qkv(self.ln(h)).split([D, self.hd, self.hd], dim=-1)
+        B, S, _ = h.shape
+        Dq = self.nheads * self.hd
+        q, k, v = self.qkv(self.ln(h)).split([Dq, self.hd, self.hd], dim=-1)
         if past is not None:
             k, v = torch.cat([past[0], k], 1), torch.cat([past[1], v], 1)
         ctx = F.scaled_dot_product_attention(q.view(B, S, self.nheads, self.hd).transpose(1, 2), k.unsqueeze(1),
                                              v.unsqueeze(1), is_causal=(past is None), enable_gqa=True)
-        h = h + self.dense(ctx.transpose(1, 2).reshape(B, S, D))
-        h = h + self.w2(F.gelu(self.w1(self.ff_ln(h)), approximate="tanh"))
+        red = (lambda t: t) if self.tp_group is None else (lambda t: tp_all_reduce(t, self.tp_group))
+        h = h + red(self.dense(ctx.transpose(1, 2).reshape(B, S, Dq)))
+        h = h + red(self.w2(F.gelu(self.w1(self.ff_ln(h)), approximate="tanh")))
         return h, ((k, v) if use_cache else None)
 
 
@@ -100,6 +103,17 @@ class EmbedGPTBigCode(nn.Module):
         self.dec_norm = nn.LayerNorm(emb_dim, eps=eps)
         self.head = nn.Linear(emb_dim, vocab, bias=False)
 
+    def reset_parameters(self):
+        """GPT-2 style init (needed after ``to_empty`` when no checkpoint is given: the storage is uninitialised)."""
+        for m in self.modules():
+            if isinstance(m, (nn.Linear, nn.Embedding)):
+                nn.init.normal_(m.weight, std=0.02)
+                if getattr(m, "bias", None) is not None:
+                    nn.init.zeros_(m.bias)
+            elif isinstance(m, nn.LayerNorm):
+                nn.init.ones_(m.weight)
+                nn.init.zeros_(m.bias)
+
     def forward(self, x, past_key_value_states=None, use_cache=False, include_embeds=False, **_):
         past = past_key_value_states
         p0 = 0 if past is None else past[0][0].size(1)
@@ -109,7 +123,10 @@ class EmbedGPTBigCode(nn.Module):
             h, c = blk(h, None if past is None else past[i], use_cache)
             cache.append(c)
         embeds = self.dec_norm(h)
-        out = [self.head(embeds)] + ([cache] if use_cache else []) + ([embeds] if include_embeds else [])
+        logits = self.head(embeds)
+        if getattr(self, "_tp_group", None) is not None:
+            logits = tp_all_gather_last(logits, self._tp_group)
+        out = [logits] + ([cache] if use_cache else []) + ([embeds] if include_embeds else [])
         return out[0] if len(out) == 1 else tuple(out)
 
 
@@ -120,7 +137,11 @@ class _MoE(nn.Module):
         self.gate = nn.Linear(d, n_experts, bias=False)
         self.w1 = nn.Parameter(torch.empty(n_experts, 2 * hidden, d))
         self.w2 = nn.Parameter(torch.empty(n_experts, d, hidden))
-        nn.init.trunc_normal_(self.w1, std=0.02); nn.init.trunc_normal_(self.w2, std=0.02)
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        for w in (self.gate.weight, self.w1, self.w2):
+            nn.init.trunc_normal_(w, std=0.02)
 
     def forward(self, x):
         B, S, D = x.shape
@@ -146,7 +167,16 @@ class EmbedMixtral(EmbedLLaMA):
             blk.moe = _MoE(self.config.emb_dim, self.config.hidden_dim, n_experts, top_k)
             del blk.ff_sub_layer
 
+    def reset_parameters(self):
+        self.shared.reset_parameters()
+        self.dec_norm.reset_parameters()
+        for blk in self.layers:
+            for m in (blk.ln, blk.ff_ln, blk.attn, blk.moe):
+                m.reset_parameters()
+
     def forward(self, x, past_key_value_states=None, use_cache=False, include_embeds=False, **_):
+        tp = getattr(self, "_tp_group", None)
+        red = (lambda t: t) if tp is None else (lambda t: tp_all_reduce(t, tp))
         B, S = x.shape
         h = self.shared(x)
         past = past_key_value_states
@@ -164,10 +194,14 @@ class EmbedMixtral(EmbedLLaMA):
             cache.append((k, v))
             ctx = F.scaled_dot_product_attention(q.transpose(1, 2), k.transpose(1, 2), v.transpose(1, 2),
                                                  is_causal=(past is None), enable_gqa=(a.kvheads != a.nheads))
-            h = a.dense(ctx.transpose(1, 2).reshape(B, S, -1), residual=h)
-            h = h + blk.moe(blk.ff_ln(h))
+            ctx = ctx.transpose(1, 2).reshape(B, S, -1)
+            h = a.dense(ctx, residual=h) if tp is None else h + red(a.dense(ctx))
+            h = h + red(blk.moe(blk.ff_ln(h)))
         embeds = self.dec_norm(h)
-        out = [self.shared(embeds, reverse=True)] + ([cache] if use_cache else []) + ([embeds] if include_embeds else [])
+        logits = self.shared(embeds, reverse=True)
+        if tp is not None:
+            logits = tp_all_gather_last(logits, tp)
+        out = [logits] + ([cache] if use_cache else []) + ([embeds] if include_embeds else [])
         return out[0] if len(out) == 1 else tuple(out)
 
 
@@ -195,7 +229,7 @@ def get_model(arch: str, variant: str, model_path: Optional[str] = None, device_
     """Stand-in for ``fms.models.get_model``: build a registered base model and, when ``model_path`` holds an HF
     checkpoint (``source='hf'``), load its weights -- Llama, GPT-BigCode and Mixtral (reference adapters
     ``train_speculator_utils.py:526-569``); without a checkpoint the registered variant is built with random weights and
-    that is said out loud.  ``distributed_strategy='tp'`` shards a Llama base over ``group``."""
+    that is said out loud.  ``distributed_strategy='tp'`` shards the base model (any of the three families) over ``group``."""
     dev = torch.device(device_type, torch.cuda.current_device()) if device_type == "cuda" else torch.device("cpu")
     has_ckpt = bool(model_path) and os.path.exists(os.path.join(model_path, "config.json"))
     if has_ckpt and arch in ("embedllama", "embedgpt_bigcode", "embedmixtral"):
@@ -218,8 +252,8 @@ def get_model(arch: str, variant: str, model_path: Optional[str] = None, device_
             model.reset_parameters()
         model = model.to(dtype)
     if distributed_strategy == "tp" and group is not None and dist.get_world_size(group) > 1:
-        from fms_fsdp_b200.parallel.tensor_parallel import shard_llama_for_tp
-        model = shard_llama_for_tp(model, group)
+        from fms_fsdp_b200.parallel.tensor_parallel import shard_for_tp
+        model = shard_for_tp(model, group)
     model = model.to(dev)
     for p in model.parameters():
         p.requires_grad_(False)

@@ -88,10 +88,25 @@ def test_other_registered_archs_forward():
     b, _ = generate(g, x, max_new_tokens=3, do_sample=False, use_cache=False)
     assert torch.equal(a, b)
     mx = EmbedMixtral(LLaMAConfig(src_vocab_size=50, emb_dim=32, nheads=4, kvheads=2, nlayers=2, multiple_of=8), n_experts=4)
-    mx.shared.reset_parameters(); [b_.ln.reset_parameters() or b_.ff_ln.reset_parameters() or b_.attn.reset_parameters() for b_ in mx.layers]
-    mx.dec_norm.reset_parameters()
+    mx.reset_parameters()
     lg, emb = mx(x, include_embeds=True)
     assert lg.shape == (2, 9, 50) and torch.isfinite(lg).all()
+
+
+def test_get_model_without_checkpoint_initialises_every_family():
+    """No HF checkpoint -> the registered variant is materialised from the meta device and must be INITIALISED (not the
+    uninitialised storage ``to_empty`` leaves behind) for all three families."""
+    from speculator.train_speculator_utils import get_model, register_model
+    register_model("embedgpt_bigcode", "test", lambda: EmbedGPTBigCode(vocab=50, emb_dim=32, nheads=4, nlayers=2, max_pos=64))
+    register_model("embedmixtral", "test", lambda: EmbedMixtral(
+        LLaMAConfig(src_vocab_size=50, emb_dim=32, nheads=4, kvheads=2, nlayers=2, multiple_of=8), n_experts=4))
+    x = torch.randint(0, 50, (2, 9))
+    for arch, variant in (("embedgpt_bigcode", "test"), ("embedmixtral", "test"), ("embedllama", "tiny")):
+        m = get_model(arch, variant, model_path=None, device_type="cpu", dtype=torch.float32)
+        assert all(torch.isfinite(p).all() and p.abs().max() < 10 for p in m.parameters()), arch
+        assert not any(p.requires_grad for p in m.parameters())
+        lg = m(x)
+        assert torch.isfinite(lg).all() and lg.std() > 0, arch
 
 
 def test_hf_loader_roundtrip():
