@@ -62,3 +62,32 @@ def test_mamba_export(monkeypatch):
     sd = torch.load(os.path.join(out, "pytorch_model.bin"))
     assert set(sd) == set(ref_sd) and all(torch.equal(sd[k], ref_sd[k]) for k in sd)
     assert os.path.exists(os.path.join(out, "config.json"))
+
+
+def test_hf_import_single_file_feeds_the_trainer(tmp_path):
+    """HF Llama directory -> ``hf_to_fms_llama.py`` -> single-file checkpoint -> ``Checkpointer.load`` into the sharded runtime:
+    the engine's logits equal the HF model's, and the load is reported as a fresh start (not a resume)."""
+    import hf_to_fms_llama as imp
+    from transformers import LlamaConfig, LlamaForCausalLM
+    torch.manual_seed(3)
+    hf = LlamaForCausalLM(LlamaConfig(vocab_size=80, hidden_size=64, intermediate_size=96, num_hidden_layers=2,
+                                      num_attention_heads=4, num_key_value_heads=2, max_position_embeddings=64,
+                                      rope_theta=50000.0, tie_word_embeddings=False)).eval()
+    hf_dir, pth = str(tmp_path / "hf"), str(tmp_path / "w" / "llama.pth")
+    hf.save_pretrained(hf_dir)
+    imp.main(hf_dir, pth, dtype="fp32")
+
+    from fms_fsdp_b200.models.hf_loader import config_from_hf
+    cfg = config_from_hf(hf.config.to_dict())
+    m = LLaMA(cfg); m.reset_parameters()
+    eng = ShardedModel(m, device="cpu"); opt = ShardedAdamW(eng)
+    _, _, _, step, tokens, resuming = Checkpointer(str(tmp_path / "save"), 2, "fsdp", 0, 0).load(eng, opt, None, path=pth)
+    assert (step, tokens, resuming) == (0, 0, False)
+    x = torch.randint(0, 80, (2, 21))
+    with torch.no_grad():
+        theirs = hf(x).logits
+        ours = eng.module(x)
+    assert torch.allclose(ours.float(), theirs, atol=2e-4, rtol=1e-3), (ours - theirs).abs().max()
+
+    with pytest.raises(ValueError, match="does not have the architecture"):
+        imp.main(hf_dir, pth, model_variant="llama2_7b")
