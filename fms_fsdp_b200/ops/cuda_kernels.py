@@ -6,9 +6,7 @@ were launched (bench.py's ``gpu_launches``).
 """
 from __future__ import annotations
 
-import math
 import os
-from typing import Optional
 
 import torch
 

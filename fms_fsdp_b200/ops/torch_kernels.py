@@ -8,7 +8,7 @@ Signatures are identical to ``cuda_kernels``.
 from __future__ import annotations
 
 import math
-from typing import Optional, Tuple
+from typing import Optional
 
 import torch
 import torch.nn.functional as F

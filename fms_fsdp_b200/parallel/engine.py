@@ -26,13 +26,12 @@ import hashlib
 import os
 
 import contextlib
-from typing import Dict, Iterable, List, Optional, Sequence, Tuple
+from typing import Dict, List, Optional, Sequence, Tuple
 
 import torch
 import torch.distributed as dist
 import torch.nn as nn
 
-from fms_fsdp_b200.ops.functional import kernels_for
 from fms_fsdp_b200.parallel.comm import make_collectives
 from fms_fsdp_b200.parallel.layout import UnitLayout, build_layout
 from fms_fsdp_b200.parallel.mesh import DPMesh, build_mesh

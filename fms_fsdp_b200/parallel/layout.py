@@ -10,8 +10,8 @@ contiguous transfers per peer.
 """
 from __future__ import annotations
 
-from dataclasses import dataclass, field
-from typing import Dict, Iterable, List, Sequence, Tuple
+from dataclasses import dataclass
+from typing import List, Sequence, Tuple
 
 ALIGN_ELEMS = 64  # 128 B at bf16, 256 B at fp32
 MATRIX_ALIGN_ELEMS = 32768  # the first matrix starts on a 64 KiB (bf16) boundary = one fused-gather ready-flag chunk

@@ -23,7 +23,7 @@ from functools import partial
 import torch
 import torch.distributed as dist
 
-from fms_fsdp_b200.policies import (MixedPrecision, apply_fsdp_checkpointing, bfSixteen, fpSixteen, get_wrapper,
+from fms_fsdp_b200.policies import (apply_fsdp_checkpointing, bfSixteen, fpSixteen, get_wrapper,
                                     param_init_function)
 
 

@@ -8,7 +8,6 @@ process group, policies, model (optionally on the meta device), data loader, sha
 precompute, selective recomputation, AdamW(0.9, 0.95, wd 0.1), checkpoint auto-resume, LR schedule,
 profiler, train -- on the B200-native engine instead of torch FSDP + torch.compile.
 """
-import math
 import os
 
 import torch

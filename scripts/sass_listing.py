@@ -5,7 +5,6 @@ import collections
 import os
 import re
 import subprocess
-import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SO = os.path.join(ROOT, "fms_fsdp_b200", "_C.so")

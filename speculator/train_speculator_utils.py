@@ -6,7 +6,7 @@ from __future__ import annotations
 
 import os
 import time
-from typing import Any, Callable, MutableMapping, Optional, Union
+from typing import Callable, Optional, Union
 
 import torch
 import torch.distributed as dist
