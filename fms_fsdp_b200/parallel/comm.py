@@ -99,28 +99,55 @@ class TorchCollectives:
             dist.barrier()
 
 
-def make_collectives(impl: str, mesh: DPMesh, device: torch.device):
+def plan_collectives(impl: str, device_type: str, world: int, shard_size: int, local_world: int, rank: int = 0):
+    """-> (implementation of the shard-group collectives, implementation of the replica-group all-reduce).
+
+    The peer-memory kernels need all ranks of a GROUP on one NVSwitch domain (one node).  Ranks are numbered node by node and
+    a shard group is ``shard_size`` consecutive ranks, so it sits inside a node iff ``shard_size`` divides ``local_world``:
+
+    * single node                      -> ("fused", "fused")
+    * multi-node HSDP, shards in-node  -> ("fused", "nccl"): all-gather inside the GEMMs, wgrad push and the flag protocol stay
+      on NVLink; only the replica all-reduce of the fp32 gradient shard (1/shard_size of the model per rank) crosses nodes
+      -- the reference's production layout (``docs/train_details.md``: shard within a node, replicate across nodes)
+    * multi-node FSDP (shards span nodes) or DDP -> ("torch", "nccl")
+    """
     impl = (impl or "auto").lower()
-    if impl == "auto":
-        # the peer-memory collectives need every rank of the job on one NVSwitch domain; a multi-node job (the
-        # reference's 96-128 GPU runs) takes the c10d/NCCL implementation of the same interface
-        local_world = int(os.environ.get("LOCAL_WORLD_SIZE", mesh.world))
-        single_node = local_world >= mesh.world
-        impl = "fused" if (device.type == "cuda" and mesh.world > 1 and single_node) else "torch"
-        if device.type == "cuda" and mesh.world > 1 and not single_node and mesh.rank == 0:
-            print(f"[fms_fsdp_b200] {mesh.world} ranks over {mesh.world // max(local_world, 1)} nodes: "
-                  "collective_impl=torch (NCCL); the NVLink peer-memory collectives are single-node")
-    if impl == "fused":
-        if device.type != "cuda":
+    if device_type != "cuda" or world == 1:
+        if impl == "fused" and device_type != "cuda":
             raise ValueError("collective_impl=fused needs CUDA devices")
-        if mesh.world == 1:
-            return TorchCollectives(mesh, device)
-        if max(mesh.shard_size, mesh.replica_size) > 32:
-            # the signal pads hold 32 ranks per channel (csrc/comm.cu); the reduce kernels themselves take any group size
-            if mesh.rank == 0:
-                print(f"[fms_fsdp_b200] group of {max(mesh.shard_size, mesh.replica_size)} ranks exceeds the 32-rank "
-                      "signal pad: collective_impl=torch (NCCL)")
-            return TorchCollectives(mesh, device)
+        return "torch", "nccl"
+    local_world = max(1, min(local_world, world))
+    multi_node = local_world < world
+    shards_in_node = shard_size > 1 and local_world % shard_size == 0
+    replica_size = world // shard_size
+    if impl == "torch":
+        return "torch", "nccl"
+    if multi_node:
+        if shards_in_node:
+            return "fused", "nccl"
+        if impl == "fused":
+            what = "multi-node ddp has no in-node shard group" if shard_size == 1 else \
+                f"shard groups of {shard_size} ranks do not fit inside a node of {local_world} GPUs"
+            raise ValueError(f"collective_impl=fused: {what}; use hsdp with hsdp_shard_size dividing {local_world}, "
+                             "or collective_impl=torch")
+        if rank == 0:
+            print(f"[fms_fsdp_b200] {world} ranks over {world // local_world} nodes with shard groups of {shard_size}: "
+                  "collective_impl=torch (NCCL); the NVLink peer-memory collectives need each shard group inside one node "
+                  "(sharding_strategy=hsdp)")
+        return "torch", "nccl"
+    if max(shard_size, replica_size) > 32:
+        # the signal pads hold 32 ranks per channel (csrc/comm.cu); the reduce kernels themselves take any group size
+        if rank == 0:
+            print(f"[fms_fsdp_b200] group of {max(shard_size, replica_size)} ranks exceeds the 32-rank signal pad: "
+                  "collective_impl=torch (NCCL)")
+        return "torch", "nccl"
+    return "fused", "fused"
+
+
+def make_collectives(impl: str, mesh: DPMesh, device: torch.device):
+    local_world = int(os.environ.get("LOCAL_WORLD_SIZE", mesh.world))
+    shard_impl, replica_impl = plan_collectives(impl, device.type, mesh.world, mesh.shard_size, local_world, mesh.rank)
+    if shard_impl == "fused":
         from fms_fsdp_b200.parallel.fused_comm import FusedCollectives
-        return FusedCollectives(mesh, device)
+        return FusedCollectives(mesh, device, replica_impl=replica_impl)
     return TorchCollectives(mesh, device)

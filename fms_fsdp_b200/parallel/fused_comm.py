@@ -111,12 +111,15 @@ class _SymGroup:
 class FusedCollectives:
     name = "fused"
 
-    def __init__(self, mesh: DPMesh, device: torch.device):
+    def __init__(self, mesh: DPMesh, device: torch.device, replica_impl: str = "fused"):
         self.mesh, self.device = mesh, device
         self.C = _ext.require()
         self.shard = _SymGroup(mesh.shard_group, mesh.shard_size, mesh.shard_rank, device) if mesh.shard_size > 1 else None
+        # replica_impl="nccl": the replica group crosses nodes (multi-node HSDP, ``comm.plan_collectives``) -- its all-reduce of
+        # the fp32 gradient shard goes through c10d/NCCL on the reduce stream, everything inside the node stays on NVLink
         self.replica = _SymGroup(mesh.replica_group, mesh.replica_size, mesh.replica_rank, device) \
-            if mesh.replica_size > 1 else None
+            if (mesh.replica_size > 1 and replica_impl == "fused") else None
+        self._replica_nccl = mesh.replica_group if (mesh.replica_size > 1 and replica_impl != "fused") else None
         self._anchor = torch.zeros(1, device=device)
         self._slice_tables: Dict[Tuple[int, int], torch.Tensor] = {}
         self._ag_state: Dict[int, list] = {}
@@ -212,7 +215,7 @@ class FusedCollectives:
         g.barrier(self.C, self._anchor, _SymGroup.CH_REDUCE)  # every rank's wgrads for this unit are complete
         if on_barrier is not None:
             on_barrier()
-        hsdp = self.replica is not None
+        hsdp = self.replica is not None or self._replica_nccl is not None
         self.C.reduce_scatter(g.table_of(full), shard32, g.index * shard32.numel(), g.size, g.index,
                               full.dtype == torch.bfloat16, float(scale), None if hsdp else sumsq)
         if not hsdp:
@@ -221,7 +224,7 @@ class FusedCollectives:
             self.last_reduce_done.record(torch.cuda.current_stream(self.device))
         g.barrier(self.C, self._anchor, _SymGroup.CH_REDUCE)  # peers are done reading my buffer before it is rewritten
         if hsdp:
-            self._allreduce(self.replica, shard32, 1.0, sumsq)
+            self._replica_allreduce(shard32, sumsq)
             self.last_reduce_done = None
 
     # ---- fused wgrad GEMM -> reduce-scatter (push) ----------------------------------------------------------------
@@ -251,15 +254,27 @@ class FusedCollectives:
             tab = torch.tensor([staging.data_ptr() + s_ * n * staging.element_size() for s_ in range(g.size)],
                                dtype=torch.int64, device=self.device)
             self._slice_tables[key] = tab
-        hsdp = self.replica is not None
+        hsdp = self.replica is not None or self._replica_nccl is not None
         self.C.reduce_scatter(tab, shard32, 0, g.size, 0, staging.dtype == torch.bfloat16, float(scale),
                               None if hsdp else sumsq, self._slotsum_ctas)
         self.last_reduce_done = None
         if hsdp:
+            self._replica_allreduce(shard32, sumsq)
+
+    def _replica_allreduce(self, shard32: torch.Tensor, sumsq: Optional[torch.Tensor]):
+        """HSDP: sum the (already scaled) fp32 gradient shard over the replicas, then its squared norm."""
+        if self.replica is not None:
             self._allreduce(self.replica, shard32, 1.0, sumsq)
+            return
+        # c10d orders the NCCL kernel after the work already enqueued on the current (reduce) stream and makes that stream
+        # wait for it, so the sumsq kernel and the optimizer see the reduced shard
+        dist.all_reduce(shard32, op=dist.ReduceOp.SUM, group=self._replica_nccl)
+        if sumsq is not None:
+            kernels_for(shard32).sumsq(shard32, out=sumsq)
 
     def all_reduce_full(self, full: torch.Tensor, scale: float, sumsq: Optional[torch.Tensor]):
         if self.replica is None:
+            assert self._replica_nccl is None, "multi-node DDP takes TorchCollectives (comm.plan_collectives)"
             if sumsq is not None:
                 kernels_for(full).sumsq(full, out=sumsq)
             return

@@ -288,3 +288,31 @@ def test_checkpoint_reshards_across_world_sizes(save_world, load_world):
     for k, v in out["sd"].items():
         assert torch.equal(r["sd"][k], v), k
     assert r["loss"] == r["loss"] and r["gn"] > 0
+
+
+def test_collective_plan_single_and_multi_node():
+    """Which collectives run where (``parallel/comm.plan_collectives``): NVLink peer kernels need a group inside one node."""
+    import pytest as _pt
+    from fms_fsdp_b200.parallel.comm import plan_collectives as plan
+    # one node: everything fused, any strategy
+    assert plan("auto", "cuda", 8, 8, 8) == ("fused", "fused")            # fsdp
+    assert plan("auto", "cuda", 8, 4, 8) == ("fused", "fused")            # hsdp 2x4 on one box
+    assert plan("auto", "cuda", 8, 1, 8) == ("fused", "fused")            # ddp
+    assert plan("fused", "cuda", 2, 2, 2) == ("fused", "fused")
+    assert plan("torch", "cuda", 8, 8, 8)[0] == "torch"
+    assert plan("auto", "cuda", 1, 1, 1)[0] == "torch" and plan("fused", "cuda", 1, 1, 8)[0] == "torch"
+    assert plan("auto", "cpu", 4, 4, 4)[0] == "torch"
+    with _pt.raises(ValueError):
+        plan("fused", "cpu", 2, 2, 2)
+    # the reference's production layout: 16 nodes x 8 GPUs, shard inside the node, replicate across nodes
+    assert plan("auto", "cuda", 128, 8, 8) == ("fused", "nccl")
+    assert plan("auto", "cuda", 16, 4, 8) == ("fused", "nccl")            # two shard groups per node
+    assert plan("fused", "cuda", 16, 8, 8) == ("fused", "nccl")
+    # shards spanning nodes (multi-node FSDP), multi-node DDP, shard size not dividing the node
+    assert plan("auto", "cuda", 16, 16, 8)[0] == "torch"
+    assert plan("auto", "cuda", 16, 1, 8)[0] == "torch"
+    assert plan("auto", "cuda", 24, 3, 8)[0] == "torch"
+    with _pt.raises(ValueError, match="do not fit inside a node"):
+        plan("fused", "cuda", 16, 16, 8)
+    # more ranks in a single-node group than a signal pad holds
+    assert plan("auto", "cuda", 64, 64, 64)[0] == "torch"
