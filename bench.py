@@ -231,6 +231,7 @@ def run_ours(a):
     sync_all()
     launches = CK.launch_count()
     fallbacks = CK.fallback_count()
+    peak_alloc = torch.cuda.max_memory_allocated(dev)   # train() below resets the peak counters at its report step
     loss_timed = float(loss_sum) / a.steps      # mean loss of steps W+1 .. W+K (what the reference arm prints too)
     ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
     if world > 1:
@@ -286,7 +287,10 @@ def run_ours(a):
             "gpu_launches": int(launches),
             "aten_fallbacks": int(fallbacks),
             "clocks": clocks,
-            "mem_gb": round(torch.cuda.max_memory_allocated(dev) / 2**30, 2),
+            # peak of torch's caching allocator, and what the DEVICE reports as in use at the end (adds the symmetric-memory
+            # buffers of the peer collectives, the allocator's cache and the CUDA context)
+            "mem_gb": round(max(peak_alloc, torch.cuda.max_memory_allocated(dev)) / 2**30, 2),
+            "mem_device_gb": round((lambda fr_to: (fr_to[1] - fr_to[0]) / 2**30)(torch.cuda.mem_get_info(dev)), 2),
         }
         if a.nlayers:
             out["invalid"] = "debug depth override"

@@ -61,3 +61,41 @@ def test_grad_dtype_and_precision_switches():
     import pytest
     with pytest.raises(NotImplementedError):
         get_policies(cfg, 1, LLaMABlock)
+
+
+def test_every_llama_zoo_variant_meets_the_native_kernel_shape_rules():
+    """The sm_100a kernels have shape preconditions (else a counted ATen fallback, ``ops/cuda_kernels.py``): attention head
+    dim 64 / 128, RMSNorm width <= 8192 and % 8, SwiGLU-epilogue hidden dim % 128, LM-head vocab % 8, and every weight matrix
+    must be eligible for the wgrad push epilogue.  All reference variants must take the native path."""
+    from fms_fsdp_b200.ops.cuda_kernels import push_eligible_shape
+    names = [n for n in list_model_variants() if n.startswith("llama") and n != "llama2_tiny"]
+    assert len(names) >= 14
+    for n in names:
+        c = get_model_config(n)
+        hd = c.head_dim
+        assert hd in (64, 128), n
+        assert c.emb_dim % 8 == 0 and c.emb_dim <= 8192, n
+        assert c.hidden_dim % 128 == 0, n
+        assert c.src_vocab_size % 8 == 0, n
+        assert c.nheads % c.kv_heads == 0, n
+        for shape in ((c.nheads * hd + 2 * c.kv_heads * hd, c.emb_dim), (c.emb_dim, c.nheads * hd),
+                      (2 * c.hidden_dim, c.emb_dim), (c.emb_dim, c.hidden_dim), (c.src_vocab_size, c.emb_dim)):
+            assert push_eligible_shape(shape), (n, shape)
+
+
+def test_memory_plan_matches_the_measured_1gpu_peak_and_scales_with_sharding():
+    """``utils/memory_plan.py`` against the one number that is directly comparable: the caching allocator's peak of the
+    Llama2-7B 1-GPU bench (133.53 GiB, profiles/bench1_on8box_r2.log)."""
+    from fms_fsdp_b200.utils.memory_plan import plan_llama
+    p1 = plan_llama("llama2_7b", gpus=1)
+    assert abs(p1.total_gib - 133.53) / 133.53 < 0.02, p1.table()
+    p8 = plan_llama("llama2_7b", gpus=8)
+    assert p8.shard_size == 8 and p8.fits() and p8.total_gib < 0.45 * p1.total_gib
+    h = plan_llama("llama2_7b", gpus=8, sharding_strategy="hsdp", hsdp_shard_size=4)
+    assert h.shard_size == 4 and h.total_gib > p8.total_gib
+    # recomputation trades activations for nothing else; the block counts follow the ac_handler selection rule
+    full = plan_llama("llama2_13b", gpus=8)
+    half = plan_llama("llama2_13b", gpus=8, fsdp_activation_checkpointing=True, selective_checkpointing="1/2")
+    assert any("20 blocks kept, 20 recomputed" in k for k in half.parts_gib) and half.total_gib < full.total_gib
+    assert not plan_llama("llama2_70b", gpus=8, fsdp_activation_checkpointing=True).fits()
+    assert plan_llama("llama2_70b", gpus=64, sharding_strategy="hsdp", hsdp_shard_size=8).shard_size == 8
