@@ -21,6 +21,17 @@ for k in gemm attn elem; do
   python scripts/ncu_summary.py $O/prof_$k.ncu-rep > $O/ncu_$k.txt
 done
 python scripts/sass_summary.py > $O/sass_summary.txt
+python scripts/sass_listing.py > /dev/null 2>&1                    # per-kernel listings -> profiles/sass/
+# collective kernels under ncu on one GPU (pointer tables over local buffers)
+ncu --set full --clock-control none -k regex:'reduce_scatter|p2p_allgather|signal_barrier|scalar_allreduce' \
+    -o $O/prof_comm python scripts/ncu_comm.py > $O/ncu_comm.log 2>&1 && python scripts/ncu_summary.py $O/prof_comm.ncu-rep > $O/ncu_comm.txt
+# attention vs cuDNN (SDPA), instruction issue rates of the softmax building blocks, fp8 forward GEMM vs bf16
+python scripts/attn_bench.py > $O/attn_bench.log 2>&1               # writes $O/attn_bench.json
+nvcc -gencode arch=compute_100a,code=sm_100a -std=c++17 -O3 scripts/pipe_bench.cu -o /tmp/pipe_bench && /tmp/pipe_bench > $O/pipe_issue_rates.txt
+python scripts/fp8_bench.py > $O/fp8_bench.log 2>&1                 # writes $O/fp8_bench.json
+python bench.py --steps 6 --warmup 3 --precision fp8 > $O/bench_fp8_nonheadline.log 2>&1
+# the public entry points on the GPU: llama train + resume + HF export, mamba, speculator (TP=2 needs 2 GPUs)
+bash scripts/gpu_entrypoints.sh > $O/entrypoints.log 2>&1
 scripts/sanitize.sh memcheck elem gemm attn
 # pipeline timeline of the attention backward, tcgen05 issue microbenchmarks
 nvcc -gencode arch=compute_100a,code=sm_100a -std=c++17 -O3 --use_fast_math -DB200_ATTN_TRACE -Ifms_fsdp_b200/csrc \
@@ -32,5 +43,6 @@ if [ "$N" -gt 1 ]; then
   $R --nproc-per-node $N --master-port 29512 bench.py --gpus $N --steps 6 --warmup 3 --profile $O/step_kernels_$N.txt \
       > $O/bench_ours_$N.log 2>&1
   $R --nproc-per-node $N --master-port 29513 bench.py --impl reference --gpus $N --steps 6 --warmup 3 > $O/bench_reference_$N.log 2>&1
+  [ "$N" -eq 8 ] && bash scripts/configs8.sh > $O/configs8.log 2>&1   # 13B selective AC, HSDP 2x4, both arms
 fi
 grep -h '"metric"' $O/bench_*.log | cut -c1-260
