@@ -206,9 +206,12 @@ class EmbedMixtral(EmbedLLaMA):
 
 
 _REGISTRY = {
-    # 2-layer toy for CPU drills and tests (not a reference variant)
+    # 2-layer toys for CPU drills and tests (not reference variants)
     ("embedllama", "tiny"): lambda: EmbedLLaMA(LLaMAConfig(src_vocab_size=512, emb_dim=64, nheads=4, kvheads=2, nlayers=2,
                                                            multiple_of=16, max_expected_seq_len=256)),
+    ("embedgpt_bigcode", "tiny"): lambda: EmbedGPTBigCode(vocab=512, emb_dim=64, nheads=4, nlayers=2, max_pos=256, hidden_mult=2),
+    ("embedmixtral", "tiny"): lambda: EmbedMixtral(LLaMAConfig(src_vocab_size=512, emb_dim=64, nheads=4, kvheads=2, nlayers=2,
+                                                               multiple_of=16, max_expected_seq_len=256), n_experts=4),
     ("embedllama", "7b"): lambda: EmbedLLaMA(LLaMAConfig(hidden_grow_factor=11008 / 4096, kvheads=32)),
     ("embedllama", "8b"): lambda: EmbedLLaMA(LLaMAConfig(src_vocab_size=128256, emb_dim=4096, nheads=32, kvheads=8,
                                                          nlayers=32, hidden_grow_factor=3.5, max_expected_seq_len=8192,

@@ -3,6 +3,7 @@ slicing a loaded LLaMA over 2 ranks (gloo) must reproduce the unsharded logits, 
 import os
 import tempfile
 
+import pytest
 import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
@@ -111,15 +112,16 @@ def test_tp2_gpt_bigcode_and_mixtral_bases_match_unsharded():
         assert r["shrink"] < 0.75, (name, r)   # the bulk of the weights really is split
 
 
-def test_speculator_entrypoint_tp2_two_stages(tmp_path):
-    """`speculator/train_speculator.py` end to end on 2 gloo ranks: (dp, tp) = (1, 2) mesh, TP-sharded frozen base model,
-    DDP speculator on the engine, stage 1 -> stage 2 (generated continuations), final checkpoint."""
+@pytest.mark.parametrize("arch", ["embedllama", "embedgpt_bigcode", "embedmixtral"])
+def test_speculator_entrypoint_tp2_two_stages(tmp_path, arch):
+    """`speculator/train_speculator.py` end to end on 2 gloo ranks: (dp, tp) = (1, 2) mesh, TP-sharded frozen base model (each
+    of the three families), DDP speculator on the engine, stage 1 -> stage 2 (generated continuations), final checkpoint."""
     import subprocess
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
            "--master-port", str(free_port()), os.path.join(root, "speculator", "train_speculator.py"),
-           "--model_arch=embedllama", "--model_variant=tiny", "--model_path=/nonexistent", "--sharding_strategy=tp",
+           f"--model_arch={arch}", "--model_variant=tiny", "--model_path=/nonexistent", "--sharding_strategy=tp",
            "--tp_size=2", "--use_dummy_dataset=True", "--num_steps=4", "--report_interval=2", "--stage2_start_step=3",
            "--stage2_batch_size=4", "--stage2_prompt_length=4", "--stage2_seq_length=8", "--n_speculator_heads=2",
            "--speculator_width=32", "--seq_length=16", "--vocab_size=512", "--batch_size=2",
