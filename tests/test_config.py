@@ -99,3 +99,77 @@ def test_memory_plan_matches_the_measured_1gpu_peak_and_scales_with_sharding():
     assert any("20 blocks kept, 20 recomputed" in k for k in half.parts_gib) and half.total_gib < full.total_gib
     assert not plan_llama("llama2_70b", gpus=8, fsdp_activation_checkpointing=True).fits()
     assert plan_llama("llama2_70b", gpus=64, sharding_strategy="hsdp", hsdp_shard_size=8).shard_size == 8
+
+
+def test_model_zoo_equals_the_reference_installs_zoo():
+    """Every variant the unmodified reference's ``get_model_config`` knows (offline install baseline/_ref; skipped when it
+    is absent) has identical architecture numbers here."""
+    import json
+    import os
+    import re
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    ref = os.path.join(root, "baseline", "_ref")
+    src = os.path.join(ref, "fms_fsdp", "utils", "config_utils.py")
+    if not os.path.exists(src):
+        pytest.skip("reference install (baseline/_ref) not present")
+    variants = sorted(set(re.findall(r'model_variant == "([a-z0-9_.]+)"', open(src).read())))
+    assert len(variants) >= 15
+    code = (
+        "import sys, json, dataclasses\n"
+        f"sys.path = [{ref!r}, {os.path.join(root, 'baseline', 'fms_shim')!r}] + [p for p in sys.path if p not in ('', {root!r})]\n"
+        "from fms_fsdp.utils.config_utils import get_model_config\n"
+        "out = {}\n"
+        f"for v in {variants!r}:\n"
+        "    c = get_model_config(v)\n"
+        "    out[v] = c if isinstance(c, dict) else dataclasses.asdict(c)\n"
+        "print('ZOO' + json.dumps(out))\n")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd="/", timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    theirs = json.loads(r.stdout.split("ZOO", 1)[1])
+    for v in variants:
+        mine = get_model_config(v)
+        if isinstance(mine, dict):      # mamba: a plain dict in both
+            assert mine == theirs[v], v
+            continue
+        for k in ("src_vocab_size", "emb_dim", "nheads", "kvheads", "nlayers", "hidden_grow_factor", "multiple_of",
+                  "max_expected_seq_len", "rope_theta", "norm_eps"):
+            assert getattr(mine, k) == theirs[v][k], (v, k, getattr(mine, k), theirs[v][k])
+
+
+def test_train_config_defaults_and_dummy_stream_equal_the_reference_install():
+    """(1) every ``train_config`` field of the unmodified reference exists here with the same default; (2) the synthetic
+    ``get_dummy_loader`` stream is the same token for token (it is what both bench arms train on)."""
+    import dataclasses
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    ref = os.path.join(root, "baseline", "_ref")
+    if not os.path.exists(os.path.join(ref, "fms_fsdp", "config", "training.py")):
+        pytest.skip("reference install (baseline/_ref) not present")
+    code = (
+        "import sys, json, dataclasses\n"
+        f"sys.path = [{ref!r}, {os.path.join(root, 'baseline', 'fms_shim')!r}] + [p for p in sys.path if p not in ('', {root!r})]\n"
+        "from fms_fsdp.config import train_config\n"
+        "from fms_fsdp.utils.dataloader_utils import get_dummy_loader\n"
+        "c = train_config(); c.seq_length, c.batch_size, c.vocab_size = 16, 2, 50\n"
+        "it = iter(get_dummy_loader(c, 1, 4))\n"
+        "batches = [[t.tolist() for t in next(it)] for _ in range(5)]\n"
+        "print('OUT' + json.dumps({'cfg': dataclasses.asdict(train_config()), 'batches': batches}))\n")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd="/", timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    theirs = json.loads(r.stdout.split("OUT", 1)[1])
+    mine = dataclasses.asdict(train_config())
+    for k, v in theirs["cfg"].items():
+        assert k in mine, f"missing train_config field {k}"
+        assert mine[k] == v, (k, mine[k], v)
+    from fms_fsdp_b200.utils.dataloader_utils import get_dummy_loader
+    c = train_config()
+    c.seq_length, c.batch_size, c.vocab_size = 16, 2, 50
+    it = iter(get_dummy_loader(c, 1, 4))
+    for want in theirs["batches"]:
+        got = [t.tolist() for t in next(it)]
+        assert got == want
