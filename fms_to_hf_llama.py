@@ -86,7 +86,11 @@ def load_dcp_into(model: torch.nn.Module, load_path: str, compiled: bool = False
     return model
 
 
-def main(model_variant, load_path, save_path, tokenizer_name_or_path=None, compiled=False, is_old_fms=False):
+def main(model_variant, compiled=False, is_old_fms=False, load_path=None, save_path=None, tokenizer_name_or_path=None):
+    """Parameter order of the reference (``fms_to_hf_llama.py:133-135``); ``--compiled`` / ``--is_old_fms`` default to False."""
+    if load_path is None or save_path is None:
+        raise SystemExit("usage: fms_to_hf_llama.py --model_variant V [--compiled] [--is_old_fms] --load_path CKPT --save_path OUT "
+                         "[--tokenizer_name_or_path TOK]")
     print("Initializing model...")
     cfg = get_model_config(model_variant)
     with torch.device("meta"):

@@ -19,12 +19,21 @@ from fms_fsdp_b200.parallel.tensor_parallel import tp_all_gather_last, tp_all_re
 
 
 # ---------------------------------------------------------------------------------- base models
+def _only_causal_contiguous(mask, position_ids):
+    """The Embed* forwards keep the reference's parameter list (``train_speculator_utils.py:432-441``); the frozen base model
+    here always runs causal attention over contiguous positions (offset by the KV cache), which is all the trainer uses."""
+    if mask is not None or position_ids is not None:
+        raise NotImplementedError("explicit attention masks / position ids are not supported by the frozen base models")
+
+
 class EmbedLLaMA(LLaMA):
     """Frozen LLaMA whose forward can also return the final hidden states ("embeds") and a KV cache.
     Inference only: prefill uses the engine's flash attention; single-token decode steps attend over the
     cache with SDPA.  With ``shard_llama_for_tp`` applied, row-parallel outputs are all-reduced."""
 
-    def forward(self, x, past_key_value_states=None, use_cache=False, include_embeds=False, **_):
+    def forward(self, x, mask=None, position_ids=None, past_key_value_states=None, use_cache=False,
+                only_last_token=False, attn_algorithm=None, include_embeds=False):
+        _only_causal_contiguous(mask, position_ids)
         tp = getattr(self, "_tp_group", None)
         B, S = x.shape
         h = self.shared(x)
@@ -56,6 +65,8 @@ class EmbedLLaMA(LLaMA):
                 h = h + tp_all_reduce(a.dense(ctx), tp)
                 h = h + tp_all_reduce(blk.ff_sub_layer.w2(ops.swiglu(blk.ff_sub_layer.wg1_fused(blk.ff_ln(h)))), tp)
         embeds = self.dec_norm(h)
+        if only_last_token:
+            embeds = embeds[:, -1, :]
         logits = self.shared(embeds, reverse=True)
         if tp is not None:
             logits = tp_all_gather_last(logits, tp)
@@ -114,7 +125,9 @@ class EmbedGPTBigCode(nn.Module):
                 nn.init.ones_(m.weight)
                 nn.init.zeros_(m.bias)
 
-    def forward(self, x, past_key_value_states=None, use_cache=False, include_embeds=False, **_):
+    def forward(self, x, mask=None, position_ids=None, past_key_value_states=None, use_cache=False,
+                only_last_token=False, attn_algorithm=None, include_embeds=False):
+        _only_causal_contiguous(mask, position_ids)
         past = past_key_value_states
         p0 = 0 if past is None else past[0][0].size(1)
         h = self.emb(x) + self.pos(torch.arange(p0, p0 + x.size(1), device=x.device))[None]
@@ -123,6 +136,8 @@ class EmbedGPTBigCode(nn.Module):
             h, c = blk(h, None if past is None else past[i], use_cache)
             cache.append(c)
         embeds = self.dec_norm(h)
+        if only_last_token:
+            embeds = embeds[:, -1, :]
         logits = self.head(embeds)
         if getattr(self, "_tp_group", None) is not None:
             logits = tp_all_gather_last(logits, self._tp_group)
@@ -174,7 +189,9 @@ class EmbedMixtral(EmbedLLaMA):
             for m in (blk.ln, blk.ff_ln, blk.attn, blk.moe):
                 m.reset_parameters()
 
-    def forward(self, x, past_key_value_states=None, use_cache=False, include_embeds=False, **_):
+    def forward(self, x, mask=None, position_ids=None, past_key_value_states=None, use_cache=False,
+                only_last_token=False, attn_algorithm=None, include_embeds=False):
+        _only_causal_contiguous(mask, position_ids)
         tp = getattr(self, "_tp_group", None)
         red = (lambda t: t) if tp is None else (lambda t: tp_all_reduce(t, tp))
         B, S = x.shape
@@ -198,6 +215,8 @@ class EmbedMixtral(EmbedLLaMA):
             h = a.dense(ctx, residual=h) if tp is None else h + red(a.dense(ctx))
             h = h + red(blk.moe(blk.ff_ln(h)))
         embeds = self.dec_norm(h)
+        if only_last_token:
+            embeds = embeds[:, -1, :]
         logits = self.shared(embeds, reverse=True)
         if tp is not None:
             logits = tp_all_gather_last(logits, tp)

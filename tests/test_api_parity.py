@@ -46,3 +46,46 @@ def test_public_names_of_reference_module_exist(path, mod):
             missing += [t.id for t in node.targets
                         if isinstance(t, ast.Name) and not t.id.startswith("_") and not hasattr(ours, t.id)]
     assert not missing, f"{mod} lacks {missing}"
+
+
+def _positional_names(fn_node):
+    a = fn_node.args
+    return [x.arg for x in a.posonlyargs + a.args if x.arg not in ("self", "cls")], [x.arg for x in a.kwonlyargs]
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree not mounted")
+@pytest.mark.parametrize("path,mod", sorted(MODULES.items()))
+def test_signatures_accept_the_reference_call_forms(path, mod):
+    """Every public function / method (and ``__init__``) takes the reference's parameters under the same names and, unless it
+    takes ``*args``, at the same positions -- so both keyword and positional call sites of reference users keep working."""
+    import inspect
+    tree = ast.parse(open(os.path.join(REF, path)).read())
+    ours = importlib.import_module(mod)
+    problems = []
+
+    def check(node, obj, label):
+        try:
+            params = list(inspect.signature(obj).parameters.values())
+        except (TypeError, ValueError):
+            return
+        names = [p.name for p in params if p.name not in ("self", "cls")]
+        var_kw = any(p.kind == p.VAR_KEYWORD for p in params)
+        var_pos = any(p.kind == p.VAR_POSITIONAL for p in params)
+        pos, kwonly = _positional_names(node)
+        for i, n in enumerate(pos):
+            if n not in names:
+                if not var_kw:
+                    problems.append(f"{label}: no parameter {n}")
+            elif names.index(n) != i and not var_pos:
+                problems.append(f"{label}: {n} is parameter {names.index(n)}, reference has it at {i}")
+        problems.extend(f"{label}: no keyword {n}" for n in kwonly if n not in names and not var_kw)
+
+    for node in tree.body:
+        if isinstance(node, ast.FunctionDef) and not node.name.startswith("_") and hasattr(ours, node.name):
+            check(node, getattr(ours, node.name), node.name)
+        elif isinstance(node, ast.ClassDef) and hasattr(ours, node.name):
+            cls = getattr(ours, node.name)
+            for b in node.body:
+                if isinstance(b, ast.FunctionDef) and (b.name == "__init__" or not b.name.startswith("_")) and hasattr(cls, b.name):
+                    check(b, getattr(cls, b.name), f"{node.name}.{b.name}")
+    assert not problems, f"{mod}: {problems}"

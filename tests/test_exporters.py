@@ -40,7 +40,7 @@ def test_llama_export_from_sharded_checkpoint(monkeypatch):
     Checkpointer(ck, 2, "fsdp", 0, 0).save(7, eng, opt, None, tokens_seen=1)
     monkeypatch.setattr(ex, "get_model_config", lambda v: LLaMAConfig(**cfg.__dict__))
     out = tempfile.mkdtemp()
-    ex.main("llama2_test", os.path.join(ck, "checkpoints", "step_7_ckp"), out)
+    ex.main("llama2_test", load_path=os.path.join(ck, "checkpoints", "step_7_ckp"), save_path=out)
     from transformers import LlamaForCausalLM
     hf = LlamaForCausalLM.from_pretrained(out)
     assert torch.equal(hf.model.embed_tokens.weight, ref_sd["shared.emb.weight"])
