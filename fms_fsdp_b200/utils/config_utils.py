@@ -100,7 +100,7 @@ def get_model_config(model_variant: str):
         return LLaMAConfig(**_LLAMA_ZOO[model_variant])
     if model_variant in _MAMBA_ZOO:
         return copy.deepcopy(_MAMBA_ZOO[model_variant])
-    raise ValueError(f"model variant {model_variant} not supported.")
+    raise ValueError(f"model variant {model_variant} not supported.  Known variants: {', '.join(sorted([*_LLAMA_ZOO, *_MAMBA_ZOO]))}")
 
 
 def list_model_variants():
