@@ -295,8 +295,14 @@ class Checkpointer:
             t1 = time.time()
             has_opt = any(k.startswith("optimizer_state.state.") for k in avail)
             if has_opt:
+                # checkpoints written under torch.compile carry the wrapper's prefix in the optimizer keys as well
+                opfx = "optimizer_state.state._orig_mod." if any(
+                    k.startswith("optimizer_state.state._orig_mod.") for k in avail) else "optimizer_state.state."
                 for which in ("exp_avg", "exp_avg_sq"):
-                    load_which(which, lambda n, w=which: f"optimizer_state.state.{n}.{w}")
+                    absent = load_which(which, lambda n, w=which: f"{opfx}{n}.{w}")
+                    if absent:
+                        self.report(f"WARNING: checkpoint has no {which} for {len(absent)} parameters (e.g. {absent[0]}); "
+                                    "their moments start from zero")
                 step_keys = [k for k in avail if k.startswith("optimizer_state.state.") and k.endswith(".step")]
                 if step_keys:
                     holder = {step_keys[0]: torch.zeros(())}

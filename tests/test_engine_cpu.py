@@ -316,3 +316,54 @@ def test_collective_plan_single_and_multi_node():
         plan("fused", "cuda", 16, 16, 8)
     # more ranks in a single-node group than a signal pad holds
     assert plan("auto", "cuda", 64, 64, 64)[0] == "torch"
+
+
+@pytest.mark.parametrize("compiled", [False, True])
+def test_checkpoint_in_the_torch_fsdp_key_layout_loads_and_training_continues(compiled):
+    """A checkpoint laid out the way the reference writes it -- torch DCP, ``model_state.<fqn>`` (``model_state._orig_mod.<fqn>``
+    under torch.compile), ``optimizer_state.state.<fqn>.{exp_avg,exp_avg_sq,step}``, ``optimizer_state.param_groups``,
+    ``metadata.pth`` (reference ``checkpointing_utils.py:283-310``) -- produced here from a PLAIN torch model and
+    ``torch.optim.AdamW`` (torch FSDP itself needs an accelerator), must resume in this runtime: the next optimizer step equals
+    the plain model's next step."""
+    import torch.distributed.checkpoint as dcp
+    from torch.distributed.checkpoint import FileSystemWriter
+    from fms_fsdp_b200.utils.checkpointing_utils import Checkpointer
+    torch.manual_seed(0)
+    plain = LLaMA(get_model_config("llama2_tiny")); plain.reset_parameters()
+    opt = torch.optim.AdamW(plain.parameters(), lr=1e-3, betas=(0.9, 0.95), weight_decay=0.1)
+
+    def plain_step(st):
+        opt.zero_grad()
+        x = _batch(0, st)
+        plain(x, labels=x).backward()
+        torch.nn.utils.clip_grad_norm_(plain.parameters(), 1.0)
+        opt.step()
+
+    for st in range(2):
+        plain_step(st)
+    names = {p: n for n, p in plain.named_parameters()}
+    pre = "_orig_mod." if compiled else ""
+    osd = opt.state_dict()
+    fqn_of = {i: names[p] for i, p in enumerate(opt.param_groups[0]["params"])}
+    state = {pre + fqn_of[i]: {k: v.clone() if torch.is_tensor(v) else v for k, v in s.items()} for i, s in osd["state"].items()}
+    groups = [{**{k: v for k, v in g.items() if k != "params"}, "params": [pre + fqn_of[i] for i in g["params"]]}
+              for g in osd["param_groups"]]
+    ckdir = tempfile.mkdtemp()
+    save_name = os.path.join(ckdir, "checkpoints", "step_2_ckp")
+    os.makedirs(save_name)
+    dcp.save({"model_state": {pre + k: v.clone() for k, v in plain.state_dict().items()},
+              "optimizer_state": {"state": state, "param_groups": groups}},
+             storage_writer=FileSystemWriter(save_name, single_file_per_rank=True), no_dist=True)
+    torch.save({"step": 2, "tokens_seen": 77}, os.path.join(save_name, "metadata.pth"))
+
+    torch.manual_seed(5)     # different init: everything must come from the checkpoint
+    m = LLaMA(get_model_config("llama2_tiny")); m.reset_parameters()
+    eng = ShardedModel(m, device="cpu"); ours = ShardedAdamW(eng, lr=1e-3, betas=(0.9, 0.95), weight_decay=0.1)
+    _, _, _, step, ntok, resuming = Checkpointer(ckdir, 5, "fsdp", 0, 0).load(eng, ours, None, path="", is_compiled=compiled)
+    assert (step, ntok, resuming) == (2, 77, True) and ours._step == 2
+    x = _batch(0, 2)
+    eng.forward_backward(x, x); eng.clip_grad_norm_(1.0); ours.step()
+    plain_step(2)
+    mine = eng.full_state_dict()
+    for k, v in plain.state_dict().items():
+        assert torch.allclose(mine[k], v, atol=2e-6, rtol=1e-5), (k, (mine[k] - v).abs().max())
