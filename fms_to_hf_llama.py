@@ -25,6 +25,8 @@ def _interleaved_to_halfsplit(w: torch.Tensor, nheads: int) -> torch.Tensor:
 
 
 def convert_to_hf(model: LLaMA, model_variant: str, is_old_fms: bool = False):
+    """``is_old_fms`` is kept for the reference's signature; this repo's LLaMA is always fused, pre-fusion checkpoints are
+    fused when they are read (``load_dcp_into``)."""
     from transformers import LlamaConfig, LlamaForCausalLM
 
     c = model.config
@@ -47,20 +49,14 @@ def convert_to_hf(model: LLaMA, model_variant: str, is_old_fms: bool = False):
         hf.model.embed_tokens.weight.copy_(sd["shared.emb.weight"])
         for i, layer in enumerate(hf.model.layers):
             p = f"layers.{i}."
-            if is_old_fms and p + "attn.query.weight" in sd:
-                q, k, v = sd[p + "attn.query.weight"], sd[p + "attn.key.weight"], sd[p + "attn.value.weight"]
-            else:
-                q, k, v = torch.split(sd[p + "attn.in_proj.qkv_fused.weight"],
-                                      [c.nheads * hd, c.kv_heads * hd, c.kv_heads * hd], dim=0)
+            q, k, v = torch.split(sd[p + "attn.in_proj.qkv_fused.weight"],
+                                  [c.nheads * hd, c.kv_heads * hd, c.kv_heads * hd], dim=0)
             layer.self_attn.q_proj.weight.copy_(_interleaved_to_halfsplit(q, c.nheads))
             layer.self_attn.k_proj.weight.copy_(_interleaved_to_halfsplit(k, c.kv_heads))
             layer.self_attn.v_proj.weight.copy_(v)
             layer.self_attn.o_proj.weight.copy_(sd[p + "attn.dense.weight"])
-            if is_old_fms and p + "ff_sub_layer.wg.weight" in sd:
-                wg, w1 = sd[p + "ff_sub_layer.wg.weight"], sd[p + "ff_sub_layer.w1.weight"]
-            else:
-                fused = sd[p + "ff_sub_layer.wg1_fused.weight"]
-                wg, w1 = torch.split(fused, [fused.size(0) // 2, fused.size(0) // 2], dim=0)
+            fused = sd[p + "ff_sub_layer.wg1_fused.weight"]
+            wg, w1 = torch.split(fused, [fused.size(0) // 2, fused.size(0) // 2], dim=0)
             layer.mlp.gate_proj.weight.copy_(wg)
             layer.mlp.up_proj.weight.copy_(w1)
             layer.mlp.down_proj.weight.copy_(sd[p + "ff_sub_layer.w2.weight"])
@@ -71,18 +67,57 @@ def convert_to_hf(model: LLaMA, model_variant: str, is_old_fms: bool = False):
     return hf
 
 
-def load_dcp_into(model: torch.nn.Module, load_path: str, compiled: bool = False):
-    """no_dist DCP read of ``model_state`` into a full CPU model (handles the ``_orig_mod`` level)."""
+def _unfused_template(model: LLaMA):
+    """State-dict template in the layout of pre-fusion FMS releases: separate ``attn.query/key/value`` and
+    ``ff_sub_layer.wg/w1`` instead of ``attn.in_proj.qkv_fused`` and ``ff_sub_layer.wg1_fused``."""
+    c, hd, out = model.config, model.config.head_dim, {}
+    for k, v in model.state_dict().items():
+        if k.endswith("attn.in_proj.qkv_fused.weight"):
+            base = k[:-len("in_proj.qkv_fused.weight")]
+            for name, rows in (("query", c.nheads * hd), ("key", c.kv_heads * hd), ("value", c.kv_heads * hd)):
+                out[base + name + ".weight"] = v.new_empty(rows, v.size(1))
+        elif k.endswith("ff_sub_layer.wg1_fused.weight"):
+            base = k[:-len("wg1_fused.weight")]
+            out[base + "wg.weight"] = v.new_empty(v.size(0) // 2, v.size(1))
+            out[base + "w1.weight"] = v.new_empty(v.size(0) // 2, v.size(1))
+        else:
+            out[k] = v
+    return out
+
+
+def _fuse_old_fms(sd):
+    out = {}
+    for k, v in sd.items():
+        if k.endswith("attn.query.weight"):
+            base = k[:-len("query.weight")]
+            out[base + "in_proj.qkv_fused.weight"] = torch.cat([v, sd[base + "key.weight"], sd[base + "value.weight"]], dim=0)
+        elif k.endswith("ff_sub_layer.wg.weight"):
+            base = k[:-len("wg.weight")]
+            out[base + "wg1_fused.weight"] = torch.cat([v, sd[base + "w1.weight"]], dim=0)
+        elif not k.endswith(("attn.key.weight", "attn.value.weight", "ff_sub_layer.w1.weight")):
+            out[k] = v
+    return out
+
+
+def load_dcp_into(model: torch.nn.Module, load_path: str, compiled: bool = False, is_old_fms: bool = False):
+    """no_dist DCP read of ``model_state`` into a full CPU model.  Handles the ``_orig_mod`` level of checkpoints written
+    under torch.compile and -- ``is_old_fms``, or detected from the keys -- checkpoints of pre-fusion FMS releases, whose
+    separate q / k / v and gate / up matrices are fused on the way in (this repo's LLaMA is always fused)."""
     import torch.distributed.checkpoint as dcp
     from torch.distributed.checkpoint import FileSystemReader
     keys = set(FileSystemReader(load_path).read_metadata().state_dict_metadata.keys())
+    unfused = is_old_fms or any(k.endswith("attn.query.weight") for k in keys)
+    if unfused and any(k.endswith("attn.in_proj.qkv_fused.weight") for k in keys):
+        unfused = False          # --is_old_fms given for a checkpoint that is already fused: nothing to do
+    template = _unfused_template(model) if unfused else model.state_dict()
     if compiled or any(k.startswith("model_state._orig_mod.") for k in keys):
-        state = {"model_state": {"_orig_mod": model.state_dict()}}
+        state = {"model_state": {"_orig_mod": template}}
     else:
-        state = {"model_state": model.state_dict()}
+        state = {"model_state": template}
     dcp.load(state, checkpoint_id=load_path, no_dist=True)
     sd = state["model_state"]
-    model.load_state_dict(sd.get("_orig_mod", sd))
+    sd = sd.get("_orig_mod", sd)
+    model.load_state_dict(_fuse_old_fms(sd) if unfused else sd)
     return model
 
 
@@ -97,7 +132,7 @@ def main(model_variant, compiled=False, is_old_fms=False, load_path=None, save_p
         model = LLaMA(cfg)
     model.to_empty(device="cpu")
     print(f"Reading state dict from {load_path}")
-    load_dcp_into(model, load_path, compiled)
+    load_dcp_into(model, load_path, compiled, is_old_fms)
     print("Converting to HF Llama...")
     hf = convert_to_hf(model, model_variant, is_old_fms)
     hf.save_pretrained(save_path)

@@ -91,3 +91,40 @@ def test_hf_import_single_file_feeds_the_trainer(tmp_path):
 
     with pytest.raises(ValueError, match="does not have the architecture"):
         imp.main(hf_dir, pth, model_variant="llama2_7b")
+
+
+@pytest.mark.parametrize("compiled,old_fms", [(True, False), (False, True), (True, True)])
+def test_llama_export_reads_compiled_and_pre_fusion_checkpoints(monkeypatch, compiled, old_fms):
+    """``--compiled`` (keys under ``model_state._orig_mod.``) and ``--is_old_fms`` (separate q/k/v and gate/up matrices on disk,
+    reference ``fms_to_hf_llama.py:60-95``) checkpoints export to the same HF model as the plain fused checkpoint."""
+    import torch.distributed.checkpoint as dcp
+    from torch.distributed.checkpoint import FileSystemWriter
+    import fms_to_hf_llama as ex
+    torch.manual_seed(4)
+    cfg = LLaMAConfig(src_vocab_size=64, emb_dim=32, nheads=4, kvheads=2, nlayers=2, multiple_of=16, max_expected_seq_len=32)
+    m = LLaMA(cfg); m.reset_parameters(); m.eval()
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    if old_fms:
+        hd, split = cfg.head_dim, {}
+        for k, v in sd.items():
+            if k.endswith("in_proj.qkv_fused.weight"):
+                q, kk, vv = torch.split(v, [cfg.nheads * hd, cfg.kv_heads * hd, cfg.kv_heads * hd])
+                base = k[:-len("in_proj.qkv_fused.weight")]
+                split.update({base + "query.weight": q.clone(), base + "key.weight": kk.clone(), base + "value.weight": vv.clone()})
+            elif k.endswith("wg1_fused.weight"):
+                g, u = v.chunk(2)
+                split.update({k[:-len("wg1_fused.weight")] + "wg.weight": g.clone(), k[:-len("wg1_fused.weight")] + "w1.weight": u.clone()})
+            else:
+                split[k] = v
+        sd = split
+    ck = tempfile.mkdtemp()
+    dcp.save({"model_state": {"_orig_mod": sd} if compiled else sd},
+             storage_writer=FileSystemWriter(ck, single_file_per_rank=True), no_dist=True)
+    monkeypatch.setattr(ex, "get_model_config", lambda v: LLaMAConfig(**cfg.__dict__))
+    out = tempfile.mkdtemp()
+    ex.main("llama2_test", compiled, old_fms, ck, out)          # the reference's positional order
+    from transformers import LlamaForCausalLM
+    hf = LlamaForCausalLM.from_pretrained(out).eval()
+    x = torch.randint(0, 64, (2, 17))
+    with torch.no_grad():
+        assert torch.allclose(m(x), hf(x).logits, atol=2e-4, rtol=1e-3)
