@@ -337,3 +337,75 @@ def test_token_stream_and_loader_checkpoints_interchange_with_the_reference(corp
             ix, iy = iter(x), iter(y)
             for _ in range(60):
                 assert list(next(ix)) == list(next(iy)), tag
+
+
+# ------------------------------------------------------------------------ parquet / auto handlers (raw text + tokenizer)
+@pytest.fixture(scope="module")
+def text_corpus():
+    """A local word-level tokenizer (saved so ``AutoTokenizer.from_pretrained(dir)`` works offline; it adds <s> ... </s> like
+    the HF Llama tokenizers do) and a corpus with one parquet text shard and one pre-tokenised arrow shard."""
+    import pyarrow.parquet as pq
+    from tokenizers import Tokenizer, models, pre_tokenizers, processors
+    from transformers import PreTrainedTokenizerFast
+    tmp = tempfile.mkdtemp()
+    words = [f"w{i}" for i in range(200)]
+    vocab = {"<s>": 1, "</s>": 2, "[UNK]": 3, **{w: 10 + i for i, w in enumerate(words)}}
+    tok = Tokenizer(models.WordLevel(vocab, unk_token="[UNK]"))
+    tok.pre_tokenizer = pre_tokenizers.Whitespace()
+    tok.post_processor = processors.TemplateProcessing(single="<s> $A </s>", special_tokens=[("<s>", 1), ("</s>", 2)])
+    PreTrainedTokenizerFast(tokenizer_object=tok, unk_token="[UNK]", bos_token="<s>", eos_token="</s>").save_pretrained(f"{tmp}/tok")
+    docs = [" ".join(words[(7 * d + j) % 200] for j in range(20 + d % 9)) for d in range(40)]
+    os.makedirs(f"{tmp}/data/mix")
+    pq.write_table(pa.table({"text": docs, "other": list(range(40))}), f"{tmp}/data/mix/part_0.parquet")
+    _write(f"{tmp}/data/mix/part_1.arrow", [[300 + 50 * d + j for j in range(30)] for d in range(20)])
+    return tmp, docs, vocab
+
+
+def test_parquet_and_auto_handlers_tokenise_strip_and_match_the_reference(text_corpus):
+    from fms_fsdp_b200.utils.dataset_utils import AutoHandler, ParquetHandler
+    tmp, docs, vocab = text_corpus
+    h = ParquetHandler(f"{tmp}/tok", "text")
+    path = f"{tmp}/data/mix/part_0.parquet"
+    assert h.is_legal(path) and not h.is_legal(f"{tmp}/data/mix/part_1.arrow") and h.length(path) == 40
+    reader = h.open(path)
+    want = [vocab[w] for w in docs[3].split()]
+    assert h.get(reader, 3, set()) == [1] + want + [2]            # the tokenizer's own <s> ... </s>
+    assert h.get(reader, 3, {1, 2}) == want                       # ... stripped when named in drop_tokens
+    assert h.slice(want, 5, 4) == want[5:9]
+    a = AutoHandler(f"{tmp}/tok", "text")
+    assert a.is_legal(path) and a.is_legal(f"{tmp}/data/mix/part_1.arrow") and not a.is_legal(f"{tmp}/tok/tokenizer.json")
+    assert a.length(path) == 40 and a.length(f"{tmp}/data/mix/part_1.arrow") == 20
+    r = a.open(f"{tmp}/data/mix/part_1.arrow")
+    assert a.slice(a.get(r, 2, set()), 0, 3) == [400, 401, 402]
+    r = a.open(path)
+    assert a.get(r, 0, {1, 2}) == [vocab[w] for w in docs[0].split()]
+
+    # the whole reader on the mixed folder: same documents, same order as the unmodified reference classes
+    REF = _reference_dataset_module()
+    ours = StreamingDocDataset(f"{tmp}/data/mix", 0, 1, AutoHandler(f"{tmp}/tok", "text"), 0, strip_tokens={1, 2}, seed=3,
+                               max_chunksize=16)
+    theirs = REF.StreamingDocDataset(f"{tmp}/data/mix", 0, 1, REF.AutoHandler(f"{tmp}/tok", "text"), 0, strip_tokens={1, 2},
+                                     seed=3, max_chunksize=16)
+    io, it = iter(ours), iter(theirs)
+    for _ in range(200):
+        assert list(next(io)) == list(next(it))
+
+
+def test_get_data_loader_with_file_type_auto_runs_on_text_and_token_shards(text_corpus, tmp_path):
+    from fms_fsdp_b200.config import train_config
+    from fms_fsdp_b200.utils.dataloader_utils import get_data_loader
+    tmp, docs, vocab = text_corpus
+    cfg = train_config()
+    cfg.data_path, cfg.datasets, cfg.weights = f"{tmp}/data", "mix", "1"
+    cfg.file_type, cfg.tokenizer_path, cfg.col_name = "auto", f"{tmp}/tok", "text"
+    cfg.seq_length, cfg.batch_size, cfg.num_workers, cfg.logical_shards = 24, 2, 0, 4
+    cfg.bos_token, cfg.eos_token, cfg.strip_tokens = None, 0, "1,2"
+    cfg.ckpt_save_path = cfg.ckpt_load_path = str(tmp_path)
+    it = iter(get_data_loader(cfg, 0, 1))
+    seen = set()
+    for _ in range(30):
+        x, y = next(it)
+        assert x.shape == (2, 24) and torch.equal(x[:, 2:], y[:, 1:-1]) and bool((y[:, 0] == -100).all())
+        seen.update(x.flatten().tolist())
+    assert 1 not in seen and 2 not in seen and 0 in seen           # tokenizer BOS/EOS stripped, loader EOS delimits
+    assert any(10 <= t < 210 for t in seen) and any(t >= 300 for t in seen)   # both the text and the token shard are read
