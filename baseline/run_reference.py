@@ -90,7 +90,8 @@ def main():
         compiled = True
     optimizer = optim.AdamW(model.parameters(), lr=cfg.learning_rate, betas=(0.9, 0.95), weight_decay=0.1)
     warm = min(2000, 1000000 // 20)
-    schedule = lambda x: min(1 - (1 - min(x, warm) / warm) ** 2, 0.1 + 0.5 * (1 - 0.1) * (1 + math.cos(min(x, 1000000) / 1000000 * math.pi)))
+    schedule = lambda x: min(1 - (1 - min(x, warm) / warm) ** 2,
+                             0.1 + 0.5 * (1 - 0.1) * (1 + math.cos(min(x, 1000000) / 1000000 * math.pi)))
     scheduler = LambdaLR(optimizer, lambda x: schedule(x))
 
     class _NoCkpt:  # the loop insists on saving at the final step; a 7B checkpoint is not part of the metric
@@ -151,7 +152,8 @@ def main():
             "metric": "tokens/sec (Llama2-7B FSDP seq4k bs2)" if a.model == "llama2_7b" else f"tokens/sec ({a.model})",
             "value": round(value, 1), "unit": "tokens/s",
             "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": round(ms_step, 3),
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": (round(value / world / PUB[a.model], 4) if a.model in PUB else None),
+            "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": (round(value / world / PUB[a.model], 4) if a.model in PUB else None),
             "dtype": "bf16", "data": DATA_NOTE, "impl": "reference",
             "tokens_per_sec_per_gpu": round(value / world, 1),
             "config": bench_config(a.model, a.batch * world, a.seq, f"fsdp{world}", a.ac),

@@ -347,9 +347,9 @@ class ShardedModel(nn.Module):
 
     # --------------------------------------------------------------------------------- buffers
     def _acquire(self, pool, unit: ShardUnit, dtype, symmetric: bool, min_depth: int = 1) -> _Buf:
-        """Oldest pooled buffer of this shape once ``min_depth`` buffers exist.  Gradient buffers need depth 2: a unit's buffer goes back to the pool the moment its
-        reduce-scatter is ENQUEUED, so the next block would otherwise pick the same buffer and stall the compute
-        stream for the whole reduce (measured: 0.58 ms idle per block at 2 GPUs, ~1.1 ms at 8)."""
+        """Oldest pooled buffer of this shape once ``min_depth`` buffers exist.  Gradient buffers need depth 2: a unit's
+        buffer goes back to the pool the moment its reduce-scatter is ENQUEUED, so the next block would otherwise pick the same
+        buffer and stall the compute stream for the whole reduce (measured: 0.58 ms idle per block at 2 GPUs, ~1.1 ms at 8)."""
         key = (unit.layout.signature(), dtype)
         lst = pool.setdefault(key, [])
         made = self._pool_made.setdefault((id(pool), key), 0)
