@@ -367,3 +367,32 @@ def test_checkpoint_in_the_torch_fsdp_key_layout_loads_and_training_continues(co
     mine = eng.full_state_dict()
     for k, v in plain.state_dict().items():
         assert torch.allclose(mine[k], v, atol=2e-6, rtol=1e-5), (k, (mine[k] - v).abs().max())
+
+
+@pytest.mark.parametrize("strategy,world,shard", [("hsdp", 4, 2), ("ddp", 2, 0)])
+def test_hsdp_and_ddp_checkpoints_load_into_other_layouts(strategy, world, shard):
+    """HSDP: only the shard group of replica 0 writes the tensor files (reference ``_do_save``); DDP: rank 0 writes.  Either
+    checkpoint must come back -- model, AdamW moments, step -- in a single-process job and in an FSDP job of 2 ranks."""
+    from fms_fsdp_b200.utils.checkpointing_utils import Checkpointer
+    ck = tempfile.mkdtemp()
+    out = _run(world, strategy, shard, ckpt_dir=ck)
+    step_dir = os.path.join(ck, "checkpoints", f"step_{STEPS}_ckp")
+    n_files = len([f for f in os.listdir(step_dir) if f.endswith(".distcp")])
+    assert n_files == (2 if strategy == "hsdp" else 1), os.listdir(step_dir)
+
+    torch.manual_seed(3)
+    m = LLaMA(get_model_config("llama2_tiny")); m.reset_parameters()
+    eng = ShardedModel(m, device="cpu"); opt = ShardedAdamW(eng, lr=1e-3)
+    _, _, _, step, ntok, resuming = Checkpointer(ck, 5, "fsdp", 0, 0).load(eng, opt, None, path="")
+    assert (step, ntok, resuming, opt._step) == (STEPS, 123, True, STEPS)
+    sd = eng.full_state_dict()
+    for k, v in out["sd"].items():
+        assert torch.equal(sd[k], v), k
+    assert all(float(u.exp_avg.abs().sum()) > 0 and float(u.exp_avg_sq.sum()) > 0 for u in eng.units)
+
+    outdir = tempfile.mkdtemp()
+    mp.spawn(_reload_worker, args=(2, free_port(), ck, outdir), nprocs=2, join=True)
+    r = torch.load(os.path.join(outdir, "reload.pt"), weights_only=False)
+    assert (r["step"], r["ntok"], r["resuming"], r["opt_step"]) == (STEPS, 123, True, STEPS + 1)
+    for k, v in out["sd"].items():
+        assert torch.equal(r["sd"][k], v), k
