@@ -145,3 +145,26 @@ def test_hf_gpt_bigcode_and_mixtral_checkpoints_load_with_equal_logits():
     ours2 = get_model("embedmixtral", "8x7b", model_path=d2, device_type="cpu", dtype=torch.float32)
     with torch.no_grad():
         assert torch.allclose(ours2(x), hf2(x).logits, atol=2e-4)
+
+
+def test_speculator_entrypoint_resumes_from_its_checkpoint(tmp_path):
+    """Stop after 4 steps, start again with ``num_steps=6`` on the same checkpoint folder: the run picks up speculator,
+    optimizer and step count (reference ``train_speculator.py:246-262``) and only trains steps 5 and 6."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    base = [sys.executable, os.path.join(root, "speculator", "train_speculator.py"), "--model_arch=embedllama",
+            "--model_variant=tiny", "--model_path=/nonexistent", "--sharding_strategy=ddp", "--use_dummy_dataset=True",
+            "--report_interval=1", "--stage2_start_step=100", "--n_speculator_heads=2", "--speculator_width=32",
+            "--seq_length=16", "--vocab_size=512", "--batch_size=2", f"--ckpt_save_path={tmp_path}",
+            f"--ckpt_load_path={tmp_path}", "--checkpoint_interval=100", "--comm_backend=gloo", "--use_torch_compile=False"]
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")}
+    env["OMP_NUM_THREADS"] = "1"
+    r1 = subprocess.run(base + ["--num_steps=4"], capture_output=True, text=True, timeout=600, cwd=root, env=env)
+    assert r1.returncode == 0, r1.stdout[-1500:] + r1.stderr[-1500:]
+    assert "step: 4" in r1.stdout and os.path.isdir(os.path.join(tmp_path, "checkpoints", "step_4_ckp"))
+    r2 = subprocess.run(base + ["--num_steps=6"], capture_output=True, text=True, timeout=600, cwd=root, env=env)
+    assert r2.returncode == 0, r2.stdout[-1500:] + r2.stderr[-1500:]
+    assert "Prior checkpoint" in r2.stdout and "step_4_ckp" in r2.stdout
+    assert "step: 5" in r2.stdout and "step: 6" in r2.stdout and "step: 3" not in r2.stdout
+    assert os.path.isdir(os.path.join(tmp_path, "checkpoints", "step_6_ckp"))
