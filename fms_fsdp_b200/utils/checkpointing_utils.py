@@ -56,6 +56,20 @@ def get_oldest(targdir, qualifier=lambda x: True, key=os.path.getctime):
     return None
 
 
+def resolve_load_path(ckpt_load_path: str) -> str:
+    """What ``--ckpt_load_path`` points at.  The reference appends ``checkpoints/`` to a run directory and takes a file as is
+    (``main_training_llama.py:121-127``); additionally a single checkpoint folder (``.../step_N_ckp``, holds ``metadata.pth``)
+    or a folder of checkpoints is accepted directly instead of silently finding nothing under ``<it>/checkpoints/``."""
+    p = ckpt_load_path
+    if os.path.isfile(p):
+        return p
+    if os.path.isdir(p) and not os.path.isdir(os.path.join(p, "checkpoints")):
+        names = os.listdir(p)
+        if "metadata.pth" in names or any(n.startswith("step_") and n.endswith("_ckp") for n in names):
+            return p
+    return os.path.join(p, "checkpoints/")
+
+
 def _step_of(path: str) -> int:
     try:
         return int(os.path.basename(os.path.normpath(path)).split("_")[1])

@@ -14,7 +14,7 @@ from fms_fsdp_b200 import config
 from fms_fsdp_b200.models.mamba import Block, MambaConfig, MambaLMHeadModel
 from fms_fsdp_b200.ops import set_kernel_path
 from fms_fsdp_b200.parallel import ShardedAdamW, ShardedModel
-from fms_fsdp_b200.utils.checkpointing_utils import Checkpointer
+from fms_fsdp_b200.utils.checkpointing_utils import Checkpointer, resolve_load_path
 from fms_fsdp_b200.utils.cli import run
 from fms_fsdp_b200.utils.config_utils import get_model_config, update_config
 from fms_fsdp_b200.utils.dataloader_utils import get_data_loader, get_dummy_loader
@@ -97,8 +97,7 @@ def main(**kwargs):
     checkpointer = Checkpointer(cfg.ckpt_save_path, 1000, sharding_strategy_policy, rank, local_rank)
     model, optimizer, _, start_step, tokens_seen, is_resuming = checkpointer.load(
         model, optimizer, None,
-        path=os.path.join(cfg.ckpt_load_path, "checkpoints/") if not os.path.isfile(cfg.ckpt_load_path)
-        else cfg.ckpt_load_path,
+        path=resolve_load_path(cfg.ckpt_load_path),
         strict=False,
     )
     if not is_resuming:

@@ -22,7 +22,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from fms_fsdp_b200 import config  # noqa: E402
 from fms_fsdp_b200.models.speculator import MLPSpeculator  # noqa: E402
 from fms_fsdp_b200.parallel import ShardedAdamW, ShardedModel  # noqa: E402
-from fms_fsdp_b200.utils.checkpointing_utils import Checkpointer  # noqa: E402
+from fms_fsdp_b200.utils.checkpointing_utils import Checkpointer, resolve_load_path  # noqa: E402
 from fms_fsdp_b200.utils.cli import run  # noqa: E402
 from fms_fsdp_b200.utils.config_utils import update_config  # noqa: E402
 from fms_fsdp_b200.utils.dataloader_utils import get_data_loader, get_dummy_loader  # noqa: E402
@@ -156,7 +156,7 @@ def main(**kwargs):
     checkpointer = Checkpointer(cfg.ckpt_save_path, 1000, "ddp", rank, local_rank)
     speculator, optimizer, train_loader, start_step, tokens_seen, is_resuming = checkpointer.load(
         speculator, optimizer, train_loader if hasattr(train_loader, "dataset") else None,
-        path=os.path.join(cfg.ckpt_load_path, "checkpoints/"), is_compiled=cfg.use_torch_compile)
+        path=resolve_load_path(cfg.ckpt_load_path), is_compiled=cfg.use_torch_compile)
     if train_loader is None:
         train_loader = get_training_data_loader(rank, cfg, world_size, speculator_mesh)
     if not is_resuming:

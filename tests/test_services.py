@@ -134,3 +134,18 @@ def test_param_init_function_materialises_meta_modules():
         param_init_function(sub, torch.device("cpu"))
     assert not any(p.is_meta for p in blk.parameters()) and all(torch.isfinite(p).all() for p in blk.parameters())
     assert float(blk.ln.weight.min()) == 1.0 and 0 < float(blk.attn.dense.weight.std()) < 0.05
+
+
+def test_resolve_load_path(tmp_path):
+    from fms_fsdp_b200.utils.checkpointing_utils import resolve_load_path
+    run = tmp_path / "run"
+    ck = run / "checkpoints" / "step_5_ckp"
+    ck.mkdir(parents=True)
+    (ck / "metadata.pth").write_bytes(b"x")
+    f = tmp_path / "model.pth"
+    f.write_bytes(b"x")
+    assert resolve_load_path(str(f)) == str(f)                                              # single file: as is
+    assert resolve_load_path(str(run)) == str(run) + "/checkpoints/"                        # run directory: reference rule
+    assert resolve_load_path(str(ck)) == str(ck)                                            # one checkpoint folder
+    assert resolve_load_path(str(run / "checkpoints")) == str(run / "checkpoints")          # folder of checkpoints
+    assert resolve_load_path(str(tmp_path / "nothing")) == str(tmp_path / "nothing") + "/checkpoints/"
