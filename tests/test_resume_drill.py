@@ -40,3 +40,25 @@ def test_kill_a_rank_restart_and_auto_resume(tmp_path):
     steps = _steps(r2.stdout)
     assert steps and steps[0] == 5 and steps[-1] == 8, steps
     assert "Checkpoint saved" in r2.stdout
+
+
+@pytest.mark.timeout(1500)
+@pytest.mark.parametrize("strategy,nproc,extra", [("hsdp", 4, ["--hsdp_shard_size=2"]), ("ddp", 2, [])])
+def test_entrypoint_hsdp_and_ddp_train_checkpoint_and_resume(tmp_path, strategy, nproc, extra):
+    """The other two data-parallel layouts through the public entry point (gloo): HSDP as a 2x2 mesh, DDP; each trains,
+    writes its checkpoint with the right writer election, and a restart resumes from it."""
+    def launch(num_steps):
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}", "--master-addr",
+               "127.0.0.1", "--master-port", str(free_port()), os.path.join(ROOT, "main_training_llama.py"),
+               "--model_variant=llama2_tiny", "--use_dummy_dataset=True", f"--sharding_strategy={strategy}", *extra,
+               "--report_interval=1", "--seq_length=32", "--vocab_size=512", "--batch_size=2", f"--ckpt_save_path={tmp_path}",
+               f"--ckpt_load_path={tmp_path}", "--checkpoint_interval=100", "--comm_backend=gloo", f"--num_steps={num_steps}"]
+        return subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT, env=dict(os.environ, OMP_NUM_THREADS="1"))
+    r1 = launch(2)
+    assert r1.returncode == 0, r1.stdout[-2000:] + r1.stderr[-2000:]
+    assert _steps(r1.stdout) == [1, 2]
+    want_mesh = "mesh=replica2xshard2" if strategy == "hsdp" else f"mesh=replica{nproc}xshard1"
+    assert want_mesh in r1.stdout, r1.stdout[-1500:]
+    r2 = launch(4)
+    assert r2.returncode == 0, r2.stdout[-2000:] + r2.stderr[-2000:]
+    assert _steps(r2.stdout) == [3, 4] and "Prior checkpoint" in r2.stdout
