@@ -62,3 +62,15 @@ def test_entrypoint_hsdp_and_ddp_train_checkpoint_and_resume(tmp_path, strategy,
     r2 = launch(4)
     assert r2.returncode == 0, r2.stdout[-2000:] + r2.stderr[-2000:]
     assert _steps(r2.stdout) == [3, 4] and "Prior checkpoint" in r2.stdout
+
+
+@pytest.mark.timeout(900)
+def test_entrypoint_policy_flags_low_cpu_init_selective_recompute_fp32(tmp_path):
+    """``--low_cpu_fsdp`` (meta-device construction, unit-at-a-time materialisation, rank 0's init broadcast),
+    ``--fsdp_activation_checkpointing --selective_checkpointing=1/2`` and ``--mixed_precision=False`` together, 2 ranks."""
+    r = _launch(tmp_path, free_port(), "--num_steps=2", "--low_cpu_fsdp=True", "--fsdp_activation_checkpointing=True",
+                "--selective_checkpointing=1/2", "--mixed_precision=False", "--checkpoint_interval=100")
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert _steps(r.stdout) == [1, 2] and "applying FSDP activation checkpointing" in r.stdout
+    losses = [float(x) for x in re.findall(r"^loss: ([0-9.]+)$", r.stdout, flags=re.M)]
+    assert len(losses) == 2 and all(5.0 < v < 9.0 for v in losses), losses      # ~ln(vocab) at initialisation, finite
