@@ -51,3 +51,29 @@ def test_arrow_corpus_train_checkpoint_and_resume(tmp_path):
     assert steps == [4, 5], steps
     losses = [float(x) for x in re.findall(r"^loss: ([0-9.eE+-]+)$", r1.stdout + r2.stdout, flags=re.M)]
     assert len(losses) == 5 and all(l == l and l < 20 for l in losses), losses
+
+
+def test_new_run_from_another_runs_weights_with_and_without_its_data_position(tmp_path):
+    """``--ckpt_load_path=<run A> --ckpt_save_path=<run B>``: B starts at step 0 from A's weights.  With
+    ``--resuming_dataset=True`` the loader additionally continues from A's position; by default the data starts over."""
+    data, a = str(tmp_path / "data"), str(tmp_path / "A")
+    _corpus(data)
+    assert _run(data, a, 3).returncode == 0
+
+    def start_b(name, *extra):
+        cmd = [sys.executable, os.path.join(ROOT, "main_training_llama.py"), "--model_variant=llama2_tiny",
+               "--use_dummy_dataset=False", f"--data_path={data}", "--datasets=dataset_1,dataset_2", "--weights=2,1",
+               "--file_type=arrow", "--col_name=tokens", "--logical_shards=8", "--num_workers=1", "--seq_length=32",
+               "--vocab_size=512", "--batch_size=2", "--eos_token=0", "--num_steps=2", "--report_interval=1",
+               "--checkpoint_interval=100", f"--ckpt_save_path={tmp_path / name}", f"--ckpt_load_path={a}",
+               "--sharding_strategy=fsdp", "--comm_backend=gloo", *extra]
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT, env=dict(os.environ, OMP_NUM_THREADS="1"))
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+        assert [int(s) for s in re.findall(r"^step: (\d+)$", r.stdout, flags=re.M)] == [1, 2]
+        assert "Prior checkpoint" in r.stdout and "step_3_ckp" in r.stdout
+        return r.stdout
+
+    with_data = start_b("B1", "--resuming_dataset=True")
+    assert "Dataset checkpoint loaded" in with_data
+    fresh_data = start_b("B2")
+    assert "Dataset checkpoint loaded" not in fresh_data and "dataset starting from scratch" in fresh_data
