@@ -145,7 +145,9 @@ def plan_collectives(impl: str, device_type: str, world: int, shard_size: int, l
 
 
 def make_collectives(impl: str, mesh: DPMesh, device: torch.device):
-    local_world = int(os.environ.get("LOCAL_WORLD_SIZE", mesh.world))
+    # FMS_B200_LOCAL_WORLD overrides torchrun's LOCAL_WORLD_SIZE: lets one 8-GPU box pretend to be two 4-GPU nodes so the
+    # multi-node composition (fused shard group + NCCL replica all-reduce) can be exercised without a second node
+    local_world = int(os.environ.get("FMS_B200_LOCAL_WORLD", os.environ.get("LOCAL_WORLD_SIZE", mesh.world)))
     shard_impl, replica_impl = plan_collectives(impl, device.type, mesh.world, mesh.shard_size, local_world, mesh.rank)
     if shard_impl == "fused":
         from fms_fsdp_b200.parallel.fused_comm import FusedCollectives
