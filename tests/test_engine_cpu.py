@@ -396,3 +396,20 @@ def test_hsdp_and_ddp_checkpoints_load_into_other_layouts(strategy, world, shard
     assert (r["step"], r["ntok"], r["resuming"], r["opt_step"]) == (STEPS, 123, True, STEPS + 1)
     for k, v in out["sd"].items():
         assert torch.equal(r["sd"][k], v), k
+
+
+def test_scaled_losses_scale_the_gradients(tiny_llama):
+    """``(loss * k).backward()`` -- gradient accumulation, loss weighting -- through both public forms: logits + external
+    cross-entropy, and the fused ``model(tokens, labels)`` loss."""
+    x = _batch(0, 0)
+    norms = []
+    for scale, fused in ((1.0, False), (0.25, False), (0.25, True)):
+        eng = ShardedModel(copy.deepcopy(tiny_llama), device="cpu")
+        if fused:
+            loss = eng(x, x)
+        else:
+            out = eng(x)
+            loss = torch.nn.functional.cross_entropy(out.view(-1, out.size(-1)), x.view(-1))
+        (loss * scale).backward()
+        norms.append(eng.clip_grad_norm_(1e9).item())
+    assert norms[1] == pytest.approx(0.25 * norms[0], rel=1e-5) and norms[2] == pytest.approx(0.25 * norms[0], rel=1e-4)
