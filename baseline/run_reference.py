@@ -62,6 +62,17 @@ def main():
             print(json.dumps({"impl": "reference", "unavailable": f"reference import failed: {e!r}"[:300]}))
         return
 
+    if a.model.startswith("mamba"):
+        # the reference's Mamba entry point needs mamba_ssm (CUDA extension package; not in the image, no index access)
+        try:
+            import mamba_ssm  # noqa: F401
+            why = "baseline/run_reference.py drives the reference's Llama entry point only"
+        except Exception as e:
+            why = f"mamba_ssm is not installed ({e!r})"
+        if rank == 0:
+            print(json.dumps({"impl": "reference", "unavailable": why[:300]}))
+        return
+
     cfg = config.train_config()
     update_config(cfg, model_variant=a.model, use_dummy_dataset=True, sharding_strategy="fsdp", seq_length=a.seq,
                   batch_size=a.batch, low_cpu_fsdp=True, use_torch_compile=not a.no_compile,
