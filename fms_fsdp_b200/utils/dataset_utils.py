@@ -670,7 +670,11 @@ class StreamingDocDataset(_StatefulDataset):
             slot = self._order.after(self.lcg_state, span)
             return slot, self.filehandler.get(reader, first + slot, self.drop)
 
+        if n_docs == 0:
+            raise RuntimeError(f"{self.dataset}: reader {self.rank} of {self.worldsize} owns no documents and cannot be iterated "
+                               f"(more readers than documents under {self.datapath}?)")
         while True:
+            emitted_before = self.tokens_seen
             for step in range(n_docs):
                 doc_index = (resume_doc + step) % n_docs
                 if doc_index == 0:
@@ -693,6 +697,10 @@ class StreamingDocDataset(_StatefulDataset):
                 for j in range(min(already_out, n_chunks)):
                     self.chunk_index = j
                     yield self._chunk(doc, j, n_chunks)
+            if self.tokens_seen == emitted_before:
+                # a whole lap over the owned documents produced nothing: the reference spins forever here
+                raise RuntimeError(f"{self.dataset}: none of the {n_docs} documents of reader {self.rank} has at least "
+                                   f"min_length={self.min_length} tokens (after stripping) -- nothing to read")
 
     def load_state_dict(self, state_dicts, sharded_input=False):
         self.setup()
