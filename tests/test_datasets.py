@@ -450,3 +450,32 @@ def test_reader_partitioning_options_equal_the_reference(corpus, world, rank, bo
     a, b = iter(build(OURS)), iter(build(REF))
     for _ in range(150):
         assert list(next(a)) == list(next(b))
+
+
+@pytest.mark.parametrize("writer_is_ours,old_world,new_world", [(True, 3, 2), (False, 4, 6), (True, 6, 4), (False, 2, 1)])
+def test_rescaled_resume_equals_the_reference_for_more_world_size_pairs(corpus, tmp_path, writer_is_ours, old_world, new_world):
+    """Loader checkpoints written at ``old_world`` ranks by one implementation, resumed at ``new_world`` ranks by both: every
+    new rank continues with the same lines in either implementation (shrinking, growing, non-divisible pairs)."""
+    import fms_fsdp_b200.utils.dataset_utils as OURS
+    REF = _reference_dataset_module()
+    writer = OURS if writer_is_ours else REF
+    ck = str(tmp_path / "ck")
+
+    def stack(D, rank, world):
+        d = D.StreamingDocDataset(corpus, rank, world, D.ArrowHandler(), -1, strip_tokens={-1}, min_length=3, seed=7)
+        d = D.ScalableShardDataset(d, -1, n_logical_shards=12)
+        d = D.SamplingDataset(corpus, d, -1, datasets=["dataset_1", "dataset_2"], weights=[3, 1], verbose=False)
+        d = D.BufferDataset(d, 33, bos_token=None, eos_token=None, pack_hard=True)
+        return D.PreloadBufferDataset(d, 50)
+
+    olds = [stack(writer, r, old_world) for r in range(old_world)]
+    for s in olds:
+        take(iter(s), 30)
+    for s in olds:
+        s.save_to_path(ck)
+    for r in range(new_world):
+        a, b = stack(OURS, r, new_world), stack(REF, r, new_world)
+        a.load_from_path(ck); b.load_from_path(ck)
+        ia, ib = iter(a), iter(b)
+        for _ in range(40):
+            assert list(next(ia)) == list(next(ib)), (r, new_world)
