@@ -479,3 +479,30 @@ def test_rescaled_resume_equals_the_reference_for_more_world_size_pairs(corpus, 
         ia, ib = iter(a), iter(b)
         for _ in range(40):
             assert list(next(ia)) == list(next(ib)), (r, new_world)
+
+
+def test_multi_worker_dataloader_stream_equals_the_reference(corpus, tmp_path):
+    """Through ``torch.utils.data.DataLoader(num_workers=2)``: each worker process derives its own partition from
+    (rank, world, worker id); the batches of both implementations are identical, including the in-worker auto-checkpoints."""
+    import fms_fsdp_b200.utils.dataset_utils as OURS
+    REF = _reference_dataset_module()
+
+    def loader(D, tag):
+        d = D.StreamingDocDataset(corpus, 1, 2, D.ArrowHandler(), -1, min_length=3, seed=3)
+        d = D.ScalableShardDataset(d, -1, n_logical_shards=8)
+        d = D.SamplingDataset(corpus, d, -1, datasets=["dataset_1", "dataset_2"], weights=[1, 1], verbose=False)
+        d = D.BufferDataset(d, 21, pack_hard=True)
+        d = D.PreloadBufferDataset(d, 20)
+        d = D.PreprocessDataset(d, torch.IntTensor)
+        d = D.CheckpointDataset(d, str(tmp_path / tag), 5, 2, str(tmp_path / tag))
+        return torch.utils.data.DataLoader(d, num_workers=2, batch_size=2)
+
+    a, b = iter(loader(OURS, "ours")), iter(loader(REF, "ref"))
+    for _ in range(24):
+        assert torch.equal(next(a), next(b))
+    del a, b
+    mine = sorted(os.listdir(tmp_path / "ours" / "checkpoints"))
+    theirs = sorted(os.listdir(tmp_path / "ref" / "checkpoints"))
+    assert mine == theirs and mine, (mine, theirs)
+    step_dir = mine[-1]
+    assert sorted(os.listdir(tmp_path / "ours" / "checkpoints" / step_dir)) == sorted(os.listdir(tmp_path / "ref" / "checkpoints" / step_dir))
