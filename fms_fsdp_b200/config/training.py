@@ -24,6 +24,7 @@ _DEFAULT_CORPORA = ",".join(
 @dataclass
 class train_config:
     # ---- which model, where checkpoints live
+    """Reference: ``fms_fsdp/config/training.py:6-74``."""
     model_variant: str = "7b"                         # key of utils.config_utils.get_model_config (e.g. llama2_7b, mamba_9.8b)
     ckpt_load_path: str = "/fsx/output/ckpt"          # where to look for a checkpoint to start from (the save dir wins if it has one)
     ckpt_save_path: str = "/fsx/output/ckpt"          # step_<N>_ckp/ directories are written under <this>/checkpoints

@@ -48,7 +48,8 @@ def is_checkpointed(module: nn.Module) -> bool:
 
 
 def apply_fsdp_checkpointing(model: nn.Module, block, p):
-    """Flag fraction ``p`` of ``block`` instances under ``model`` for recompute."""
+    """Flag fraction ``p`` of ``block`` instances under ``model`` for recompute.
+    Reference: ``fms_fsdp/policies/ac_handler.py:16-64``."""
     blocks = [m for m in model.modules() if isinstance(m, block)]
     for m, sel in zip(blocks, selection_mask(len(blocks), p)):
         setattr(m, _FLAG, bool(sel))

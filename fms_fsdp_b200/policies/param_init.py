@@ -9,6 +9,7 @@ import torch.nn as nn
 
 
 def param_init_function(module: nn.Module, device=None):
+    """Reference: ``fms_fsdp/policies/param_init.py:9-18``."""
     device = device if device is not None else (
         torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else torch.device("cpu"))
     if any(p.is_meta for p in module.parameters(recurse=False)) or any(

@@ -17,4 +17,5 @@ def unit_policy(module: nn.Module, block_classes: Set[Type[nn.Module]]) -> bool:
 
 
 def get_wrapper(block):
+    """Reference: ``fms_fsdp/policies/wrapping.py:6-14``."""
     return functools.partial(unit_policy, block_classes={block})

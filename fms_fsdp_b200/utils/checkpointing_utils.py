@@ -39,7 +39,8 @@ def _entries(targdir, qualifier):
 
 
 def get_latest(targdir, qualifier=lambda x: True, key=os.path.getctime):
-    """Full path of the newest qualifying entry of ``targdir`` (None if empty / nonexistent)."""
+    """Full path of the newest qualifying entry of ``targdir`` (None if empty / nonexistent).
+    Reference: ``fms_fsdp/utils/checkpointing_utils.py:23-41``."""
     if os.path.exists(targdir) and len(os.listdir(targdir)) > 0:
         cands = _entries(targdir, qualifier)
         if cands:
@@ -48,7 +49,8 @@ def get_latest(targdir, qualifier=lambda x: True, key=os.path.getctime):
 
 
 def get_oldest(targdir, qualifier=lambda x: True, key=os.path.getctime):
-    """Full path of the oldest qualifying entry of ``targdir`` (None if empty / nonexistent)."""
+    """Full path of the oldest qualifying entry of ``targdir`` (None if empty / nonexistent).
+    Reference: ``fms_fsdp/utils/checkpointing_utils.py:44-62``."""
     if os.path.exists(targdir) and len(os.listdir(targdir)) > 0:
         cands = _entries(targdir, qualifier)
         if cands:
@@ -78,7 +80,8 @@ def _step_of(path: str) -> int:
 
 
 class Checkpointer:
-    """Save / load sharded checkpoints of a ``ShardedModel`` (+ ``ShardedAdamW``, + loader)."""
+    """Save / load sharded checkpoints of a ``ShardedModel`` (+ ``ShardedAdamW``, + loader).
+    Reference: ``fms_fsdp/utils/checkpointing_utils.py:65-316``."""
 
     def __init__(self, ckpdir, n_to_save, parallel_mode, rank, local_rank, report_fn=None,
                  model_auto_placement=False):

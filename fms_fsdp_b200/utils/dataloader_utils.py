@@ -19,7 +19,8 @@ _handler_map = {
 
 
 def causal_lm(data_seq, prompt_len: int = 1):
-    """(inputs, labels) = (x[:-1], x[1:]) with the first ``prompt_len`` labels masked to -100."""
+    """(inputs, labels) = (x[:-1], x[1:]) with the first ``prompt_len`` labels masked to -100.
+    Reference: ``fms_fsdp/utils/dataloader_utils.py:24-33``."""
     data_seq = data_seq.int() if isinstance(data_seq, torch.Tensor) else torch.IntTensor(data_seq)
     t = data_seq.clone()[1:]
     data_seq = data_seq[:-1]
@@ -44,6 +45,7 @@ class _SteadyCounter(torch.utils.data.IterableDataset):
 
 
 def get_dummy_loader(cfg, rank, world_size):
+    """Reference: ``fms_fsdp/utils/dataloader_utils.py:36-57``."""
     return iter(torch.utils.data.DataLoader(_SteadyCounter(cfg.seq_length, cfg.vocab_size),
                                             batch_size=cfg.batch_size))
 
@@ -61,7 +63,8 @@ def parse_data_args(datas, weights):
 
 def get_data_loader(cfg, rank, world_size, postprocess=[causal_lm]):
     """Stateful, rescalable streaming loader. ``postprocess`` is applied after tensor conversion
-    (the speculator passes [] to keep unshifted sequences)."""
+    (the speculator passes [] to keep unshifted sequences).
+    Reference: ``fms_fsdp/utils/dataloader_utils.py:60-146``."""
     datasets, weights = parse_data_args(cfg.datasets, cfg.weights)
 
     def _tok(x):

@@ -58,11 +58,13 @@ def covering_range(n_items: int, rank: int, worldsize: int) -> Tuple[int, int]:
 
 
 def _shard_partition(itemlist: List[Any], rank: int, worldsize: int) -> List[Any]:
+    """Reference: ``fms_fsdp/utils/dataset_utils.py:45-51``."""
     lo, hi = owned_range(len(itemlist), rank, worldsize)
     return itemlist[lo:hi]
 
 
 def _shard_inclusive(itemlist: List[Any], rank: int, worldsize: int) -> List[Any]:
+    """Reference: ``fms_fsdp/utils/dataset_utils.py:54-61``."""
     lo, hi = covering_range(len(itemlist), rank, worldsize)
     return itemlist[lo:hi]
 
@@ -174,7 +176,8 @@ class _StatefulDataset(data.IterableDataset):
 
 class _WrapperDataset(_StatefulDataset):
     """A layer around one sub-dataset.  ``_setup_children`` is the single customisation point: the default prepares the
-    wrapped dataset itself; layers that fan out (logical shards, corpora) build their clones there instead."""
+    wrapped dataset itself; layers that fan out (logical shards, corpora) build their clones there instead.
+    Reference: ``fms_fsdp/utils/dataset_utils.py:223-280``."""
 
     def __init__(self, dataset: _StatefulDataset):
         self.dataset = dataset
@@ -215,7 +218,8 @@ class _WrapperDataset(_StatefulDataset):
 
 # ======================================================================================= file handlers
 class _ShardFileHandler:
-    """Format adapter: which files qualify, how to open them, and how to count / fetch / slice documents."""
+    """Format adapter: which files qualify, how to open them, and how to count / fetch / slice documents.
+    Reference: ``fms_fsdp/utils/dataset_utils.py:286-330``."""
 
     def is_legal(self, filepath: str) -> bool:
         return os.path.isfile(filepath)
@@ -239,7 +243,8 @@ def _has_ext(path: str, tag: str) -> bool:
 
 class ArrowHandler(_ShardFileHandler):
     """Pre-tokenised Arrow IPC shards, one RecordBatch per document with the tokens in ``col_name``.  Memory-mapped:
-    only the slice of a document that a chunk needs is ever turned into Python objects."""
+    only the slice of a document that a chunk needs is ever turned into Python objects.
+    Reference: ``fms_fsdp/utils/dataset_utils.py:333-368``."""
 
     def __init__(self, col_name: str = "tokens"):
         self.col_name = col_name
@@ -272,7 +277,8 @@ class ArrowHandler(_ShardFileHandler):
 
 
 class ParquetHandler(_ShardFileHandler):
-    """HF-style parquet shards with a raw text column, tokenised on the fly."""
+    """HF-style parquet shards with a raw text column, tokenised on the fly.
+    Reference: ``fms_fsdp/utils/dataset_utils.py:371-404``."""
 
     def __init__(self, tokenizer_path: str, col_name: str = "text"):
         from transformers import AutoTokenizer
@@ -302,7 +308,8 @@ class ParquetHandler(_ShardFileHandler):
 
 
 class AutoHandler(_ShardFileHandler):
-    """Picks Arrow or parquet per file extension."""
+    """Picks Arrow or parquet per file extension.
+    Reference: ``fms_fsdp/utils/dataset_utils.py:407-457``."""
 
     def __init__(self, tokenizer_path: str, col_name: str = "text"):
         self.PHandler = ParquetHandler(tokenizer_path, col_name)
@@ -331,7 +338,8 @@ class AutoHandler(_ShardFileHandler):
 
 # ===================================================================================== thin wrappers
 class PreprocessDataset(_WrapperDataset):
-    """Stateless map over the stream."""
+    """Stateless map over the stream.
+    Reference: ``fms_fsdp/utils/dataset_utils.py:463-488``."""
 
     def __init__(self, dataset: _StatefulDataset, aug_fn: Callable):
         super().__init__(dataset)
@@ -345,7 +353,8 @@ class CheckpointDataset(_WrapperDataset):
     """Saves the loader state from INSIDE the worker every ``interval`` batches (``steps_per_batch`` items each) into
     ``<save>/checkpoints/step_<N>_ckp/`` -- the folder the model ``Checkpointer`` writes, so model and loader shards sit
     together -- and restores on setup: the newest checkpoint of the save folder if there is one (a restarted job), else
-    the newest of the load folder with the step counter back at zero (someone else's checkpoint)."""
+    the newest of the load folder with the step counter back at zero (someone else's checkpoint).
+    Reference: ``fms_fsdp/utils/dataset_utils.py:491-618``."""
 
     def __init__(self, dataset: _StatefulDataset, load_path: str, interval: int, steps_per_batch: int = 1,
                  save_path: str = ""):
@@ -418,7 +427,8 @@ class CheckpointDataset(_WrapperDataset):
 class PreloadBufferDataset(_WrapperDataset):
     """Local shuffle through one reservoir of ``window_size`` lines: while the reservoir is short it takes one extra
     line per draw; a uniformly random slot is emitted and refilled.  After a down-scale the (re-dealt) reservoir may be
-    over-full: it then drains by one line per draw until it is back at ``window_size``."""
+    over-full: it then drains by one line per draw until it is back at ``window_size``.
+    Reference: ``fms_fsdp/utils/dataset_utils.py:621-696``."""
 
     def __init__(self, dataset: _StatefulDataset, window_size: int):
         super().__init__(dataset)
@@ -465,7 +475,8 @@ class PreloadBufferDataset(_WrapperDataset):
 class BufferDataset(_WrapperDataset):
     """Packs variable-length chunks into lines of exactly ``seq_len`` tokens.  ``pack_hard``: a chunk that does not fit
     is split across lines; otherwise the line is closed (EOS) and padded.  Optional per-line BOS / EOS are not
-    duplicated when the token is already in place.  The carry-over is scalar state: it is dropped on a rescale."""
+    duplicated when the token is already in place.  The carry-over is scalar state: it is dropped on a rescale.
+    Reference: ``fms_fsdp/utils/dataset_utils.py:699-794``."""
 
     def __init__(self, dataset: _StatefulDataset, seq_len: int, pack_hard: bool, bos_token=None, eos_token=None,
                  pad_token=None):
@@ -554,7 +565,8 @@ class StreamingDocDataset(_StatefulDataset):
     shuffled with ``random.seed(seed + rank)``; inside a file the documents follow an LCG permutation (``_LcgOrder``),
     so no index list is materialised.  A document is emitted as chunks of at most ``max_chunksize`` tokens; the first
     chunk carries the optional BOS, the last one the delimiter.  The reader resumes in the middle of a document and
-    replays that document's already-emitted head chunks at the very end of the epoch."""
+    replays that document's already-emitted head chunks at the very end of the epoch.
+    Reference: ``fms_fsdp/utils/dataset_utils.py:797-1145``."""
 
     def __init__(self, datapath: str, rank: int, worldsize: int, filehandler: _ShardFileHandler, delimiter_token: Any,
                  bos_token: Optional[Any] = None, strip_tokens: Optional[Set[Any]] = None, seed: int = 42,
@@ -718,7 +730,8 @@ class ScalableShardDataset(_WrapperDataset):
     """Makes the reader rescalable: the corpus is cut into a FIXED number of logical readers (``n_logical_shards``,
     independent of the job size); a worker hosts ``n_logical_shards / worldsize`` of them and draws its next document
     from one picked with probability proportional to the documents it has left this epoch.  On a rescale the logical
-    readers' states simply move to their new hosts."""
+    readers' states simply move to their new hosts.
+    Reference: ``fms_fsdp/utils/dataset_utils.py:1148-1282``."""
 
     def __init__(self, dataset: StreamingDocDataset, delimiter_token: Any, n_logical_shards: int = 2048,
                  verbose: bool = False):
@@ -792,7 +805,8 @@ class ScalableShardDataset(_WrapperDataset):
 # ======================================================================================== corpus mixing
 class SamplingDataset(_WrapperDataset):
     """Mixes corpora (sub-directories of ``datapath``) by token share: whenever a document ends, continue with the
-    corpus whose share of the tokens emitted so far is furthest below its target weight."""
+    corpus whose share of the tokens emitted so far is furthest below its target weight.
+    Reference: ``fms_fsdp/utils/dataset_utils.py:1285-1417``."""
 
     def __init__(self, datapath: str, dataset: Union[ScalableShardDataset, StreamingDocDataset], delimiter_token: Any,
                  datasets=None, weights=None, verbose=False):

@@ -36,7 +36,8 @@ def pick_backend(cfg=None) -> str:
 
 
 def setup(backend: str = None, cfg=None):
-    """Rendezvous only (NCCL on GPU, gloo on CPU); hot-path collectives are the engine's own."""
+    """Rendezvous only (NCCL on GPU, gloo on CPU); hot-path collectives are the engine's own.
+    Reference: ``fms_fsdp/utils/train_utils.py:183-184``."""
     backend = backend or pick_backend(cfg)
     if not dist.is_initialized():
         dist.init_process_group(backend, timeout=timedelta(seconds=60 * 60))
@@ -44,6 +45,7 @@ def setup(backend: str = None, cfg=None):
 
 
 def setup_environ_flags():
+    """Reference: ``fms_fsdp/utils/train_utils.py:187-189``."""
     os.environ["TORCH_SHOW_CPP_STACKTRACES"] = str(1)
     os.environ["NCCL_ASYNC_ERROR_HANDLING"] = str(1)
     os.environ.setdefault("TORCH_NCCL_ASYNC_ERROR_HANDLING", str(1))
@@ -56,7 +58,8 @@ def torchrun_env():
 
 # ----------------------------------------------------------------------------------------- policies
 def get_mixed_precision_policy(cfg, rank):
-    """bf16 everywhere when the device supports it (always on B200), fp16 otherwise, None when off."""
+    """bf16 everywhere when the device supports it (always on B200), fp16 otherwise, None when off.
+    Reference: ``fms_fsdp/utils/train_utils.py:192-214``."""
     if not cfg.mixed_precision:
         return None
     bf16_ready = (not torch.cuda.is_available()) or torch.cuda.is_bf16_supported()
@@ -75,7 +78,8 @@ _STRATEGIES = {"fsdp": "fsdp", "hsdp": "hsdp", "ddp": "ddp"}
 
 
 def get_policies(cfg, rank, block):
-    """(mixed_precision_policy, wrapping_policy, sharding_strategy, apply_selective_ac, param_init_fn)."""
+    """(mixed_precision_policy, wrapping_policy, sharding_strategy, apply_selective_ac, param_init_fn).
+    Reference: ``fms_fsdp/utils/train_utils.py:217-253``."""
     precision = getattr(cfg, "precision", "bf16")
     if precision not in ("bf16", "fp8"):
         raise NotImplementedError(f"precision={precision!r}: bf16 (default) and fp8 (row-wise scaled e4m3 forward GEMMs, bf16 "
@@ -95,6 +99,7 @@ def get_policies(cfg, rank, block):
 
 
 def get_profiler(cfg, rank):
+    """Reference: ``fms_fsdp/utils/train_utils.py:256-271``."""
     if not cfg.use_profiler:
         return None
     if cfg.profiler_rank0_only and rank != 0:
@@ -251,6 +256,7 @@ class _LossReadback:
 
 def train(cfg, model, local_rank, rank, train_loader, optimizer, scheduler, profiler, checkpointer,
           start_step, tokens_seen):
+    """Reference: ``fms_fsdp/utils/train_utils.py:21-180``."""
     tracker_fn = _init_tracker(cfg, rank)
     is_cuda = torch.cuda.is_available() and getattr(model, "is_cuda", True)
     device = getattr(model, "device", torch.device("cuda", local_rank) if is_cuda else torch.device("cpu"))

@@ -31,7 +31,8 @@ from speculator.train_speculator_utils import generate, get_model, train_specula
 
 
 def test_model(rank, model, arch, cfg, prompt_type="chat"):
-    """Greedy 100-token smoke generation from the base model (skipped when no tokenizer ships with it)."""
+    """Greedy 100-token smoke generation from the base model (skipped when no tokenizer ships with it).
+    Reference: ``speculator/train_speculator.py:34-65``."""
     try:
         from transformers import AutoTokenizer
         tokenizer = AutoTokenizer.from_pretrained(cfg.model_path)
@@ -55,6 +56,7 @@ def test_model(rank, model, arch, cfg, prompt_type="chat"):
 
 
 def get_emb_dim(model):
+    """Reference: ``speculator/train_speculator.py:68-77``."""
     for k in ("emb_dim", "dim", "hidden_size"):
         if hasattr(getattr(model, "config", None), k):
             return getattr(model.config, k)
@@ -64,6 +66,7 @@ def get_emb_dim(model):
 
 
 def get_vocab_size(model):
+    """Reference: ``speculator/train_speculator.py:80-87``."""
     for k in ("src_vocab_size", "vocab_size"):
         if hasattr(getattr(model, "config", None), k):
             return getattr(model.config, k)
@@ -73,6 +76,7 @@ def get_vocab_size(model):
 
 
 def get_training_data_loader(rank, cfg, world_size, speculator_mesh):
+    """Reference: ``speculator/train_speculator.py:90-104``."""
     if rank == 0:
         print(f"{time.time()} Constructing datasets...")
     if cfg.use_dummy_dataset:
@@ -99,6 +103,7 @@ def speculator_lr_schedule(cfg):
 
 
 def main(**kwargs):
+    """Reference: ``speculator/train_speculator.py:107-326``."""
     cfg = config.train_config()
     update_config(cfg, **kwargs)
     cfg.seq_length = cfg.seq_length + cfg.n_speculator_heads + 1

@@ -29,7 +29,8 @@ def _only_causal_contiguous(mask, position_ids):
 class EmbedLLaMA(LLaMA):
     """Frozen LLaMA whose forward can also return the final hidden states ("embeds") and a KV cache.
     Inference only: prefill uses the engine's flash attention; single-token decode steps attend over the
-    cache with SDPA.  With ``shard_llama_for_tp`` applied, row-parallel outputs are all-reduced."""
+    cache with SDPA.  With ``shard_llama_for_tp`` applied, row-parallel outputs are all-reduced.
+    Reference: ``speculator/train_speculator_utils.py:464-492``."""
 
     def forward(self, x, mask=None, position_ids=None, past_key_value_states=None, use_cache=False,
                 only_last_token=False, attn_algorithm=None, include_embeds=False):
@@ -104,7 +105,8 @@ class _GPTBigCodeBlock(nn.Module):
 
 
 class EmbedGPTBigCode(nn.Module):
-    """GPT-BigCode (MQA, learned absolute positions, LayerNorm, GELU MLP) returning hidden states."""
+    """GPT-BigCode (MQA, learned absolute positions, LayerNorm, GELU MLP) returning hidden states.
+    Reference: ``speculator/train_speculator_utils.py:430-461``."""
 
     def __init__(self, vocab=49152, emb_dim=6144, nheads=48, nlayers=52, max_pos=8192, hidden_mult=4, eps=1e-5, **_):
         super().__init__()
@@ -174,7 +176,8 @@ class _MoE(nn.Module):
 
 
 class EmbedMixtral(EmbedLLaMA):
-    """Mixtral = the LLaMA block with a top-2-of-8 sparse MoE feed-forward; returns hidden states."""
+    """Mixtral = the LLaMA block with a top-2-of-8 sparse MoE feed-forward; returns hidden states.
+    Reference: ``speculator/train_speculator_utils.py:495-523``."""
 
     def __init__(self, config: Optional[LLaMAConfig] = None, n_experts=8, top_k=2, **kw):
         super().__init__(config, **kw)
@@ -400,7 +403,8 @@ def stage2_loss(cfg, model, speculator, base_model_input, input, loss_fn, ddp_st
 
 def do_ckpt(ckpt_save_path, reset=False):
     """Operator-triggered checkpoint: writing ``1`` into ``<ckpt_save_path>/do_ckpt`` asks the loop for a checkpoint at
-    the next step; the loop acknowledges with ``reset=True``, which writes ``0`` back."""
+    the next step; the loop acknowledges with ``reset=True``, which writes ``0`` back.
+    Reference: ``speculator/train_speculator_utils.py:246-260``."""
     flag = os.path.join(ckpt_save_path, "do_ckpt")
     if not os.path.isfile(flag):
         return False
@@ -415,7 +419,8 @@ def do_ckpt(ckpt_save_path, reset=False):
 # ---------------------------------------------------------------------------------------- loop
 def train_speculator(cfg, model, speculator, local_rank, rank, train_loader, optimizer, scheduler, checkpointer,
                      start_step: int = 0, n_tok: int = 0, profiler=None, base_model_mesh=None):
-    """Speculator training loop; ``speculator`` is a ``ShardedModel`` (NO_SHARD) around ``MLPSpeculator``."""
+    """Speculator training loop; ``speculator`` is a ``ShardedModel`` (NO_SHARD) around ``MLPSpeculator``.
+    Reference: ``speculator/train_speculator_utils.py:263-427``."""
     model.eval()
     speculator.train()
     device = speculator.device
