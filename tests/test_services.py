@@ -149,3 +149,12 @@ def test_resolve_load_path(tmp_path):
     assert resolve_load_path(str(ck)) == str(ck)                                            # one checkpoint folder
     assert resolve_load_path(str(run / "checkpoints")) == str(run / "checkpoints")          # folder of checkpoints
     assert resolve_load_path(str(tmp_path / "nothing")) == str(tmp_path / "nothing") + "/checkpoints/"
+
+
+def test_doctor_reports_the_environment_without_a_gpu():
+    from fms_fsdp_b200.utils import doctor
+    info = doctor.collect()
+    assert info["torch"] == torch.__version__ and isinstance(info["gpus"], list)
+    if not torch.cuda.is_available():
+        assert info["gpus"] == [] and info["problems"] == [] and any("ATen path" in n for n in info["notes"])
+        assert doctor.main() == 0
