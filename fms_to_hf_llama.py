@@ -110,14 +110,22 @@ def load_dcp_into(model: torch.nn.Module, load_path: str, compiled: bool = False
     if unfused and any(k.endswith("attn.in_proj.qkv_fused.weight") for k in keys):
         unfused = False          # --is_old_fms given for a checkpoint that is already fused: nothing to do
     template = _unfused_template(model) if unfused else model.state_dict()
-    if compiled or any(k.startswith("model_state._orig_mod.") for k in keys):
-        state = {"model_state": {"_orig_mod": template}}
-    else:
-        state = {"model_state": template}
+    nested = compiled or any(k.startswith("model_state._orig_mod.") for k in keys)
+    prefix = "model_state._orig_mod." if nested else "model_state."
+    # tied parameters (e.g. Mamba ``lm_head.weight`` = ``backbone.embedding.weight``) are stored once by this runtime: ask
+    # only for what the checkpoint holds, and let the module's own tying supply the alias
+    absent = [k for k in template if prefix + k not in keys]
+    template = {k: v for k, v in template.items() if prefix + k in keys}
+    state = {"model_state": {"_orig_mod": template} if nested else template}
     dcp.load(state, checkpoint_id=load_path, no_dist=True)
     sd = state["model_state"]
     sd = sd.get("_orig_mod", sd)
-    model.load_state_dict(_fuse_old_fms(sd) if unfused else sd)
+    sd = _fuse_old_fms(sd) if unfused else sd
+    loaded_ptrs = {p.data_ptr() for n, p in model.state_dict().items() if n in sd}
+    untied = [k for k in absent if model.state_dict()[k].data_ptr() not in loaded_ptrs] if not unfused else []
+    if untied:
+        raise RuntimeError(f"checkpoint {load_path} lacks {untied[:5]} (and they are not aliases of loaded parameters)")
+    model.load_state_dict(sd, strict=not absent)
     return model
 
 

@@ -128,3 +128,45 @@ def test_llama_export_reads_compiled_and_pre_fusion_checkpoints(monkeypatch, com
     x = torch.randint(0, 64, (2, 17))
     with torch.no_grad():
         assert torch.allclose(m(x), hf(x).logits, atol=2e-4, rtol=1e-3)
+
+
+def test_mamba_export_in_transformers_format(monkeypatch):
+    """``fms_to_hf_mamba.py --transformers_format``: a pure-Mamba2 checkpoint becomes a directory
+    ``transformers.Mamba2ForCausalLM.from_pretrained`` loads, with the same logits; hybrid models are refused with a reason."""
+    import fms_to_hf_mamba as ex
+    from fms_fsdp_b200.models.mamba import MambaConfig, MambaLMHeadModel
+    from fms_fsdp_b200.utils.config_utils import get_model_config
+    pure = dict(d_model=64, d_intermediate=0, n_layer=2, vocab_size=256, attn_layer_idx=[], attn_cfg={},
+                ssm_cfg={"layer": "Mamba2", "headdim": 16, "d_state": 16, "chunk_size": 16}, rms_norm=True, residual_in_fp32=True,
+                fused_add_norm=True, pad_vocab_size_multiple=16, tie_embeddings=True)
+    torch.manual_seed(5)
+    m = MambaLMHeadModel(MambaConfig(**pure)); m.reset_parameters(); m.eval()
+    eng = ShardedModel(m, device="cpu")
+    ck = tempfile.mkdtemp()
+    Checkpointer(ck, 2, "fsdp", 0, 0).save(1, eng, None, None)
+    real = get_model_config
+    monkeypatch.setattr(ex, "get_model_config", lambda v: dict(pure) if v == "mamba_pure_test" else real(v))
+    out = tempfile.mkdtemp()
+    ex.main("mamba_pure_test", os.path.join(ck, "checkpoints", "step_1_ckp"), out, transformers_format=True)
+    from transformers import Mamba2ForCausalLM
+    hf = Mamba2ForCausalLM.from_pretrained(out).eval()
+    x = torch.randint(0, 256, (2, 23))
+    with torch.no_grad():
+        with eng.summon_full_params():
+            a = eng.module(x)
+        a = a.logits if hasattr(a, "logits") else a
+        b = hf(x).logits
+    assert torch.allclose(a, b, atol=1e-5, rtol=1e-4), (a - b).abs().max()
+    with pytest.raises(ValueError, match="pure Mamba2"):
+        ex.to_transformers(MambaLMHeadModel(MambaConfig(**get_model_config("mamba_tiny"))))
+    # the tied head is stored once; the mamba_ssm-layout export and a trainer resume both restore the alias
+    out2 = tempfile.mkdtemp()
+    ex.main("mamba_pure_test", os.path.join(ck, "checkpoints", "step_1_ckp"), out2)
+    sd = torch.load(os.path.join(out2, "pytorch_model.bin"))
+    assert torch.equal(sd["lm_head.weight"], sd["backbone.embedding.weight"])
+    torch.manual_seed(9)
+    m2 = MambaLMHeadModel(MambaConfig(**pure)); m2.reset_parameters()
+    eng2 = ShardedModel(m2, device="cpu")
+    Checkpointer(tempfile.mkdtemp(), 2, "fsdp", 0, 0).load(eng2, None, None, path=os.path.join(ck, "checkpoints", "step_1_ckp"))
+    a2, b2 = eng.full_state_dict(), eng2.full_state_dict()
+    assert set(a2) == set(b2) and all(torch.equal(a2[k], b2[k]) for k in a2)

@@ -103,3 +103,39 @@ def test_mamba_entrypoint_resume_and_export(tmp_path):
                         capture_output=True, text=True, timeout=300, cwd=ROOT)
     assert r3.returncode == 0, r3.stdout[-1500:] + r3.stderr[-1500:]
     assert os.path.exists(os.path.join(out, "config.json")) and any(f.endswith((".bin", ".safetensors")) for f in os.listdir(out))
+
+
+def test_mamba2_matches_the_transformers_implementation():
+    """An independent implementation of the same architecture: ``transformers.Mamba2ForCausalLM`` (its pure-torch path) loaded
+    with OUR state dict (one key renamed) produces the same logits and the same gradients -- conv1d, SSD scan incl. a sequence
+    that is not a multiple of the chunk size, D skip, dt bias + softplus, gated RMSNorm, fp32 residual stream."""
+    from transformers import Mamba2Config, Mamba2ForCausalLM
+    from fms_fsdp_b200.models.mamba import MambaConfig, MambaLMHeadModel
+    torch.manual_seed(0)
+    cfg = MambaConfig(d_model=128, d_intermediate=0, n_layer=2, vocab_size=512,
+                      ssm_cfg={"layer": "Mamba2", "headdim": 32, "d_state": 32, "chunk_size": 32}, attn_layer_idx=[], attn_cfg={},
+                      rms_norm=True, residual_in_fp32=True, fused_add_norm=True, pad_vocab_size_multiple=16, tie_embeddings=False)
+    ours = MambaLMHeadModel(cfg); ours.reset_parameters()
+    with torch.no_grad():
+        for n, p in ours.named_parameters():
+            if n.endswith(("conv1d.bias", ".D", "dt_bias")):
+                p.normal_(0, 0.3)
+    hf = Mamba2ForCausalLM(Mamba2Config(
+        vocab_size=512, hidden_size=128, state_size=32, num_hidden_layers=2, head_dim=32, num_heads=8, expand=2, n_groups=1,
+        conv_kernel=4, chunk_size=32, tie_word_embeddings=False, rms_norm=True, use_bias=False, use_conv_bias=True,
+        residual_in_fp32=True, layer_norm_epsilon=1e-5, hidden_act="silu"))
+    hf.load_state_dict({("backbone.embeddings.weight" if k == "backbone.embedding.weight" else k): v.clone()
+                        for k, v in ours.state_dict().items()}, strict=True)
+    x = torch.randint(0, 512, (2, 48))
+    a = ours(x)
+    a = a.logits if hasattr(a, "logits") else a
+    b = hf(x).logits
+    assert torch.allclose(a, b, atol=1e-5, rtol=1e-4), (a - b).abs().max()
+    w = torch.randn_like(a)
+    (a * w).sum().backward()
+    (b * w).sum().backward()
+    theirs = dict(hf.named_parameters())
+    for n, p in ours.named_parameters():
+        q = theirs["backbone.embeddings.weight" if n == "backbone.embedding.weight" else n]
+        err, scale = (p.grad - q.grad).abs().max().item(), q.grad.abs().max().item()
+        assert err <= 1e-4 * scale + 1e-6, (n, err, scale)          # fp32 summation-order noise only
