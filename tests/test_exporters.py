@@ -130,6 +130,11 @@ def test_llama_export_reads_compiled_and_pre_fusion_checkpoints(monkeypatch, com
         assert torch.allclose(m(x), hf(x).logits, atol=2e-4, rtol=1e-3)
 
 
+def _init(m):
+    m.reset_parameters()
+    return m
+
+
 def test_mamba_export_in_transformers_format(monkeypatch):
     """``fms_to_hf_mamba.py --transformers_format``: a pure-Mamba2 checkpoint becomes a directory
     ``transformers.Mamba2ForCausalLM.from_pretrained`` loads, with the same logits; hybrid models are refused with a reason."""
@@ -157,8 +162,9 @@ def test_mamba_export_in_transformers_format(monkeypatch):
         a = a.logits if hasattr(a, "logits") else a
         b = hf(x).logits
     assert torch.allclose(a, b, atol=1e-5, rtol=1e-4), (a - b).abs().max()
-    with pytest.raises(ValueError, match="pure Mamba2"):
-        ex.to_transformers(MambaLMHeadModel(MambaConfig(**get_model_config("mamba_tiny"))))
+    assert type(ex.to_transformers(_init(MambaLMHeadModel(MambaConfig(**get_model_config("mamba_tiny")))))).__name__ == "BambaForCausalLM"
+    with pytest.raises(ValueError, match="pure Mamba2 stack"):      # attention layers but no MLP: neither layout fits
+        ex.to_transformers(MambaLMHeadModel(MambaConfig(**{**get_model_config("mamba_tiny"), "d_intermediate": 0})))
     # the tied head is stored once; the mamba_ssm-layout export and a trainer resume both restore the alias
     out2 = tempfile.mkdtemp()
     ex.main("mamba_pure_test", os.path.join(ck, "checkpoints", "step_1_ckp"), out2)

@@ -139,3 +139,62 @@ def test_mamba2_matches_the_transformers_implementation():
         q = theirs["backbone.embeddings.weight" if n == "backbone.embedding.weight" else n]
         err, scale = (p.grad - q.grad).abs().max().item(), q.grad.abs().max().item()
         assert err <= 1e-4 * scale + 1e-6, (n, err, scale)          # fp32 summation-order noise only
+
+
+def test_hybrid_matches_transformers_bamba_and_partial_rotary_matches_the_formula():
+    """The Mamba2 + attention (GQA, rotary) + gated-MLP hybrid against ``transformers.BambaForCausalLM`` carrying our weights
+    (``fms_to_hf_mamba.to_transformers``): same logits, same gradients.  transformers 5.5 builds full-width rotary tables for
+    Bamba, so that comparison uses ``rotary_emb_dim = head_dim``; the partial rotary of ``mamba_9.8b`` (first half of each head,
+    GPT-NeoX pairing) is checked against the written-out formula."""
+    import fms_to_hf_mamba as ex
+    from fms_fsdp_b200.models.mamba import MambaConfig, MambaLMHeadModel
+    from fms_fsdp_b200.utils.config_utils import get_model_config
+    d = get_model_config("mamba_tiny")
+    d["attn_cfg"]["rotary_emb_dim"] = d["attn_cfg"]["head_dim"]
+    torch.manual_seed(0)
+    ours = MambaLMHeadModel(MambaConfig(**d)); ours.reset_parameters()
+    with torch.no_grad():
+        for n, p in ours.named_parameters():
+            if n.endswith(("conv1d.bias", ".D", "dt_bias")):
+                p.normal_(0, 0.3)
+    hf = ex.to_transformers(ours)
+    assert type(hf).__name__ == "BambaForCausalLM"
+    x = torch.randint(0, 512, (2, 48))
+    a = ours(x)
+    a = a.logits if hasattr(a, "logits") else a
+    b = hf(x).logits
+    assert torch.allclose(a, b, atol=1e-5, rtol=1e-4), (a - b).abs().max()
+    w = torch.randn_like(a)
+    (a * w).sum().backward()
+    (b * w).sum().backward()
+    g = {n: p.grad for n, p in hf.named_parameters()}
+    blk = ours.backbone.layers[2]                                   # the attention block
+    H, KV, hd = 4, 2, 32
+    q, k, v = blk.mixer.in_proj.weight.grad.split([H * hd, KV * hd, KV * hd])
+    for mine, theirs in ((q, "self_attn.q_proj"), (k, "self_attn.k_proj"), (v, "self_attn.v_proj"),
+                         (blk.mixer.out_proj.weight.grad, "self_attn.o_proj"), (blk.mlp.fc2.weight.grad, "feed_forward.down_proj"),
+                         (blk.mlp.fc1.weight.grad.chunk(2)[1], "feed_forward.gate_proj")):
+        t = g[f"model.layers.2.{theirs}.weight"]
+        assert (mine - t).abs().max() <= 1e-4 * t.abs().max() + 1e-6, theirs
+    t = g["model.layers.0.mamba.in_proj.weight"]
+    assert (ours.backbone.layers[0].mixer.in_proj.weight.grad - t).abs().max() <= 1e-4 * t.abs().max() + 1e-6
+
+    # partial rotary (rotary_emb_dim = head_dim / 2, the mamba_9.8b setting) vs the formula
+    torch.manual_seed(1)
+    att = MambaLMHeadModel(MambaConfig(**get_model_config("mamba_tiny"))).backbone.layers[2].mixer
+    att.reset_parameters()
+    h = torch.randn(2, 40, 128)
+    rd = 16
+    with torch.no_grad():
+        y = att(h)
+        qq, kk, vv = att.in_proj(h).split([H * hd, KV * hd, KV * hd], -1)
+        qq, kk, vv = (t.view(2, 40, -1, hd).transpose(1, 2) for t in (qq, kk, vv))
+        ang = torch.outer(torch.arange(40).float(), 1.0 / (10000.0 ** (torch.arange(0, rd, 2).float() / rd)))
+        cos, sin = torch.cat([ang.cos(), ang.cos()], -1), torch.cat([ang.sin(), ang.sin()], -1)
+
+        def rot(t):
+            r, keep = t[..., :rd], t[..., rd:]
+            return torch.cat([r * cos + torch.cat([-r[..., rd // 2:], r[..., :rd // 2]], -1) * sin, keep], -1)
+        o = torch.nn.functional.scaled_dot_product_attention(rot(qq), rot(kk), vv, is_causal=True, enable_gqa=True)
+        want = att.out_proj(o.transpose(1, 2).reshape(2, 40, H * hd))
+    assert torch.allclose(y, want, atol=1e-5, rtol=1e-4), (y - want).abs().max()
