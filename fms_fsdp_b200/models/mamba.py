@@ -219,6 +219,60 @@ def _conv_w(conv: _Conv1dParams):
     return _ConvW.apply(conv.weight)
 
 
+class _WB(nn.Module):
+    """Linear parameter holder with a bias (``dt_proj`` of Mamba1: the bias goes into the scan as ``delta_bias``)."""
+
+    def __init__(self, out_features, in_features, device=None, dtype=None):
+        super().__init__()
+        self.weight = nn.Parameter(torch.empty(out_features, in_features, device=device, dtype=dtype))
+        self.bias = nn.Parameter(torch.empty(out_features, device=device, dtype=dtype))
+
+
+class Mamba1(nn.Module):
+    """Mamba (v1) mixer, ``ssm_cfg = {"layer": "Mamba1"}`` -- mamba_ssm's default layer type: ``in_proj`` -> (x, z);
+    causal depthwise conv + SiLU on x; ``x_proj`` -> (dt, B, C); ``dt_proj``; selective scan with per-channel state
+    ``A = -exp(A_log)`` of width ``d_state``, skip ``D``, gate ``silu(z)``, ``delta = softplus(dt + dt_proj.bias)``; ``out_proj``.
+    Parameter names are mamba_ssm's (and ``transformers.MambaForCausalLM``'s, against which the math is tested)."""
+
+    def __init__(self, d_model, d_state=16, d_conv=4, expand=2, dt_rank="auto", dt_min=0.001, dt_max=0.1, dt_scale=1.0,
+                 dt_init_floor=1e-4, conv_bias=True, layer_idx=None, device=None, dtype=None, **_unused):
+        super().__init__()
+        self.d_model, self.d_state, self.d_conv, self.expand = d_model, d_state, d_conv, expand
+        self.d_inner = expand * d_model
+        self.dt_rank = math.ceil(d_model / 16) if dt_rank == "auto" else int(dt_rank)
+        self.dt_min, self.dt_max, self.dt_scale, self.dt_init_floor = dt_min, dt_max, dt_scale, dt_init_floor
+        self.layer_idx = layer_idx
+        self.in_proj = _W(2 * self.d_inner, d_model, device, dtype)
+        self.conv1d = _Conv1dParams(self.d_inner, d_conv, conv_bias, device, dtype)
+        self.x_proj = _W(self.dt_rank + 2 * d_state, self.d_inner, device, dtype)
+        self.dt_proj = _WB(self.d_inner, self.dt_rank, device, dtype)
+        self.A_log = nn.Parameter(torch.empty(self.d_inner, d_state, device=device, dtype=dtype))
+        self.D = nn.Parameter(torch.empty(self.d_inner, device=device, dtype=dtype))
+        self.out_proj = _W(d_model, self.d_inner, device, dtype)
+
+    def reset_parameters(self):
+        for m in (self.in_proj, self.x_proj, self.out_proj, self.conv1d):
+            m.reset_parameters()
+        with torch.no_grad():
+            std = self.dt_rank ** -0.5 * self.dt_scale
+            nn.init.uniform_(self.dt_proj.weight, -std, std)
+            dt = torch.exp(torch.rand(self.d_inner) * (math.log(self.dt_max) - math.log(self.dt_min))
+                           + math.log(self.dt_min)).clamp(min=self.dt_init_floor)
+            self.dt_proj.bias.copy_(dt + torch.log(-torch.expm1(-dt)))            # inverse softplus
+            self.A_log.copy_(torch.log(torch.arange(1, self.d_state + 1, dtype=torch.float32)).expand(self.d_inner, -1))
+            self.D.fill_(1.0)
+
+    def forward(self, u):
+        B, S, _ = u.shape
+        x, z = self.in_proj(u).view(B * S, -1).chunk(2, dim=-1)
+        x = ops.causal_conv1d(x.contiguous(), _conv_w(self.conv1d), self.conv1d.bias, S, True)
+        dt, Bm, Cm = torch.split(ops.linear(x, self.x_proj.weight), [self.dt_rank, self.d_state, self.d_state], dim=-1)
+        delta = ops.linear(dt.contiguous(), self.dt_proj.weight)
+        y = ops.selective_scan(x, delta, _neg_exp(self.A_log), Bm.contiguous(), Cm.contiguous(), self.D, z.contiguous(),
+                               self.dt_proj.bias, S)
+        return self.out_proj(y.view(B, S, self.d_inner))
+
+
 class MHA(nn.Module):
     """Attention layer of the hybrid: fused in_proj -> partial rotary (half-split) -> causal GQA flash
     attention -> out_proj (mamba_ssm ``MHA`` with ``d_conv=0``, no biases)."""
@@ -314,7 +368,10 @@ class MixerModel(nn.Module):
                             a.get("rotary_emb_dim", 0), layer_idx=i, device=device, dtype=dtype)
             else:
                 s = {k: v for k, v in cfg.ssm_cfg.items() if k != "layer"}
-                mixer = Mamba2(cfg.d_model, layer_idx=i, device=device, dtype=dtype, **s)
+                kind = cfg.ssm_cfg.get("layer", "Mamba1")        # mamba_ssm's default (``create_block``)
+                if kind not in ("Mamba1", "Mamba2"):
+                    raise ValueError(f"Invalid ssm_layer: {kind}, only support Mamba1 and Mamba2")
+                mixer = (Mamba2 if kind == "Mamba2" else Mamba1)(cfg.d_model, layer_idx=i, device=device, dtype=dtype, **s)
             mlp = GatedMLP(cfg.d_model, cfg.d_intermediate, device, dtype) if cfg.d_intermediate > 0 else None
             layers.append(Block(cfg.d_model, mixer, mlp, cfg.norm_epsilon, cfg.residual_in_fp32, device, dtype))
         self.layers = nn.ModuleList(layers)

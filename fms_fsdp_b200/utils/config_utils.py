@@ -82,6 +82,13 @@ _MAMBA_ZOO: Dict[str, Dict[str, Any]] = {
         "rms_norm": True, "residual_in_fp32": True, "fused_add_norm": True,
         "pad_vocab_size_multiple": 16, "tie_embeddings": True,
     },
+    # Mamba (v1) stack: selective-scan mixers, no attention, no MLP (plumbing / CPU tests of the Mamba1 layer type)
+    "mamba1_tiny": {
+        "d_model": 128, "d_intermediate": 0, "n_layer": 3, "vocab_size": 512,
+        "ssm_cfg": {"layer": "Mamba1", "d_state": 16}, "attn_layer_idx": [], "attn_cfg": {},
+        "rms_norm": True, "residual_in_fp32": True, "fused_add_norm": True,
+        "pad_vocab_size_multiple": 16, "tie_embeddings": True,
+    },
     "mamba_tiny": {
         "d_model": 128, "d_intermediate": 256, "n_layer": 4, "vocab_size": 512,
         "ssm_cfg": {"layer": "Mamba2", "headdim": 32, "d_state": 32, "chunk_size": 32},

@@ -27,6 +27,21 @@ def _to_mamba2(model: MambaLMHeadModel):
     return hf
 
 
+def _to_mamba1(model: MambaLMHeadModel):
+    from transformers import MambaConfig as HFMambaConfig
+    from transformers import MambaForCausalLM
+    c = model.config
+    mixer = model.backbone.layers[0].mixer
+    hf = MambaForCausalLM(HFMambaConfig(
+        vocab_size=c.padded_vocab, hidden_size=c.d_model, state_size=mixer.d_state, num_hidden_layers=c.n_layer,
+        expand=mixer.expand, conv_kernel=mixer.d_conv, use_bias=False, use_conv_bias=mixer.conv1d.bias is not None,
+        time_step_rank=mixer.dt_rank, residual_in_fp32=bool(c.residual_in_fp32), layer_norm_epsilon=c.norm_epsilon,
+        hidden_act="silu", tie_word_embeddings=bool(c.tie_embeddings), use_mambapy=False))
+    sd = {("backbone.embeddings.weight" if k == "backbone.embedding.weight" else k): v for k, v in model.state_dict().items()}
+    hf.load_state_dict(sd, strict=not c.tie_embeddings)
+    return hf
+
+
 def _to_bamba(model: MambaLMHeadModel):
     """Mamba2 + attention + gated-MLP hybrid (``mamba_9.8b``) -> ``transformers.BambaForCausalLM``: fused attention ``in_proj``
     is split into q / k / v, ``mlp.fc1`` = (value | gate) halves become ``up_proj`` / ``gate_proj``, the two block norms become
@@ -78,18 +93,19 @@ def _to_bamba(model: MambaLMHeadModel):
 
 
 def to_transformers(model: MambaLMHeadModel):
-    """A ``transformers`` model carrying the weights: ``Mamba2ForCausalLM`` for pure Mamba2 stacks, ``BambaForCausalLM`` for the
-    Mamba2 + attention + MLP hybrid.  Same logits as this repo's model (``tests/test_mamba.py``; for the hybrid with full
+    """A ``transformers`` model carrying the weights: ``MambaForCausalLM`` / ``Mamba2ForCausalLM`` for pure Mamba1 / Mamba2
+    stacks, ``BambaForCausalLM`` for the Mamba2 + attention + MLP hybrid.  Same logits as this repo's model (``tests/test_mamba.py``; for the hybrid with full
     rotary -- transformers 5.5 builds full-width rotary tables for Bamba whatever ``partial_rotary_factor`` says, so a
     partially rotated export only reproduces there what that version computes)."""
     c = model.config
-    if (c.ssm_cfg or {}).get("layer", "Mamba2") != "Mamba2":
-        raise ValueError("--transformers_format needs Mamba2 mixers")
+    kind = (c.ssm_cfg or {}).get("layer", "Mamba1")
     if not c.attn_layer_idx and not c.d_intermediate:
-        return _to_mamba2(model)
+        return _to_mamba2(model) if kind == "Mamba2" else _to_mamba1(model)
+    if kind != "Mamba2":
+        raise ValueError("--transformers_format: hybrids are exported as Bamba, which needs Mamba2 mixers")
     if c.attn_layer_idx and c.d_intermediate:
         return _to_bamba(model)
-    raise ValueError("--transformers_format covers a pure Mamba2 stack (no attention layers, d_intermediate = 0) or the full "
+    raise ValueError("--transformers_format covers a pure Mamba1 / Mamba2 stack (no attention layers, d_intermediate = 0) or the full "
                      "hybrid (attention layers + MLP in every block); other mixes export in the mamba_ssm layout")
 
 

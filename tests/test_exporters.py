@@ -163,7 +163,7 @@ def test_mamba_export_in_transformers_format(monkeypatch):
         b = hf(x).logits
     assert torch.allclose(a, b, atol=1e-5, rtol=1e-4), (a - b).abs().max()
     assert type(ex.to_transformers(_init(MambaLMHeadModel(MambaConfig(**get_model_config("mamba_tiny")))))).__name__ == "BambaForCausalLM"
-    with pytest.raises(ValueError, match="pure Mamba2 stack"):      # attention layers but no MLP: neither layout fits
+    with pytest.raises(ValueError, match="pure Mamba1 / Mamba2 stack"):      # attention layers but no MLP: neither layout fits
         ex.to_transformers(MambaLMHeadModel(MambaConfig(**{**get_model_config("mamba_tiny"), "d_intermediate": 0})))
     # the tied head is stored once; the mamba_ssm-layout export and a trainer resume both restore the alias
     out2 = tempfile.mkdtemp()

@@ -198,3 +198,37 @@ def test_hybrid_matches_transformers_bamba_and_partial_rotary_matches_the_formul
         o = torch.nn.functional.scaled_dot_product_attention(rot(qq), rot(kk), vv, is_causal=True, enable_gqa=True)
         want = att.out_proj(o.transpose(1, 2).reshape(2, 40, H * hd))
     assert torch.allclose(y, want, atol=1e-5, rtol=1e-4), (y - want).abs().max()
+
+
+def test_mamba1_layer_type_matches_transformers_and_trains_through_the_engine():
+    """``ssm_cfg = {"layer": "Mamba1"}`` (mamba_ssm's default layer type): the selective-scan mixer equals
+    ``transformers.MambaForCausalLM`` with the same weights (logits + every gradient), the sharded runtime reproduces plain
+    autograd + AdamW on it, and the exporter writes the ``transformers`` layout."""
+    import fms_to_hf_mamba as ex
+    torch.manual_seed(0)
+    ours = MambaLMHeadModel(MambaConfig(**get_model_config("mamba1_tiny"))); ours.reset_parameters()
+    assert [type(b.mixer).__name__ for b in ours.backbone.layers] == ["Mamba1"] * 3
+    hf = ex.to_transformers(ours)
+    assert type(hf).__name__ == "MambaForCausalLM"
+    x = torch.randint(0, 512, (2, 40))
+    a, b = ours(x).logits, hf(x).logits
+    assert torch.allclose(a, b, atol=1e-5, rtol=1e-4), (a - b).abs().max()
+    w = torch.randn_like(a)
+    (a * w).sum().backward()
+    (b * w).sum().backward()
+    theirs = dict(hf.named_parameters())
+    for n, p in ours.named_parameters():
+        q = theirs["backbone.embeddings.weight" if n == "backbone.embedding.weight" else n]
+        assert (p.grad - q.grad).abs().max() <= 1e-4 * q.grad.abs().max() + 1e-6, n
+    ours.zero_grad()
+
+    ref = copy.deepcopy(ours)
+    eng = ShardedModel(ours, device="cpu"); opt = ShardedAdamW(eng, lr=2e-3)
+    ropt = torch.optim.AdamW(ref.parameters(), lr=2e-3, betas=(0.9, 0.95), weight_decay=0.1)
+    for _ in range(3):
+        l = eng.forward_backward(x, x); gn = eng.clip_grad_norm_(1.0); opt.step()
+        ropt.zero_grad(); rl = ref(x, labels=x); rl.backward()
+        rgn = torch.nn.utils.clip_grad_norm_(ref.parameters(), 1.0); ropt.step()
+        assert l.item() == pytest.approx(rl.item(), rel=1e-5) and gn.item() == pytest.approx(rgn.item(), rel=1e-4)
+    with pytest.raises(ValueError, match="Invalid ssm_layer"):
+        MambaLMHeadModel(MambaConfig(**{**get_model_config("mamba1_tiny"), "ssm_cfg": {"layer": "Mamba3"}}))
