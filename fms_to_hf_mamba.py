@@ -95,8 +95,9 @@ def _to_bamba(model: MambaLMHeadModel):
 def to_transformers(model: MambaLMHeadModel):
     """A ``transformers`` model carrying the weights: ``MambaForCausalLM`` / ``Mamba2ForCausalLM`` for pure Mamba1 / Mamba2
     stacks, ``BambaForCausalLM`` for the Mamba2 + attention + MLP hybrid.  Same logits as this repo's model
-    (``tests/test_mamba.py``; for the hybrid with full rotary -- transformers 5.5 builds full-width rotary tables for Bamba whatever ``partial_rotary_factor`` says, so a
-    partially rotated export only reproduces there what that version computes)."""
+    (``tests/test_mamba.py``).  For the hybrid that holds with full rotary: transformers 5.5 builds full-width rotary tables
+    for Bamba whatever ``partial_rotary_factor`` says, so a partially rotated export reproduces there only what that version
+    computes."""
     c = model.config
     kind = (c.ssm_cfg or {}).get("layer", "Mamba1")
     if not c.attn_layer_idx and not c.d_intermediate:
