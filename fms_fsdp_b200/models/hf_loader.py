@@ -23,7 +23,24 @@ def _halfsplit_to_interleaved(w: torch.Tensor, nheads: int) -> torch.Tensor:
     return w.view(nheads, 2, -1, w.size(1)).transpose(1, 2).reshape(*w.size())
 
 
+def _refuse_unsupported(hf_cfg: dict):
+    """Features this repo's models do not implement must stop the load instead of silently changing the logits."""
+    scaling = hf_cfg.get("rope_scaling") or {}
+    params = hf_cfg.get("rope_parameters") or {}
+    kind = scaling.get("rope_type") or scaling.get("type") or params.get("rope_type") or "default"
+    if kind not in ("default", None):
+        raise NotImplementedError(f"HF checkpoint uses rope scaling {kind!r} (e.g. Llama 3.1 long-context frequencies); only plain "
+                                  "RoPE is implemented, loading it would change the logits")
+    window = hf_cfg.get("sliding_window")
+    if window and window < hf_cfg.get("max_position_embeddings", window):
+        raise NotImplementedError(f"HF checkpoint uses sliding-window attention (window {window}); only full causal attention is "
+                                  "implemented")
+    if hf_cfg.get("attention_bias") or hf_cfg.get("mlp_bias"):
+        raise NotImplementedError("HF checkpoint has attention / MLP biases; the LLaMA blocks here are bias-free")
+
+
 def config_from_hf(hf_cfg: dict) -> LLaMAConfig:
+    _refuse_unsupported(hf_cfg)
     D, F = hf_cfg["hidden_size"], hf_cfg["intermediate_size"]
     rope = hf_cfg.get("rope_theta") or (hf_cfg.get("rope_parameters") or {}).get("rope_theta", 10000.0)
     return LLaMAConfig(
