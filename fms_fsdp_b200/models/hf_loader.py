@@ -28,9 +28,9 @@ def _refuse_unsupported(hf_cfg: dict):
     scaling = hf_cfg.get("rope_scaling") or {}
     params = hf_cfg.get("rope_parameters") or {}
     kind = scaling.get("rope_type") or scaling.get("type") or params.get("rope_type") or "default"
-    if kind not in ("default", None):
-        raise NotImplementedError(f"HF checkpoint uses rope scaling {kind!r} (e.g. Llama 3.1 long-context frequencies); only plain "
-                                  "RoPE is implemented, loading it would change the logits")
+    if kind not in ("default", None, "llama3", "linear"):
+        raise NotImplementedError(f"HF checkpoint uses rope scaling {kind!r}; plain RoPE, 'linear' and 'llama3' (Llama 3.1 / 3.2) "
+                                  "are implemented, loading it would change the logits")
     window = hf_cfg.get("sliding_window")
     if window and window < hf_cfg.get("max_position_embeddings", window):
         raise NotImplementedError(f"HF checkpoint uses sliding-window attention (window {window}); only full causal attention is "
@@ -43,11 +43,15 @@ def config_from_hf(hf_cfg: dict) -> LLaMAConfig:
     _refuse_unsupported(hf_cfg)
     D, F = hf_cfg["hidden_size"], hf_cfg["intermediate_size"]
     rope = hf_cfg.get("rope_theta") or (hf_cfg.get("rope_parameters") or {}).get("rope_theta", 10000.0)
+    scaling = hf_cfg.get("rope_scaling") or hf_cfg.get("rope_parameters") or {}
+    kind = scaling.get("rope_type") or scaling.get("type")
+    rope_scaling = {k: v for k, v in scaling.items() if k != "rope_theta"} if kind in ("llama3", "linear") else None
     return LLaMAConfig(
         src_vocab_size=hf_cfg["vocab_size"], emb_dim=D, norm_eps=hf_cfg.get("rms_norm_eps", 1e-5),
         nheads=hf_cfg["num_attention_heads"], kvheads=hf_cfg.get("num_key_value_heads", 0) or 0,
         nlayers=hf_cfg["num_hidden_layers"], hidden_grow_factor=F / D, multiple_of=1,
-        max_expected_seq_len=hf_cfg.get("max_position_embeddings", 4096), rope_theta=float(rope))
+        max_expected_seq_len=hf_cfg.get("max_position_embeddings", 4096), rope_theta=float(rope),
+        rope_scaling=rope_scaling)
 
 
 def _read_hf_tensors(model_path: str) -> Dict[str, torch.Tensor]:

@@ -44,6 +44,9 @@ class LLaMAConfig:
     rope_theta: float = 10000.0
     linear_config: Optional[dict] = None
     fused_weights: bool = True
+    # extension (not an fms field): HF-style frequency rescaling of long-context checkpoints, e.g. Llama 3.1
+    # {"rope_type": "llama3", "factor": 8.0, "low_freq_factor": 1.0, "high_freq_factor": 4.0, "original_max_position_embeddings": 8192}
+    rope_scaling: Optional[dict] = None
 
     @property
     def hidden_dim(self) -> int:
@@ -94,9 +97,10 @@ class RotaryEmbedding(nn.Module):
     """cos/sin table cache; attrs mirror what the reference exporter reads
     (``dim, ratio, max_seq_len, ntk_scaling, _alpha``: reference ``fms_to_hf_llama.py:43-51``)."""
 
-    def __init__(self, dim: int, ratio: float = 10000.0, max_seq_len: int = 2048, ntk_scaling: bool = False):
+    def __init__(self, dim: int, ratio: float = 10000.0, max_seq_len: int = 2048, ntk_scaling: bool = False, scaling=None):
         super().__init__()
         self.dim, self.ratio, self.max_seq_len, self.ntk_scaling = dim, ratio, max_seq_len, ntk_scaling
+        self.scaling = dict(scaling) if scaling else None
         self._tables = {}
 
     def _alpha(self, seq_len) -> int:
@@ -112,7 +116,7 @@ class RotaryEmbedding(nn.Module):
         tab = self._tables.get(key)
         if tab is None or tab.shape[0] < max_seq_len:
             n = max(max_seq_len, self.max_seq_len * alpha)
-            tab = torch_kernels.rope_table(n, self.dim, self.ratio, float(alpha), device=device)
+            tab = torch_kernels.rope_table(n, self.dim, self.ratio, float(alpha), device=device, scaling=self.scaling)
             self._tables[key] = tab
         return tab
 
@@ -217,7 +221,8 @@ class LLaMA(nn.Module):
         self.pad_id = cfg.pad_id
         self.max_expected_seq_len = cfg.max_expected_seq_len
         self.shared = WordEmbedding(cfg, device, dtype)
-        self.rot_emb = RotaryEmbedding(cfg.head_dim, cfg.rope_theta, cfg.max_expected_seq_len, cfg.ntk_scaling)
+        self.rot_emb = RotaryEmbedding(cfg.head_dim, cfg.rope_theta, cfg.max_expected_seq_len, cfg.ntk_scaling,
+                                       getattr(cfg, "rope_scaling", None))
         self.layers = nn.ModuleList([LLaMABlock(cfg, self.rot_emb, device, dtype) for _ in range(cfg.nlayers)])
         self.dec_norm = RMSNorm(cfg.emb_dim, cfg.norm_eps, device, dtype)
 

@@ -105,9 +105,30 @@ def rmsnorm_gated_bwd(dy, x, z, w, rstd, group_size):
 # RoPE, FMS "interleaved pair" convention: (x[2i], x[2i+1]) rotated by pos * theta^(-2i/rot_dim).
 # Operates IN PLACE on the q and k sections of a fused [M, (H+2*KVH)*hd] projection.
 # ----------------------------------------------------------------------------------------------
-def rope_table(max_seq_len, rot_dim, theta=10000.0, ntk_alpha=1.0, device=None):
+def scaled_inv_freq(inv, scaling):
+    """Frequency rescaling of long-context checkpoints (HF ``rope_scaling``): ``linear`` divides every frequency by ``factor``;
+    ``llama3`` (Llama 3.1 / 3.2) leaves short wavelengths alone, divides wavelengths beyond
+    ``original_max_position_embeddings / low_freq_factor`` by ``factor`` and interpolates in between."""
+    kind = scaling.get("rope_type") or scaling.get("type")
+    factor = float(scaling["factor"])
+    if kind == "linear":
+        return inv / factor
+    if kind != "llama3":
+        raise NotImplementedError(f"rope scaling {kind!r}")
+    lo, hi = float(scaling.get("low_freq_factor", 1.0)), float(scaling.get("high_freq_factor", 4.0))
+    old_len = float(scaling.get("original_max_position_embeddings", 8192))
+    wavelen = 2 * math.pi / inv
+    out = torch.where(wavelen > old_len / lo, inv / factor, inv)
+    smooth = (old_len / wavelen - lo) / (hi - lo)
+    medium = ~(wavelen < old_len / hi) & ~(wavelen > old_len / lo)
+    return torch.where(medium, (1 - smooth) * out / factor + smooth * out, out)
+
+
+def rope_table(max_seq_len, rot_dim, theta=10000.0, ntk_alpha=1.0, device=None, scaling=None):
     ratio = theta * (ntk_alpha ** (rot_dim / (rot_dim - 2))) if ntk_alpha != 1.0 else theta
     inv = 1.0 / (ratio ** (torch.arange(0, rot_dim, 2, device=device, dtype=torch.float32) / rot_dim))
+    if scaling:
+        inv = scaled_inv_freq(inv, scaling)
     ang = torch.outer(torch.arange(max_seq_len, device=device, dtype=torch.float32), inv)
     return torch.stack([ang.cos(), ang.sin()], dim=-1).contiguous()  # [S, rot_dim/2, 2]
 

@@ -42,6 +42,8 @@ def convert_to_hf(model: LLaMA, model_variant: str, is_old_fms: bool = False):
     )
     if "llama3" in model_variant:
         kw.update(bos_token_id=128000, eos_token_id=128001)
+    if getattr(c, "rope_scaling", None):          # long-context frequency rescaling travels with the export
+        kw["rope_scaling"] = dict(c.rope_scaling)
     hf = LlamaForCausalLM(LlamaConfig(**kw))
     sd = model.state_dict()
     hd = c.head_dim

@@ -176,3 +176,34 @@ def test_mamba_export_in_transformers_format(monkeypatch):
     Checkpointer(tempfile.mkdtemp(), 2, "fsdp", 0, 0).load(eng2, None, None, path=os.path.join(ck, "checkpoints", "step_1_ckp"))
     a2, b2 = eng.full_state_dict(), eng2.full_state_dict()
     assert set(a2) == set(b2) and all(torch.equal(a2[k], b2[k]) for k in a2)
+
+
+@pytest.mark.parametrize("scaling", [
+    {"rope_type": "llama3", "factor": 8.0, "low_freq_factor": 1.0, "high_freq_factor": 4.0, "original_max_position_embeddings": 32},
+    {"rope_type": "linear", "factor": 4.0}])
+def test_rope_scaled_hf_checkpoints_load_and_export_with_equal_logits(tmp_path, scaling):
+    """Llama 3.1-style (``llama3``) and ``linear`` rope scaling: an HF checkpoint that uses it loads with the same logits
+    (the scaling only changes the cos / sin table the kernels read), and exporting it again reproduces the HF model."""
+    import fms_to_hf_llama as ex
+    from transformers import LlamaConfig, LlamaForCausalLM
+    from fms_fsdp_b200.models.hf_loader import load_hf_llama
+    torch.manual_seed(6)
+    hf = LlamaForCausalLM(LlamaConfig(vocab_size=96, hidden_size=64, intermediate_size=96, num_hidden_layers=2,
+                                      num_attention_heads=4, num_key_value_heads=2, max_position_embeddings=256,
+                                      rope_theta=10000.0, rope_scaling=dict(scaling), tie_word_embeddings=False)).eval()
+    d = str(tmp_path / "hf")
+    hf.save_pretrained(d)
+    ours = load_hf_llama(d, "cpu", torch.float32).eval()
+    assert ours.config.rope_scaling and (ours.config.rope_scaling.get("rope_type") == scaling["rope_type"])
+    x = torch.randint(0, 96, (2, 200))                      # long enough that the rescaled low frequencies matter
+    with torch.no_grad():
+        want = hf(x).logits
+        got = ours(x)
+        plain = LLaMA(LLaMAConfig(**{**ours.config.__dict__, "rope_scaling": None}))
+        plain.load_state_dict(ours.state_dict())
+        unscaled = plain.eval()(x)
+    assert torch.allclose(got, want, atol=3e-4, rtol=1e-3), (got - want).abs().max()
+    assert (unscaled - want).abs().max() > 10 * (got - want).abs().max()        # the scaling is not a no-op here
+    back = ex.convert_to_hf(ours, "llama3_x").eval()
+    with torch.no_grad():
+        assert torch.allclose(back(x).logits, want, atol=3e-4, rtol=1e-3)

@@ -171,8 +171,9 @@ def test_speculator_entrypoint_resumes_from_its_checkpoint(tmp_path):
 
 
 def test_hf_loader_refuses_what_it_cannot_reproduce():
-    """Rope scaling (Llama 3.1), sliding-window attention and projection biases would load without error and silently change
-    the logits: the loader must stop instead."""
+    """Rope scaling types that are not implemented (yarn, dynamic), sliding-window attention and projection biases would load
+    without error and silently change the logits: the loader must stop instead.  ``llama3`` / ``linear`` scaling is carried
+    into the model config (``tests/test_exporters.py`` checks the logits)."""
     from fms_fsdp_b200.models.hf_loader import config_from_hf
     base = dict(vocab_size=64, hidden_size=32, intermediate_size=64, num_hidden_layers=1, num_attention_heads=2,
                 max_position_embeddings=128, rope_theta=10000.0)
@@ -180,8 +181,9 @@ def test_hf_loader_refuses_what_it_cannot_reproduce():
     assert config_from_hf({**base, "rope_scaling": None, "sliding_window": None}).nlayers == 1
     v5 = {k: v for k, v in base.items() if k != "rope_theta"}       # transformers 5 keeps theta inside rope_parameters
     assert config_from_hf({**v5, "rope_parameters": {"rope_type": "default", "rope_theta": 5e5}}).rope_theta == 5e5
-    for bad, msg in (({"rope_scaling": {"rope_type": "llama3", "factor": 8.0}}, "rope scaling"),
-                     ({"rope_scaling": {"type": "linear", "factor": 2.0}}, "rope scaling"),
+    assert config_from_hf({**base, "rope_scaling": {"rope_type": "llama3", "factor": 8.0}}).rope_scaling["factor"] == 8.0
+    assert config_from_hf({**base, "rope_scaling": {"type": "linear", "factor": 2.0}}).rope_scaling["type"] == "linear"
+    for bad, msg in (({"rope_scaling": {"rope_type": "dynamic", "factor": 2.0}}, "rope scaling"),
                      ({"rope_parameters": {"rope_type": "yarn", "rope_theta": 1e4}}, "rope scaling"),
                      ({"sliding_window": 64}, "sliding-window"), ({"attention_bias": True}, "biases")):
         with pytest.raises(NotImplementedError, match=msg):
