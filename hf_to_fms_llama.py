@@ -20,7 +20,7 @@ from fms_fsdp_b200.models.hf_loader import _read_hf_tensors, config_from_hf, con
 from fms_fsdp_b200.utils.cli import run
 from fms_fsdp_b200.utils.config_utils import get_model_config
 
-_CHECKED = ("src_vocab_size", "emb_dim", "nheads", "kv_heads", "nlayers", "hidden_dim")
+_CHECKED = ("src_vocab_size", "emb_dim", "nheads", "kv_heads", "nlayers", "hidden_dim", "rope_theta", "rope_scaling")
 
 
 def main(hf_path: str, save_path: str, model_variant: str = "", dtype: str = "bf16"):
