@@ -188,3 +188,24 @@ def test_hf_loader_refuses_what_it_cannot_reproduce():
                      ({"sliding_window": 64}, "sliding-window"), ({"attention_bias": True}, "biases")):
         with pytest.raises(NotImplementedError, match=msg):
             config_from_hf({**base, **bad})
+
+
+def test_greedy_generation_equals_transformers_generate(tmp_path):
+    """Prefill + KV-cache decode of the frozen base model against an independent decoder: the same HF Llama weights, greedy
+    decoding, ``transformers.generate`` vs ``generate(..., use_cache=True)`` and ``use_cache=False`` -- identical tokens."""
+    from transformers import LlamaConfig, LlamaForCausalLM
+    from speculator.train_speculator_utils import get_model
+    torch.manual_seed(11)
+    hf = LlamaForCausalLM(LlamaConfig(vocab_size=128, hidden_size=64, intermediate_size=96, num_hidden_layers=2,
+                                      num_attention_heads=4, num_key_value_heads=2, max_position_embeddings=128,
+                                      rope_theta=10000.0, tie_word_embeddings=False)).eval()
+    d = str(tmp_path / "hf")
+    hf.save_pretrained(d)
+    ours = get_model("embedllama", "7b", model_path=d, device_type="cpu", dtype=torch.float32)
+    prompt = torch.randint(0, 128, (3, 9))
+    with torch.no_grad():
+        want = hf.generate(prompt, max_new_tokens=14, do_sample=False, pad_token_id=0)
+        got, embeds = generate(ours, prompt, max_new_tokens=14, do_sample=False, use_cache=True)
+        got2 = generate(ours, prompt, max_new_tokens=14, do_sample=False, use_cache=False, include_embeds=False)
+    assert torch.equal(got, want) and torch.equal(got2, want)
+    assert embeds.shape[0] == 3 and embeds.shape[-1] == 64
