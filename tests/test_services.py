@@ -158,3 +158,25 @@ def test_doctor_reports_the_environment_without_a_gpu():
     if not torch.cuda.is_available():
         assert info["gpus"] == [] and info["problems"] == [] and any("ATen path" in n for n in info["notes"])
         assert doctor.main() == 0
+
+
+def test_scheduler_driven_learning_rate_matches_torch_adamw(tiny_llama):
+    """``LambdaLR`` drives ``ShardedAdamW.param_groups[0]["lr"]`` exactly as it drives ``torch.optim.AdamW``: warm-up + decay
+    over several steps with gradient clipping -- parameters stay equal to the plain-PyTorch run."""
+    import copy
+    from torch.optim.lr_scheduler import LambdaLR
+    ref = copy.deepcopy(tiny_llama)
+    eng = ShardedModel(tiny_llama, device="cpu")
+    sched_fn = lambda s: min(1.0, (s + 1) / 3) * (0.5 ** (s // 4))     # noqa: E731
+    ours, theirs = ShardedAdamW(eng, lr=2e-3), torch.optim.AdamW(ref.parameters(), lr=2e-3, betas=(0.9, 0.95), weight_decay=0.1)
+    so, st = LambdaLR(ours, sched_fn), LambdaLR(theirs, sched_fn)
+    g = torch.Generator().manual_seed(0)
+    for _ in range(6):
+        x = torch.randint(0, 1024, (2, 24), generator=g)
+        eng.forward_backward(x, x); eng.clip_grad_norm_(0.5); ours.step(); so.step()
+        theirs.zero_grad(); ref(x, labels=x).backward()
+        torch.nn.utils.clip_grad_norm_(ref.parameters(), 0.5); theirs.step(); st.step()
+        assert so.get_last_lr() == st.get_last_lr()
+    mine = eng.full_state_dict()
+    for k, v in ref.state_dict().items():
+        assert torch.allclose(mine[k], v, atol=3e-6, rtol=1e-5), (k, (mine[k] - v).abs().max())
