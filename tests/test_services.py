@@ -180,3 +180,33 @@ def test_scheduler_driven_learning_rate_matches_torch_adamw(tiny_llama):
     mine = eng.full_state_dict()
     for k, v in ref.state_dict().items():
         assert torch.allclose(mine[k], v, atol=3e-6, rtol=1e-5), (k, (mine[k] - v).abs().max())
+
+
+def test_train_loop_reports_to_the_tracker_with_the_reference_keys(tiny_llama, monkeypatch, tmp_path, capsys):
+    """``train()`` in-process on CPU with a stand-in ``wandb``: one tracker call per report step carrying exactly the keys the
+    reference logs (``train_utils.py:151-165``), the reference's stdout lines, and a final checkpoint."""
+    from torch.optim.lr_scheduler import LambdaLR
+    from fms_fsdp_b200.utils.checkpointing_utils import Checkpointer
+    from fms_fsdp_b200.utils.dataloader_utils import get_dummy_loader
+    logged = []
+    fake = types.SimpleNamespace(init=lambda **kw: None, log=lambda vals, step=None: logged.append((step, dict(vals))),
+                                 errors=types.SimpleNamespace(UsageError=RuntimeError))
+    monkeypatch.setitem(sys.modules, "wandb", fake)
+    for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK"):
+        monkeypatch.delenv(k, raising=False)
+    cfg = train_config()
+    cfg.model_variant, cfg.tracker, cfg.use_dummy_dataset = "llama2_tiny", "wandb", True
+    cfg.seq_length, cfg.batch_size, cfg.vocab_size, cfg.num_steps = 32, 2, 1024, 3
+    cfg.report_interval, cfg.checkpoint_interval, cfg.ckpt_save_path = 1, 100, str(tmp_path)
+    eng = ShardedModel(tiny_llama, device="cpu")
+    opt = ShardedAdamW(eng, lr=1e-3)
+    TU.train(cfg, eng, 0, 0, get_dummy_loader(cfg, 0, 1), opt, LambdaLR(opt, lambda s: 1.0), None,
+             Checkpointer(str(tmp_path), 2, "fsdp", 0, 0), 0, 0)
+    assert [s for s, _ in logged] == [1, 2, 3]
+    assert set(logged[0][1]) == {"learning rate", "loss", "gradient norm", "token seen",
+                                 "current throughput (token per gpu per sec)", "overall throughput (token per gpu per sec)",
+                                 "gpu reserved memory", "gpu allocated memory"}
+    assert logged[2][1]["token seen"] == 3 * 2 * 32 and all(math.isfinite(v["loss"]) for _, v in logged)
+    out = capsys.readouterr().out
+    for line in ("step: 3", "loss:", "LR:", "tokens seen: 192", "gradient norm:", "overall token per day:", "Checkpoint saved"):
+        assert line in out, line
