@@ -112,10 +112,10 @@ def test_tp2_gpt_bigcode_and_mixtral_bases_match_unsharded():
         assert r["shrink"] < 0.75, (name, r)   # the bulk of the weights really is split
 
 
-@pytest.mark.parametrize("arch", ["embedllama", "embedgpt_bigcode", "embedmixtral"])
+@pytest.mark.parametrize("arch", ["embedllama", "embedgpt_bigcode"])   # Mixtral: TP math + init are covered in-process
 def test_speculator_entrypoint_tp2_two_stages(tmp_path, arch):
-    """`speculator/train_speculator.py` end to end on 2 gloo ranks: (dp, tp) = (1, 2) mesh, TP-sharded frozen base model (each
-    of the three families), DDP speculator on the engine, stage 1 -> stage 2 (generated continuations), final checkpoint."""
+    """`speculator/train_speculator.py` end to end on 2 gloo ranks: (dp, tp) = (1, 2) mesh, TP-sharded frozen base model (Llama and
+    GPT-BigCode; all three families are compared with their unsharded selves above), DDP speculator on the engine, stage 1 -> stage 2 (generated continuations), final checkpoint."""
     import subprocess
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
