@@ -104,6 +104,11 @@ def load_hf_gpt_bigcode(model_path: str, model_cls, device="cpu", dtype=torch.bf
         c = json.load(f)
     if not c.get("multi_query", True):
         raise ValueError("only multi-query GPT-BigCode checkpoints are supported")
+    act = c.get("activation_function", "gelu_pytorch_tanh")
+    if act not in ("gelu_pytorch_tanh", "gelu_new", "gelu_fast"):     # all three are the tanh approximation the block computes
+        raise NotImplementedError(f"GPT-BigCode activation {act!r}: the block implements tanh-approximated GELU only")
+    if not c.get("scale_attn_weights", True):
+        raise NotImplementedError("GPT-BigCode checkpoints with scale_attn_weights=False are not supported")
     D = c["n_embd"]
     hidden = c.get("n_inner") or 4 * D
     if hidden % D:
