@@ -209,3 +209,27 @@ def test_greedy_generation_equals_transformers_generate(tmp_path):
         got2 = generate(ours, prompt, max_new_tokens=14, do_sample=False, use_cache=False, include_embeds=False)
     assert torch.equal(got, want) and torch.equal(got2, want)
     assert embeds.shape[0] == 3 and embeds.shape[-1] == 64
+
+
+def test_mixtral_loader_reads_the_fused_in_memory_expert_layout(tmp_path):
+    """Besides the hub layout (``block_sparse_moe.experts.N.w1/w2/w3``, what ``save_pretrained`` writes) the loader accepts the
+    fused tensors of recent ``transformers`` state dicts (``mlp.experts.gate_up_proj`` / ``down_proj``) -- same logits."""
+    import json
+    from safetensors.torch import save_file
+    from transformers import MixtralConfig, MixtralForCausalLM
+    from speculator.train_speculator_utils import get_model
+    torch.manual_seed(8)
+    cfg = MixtralConfig(vocab_size=50, hidden_size=32, intermediate_size=48, num_hidden_layers=2, num_attention_heads=4,
+                        num_key_value_heads=2, num_local_experts=4, num_experts_per_tok=2, max_position_embeddings=64)
+    hf = MixtralForCausalLM(cfg).eval()
+    sd = {k: v.detach().clone().contiguous() for k, v in hf.state_dict().items()}
+    if not any(k.endswith("mlp.experts.gate_up_proj") for k in sd):
+        pytest.skip("this transformers version keeps per-expert tensors in memory")
+    os.makedirs(tmp_path / "m")
+    save_file(sd, str(tmp_path / "m" / "model.safetensors"))
+    with open(tmp_path / "m" / "config.json", "w") as f:
+        json.dump(cfg.to_dict(), f)
+    ours = get_model("embedmixtral", "8x7b", model_path=str(tmp_path / "m"), device_type="cpu", dtype=torch.float32)
+    x = torch.randint(0, 50, (2, 13))
+    with torch.no_grad():
+        assert torch.allclose(ours(x), hf(x).logits, atol=2e-4)
