@@ -233,3 +233,26 @@ def test_mixtral_loader_reads_the_fused_in_memory_expert_layout(tmp_path):
     x = torch.randint(0, 50, (2, 13))
     with torch.no_grad():
         assert torch.allclose(ours(x), hf(x).logits, atol=2e-4)
+
+
+def test_hf_loader_reads_pytorch_bin_checkpoints(tmp_path):
+    """Older HF checkpoints ship ``pytorch_model.bin`` instead of safetensors: same loader, same logits."""
+    from transformers import LlamaConfig, LlamaForCausalLM
+    from fms_fsdp_b200.models.hf_loader import load_hf_llama
+    torch.manual_seed(9)
+    hf = LlamaForCausalLM(LlamaConfig(vocab_size=60, hidden_size=32, intermediate_size=48, num_hidden_layers=1,
+                                      num_attention_heads=4, num_key_value_heads=4, max_position_embeddings=64,
+                                      tie_word_embeddings=True)).eval()          # tied head: no lm_head tensor on disk
+    d = str(tmp_path / "m")
+    os.makedirs(d)
+    torch.save({k: v for k, v in hf.state_dict().items() if k != "lm_head.weight"}, os.path.join(d, "pytorch_model.bin"))
+    hf.config.save_pretrained(d)
+    ours = load_hf_llama(d, "cpu", torch.float32).eval()
+    x = torch.randint(0, 60, (2, 12))
+    with torch.no_grad():
+        assert torch.allclose(ours(x), hf(x).logits, atol=2e-4)
+    empty = str(tmp_path / "empty")
+    os.makedirs(empty)
+    hf.config.save_pretrained(empty)
+    with pytest.raises(FileNotFoundError, match="no safetensors"):
+        load_hf_llama(empty, "cpu", torch.float32)
